@@ -1,0 +1,220 @@
+"""TEST INFRASTRUCTURE ONLY: ctypes view of oracle/_ref/liboracle.so (the plain-C
+restatement in oracle/qpde_oracle.c) plus a runner for oracle/_ref/qpde_ref (the
+unmodified reference headers compiled against oracle/shim).
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl
+reference legs may import this module.  The product package never does.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "_ref", "liboracle.so")
+REF_PATH = os.path.join(HERE, "_ref", "qpde_ref")
+
+SCHEMES = {"rannacher": 0, "cn": 1, "bdf1": 2, "bdf2": 3}
+
+
+class Step(C.Structure):
+    _fields_ = [("t", C.c_double), ("dt", C.c_double), ("same_dt", C.c_int),
+                ("event_after", C.c_int), ("user_events", C.c_int)]
+
+
+class Problem(C.Structure):
+    _fields_ = [("n", C.c_int), ("T", C.c_double),
+                ("S", C.POINTER(C.c_double)),
+                ("lo", C.POINTER(C.c_double)), ("di", C.POINTER(C.c_double)),
+                ("up", C.POINTER(C.c_double)),
+                ("v0", C.POINTER(C.c_double)),
+                ("scheme", C.c_int), ("n_steps", C.c_int),
+                ("steps", C.POINTER(Step)),
+                ("american", C.c_int),
+                ("obstacle", C.POINTER(C.c_double)),
+                ("tolerance", C.c_double), ("scale", C.c_double),
+                ("penalty_tol", C.c_double), ("max_inner", C.c_int),
+                ("event_obstacle", C.POINTER(C.c_double))]
+
+
+_lib = None
+
+
+def build():
+    subprocess.check_call(["make", "-s", "-C", HERE])
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            build()
+        _lib = C.CDLL(LIB_PATH)
+        _lib.qpo_interp.restype = C.c_double
+        _lib.qpo_interp.argtypes = [C.c_int, C.POINTER(C.c_double),
+                                    C.POINTER(C.c_double), C.c_double]
+    return _lib
+
+
+def _dp(a):
+    return a.ctypes.data_as(C.POINTER(C.c_double))
+
+
+def special_axis():
+    out = np.zeros(33)
+    lib().qpo_axis_special(_dp(out))
+    return out
+
+
+def axis_union(a, b):
+    a = np.ascontiguousarray(a, dtype=np.float64)
+    b = np.ascontiguousarray(b, dtype=np.float64)
+    out = np.zeros(len(a) + len(b))
+    n = lib().qpo_axis_union(_dp(a), len(a), _dp(b), len(b), _dp(out))
+    return out[:n].copy()
+
+
+def refine(axis, times):
+    axis = np.ascontiguousarray(axis, dtype=np.float64)
+    n = lib().qpo_axis_refine(_dp(axis), len(axis), int(times), None)
+    out = np.zeros(n)
+    lib().qpo_axis_refine(_dp(axis), len(axis), int(times), _dp(out))
+    return out
+
+
+TUTORIAL_AXIS = np.array([
+    0., 10., 20., 30., 40., 50., 60., 70., 75., 80., 84., 88., 92., 94., 96.,
+    98., 100., 102., 104., 106., 108., 110., 114., 118., 123., 130., 140.,
+    150., 175., 225., 300., 750., 2000., 10000.])
+
+
+def vanilla_grid(K, S0=None, refine_times=0):
+    """(S_0 * Axis::special) + (K * Axis::special), refined
+    (examples/vanilla_options.cpp:156, :48)."""
+    S0 = K if S0 is None else S0
+    sp = special_axis()
+    return refine(axis_union(sp * S0, sp * K), refine_times)
+
+
+def schedule(T, dt, event_times=()):
+    ev = np.ascontiguousarray(event_times, dtype=np.float64)
+    cap = int(T / dt) + 8 + 2 * len(ev)
+    buf = (Step * cap)()
+    n = lib().qpo_schedule(C.c_double(T), C.c_double(dt), _dp(ev) if len(ev) else None,
+                           len(ev), buf, cap)
+    assert n <= cap
+    return buf, n
+
+
+def bs_coeffs(S, r, v, q, lam=None, kappa=0.0):
+    S = np.ascontiguousarray(S, dtype=np.float64)
+    n = len(S)
+    bc = lambda x: np.ascontiguousarray(np.broadcast_to(np.asarray(x, dtype=np.float64), (n,)))
+    r, v, q = bc(r), bc(v), bc(q)
+    lamp = _dp(bc(lam)) if lam is not None else None
+    lo, di, up = np.zeros(n), np.zeros(n), np.zeros(n)
+    lib().qpo_bs_coeffs(n, _dp(S), _dp(r), _dp(v), _dp(q), lamp,
+                        C.c_double(kappa), _dp(lo), _dp(di), _dp(up))
+    return lo, di, up
+
+
+def interp(x, v, c):
+    x = np.ascontiguousarray(x, dtype=np.float64)
+    v = np.ascontiguousarray(v, dtype=np.float64)
+    return lib().qpo_interp(len(x), _dp(x), _dp(v), C.c_double(c))
+
+
+def sweep(S, lo, di, up, v0, T, steps, n_steps, scheme="rannacher",
+          american=False, obstacle=None, event_obstacle=None,
+          tolerance=1e-6, scale=1.0, penalty_tol=1e-6, max_inner=1000):
+    """Returns dict(V, inner, mask, status)."""
+    n = len(S)
+    arrs = [np.ascontiguousarray(a, dtype=np.float64) for a in (S, lo, di, up, v0)]
+    p = Problem()
+    p.n = n
+    p.T = T
+    p.S, p.lo, p.di, p.up, p.v0 = [_dp(a) for a in arrs]
+    p.scheme = SCHEMES[scheme]
+    p.n_steps = n_steps
+    p.steps = C.cast(steps, C.POINTER(Step))
+    p.american = int(american)
+    if obstacle is not None:
+        obstacle = np.ascontiguousarray(obstacle, dtype=np.float64)
+        p.obstacle = _dp(obstacle)
+    if event_obstacle is not None:
+        event_obstacle = np.ascontiguousarray(event_obstacle, dtype=np.float64)
+        p.event_obstacle = _dp(event_obstacle)
+    p.tolerance, p.scale, p.penalty_tol, p.max_inner = tolerance, scale, penalty_tol, max_inner
+    V = np.zeros(n)
+    inner = np.zeros(n_steps, dtype=np.int32)
+    mask = np.zeros(n, dtype=np.uint8)
+    status = lib().qpo_sweep_1d(C.byref(p), _dp(V),
+                                inner.ctypes.data_as(C.POINTER(C.c_int)),
+                                mask.ctypes.data_as(C.POINTER(C.c_ubyte)))
+    return dict(V=V, inner=inner, mask=mask, status=status)
+
+
+def american_put(K, r, vol, T, n_steps, refine_times, q=0.0, S0=None, call=False,
+                 american=True, scheme="rannacher"):
+    """The vanilla_options.cpp wiring on the oracle."""
+    S = vanilla_grid(K, S0, refine_times)
+    lo, di, up = bs_coeffs(S, r, vol, q)
+    payoff = np.where(S < K, 0.0, S - K) if call else np.where(S < K, K - S, 0.0)
+    steps, n = schedule(T, T / n_steps)
+    out = sweep(S, lo, di, up, payoff, T, steps, n, scheme=scheme,
+                american=american, obstacle=payoff)
+    out["S"] = S
+    out["n_steps"] = n
+    return out
+
+
+def bermudan_put(K, r, alpha, T, n_steps, E, refine_times, q=0.0, scheme="bdf2"):
+    """The tutorial.cpp wiring on the oracle (local volatility alpha / S)."""
+    S = refine(TUTORIAL_AXIS * (K / 100.0), refine_times)
+    with np.errstate(divide="ignore"):
+        vol = alpha / S
+    lo, di, up = bs_coeffs(S, r, vol, q)
+    payoff = np.maximum(K - S, 0.0)
+    ev = [T / E * e for e in range(E)]
+    steps, n = schedule(T, T / n_steps, ev)
+    out = sweep(S, lo, di, up, payoff, T, steps, n, scheme=scheme,
+                american=False, obstacle=payoff, event_obstacle=K - S)
+    out["S"] = S
+    out["n_steps"] = n
+    return out
+
+
+# --------------------------------------------------------------------------
+# Runner for the compiled reference (oracle/_ref/qpde_ref)
+# --------------------------------------------------------------------------
+
+def have_ref():
+    return os.path.exists(REF_PATH)
+
+
+def run_ref(mode, **kw):
+    """Runs oracle/_ref/qpde_ref and parses its dump into numpy arrays."""
+    args = [REF_PATH, mode] + ["%s=%s" % (k, repr(v) if isinstance(v, float) else v)
+                               for k, v in kw.items()]
+    txt = subprocess.check_output(args).decode()
+    toks = txt.split()
+    out = {}
+    i = 0
+    while i < len(toks):
+        key = toks[i]
+        if key in ("value",):
+            out[key] = float.fromhex(toks[i + 1]); i += 2
+        elif key in ("seconds",):
+            out[key] = float(toks[i + 1]); i += 2
+        elif key in ("steps",):
+            out[key] = int(toks[i + 1]); i += 2
+        else:
+            n = int(toks[i + 1])
+            vals = toks[i + 2:i + 2 + n]
+            if key in ("inner", "mask"):
+                out[key] = np.array([int(x) for x in vals], dtype=np.int64)
+            else:
+                out[key] = np.array([float.fromhex(x) for x in vals])
+            i += 2 + n
+    return out

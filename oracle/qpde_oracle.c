@@ -1,0 +1,503 @@
+/* TEST INFRASTRUCTURE ONLY — see qpde_oracle.h.  Plain-C restatement of the
+ * reference's 1-D sweep.  Compile WITHOUT -ffast-math / -march=native and with
+ * -ffp-contract=off: the reference's Release build is plain -O3 x86-64
+ * (CMakeLists.txt:9,29), i.e. no fused multiply-add.
+ *
+ * Citations are file:line under /root/reference/QuantPDE/src.
+ */
+#include "qpde_oracle.h"
+
+#include <float.h>
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+
+/* ------------------------------------------------------------------------ */
+/* Grid generation                                                           */
+/* ------------------------------------------------------------------------ */
+
+/* Core/Axis.hpp:445-459 */
+int qpo_axis_special(double *out) {
+	static const double ticks[33] = {
+		0., .1, .2, .3, .4, .5, .6, .7, .80, .84, .88, .92, .94, .96, .98,
+		1., 1.02, 1.04, 1.06, 1.08, 1.10, 1.14, 1.18, 1.23, 1.30, 1.40,
+		1.50, 1.75, 2.25, 3.00, 7.50, 20., 100.
+	};
+	memcpy(out, ticks, sizeof(ticks));
+	return 33;
+}
+
+/* Core/Axis.hpp:270-313: merge of two strictly increasing tick arrays,
+ * exact-equality duplicates dropped. */
+int qpo_axis_union(const double *a, int na, const double *b, int nb,
+		double *out) {
+	int i = 0, j = 0, k = 0;
+	while(i < na && j < nb) {
+		if(a[i] == b[j])      { out[k++] = a[i++]; ++j; }
+		else if(a[i] < b[j])  { out[k++] = a[i++]; }
+		else                  { out[k++] = b[j++]; }
+	}
+	while(i < na) out[k++] = a[i++];
+	while(j < nb) out[k++] = b[j++];
+	return k;
+}
+
+/* Core/Domain.hpp:1092-1151: tmp = 2^times sub-intervals per interval,
+ * new ticks k * dx + left with dx = (right - left) / tmp. */
+int qpo_axis_refine(const double *in, int n, int times, double *out) {
+	int tmp = 1, i, j, k;
+	if(times <= 0 || n < 2) {
+		if(out) memcpy(out, in, sizeof(double) * (size_t)n);
+		return n;
+	}
+	for(i = 0; i < times; ++i) tmp *= 2;
+	if(!out) return tmp * (n - 1) + 1;
+	out[0] = in[0];
+	j = 1;
+	for(i = 1; i < n; ++i) {
+		const double dx = (in[i] - in[i - 1]) / tmp;
+		for(k = 1; k < tmp; ++k) out[j++] = k * dx + in[i - 1];
+		out[j++] = in[i];
+	}
+	return j;
+}
+
+/* ------------------------------------------------------------------------ */
+/* Time loop replay: Core/IterativeMethod.hpp:1259-1317, Core/Stepper.hpp:16 */
+/* ------------------------------------------------------------------------ */
+
+static int cmp_desc(const void *a, const void *b) {
+	const double x = *(const double *)a, y = *(const double *)b;
+	return x < y ? 1 : (x > y ? -1 : 0);
+}
+
+int qpo_schedule(double T, double dt_const, const double *event_times,
+		int n_events, qpo_step *out, int max_steps) {
+	/* Reverse time: the priority queue pops the largest time first
+	 * (IterativeMethod.hpp:1340-1358); a NullEvent sits at t = 0 (:1268-1276). */
+	double *ev = (double *)malloc(sizeof(double) * (size_t)(n_events + 1));
+	int n = 0, e = 0, i;
+	double t = T, dt = -1., dtPrevious;
+	for(i = 0; i < n_events; ++i) ev[i] = event_times[i];
+	qsort(ev, (size_t)n_events, sizeof(double), cmp_desc);
+
+	do {
+		/* top of the queue: the largest remaining user event time, or the
+		 * NullEvent at 0 */
+		const double nextEventTime = e < n_events ? ev[e] : 0.;
+		int users = 0;
+		do {
+			double tmp;
+			dtPrevious = dt;
+			dt = dt_const;
+			tmp = t + -1. * dt;
+			if(fabs(tmp - nextEventTime) < DBL_EPSILON) {
+				tmp = nextEventTime;
+			} else if(tmp < nextEventTime) {
+				tmp = nextEventTime;
+				dt = -1. * (nextEventTime - t);
+			}
+			t = tmp;
+			if(n < max_steps) {
+				out[n].t = t;
+				out[n].dt = dt;
+				out[n].same_dt = (dt == dtPrevious);
+				out[n].event_after = 0;
+				out[n].user_events = 0;
+			}
+			++n;
+		} while(nextEventTime < t + -1. * DBL_EPSILON);
+		t = nextEventTime;
+		/* pop every event at exactly this time (:1283-1288) */
+		while(e < n_events && ev[e] == t) { ++e; ++users; }
+		if(n - 1 < max_steps) {
+			out[n - 1].event_after = 1;
+			out[n - 1].user_events = users;
+		}
+	} while(0. < t);
+
+	free(ev);
+	return n;
+}
+
+/* ------------------------------------------------------------------------ */
+/* Operator rows: Modules/Operators/BlackScholes.hpp:136-226                 */
+/* ------------------------------------------------------------------------ */
+
+void qpo_bs_coeffs(int n, const double *S, const double *r, const double *v,
+		const double *q, const double *lambda, double kappa,
+		double *lo, double *di, double *up) {
+	int i;
+	lo[0] = 0.; di[0] = r[0]; up[0] = 0.;                 /* :173-176 */
+	lo[n - 1] = 0.; di[n - 1] = q[n - 1]; up[n - 1] = 0.; /* :177-180 */
+	for(i = 1; i < n - 1; ++i) {
+		const double r_i = r[i], v_i = v[i], q_i = q[i];
+		const double l_i = lambda ? lambda[i] : 0.;
+		const double dSb = S[i] - S[i - 1];
+		const double dSc = S[i + 1] - S[i - 1];
+		const double dSf = S[i + 1] - S[i];
+		const double tmp1 = v_i * v_i * S[i] * S[i];
+		const double tmp2 = (r_i - q_i - l_i * kappa) * S[i];
+		const double alpha_common = tmp1 / dSb / dSc;
+		const double beta_common = tmp1 / dSf / dSc;
+		double alpha_i = alpha_common - tmp2 / dSc;
+		double beta_i = beta_common + tmp2 / dSc;
+		if(alpha_i < 0.) {
+			alpha_i = alpha_common;
+			beta_i = beta_common + tmp2 / dSf;
+		} else if(beta_i < 0.) {
+			alpha_i = alpha_common - tmp2 / dSb;
+			beta_i = beta_common;
+		}
+		lo[i] = -alpha_i;
+		di[i] = alpha_i + beta_i + r_i + l_i;
+		up[i] = -beta_i;
+	}
+}
+
+/* ------------------------------------------------------------------------ */
+/* Interpolation: Core/Interpolant.hpp:153-181 and :331-374                  */
+/* ------------------------------------------------------------------------ */
+
+double qpo_interp(int n, const double *x, const double *v, double c) {
+	int idx = 0;
+	double w = 0., sum = 0.;
+	if(c <= x[0]) { idx = 0; w = 1.; }
+	else if(c >= x[n - 1]) { idx = n - 2; w = 0.; }
+	else {
+		int lo = 0, hi = n - 2, mid = 0;
+		while(lo <= hi) {
+			mid = (lo + hi) / 2;
+			if(c < x[mid]) hi = mid - 1;
+			else if(c >= x[mid + 1]) lo = mid + 1;
+			else { w = (x[mid + 1] - c) / (x[mid + 1] - x[mid]); break; }
+		}
+		idx = mid;
+	}
+	/* corners with factor <= epsilon are skipped (:369-371) */
+	if(w > DBL_EPSILON) sum += w * v[idx];
+	if(1. - w > DBL_EPSILON) sum += (1. - w) * v[idx + 1];
+	return sum;
+}
+
+/* ------------------------------------------------------------------------ */
+/* Tridiagonal LU with row partial pivoting, natural order.  Same operation  */
+/* order as oracle/shim's banded SparseLU stand-in with kl = ku = 1 (the     */
+/* pivot policy Eigen::SparseLU defaults to: keep the diagonal unless a      */
+/* strictly larger entry lies below it).                                     */
+/* ------------------------------------------------------------------------ */
+
+typedef struct {
+	int n;
+	double *dl;  /* multipliers                */
+	double *d;   /* U diagonal                 */
+	double *du;  /* U first superdiagonal      */
+	double *du2; /* U second superdiagonal     */
+	int *swap;   /* 1 if rows j, j+1 swapped   */
+} tri_lu;
+
+static void tri_alloc(tri_lu *f, int n) {
+	f->n = n;
+	f->dl = (double *)malloc(sizeof(double) * (size_t)n);
+	f->d = (double *)malloc(sizeof(double) * (size_t)n);
+	f->du = (double *)malloc(sizeof(double) * (size_t)n);
+	f->du2 = (double *)malloc(sizeof(double) * (size_t)n);
+	f->swap = (int *)malloc(sizeof(int) * (size_t)n);
+}
+
+static void tri_free(tri_lu *f) {
+	free(f->dl); free(f->d); free(f->du); free(f->du2); free(f->swap);
+}
+
+/* a: sub (a[0] unused), b: diag, c: super (c[n-1] unused) */
+static void tri_factor(tri_lu *f, const double *a, const double *b,
+		const double *c) {
+	const int n = f->n;
+	int j;
+	/* working copy of rows j, j+1 */
+	for(j = 0; j < n; ++j) {
+		f->d[j] = b[j];
+		f->du[j] = j < n - 1 ? c[j] : 0.;
+		f->du2[j] = 0.;
+		f->dl[j] = j < n - 1 ? a[j + 1] : 0.;
+	}
+	for(j = 0; j < n - 1; ++j) {
+		/* pivot search among rows j, j+1 of column j */
+		if(fabs(f->dl[j]) > fabs(f->d[j])) {
+			/* swap rows j and j+1 (columns j .. j+2) */
+			double t;
+			t = f->d[j];  f->d[j] = f->dl[j];      f->dl[j] = t;
+			t = f->du[j]; f->du[j] = f->d[j + 1];  f->d[j + 1] = t;
+			t = f->du2[j]; f->du2[j] = f->du[j + 1]; f->du[j + 1] = t;
+			f->swap[j] = 1;
+		} else {
+			f->swap[j] = 0;
+		}
+		f->dl[j] /= f->d[j];
+		if(f->du[j] != 0.)  f->d[j + 1]  -= f->dl[j] * f->du[j];
+		if(f->du2[j] != 0.) f->du[j + 1] -= f->dl[j] * f->du2[j];
+	}
+	f->swap[n - 1] = 0;
+}
+
+static void tri_solve(const tri_lu *f, double *x) {
+	const int n = f->n;
+	int j;
+	for(j = 0; j < n - 1; ++j) {
+		if(f->swap[j]) { const double t = x[j]; x[j] = x[j + 1]; x[j + 1] = t; }
+		x[j + 1] -= f->dl[j] * x[j];
+	}
+	/* column-oriented back substitution, same update order as the banded
+	 * stand-in: x[j] /= U_jj, then x[i] -= U_ij x[j] for i = j-2, j-1 */
+	for(j = n - 1; j >= 0; --j) {
+		x[j] /= f->d[j];
+		if(j >= 2) x[j - 2] -= f->du2[j - 2] * x[j];
+		if(j >= 1) x[j - 1] -= f->du[j - 1] * x[j];
+	}
+}
+
+/* ------------------------------------------------------------------------ */
+/* relativeError: Core/IterativeMethod.hpp:1125-1137                         */
+/* ------------------------------------------------------------------------ */
+
+static double relative_error(int n, const double *a, const double *b,
+		double scale) {
+	double m = 0.;
+	int i;
+	for(i = 0; i < n; ++i) {
+		const double fa = fabs(a[i]), fb = fabs(b[i]);
+		double den = fa < fb ? fb : fa;      /* a.cwiseAbs().cwiseMax(b.cwiseAbs()) */
+		double quo;
+		den = (scale * 1.) < den ? den : (scale * 1.); /* (scale*Ones).cwiseMax(..) */
+		quo = fabs(a[i] - b[i]) / den;
+		if(i == 0 || quo > m) m = quo;
+	}
+	return m;
+}
+
+/* ------------------------------------------------------------------------ */
+/* The sweep                                                                 */
+/* ------------------------------------------------------------------------ */
+
+/* row-major SpMV of the tridiagonal (lo, di, up): accumulate from zero in
+ * column order (the binding's operator*, standing in for Eigen's). */
+static void tri_spmv(int n, const double *lo, const double *di,
+		const double *up, const double *x, double *y) {
+	int i;
+	for(i = 0; i < n; ++i) {
+		double acc = 0.;
+		if(i > 0) acc += lo[i] * x[i - 1];
+		acc += di[i] * x[i];
+		if(i < n - 1) acc += up[i] * x[i + 1];
+		y[i] = acc;
+	}
+}
+
+int qpo_sweep_1d(const qpo_problem *p, double *V, int *inner,
+		unsigned char *mask) {
+	const int n = p->n;
+	const double pen = 1. / p->penalty_tol;   /* PenaltyMethod.hpp:85 */
+	double *A_lo = (double *)malloc(sizeof(double) * (size_t)n);
+	double *A_di = (double *)malloc(sizeof(double) * (size_t)n);
+	double *A_up = (double *)malloc(sizeof(double) * (size_t)n);
+	double *M_lo = (double *)malloc(sizeof(double) * (size_t)n);
+	double *M_di = (double *)malloc(sizeof(double) * (size_t)n);
+	double *M_up = (double *)malloc(sizeof(double) * (size_t)n);
+	double *P_di = (double *)malloc(sizeof(double) * (size_t)n);
+	double *lb = (double *)malloc(sizeof(double) * (size_t)n);
+	double *rhs = (double *)malloc(sizeof(double) * (size_t)n);
+	double *x = (double *)malloc(sizeof(double) * (size_t)n);
+	double *xprev = (double *)malloc(sizeof(double) * (size_t)n);
+	double *v1 = (double *)malloc(sizeof(double) * (size_t)n); /* iterand(0) */
+	double *v0 = (double *)malloc(sizeof(double) * (size_t)n); /* iterand(1) */
+	tri_lu lu;
+	int s, i, status = 0;
+	/* stepper history: times of iterand(0), iterand(1) */
+	double time1 = 0., time0 = 0.;
+	int hist = 0;          /* number of iterands in the stepper's ring */
+	int initialized = 0;   /* IterativeMethod.hpp:1150-1157 */
+	/* node state machines */
+	int ran_phase = 1;     /* Rannacher: 1,2 = implicit steps, 3 = first CN, 4 = CN */
+	int bdf_phase = 1;     /* BDFTwo: 1 = BDF1 step, 2 = first BDF2, 3 = BDF2 */
+
+	tri_alloc(&lu, n);
+	memcpy(v1, p->v0, sizeof(double) * (size_t)n);
+	/* the stepper pushes (T, V^0) (:1171-1174) */
+	time1 = p->T;
+	hist = 1;
+
+	for(s = 0; s < p->n_steps; ++s) {
+		const qpo_step *st = &p->steps[s];
+		const double t = st->t;
+		int a_same, its = 0;
+		int use_cn = 0, use_bdf2 = 0;
+		double hA = 0.;
+
+		/* --- which A / b formulas apply at this step ------------------- */
+		switch(p->scheme) {
+		case QPO_SCHEME_RANNACHER:
+			/* Rannacher.hpp:23-30, 75-92 */
+			use_cn = ran_phase >= 3;
+			a_same = (ran_phase == 3) ? 0 : st->same_dt;
+			break;
+		case QPO_SCHEME_CN:
+			use_cn = 2; /* CrankNicolson.hpp:52-78 rounding: (L*theta)*dt */
+			a_same = st->same_dt; /* :82-90 */
+			break;
+		case QPO_SCHEME_BDF1:
+			a_same = st->same_dt; /* BDF.hpp:511-513 */
+			break;
+		default:
+			use_bdf2 = bdf_phase >= 2;
+			a_same = (bdf_phase <= 2) ? 0 : st->same_dt; /* BDF.hpp:20-26,531-550 */
+			break;
+		}
+		/* PenaltyMethod keeps LinearSystem's default isATheSame() == false
+		 * (IterativeMethod.hpp:143-146) */
+		if(p->american) a_same = 0;
+
+		/* --- left-hand side  lA  and right-hand side  lb ----------------- */
+		{
+			const double h0 = time1 - t; /* difference(t1, t0), reverse time */
+			if(use_bdf2) {
+				/* BDF.hpp:68-117 */
+				const double h1 = time1 - t;
+				const double hh0 = time0 - t;
+				const double hh = (hh0 * h1) / (hh0 + h1);
+				const double c1 = hh0 / h1, c0 = h1 / hh0, den = hh0 - h1;
+				hA = hh;
+				for(i = 0; i < n; ++i) {
+					M_lo[i] = hh * p->lo[i];
+					M_di[i] = 1. + hh * p->di[i];
+					M_up[i] = hh * p->up[i];
+					lb[i] = ((c1 * v1[i] - c0 * v0[i]) / den + 0.) * hh;
+				}
+			} else if(use_cn == 1) {
+				/* Rannacher.hpp:50-73 */
+				hA = h0;
+				for(i = 0; i < n; ++i) {
+					M_lo[i] = p->lo[i] * h0 / 2.;
+					M_di[i] = 1. + p->di[i] * h0 / 2.;
+					M_up[i] = p->up[i] * h0 / 2.;
+				}
+				for(i = 0; i < n; ++i) {
+					/* (I - A h0/2) v0 + (b(t1)+b(t0))/2, SpMV in column order */
+					double acc = 0.;
+					if(i > 0) acc += (0. - p->lo[i] * h0 / 2.) * v1[i - 1];
+					acc += (1. - p->di[i] * h0 / 2.) * v1[i];
+					if(i < n - 1) acc += (0. - p->up[i] * h0 / 2.) * v1[i + 1];
+					lb[i] = acc + (0. + 0.) / 2.;
+				}
+			} else if(use_cn == 2) {
+				/* CrankNicolson.hpp:52-78 with theta = 1/2 */
+				const double theta = 0.5;
+				hA = h0;
+				for(i = 0; i < n; ++i) {
+					M_lo[i] = p->lo[i] * theta * h0;
+					M_di[i] = 1. + p->di[i] * theta * h0;
+					M_up[i] = p->up[i] * theta * h0;
+				}
+				for(i = 0; i < n; ++i) {
+					double acc = 0.;
+					if(i > 0) acc += (0. - p->lo[i] * (1 - theta) * h0) * v1[i - 1];
+					acc += (1. - p->di[i] * (1 - theta) * h0) * v1[i];
+					if(i < n - 1) acc += (0. - p->up[i] * (1 - theta) * h0) * v1[i + 1];
+					lb[i] = acc + (theta * 0. + (1 - theta) * 0.);
+				}
+			} else {
+				/* implicit Euler: Rannacher.hpp:32-48 / BDF.hpp:32-46 */
+				hA = h0;
+				for(i = 0; i < n; ++i) {
+					M_lo[i] = p->lo[i] * h0;
+					M_di[i] = 1. + p->di[i] * h0;
+					M_up[i] = p->up[i] * h0;
+					lb[i] = v1[i] + 0. * h0;
+				}
+			}
+		}
+		(void)hA;
+
+		if(!p->american) {
+			/* IterativeMethod.hpp:899-917 */
+			if(!initialized || !a_same) {
+				memcpy(A_lo, M_lo, sizeof(double) * (size_t)n);
+				memcpy(A_di, M_di, sizeof(double) * (size_t)n);
+				memcpy(A_up, M_up, sizeof(double) * (size_t)n);
+				tri_factor(&lu, A_lo, A_di, A_up);
+			}
+			memcpy(x, lb, sizeof(double) * (size_t)n);
+			tri_solve(&lu, x);
+			its = 1;
+		} else {
+			/* ToleranceIteration (:1211-1254) over PenaltyMethodDifference
+			 * (PenaltyMethod.hpp:37-69,96-119,259-273) */
+			memcpy(x, v1, sizeof(double) * (size_t)n);
+			do {
+				memcpy(xprev, x, sizeof(double) * (size_t)n);
+				for(i = 0; i < n; ++i) {
+					/* predicate = I x - payoff ; c = (scale*pred) < 0 */
+					const double acc = 0. + 1. * xprev[i];
+					const double pred = acc - p->obstacle[i];
+					const int c = (pen * pred) < 0.;
+					P_di[i] = c ? pen : 0.;
+					/* A = Q lA + P rA ; b = Q lb + P rb   (Q = I, rA = I) */
+					A_lo[i] = M_lo[i];
+					A_di[i] = c ? (M_di[i] + pen * 1.) : M_di[i];
+					A_up[i] = M_up[i];
+					rhs[i] = c ? (lb[i] + pen * p->obstacle[i]) : lb[i];
+				}
+				tri_factor(&lu, A_lo, A_di, A_up);
+				memcpy(x, rhs, sizeof(double) * (size_t)n);
+				tri_solve(&lu, x);
+				++its;
+				if(its >= p->max_inner) { status = 1; break; }
+			} while(relative_error(n, x, xprev, p->scale) > p->tolerance);
+		}
+		initialized = 1;
+		if(inner) inner[s] = its;
+
+		/* stepper history push (lookback 2 when BDF2, else >= 1) */
+		memcpy(v0, v1, sizeof(double) * (size_t)n);
+		time0 = time1;
+		memcpy(v1, x, sizeof(double) * (size_t)n);
+		time1 = t;
+		if(hist < 2) ++hist;
+
+		/* node onIterationEnd (called by the stepper's endNodes) */
+		if(ran_phase < 4) ++ran_phase;  /* Rannacher.hpp:75-92 */
+		if(bdf_phase < 3) ++bdf_phase;  /* BDF.hpp:531-545 */
+
+		if(st->event_after) {
+			/* IterativeMethod.hpp:1279-1295 */
+			if(p->event_obstacle && st->user_events > 0) {
+				/* Event.hpp:100-112 with the exercise transform
+				 * max(V(S), K - S) (QuantPDE::max, EarlyInclude.hpp:48);
+				 * applying it user_events times is idempotent */
+				for(i = 0; i < n; ++i) {
+					const double ex = p->event_obstacle[i];
+					v1[i] = v1[i] > ex ? v1[i] : ex;
+				}
+			}
+			/* afterEvent(): default IterationNode::onAfterEvent -> clear()
+			 * (IterativeMethod.hpp:780-783); Rannacher overrides it with a
+			 * no-op (Rannacher.hpp:115-117) */
+			bdf_phase = 1;
+			hist = 1;
+		}
+	}
+
+	if(mask) {
+		/* PenaltyMethod::constraintMask (PenaltyMethod.hpp:127-139) on the
+		 * tolerance iteration's last iterand */
+		for(i = 0; i < n; ++i) {
+			const double acc = 0. + 1. * v1[i];
+			mask[i] = (acc - (p->obstacle ? p->obstacle[i] : 0.)) < 0.;
+		}
+	}
+	memcpy(V, v1, sizeof(double) * (size_t)n);
+
+	tri_free(&lu);
+	free(A_lo); free(A_di); free(A_up); free(M_lo); free(M_di); free(M_up);
+	free(P_di); free(lb); free(rhs); free(x); free(xprev); free(v1); free(v0);
+	return status;
+}

@@ -1,0 +1,89 @@
+/* TEST INFRASTRUCTURE ONLY.  CPU restatement (plain C) of the reference's 1-D
+ * time-stepping hot path, used as the parity checker by tests/, by
+ * __graft_entry__.smoke() and by bench.py's cpu_baseline leg.  The product
+ * path (quantpde_b200/, libqpde_b200.so) never includes, links or calls this.
+ *
+ * Parity pin: every function here is checked bit-for-bit against programs
+ * built from the UNMODIFIED reference headers (oracle/_ref/qpde_ref, see
+ * oracle/Makefile) and against the committed fixtures in tests/golden/.
+ * The linear algebra underneath those programs is oracle/shim's (Eigen 3 is
+ * not available offline), so the LU arithmetic is "Eigen-like", not Eigen's.
+ *
+ * All citations are file:line under /root/reference/QuantPDE/src.
+ */
+#ifndef QPDE_ORACLE_H
+#define QPDE_ORACLE_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+enum {
+	QPO_SCHEME_RANNACHER = 0, /* Core/Rannacher.hpp:23-121 */
+	QPO_SCHEME_CN        = 1, /* Core/CrankNicolson.hpp:52-78, theta = 1/2 */
+	QPO_SCHEME_BDF1      = 2, /* Core/BDF.hpp:32-46,484-517 */
+	QPO_SCHEME_BDF2      = 3  /* Core/BDF.hpp:68-117,522-590 */
+};
+
+/* One entry of the replayed time loop (Core/IterativeMethod.hpp:1259-1317). */
+typedef struct {
+	double t;        /* implicit time of the step                         */
+	double dt;       /* the stepper's dt variable after clamping          */
+	int    same_dt;  /* TimeIteration::isTimestepTheSame(): dt==dtPrevious */
+	int    event_after; /* 1 if the event loop body ends after this step
+	                       (afterEvent() + history clear follow)           */
+	int    user_events; /* user events applied after this step (0 when only
+	                       the terminating NullEvent fires)                */
+} qpo_step;
+
+/* Axis::special, 33 ticks (Core/Axis.hpp:445-459). Returns 33. */
+int qpo_axis_special(double *out);
+/* Axis union (Core/Axis.hpp:270-313). out must hold na+nb. Returns size. */
+int qpo_axis_union(const double *a, int na, const double *b, int nb, double *out);
+/* RectilinearGrid::refined (Core/Domain.hpp:1092-1151). Returns new size
+ * 2^times (n-1) + 1; out may be NULL to query the size. */
+int qpo_axis_refine(const double *in, int n, int times, double *out);
+
+/* Replays ReverseConstantStepper over [0, T] with events at event_times
+ * (any order).  Returns the number of steps (writes at most max_steps). */
+int qpo_schedule(double T, double dt, const double *event_times, int n_events,
+		qpo_step *out, int max_steps);
+
+/* BlackScholes<1,0>::A rows (Modules/Operators/BlackScholes.hpp:136-226).
+ * r, v, q, lambda are per-node arrays of length n. */
+void qpo_bs_coeffs(int n, const double *S, const double *r, const double *v,
+		const double *q, const double *lambda, double kappa,
+		double *lo, double *di, double *up);
+
+/* Piecewise-linear read-out (Core/Interpolant.hpp:153-181,331-374). */
+double qpo_interp(int n, const double *x, const double *v, double c);
+
+typedef struct {
+	int n;                 /* nodes */
+	double T;              /* initial (expiry) time of the reverse sweep   */
+	const double *S;       /* [n] */
+	const double *lo, *di, *up; /* operator rows from qpo_bs_coeffs        */
+	const double *v0;      /* [n] initial condition at t = T               */
+	int scheme;            /* QPO_SCHEME_*                                 */
+	int n_steps;
+	const qpo_step *steps; /* from qpo_schedule                            */
+	int american;          /* 1: MinPenaltyMethodDifference + ToleranceIteration */
+	const double *obstacle;/* [n] payoff for the penalty / exercise events */
+	double tolerance;      /* ToleranceIteration tolerance (1e-6)          */
+	double scale;          /* relativeError scale (1)                      */
+	double penalty_tol;    /* PenaltyMethod tolerance; scale = 1/this      */
+	int max_inner;         /* guard (the reference has none)               */
+	const double *event_obstacle; /* [n] or NULL: at each user event
+	                          V = max(V, event_obstacle) (tutorial.cpp:103-105) */
+} qpo_problem;
+
+/* Runs the sweep.  V [n] out; inner [n_steps] out (may be NULL); mask [n] out
+ * (may be NULL).  Returns 0, or 1 if some step hit max_inner. */
+int qpo_sweep_1d(const qpo_problem *p, double *V, int *inner,
+		unsigned char *mask);
+
+#ifdef __cplusplus
+}
+#endif
+
+#endif

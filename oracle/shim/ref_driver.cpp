@@ -1,0 +1,281 @@
+// TEST INFRASTRUCTURE ONLY (oracle/_ref).  Never linked into the product path.
+//
+// A client of the UNMODIFIED reference headers under /root/reference, compiled
+// against oracle/shim/qpde_linalg_binding.hpp through the reference's own
+// QUANT_PDE_BOUND seam (QuantPDE/Core:6-9).  It wires the reference classes the
+// way the reference's example programs do
+//   american / european : examples/vanilla_options.cpp:34-130
+//   bermudan            : examples/tutorial.cpp:58-141
+//   hjb                 : examples/unequal_borrowing_lending_rates.cpp:90-170
+//   jump                : examples/jump_diffusion.cpp:60-160
+// and dumps every node value (hex floats), the per-step inner iteration counts,
+// the final penalty active set and the wall-clock of stepper.solve (timed as
+// Modules/Utilities/Results.hpp:103-108 does).
+//
+// Usage: qpde_ref <mode> key=value ...        (see usage() below)
+
+#include <QuantPDE/src/Core/EarlyInclude.hpp>
+#include "qpde_linalg_binding.hpp"
+#include <QuantPDE/Core>
+#include <QuantPDE/Modules/Lambdas>
+#include <QuantPDE/Modules/Operators>
+
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
+#include <map>
+#include <memory>
+#include <string>
+
+using namespace QuantPDE;
+using namespace QuantPDE::Modules;
+
+namespace {
+
+typedef std::map<std::string, std::string> Args;
+
+double num(const Args &a, const char *key, double dflt) {
+	auto it = a.find(key);
+	return it == a.end() ? dflt : std::strtod(it->second.c_str(), nullptr);
+}
+
+long integer(const Args &a, const char *key, long dflt) {
+	auto it = a.find(key);
+	return it == a.end() ? dflt : std::strtol(it->second.c_str(), nullptr, 10);
+}
+
+std::string str(const Args &a, const char *key, const char *dflt) {
+	auto it = a.find(key);
+	return it == a.end() ? std::string(dflt) : it->second;
+}
+
+void dumpReals(const char *name, const std::vector<double> &v) {
+	std::printf("%s %zu\n", name, v.size());
+	for(size_t i = 0; i < v.size(); ++i) {
+		std::printf("%a%c", v[i], (i + 1) % 8 == 0 ? '\n' : ' ');
+	}
+	if(v.size() % 8 != 0) std::printf("\n");
+}
+
+void dumpInts(const char *name, const std::vector<long> &v) {
+	std::printf("%s %zu\n", name, v.size());
+	for(size_t i = 0; i < v.size(); ++i) {
+		std::printf("%ld%c", v[i], (i + 1) % 32 == 0 ? '\n' : ' ');
+	}
+	if(v.size() % 32 != 0) std::printf("\n");
+}
+
+// Base axis selection: "special" = K/100-scaled Axis::special times 100 (what
+// vanilla_options builds with S_0 = K), "tutorial" = the 34-tick hand-picked
+// axis of examples/tutorial.cpp:41-56 scaled by K/100, "jump" = the
+// jump_diffusion.cpp:166 axis.
+Axis baseAxis(const std::string &kind, Real S0, Real K) {
+	if(kind == "special") {
+		return (S0 * Axis::special) + (K * Axis::special);
+	}
+	if(kind == "tutorial") {
+		Axis a {
+			0., 10., 20., 30., 40., 50., 60., 70., 75., 80., 84., 88.,
+			92., 94., 96., 98., 100., 102., 104., 106., 108., 110., 114.,
+			118., 123., 130., 140., 150., 175., 225., 300., 750., 2000.,
+			10000.
+		};
+		return a * (K / 100.);
+	}
+	std::fprintf(stderr, "unknown axis kind %s\n", kind.c_str());
+	std::exit(2);
+}
+
+template <typename G, typename I>
+std::vector<double> nodeValues(const G &grid, const I &solution) {
+	const Axis &S = grid[0];
+	std::vector<double> v((size_t)S.size());
+	for(Index i = 0; i < S.size(); ++i) v[i] = solution(S[i]);
+	return v;
+}
+
+template <typename G>
+std::vector<double> nodes(const G &grid) {
+	const Axis &S = grid[0];
+	std::vector<double> v((size_t)S.size());
+	for(Index i = 0; i < S.size(); ++i) v[i] = S[i];
+	return v;
+}
+
+////////////////////////////////////////////////////////////////////////////////
+// vanilla: European / American put or call, Rannacher (default), plain
+// Crank-Nicolson, BDF1 or BDF2 time stepping, penalty method for American
+////////////////////////////////////////////////////////////////////////////////
+
+int runVanilla(const Args &a) {
+	const Real K = num(a, "K", 100.), S0 = num(a, "S0", K);
+	const Real r = num(a, "r", .04), vol = num(a, "vol", .2);
+	const Real q = num(a, "q", 0.), T = num(a, "T", 1.);
+	const long steps = integer(a, "steps", 12);
+	const int refine = (int) integer(a, "refine", 0);
+	const bool american = integer(a, "american", 1) != 0;
+	const bool call = integer(a, "call", 0) != 0;
+	const std::string scheme = str(a, "scheme", "rannacher");
+	const int repeat = (int) integer(a, "repeat", 1);
+
+	RectilinearGrid1 coarse( baseAxis(str(a, "axis", "special"), S0, K) );
+	auto grid = coarse.refined(refine);
+
+	Function1 payoff = call ? callPayoff(K) : putPayoff(K);
+
+	double seconds = 0.;
+	std::vector<double> values;
+	std::vector<long> inner, mask;
+	long timesteps = 0;
+
+	for(int rep = 0; rep < repeat; ++rep) {
+		BlackScholes1 bs(grid, r, vol, q);
+		ReverseConstantStepper stepper(0., T, T / steps);
+
+		std::unique_ptr<IterationNode> discretization;
+		if(scheme == "rannacher") {
+			discretization.reset(new ReverseRannacher(grid, bs));
+		} else if(scheme == "cn") {
+			discretization.reset(new ReverseCrankNicolson(grid, bs));
+		} else if(scheme == "bdf1") {
+			discretization.reset(new ReverseBDFOne(grid, bs));
+		} else if(scheme == "bdf2") {
+			discretization.reset(new ReverseBDFTwo(grid, bs));
+		} else {
+			std::fprintf(stderr, "unknown scheme\n");
+			return 2;
+		}
+		discretization->setIteration(stepper);
+
+		ToleranceIteration tolerance;
+		std::unique_ptr<MinPenaltyMethodDifference1> penalty;
+		IterationNode *root = discretization.get();
+		if(american) {
+			penalty.reset(new MinPenaltyMethodDifference1(
+					grid, *discretization, payoff));
+			penalty->setIteration(tolerance);
+			stepper.setInnerIteration(tolerance);
+			root = penalty.get();
+		}
+
+		SparseLUSolver solver;
+
+		auto begin = std::chrono::steady_clock::now();
+		auto solution = stepper.solve(grid, payoff, *root, solver);
+		auto end = std::chrono::steady_clock::now();
+		seconds += std::chrono::duration<double>(end - begin).count();
+
+		if(rep == 0) {
+			values = nodeValues(grid, solution);
+			timesteps = (long) stepper.iterations()[0];
+			if(american) {
+				for(auto k : tolerance.iterations()) inner.push_back((long)k);
+				for(bool b : penalty->constraintMask()) mask.push_back(b);
+			}
+			std::printf("value %a\n", (double) solution(S0));
+		}
+	}
+
+	std::printf("seconds %.9g\n", seconds / repeat);
+	std::printf("steps %ld\n", timesteps);
+	dumpReals("S", nodes(grid));
+	dumpReals("V", values);
+	dumpInts("inner", inner);
+	dumpInts("mask", mask);
+	return 0;
+}
+
+////////////////////////////////////////////////////////////////////////////////
+// bermudan: local volatility alpha / S, E exercise dates at T e / E,
+// BDF2 (tutorial.cpp) or Rannacher, no inner iteration
+////////////////////////////////////////////////////////////////////////////////
+
+int runBermudan(const Args &a) {
+	const Real K = num(a, "K", 100.);
+	const Real r = num(a, "r", .04), alpha = num(a, "alpha", 20.);
+	const Real q = num(a, "q", 0.), T = num(a, "T", 1.);
+	const long steps = integer(a, "steps", 100);
+	const int E = (int) integer(a, "E", 10);
+	const int refine = (int) integer(a, "refine", 0);
+	const std::string scheme = str(a, "scheme", "bdf2");
+	const int repeat = (int) integer(a, "repeat", 1);
+
+	RectilinearGrid1 coarse( baseAxis(str(a, "axis", "tutorial"), K, K) );
+	auto grid = coarse.refined(refine);
+
+	auto payoff = [K] (Real S) { return max(K - S, 0.); };
+	auto exercise = [K] (const Interpolant1 &V, Real S) {
+		return max(V(S), K - S);
+	};
+	auto localVol = [alpha] (Real S) { return alpha / S; };
+
+	double seconds = 0.;
+	std::vector<double> values;
+	long timesteps = 0;
+
+	for(int rep = 0; rep < repeat; ++rep) {
+		ReverseConstantStepper stepper(0., T, T / steps);
+		for(int e = 0; e < E; ++e) {
+			stepper.add(T / E * e, exercise, grid);
+		}
+
+		BlackScholes1 bs(grid, r, localVol, q);
+
+		std::unique_ptr<IterationNode> discretization;
+		if(scheme == "bdf2") {
+			discretization.reset(new ReverseBDFTwo(grid, bs));
+		} else if(scheme == "bdf1") {
+			discretization.reset(new ReverseBDFOne(grid, bs));
+		} else if(scheme == "rannacher") {
+			discretization.reset(new ReverseRannacher(grid, bs));
+		} else {
+			discretization.reset(new ReverseCrankNicolson(grid, bs));
+		}
+		discretization->setIteration(stepper);
+
+		SparseLUSolver solver;
+
+		auto begin = std::chrono::steady_clock::now();
+		auto solution = stepper.solve(grid, payoff, *discretization, solver);
+		auto end = std::chrono::steady_clock::now();
+		seconds += std::chrono::duration<double>(end - begin).count();
+
+		if(rep == 0) {
+			values = nodeValues(grid, solution);
+			timesteps = (long) stepper.iterations()[0];
+			std::printf("value %a\n", (double) solution(K));
+		}
+	}
+
+	std::printf("seconds %.9g\n", seconds / repeat);
+	std::printf("steps %ld\n", timesteps);
+	dumpReals("S", nodes(grid));
+	dumpReals("V", values);
+	return 0;
+}
+
+void usage() {
+	std::fprintf(stderr,
+		"qpde_ref vanilla  K= S0= r= vol= q= T= steps= refine= american=0|1 "
+		"call=0|1 scheme=rannacher|cn|bdf1|bdf2 axis=special|tutorial repeat=\n"
+		"qpde_ref bermudan K= r= alpha= q= T= steps= E= refine= "
+		"scheme=bdf2|bdf1|rannacher|cn axis= repeat=\n");
+}
+
+} // namespace
+
+int main(int argc, char **argv) {
+	if(argc < 2) { usage(); return 2; }
+	Args a;
+	for(int i = 2; i < argc; ++i) {
+		std::string s(argv[i]);
+		const size_t eq = s.find('=');
+		if(eq == std::string::npos) { usage(); return 2; }
+		a[s.substr(0, eq)] = s.substr(eq + 1);
+	}
+	const std::string mode(argv[1]);
+	if(mode == "vanilla")  return runVanilla(a);
+	if(mode == "bermudan") return runBermudan(a);
+	usage();
+	return 2;
+}
