@@ -1,0 +1,345 @@
+#!/usr/bin/env python
+"""bench.py — option PDE solves/sec on BASELINE.json's configs[1]:
+a batch of American puts (varied strike / vol / T / r, seeded as SURVEY.md
+§8(d)), 1-D Rannacher(CN) + PenaltyMethod, 2049 nodes x 1000 steps, FP64.
+
+    python bench.py --gpus N --steps K --warmup W [--impl reference]
+    torchrun ... bench.py --gpus N ...      (one rank per GPU, N > 1)
+
+A "step" is one pass of the hot path over one batch (one qpde_bs1d_plan_run of
+all contracts).  `value` = contracts / device time with the batch resident in
+HBM; `e2e` = the same through qpde_bs1d_sweep with HOST buffers (H2D + run +
+D2H inside the timed region).  Contracts shard across ranks with no data-path
+collective (weak scaling: each rank owns --contracts contracts).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+N_NODES_REFINE = 6          # Axis::special (33 ticks) refined 6x -> 2049 nodes
+N_STEPS = 1000
+ALG_BYTES_PER_NODE_SOLVE = 56   # 7 FP64 vectors per inner solve
+
+
+def contract_parameters(n, rank=0):
+    """default_rng(1234); K, sigma, T, r drawn in this
+    order.  Rank k > 0 draws its own disjoint batch from seed 1234 + k."""
+    rng = np.random.default_rng(1234 + rank)
+    K = rng.uniform(50, 150, n)
+    vol = rng.uniform(0.10, 0.60, n)
+    T = rng.uniform(0.25, 2.0, n)
+    r = rng.uniform(0.01, 0.08, n)
+    return K, vol, T, r
+
+
+SPECIAL = np.array([0., .1, .2, .3, .4, .5, .6, .7, .80, .84, .88, .92, .94, .96, .98, 1.,
+                    1.02, 1.04, 1.06, 1.08, 1.10, 1.14, 1.18, 1.23, 1.30, 1.40, 1.50, 1.75,
+                    2.25, 3.00, 7.50, 20., 100.])   # Axis::special, Core/Axis.hpp:445-459
+
+
+def load_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        return float(json.load(open(path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def load_traffic(kernel):
+    """dram bytes per launch from the committed ncu --set full capture, if any."""
+    path = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(path):
+        d = json.load(open(path))
+        return d.get(kernel)
+    return None
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                 "--format=csv,noheader,nounits", "-lms", "200"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, smax, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); smax = float(f[2])
+            except ValueError:
+                continue
+            for name, val in zip(names, f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": smax,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ---------------------------------------------------------------------------
+# CPU arm: the reference's own implementation of the path on the host cores
+# ---------------------------------------------------------------------------
+
+def _cpu_one(args):
+    """One contract on one core.  kind 'reference' = oracle/_ref/qpde_ref (the
+    unmodified reference headers on oracle/shim's linear algebra), else the C
+    restatement oracle/qpde_oracle.c."""
+    kind, K, vol, T, r = args
+    from oracle import pyoracle as po
+    t0 = time.perf_counter()
+    if kind == "reference":
+        out = po.run_ref("vanilla", american=1, steps=N_STEPS, refine=N_NODES_REFINE,
+                         K=float(K), r=float(r), vol=float(vol), T=float(T))
+        inner = int(out["inner"].sum())
+        secs = out["seconds"]            # steady_clock around stepper.solve (Results.hpp:103-108)
+    else:
+        out = po.american_put(float(K), float(r), float(vol), float(T), N_STEPS, N_NODES_REFINE)
+        inner = int(out["inner"].sum())
+        secs = time.perf_counter() - t0
+    return secs, inner
+
+
+def cpu_baseline(n_sample, kind=None):
+    """Times a bounded sample of the workload on all host cores (one contract
+    per worker process, as BASELINE.md §3 prescribes for the single-threaded
+    reference).  Returns solves/s for the whole host."""
+    from concurrent.futures import ProcessPoolExecutor
+    from oracle import pyoracle as po
+    po.lib()
+    if kind is None:
+        kind = "reference" if po.have_ref() else "port"
+    cores = os.cpu_count() or 1
+    K, vol, T, r = contract_parameters(n_sample)
+    jobs = [(kind, K[i], vol[i], T[i], r[i]) for i in range(n_sample)]
+    t0 = time.perf_counter()
+    with ProcessPoolExecutor(max_workers=cores) as ex:
+        results = list(ex.map(_cpu_one, jobs))
+    wall = time.perf_counter() - t0
+    per_contract = float(np.mean([s for s, _ in results]))
+    return {"value": n_sample / wall, "unit": "solves/s", "cores": cores, "kind": kind,
+            "sample": "%d contracts of the same seeded workload (2049 nodes x 1000 steps), one per "
+                      "worker process on %d cores; %.3f s per contract single-threaded; LU is "
+                      "oracle/shim's stand-in, not Eigen's" % (n_sample, cores, per_contract),
+            "seconds_per_contract_1core": per_contract, "wall_s": wall}
+
+
+# ---------------------------------------------------------------------------
+
+def run_reference_arm(args, rank, world):
+    if rank != 0:
+        return
+    from oracle import pyoracle as po
+    po.lib()
+    cores = os.cpu_count() or 1
+    n_sample = args.cpu_sample or max(cores, 8)
+    for _ in range(args.warmup):
+        cpu_baseline(min(cores, n_sample))
+    vals, walls = [], []
+    for _ in range(args.steps):
+        b = cpu_baseline(n_sample)
+        vals.append(b["value"]); walls.append(b["wall_s"])
+    value = float(n_sample * len(walls) / sum(walls))
+    line = {
+        "impl": "reference", "metric": "option PDE solves/sec (N=2049, 1000 CN steps)",
+        "value": value, "unit": "solves/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * float(np.mean(walls)),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic",
+        "config": {"workload": "american_put_batch_2049x1000 (BASELINE.json configs[1])",
+                   "contracts_per_step": n_sample, "nodes": 2049, "time_steps": N_STEPS,
+                   "scheme": "rannacher+penalty"},
+        "cpu_baseline": {k: b[k] for k in ("value", "unit", "cores", "kind", "sample")},
+        "e2e": {"value": value, "unit": "solves/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    line["cpu_baseline"]["value"] = value
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--contracts", type=int, default=65536, help="contracts per GPU")
+    ap.add_argument("--kernel", default="auto", choices=["auto", "interleaved", "resident"])
+    ap.add_argument("--cpu-sample", type=int, default=0)
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if args.impl == "reference":
+        run_reference_arm(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from quantpde_b200 import capi
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    Cn = args.contracts
+    K, vol, T, r = contract_parameters(Cn, rank)
+    axis = np.ascontiguousarray(K[:, None] * SPECIAL[None, :])     # K * Axis::special (S_0 = K)
+    handle = capi.Handle(local)
+    outputs = capi.OUT_V | capi.OUT_VALUE | capi.OUT_INNER_TOTAL | capi.OUT_STATUS | capi.OUT_STEPS
+    spec = capi.BatchSpec(axis=axis, refine=N_NODES_REFINE, r=r, sigma=vol, q=0.0, T=T,
+                          dt=T / N_STEPS, strike=K, american=True, payoff="put",
+                          kernel=args.kernel, outputs=outputs)
+    plan = capi.Plan(handle, spec)
+    N = plan.N
+    stream = torch.cuda.ExternalStream(handle.stream, device=torch.device("cuda", local))
+    flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device="cuda")  # > 126 MB L2
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def flush_l2():
+        flush.fill_(1.0)
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        plan.run()
+        handle.synchronize()
+
+    sampler = ClockSampler(local)
+    barrier()
+    sampler.start()
+    launches0 = handle.launches
+    times_ms = []
+    for _ in range(args.steps):
+        flush_l2()
+        e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        plan.run()
+        e1.record(stream)
+        e1.synchronize()
+        times_ms.append(e0.elapsed_time(e1))
+    launches = handle.launches - launches0
+    barrier()
+    clocks = sampler.stop()
+    total_ms = float(sum(times_ms))
+
+    res = plan.fetch(capi.OUT_INNER_TOTAL | capi.OUT_STATUS | capi.OUT_STEPS)
+    inner_sum = int(res.inner_total.astype(np.int64).sum())
+    not_converged = int((res.status != 0).sum())
+
+    # ---- e2e: qpde_bs1d_sweep with host buffers, copies inside the timed region
+    e2e = None
+    if not args.no_e2e:
+        e2e_out = capi.OUT_V | capi.OUT_VALUE | capi.OUT_INNER_TOTAL | capi.OUT_STATUS
+        e2e_times = []
+        for i in range(1 + min(args.steps, 2)):
+            barrier()
+            t0 = time.perf_counter()
+            r2 = capi.sweep(handle, spec, outputs=e2e_out)
+            torch.cuda.synchronize()
+            dt_s = time.perf_counter() - t0
+            if i > 0:
+                e2e_times.append(dt_s)
+        h2d = axis.nbytes + 6 * 8 * Cn
+        d2h = r2.V.nbytes + r2.value.nbytes + r2.inner_total.nbytes + r2.status.nbytes
+        e2e_ms = 1e3 * float(np.mean(e2e_times))
+        del r2
+    if world > 1:
+        tt = torch.tensor([total_ms, e2e_ms if not args.no_e2e else 0.0], device="cuda", dtype=torch.float64)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        ii = torch.tensor([inner_sum, not_converged], device="cuda", dtype=torch.int64)
+        dist.all_reduce(ii, op=dist.ReduceOp.SUM)
+        total_ms, e2e_ms_max = float(tt[0]), float(tt[1])
+        inner_sum_all, not_converged = int(ii[0]), int(ii[1])
+    else:
+        e2e_ms_max = e2e_ms if not args.no_e2e else 0.0
+        inner_sum_all = inner_sum
+    if not args.no_e2e:
+        e2e = {"value": Cn * world / (e2e_ms_max / 1e3), "unit": "solves/s",
+               "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+               "ms_per_step": e2e_ms_max,
+               "api": "qpde_bs1d_sweep (host pointers; V[C][N] + value + inner_total + status returned)"}
+
+    ms_per_step = total_ms / args.steps
+    value = Cn * world / (ms_per_step / 1e3)
+
+    peak, peak_src = load_peaks()
+    alg_bytes = ALG_BYTES_PER_NODE_SOLVE * N * (inner_sum_all / world)   # per launch (one rank's batch)
+    achieved = alg_bytes / (ms_per_step / 1e3) / 1e9
+    traffic = load_traffic(plan.kernel)
+    line = {
+        "metric": "option PDE solves/sec (N=2049, 1000 CN steps)", "value": value, "unit": "solves/s",
+        "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic",
+        "config": {"workload": "american_put_batch_2049x1000 (BASELINE.json configs[1])",
+                   "contracts_per_gpu": Cn, "nodes": N, "time_steps": N_STEPS,
+                   "scheme": "rannacher+penalty", "kernel": plan.kernel,
+                   "mean_inner_iterations_per_step": inner_sum_all / (world * Cn * float(N_STEPS)),
+                   "not_converged": not_converged,
+                   "l2": "flushed between timed steps (256 MiB write)",
+                   "parallelism": "contracts sharded over %d rank(s), no collective" % world},
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                     "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                     "algorithmic_bytes_per_launch": alg_bytes,
+                     "model": "56 B x nodes x sum of inner solves (SURVEY.md 8d); the RESIDENT kernel "
+                              "keeps state on chip, so frac > 1 means it has left the HBM roofline"},
+        "clocks": clocks, "gpu_launches": int(launches), "e2e": e2e,
+    }
+    if rank == 0 and not args.no_cpu:
+        cores = os.cpu_count() or 1
+        line["cpu_baseline"] = {k: v for k, v in cpu_baseline(args.cpu_sample or max(cores, 8)).items()
+                                if k in ("value", "unit", "cores", "kind", "sample")}
+    plan.close()
+    handle.close()
+    if rank == 0:
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,237 @@
+/* qpde_b200.h — C ABI of libqpde_b200.so
+ *
+ * A B200 (sm_100a, FP64) replacement for ONE path of parsiad/QuantPDE: the
+ * backward time-stepping sweep over a 1-D RectilinearGrid, batched across
+ * contracts.  One call does what one `stepper.solve(grid, payoff, root, solver)`
+ * does in the reference (QuantPDE/src/Core/IterativeMethod.hpp:1065-1079) for
+ * every contract of a batch, where the reference's iteration tree is
+ *
+ *   ReverseConstantStepper                   Core/Stepper.hpp:9-38
+ *    └ [ToleranceIteration]                  Core/IterativeMethod.hpp:1211-1254
+ *   root = [MinPenaltyMethodDifference1 ∘]   Core/PenaltyMethod.hpp:168-303
+ *          ReverseRannacher | ReverseCrankNicolson | ReverseBDFOne | ReverseBDFTwo
+ *                                            Core/Rannacher.hpp, CrankNicolson.hpp, BDF.hpp
+ *          ∘ BlackScholes1(grid, r, v, q)    Modules/Operators/BlackScholes.hpp:114-237
+ *   events: Bermudan exercise  V <- max(V, obstacle)     Core/Event.hpp:100-112
+ *   solver: SparseLUSolver (replaced by the in-kernel tridiagonal solve)
+ *                                            Bindings/Eigen.hpp:143-165
+ *
+ * Plain pointers and sizes only; no C++ or torch types.  Every function
+ * returns QPDE_OK (0) or a negative error code; qpde_last_error() gives text.
+ * All array arguments are HOST pointers unless a name ends in `_dev`.
+ * Arrays over contracts and nodes are contract-major: element (c, i) lives at
+ * base[c * stride + i]; a stride of 0 shares one row between all contracts.
+ *
+ * There is no CPU fallback: qpde_create() fails if no sm_100 device is present.
+ */
+#ifndef QPDE_B200_H
+#define QPDE_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define QPDE_ABI_VERSION 1
+
+/* ---- status codes ----------------------------------------------------- */
+enum {
+	QPDE_OK             =  0,
+	QPDE_ERR_INVALID    = -1, /* bad argument (message says which)          */
+	QPDE_ERR_CUDA       = -2, /* CUDA runtime error                         */
+	QPDE_ERR_NO_DEVICE  = -3, /* no sm_100 GPU: there is no CPU fallback    */
+	QPDE_ERR_NOT_CONVERGED = -4, /* informational: some contract hit max_inner;
+	                                results are still written, see status[] */
+	QPDE_ERR_UNSUPPORTED = -5
+};
+
+/* ---- time discretisation (which reference IterationNode is the root) -- */
+enum {
+	QPDE_SCHEME_RANNACHER = 0, /* ReverseRannacher,      Core/Rannacher.hpp:23-135   */
+	QPDE_SCHEME_CN        = 1, /* ReverseCrankNicolson,  Core/CrankNicolson.hpp:52-105 */
+	QPDE_SCHEME_BDF1      = 2, /* ReverseBDFOne,         Core/BDF.hpp:484-517        */
+	QPDE_SCHEME_BDF2      = 3  /* ReverseBDFTwo,         Core/BDF.hpp:522-590        */
+};
+
+/* ---- initial condition / obstacle generators (Modules/Lambdas/Payoffs.hpp:13-51) */
+enum {
+	QPDE_PAYOFF_ARRAY        = 0, /* use the array given                    */
+	QPDE_PAYOFF_PUT          = 1, /* S < K ? K - S : 0          :38-40      */
+	QPDE_PAYOFF_CALL         = 2, /* S < K ? 0 : S - K          :29-31      */
+	QPDE_PAYOFF_DIGITAL_PUT  = 3, /* S > K ? 0 : 1              :20-22      */
+	QPDE_PAYOFF_DIGITAL_CALL = 4, /* S < K ? 0 : 1              :13-15      */
+	QPDE_PAYOFF_STRADDLE     = 5, /* S < K ? K - S : S - K      :47-49      */
+	QPDE_PAYOFF_K_MINUS_S    = 6  /* K - S (exercise value of tutorial.cpp:103-105) */
+};
+
+/* ---- volatility model of BlackScholes1's `v` argument ----------------- */
+enum {
+	QPDE_VOL_CONST     = 0, /* v = sigma[c]                                 */
+	QPDE_VOL_INVERSE_S = 1, /* v(S) = sigma[c] / S  (tutorial.cpp:120-123)  */
+	QPDE_VOL_NODES     = 2  /* v given per node in sigma_nodes              */
+};
+
+/* ---- kernel selection -------------------------------------------------- */
+enum {
+	QPDE_KERNEL_AUTO        = 0,
+	QPDE_KERNEL_INTERLEAVED = 1, /* one thread per contract, [N][C] HBM layout */
+	QPDE_KERNEL_RESIDENT    = 2  /* one CTA per contract, state in registers/SMEM */
+};
+
+/* ---- output selection (bit mask) -------------------------------------- */
+enum {
+	QPDE_OUT_V           = 1,
+	QPDE_OUT_S           = 2,
+	QPDE_OUT_VALUE       = 4,
+	QPDE_OUT_STEPS       = 8,
+	QPDE_OUT_INNER_TOTAL = 16,
+	QPDE_OUT_INNER       = 32,
+	QPDE_OUT_ACTIVE      = 64,
+	QPDE_OUT_STATUS      = 128,
+	QPDE_OUT_ALL         = 255
+};
+
+typedef struct qpde_handle qpde_handle;       /* device context + stream   */
+typedef struct qpde_bs1d_plan qpde_bs1d_plan; /* device-resident batch     */
+
+/* One entry of the replayed ReverseConstantStepper time loop
+ * (Core/IterativeMethod.hpp:1259-1317, Core/Stepper.hpp:16-18). */
+typedef struct {
+	double  t;           /* implicit time of the step                      */
+	double  dt;          /* stepper's dt after event clamping              */
+	int32_t same_dt;     /* isTimestepTheSame(): dt == dtPrevious          */
+	int32_t event_after; /* the event-loop body ends after this step       */
+	int32_t user_events; /* user events applied after this step            */
+	int32_t reserved;
+} qpde_step;
+
+/* Batch description: C contracts on grids of N nodes each. */
+typedef struct {
+	int32_t abi_version;     /* QPDE_ABI_VERSION                            */
+	int32_t n_contracts;     /* C >= 1                                      */
+
+	/* --- grid: RectilinearGrid1(axis).refined(refine)  (Core/Domain.hpp:1092-1151)
+	 * axis: coarse ticks, strictly increasing, [C][n_axis] with axis_stride
+	 * (0 = one axis shared by all contracts).  N = 2^refine (n_axis - 1) + 1. */
+	const double *axis;
+	int64_t axis_stride;
+	int32_t n_axis;
+	int32_t refine;
+
+	/* --- operator BlackScholes1(grid, r, v, q)  (BlackScholes.hpp:114-226) */
+	const double *r;         /* [C] interest rate                           */
+	const double *sigma;     /* [C] volatility parameter (see vol_model)    */
+	const double *q;         /* [C] dividend rate                           */
+	int32_t vol_model;       /* QPDE_VOL_*                                  */
+	int32_t reserved0;
+	const double *sigma_nodes; /* [C][N] when vol_model == QPDE_VOL_NODES   */
+	int64_t sigma_nodes_stride;
+
+	/* --- stepper ReverseConstantStepper(0, T, dt)  (Stepper.hpp:27-36) */
+	const double *T;         /* [C] expiry                                  */
+	const double *dt;        /* [C] step size (e.g. T / 1000)               */
+	int32_t scheme;          /* QPDE_SCHEME_*                               */
+	int32_t max_steps;       /* upper bound on replayed steps per contract;
+	                            0 = derive (the library replays the loop)   */
+
+	/* --- events: stepper.add(te, exerciseEvent, grid), te = T e / E for
+	 * e = 0 .. n_exercise-1 (tutorial.cpp:108-114); 0 = none */
+	int32_t n_exercise;
+	int32_t exercise_kind;   /* QPDE_PAYOFF_* generator of the exercise value */
+
+	/* --- initial condition and obstacle */
+	const double *strike;    /* [C] K for the generators                    */
+	int32_t payoff_kind;     /* initial condition V(T, S)                   */
+	int32_t obstacle_kind;   /* penalty obstacle (american) — usually = payoff_kind */
+	const double *payoff;    /* [C][N] when payoff_kind == QPDE_PAYOFF_ARRAY */
+	int64_t payoff_stride;
+	const double *obstacle;  /* [C][N] when obstacle_kind == QPDE_PAYOFF_ARRAY */
+	int64_t obstacle_stride;
+
+	/* --- American constraint: MinPenaltyMethodDifference1 + ToleranceIteration */
+	int32_t american;        /* 0 = European/Bermudan (root = discretisation) */
+	int32_t max_inner;       /* iteration guard per step (the reference has
+	                            none and would loop forever); e.g. 100       */
+	double  tolerance;       /* ToleranceIteration tolerance, 1e-6  (IterativeMethod.hpp:1243) */
+	double  scale;           /* relativeError scale, 1              (EarlyInclude.hpp:63)     */
+	double  penalty_tolerance; /* PenaltyMethod tolerance, 1e-6; penalty = 1/this (PenaltyMethod.hpp:85) */
+
+	/* --- read-out point: value[c] = V(spot[c]) piecewise linear
+	 * (Core/Interpolant.hpp:153-181,331-374); NULL = strike */
+	const double *spot;
+
+	int32_t kernel;          /* QPDE_KERNEL_* (AUTO picks by N)             */
+	int32_t outputs;         /* split form only: QPDE_OUT_* mask of the outputs
+	                            to keep on the device; 0 = all.  The one-shot
+	                            call derives it from the result pointers.   */
+} qpde_bs1d_batch;
+
+/* Output buffers (HOST).  Any pointer may be NULL to skip that output. */
+typedef struct {
+	double  *V;           /* [C][N] node values at t = 0                    */
+	int64_t  V_stride;    /* >= N                                           */
+	double  *S;           /* [C][N] the refined grid actually used          */
+	int64_t  S_stride;
+	double  *value;       /* [C] V(spot)                                    */
+	int32_t *n_steps;     /* [C] time steps taken (Iteration::iterations()[0]) */
+	int32_t *inner_total; /* [C] sum over steps of inner iterations         */
+	uint8_t *inner;       /* [C][inner_stride] per-step inner iteration counts
+	                         (ToleranceIteration::iterations(), saturated at 255) */
+	int64_t  inner_stride;/* >= max steps                                   */
+	uint8_t *active;      /* [C][N] final penalty active set, 0/1
+	                         (PenaltyMethod::constraintMask, PenaltyMethod.hpp:127-139) */
+	int64_t  active_stride;
+	int32_t *status;      /* [C] 0 ok, 1 = some step hit max_inner          */
+} qpde_bs1d_result;
+
+/* ---- context ---------------------------------------------------------- */
+int qpde_abi_version(void);
+int qpde_create(int device, qpde_handle **out);
+int qpde_destroy(qpde_handle *h);
+const char *qpde_last_error(const qpde_handle *h); /* h may be NULL: global */
+/* The CUDA stream (cudaStream_t) every launch of this handle goes to, for
+ * callers that time with their own CUDA events. */
+void *qpde_stream(qpde_handle *h);
+int qpde_synchronize(qpde_handle *h);
+/* Number of kernel launches issued by this handle so far. */
+int64_t qpde_launch_count(const qpde_handle *h);
+/* Multiprocessor count of the device (grid sizing / reporting). */
+int qpde_sm_count(const qpde_handle *h);
+
+/* Pinned host memory for callers that want asynchronous, full-rate copies. */
+int qpde_host_alloc(size_t bytes, void **out);
+int qpde_host_free(void *p);
+
+/* ---- host-only helpers (no GPU needed) --------------------------------- */
+/* Replays the reference time loop.  Returns the number of steps (>= 0) and
+ * writes min(n, max_steps) entries; out may be NULL to count. */
+int qpde_make_schedule(double T, double dt, const double *event_times,
+		int n_events, qpde_step *out, int max_steps);
+/* N after refinement. */
+int qpde_refined_size(int n_axis, int refine);
+
+/* ---- the sweep -------------------------------------------------------- */
+/* One-shot: upload (H2D), run, download (D2H).  This is the call the
+ * reference-facing host API makes (quantpde_b200/include/QuantPDE_B200). */
+int qpde_bs1d_sweep(qpde_handle *h, const qpde_bs1d_batch *batch,
+		qpde_bs1d_result *result);
+
+/* Split form, for callers that keep a batch resident in HBM. */
+int qpde_bs1d_plan_create(qpde_handle *h, const qpde_bs1d_batch *batch,
+		qpde_bs1d_plan **out);      /* validates, allocates, uploads      */
+int qpde_bs1d_plan_run(qpde_bs1d_plan *plan);    /* async on qpde_stream() */
+int qpde_bs1d_plan_fetch(qpde_bs1d_plan *plan, qpde_bs1d_result *result); /* syncs */
+int qpde_bs1d_plan_destroy(qpde_bs1d_plan *plan);
+/* Which kernel the plan resolved to (QPDE_KERNEL_*), and N. */
+int qpde_bs1d_plan_kernel(const qpde_bs1d_plan *plan);
+int qpde_bs1d_plan_nodes(const qpde_bs1d_plan *plan);
+/* Row length of the per-step `inner` output (upper bound on steps). */
+int qpde_bs1d_plan_max_steps(const qpde_bs1d_plan *plan);
+
+#ifdef __cplusplus
+}
+#endif
+
+#endif /* QPDE_B200_H */

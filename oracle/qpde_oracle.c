@@ -329,7 +329,7 @@ int qpo_sweep_1d(const qpo_problem *p, double *V, int *inner,
 	for(s = 0; s < p->n_steps; ++s) {
 		const qpo_step *st = &p->steps[s];
 		const double t = st->t;
-		int a_same, its = 0;
+		int a_same, its = 0, notdone = 0;
 		int use_cn = 0, use_bdf2 = 0;
 		double hA = 0.;
 
@@ -450,8 +450,10 @@ int qpo_sweep_1d(const qpo_problem *p, double *V, int *inner,
 				memcpy(x, rhs, sizeof(double) * (size_t)n);
 				tri_solve(&lu, x);
 				++its;
-				if(its >= p->max_inner) { status = 1; break; }
-			} while(relative_error(n, x, xprev, p->scale) > p->tolerance);
+				notdone = relative_error(n, x, xprev, p->scale) > p->tolerance;
+				/* guard only; the reference would keep iterating */
+				if(notdone && its >= p->max_inner) { status = 1; break; }
+			} while(notdone);
 		}
 		initialized = 1;
 		if(inner) inner[s] = its;

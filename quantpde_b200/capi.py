@@ -1,0 +1,324 @@
+"""ctypes view of libqpde_b200.so (include/qpde_b200.h).
+
+This is plumbing for tests/ and bench.py: it declares the C structs, loads the
+in-tree shared library and turns error codes into exceptions.  There is no
+fallback of any kind — if the library is missing or no B200 is present the
+calls raise.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "lib", "libqpde_b200.so")
+
+ABI_VERSION = 1
+
+OK, ERR_INVALID, ERR_CUDA, ERR_NO_DEVICE, ERR_NOT_CONVERGED, ERR_UNSUPPORTED = 0, -1, -2, -3, -4, -5
+
+SCHEME = {"rannacher": 0, "cn": 1, "bdf1": 2, "bdf2": 3}
+PAYOFF = {"array": 0, "put": 1, "call": 2, "digital_put": 3, "digital_call": 4,
+          "straddle": 5, "k_minus_s": 6}
+VOL = {"const": 0, "inverse_s": 1, "nodes": 2}
+KERNEL = {"auto": 0, "interleaved": 1, "resident": 2}
+KERNEL_NAME = {v: k for k, v in KERNEL.items()}
+
+OUT_V, OUT_S, OUT_VALUE, OUT_STEPS, OUT_INNER_TOTAL, OUT_INNER, OUT_ACTIVE, OUT_STATUS = (
+    1, 2, 4, 8, 16, 32, 64, 128)
+OUT_ALL = 255
+
+_dp = C.POINTER(C.c_double)
+
+
+class Step(C.Structure):
+    _fields_ = [("t", C.c_double), ("dt", C.c_double), ("same_dt", C.c_int32),
+                ("event_after", C.c_int32), ("user_events", C.c_int32),
+                ("reserved", C.c_int32)]
+
+
+class Batch(C.Structure):
+    _fields_ = [
+        ("abi_version", C.c_int32), ("n_contracts", C.c_int32),
+        ("axis", _dp), ("axis_stride", C.c_int64), ("n_axis", C.c_int32), ("refine", C.c_int32),
+        ("r", _dp), ("sigma", _dp), ("q", _dp),
+        ("vol_model", C.c_int32), ("reserved0", C.c_int32),
+        ("sigma_nodes", _dp), ("sigma_nodes_stride", C.c_int64),
+        ("T", _dp), ("dt", _dp), ("scheme", C.c_int32), ("max_steps", C.c_int32),
+        ("n_exercise", C.c_int32), ("exercise_kind", C.c_int32),
+        ("strike", _dp), ("payoff_kind", C.c_int32), ("obstacle_kind", C.c_int32),
+        ("payoff", _dp), ("payoff_stride", C.c_int64),
+        ("obstacle", _dp), ("obstacle_stride", C.c_int64),
+        ("american", C.c_int32), ("max_inner", C.c_int32),
+        ("tolerance", C.c_double), ("scale", C.c_double), ("penalty_tolerance", C.c_double),
+        ("spot", _dp),
+        ("kernel", C.c_int32), ("outputs", C.c_int32),
+    ]
+
+
+class Result(C.Structure):
+    _fields_ = [
+        ("V", _dp), ("V_stride", C.c_int64),
+        ("S", _dp), ("S_stride", C.c_int64),
+        ("value", _dp),
+        ("n_steps", C.POINTER(C.c_int32)),
+        ("inner_total", C.POINTER(C.c_int32)),
+        ("inner", C.POINTER(C.c_uint8)), ("inner_stride", C.c_int64),
+        ("active", C.POINTER(C.c_uint8)), ("active_stride", C.c_int64),
+        ("status", C.POINTER(C.c_int32)),
+    ]
+
+
+# every symbol include/qpde_b200.h declares
+EXPORTS = [
+    "qpde_abi_version", "qpde_create", "qpde_destroy", "qpde_last_error", "qpde_stream",
+    "qpde_synchronize", "qpde_launch_count", "qpde_sm_count", "qpde_host_alloc",
+    "qpde_host_free", "qpde_make_schedule", "qpde_refined_size", "qpde_bs1d_sweep",
+    "qpde_bs1d_plan_create", "qpde_bs1d_plan_run", "qpde_bs1d_plan_fetch",
+    "qpde_bs1d_plan_destroy", "qpde_bs1d_plan_kernel", "qpde_bs1d_plan_nodes",
+    "qpde_bs1d_plan_max_steps",
+]
+
+_lib = None
+
+
+class QpdeError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__("libqpde_b200 error %d: %s" % (code, msg))
+        self.code = code
+
+
+def lib():
+    """Loads quantpde_b200/lib/libqpde_b200.so.  Raises if it has not been built
+    (run `python -c 'import __graft_entry__ as g; g.build()'` or make -C quantpde_b200/csrc)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise FileNotFoundError(
+                "%s is missing: build it with __graft_entry__.build(); there is no fallback" % LIB_PATH)
+        L = C.CDLL(LIB_PATH)
+        L.qpde_last_error.restype = C.c_char_p
+        L.qpde_last_error.argtypes = [C.c_void_p]
+        L.qpde_stream.restype = C.c_void_p
+        L.qpde_stream.argtypes = [C.c_void_p]
+        L.qpde_launch_count.restype = C.c_int64
+        L.qpde_launch_count.argtypes = [C.c_void_p]
+        L.qpde_sm_count.argtypes = [C.c_void_p]
+        L.qpde_create.argtypes = [C.c_int, C.POINTER(C.c_void_p)]
+        L.qpde_destroy.argtypes = [C.c_void_p]
+        L.qpde_synchronize.argtypes = [C.c_void_p]
+        L.qpde_host_alloc.argtypes = [C.c_size_t, C.POINTER(C.c_void_p)]
+        L.qpde_host_free.argtypes = [C.c_void_p]
+        L.qpde_make_schedule.argtypes = [C.c_double, C.c_double, _dp, C.c_int,
+                                         C.POINTER(Step), C.c_int]
+        L.qpde_refined_size.argtypes = [C.c_int, C.c_int]
+        L.qpde_bs1d_sweep.argtypes = [C.c_void_p, C.POINTER(Batch), C.POINTER(Result)]
+        L.qpde_bs1d_plan_create.argtypes = [C.c_void_p, C.POINTER(Batch), C.POINTER(C.c_void_p)]
+        L.qpde_bs1d_plan_run.argtypes = [C.c_void_p]
+        L.qpde_bs1d_plan_fetch.argtypes = [C.c_void_p, C.POINTER(Result)]
+        L.qpde_bs1d_plan_destroy.argtypes = [C.c_void_p]
+        L.qpde_bs1d_plan_kernel.argtypes = [C.c_void_p]
+        L.qpde_bs1d_plan_nodes.argtypes = [C.c_void_p]
+        L.qpde_bs1d_plan_max_steps.argtypes = [C.c_void_p]
+        _lib = L
+    return _lib
+
+
+def check(code, handle=None):
+    if code != OK:
+        msg = lib().qpde_last_error(handle)
+        raise QpdeError(code, msg.decode() if msg else "")
+    return code
+
+
+def make_schedule(T, dt, event_times=()):
+    """Host-only replay of the reference time loop (no GPU needed)."""
+    ev = np.ascontiguousarray(event_times, dtype=np.float64)
+    evp = ev.ctypes.data_as(_dp) if len(ev) else None
+    n = lib().qpde_make_schedule(T, dt, evp, len(ev), None, 0)
+    if n < 0:
+        raise QpdeError(n, "qpde_make_schedule")
+    buf = (Step * n)()
+    lib().qpde_make_schedule(T, dt, evp, len(ev), buf, n)
+    return buf
+
+
+def refined_size(n_axis, refine):
+    return lib().qpde_refined_size(n_axis, refine)
+
+
+class Handle:
+    """qpde_create / qpde_destroy."""
+
+    def __init__(self, device=0):
+        self.ptr = C.c_void_p()
+        check(lib().qpde_create(device, C.byref(self.ptr)))
+
+    def close(self):
+        if self.ptr:
+            lib().qpde_destroy(self.ptr)
+            self.ptr = C.c_void_p()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    @property
+    def stream(self):
+        return lib().qpde_stream(self.ptr)
+
+    def synchronize(self):
+        check(lib().qpde_synchronize(self.ptr), self.ptr)
+
+    @property
+    def launches(self):
+        return lib().qpde_launch_count(self.ptr)
+
+    @property
+    def sm_count(self):
+        return lib().qpde_sm_count(self.ptr)
+
+
+def _arr(x, n, dtype=np.float64):
+    a = np.ascontiguousarray(np.broadcast_to(np.asarray(x, dtype=dtype), (n,)))
+    return a
+
+
+class BatchSpec:
+    """Keeps the numpy arrays a qpde_bs1d_batch points into alive."""
+
+    def __init__(self, *, axis, refine, r, sigma, q, T, dt, strike, scheme="rannacher",
+                 american=False, payoff="put", obstacle=None, payoff_array=None,
+                 obstacle_array=None, vol_model="const", sigma_nodes=None,
+                 n_exercise=0, exercise="k_minus_s", spot=None, tolerance=1e-6, scale=1.0,
+                 penalty_tolerance=1e-6, max_inner=100, kernel="auto", outputs=OUT_ALL,
+                 n_contracts=None):
+        axis = np.ascontiguousarray(axis, dtype=np.float64)
+        if n_contracts is None:
+            n_contracts = axis.shape[0] if axis.ndim == 2 else len(np.atleast_1d(strike))
+        Cn = int(n_contracts)
+        self.C = Cn
+        self.keep = []
+        b = Batch()
+        b.abi_version = ABI_VERSION
+        b.n_contracts = Cn
+        self.axis = axis
+        b.axis = axis.ctypes.data_as(_dp)
+        b.axis_stride = axis.shape[1] if axis.ndim == 2 else 0
+        b.n_axis = axis.shape[-1]
+        b.refine = int(refine)
+        self.N = refined_size(b.n_axis, b.refine)
+
+        def vec(x):
+            a = _arr(x, Cn)
+            self.keep.append(a)
+            return a.ctypes.data_as(_dp)
+
+        def rows(x):
+            a = np.ascontiguousarray(x, dtype=np.float64)
+            self.keep.append(a)
+            stride = a.shape[1] if a.ndim == 2 else 0
+            return a.ctypes.data_as(_dp), stride
+
+        b.r, b.sigma, b.q = vec(r), vec(sigma), vec(q)
+        b.vol_model = VOL[vol_model]
+        if sigma_nodes is not None:
+            b.sigma_nodes, b.sigma_nodes_stride = rows(sigma_nodes)
+        b.T, b.dt = vec(T), vec(dt)
+        b.scheme = SCHEME[scheme]
+        b.max_steps = 0
+        b.n_exercise = int(n_exercise)
+        b.exercise_kind = PAYOFF[exercise]
+        b.strike = vec(strike)
+        b.payoff_kind = PAYOFF["array"] if payoff_array is not None else PAYOFF[payoff]
+        if payoff_array is not None:
+            b.payoff, b.payoff_stride = rows(payoff_array)
+        if obstacle is None:
+            obstacle = payoff
+        b.obstacle_kind = PAYOFF["array"] if obstacle_array is not None else PAYOFF[obstacle]
+        if obstacle_array is not None:
+            b.obstacle, b.obstacle_stride = rows(obstacle_array)
+        b.american = int(bool(american))
+        b.max_inner = int(max_inner)
+        b.tolerance, b.scale, b.penalty_tolerance = tolerance, scale, penalty_tolerance
+        if spot is not None:
+            b.spot = vec(spot)
+        b.kernel = KERNEL[kernel]
+        b.outputs = int(outputs)
+        self.struct = b
+
+
+class ResultBuffers:
+    """Host output buffers for qpde_bs1d_result."""
+
+    def __init__(self, C_, N, max_steps, outputs=OUT_ALL):
+        r = Result()
+        self.V = self.S = self.value = self.n_steps = self.inner_total = None
+        self.inner = self.active = self.status = None
+        if outputs & OUT_V:
+            self.V = np.zeros((C_, N)); r.V = self.V.ctypes.data_as(_dp); r.V_stride = N
+        if outputs & OUT_S:
+            self.S = np.zeros((C_, N)); r.S = self.S.ctypes.data_as(_dp); r.S_stride = N
+        if outputs & OUT_VALUE:
+            self.value = np.zeros(C_); r.value = self.value.ctypes.data_as(_dp)
+        if outputs & OUT_STEPS:
+            self.n_steps = np.zeros(C_, dtype=np.int32)
+            r.n_steps = self.n_steps.ctypes.data_as(C.POINTER(C.c_int32))
+        if outputs & OUT_INNER_TOTAL:
+            self.inner_total = np.zeros(C_, dtype=np.int32)
+            r.inner_total = self.inner_total.ctypes.data_as(C.POINTER(C.c_int32))
+        if outputs & OUT_INNER:
+            self.inner = np.zeros((C_, max_steps), dtype=np.uint8)
+            r.inner = self.inner.ctypes.data_as(C.POINTER(C.c_uint8)); r.inner_stride = max_steps
+        if outputs & OUT_ACTIVE:
+            self.active = np.zeros((C_, N), dtype=np.uint8)
+            r.active = self.active.ctypes.data_as(C.POINTER(C.c_uint8)); r.active_stride = N
+        if outputs & OUT_STATUS:
+            self.status = np.zeros(C_, dtype=np.int32)
+            r.status = self.status.ctypes.data_as(C.POINTER(C.c_int32))
+        self.struct = r
+
+
+class Plan:
+    """qpde_bs1d_plan_*: a batch resident in HBM."""
+
+    def __init__(self, handle, spec):
+        self.handle, self.spec = handle, spec
+        self.ptr = C.c_void_p()
+        check(lib().qpde_bs1d_plan_create(handle.ptr, C.byref(spec.struct), C.byref(self.ptr)), handle.ptr)
+        self.N = lib().qpde_bs1d_plan_nodes(self.ptr)
+        self.max_steps = lib().qpde_bs1d_plan_max_steps(self.ptr)
+        self.kernel = KERNEL_NAME[lib().qpde_bs1d_plan_kernel(self.ptr)]
+
+    def run(self):
+        check(lib().qpde_bs1d_plan_run(self.ptr), self.handle.ptr)
+
+    def fetch(self, outputs=None):
+        outputs = self.spec.struct.outputs if outputs is None else outputs
+        res = ResultBuffers(self.spec.C, self.N, self.max_steps, outputs)
+        check(lib().qpde_bs1d_plan_fetch(self.ptr, C.byref(res.struct)), self.handle.ptr)
+        return res
+
+    def close(self):
+        if self.ptr:
+            lib().qpde_bs1d_plan_destroy(self.ptr)
+            self.ptr = C.c_void_p()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+
+def sweep(handle, spec, outputs=OUT_ALL):
+    """qpde_bs1d_sweep: host buffers in, host buffers out."""
+    N = spec.N
+    Tmax = np.max(np.ctypeslib.as_array(spec.struct.T, (spec.C,)) /
+                  np.ctypeslib.as_array(spec.struct.dt, (spec.C,)))
+    max_steps = int(np.floor(Tmax)) + 3 + 2 * spec.struct.n_exercise
+    res = ResultBuffers(spec.C, N, max_steps, outputs)
+    check(lib().qpde_bs1d_sweep(handle.ptr, C.byref(spec.struct), C.byref(res.struct)), handle.ptr)
+    return res

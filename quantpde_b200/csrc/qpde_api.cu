@@ -1,0 +1,480 @@
+// qpde_api.cu — the C ABI of libqpde_b200.so (include/qpde_b200.h): context,
+// device-resident plans, host<->device staging and kernel dispatch.  No torch,
+// no C++ types across the boundary.  There is no CPU fallback: without an
+// sm_100 device qpde_create() fails with QPDE_ERR_NO_DEVICE.
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <algorithm>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "qpde_kernels.cuh"
+
+using namespace qpde;
+
+namespace {
+
+std::mutex g_err_mutex;
+std::string g_last_error;
+
+void set_global_error(const std::string &s) {
+	std::lock_guard<std::mutex> lock(g_err_mutex);
+	g_last_error = s;
+}
+
+} // namespace
+
+struct qpde_handle {
+	int device;
+	int sm_count;
+	cudaStream_t stream;
+	long long launches;
+	std::string error;
+};
+
+struct qpde_bs1d_plan {
+	qpde_handle *h;
+	DeviceBatch b;
+	DeviceResult out;
+	InterleavedWork w;
+	int kernel;
+	int outputs;
+	std::vector<void *> allocations;
+};
+
+namespace {
+
+int fail(qpde_handle *h, int code, const char *fmt, ...) {
+	char buf[512];
+	va_list ap;
+	va_start(ap, fmt);
+	vsnprintf(buf, sizeof(buf), fmt, ap);
+	va_end(ap);
+	if(h) h->error = buf;
+	set_global_error(buf);
+	return code;
+}
+
+#define QPDE_CUDA(h, call) \
+	do { \
+		cudaError_t qpde_err_ = (call); \
+		if(qpde_err_ != cudaSuccess) { \
+			return fail((h), QPDE_ERR_CUDA, "%s failed: %s (%s:%d)", #call, \
+				cudaGetErrorString(qpde_err_), __FILE__, __LINE__); \
+		} \
+	} while(0)
+
+template <typename T>
+int dev_alloc(qpde_bs1d_plan *p, T **out, size_t count) {
+	void *ptr = nullptr;
+	QPDE_CUDA(p->h, cudaMalloc(&ptr, count * sizeof(T) > 0 ? count * sizeof(T) : 8));
+	p->allocations.push_back(ptr);
+	*out = (T *)ptr;
+	return QPDE_OK;
+}
+
+// Uploads a [rows][cols] host array with row stride `stride` (0 = one shared
+// row) into a dense device array; returns the device stride through dstride.
+int upload_rows(qpde_bs1d_plan *p, const double *host, long long stride,
+		int rows, int cols, const double **dev, long long *dstride) {
+	double *d = nullptr;
+	if(stride == 0) {
+		int rc = dev_alloc(p, &d, (size_t)cols);
+		if(rc) return rc;
+		QPDE_CUDA(p->h, cudaMemcpyAsync(d, host, sizeof(double) * cols,
+			cudaMemcpyHostToDevice, p->h->stream));
+		*dstride = 0;
+	} else {
+		int rc = dev_alloc(p, &d, (size_t)rows * cols);
+		if(rc) return rc;
+		QPDE_CUDA(p->h, cudaMemcpy2DAsync(d, sizeof(double) * cols, host,
+			sizeof(double) * stride, sizeof(double) * cols, rows,
+			cudaMemcpyHostToDevice, p->h->stream));
+		*dstride = cols;
+	}
+	*dev = d;
+	return QPDE_OK;
+}
+
+int upload_vec(qpde_bs1d_plan *p, const double *host, int n, const double **dev) {
+	double *d = nullptr;
+	int rc = dev_alloc(p, &d, (size_t)n);
+	if(rc) return rc;
+	QPDE_CUDA(p->h, cudaMemcpyAsync(d, host, sizeof(double) * n,
+		cudaMemcpyHostToDevice, p->h->stream));
+	*dev = d;
+	return QPDE_OK;
+}
+
+bool is_generator(int kind) {
+	return kind >= QPDE_PAYOFF_PUT && kind <= QPDE_PAYOFF_K_MINUS_S;
+}
+
+} // namespace
+
+extern "C" {
+
+int qpde_abi_version(void) { return QPDE_ABI_VERSION; }
+
+const char *qpde_last_error(const qpde_handle *h) {
+	if(h) return h->error.c_str();
+	std::lock_guard<std::mutex> lock(g_err_mutex);
+	static thread_local std::string copy;
+	copy = g_last_error;
+	return copy.c_str();
+}
+
+int qpde_create(int device, qpde_handle **out) {
+	if(!out) return fail(nullptr, QPDE_ERR_INVALID, "qpde_create: out is NULL");
+	*out = nullptr;
+	int count = 0;
+	cudaError_t err = cudaGetDeviceCount(&count);
+	if(err != cudaSuccess || count <= 0) {
+		return fail(nullptr, QPDE_ERR_NO_DEVICE,
+			"qpde_create: no CUDA device (%s); libqpde_b200 has no CPU fallback",
+			err != cudaSuccess ? cudaGetErrorString(err) : "device count is 0");
+	}
+	if(device < 0 || device >= count) {
+		return fail(nullptr, QPDE_ERR_INVALID, "qpde_create: device %d out of range [0, %d)",
+			device, count);
+	}
+	cudaDeviceProp prop;
+	QPDE_CUDA(nullptr, cudaGetDeviceProperties(&prop, device));
+	if(prop.major != 10) {
+		return fail(nullptr, QPDE_ERR_NO_DEVICE,
+			"qpde_create: device %d is sm_%d%d; this library holds sm_100a code only",
+			device, prop.major, prop.minor);
+	}
+	QPDE_CUDA(nullptr, cudaSetDevice(device));
+	qpde_handle *h = new qpde_handle();
+	h->device = device;
+	h->sm_count = prop.multiProcessorCount;
+	h->launches = 0;
+	cudaError_t serr = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
+	if(serr != cudaSuccess) {
+		delete h;
+		return fail(nullptr, QPDE_ERR_CUDA, "cudaStreamCreate failed: %s", cudaGetErrorString(serr));
+	}
+	*out = h;
+	return QPDE_OK;
+}
+
+int qpde_destroy(qpde_handle *h) {
+	if(!h) return QPDE_OK;
+	cudaSetDevice(h->device);
+	cudaStreamSynchronize(h->stream);
+	cudaStreamDestroy(h->stream);
+	delete h;
+	return QPDE_OK;
+}
+
+void *qpde_stream(qpde_handle *h) { return h ? (void *)h->stream : nullptr; }
+
+int qpde_synchronize(qpde_handle *h) {
+	if(!h) return fail(nullptr, QPDE_ERR_INVALID, "qpde_synchronize: NULL handle");
+	QPDE_CUDA(h, cudaSetDevice(h->device));
+	QPDE_CUDA(h, cudaStreamSynchronize(h->stream));
+	return QPDE_OK;
+}
+
+int64_t qpde_launch_count(const qpde_handle *h) { return h ? h->launches : 0; }
+int qpde_sm_count(const qpde_handle *h) { return h ? h->sm_count : 0; }
+
+int qpde_host_alloc(size_t bytes, void **out) {
+	if(!out) return fail(nullptr, QPDE_ERR_INVALID, "qpde_host_alloc: out is NULL");
+	QPDE_CUDA(nullptr, cudaHostAlloc(out, bytes, cudaHostAllocDefault));
+	return QPDE_OK;
+}
+
+int qpde_host_free(void *p) {
+	if(p) QPDE_CUDA(nullptr, cudaFreeHost(p));
+	return QPDE_OK;
+}
+
+// ---- host-only helpers -----------------------------------------------------
+
+int qpde_make_schedule(double T, double dt, const double *event_times,
+		int n_events, qpde_step *out, int max_steps) {
+	// General (non-uniform) event times: same loop as qpde::Replay with an
+	// explicit, descending event list.
+	if(!(T > 0.) || !(dt > 0.) || n_events < 0) return QPDE_ERR_INVALID;
+	std::vector<double> ev(event_times, event_times + n_events);
+	std::sort(ev.begin(), ev.end(), [] (double a, double b) { return a > b; });
+	int n = 0;
+	size_t e = 0;
+	double t = T, step = -1., prev;
+	do {
+		const double nextEventTime = e < ev.size() ? ev[e] : 0.;
+		do {
+			prev = step;
+			step = dt;
+			double tmp = t + -1. * step;
+			if(fabs(tmp - nextEventTime) < DBL_EPSILON) {
+				tmp = nextEventTime;
+			} else if(tmp < nextEventTime) {
+				tmp = nextEventTime;
+				step = -1. * (nextEventTime - t);
+			}
+			t = tmp;
+			if(out && n < max_steps) {
+				out[n].t = t; out[n].dt = step; out[n].same_dt = step == prev;
+				out[n].event_after = 0; out[n].user_events = 0; out[n].reserved = 0;
+			}
+			++n;
+		} while(nextEventTime < t + -1. * DBL_EPSILON);
+		t = nextEventTime;
+		int users = 0;
+		while(e < ev.size() && ev[e] == t) { ++e; ++users; }
+		if(out && n - 1 < max_steps) { out[n - 1].event_after = 1; out[n - 1].user_events = users; }
+	} while(0. < t);
+	return n;
+}
+
+int qpde_refined_size(int n_axis, int refine) {
+	if(n_axis < 1 || refine < 0 || refine > 20) return QPDE_ERR_INVALID;
+	if(n_axis < 2) return n_axis;
+	return (1 << refine) * (n_axis - 1) + 1;
+}
+
+// ---- plans -----------------------------------------------------------------
+
+int qpde_bs1d_plan_destroy(qpde_bs1d_plan *p) {
+	if(!p) return QPDE_OK;
+	cudaSetDevice(p->h->device);
+	cudaStreamSynchronize(p->h->stream);
+	for(void *ptr : p->allocations) cudaFree(ptr);
+	delete p;
+	return QPDE_OK;
+}
+
+int qpde_bs1d_plan_kernel(const qpde_bs1d_plan *p) { return p ? p->kernel : QPDE_ERR_INVALID; }
+int qpde_bs1d_plan_nodes(const qpde_bs1d_plan *p) { return p ? p->b.N : QPDE_ERR_INVALID; }
+
+static int plan_create_impl(qpde_handle *h, const qpde_bs1d_batch *in,
+		int outputs, qpde_bs1d_plan **out) {
+	if(!h) return fail(nullptr, QPDE_ERR_INVALID, "plan_create: NULL handle");
+	if(!in || !out) return fail(h, QPDE_ERR_INVALID, "plan_create: NULL argument");
+	*out = nullptr;
+	if(in->abi_version != QPDE_ABI_VERSION) {
+		return fail(h, QPDE_ERR_INVALID, "batch.abi_version %d != %d", in->abi_version, QPDE_ABI_VERSION);
+	}
+	const int C = in->n_contracts;
+	if(C < 1) return fail(h, QPDE_ERR_INVALID, "n_contracts must be >= 1");
+	if(!in->axis || in->n_axis < 3) return fail(h, QPDE_ERR_INVALID, "axis must hold >= 3 ticks");
+	if(in->refine < 0 || in->refine > 16) return fail(h, QPDE_ERR_INVALID, "refine out of range");
+	if(in->axis_stride != 0 && in->axis_stride < in->n_axis) return fail(h, QPDE_ERR_INVALID, "axis_stride < n_axis");
+	if(!in->r || !in->sigma || !in->q || !in->T || !in->dt) {
+		return fail(h, QPDE_ERR_INVALID, "r, sigma, q, T and dt are required");
+	}
+	if(in->scheme < QPDE_SCHEME_RANNACHER || in->scheme > QPDE_SCHEME_BDF2) return fail(h, QPDE_ERR_INVALID, "unknown scheme");
+	if(in->vol_model < QPDE_VOL_CONST || in->vol_model > QPDE_VOL_NODES) return fail(h, QPDE_ERR_INVALID, "unknown vol_model");
+	if(in->vol_model == QPDE_VOL_NODES && !in->sigma_nodes) return fail(h, QPDE_ERR_INVALID, "sigma_nodes required");
+	if(in->payoff_kind == QPDE_PAYOFF_ARRAY ? !in->payoff : !is_generator(in->payoff_kind)) {
+		return fail(h, QPDE_ERR_INVALID, "payoff: array missing or unknown generator");
+	}
+	const bool need_strike = is_generator(in->payoff_kind)
+		|| (in->american && is_generator(in->obstacle_kind))
+		|| in->n_exercise > 0 || !in->spot;
+	if(need_strike && !in->strike) return fail(h, QPDE_ERR_INVALID, "strike required");
+	if(in->american) {
+		if(in->obstacle_kind == QPDE_PAYOFF_ARRAY ? !in->obstacle : !is_generator(in->obstacle_kind)) {
+			return fail(h, QPDE_ERR_INVALID, "obstacle: array missing or unknown generator");
+		}
+		if(!(in->tolerance > 0.) || !(in->scale > 0.) || !(in->penalty_tolerance > 0.)) {
+			return fail(h, QPDE_ERR_INVALID, "tolerance, scale and penalty_tolerance must be > 0");
+		}
+		if(in->max_inner < 1) return fail(h, QPDE_ERR_INVALID, "max_inner must be >= 1");
+	}
+	if(in->n_exercise < 0) return fail(h, QPDE_ERR_INVALID, "n_exercise < 0");
+	if(in->n_exercise > 0 && !is_generator(in->exercise_kind)) return fail(h, QPDE_ERR_INVALID, "exercise_kind must be a generator");
+	for(int c = 0; c < C; ++c) {
+		if(!(in->T[c] > 0.) || !(in->dt[c] > DBL_EPSILON) || in->dt[c] > in->T[c]) {
+			return fail(h, QPDE_ERR_INVALID, "contract %d: need 0 < dt <= T", c);
+		}
+	}
+
+	QPDE_CUDA(h, cudaSetDevice(h->device));
+	qpde_bs1d_plan *p = new qpde_bs1d_plan();
+	p->h = h;
+	p->outputs = outputs;
+	memset(&p->b, 0, sizeof(p->b));
+	memset(&p->out, 0, sizeof(p->out));
+	memset(&p->w, 0, sizeof(p->w));
+	DeviceBatch &b = p->b;
+	b.C = C;
+	b.n_axis = in->n_axis; b.refine = in->refine;
+	b.N = qpde_refined_size(in->n_axis, in->refine);
+	const int N = b.N;
+	b.vol_model = in->vol_model;
+	b.scheme = in->scheme;
+	b.n_exercise = in->n_exercise; b.exercise_kind = in->exercise_kind;
+	b.payoff_kind = in->payoff_kind;
+	b.obstacle_kind = in->american ? in->obstacle_kind : 0;
+	b.american = in->american ? 1 : 0;
+	b.max_inner = in->max_inner;
+	b.tolerance = in->tolerance; b.scale = in->scale; b.penalty_tolerance = in->penalty_tolerance;
+
+	int max_steps = in->max_steps;
+	if(max_steps <= 0) {
+		for(int c = 0; c < C; ++c) {
+			const int bound = replay_step_bound(in->T[c], in->dt[c], in->n_exercise);
+			if(bound > max_steps) max_steps = bound;
+		}
+	}
+	b.max_steps = max_steps;
+
+	int rc = QPDE_OK;
+#define QPDE_TRY(expr) do { rc = (expr); if(rc != QPDE_OK) { qpde_bs1d_plan_destroy(p); return rc; } } while(0)
+	QPDE_TRY(upload_rows(p, in->axis, in->axis_stride, C, in->n_axis, &b.axis, &b.axis_stride));
+	QPDE_TRY(upload_vec(p, in->r, C, &b.r));
+	QPDE_TRY(upload_vec(p, in->sigma, C, &b.sigma));
+	QPDE_TRY(upload_vec(p, in->q, C, &b.q));
+	QPDE_TRY(upload_vec(p, in->T, C, &b.T));
+	QPDE_TRY(upload_vec(p, in->dt, C, &b.dt));
+	if(in->strike) QPDE_TRY(upload_vec(p, in->strike, C, &b.strike));
+	else           QPDE_TRY(upload_vec(p, in->spot, C, &b.strike));
+	if(in->spot) QPDE_TRY(upload_vec(p, in->spot, C, &b.spot));
+	if(in->vol_model == QPDE_VOL_NODES) {
+		QPDE_TRY(upload_rows(p, in->sigma_nodes, in->sigma_nodes_stride ? in->sigma_nodes_stride : 0,
+			C, N, &b.sigma_nodes, &b.sigma_nodes_stride));
+	}
+	if(in->payoff_kind == QPDE_PAYOFF_ARRAY) {
+		QPDE_TRY(upload_rows(p, in->payoff, in->payoff_stride, C, N, &b.payoff, &b.payoff_stride));
+	}
+	if(in->american && in->obstacle_kind == QPDE_PAYOFF_ARRAY) {
+		QPDE_TRY(upload_rows(p, in->obstacle, in->obstacle_stride, C, N, &b.obstacle, &b.obstacle_stride));
+	}
+
+	// outputs
+	DeviceResult &o = p->out;
+	if(outputs & QPDE_OUT_V)      { QPDE_TRY(dev_alloc(p, &o.V, (size_t)C * N)); o.V_stride = N; }
+	if(outputs & QPDE_OUT_S)      { QPDE_TRY(dev_alloc(p, &o.S, (size_t)C * N)); o.S_stride = N; }
+	if(outputs & QPDE_OUT_VALUE)  QPDE_TRY(dev_alloc(p, &o.value, (size_t)C));
+	if(outputs & QPDE_OUT_STEPS)  QPDE_TRY(dev_alloc(p, &o.n_steps, (size_t)C));
+	if(outputs & QPDE_OUT_INNER_TOTAL) QPDE_TRY(dev_alloc(p, &o.inner_total, (size_t)C));
+	if(outputs & QPDE_OUT_INNER)  { QPDE_TRY(dev_alloc(p, &o.inner, (size_t)C * max_steps)); o.inner_stride = max_steps; }
+	if(outputs & QPDE_OUT_ACTIVE) { QPDE_TRY(dev_alloc(p, &o.active, (size_t)C * N)); o.active_stride = N; }
+	if(outputs & QPDE_OUT_STATUS) QPDE_TRY(dev_alloc(p, &o.status, (size_t)C));
+	if(o.inner) QPDE_CUDA(h, cudaMemsetAsync(o.inner, 0, (size_t)C * max_steps, h->stream));
+
+	// kernel choice
+	int kernel = in->kernel;
+	if(kernel == QPDE_KERNEL_AUTO) {
+		kernel = resident_supported(b) ? QPDE_KERNEL_RESIDENT : QPDE_KERNEL_INTERLEAVED;
+	}
+	if(kernel == QPDE_KERNEL_RESIDENT && !resident_supported(b)) {
+		qpde_bs1d_plan_destroy(p);
+		return fail(h, QPDE_ERR_UNSUPPORTED, "the RESIDENT kernel does not support N = %d with this configuration", N);
+	}
+	if(kernel != QPDE_KERNEL_RESIDENT && kernel != QPDE_KERNEL_INTERLEAVED) {
+		qpde_bs1d_plan_destroy(p);
+		return fail(h, QPDE_ERR_INVALID, "unknown kernel %d", kernel);
+	}
+	p->kernel = kernel;
+
+	if(kernel == QPDE_KERNEL_INTERLEAVED) {
+		const size_t NC = (size_t)N * C;
+		InterleavedWork &w = p->w;
+		QPDE_TRY(dev_alloc(p, &w.S, NC));  QPDE_TRY(dev_alloc(p, &w.lo, NC));
+		QPDE_TRY(dev_alloc(p, &w.di, NC)); QPDE_TRY(dev_alloc(p, &w.up, NC));
+		QPDE_TRY(dev_alloc(p, &w.x, NC));  QPDE_TRY(dev_alloc(p, &w.lb, NC));
+		QPDE_TRY(dev_alloc(p, &w.cp, NC)); QPDE_TRY(dev_alloc(p, &w.dp, NC));
+		if(b.scheme == QPDE_SCHEME_BDF2) QPDE_TRY(dev_alloc(p, &w.xprev, NC));
+		else w.xprev = w.x;
+		if(b.american) QPDE_TRY(dev_alloc(p, &w.obst, NC));
+		if(b.n_exercise > 0) QPDE_TRY(dev_alloc(p, &w.evobst, NC));
+	}
+#undef QPDE_TRY
+	*out = p;
+	return QPDE_OK;
+}
+
+int qpde_bs1d_plan_create(qpde_handle *h, const qpde_bs1d_batch *batch, qpde_bs1d_plan **out) {
+	const int outputs = batch && batch->outputs ? batch->outputs : QPDE_OUT_ALL;
+	return plan_create_impl(h, batch, outputs, out);
+}
+
+int qpde_bs1d_plan_run(qpde_bs1d_plan *p) {
+	if(!p) return fail(nullptr, QPDE_ERR_INVALID, "plan_run: NULL plan");
+	qpde_handle *h = p->h;
+	QPDE_CUDA(h, cudaSetDevice(h->device));
+	if(p->kernel == QPDE_KERNEL_INTERLEAVED) {
+		launch_interleaved(p->b, p->w, p->out, h->stream, &h->launches);
+	} else {
+		int rc = launch_resident(p->b, p->out, h->stream, h->sm_count, &h->launches);
+		if(rc != QPDE_OK) return fail(h, rc, "launch_resident failed");
+	}
+	QPDE_CUDA(h, cudaGetLastError());
+	return QPDE_OK;
+}
+
+int qpde_bs1d_plan_fetch(qpde_bs1d_plan *p, qpde_bs1d_result *r) {
+	if(!p || !r) return fail(nullptr, QPDE_ERR_INVALID, "plan_fetch: NULL argument");
+	qpde_handle *h = p->h;
+	const int C = p->b.C, N = p->b.N;
+	const DeviceResult &o = p->out;
+	QPDE_CUDA(h, cudaSetDevice(h->device));
+#define QPDE_NEED(hostptr, devptr, name) \
+	if((hostptr) && !(devptr)) return fail(h, QPDE_ERR_INVALID, "output '%s' was not enabled in batch.outputs", name)
+	QPDE_NEED(r->V, o.V, "V"); QPDE_NEED(r->S, o.S, "S"); QPDE_NEED(r->value, o.value, "value");
+	QPDE_NEED(r->n_steps, o.n_steps, "n_steps"); QPDE_NEED(r->inner_total, o.inner_total, "inner_total");
+	QPDE_NEED(r->inner, o.inner, "inner"); QPDE_NEED(r->active, o.active, "active");
+	QPDE_NEED(r->status, o.status, "status");
+#undef QPDE_NEED
+	if(r->V) {
+		const long long hs = r->V_stride ? r->V_stride : N;
+		if(hs < N) return fail(h, QPDE_ERR_INVALID, "V_stride < N");
+		QPDE_CUDA(h, cudaMemcpy2DAsync(r->V, sizeof(double) * hs, o.V, sizeof(double) * o.V_stride,
+			sizeof(double) * N, C, cudaMemcpyDeviceToHost, h->stream));
+	}
+	if(r->S) {
+		const long long hs = r->S_stride ? r->S_stride : N;
+		if(hs < N) return fail(h, QPDE_ERR_INVALID, "S_stride < N");
+		QPDE_CUDA(h, cudaMemcpy2DAsync(r->S, sizeof(double) * hs, o.S, sizeof(double) * o.S_stride,
+			sizeof(double) * N, C, cudaMemcpyDeviceToHost, h->stream));
+	}
+	if(r->value) QPDE_CUDA(h, cudaMemcpyAsync(r->value, o.value, sizeof(double) * C, cudaMemcpyDeviceToHost, h->stream));
+	if(r->n_steps) QPDE_CUDA(h, cudaMemcpyAsync(r->n_steps, o.n_steps, sizeof(int) * C, cudaMemcpyDeviceToHost, h->stream));
+	if(r->inner_total) QPDE_CUDA(h, cudaMemcpyAsync(r->inner_total, o.inner_total, sizeof(int) * C, cudaMemcpyDeviceToHost, h->stream));
+	if(r->inner) {
+		const long long hs = r->inner_stride ? r->inner_stride : p->b.max_steps;
+		const long long width = hs < o.inner_stride ? hs : o.inner_stride;
+		QPDE_CUDA(h, cudaMemcpy2DAsync(r->inner, (size_t)hs, o.inner, (size_t)o.inner_stride,
+			(size_t)width, C, cudaMemcpyDeviceToHost, h->stream));
+	}
+	if(r->active) {
+		const long long hs = r->active_stride ? r->active_stride : N;
+		if(hs < N) return fail(h, QPDE_ERR_INVALID, "active_stride < N");
+		QPDE_CUDA(h, cudaMemcpy2DAsync(r->active, (size_t)hs, o.active, (size_t)o.active_stride,
+			(size_t)N, C, cudaMemcpyDeviceToHost, h->stream));
+	}
+	if(r->status) QPDE_CUDA(h, cudaMemcpyAsync(r->status, o.status, sizeof(int) * C, cudaMemcpyDeviceToHost, h->stream));
+	QPDE_CUDA(h, cudaStreamSynchronize(h->stream));
+	return QPDE_OK;
+}
+
+int qpde_bs1d_plan_max_steps(const qpde_bs1d_plan *p) { return p ? p->b.max_steps : QPDE_ERR_INVALID; }
+
+int qpde_bs1d_sweep(qpde_handle *h, const qpde_bs1d_batch *batch, qpde_bs1d_result *r) {
+	if(!r) return fail(h, QPDE_ERR_INVALID, "qpde_bs1d_sweep: NULL result");
+	int outputs = 0;
+	if(r->V) outputs |= QPDE_OUT_V;
+	if(r->S) outputs |= QPDE_OUT_S;
+	if(r->value) outputs |= QPDE_OUT_VALUE;
+	if(r->n_steps) outputs |= QPDE_OUT_STEPS;
+	if(r->inner_total) outputs |= QPDE_OUT_INNER_TOTAL;
+	if(r->inner) outputs |= QPDE_OUT_INNER;
+	if(r->active) outputs |= QPDE_OUT_ACTIVE;
+	if(r->status) outputs |= QPDE_OUT_STATUS;
+	qpde_bs1d_plan *p = nullptr;
+	int rc = plan_create_impl(h, batch, outputs, &p);
+	if(rc != QPDE_OK) return rc;
+	rc = qpde_bs1d_plan_run(p);
+	if(rc == QPDE_OK) rc = qpde_bs1d_plan_fetch(p, r);
+	qpde_bs1d_plan_destroy(p);
+	return rc;
+}
+
+} // extern "C"

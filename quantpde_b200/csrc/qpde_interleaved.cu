@@ -1,0 +1,241 @@
+// qpde_interleaved.cu — kernel family "INTERLEAVED": one thread per contract,
+// every per-node array stored node-major / contract-minor ([N][C]) in HBM so
+// that the 32 lanes of a warp touch 32 consecutive doubles at every node.
+// The whole sweep (all time steps, all penalty iterations) is one launch;
+// nothing returns to the host in between.
+//
+// Replaces, per contract, the reference call stack of SURVEY.md §3.1/§3.2:
+//   TimeIteration<false>::iterateUntilDone     Core/IterativeMethod.hpp:1163-1204,1259-1317
+//   ToleranceIteration + relativeError         Core/IterativeMethod.hpp:1125-1137,1211-1254
+//   PenaltyMethodDifference::onIterationStart  Core/PenaltyMethod.hpp:37-69,96-119
+//   Rannacher / CrankNicolson / BDFOne / BDFTwo A(), b()
+//   SparseLUSolver::initialize/solve           Bindings/Eigen.hpp:143-165
+//     -> Thomas elimination (no pivoting: every system here is a strictly
+//        diagonally dominant M-matrix)
+//
+// Algorithmic HBM bytes per inner solve and node: reads lo, di,
+// up, lb, obstacle, x_old (48 B) + writes cp, dp (16 B) in the forward pass;
+// reads cp, dp, x_old (24 B) + writes x_new (8 B) in the backward pass.
+#include "qpde_kernels.cuh"
+
+namespace qpde {
+
+// ---------------------------------------------------------------------------
+// Setup: refined grid, operator rows, initial condition, obstacles.
+// One thread per contract walks its nodes; lanes stay coalesced on [N][C].
+// ---------------------------------------------------------------------------
+__global__ void k_interleaved_setup(DeviceBatch b, InterleavedWork w) {
+	const int c = blockIdx.x * blockDim.x + threadIdx.x;
+	if(c >= b.C) return;
+	const int N = b.N;
+	const size_t C = (size_t)b.C;
+	const double *axis = b.axis + (size_t)c * b.axis_stride;
+	const double K = b.strike[c];
+	const double r = b.r[c], q = b.q[c], sig = b.sigma[c];
+
+	double Sm = 0., Si = refined_node(axis, b.refine, 0);
+	double Sp = N > 1 ? refined_node(axis, b.refine, 1) : Si;
+	for(int i = 0; i < N; ++i) {
+		const size_t at = (size_t)i * C + c;
+		const double v_i = b.vol_model == QPDE_VOL_NODES
+			? b.sigma_nodes[(size_t)c * b.sigma_nodes_stride + i]
+			: vol_value(b.vol_model, sig, Si);
+		const Row row = bs_row(i, N, Sm, Si, Sp, r, v_i, q);
+		w.S[at] = Si;
+		w.lo[at] = row.lo; w.di[at] = row.di; w.up[at] = row.up;
+		w.x[at] = b.payoff_kind == QPDE_PAYOFF_ARRAY
+			? b.payoff[(size_t)c * b.payoff_stride + i]
+			: payoff_value(b.payoff_kind, Si, K);
+		if(w.obst) {
+			w.obst[at] = b.obstacle_kind == QPDE_PAYOFF_ARRAY
+				? b.obstacle[(size_t)c * b.obstacle_stride + i]
+				: payoff_value(b.obstacle_kind, Si, K);
+		}
+		if(w.evobst) w.evobst[at] = payoff_value(b.exercise_kind, Si, K);
+		Sm = Si; Si = Sp;
+		Sp = i + 2 < N ? refined_node(axis, b.refine, i + 2) : Sp;
+	}
+}
+
+// ---------------------------------------------------------------------------
+// The sweep.
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(128)
+k_interleaved_sweep(DeviceBatch b, InterleavedWork w, DeviceResult out) {
+	const int c = blockIdx.x * blockDim.x + threadIdx.x;
+	if(c >= b.C) return;
+	const int N = b.N;
+	const size_t C = (size_t)b.C;
+	const double tol = b.tolerance, scale = b.scale;
+	const double pen = 1. / b.penalty_tolerance; // PenaltyMethod.hpp:85
+	const double *lo = w.lo + c, *di = w.di + c, *up = w.up + c;
+	double *x = w.x + c, *xp = w.xprev + c, *lb = w.lb + c;
+	double *cp = w.cp + c, *dp = w.dp + c;
+	const double *ob = w.obst ? w.obst + c : nullptr;
+	const double *evob = w.evobst ? w.evobst + c : nullptr;
+
+	Replay rp; rp.start(b.T[c], b.dt[c], b.n_exercise);
+	NodeState ns; ns.start(b.scheme);
+	double time1 = rp.T, time0 = rp.T; // times of iterand(0), iterand(1)
+	Gamma gA; gA.kind = STEP_IMPLICIT; gA.h = 0.; // what the factorised A was built with
+	int n_steps = 0, inner_total = 0, status = 0;
+	bool more = true;
+
+	while(more) {
+		qpde_step st;
+		more = rp.next(st);
+		const double t = st.t;
+		const int kind = ns.kind();
+		const double h0 = time1 - t;
+		Gamma gb; gb.kind = kind; gb.h = h0;
+		double c1 = 0., c0 = 0., den = 1.;
+		if(kind == STEP_BDF2) {
+			const double h1 = time1 - t, hh0 = time0 - t;     // BDF.hpp:68-73
+			gb.h = (hh0 * h1) / (hh0 + h1);
+			c1 = hh0 / h1; c0 = h1 / hh0; den = hh0 - h1;
+		}
+		// IterativeMethod.hpp:906: re-assemble A unless the root says it is the same
+		if(b.american || !ns.initialized || !ns.a_same(st.same_dt)) gA = gb;
+
+		// ---- lb = root.b(t) of the discretisation node ------------------
+		// x holds iterand(0) = V^n, xp holds iterand(1) for BDF2.
+		{
+			double vm = 0., vi = x[0], vp = N > 1 ? x[C] : 0.;
+			for(int i = 0; i < N; ++i) {
+				const size_t at = (size_t)i * C;
+				double val;
+				if(kind == STEP_IMPLICIT) {
+					val = vi + 0. * h0;
+				} else if(kind == STEP_BDF2) {
+					val = ((c1 * vi - c0 * xp[at]) / den + 0.) * gb.h;
+				} else {
+					// (I - A h/2) v0, row-major SpMV from zero in column order
+					double acc = 0.;
+					if(i > 0) acc += (0. - gb.off(lo[at])) * vm;
+					acc += (1. - gb.off(di[at])) * vi;
+					if(i < N - 1) acc += (0. - gb.off(up[at])) * vp;
+					val = acc + 0.;
+				}
+				lb[at] = val;
+				vm = vi; vi = vp;
+				vp = i + 2 < N ? x[at + 2 * C] : 0.;
+			}
+		}
+		// history push: iterand(1) <- iterand(0).  For BDF2 the previous
+		// iterand must survive the solve, so copy it before x is overwritten.
+		if(b.scheme == QPDE_SCHEME_BDF2) {
+			for(int i = 0; i < N; ++i) xp[(size_t)i * C] = x[(size_t)i * C];
+		}
+
+		int its = 0;
+		bool again;
+		do {
+			// ---- forward elimination of (lA + P) x = lb + P obstacle ------
+			double cprev = 0., dprev = 0.;
+			for(int i = 0; i < N; ++i) {
+				const size_t at = (size_t)i * C;
+				double a_i = gA.off(lo[at]);
+				double b_i = 1. + gA.off(di[at]);
+				double c_i = gA.off(up[at]);
+				double rhs = lb[at];
+				if(b.american) {
+					// PenaltyMethod.hpp:45,61-68: predicate on the previous iterand
+					const double pred = (0. + 1. * x[at]) - ob[at];
+					if((pen * pred) < 0.) { b_i = b_i + pen * 1.; rhs = rhs + pen * ob[at]; }
+				}
+				const double denom = b_i - a_i * cprev;
+				const double inv = 1. / denom;
+				cprev = c_i * inv;
+				dprev = (rhs - a_i * dprev) * inv;
+				cp[at] = cprev; dp[at] = dprev;
+			}
+			// ---- back substitution + relativeError --------------------------
+			double xn = 0.;
+			bool notdone = false;
+			for(int i = N - 1; i >= 0; --i) {
+				const size_t at = (size_t)i * C;
+				xn = dp[at] - cp[at] * xn;
+				if(b.american) {
+					const double xo = x[at];
+					const double fa = fabs(xn), fb = fabs(xo);
+					double d = fa < fb ? fb : fa;
+					d = scale < d ? d : scale;
+					if(fabs(xn - xo) / d > tol) notdone = true;  // IterativeMethod.hpp:1131-1135
+				}
+				x[at] = xn;
+			}
+			++its;
+			again = b.american && notdone;
+			if(again && its >= b.max_inner) { status = 1; again = false; }
+		} while(again);
+
+		if(out.inner) {
+			out.inner[(size_t)c * out.inner_stride + n_steps] = (uint8_t)(its > 255 ? 255 : its);
+		}
+		inner_total += its;
+		++n_steps;
+		time0 = time1; time1 = t;
+		ns.end_step();
+
+		if(st.event_after) {
+			if(st.user_events > 0 && evob) {
+				for(int i = 0; i < N; ++i) {
+					const size_t at = (size_t)i * C;
+					const double ex = evob[at], v = x[at];
+					x[at] = v > ex ? v : ex;       // QuantPDE::max, EarlyInclude.hpp:48
+				}
+			}
+			ns.after_event();
+		}
+	}
+
+	// ---- outputs (contract-major) ------------------------------------------
+	if(out.V) for(int i = 0; i < N; ++i) out.V[(size_t)c * out.V_stride + i] = x[(size_t)i * C];
+	if(out.S) for(int i = 0; i < N; ++i) out.S[(size_t)c * out.S_stride + i] = w.S[(size_t)i * C + c];
+	if(out.active) {
+		for(int i = 0; i < N; ++i) {
+			const double pred = ob ? (0. + 1. * x[(size_t)i * C]) - ob[(size_t)i * C] : 0.;
+			out.active[(size_t)c * out.active_stride + i] = pred < 0. ? 1 : 0;
+		}
+	}
+	if(out.value) {
+		// PiecewiseLinear::interpolate (Core/Interpolant.hpp:153-181,331-374)
+		const double *S = w.S + c;
+		const double s0 = b.spot ? b.spot[c] : b.strike[c];
+		int idx; double wgt;
+		if(s0 <= S[0]) { idx = 0; wgt = 1.; }
+		else if(s0 >= S[(size_t)(N - 1) * C]) { idx = N - 2; wgt = 0.; }
+		else {
+			int l = 0, hgh = N - 2, mid = 0; wgt = 0.;
+			while(l <= hgh) {
+				mid = (l + hgh) / 2;
+				if(s0 < S[(size_t)mid * C]) hgh = mid - 1;
+				else if(s0 >= S[(size_t)(mid + 1) * C]) l = mid + 1;
+				else {
+					wgt = (S[(size_t)(mid + 1) * C] - s0)
+						/ (S[(size_t)(mid + 1) * C] - S[(size_t)mid * C]);
+					break;
+				}
+			}
+			idx = mid;
+		}
+		double sum = 0.;
+		if(wgt > DBL_EPSILON) sum += wgt * x[(size_t)idx * C];
+		if(1. - wgt > DBL_EPSILON) sum += (1. - wgt) * x[(size_t)(idx + 1) * C];
+		out.value[c] = sum;
+	}
+	if(out.n_steps) out.n_steps[c] = n_steps;
+	if(out.inner_total) out.inner_total[c] = inner_total;
+	if(out.status) out.status[c] = status;
+}
+
+void launch_interleaved(const DeviceBatch &b, const InterleavedWork &w,
+		const DeviceResult &out, cudaStream_t stream, long long *launches) {
+	const int threads = 128;
+	const int blocks = (b.C + threads - 1) / threads;
+	k_interleaved_setup<<<blocks, threads, 0, stream>>>(b, w);
+	k_interleaved_sweep<<<blocks, threads, 0, stream>>>(b, w, out);
+	*launches += 2;
+}
+
+} // namespace qpde

@@ -1,0 +1,56 @@
+"""Generates tests/golden/reference_cases.npz by running oracle/_ref/qpde_ref —
+the UNMODIFIED reference headers under /root/reference compiled against
+oracle/shim (see oracle/Makefile).  Run in the build container only (the GPU
+box has no /root/reference and uses the committed .npz):
+
+    make -C oracle && python tests/golden/make_golden.py
+"""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+from oracle import pyoracle as po  # noqa: E402
+
+CASES = []
+# config 1: examples/vanilla_options.cpp American put convergence table, k = 0..3
+for k in range(4):
+    CASES.append(("american_table_k%d" % k, "vanilla",
+                  dict(american=1, steps=12 * 4 ** k, refine=k, K=100.0, r=0.04, vol=0.2, T=1.0)))
+# config 2 style: varied strike / vol / T / r (seeded), 100 steps, 257 nodes
+rng = np.random.default_rng(1234)
+for j in range(4):
+    K = float(rng.uniform(50, 150)); vol = float(rng.uniform(.1, .6))
+    T = float(rng.uniform(.25, 2.)); r = float(rng.uniform(.01, .08))
+    CASES.append(("american_varied_%d" % j, "vanilla",
+                  dict(american=1, steps=100, refine=3, K=K, r=r, vol=vol, T=T)))
+# American call with dividends (early exercise matters)
+CASES.append(("american_call_div", "vanilla",
+              dict(american=1, call=1, steps=64, refine=2, K=100.0, r=0.03, vol=0.3, T=1.5, q=0.06)))
+# European, every scheme
+for sch in ("rannacher", "cn", "bdf1", "bdf2"):
+    CASES.append(("european_%s" % sch, "vanilla",
+                  dict(american=0, steps=100, refine=2, K=100.0, r=0.04, vol=0.2, T=1.0, scheme=sch)))
+# config 3: examples/tutorial.cpp Bermudan put, local volatility, 10 exercise dates
+for sch in ("bdf2", "rannacher", "bdf1", "cn"):
+    for k in (0, 1):
+        CASES.append(("bermudan_%s_k%d" % (sch, k), "bermudan",
+                      dict(steps=100 * 2 ** k, refine=k, scheme=sch, K=100.0, r=0.04, alpha=20.0, T=1.0, E=10)))
+
+out = {}
+names = []
+for name, mode, kw in CASES:
+    ref = po.run_ref(mode, **kw)
+    names.append(name)
+    out[name + "/mode"] = np.array(mode)
+    out[name + "/args"] = np.array(repr(kw))
+    for key in ("S", "V", "inner", "mask"):
+        if key in ref:
+            out[name + "/" + key] = ref[key]
+    out[name + "/steps"] = np.array(ref["steps"])
+    out[name + "/value"] = np.array(ref["value"])
+    print(name, ref["steps"], ref["value"])
+out["names"] = np.array(names)
+np.savez_compressed(os.path.join(os.path.dirname(os.path.abspath(__file__)), "reference_cases.npz"), **out)

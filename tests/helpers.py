@@ -1,0 +1,48 @@
+"""Shared helpers: run one golden case on the oracle / through the C ABI."""
+import ast
+
+import numpy as np
+
+# The parity bar of BASELINE.json's north_star: "every node value matches the
+# reference's CPU path ... to within 1e-9 relative".  Relative is measured the
+# way the reference itself measures it (relativeError, scale = 1:
+# Core/IterativeMethod.hpp:1125-1137): |a-b| / max(1, |a|, |b|).
+REL_TOL = 1e-9
+
+
+def rel_err(a, b):
+    a = np.asarray(a, dtype=np.float64); b = np.asarray(b, dtype=np.float64)
+    return np.abs(a - b) / np.maximum(1.0, np.maximum(np.abs(a), np.abs(b)))
+
+
+def case_args(golden, name):
+    return str(golden[name + "/mode"]), ast.literal_eval(str(golden[name + "/args"]))
+
+
+def run_oracle_case(po, mode, kw):
+    if mode == "vanilla":
+        return po.american_put(kw["K"], kw["r"], kw["vol"], kw["T"], kw["steps"], kw["refine"],
+                               q=kw.get("q", 0.0), call=bool(kw.get("call", 0)),
+                               american=bool(kw["american"]), scheme=kw.get("scheme", "rannacher"))
+    return po.bermudan_put(kw["K"], kw["r"], kw["alpha"], kw["T"], kw["steps"], kw["E"],
+                           kw["refine"], scheme=kw["scheme"])
+
+
+def spec_for_case(qpde, po, mode, kw, kernel="auto", copies=1):
+    """BatchSpec reproducing a golden case (optionally replicated `copies` times)."""
+    if mode == "vanilla":
+        K = kw["K"]
+        axis = po.axis_union(po.special_axis() * K, po.special_axis() * K)
+        call = bool(kw.get("call", 0))
+        return qpde.BatchSpec(
+            axis=np.tile(axis, (copies, 1)), refine=kw["refine"], r=kw["r"], sigma=kw["vol"],
+            q=kw.get("q", 0.0), T=kw["T"], dt=kw["T"] / kw["steps"], strike=np.full(copies, K),
+            scheme=kw.get("scheme", "rannacher"), american=bool(kw["american"]),
+            payoff="call" if call else "put", kernel=kernel)
+    K = kw["K"]
+    axis = po.TUTORIAL_AXIS * (K / 100.0)
+    return qpde.BatchSpec(
+        axis=np.tile(axis, (copies, 1)), refine=kw["refine"], r=kw["r"], sigma=kw["alpha"], q=0.0,
+        T=kw["T"], dt=kw["T"] / kw["steps"], strike=np.full(copies, K), scheme=kw["scheme"],
+        american=False, payoff="put", vol_model="inverse_s", n_exercise=kw["E"],
+        exercise="k_minus_s", kernel=kernel)

@@ -1,0 +1,100 @@
+"""CPU: the oracle (oracle/qpde_oracle.c) against the committed outputs of the
+reference itself (tests/golden/reference_cases.npz, made by
+tests/golden/make_golden.py from the unmodified reference headers), against the
+live reference binary when it is present, and against closed-form anchors."""
+import math
+
+import numpy as np
+import pytest
+
+from helpers import case_args, run_oracle_case
+
+
+def test_golden_cases_bit_exact(oracle, golden):
+    names = [str(n) for n in golden["names"]]
+    assert len(names) >= 20
+    for name in names:
+        mode, kw = case_args(golden, name)
+        out = run_oracle_case(oracle, mode, kw)
+        assert out["n_steps"] == int(golden[name + "/steps"]), name
+        assert np.array_equal(out["S"], golden[name + "/S"]), name
+        # bit-exact: same operation order as the reference + the LU stand-in
+        assert np.array_equal(out["V"], golden[name + "/V"]), name
+        if name + "/inner" in golden.files and len(golden[name + "/inner"]):
+            assert np.array_equal(out["inner"], golden[name + "/inner"]), name
+            assert np.array_equal(out["mask"], golden[name + "/mask"]), name
+
+
+def test_live_reference_when_present(oracle):
+    if not oracle.have_ref():
+        pytest.skip("oracle/_ref/qpde_ref not built")
+    kw = dict(american=1, steps=60, refine=2, K=87.5, r=0.03, vol=0.45, T=0.7)
+    ref = oracle.run_ref("vanilla", **kw)
+    out = oracle.american_put(kw["K"], kw["r"], kw["vol"], kw["T"], kw["steps"], kw["refine"])
+    assert np.array_equal(out["V"], ref["V"])
+    assert np.array_equal(out["inner"], ref["inner"])
+    assert np.array_equal(out["mask"], ref["mask"])
+
+
+def test_axis_special_and_refine(oracle):
+    sp = oracle.special_axis()
+    assert len(sp) == 33 and sp[0] == 0.0 and sp[-1] == 100.0 and sp[15] == 1.0
+    fine = oracle.refine(sp * 100.0, 6)
+    assert len(fine) == 2049                       # 2^6 * 32 + 1  
+    assert np.all(np.diff(fine) > 0)
+    assert np.array_equal(fine[::64], sp * 100.0)  # coarse ticks survive refinement
+    assert np.array_equal(oracle.refine(sp, 0), sp)
+    u = oracle.axis_union(np.array([0., 1., 2.]), np.array([1., 1.5, 3.]))
+    assert np.array_equal(u, np.array([0., 1., 1.5, 2., 3.]))
+
+
+def test_schedule_artifacts(oracle):
+    # constant steps that divide T exactly in floating point
+    st, n = oracle.schedule(1.0, 0.25)
+    assert n == 4 and st[n - 1].t == 0.0 and st[n - 1].event_after == 1
+    # accumulated t -= dt can miss 0 by more than eps: one extra tiny step
+    # (the 97/385/1537/6145 step counts of examples/jump_diffusion.cpp:184-190)
+    counts = [oracle.schedule(0.25, 0.25 / (12 * 2 ** k * 8))[1] for k in range(7)]
+    assert all(c in (96 * 2 ** k, 96 * 2 ** k + 1) for k, c in enumerate(counts))
+    # events: each of the E bodies ends with event_after, user events are counted
+    T, E = 1.0, 10
+    st, n = oracle.schedule(T, 0.01, [T / E * e for e in range(E)])
+    ends = [i for i in range(n) if st[i].event_after]
+    assert len(ends) == E and sum(st[i].user_events for i in ends) == E
+    assert st[n - 1].t == 0.0 and st[n - 1].user_events == 1  # event at t = 0 fires with the NullEvent
+
+
+def _bs_put(S, K, r, vol, T):
+    d1 = (math.log(S / K) + (r + vol * vol / 2) * T) / (vol * math.sqrt(T))
+    d2 = d1 - vol * math.sqrt(T)
+    N = lambda x: 0.5 * (1 + math.erf(x / math.sqrt(2)))
+    return K * math.exp(-r * T) * N(-d2) - S * N(-d1)
+
+
+def test_european_converges_to_black_scholes(oracle):
+    exact = _bs_put(100., 100., .04, .2, 1.)
+    errs = []
+    for k in range(4):
+        out = oracle.american_put(100., .04, .2, 1., 12 * 2 ** k, k, american=False)
+        errs.append(abs(oracle.interp(out["S"], out["V"], 100.) - exact))
+    assert errs[-1] < 2e-3
+    ratios = [errs[i] / errs[i + 1] for i in range(len(errs) - 1)]
+    assert all(r > 3.0 for r in ratios)            # second order: ratio -> 4
+
+
+def test_american_table_ratio_and_properties(oracle):
+    vals, its = [], []
+    for k in range(4):
+        out = oracle.american_put(100., .04, .2, 1., 12 * 4 ** k, k)
+        vals.append(oracle.interp(out["S"], out["V"], 100.))
+        its.append(out["inner"].mean())
+        payoff = np.maximum(100. - out["S"], 0.)
+        assert np.all(out["V"] >= payoff - 1e-6 * np.maximum(1., payoff))
+        m = out["mask"].astype(bool)
+        assert m[0] and not m[-1]
+        assert np.all(np.diff(m.astype(int)) <= 0)  # active set is a prefix in S for a put
+        assert out["status"] == 0 and out["inner"].min() >= 1
+    changes = np.diff(vals)
+    assert all(c > 0 for c in changes)
+    assert 2.0 < changes[0] / changes[1] < 8.0 and 2.0 < changes[1] / changes[2] < 8.0
+    assert all(1.5 < x < 3.0 for x in its)

@@ -1,0 +1,168 @@
+"""GPU: the CUDA path, called through the C ABI, against (i) the committed
+outputs of the reference itself and (ii) the oracle on seeded inputs.
+
+Bar (BASELINE.json north_star): every node value within 1e-9 relative
+(|a-b| / max(1,|a|,|b|), the reference's own relativeError with scale 1),
+identical per-step inner iteration counts, identical final active sets."""
+import numpy as np
+import pytest
+
+from helpers import REL_TOL, case_args, rel_err, run_oracle_case, spec_for_case
+
+pytestmark = pytest.mark.gpu
+
+KERNELS = ["interleaved", "resident"]
+
+
+def _supported(qpde, handle, spec):
+    try:
+        return qpde.Plan(handle, spec)
+    except qpde.QpdeError as e:
+        if e.code == qpde.ERR_UNSUPPORTED:
+            return None
+        raise
+
+
+@pytest.mark.parametrize("kernel", KERNELS)
+def test_golden_cases(qpde, handle, oracle, golden, kernel):
+    ran = 0
+    for name in [str(n) for n in golden["names"]]:
+        mode, kw = case_args(golden, name)
+        spec = spec_for_case(qpde, oracle, mode, kw, kernel=kernel, copies=3)
+        plan = _supported(qpde, handle, spec)
+        if plan is None:
+            continue
+        with plan:
+            plan.run()
+            res = plan.fetch()
+        ran += 1
+        V_ref, S_ref = golden[name + "/V"], golden[name + "/S"]
+        for c in range(3):
+            assert np.array_equal(res.S[c], S_ref), name                 # grid: bit-exact
+            err = rel_err(res.V[c], V_ref).max()
+            assert err <= REL_TOL, "%s: node error %.3e" % (name, err)
+            assert res.n_steps[c] == int(golden[name + "/steps"]), name
+            assert res.status[c] == 0
+            if name + "/inner" in golden.files and len(golden[name + "/inner"]):
+                n = res.n_steps[c]
+                assert np.array_equal(res.inner[c, :n], golden[name + "/inner"]), name
+                assert res.inner_total[c] == golden[name + "/inner"].sum()
+                assert np.array_equal(res.active[c], golden[name + "/mask"]), name
+            assert rel_err(res.value[c], float(golden[name + "/value"])) <= REL_TOL
+    assert ran >= (20 if kernel == "interleaved" else 1)
+
+
+@pytest.mark.parametrize("kernel", KERNELS)
+def test_american_batch_vs_oracle(qpde, handle, oracle, kernel):
+    """config-2 style: varied strike / vol / T / r, seeded as SURVEY.md §8(d)."""
+    rng = np.random.default_rng(1234)
+    Cn, refine, steps = 24, 4, 200        # N = 513
+    K = rng.uniform(50, 150, Cn); vol = rng.uniform(.1, .6, Cn)
+    T = rng.uniform(.25, 2., Cn); r = rng.uniform(.01, .08, Cn)
+    sp = oracle.special_axis()
+    axis = np.stack([oracle.axis_union(sp * k, sp * k) for k in K])
+    spec = qpde.BatchSpec(axis=axis, refine=refine, r=r, sigma=vol, q=0.0, T=T, dt=T / steps,
+                          strike=K, american=True, payoff="put", kernel=kernel)
+    plan = _supported(qpde, handle, spec)
+    if plan is None:
+        pytest.skip("kernel does not support this size")
+    with plan:
+        plan.run()
+        res = plan.fetch()
+    worst, iters_equal, masks_equal = 0.0, 0, 0
+    for c in range(Cn):
+        o = oracle.american_put(K[c], r[c], vol[c], T[c], steps, refine)
+        assert np.array_equal(res.S[c], o["S"])
+        worst = max(worst, rel_err(res.V[c], o["V"]).max())
+        assert res.n_steps[c] == o["n_steps"]
+        iters_equal += int(np.array_equal(res.inner[c, :o["n_steps"]], o["inner"]))
+        masks_equal += int(np.array_equal(res.active[c], o["mask"]))
+        assert rel_err(res.value[c], oracle.interp(o["S"], o["V"], K[c])) <= REL_TOL
+    assert worst <= REL_TOL, "worst node error %.3e" % worst
+    assert iters_equal == Cn and masks_equal == Cn
+
+
+@pytest.mark.parametrize("kernel", KERNELS)
+def test_full_size_properties(qpde, handle, oracle, kernel):
+    """N = 2049 x 1000 steps (BASELINE.json configs[1] shape, small batch):
+    one contract against the oracle, plus size-independent properties."""
+    rng = np.random.default_rng(7)
+    Cn, refine, steps = 8, 6, 1000
+    K = rng.uniform(50, 150, Cn); vol = rng.uniform(.1, .6, Cn)
+    T = rng.uniform(.25, 2., Cn); r = rng.uniform(.01, .08, Cn)
+    K[1], vol[1], T[1], r[1] = K[0], vol[0], T[0], r[0]       # duplicate contract
+    sp = oracle.special_axis()
+    axis = np.stack([oracle.axis_union(sp * k, sp * k) for k in K])
+    spec = qpde.BatchSpec(axis=axis, refine=refine, r=r, sigma=vol, q=0.0, T=T, dt=T / steps,
+                          strike=K, american=True, payoff="put", kernel=kernel)
+    plan = _supported(qpde, handle, spec)
+    if plan is None:
+        pytest.skip("kernel does not support this size")
+    with plan:
+        plan.run()
+        res = plan.fetch()
+        plan.run()                       # idempotence: a second run gives the same bits
+        res2 = plan.fetch()
+    assert np.array_equal(res.V, res2.V)
+    assert np.array_equal(res.V[0], res.V[1])                   # determinism across the batch
+    assert np.all(res.status == 0)
+    payoff = np.maximum(K[:, None] - res.S, 0.0)
+    assert np.all(res.V >= payoff - 1e-6 * np.maximum(1.0, payoff))   # V >= obstacle - penalty slack
+    act = res.active.astype(np.int8)
+    assert np.all(np.diff(act, axis=1) <= 0) and np.all(act[:, 0] == 1) and np.all(act[:, -1] == 0)
+    assert np.all(res.n_steps >= steps) and np.all(res.n_steps <= steps + 1)
+    for c in (0, 5):
+        o = oracle.american_put(K[c], r[c], vol[c], T[c], steps, refine)
+        err = rel_err(res.V[c], o["V"]).max()
+        assert err <= REL_TOL, "contract %d: %.3e" % (c, err)
+        assert np.array_equal(res.inner[c, :o["n_steps"]], o["inner"])
+        assert np.array_equal(res.active[c], o["mask"])
+
+
+def test_one_shot_sweep_host_buffers(qpde, handle, oracle):
+    """qpde_bs1d_sweep: the reference-facing call (host pointers in and out)."""
+    o = oracle.american_put(100., .04, .2, 1., 48, 1)
+    axis = oracle.axis_union(oracle.special_axis() * 100., oracle.special_axis() * 100.)
+    spec = qpde.BatchSpec(axis=axis[None, :], refine=1, r=.04, sigma=.2, q=0., T=1., dt=1. / 48,
+                          strike=[100.], american=True, payoff="put")
+    res = qpde.sweep(handle, spec, outputs=qpde.OUT_V | qpde.OUT_VALUE | qpde.OUT_INNER_TOTAL)
+    assert rel_err(res.V[0], o["V"]).max() <= REL_TOL
+    assert res.inner_total[0] == o["inner"].sum()
+    assert res.S is None and res.active is None
+
+
+def test_payoff_and_sigma_arrays(qpde, handle, oracle):
+    """explicit [C][N] initial condition / obstacle / per-node volatility."""
+    K, refine, steps = 100., 2, 80
+    S = oracle.refine(oracle.TUTORIAL_AXIS, refine)
+    with np.errstate(divide="ignore"):
+        vol = 20. / S
+    vol[0] = 0.3                                           # node 0 is a boundary row; value unused
+    lo, di, up = oracle.bs_coeffs(S, .04, vol, 0.)
+    payoff = np.abs(S - K)                                 # straddle as an array
+    st, n = oracle.schedule(1., 1. / steps)
+    o = oracle.sweep(S, lo, di, up, payoff, 1., st, n, american=True, obstacle=payoff)
+    spec = qpde.BatchSpec(axis=np.tile(oracle.TUTORIAL_AXIS, (2, 1)), refine=refine, r=.04, sigma=0.,
+                          q=0., T=1., dt=1. / steps, strike=[K, K], american=True,
+                          payoff_array=np.tile(payoff, (2, 1)), obstacle_array=np.tile(payoff, (2, 1)),
+                          vol_model="nodes", sigma_nodes=np.tile(vol, (2, 1)))
+    with qpde.Plan(handle, spec) as plan:
+        plan.run()
+        res = plan.fetch()
+    assert rel_err(res.V[1], o["V"]).max() <= REL_TOL
+    assert np.array_equal(res.inner[1, :n], o["inner"])
+    assert np.array_equal(res.active[1], o["mask"])
+
+
+def test_invalid_arguments(qpde, handle):
+    axis = np.array([[0., 1., 2., 3.]])
+    good = dict(axis=axis, refine=1, r=.04, sigma=.2, q=0., T=1., dt=.1, strike=[1.], american=True)
+    with pytest.raises(qpde.QpdeError) as e:
+        qpde.Plan(handle, qpde.BatchSpec(**{**good, "dt": 2.0}))
+    assert e.value.code == qpde.ERR_INVALID
+    with pytest.raises(qpde.QpdeError):
+        qpde.Plan(handle, qpde.BatchSpec(**{**good, "max_inner": 0}))
+    spec = qpde.BatchSpec(**good)
+    spec.struct.abi_version = 99
+    with pytest.raises(qpde.QpdeError):
+        qpde.Plan(handle, spec)
