@@ -35,7 +35,7 @@ class Problem(C.Structure):
                 ("obstacle", C.POINTER(C.c_double)),
                 ("tolerance", C.c_double), ("scale", C.c_double),
                 ("penalty_tol", C.c_double), ("max_inner", C.c_int),
-                ("event_obstacle", C.POINTER(C.c_double))]
+                ("event_obstacle", C.POINTER(C.c_double)), ("solver", C.c_int)]
 
 
 _lib = None
@@ -127,7 +127,7 @@ def interp(x, v, c):
 
 def sweep(S, lo, di, up, v0, T, steps, n_steps, scheme="rannacher",
           american=False, obstacle=None, event_obstacle=None,
-          tolerance=1e-6, scale=1.0, penalty_tol=1e-6, max_inner=1000):
+          tolerance=1e-6, scale=1.0, penalty_tol=1e-6, max_inner=1000, solver=0):
     """Returns dict(V, inner, mask, status)."""
     n = len(S)
     arrs = [np.ascontiguousarray(a, dtype=np.float64) for a in (S, lo, di, up, v0)]
@@ -146,6 +146,7 @@ def sweep(S, lo, di, up, v0, T, steps, n_steps, scheme="rannacher",
         event_obstacle = np.ascontiguousarray(event_obstacle, dtype=np.float64)
         p.event_obstacle = _dp(event_obstacle)
     p.tolerance, p.scale, p.penalty_tol, p.max_inner = tolerance, scale, penalty_tol, max_inner
+    p.solver = solver
     V = np.zeros(n)
     inner = np.zeros(n_steps, dtype=np.int32)
     mask = np.zeros(n, dtype=np.uint8)
@@ -156,14 +157,14 @@ def sweep(S, lo, di, up, v0, T, steps, n_steps, scheme="rannacher",
 
 
 def american_put(K, r, vol, T, n_steps, refine_times, q=0.0, S0=None, call=False,
-                 american=True, scheme="rannacher"):
+                 american=True, scheme="rannacher", solver=0):
     """The vanilla_options.cpp wiring on the oracle."""
     S = vanilla_grid(K, S0, refine_times)
     lo, di, up = bs_coeffs(S, r, vol, q)
     payoff = np.where(S < K, 0.0, S - K) if call else np.where(S < K, K - S, 0.0)
     steps, n = schedule(T, T / n_steps)
     out = sweep(S, lo, di, up, payoff, T, steps, n, scheme=scheme,
-                american=american, obstacle=payoff)
+                american=american, obstacle=payoff, solver=solver)
     out["S"] = S
     out["n_steps"] = n
     return out

@@ -256,6 +256,28 @@ static void tri_solve(const tri_lu *f, double *x) {
 	}
 }
 
+/* Arithmetic model of the product's INTERLEAVED kernel (Thomas elimination
+ * without pivoting, one reciprocal per row, no FMA).  Selected with
+ * qpo_problem.solver = 1; used by the tests to tell apart "the kernel differs
+ * from its own arithmetic model" (a bug) from "a different but valid
+ * elimination order moved a value by one ulp" (a tie). */
+static void thomas_model(int n, const double *a, const double *b,
+		const double *c, double *x, double *cp, double *dp) {
+	double cprev = 0., dprev = 0., xn = 0.;
+	int i;
+	for(i = 0; i < n; ++i) {
+		const double denom = b[i] - a[i] * cprev;
+		const double inv = 1. / denom;
+		cprev = c[i] * inv;
+		dprev = (x[i] - a[i] * dprev) * inv;
+		cp[i] = cprev; dp[i] = dprev;
+	}
+	for(i = n - 1; i >= 0; --i) {
+		xn = dp[i] - cp[i] * xn;
+		x[i] = xn;
+	}
+}
+
 /* ------------------------------------------------------------------------ */
 /* relativeError: Core/IterativeMethod.hpp:1125-1137                         */
 /* ------------------------------------------------------------------------ */
@@ -423,10 +445,11 @@ int qpo_sweep_1d(const qpo_problem *p, double *V, int *inner,
 				memcpy(A_lo, M_lo, sizeof(double) * (size_t)n);
 				memcpy(A_di, M_di, sizeof(double) * (size_t)n);
 				memcpy(A_up, M_up, sizeof(double) * (size_t)n);
-				tri_factor(&lu, A_lo, A_di, A_up);
+				if(!p->solver) tri_factor(&lu, A_lo, A_di, A_up);
 			}
 			memcpy(x, lb, sizeof(double) * (size_t)n);
-			tri_solve(&lu, x);
+			if(p->solver) thomas_model(n, A_lo, A_di, A_up, x, xprev, rhs);
+			else tri_solve(&lu, x);
 			its = 1;
 		} else {
 			/* ToleranceIteration (:1211-1254) over PenaltyMethodDifference
@@ -446,9 +469,13 @@ int qpo_sweep_1d(const qpo_problem *p, double *V, int *inner,
 					A_up[i] = M_up[i];
 					rhs[i] = c ? (lb[i] + pen * p->obstacle[i]) : lb[i];
 				}
-				tri_factor(&lu, A_lo, A_di, A_up);
 				memcpy(x, rhs, sizeof(double) * (size_t)n);
-				tri_solve(&lu, x);
+				if(p->solver) {
+					thomas_model(n, A_lo, A_di, A_up, x, P_di, rhs);
+				} else {
+					tri_factor(&lu, A_lo, A_di, A_up);
+					tri_solve(&lu, x);
+				}
 				++its;
 				notdone = relative_error(n, x, xprev, p->scale) > p->tolerance;
 				/* guard only; the reference would keep iterating */

@@ -75,6 +75,8 @@ typedef struct {
 	int max_inner;         /* guard (the reference has none)               */
 	const double *event_obstacle; /* [n] or NULL: at each user event
 	                          V = max(V, event_obstacle) (tutorial.cpp:103-105) */
+	int solver;            /* 0: pivoted LU (the reference's policy);
+	                          1: arithmetic model of the INTERLEAVED kernel   */
 } qpo_problem;
 
 /* Runs the sweep.  V [n] out; inner [n_steps] out (may be NULL); mask [n] out

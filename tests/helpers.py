@@ -15,6 +15,26 @@ def rel_err(a, b):
     return np.abs(a - b) / np.maximum(1.0, np.maximum(np.abs(a), np.abs(b)))
 
 
+def mask_mismatches(mask, mask_ref, V_ref, obstacle):
+    """Active-set comparison with the tie policy of DESIGN.md §6: the sets must be
+    identical except at nodes where the reference's own V - obstacle is within a
+    few ulp of zero.  There the sign is decided by the last rounding of the
+    elimination (Thomas / partition / pivoted LU all differ) — typically the
+    free-boundary node after the reference's extra ~1e-16-long last time step
+    (SURVEY.md §8(a) row 3), where V - obstacle = O(1e-14).
+    Returns (hard_mismatches, ties)."""
+    mask = np.asarray(mask).astype(bool); mask_ref = np.asarray(mask_ref).astype(bool)
+    diff = mask != mask_ref
+    gap = np.abs(np.asarray(V_ref) - np.asarray(obstacle))
+    tie = gap <= 64 * np.finfo(np.float64).eps * np.maximum(1.0, np.abs(obstacle))
+    return int(np.sum(diff & ~tie)), int(np.sum(diff & tie))
+
+
+def case_obstacle(kw, S):
+    K = kw["K"]
+    return np.where(S < K, 0.0, S - K) if kw.get("call", 0) else np.where(S < K, K - S, 0.0)
+
+
 def case_args(golden, name):
     return str(golden[name + "/mode"]), ast.literal_eval(str(golden[name + "/args"]))
 
