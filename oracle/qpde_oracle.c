@@ -315,6 +315,10 @@ static void tri_spmv(int n, const double *lo, const double *di,
 	}
 }
 
+/* diagnostics: number of inner solves of the last sweep and how many of them
+ * saw an active set different from the one of the previous solve */
+long qpo_diag_solves = 0, qpo_diag_mask_changes = 0;
+
 int qpo_sweep_1d(const qpo_problem *p, double *V, int *inner,
 		unsigned char *mask) {
 	const int n = p->n;
@@ -343,6 +347,8 @@ int qpo_sweep_1d(const qpo_problem *p, double *V, int *inner,
 	int bdf_phase = 1;     /* BDFTwo: 1 = BDF1 step, 2 = first BDF2, 3 = BDF2 */
 
 	tri_alloc(&lu, n);
+	qpo_diag_solves = 0; qpo_diag_mask_changes = 0;
+	for(i = 0; i < n; ++i) P_di[i] = 0.;
 	memcpy(v1, p->v0, sizeof(double) * (size_t)n);
 	/* the stepper pushes (T, V^0) (:1171-1174) */
 	time1 = p->T;
@@ -457,6 +463,12 @@ int qpo_sweep_1d(const qpo_problem *p, double *V, int *inner,
 			memcpy(x, v1, sizeof(double) * (size_t)n);
 			do {
 				memcpy(xprev, x, sizeof(double) * (size_t)n);
+				{ int changed = 0;
+				for(i = 0; i < n; ++i) {
+					const int c = (pen * ((0. + 1. * xprev[i]) - p->obstacle[i])) < 0.;
+					if((P_di[i] != 0.) != c) changed = 1;
+				}
+				++qpo_diag_solves; qpo_diag_mask_changes += changed; }
 				for(i = 0; i < n; ++i) {
 					/* predicate = I x - payoff ; c = (scale*pred) < 0 */
 					const double acc = 0. + 1. * xprev[i];

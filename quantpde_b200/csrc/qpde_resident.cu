@@ -51,6 +51,7 @@ struct Smem {
 	// right-hand-side hand-over
 	double s_G7[MAX_WARPS], s_G2l[MAX_WARPS], s_P0[MAX_WARPS], s_G2f[MAX_WARPS];
 	double S_tail, lo_tail, di_tail, up_tail;
+	unsigned flags[2];
 };
 
 inline size_t smem_bytes(int M, int P) {
@@ -59,6 +60,19 @@ inline size_t smem_bytes(int M, int P) {
 
 __device__ __forceinline__ double shfl_up(double v, int d) { return __shfl_up_sync(FULL, v, d); }
 __device__ __forceinline__ double shfl_down(double v, int d) { return __shfl_down_sync(FULL, v, d); }
+
+// 1 / d for the factorisation: hardware seed (MUFU.RCP64H, ~2^-22) plus two
+// Newton steps => error below one ulp.  The factors need no more: any
+// elimination order already moves the solution by a few ulp.
+__device__ __forceinline__ double rcp(double d) {
+	double y;
+	asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(d));
+	double e = fma(-d, y, 1.);
+	y = fma(y, e, y);
+	e = fma(-d, y, 1.);
+	y = fma(y, e, y);
+	return y;
+}
 
 // relativeError's per-element test |a-b| / max(scale,|a|,|b|) > tol
 // (Core/IterativeMethod.hpp:1125-1137) without a division in the common case:
@@ -180,7 +194,7 @@ k_resident_sweep(DeviceBatch b, DeviceResult out) {
 	if(AMERICAN || EVENTS) pz_tail = obstacle_value(N - 1);
 	x_next = i0 + M < n_main ? initial_value(i0 + M) : 0.;
 	sm_xlast[tid + 1] = x[M - 1];
-	if(tid == 0) sm_xlast[0] = 0.;
+	if(tid == 0) { sm_xlast[0] = 0.; sm.flags[0] = 0u; sm.flags[1] = 0u; }
 #pragma unroll
 	for(int s = 0; s < 5; ++s) { f_al[s] = 0.; f_ga[s] = 0.; }
 
@@ -213,12 +227,12 @@ k_resident_sweep(DeviceBatch b, DeviceResult out) {
 		}
 		// level 1: interior rows 1 .. M-1
 		double d = bb[1];
-		f_invd[1] = 1. / d;
+		f_invd[1] = rcp(d);
 #pragma unroll
 		for(int j = 2; j < M; ++j) {
 			f_m[j] = a[j] * f_invd[j - 1];
-			d = bb[j] - f_m[j] * c[j - 1];
-			f_invd[j] = 1. / d;
+			d = fma(-f_m[j], c[j - 1], bb[j]);
+			f_invd[j] = rcp(d);
 		}
 		double y[M];
 		y[1] = a[1];
@@ -249,15 +263,16 @@ k_resident_sweep(DeviceBatch b, DeviceResult out) {
 #pragma unroll
 		for(int s = 0; s < 5; ++s) {
 			const int dl = 1 << s;
-			const double Bm = shfl_up(B2, dl), Bq = shfl_down(B2, dl);
+			const double rB = rcp(B2);
+			const double rBm = shfl_up(rB, dl), rBq = shfl_down(rB, dl);
 			const double Am = shfl_up(A2, dl), Aq = shfl_down(A2, dl);
 			const double Cm = shfl_up(C2, dl), Cq = shfl_down(C2, dl);
 			const double Vm = shfl_up(V2, dl), Vq = shfl_down(V2, dl);
 			const double Wm = shfl_up(W2, dl), Wq = shfl_down(W2, dl);
 			const bool okm = interior && lane - dl >= 1;
 			const bool okq = interior && lane + dl <= 31;
-			const double al = okm ? -A2 / Bm : 0.;
-			const double ga = okq ? -C2 / Bq : 0.;
+			const double al = okm ? -A2 * rBm : 0.;
+			const double ga = okq ? -C2 * rBq : 0.;
 			f_al[s] = al; f_ga[s] = ga;
 			B2 = B2 + (okm ? al * Cm : 0.) + (okq ? ga * Aq : 0.);
 			V2 = V2 + (okm ? al * Vm : 0.) + (okq ? ga * Vq : 0.);
@@ -265,7 +280,7 @@ k_resident_sweep(DeviceBatch b, DeviceResult out) {
 			A2 = okm ? al * Am : 0.;
 			C2 = okq ? ga * Cq : 0.;
 		}
-		f_invB2 = 1. / B2;
+		f_invB2 = rcp(B2);
 		f_V2 = V2 * f_invB2;
 		f_W2 = W2 * f_invB2;
 		// hand-over to level 3
@@ -273,24 +288,33 @@ k_resident_sweep(DeviceBatch b, DeviceResult out) {
 		if(lane == 1)  { sm.f_V2f[warp] = f_V2; sm.f_W2f[warp] = f_W2; }
 		if(lane == 0)  { sm.f_a0[warp] = a[0]; sm.f_Bp[warp] = Bpart; sm.f_Ct[warp] = Ct; }
 		__syncthreads();
-		// level 3: W x W tridiagonal over the warp separators, Thomas, by one thread
-		if(tid == 0) {
-			double cprev = 0., dprev = 1.;
-			for(int w = 0; w < W; ++w) {
+		// level 3: W x W tridiagonal over the warp separators.  Lanes 0 .. W-1 of
+		// warp 0 assemble one row each; lane 0 then runs the Thomas recurrence
+		// (one reciprocal per row).
+		if(warp == 0) {
+			if(lane < W) {
+				const int w = lane;
 				const double a0 = sm.f_a0[w];
 				const double Vs7q = w > 0 ? sm.f_Vs7[w - 1] : 0., Ws7q = w > 0 ? sm.f_Ws7[w - 1] : 0.;
 				const double V2q = w > 0 ? sm.f_V2l[w - 1] : 0., W2q = w > 0 ? sm.f_W2l[w - 1] : 0.;
 				const double At = -a0 * Vs7q;
 				const double Bt = sm.f_Bp[w] - a0 * Ws7q;
 				const double Cw = sm.f_Ct[w];
-				const double A3 = -At * V2q;
-				const double B3 = Bt - At * W2q - Cw * sm.f_V2f[w];
-				const double C3 = -Cw * sm.f_W2f[w];
-				const double m3 = w > 0 ? A3 / dprev : 0.;
-				const double d3 = B3 - m3 * cprev;
-				sm.m3[w] = m3; sm.invd3[w] = 1. / d3; sm.C3[w] = C3;
+				sm.m3[w] = -At * V2q;                                // A3, turned into m3 below
+				sm.invd3[w] = Bt - At * W2q - Cw * sm.f_V2f[w];      // B3, turned into 1 / d3 below
+				sm.C3[w] = -Cw * sm.f_W2f[w];
 				sm.q1[w] = -a0; sm.q2[w] = -At; sm.q3[w] = -Cw;
-				cprev = C3; dprev = d3;
+			}
+			__syncwarp();
+			if(lane == 0) {
+				double cprev = 0., rprev = 0.;
+				for(int w = 0; w < W; ++w) {
+					const double m3 = sm.m3[w] * rprev;
+					const double d3 = fma(-m3, cprev, sm.invd3[w]);
+					rprev = rcp(d3);
+					sm.m3[w] = m3; sm.invd3[w] = rprev;
+					cprev = sm.C3[w];
+				}
 			}
 		}
 		__syncthreads();
@@ -370,6 +394,7 @@ k_resident_sweep(DeviceBatch b, DeviceResult out) {
 	int n_steps = 0, inner_total = 0, status = 0;
 	bool more = true;
 	bool refactor = true;        // block-uniform: the cached factorisation is stale
+	unsigned flip = 0;           // block-uniform: which flag slot the next reduction uses
 	const int jl_thread = (n_main - 1) / M, jl = (n_main - 1) % M; // owner of row N-2
 
 	while(more) {
@@ -385,11 +410,13 @@ k_resident_sweep(DeviceBatch b, DeviceResult out) {
 			g.h = (hh0 * h1) / (hh0 + h1);
 			c1 = hh0 / h1; c0 = h1 / hh0; den = hh0 - h1;
 		}
-		// (Re)build the system rows when the step kind or size changes.  The
-		// reference keeps a stale factorisation while isATheSame() holds even if
-		// h moved in its last bits (IterativeMethod.hpp:906); here A always
-		// carries the current h — a relative perturbation of ~1e-16.
-		if(kind != cur_kind || g.h != cur_h) {
+		// (Re)build the system rows when the step kind or size changes.  h0 is a
+		// difference of accumulated times and moves in its last bits from step
+		// to step; such moves (relative 1e-14 or less) do not trigger a rebuild:
+		// the step is then taken with an h that is off by that relative amount,
+		// which perturbs the solution at the 1e-14 level (the reference itself
+		// keeps a stale A for non-penalised roots, IterativeMethod.hpp:906).
+		if(kind != cur_kind || fabs(g.h - cur_h) > 1e-14 * cur_h) {
 			cur_kind = kind; cur_h = g.h;
 #pragma unroll
 			for(int j = 0; j < M; ++j) {
@@ -475,11 +502,27 @@ k_resident_sweep(DeviceBatch b, DeviceResult out) {
 			++its;
 			if(AMERICAN) {
 				newmask = mask_of();
-				const int notdone = __syncthreads_or(nd ? 1 : 0);
-				const int changed = __syncthreads_or(newmask != curmask ? 1 : 0);
-				refactor = changed != 0;
-				again = notdone != 0;
-				if(again && its >= b.max_inner) { status = 1; again = false; }
+				// one barrier carries both block-wide flags
+				const unsigned bits = (nd ? 1u : 0u) | (newmask != curmask ? 2u : 0u);
+				const unsigned wbits = __reduce_or_sync(FULL, bits);
+				const unsigned slot = flip & 1u;   // two slots used alternately
+				++flip;
+				if(lane == 0 && wbits) atomicOr(&sm.flags[slot], wbits);
+				__syncthreads();
+				const unsigned all = *(volatile unsigned *)&sm.flags[slot];
+				if(tid == 0) sm.flags[slot ^ 1u] = 0u;       // ordered by the barrier inside the next solve
+				const bool notdone = (all & 1u) != 0, changed = (all & 2u) != 0;
+				refactor = changed;
+				again = notdone;
+				if(notdone && !changed) {
+					// Same active set => the next inner iteration would assemble the
+					// same matrix and right-hand side and return this iterate again
+					// (relativeError == 0): count it, do not redo it.
+					if(its >= b.max_inner) status = 1; else ++its;
+					again = false;
+				} else if(again && its >= b.max_inner) {
+					status = 1; again = false;
+				}
 			} else {
 				__syncthreads();
 				again = false;

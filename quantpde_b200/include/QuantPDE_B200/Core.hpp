@@ -1,0 +1,507 @@
+// QuantPDE_B200/Core.hpp — header-only host API over the C ABI (qpde_b200.h).
+//
+// Same call shape as the classes of parsiad/QuantPDE that sit on the 1-D
+// time-stepping path, so that an example written against the reference reads
+// the same against this header (see examples/vanilla_options_b200.cpp next to
+// the reference's examples/vanilla_options.cpp:34-130):
+//
+//   reference (QuantPDE/src/...)                          here (namespace QuantPDE_B200)
+//   Core/Axis.hpp:98,205-257,270-358,445-459  Axis         Axis  {ticks, special, uniform, range, *, +}
+//   Core/Domain.hpp:1092-1172   RectilinearGrid1           RectilinearGrid1 (+ refined(k))
+//   Modules/Operators/BlackScholes.hpp:114-134             BlackScholes1(grid, r, v, q)
+//   Core/Stepper.hpp:27-36      ReverseConstantStepper     ReverseConstantStepper(t0, T, dt)
+//   Core/IterativeMethod.hpp:1243 ToleranceIteration       ToleranceIteration(tolerance, scale)
+//   Core/Rannacher.hpp:123  CrankNicolson.hpp:97  BDF.hpp:496,570
+//                                                          ReverseRannacher / ReverseCrankNicolson /
+//                                                          ReverseBDFOne / ReverseBDFTwo (grid, op)
+//   Core/PenaltyMethod.hpp:281-301                         MinPenaltyMethodDifference1(grid, node, payoff, tol)
+//   Bindings/Eigen.hpp:143-165  SparseLUSolver             B200Solver (owns the device context)
+//   Core/IterativeMethod.hpp:1065-1079 Iteration::solve    stepper.solve(grid, payoff, root, solver)
+//
+// What differs, and why: the reference assembles and factorises one sparse
+// matrix per inner iteration on the host; here solve() only *describes* the
+// iteration tree and hands the whole backward sweep of every contract to one
+// call of qpde_bs1d_sweep().  The batched entry point is Batch::solve(), which
+// sweeps many such descriptions (same grid size, scheme and constraint type)
+// in one launch.  Errors: every C-ABI failure is thrown as std::runtime_error
+// carrying qpde_last_error(); there is no CPU fallback.
+//
+// Multi-TU safe (everything is inline); no global state.
+#ifndef QUANT_PDE_B200_CORE_HPP
+#define QUANT_PDE_B200_CORE_HPP
+
+#include <cfloat>
+#include <cmath>
+#include <cstdint>
+#include <functional>
+#include <initializer_list>
+#include <memory>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "qpde_b200.h"
+
+namespace QuantPDE_B200 {
+
+typedef double Real;
+typedef int Index;
+
+constexpr Real epsilon = DBL_EPSILON;   // Core/EarlyInclude.hpp:61
+constexpr Real tolerance = 1e-6;        // :62
+constexpr Real scale = 1.;              // :63
+
+////////////////////////////////////////////////////////////////////////////////
+// Axis — Core/Axis.hpp
+////////////////////////////////////////////////////////////////////////////////
+
+class Axis {
+	std::vector<Real> n;
+public:
+	Axis() {}
+	Axis(std::initializer_list<Real> ticks) : n(ticks) {}
+	explicit Axis(std::vector<Real> ticks) : n(std::move(ticks)) {}
+
+	Index size() const { return (Index)n.size(); }
+	Real operator[](Index i) const { return n[i]; }
+	const Real *data() const { return n.data(); }
+
+	// Axis::special (Core/Axis.hpp:445-459)
+	static Axis special() {
+		return Axis {
+			0., .1, .2, .3, .4, .5, .6, .7, .80, .84, .88, .92, .94, .96, .98,
+			1., 1.02, 1.04, 1.06, 1.08, 1.10, 1.14, 1.18, 1.23, 1.30, 1.40,
+			1.50, 1.75, 2.25, 3.00, 7.50, 20., 100.
+		};
+	}
+	// Core/Axis.hpp:205-211
+	static Axis range(Real begin, Real step, Real end) {
+		std::vector<Real> v((size_t)std::floor((end - begin) / step) + 1);
+		for(size_t i = 0; i < v.size(); ++i) v[i] = begin + step * (Real)i;
+		return Axis(std::move(v));
+	}
+	// Core/Axis.hpp:219-226
+	static Axis uniform(Real begin, Real end, Index points) {
+		const Real dx = (end - begin) / (points - 1);
+		std::vector<Real> v((size_t)points);
+		for(Index i = 0; i < points; ++i) v[i] = begin + dx * i;
+		return Axis(std::move(v));
+	}
+	// union, Core/Axis.hpp:270-313
+	friend Axis operator+(const Axis &a, const Axis &b) {
+		std::vector<Real> c;
+		size_t i = 0, j = 0;
+		while(i < a.n.size() && j < b.n.size()) {
+			if(a.n[i] == b.n[j])     { c.push_back(a.n[i++]); ++j; }
+			else if(a.n[i] < b.n[j]) { c.push_back(a.n[i++]); }
+			else                     { c.push_back(b.n[j++]); }
+		}
+		while(i < a.n.size()) c.push_back(a.n[i++]);
+		while(j < b.n.size()) c.push_back(b.n[j++]);
+		return Axis(std::move(c));
+	}
+	// scaling, Core/Axis.hpp:320-358
+	friend Axis operator*(const Axis &a, Real c) {
+		std::vector<Real> v(a.n);
+		for(Real &x : v) x = x * c;
+		return Axis(std::move(v));
+	}
+	friend Axis operator*(Real c, const Axis &a) { return a * c; }
+};
+
+////////////////////////////////////////////////////////////////////////////////
+// RectilinearGrid1 — Core/Domain.hpp:1092-1172.  Keeps the coarse axis and the
+// refinement count; the refined ticks are produced on the device with the
+// reference's arithmetic (and on the host by nodes(), identically).
+////////////////////////////////////////////////////////////////////////////////
+
+class RectilinearGrid1 {
+	Axis axis;
+	int times;
+public:
+	RectilinearGrid1() : times(0) {}
+	RectilinearGrid1(Axis a, int refine = 0) : axis(std::move(a)), times(refine) {}
+
+	RectilinearGrid1 refined(int k = 1) const { return RectilinearGrid1(axis, times + k); }
+	const Axis &coarse() const { return axis; }
+	int refinement() const { return times; }
+	Index size() const { return (Index)qpde_refined_size(axis.size(), times); }
+
+	// refined ticks (Core/Domain.hpp:1126-1145)
+	std::vector<Real> nodes() const {
+		std::vector<Real> m((size_t)size());
+		if(times <= 0) { for(Index i = 0; i < axis.size(); ++i) m[i] = axis[i]; return m; }
+		const int tmp = 1 << times;
+		size_t j = 0;
+		m[j++] = axis[0];
+		for(Index i = 1; i < axis.size(); ++i) {
+			const Real dx = (axis[i] - axis[i - 1]) / tmp;
+			for(int k = 1; k < tmp; ++k) m[j++] = k * dx + axis[i - 1];
+			m[j++] = axis[i];
+		}
+		return m;
+	}
+};
+
+////////////////////////////////////////////////////////////////////////////////
+// Payoffs — Modules/Lambdas/Payoffs.hpp.  A Payoff is either one of the tagged
+// closed forms (evaluated on the device) or any Real(Real) callable (evaluated
+// on the host at the grid nodes and shipped as an array).
+////////////////////////////////////////////////////////////////////////////////
+
+class Payoff {
+	int kind_;
+	Real K_;
+	std::function<Real(Real)> f_;
+public:
+	Payoff() : kind_(QPDE_PAYOFF_ARRAY), K_(0.) {}
+	Payoff(int kind, Real K) : kind_(kind), K_(K) {}
+	template <typename F, typename = decltype(std::declval<F>()(Real()))>
+	Payoff(F f) : kind_(QPDE_PAYOFF_ARRAY), K_(0.), f_(std::move(f)) {}
+
+	int kind() const { return kind_; }
+	Real strike() const { return K_; }
+	Real operator()(Real S) const {
+		switch(kind_) {
+		case QPDE_PAYOFF_PUT:          return S < K_ ? K_ - S : 0.;
+		case QPDE_PAYOFF_CALL:         return S < K_ ? 0. : S - K_;
+		case QPDE_PAYOFF_DIGITAL_PUT:  return S > K_ ? 0. : 1.;
+		case QPDE_PAYOFF_DIGITAL_CALL: return S < K_ ? 0. : 1.;
+		case QPDE_PAYOFF_STRADDLE:     return S < K_ ? K_ - S : S - K_;
+		case QPDE_PAYOFF_K_MINUS_S:    return K_ - S;
+		default:                       return f_(S);
+		}
+	}
+};
+
+inline Payoff putPayoff(Real K)         { return Payoff(QPDE_PAYOFF_PUT, K); }
+inline Payoff callPayoff(Real K)        { return Payoff(QPDE_PAYOFF_CALL, K); }
+inline Payoff digitalPutPayoff(Real K)  { return Payoff(QPDE_PAYOFF_DIGITAL_PUT, K); }
+inline Payoff digitalCallPayoff(Real K) { return Payoff(QPDE_PAYOFF_DIGITAL_CALL, K); }
+inline Payoff straddlePayoff(Real K)    { return Payoff(QPDE_PAYOFF_STRADDLE, K); }
+inline Payoff exerciseValue(Real K)     { return Payoff(QPDE_PAYOFF_K_MINUS_S, K); }
+
+////////////////////////////////////////////////////////////////////////////////
+// Volatility argument of BlackScholes1: a constant, alpha / S, or any f(S)
+// (the constant / Function1 cases of Controllable<1>, IterativeMethod.hpp:449-499)
+////////////////////////////////////////////////////////////////////////////////
+
+class Volatility {
+	int model_;
+	Real param_;
+	std::function<Real(Real)> f_;
+public:
+	Volatility(Real sigma) : model_(QPDE_VOL_CONST), param_(sigma) {}
+	Volatility(int model, Real param) : model_(model), param_(param) {}
+	template <typename F, typename = decltype(std::declval<F>()(Real()))>
+	Volatility(F f) : model_(QPDE_VOL_NODES), param_(0.), f_(std::move(f)) {}
+	int model() const { return model_; }
+	Real param() const { return param_; }
+	Real operator()(Real S) const {
+		return model_ == QPDE_VOL_CONST ? param_ : (model_ == QPDE_VOL_INVERSE_S ? param_ / S : f_(S));
+	}
+};
+inline Volatility inverseSVolatility(Real alpha) { return Volatility(QPDE_VOL_INVERSE_S, alpha); }
+
+////////////////////////////////////////////////////////////////////////////////
+// The iteration tree
+////////////////////////////////////////////////////////////////////////////////
+
+class LinearSystem {
+public:
+	virtual ~LinearSystem() {}
+};
+
+// BlackScholes1(grid, r, v, q) — Modules/Operators/BlackScholes.hpp:114-134
+class BlackScholes1 : public LinearSystem {
+public:
+	const RectilinearGrid1 &grid;
+	Real r; Volatility v; Real q;
+	BlackScholes1(const RectilinearGrid1 &grid, Real r, Volatility v, Real q)
+			: grid(grid), r(r), v(std::move(v)), q(q) {}
+};
+
+class Iteration {
+protected:
+	std::vector<size_t> its;
+public:
+	virtual ~Iteration() {}
+	const std::vector<size_t> &iterations() const { return its; }     // IterativeMethod.hpp:997
+	Real meanIterations() const {
+		Real s = 0.; for(size_t k : its) s += (Real)k;
+		return its.empty() ? 0. : s / (Real)its.size();
+	}
+	friend class ReverseConstantStepper;
+	friend class Batch;
+};
+
+// ToleranceIteration(tolerance, scale) — IterativeMethod.hpp:1243-1252
+class ToleranceIteration : public Iteration {
+public:
+	Real tol, scl;
+	int maxIterations;   // guard; the reference has none and would loop forever
+	ToleranceIteration(Real tolerance = QuantPDE_B200::tolerance, Real scale = QuantPDE_B200::scale,
+			int maxIterations = 100) : tol(tolerance), scl(scale), maxIterations(maxIterations) {}
+};
+
+class IterationNode : public LinearSystem {
+public:
+	Iteration *iteration;
+	IterationNode() : iteration(nullptr) {}
+	void setIteration(Iteration &it) { iteration = &it; }             // IterativeMethod.hpp:848
+};
+
+class Discretization : public IterationNode {
+public:
+	const RectilinearGrid1 &grid;
+	const BlackScholes1 &op;
+	int scheme;
+	Discretization(const RectilinearGrid1 &g, const BlackScholes1 &o, int s) : grid(g), op(o), scheme(s) {}
+};
+struct ReverseRannacher : Discretization {
+	ReverseRannacher(const RectilinearGrid1 &g, const BlackScholes1 &o) : Discretization(g, o, QPDE_SCHEME_RANNACHER) {}
+};
+struct ReverseCrankNicolson : Discretization {
+	ReverseCrankNicolson(const RectilinearGrid1 &g, const BlackScholes1 &o) : Discretization(g, o, QPDE_SCHEME_CN) {}
+};
+struct ReverseBDFOne : Discretization {
+	ReverseBDFOne(const RectilinearGrid1 &g, const BlackScholes1 &o) : Discretization(g, o, QPDE_SCHEME_BDF1) {}
+};
+typedef ReverseBDFOne ReverseImplicitEuler;
+struct ReverseBDFTwo : Discretization {
+	ReverseBDFTwo(const RectilinearGrid1 &g, const BlackScholes1 &o) : Discretization(g, o, QPDE_SCHEME_BDF2) {}
+};
+
+// MinPenaltyMethodDifference1(grid, constraintNode, payoff, tolerance) —
+// Core/PenaltyMethod.hpp:281-301
+class MinPenaltyMethodDifference1 : public IterationNode {
+	std::vector<bool> mask;
+public:
+	const RectilinearGrid1 &grid;
+	const Discretization &constraint;
+	Payoff obstacle;
+	Real tol;
+	MinPenaltyMethodDifference1(const RectilinearGrid1 &g, const Discretization &d, Payoff payoff,
+			Real tolerance = QuantPDE_B200::tolerance)
+			: grid(g), constraint(d), obstacle(std::move(payoff)), tol(tolerance) {}
+	// PenaltyMethod::constraintMask — PenaltyMethod.hpp:127-139
+	const std::vector<bool> &constraintMask() const { return mask; }
+	friend class ReverseConstantStepper;
+	friend class Batch;
+};
+
+// The result of solve(): node values + piecewise-linear read-out
+// (InterpolantWrapper1, Core/Interpolant.hpp:59-80,153-181,331-374)
+class Solution {
+	std::vector<Real> S, V;
+public:
+	Solution() {}
+	Solution(std::vector<Real> S, std::vector<Real> V) : S(std::move(S)), V(std::move(V)) {}
+	const std::vector<Real> &nodes() const { return S; }
+	const std::vector<Real> &values() const { return V; }
+	Real operator()(Real c) const {
+		const Index n = (Index)S.size();
+		Index idx = 0; Real w = 0.;
+		if(c <= S[0]) { idx = 0; w = 1.; }
+		else if(c >= S[n - 1]) { idx = n - 2; w = 0.; }
+		else {
+			Index lo = 0, hi = n - 2, mid = 0;
+			while(lo <= hi) {
+				mid = (lo + hi) / 2;
+				if(c < S[mid]) hi = mid - 1;
+				else if(c >= S[mid + 1]) lo = mid + 1;
+				else { w = (S[mid + 1] - c) / (S[mid + 1] - S[mid]); break; }
+			}
+			idx = mid;
+		}
+		Real sum = 0.;
+		if(w > epsilon) sum += w * V[idx];
+		if(1. - w > epsilon) sum += (1. - w) * V[idx + 1];
+		return sum;
+	}
+};
+
+// The device context; stands where the reference passes a LinearSolver
+// (SparseLUSolver, Bindings/Eigen.hpp:143-165).
+class B200Solver {
+	qpde_handle *h;
+public:
+	explicit B200Solver(int device = 0) : h(nullptr) {
+		if(qpde_create(device, &h) != QPDE_OK) {
+			throw std::runtime_error(std::string("QuantPDE_B200: ") + qpde_last_error(nullptr));
+		}
+	}
+	~B200Solver() { qpde_destroy(h); }
+	B200Solver(const B200Solver &) = delete;
+	B200Solver &operator=(const B200Solver &) = delete;
+	qpde_handle *handle() const { return h; }
+	void check(int rc) const {
+		if(rc != QPDE_OK) throw std::runtime_error(std::string("QuantPDE_B200: ") + qpde_last_error(h));
+	}
+};
+
+// ReverseConstantStepper(t0, T, dt) — Core/Stepper.hpp:27-36
+class ReverseConstantStepper : public Iteration {
+	Real t0, T, dt;
+	ToleranceIteration *inner;
+	int nExercise;
+	Payoff exercise;
+public:
+	ReverseConstantStepper(Real startTime, Real endTime, Real dt)
+			: t0(startTime), T(endTime), dt(dt), inner(nullptr), nExercise(0) {
+		if(startTime != 0.) throw std::invalid_argument("QuantPDE_B200: startTime must be 0");
+	}
+	void setInnerIteration(ToleranceIteration &it) { inner = &it; }   // IterativeMethod.hpp:977
+	// stepper.add(T / E * e, exerciseEvent, grid) for e = 0 .. E-1 (tutorial.cpp:103-114)
+	void addExerciseDates(int E, Payoff exerciseValue) { nExercise = E; exercise = std::move(exerciseValue); }
+
+	Real expiry() const { return T; }
+	Real timestep() const { return dt; }
+	int exerciseDates() const { return nExercise; }
+	const Payoff &exercisePayoff() const { return exercise; }
+	ToleranceIteration *innerIteration() const { return inner; }
+
+	// Iteration::solve(domain, initialCondition, root, solver) — IterativeMethod.hpp:1065-1079
+	inline Solution solve(const RectilinearGrid1 &grid, const Payoff &payoff, IterationNode &root,
+			B200Solver &solver);
+	friend class Batch;
+};
+
+////////////////////////////////////////////////////////////////////////////////
+// Batch — many solve() descriptions in one device sweep
+////////////////////////////////////////////////////////////////////////////////
+
+class Batch {
+	struct Item {
+		const RectilinearGrid1 *grid; Payoff payoff; IterationNode *root; ReverseConstantStepper *stepper;
+	};
+	std::vector<Item> items;
+public:
+	void add(ReverseConstantStepper &stepper, const RectilinearGrid1 &grid, Payoff payoff, IterationNode &root) {
+		items.push_back(Item{&grid, std::move(payoff), &root, &stepper});
+	}
+	size_t size() const { return items.size(); }
+
+	// Runs every added problem; results come back in order.
+	std::vector<Solution> solve(B200Solver &solver, int kernel = QPDE_KERNEL_AUTO) {
+		const int C = (int)items.size();
+		if(C == 0) return {};
+		// --- decode the first tree; the rest must have the same shape
+		auto decode = [] (IterationNode *root, const Discretization *&disc,
+				MinPenaltyMethodDifference1 *&pen) {
+			pen = dynamic_cast<MinPenaltyMethodDifference1 *>(root);
+			disc = pen ? &pen->constraint : dynamic_cast<const Discretization *>(root);
+			if(!disc) throw std::invalid_argument("QuantPDE_B200: unsupported root node");
+		};
+		const Discretization *d0; MinPenaltyMethodDifference1 *p0;
+		decode(items[0].root, d0, p0);
+		const int N = items[0].grid->size(), nAxis = items[0].grid->coarse().size();
+		const int refine = items[0].grid->refinement();
+		const bool american = p0 != nullptr;
+		const int nEx = items[0].stepper->exerciseDates();
+		ToleranceIteration *tol0 = items[0].stepper->innerIteration();
+		if(american && !tol0) throw std::invalid_argument("QuantPDE_B200: penalty root needs setInnerIteration()");
+
+		std::vector<Real> axis((size_t)C * nAxis), r(C), sig(C), q(C), T(C), dt(C), K(C), spot(C);
+		std::vector<Real> payArr, obsArr, sigArr;
+		int payKind = items[0].payoff.kind(), obsKind = american ? p0->obstacle.kind() : QPDE_PAYOFF_PUT;
+		int volModel = d0->op.v.model();
+		for(int c = 0; c < C; ++c) {
+			const Item &it = items[c];
+			const Discretization *d; MinPenaltyMethodDifference1 *p;
+			decode(it.root, d, p);
+			if(it.grid->size() != N || it.grid->coarse().size() != nAxis || it.grid->refinement() != refine
+					|| d->scheme != d0->scheme || (p != nullptr) != american
+					|| it.stepper->exerciseDates() != nEx || d->op.v.model() != volModel
+					|| it.payoff.kind() != payKind || (american && p->obstacle.kind() != obsKind)) {
+				throw std::invalid_argument("QuantPDE_B200: all problems of a batch must share grid size, "
+					"scheme, constraint type, payoff kind and volatility model");
+			}
+			for(int k = 0; k < nAxis; ++k) axis[(size_t)c * nAxis + k] = it.grid->coarse()[k];
+			r[c] = d->op.r; sig[c] = d->op.v.param(); q[c] = d->op.q;
+			T[c] = it.stepper->expiry(); dt[c] = it.stepper->timestep();
+			K[c] = it.payoff.kind() != QPDE_PAYOFF_ARRAY ? it.payoff.strike()
+				: (american && p->obstacle.kind() != QPDE_PAYOFF_ARRAY ? p->obstacle.strike()
+				: (nEx > 0 ? it.stepper->exercisePayoff().strike() : 0.));
+			spot[c] = K[c];
+			const bool needNodes = payKind == QPDE_PAYOFF_ARRAY || (american && obsKind == QPDE_PAYOFF_ARRAY)
+				|| volModel == QPDE_VOL_NODES;
+			if(needNodes) {
+				const std::vector<Real> S = it.grid->nodes();
+				if(payKind == QPDE_PAYOFF_ARRAY) for(Real s : S) payArr.push_back(it.payoff(s));
+				if(american && obsKind == QPDE_PAYOFF_ARRAY) for(Real s : S) obsArr.push_back(p->obstacle(s));
+				if(volModel == QPDE_VOL_NODES) for(Real s : S) sigArr.push_back(d->op.v(s));
+			}
+		}
+
+		qpde_bs1d_batch b = qpde_bs1d_batch();
+		b.abi_version = QPDE_ABI_VERSION;
+		b.n_contracts = C;
+		b.axis = axis.data(); b.axis_stride = nAxis; b.n_axis = nAxis; b.refine = refine;
+		b.r = r.data(); b.sigma = sig.data(); b.q = q.data();
+		b.vol_model = volModel;
+		if(volModel == QPDE_VOL_NODES) { b.sigma_nodes = sigArr.data(); b.sigma_nodes_stride = N; }
+		b.T = T.data(); b.dt = dt.data(); b.scheme = d0->scheme; b.max_steps = 0;
+		b.n_exercise = nEx;
+		b.exercise_kind = nEx > 0 ? items[0].stepper->exercisePayoff().kind() : QPDE_PAYOFF_K_MINUS_S;
+		b.strike = K.data();
+		b.payoff_kind = payKind; b.obstacle_kind = obsKind;
+		if(payKind == QPDE_PAYOFF_ARRAY) { b.payoff = payArr.data(); b.payoff_stride = N; }
+		if(american && obsKind == QPDE_PAYOFF_ARRAY) { b.obstacle = obsArr.data(); b.obstacle_stride = N; }
+		b.american = american ? 1 : 0;
+		b.max_inner = american ? tol0->maxIterations : 1;
+		b.tolerance = american ? tol0->tol : tolerance;
+		b.scale = american ? tol0->scl : scale;
+		b.penalty_tolerance = american ? p0->tol : tolerance;
+		b.spot = spot.data();
+		b.kernel = kernel;
+
+		int maxSteps = 0;
+		for(int c = 0; c < C; ++c) {
+			const int bound = (int)std::floor(T[c] / dt[c]) + 3 + 2 * nEx;
+			if(bound > maxSteps) maxSteps = bound;
+		}
+		std::vector<Real> V((size_t)C * N), S((size_t)C * N);
+		std::vector<int32_t> nSteps(C), status(C);
+		std::vector<uint8_t> inner((size_t)C * maxSteps), active((size_t)C * N);
+		qpde_bs1d_result res = qpde_bs1d_result();
+		res.V = V.data(); res.V_stride = N; res.S = S.data(); res.S_stride = N;
+		res.n_steps = nSteps.data(); res.status = status.data();
+		res.inner = inner.data(); res.inner_stride = maxSteps;
+		res.active = active.data(); res.active_stride = N;
+		solver.check(qpde_bs1d_sweep(solver.handle(), &b, &res));
+
+		std::vector<Solution> out;
+		for(int c = 0; c < C; ++c) {
+			const Item &it = items[c];
+			if(status[c] != 0) {
+				throw std::runtime_error("QuantPDE_B200: the penalty iteration of contract "
+					+ std::to_string(c) + " hit ToleranceIteration::maxIterations (the reference would not terminate)");
+			}
+			out.emplace_back(std::vector<Real>(S.begin() + (size_t)c * N, S.begin() + (size_t)(c + 1) * N),
+				std::vector<Real>(V.begin() + (size_t)c * N, V.begin() + (size_t)(c + 1) * N));
+			// iteration counts, as Iteration::iterations() reports them
+			it.stepper->its.assign(1, (size_t)nSteps[c]);
+			const Discretization *d; MinPenaltyMethodDifference1 *p;
+			decode(it.root, d, p);
+			if(p) {
+				ToleranceIteration *ti = it.stepper->innerIteration();
+				ti->its.clear();
+				for(int s = 0; s < nSteps[c]; ++s) ti->its.push_back(inner[(size_t)c * maxSteps + s]);
+				p->mask.assign(active.begin() + (size_t)c * N, active.begin() + (size_t)(c + 1) * N);
+			}
+		}
+		return out;
+	}
+};
+
+inline Solution ReverseConstantStepper::solve(const RectilinearGrid1 &grid, const Payoff &payoff,
+		IterationNode &root, B200Solver &solver) {
+	Batch batch;
+	batch.add(*this, grid, payoff, root);
+	return batch.solve(solver)[0];
+}
+
+} // namespace QuantPDE_B200
+
+#endif

@@ -81,9 +81,13 @@ def test_american_batch_vs_oracle(qpde, handle, oracle, kernel):
         iters_equal += int(np.array_equal(res.inner[c, :o["n_steps"]], o["inner"]))
         hard, tie = mask_mismatches(res.active[c], o["mask"], o["V"], np.maximum(K[c] - o["S"], 0.0))
         hard_total += hard; ties += tie
+        if o["n_steps"] == steps:
+            # no ~1e-16-long extra last step: the penalty gap V - obstacle is O(1e-8), no ties
+            assert tie == 0
         assert rel_err(res.value[c], oracle.interp(o["S"], o["V"], K[c])) <= REL_TOL
     assert worst <= REL_TOL, "worst node error %.3e" % worst
-    assert iters_equal == Cn and hard_total == 0 and ties <= Cn
+    assert iters_equal == Cn and hard_total == 0
+    print("active-set ties (within 64 ulp of the obstacle, see DESIGN.md): %d nodes" % ties)
 
 
 @pytest.mark.parametrize("kernel", KERNELS)
@@ -112,7 +116,9 @@ def test_full_size_properties(qpde, handle, oracle, kernel):
     assert np.all(res.status == 0)
     payoff = np.maximum(K[:, None] - res.S, 0.0)
     assert np.all(res.V >= payoff - 1e-6 * np.maximum(1.0, payoff))   # V >= obstacle - penalty slack
-    act = res.active.astype(np.int8)
+    # Without the reference's extra ~1e-16-long last step the active set of a put is a
+    # prefix in S; with it, V - obstacle collapses to rounding level and the set is noise.
+    act = res.active.astype(np.int8)[res.n_steps == steps]
     assert np.all(np.diff(act, axis=1) <= 0) and np.all(act[:, 0] == 1) and np.all(act[:, -1] == 0)
     assert np.all(res.n_steps >= steps) and np.all(res.n_steps <= steps + 1)
     for c in (0, 5):
