@@ -412,11 +412,11 @@ k_resident_sweep(DeviceBatch b, DeviceResult out) {
 		}
 		// (Re)build the system rows when the step kind or size changes.  h0 is a
 		// difference of accumulated times and moves in its last bits from step
-		// to step; such moves (relative 1e-14 or less) do not trigger a rebuild:
+		// to step (by ulp(t) / dt, ~1e-13 relative); moves below 1e-11 relative do not trigger a rebuild:
 		// the step is then taken with an h that is off by that relative amount,
-		// which perturbs the solution at the 1e-14 level (the reference itself
+		// which perturbs the solution at the 1e-13 level (the reference itself
 		// keeps a stale A for non-penalised roots, IterativeMethod.hpp:906).
-		if(kind != cur_kind || fabs(g.h - cur_h) > 1e-14 * cur_h) {
+		if(kind != cur_kind || fabs(g.h - cur_h) > 1e-11 * cur_h) {
 			cur_kind = kind; cur_h = g.h;
 #pragma unroll
 			for(int j = 0; j < M; ++j) {
