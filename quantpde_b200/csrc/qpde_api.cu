@@ -315,6 +315,7 @@ static int plan_create_impl(qpde_handle *h, const qpde_bs1d_batch *in,
 	b.american = in->american ? 1 : 0;
 	b.max_inner = in->max_inner;
 	b.tolerance = in->tolerance; b.scale = in->scale; b.penalty_tolerance = in->penalty_tolerance;
+	b.pen = in->american ? 1. / in->penalty_tolerance : 0.;
 
 	int max_steps = in->max_steps;
 	if(max_steps <= 0) {

@@ -25,6 +25,7 @@ struct DeviceBatch {
 	const double *obstacle; long long obstacle_stride;
 	int american, max_inner;
 	double tolerance, scale, penalty_tolerance;
+	double pen;   // 1 / penalty_tolerance (PenaltyMethod.hpp:85), formed on the host
 	const double *spot;
 };
 

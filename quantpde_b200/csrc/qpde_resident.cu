@@ -30,29 +30,33 @@
 //   Event<1>::_doEvent (exercise)            Core/Event.hpp:100-112
 #include <math_constants.h>
 
+#include <cstdlib>
+#include <cstring>
+
 #include "qpde_kernels.cuh"
 
 namespace qpde {
 
 namespace {
 
-constexpr int MAX_THREADS = 256; // 8 warps; M rows per thread (template) => N - 1 <= 256 M
-constexpr int MAX_WARPS = MAX_THREADS / 32;
-constexpr int L3_STAGES = 3;     // ceil(log2(MAX_WARPS))
+constexpr int MAX_WARPS = 16;    // PT <= 512 threads per CTA
 constexpr unsigned FULL = 0xffffffffu;
-constexpr int N_ROW_ARRAYS = 10; // S, lo, di, up, a, bd, c, na, me, nc
+__host__ __device__ constexpr int ilog2_ceil(int n) { return n <= 1 ? 0 : 1 + ilog2_ceil((n + 1) / 2); }
+constexpr int N_ROW_ARRAYS = 11; // S, lo, di, up, a, bd, c, na, me, nc, lb
 
-// Fixed part of the shared memory of one CTA.  The per-row arrays ([M][P]
+// Fixed part of the shared memory of one CTA.  The per-row arrays ([M][PT]
 // each, laid out [j][thread] so that a warp reading "row j of every thread"
-// touches consecutive doubles) and xlast / xfirst ([P + 1] each) follow it in
-// dynamic shared memory, sized by the actual thread count P.
+// touches consecutive doubles) and xlast / xfirst ([PT + 1] each) follow it in
+// dynamic shared memory.
 struct Smem {
 	// level 1/2 -> level 3 hand-over of the factorisation, one slot per warp
 	double f_Vs7[MAX_WARPS], f_Ws7[MAX_WARPS], f_V2l[MAX_WARPS], f_W2l[MAX_WARPS];
 	double f_V2f[MAX_WARPS], f_W2f[MAX_WARPS], f_a0[MAX_WARPS], f_Bp[MAX_WARPS], f_Ct[MAX_WARPS];
 	// right-hand-side hand-over
 	double s_G7[MAX_WARPS], s_G2l[MAX_WARPS], s_P0[MAX_WARPS], s_G2f[MAX_WARPS];
-	double S_tail, di_tail, ctail;
+	// the scalar "tail" equation (row N-1 when N = P M + 1); touched only by
+	// its owner, the last thread
+	struct Tail { double S, di, x, pz, bd, me, lb, invb, pq, vprev, c; } tail;
 	unsigned flags[2];
 };
 
@@ -77,47 +81,59 @@ __device__ __forceinline__ double rcp(double d) {
 	return y;
 }
 
-// Constants of relativeError's per-element test  |a-b| / max(scale,|a|,|b|) > tol
-// (Core/IterativeMethod.hpp:1125-1137).  Two cheap sufficient tests decide
-// almost every row; only rows inside the narrow band between them form the
-// reference's quotient, so the decision is always the reference's.
+// relativeError's per-element test  |a-b| / max(scale,|a|,|b|) > tol
+// (Core/IterativeMethod.hpp:1125-1137), decided per thread from two integer
+// maxima (the high words of max |a-b| and max |a| over the thread's rows):
+//   every |a-b| <= tol scale (1 - eps)                        => converged
+//   max |a-b| > tol (1 + eps) (max|a| + max|a-b| + scale)     => not converged
+// and only a thread that falls between the two forms the reference's quotients
+// row by row — so the decision is always the reference's.
 struct ConvTest {
-	double kap;      // d > kap (|x_old| + scale)  =>  d / den > tol        (den <= |x_old| + d)
-	double small;    // d <= small                 =>  d / den <= tol       (den >= scale)
-	double scale, tol;
-	__device__ __forceinline__ void init(double tol_, double scale_) {
-		tol = tol_; scale = scale_;
-		const double tp = tol_ * (1. + 4e-16);
-		kap = tp / (1. - tp) * (1. + 4e-16);
-		small = tol_ * scale_ * (1. - 4e-16);
+	__device__ __forceinline__ static void track(double xn, double xo, int &dmax_hi, int &xmax_hi) {
+		dmax_hi = max(dmax_hi, __double2hiint(fabs(xn - xo)));
+		xmax_hi = max(xmax_hi, __double2hiint(fabs(xn)));
 	}
-	__device__ __forceinline__ bool not_converged(double xn, double xo) const {
-		const double d = fabs(xn - xo);
-		if(d <= small) return false;
-		if(d > kap * (fabs(xo) + scale)) return true;
+	// 0: converged, 1: not converged, 2: undecided (run exact())
+	__device__ __forceinline__ static int screen(int dmax_hi, int xmax_hi, double tol, double scale) {
+		const double D_up = __hiloint2double(dmax_hi + 1, 0);   // > every |a-b|
+		if(D_up <= tol * scale * (1. - 8e-16)) return 0;
+		const double D_dn = __hiloint2double(dmax_hi, 0);       // <= max |a-b|
+		const double XN_up = __hiloint2double(xmax_hi + 1, 0);  // > every |a|
+		// den <= max(scale, |a| + |a-b|)
+		return D_dn > tol * (1. + 8e-16) * (XN_up + D_up + scale) ? 1 : 2;
+	}
+	__device__ __forceinline__ static bool exact(double xn, double xo, double tol, double scale) {
 		const double fa = fabs(xn), fb = fabs(xo);
 		double den = fa < fb ? fb : fa;
 		den = scale < den ? den : scale;
-		return d / den > tol;
+		return fabs(xn - xo) / den > tol;
 	}
 };
 
 } // namespace
 
-template <int M, bool AMERICAN, bool BDF2, bool EVENTS>
-__global__ void __launch_bounds__(MAX_THREADS, 1)
+template <int M, int PT, bool AMERICAN, bool BDF2, bool EVENTS>
+__global__ void __launch_bounds__(PT, 1)
 k_resident_sweep(DeviceBatch b, DeviceResult out) {
+	constexpr int P = PT;                    // blockDim.x == PT
+	constexpr int W = PT / 32;               // warps = level-3 unknowns
+	constexpr int L3_STAGES = ilog2_ceil(W);
+	static_assert(W <= MAX_WARPS && W <= 32, "too many warps");
 	extern __shared__ __align__(16) unsigned char smem_raw[];
 	Smem &sm = *reinterpret_cast<Smem *>(smem_raw);
 
 	const int cidx = blockIdx.x;
 	const int tid = threadIdx.x;
-	const int P = blockDim.x;
-	const int lane = tid & 31, warp = tid >> 5, W = P >> 5;
+	const int lane = tid & 31, warp = tid >> 5;
 	const int N = b.N;
-	const int n_main = N - 1;        // rows 0 .. N-2; row N-1 (decoupled, lo = 0) is the "tail"
+	// P M rows are available.  A grid of exactly P M + 1 nodes (2049 = 256 * 8 + 1)
+	// keeps its last row — diagonal-only in BlackScholes::A, BlackScholes.hpp:177-180 —
+	// as a scalar "tail" equation folded into row N-2 (last row of the last thread);
+	// smaller grids fit entirely and have no tail.
+	const bool has_tail = N == P * M + 1;
+	const int n_main = has_tail ? N - 1 : N;
 	const int i0 = tid * M;
-	const int MP = M * P;
+	constexpr int MP = M * P;
 
 	double *const sm_S  = reinterpret_cast<double *>(smem_raw + sizeof(Smem));
 	double *const sm_lo = sm_S + MP;   // operator rows of BlackScholes::A
@@ -129,12 +145,11 @@ k_resident_sweep(DeviceBatch b, DeviceResult out) {
 	double *const sm_na = sm_c + MP;   // right-hand-side rows of Crank-Nicolson: (0 - a, 1 - e, 0 - c)
 	double *const sm_me = sm_na + MP;
 	double *const sm_nc = sm_me + MP;
-	double *const sm_xlast = sm_nc + MP;        // [P + 1]: x of each thread's last row, shifted by one
+	double *const sm_lb = sm_nc + MP;  // right-hand side of the discretisation node (without penalty terms)
+	double *const sm_xlast = sm_lb + MP;        // [P + 1]: x of each thread's last row, shifted by one
 	double *const sm_xfirst = sm_xlast + P + 1; // [P + 1]: x of each thread's first row
 
-	const double pen = AMERICAN ? 1. / b.penalty_tolerance : 0.;   // PenaltyMethod.hpp:85
 	const double K = b.strike[cidx];
-	ConvTest conv; conv.init(b.tolerance, b.scale);
 
 	// ------------------------------------------------------------------
 	// Setup: refined grid -> shared memory, operator rows, payoff, obstacle
@@ -143,22 +158,22 @@ k_resident_sweep(DeviceBatch b, DeviceResult out) {
 		const double *axis = b.axis + (size_t)cidx * b.axis_stride;
 		for(int j = 0; j < M; ++j) {
 			const int i = i0 + j;
-			sm_S[j * P + tid] = i < N ? refined_node(axis, b.refine, i) : 0.;
+			sm_S[j * P + tid] = i < n_main ? refined_node(axis, b.refine, i) : 0.;
 		}
-		if(tid == 0) sm.S_tail = refined_node(axis, b.refine, N - 1);
+		if(tid == 0) sm.tail.S = has_tail ? refined_node(axis, b.refine, N - 1) : 0.;
 	}
 	__syncthreads();
 	auto S_at = [&] (int i) -> double {       // node i of the refined grid, 0 <= i < N
-		return i == N - 1 ? sm.S_tail : sm_S[(i % M) * P + (i / M)];
+		return i >= n_main ? sm.tail.S : sm_S[(i % M) * P + (i / M)];
 	};
 	{
 		const double r = b.r[cidx], q = b.q[cidx], sig = b.sigma[cidx];
 		for(int j = 0; j <= M; ++j) {
 			const bool tail = j == M;             // the tail row is handled by thread 0
-			if(tail && tid != 0) break;
+			if(tail && (tid != 0 || !has_tail)) break;
 			const int i = tail ? N - 1 : i0 + j;
 			Row row; row.lo = 0.; row.di = 0.; row.up = 0.;
-			if(i < N && (tail || i < n_main)) {
+			if(tail || i < n_main) {
 				const double Si = S_at(i);
 				const double Sm = i > 0 ? S_at(i - 1) : 0.;
 				const double Sp = i < N - 1 ? S_at(i + 1) : 0.;
@@ -167,7 +182,7 @@ k_resident_sweep(DeviceBatch b, DeviceResult out) {
 					: vol_value(b.vol_model, sig, Si);
 				row = bs_row(i, N, Sm, Si, Sp, r, v_i, q);
 			}
-			if(tail) sm.di_tail = row.di;
+			if(tail) sm.tail.di = row.di;
 			else { sm_lo[j * P + tid] = row.lo; sm_di[j * P + tid] = row.di; sm_up[j * P + tid] = row.up; }
 		}
 	}
@@ -175,19 +190,18 @@ k_resident_sweep(DeviceBatch b, DeviceResult out) {
 	// ---- per-thread state (registers) ---------------------------------
 	double x[M];        // current iterate / solution V^n
 	double pz[M];       // obstacle (AMERICAN) or exercise value (EVENTS)
-	double lb[M];       // right-hand side of the discretisation node
+	double rr[M];       // right-hand side lb + penalty terms for the current active set
 	double vprev[BDF2 ? M : 1]; // iterand(1) for BDF2
-	double x_tail, pz_tail = 0., bd_tail = 1., me_tail = 1., lb_tail = 0., vprev_tail = 0.;
 	double x_next;      // x of the next thread's first row
 	// cached factorisation
 	double f_m[M], f_invd[M], f_u[M], f_Vs[M], f_Ws[M];   // level 1 (index 0 unused)
 	double f_a0 = 0., f_c0 = 0.;
 	double f_al[5], f_ga[5], f_invB2 = 1., f_V2 = 0., f_W2 = 0.;   // level 2
-	double f_q1 = 0., f_q2 = 0., f_q3 = 0., f_al3[L3_STAGES], f_ga3[L3_STAGES], f_invB3 = 1.; // level 3 (lanes < W)
+	double f_q1 = 0., f_q2 = 0., f_q3 = 0., f_al3[L3_STAGES > 0 ? L3_STAGES : 1], f_ga3[L3_STAGES > 0 ? L3_STAGES : 1], f_invB3 = 1.; // level 3 (lanes < W)
 	unsigned curmask = 0, newmask = 0;  // bit j: row j penalised; bit M: tail row
-	// row N-2 couples to the tail row; its owner folds that coupling into the rhs
-	const int jl = tid == (n_main - 1) / M ? (n_main - 1) % M : -1;
-	double ctail = 0.;
+	// row N-2 (row M-1 of the last thread) couples to the tail row; that thread
+	// owns the tail equation and folds the coupling into its rhs.
+	const bool tail_owner = has_tail && tid == P - 1;
 
 	auto initial_value = [&] (int i) -> double {
 		return b.payoff_kind == QPDE_PAYOFF_ARRAY
@@ -210,17 +224,20 @@ k_resident_sweep(DeviceBatch b, DeviceResult out) {
 		pz[j] = real && (AMERICAN || EVENTS) ? obstacle_value(i) : -CUDART_INF;
 		if(BDF2) vprev[j] = 0.;
 		f_m[j] = 0.; f_invd[j] = 1.; f_u[j] = 0.; f_Vs[j] = 0.; f_Ws[j] = 0.;
-		lb[j] = 0.;
+		rr[j] = 0.;
 	}
-	x_tail = initial_value(N - 1);
-	if(AMERICAN || EVENTS) pz_tail = obstacle_value(N - 1);
+	if(tail_owner) {
+		sm.tail.x = initial_value(N - 1);
+		sm.tail.pz = AMERICAN || EVENTS ? obstacle_value(N - 1) : -CUDART_INF;
+		sm.tail.vprev = 0.; sm.tail.c = 0.; sm.tail.bd = 1.; sm.tail.me = 1.; sm.tail.invb = 1.; sm.tail.pq = 0.;
+	}
 	x_next = i0 + M < n_main ? initial_value(i0 + M) : 0.;
 	sm_xlast[tid + 1] = x[M - 1];
 	if(tid == 0) { sm_xlast[0] = 0.; sm.flags[0] = 0u; sm.flags[1] = 0u; }
 #pragma unroll
 	for(int s = 0; s < 5; ++s) { f_al[s] = 0.; f_ga[s] = 0.; }
 #pragma unroll
-	for(int s = 0; s < L3_STAGES; ++s) { f_al3[s] = 0.; f_ga3[s] = 0.; }
+	for(int s = 0; s < (L3_STAGES > 0 ? L3_STAGES : 1); ++s) { f_al3[s] = 0.; f_ga3[s] = 0.; }
 
 	// PenaltyMethod.hpp:45,61-66: row penalised iff (scale * (x - payoff)) < 0,
 	// i.e. iff x < payoff (scale > 0 and the difference of two distinct doubles
@@ -231,7 +248,7 @@ k_resident_sweep(DeviceBatch b, DeviceResult out) {
 		if(AMERICAN) { \
 			_Pragma("unroll") \
 			for(int j = 0; j < M; ++j) if(x[j] < pz[j]) mk_ |= 1u << j; \
-			if(x_tail < pz_tail) mk_ |= 1u << M; \
+			if(tail_owner && sm.tail.x < sm.tail.pz) mk_ |= 1u << M; \
 		} \
 		dst = mk_; \
 	} while(0)
@@ -278,45 +295,56 @@ k_resident_sweep(DeviceBatch b, DeviceResult out) {
 				const double aj = g.off(sm_lo[at]), ej = g.off(sm_di[at]);
 				double cj = g.off(sm_up[at]);
 				sm_na[at] = 0. - aj; sm_me[at] = 1. - ej; sm_nc[at] = 0. - cj;
-				if(j == jl) { ctail = cj; cj = 0.; }
+				if(j == M - 1 && tail_owner) { sm.tail.c = cj; cj = 0.; }
 				sm_a[at] = aj; sm_bd[at] = 1. + ej; sm_c[at] = cj;
 			}
-			const double et = g.off(sm.di_tail);
-			bd_tail = 1. + et; me_tail = 1. - et;
+			if(tail_owner) {
+				const double et = g.off(sm.tail.di);
+				sm.tail.bd = 1. + et; sm.tail.me = 1. - et;
+			}
 			refactor = true;
 			// rows are private to their thread: no barrier needed
 		}
 
-		// ---- lb = b(t) of the discretisation node (V^n = x) -------------
-		if(kind == STEP_IMPLICIT) {
+		// ---- lb = b(t) of the discretisation node (V^n = x), kept in shared
+		// memory; rr = lb + penalty terms of the current active set ----------
+		{
+			double lb[M];
+			if(kind == STEP_IMPLICIT) {
 #pragma unroll
-			for(int j = 0; j < M; ++j) lb[j] = x[j] + 0. * h0;
-			lb_tail = x_tail + 0. * h0;
-		} else if(BDF2 && kind == STEP_BDF2) {
+				for(int j = 0; j < M; ++j) lb[j] = x[j] + 0. * h0;
+				if(tail_owner) sm.tail.lb = sm.tail.x + 0. * h0;
+			} else if(BDF2 && kind == STEP_BDF2) {
 #pragma unroll
-			for(int j = 0; j < M; ++j) lb[j] = ((c1 * x[j] - c0 * vprev[j]) / den + 0.) * g.h;
-			lb_tail = ((c1 * x_tail - c0 * vprev_tail) / den + 0.) * g.h;
-		} else {
-			// (I - A h/2) V^n: row-major SpMV accumulated from zero in column order
-			const double xm = sm_xlast[tid];       // x of row i0 - 1
+				for(int j = 0; j < M; ++j) lb[j] = ((c1 * x[j] - c0 * vprev[j]) / den + 0.) * g.h;
+				if(tail_owner) sm.tail.lb = ((c1 * sm.tail.x - c0 * sm.tail.vprev) / den + 0.) * g.h;
+			} else {
+				// (I - A h/2) V^n: row-major SpMV accumulated from zero in column order
+				const double xm = sm_xlast[tid];       // x of row i0 - 1
+#pragma unroll
+				for(int j = 0; j < M; ++j) {
+					const int at = j * P + tid;
+					const double vm = j == 0 ? xm : x[j - 1];
+					const double vp = j == M - 1 ? x_next : x[j + 1];
+					double acc = 0.;
+					acc += sm_na[at] * vm;
+					acc += sm_me[at] * x[j];
+					acc += sm_nc[at] * vp;                      // vp = 0 for the tail owner's last row
+					if(j == M - 1 && tail_owner) acc += (0. - sm.tail.c) * sm.tail.x;
+					lb[j] = acc + 0.;
+				}
+				if(tail_owner) sm.tail.lb = (0. + sm.tail.me * sm.tail.x) + 0.;
+			}
 #pragma unroll
 			for(int j = 0; j < M; ++j) {
-				const int at = j * P + tid;
-				const double vm = j == 0 ? xm : x[j - 1];
-				const double vp = j == M - 1 ? x_next : x[j + 1];
-				double acc = 0.;
-				acc += sm_na[at] * vm;
-				acc += sm_me[at] * x[j];
-				acc += sm_nc[at] * vp;
-				if(j == jl) acc += (0. - ctail) * x_tail;   // sm_nc holds -up for this row: see below
-				lb[j] = acc + 0.;
+				sm_lb[j * P + tid] = lb[j];
+				rr[j] = AMERICAN && (curmask >> j & 1u) ? lb[j] + b.pen * pz[j] : lb[j];
 			}
-			lb_tail = (0. + me_tail * x_tail) + 0.;
 		}
 		if(BDF2) {
 #pragma unroll
 			for(int j = 0; j < M; ++j) vprev[j] = x[j];
-			vprev_tail = x_tail;
+			if(tail_owner) sm.tail.vprev = sm.tail.x;
 		}
 
 		int its = 0;
@@ -336,7 +364,15 @@ k_resident_sweep(DeviceBatch b, DeviceResult out) {
 					for(int j = 0; j < M; ++j) {
 						const int at = j * P + tid;
 						aa[j] = sm_a[at]; bb[j] = sm_bd[at]; cc[j] = sm_c[at];
-						if(AMERICAN && (curmask >> j & 1u)) bb[j] = bb[j] + pen * 1.;
+						const bool act = AMERICAN && (curmask >> j & 1u);
+						if(act) bb[j] = bb[j] + b.pen * 1.;
+						const double lbj = sm_lb[at];
+						rr[j] = act ? lbj + b.pen * pz[j] : lbj;      // PenaltyMethod.hpp:96-119
+					}
+					if(tail_owner) {
+						const bool act = AMERICAN && (curmask >> M & 1u);
+						sm.tail.invb = rcp(act ? sm.tail.bd + b.pen * 1. : sm.tail.bd);
+						sm.tail.pq = act ? b.pen * sm.tail.pz : 0.;
 					}
 					bb0 = bb[0]; f_a0 = aa[0]; f_c0 = cc[0];
 					f_invd[1] = rcp(bb[1]);
@@ -446,19 +482,17 @@ k_resident_sweep(DeviceBatch b, DeviceResult out) {
 			// ==============================================================
 			// right-hand side with penalty terms (PenaltyMethod.hpp:96-119); the
 			// tail row is a scalar equation, folded into row N-2
-			double bt = bd_tail, rt = lb_tail;
-			if(AMERICAN && (curmask >> M & 1u)) { bt = bt + pen * 1.; rt = fma(pen, pz_tail, rt); }
-			const double xt_new = rt / bt;
+			double xt_new = 0., r_last = rr[M - 1];
+			if(tail_owner) {
+				xt_new = (sm.tail.lb + sm.tail.pq) * sm.tail.invb;
+				r_last = fma(-sm.tail.c, xt_new, r_last);
+			}
 			double G[M];
 			double r0;
 			{
 				double r[M];
 #pragma unroll
-				for(int j = 0; j < M; ++j) {
-					r[j] = lb[j];
-					if(AMERICAN && (curmask >> j & 1u)) r[j] = fma(pen, pz[j], lb[j]);
-					if(j == jl) r[j] = fma(-ctail, xt_new, r[j]);
-				}
+				for(int j = 0; j < M; ++j) r[j] = j == M - 1 ? r_last : rr[j];
 				r0 = r[0];
 				// level 1: G = T^-1 r on the interior rows
 				G[1] = r[1];
@@ -503,16 +537,26 @@ k_resident_sweep(DeviceBatch b, DeviceResult out) {
 			const double ysep = lane == 0 ? Yw : fma(-Yn, f_W2, fma(-Yw, f_V2, G2));
 			double ynext = shfl_down(ysep, 1);
 			if(lane == 31) ynext = Yn;
-			bool nd = false;
-			if(AMERICAN) nd = conv.not_converged(ysep, x[0]) | conv.not_converged(xt_new, x_tail);
-			x[0] = ysep;
+			G[0] = ysep;
 #pragma unroll
-			for(int j = 1; j < M; ++j) {
-				const double xn = fma(-ynext, f_Ws[j], fma(-ysep, f_Vs[j], G[j]));
-				if(AMERICAN) nd = nd | conv.not_converged(xn, x[j]);
-				x[j] = xn;
+			for(int j = 1; j < M; ++j) G[j] = fma(-ynext, f_Ws[j], fma(-ysep, f_Vs[j], G[j]));
+			bool nd = false;
+			if(AMERICAN) {
+				int dmax_hi = 0, xmax_hi = 0;
+#pragma unroll
+				for(int j = 0; j < M; ++j) ConvTest::track(G[j], x[j], dmax_hi, xmax_hi);
+				if(tail_owner) ConvTest::track(xt_new, sm.tail.x, dmax_hi, xmax_hi);
+				const int verdict = ConvTest::screen(dmax_hi, xmax_hi, b.tolerance, b.scale);
+				nd = verdict == 1;
+				if(verdict == 2) {
+#pragma unroll
+					for(int j = 0; j < M; ++j) nd = nd | ConvTest::exact(G[j], x[j], b.tolerance, b.scale);
+					if(tail_owner) nd = nd | ConvTest::exact(xt_new, sm.tail.x, b.tolerance, b.scale);
+				}
 			}
-			x_tail = xt_new;
+#pragma unroll
+			for(int j = 0; j < M; ++j) x[j] = G[j];
+			if(tail_owner) sm.tail.x = xt_new;
 			x_next = ynext;
 			sm_xlast[tid + 1] = x[M - 1];
 			++its;
@@ -558,7 +602,7 @@ k_resident_sweep(DeviceBatch b, DeviceResult out) {
 				// Event<1>::_doEvent with max(V(S), K - S): Core/Event.hpp:100-112
 #pragma unroll
 				for(int j = 0; j < M; ++j) x[j] = x[j] > pz[j] ? x[j] : pz[j];
-				x_tail = x_tail > pz_tail ? x_tail : pz_tail;
+				if(tail_owner) sm.tail.x = sm.tail.x > sm.tail.pz ? sm.tail.x : sm.tail.pz;
 				sm_xfirst[tid] = x[0];
 				sm_xlast[tid + 1] = x[M - 1];
 				if(tid == 0) sm_xfirst[P] = 0.;
@@ -585,13 +629,16 @@ k_resident_sweep(DeviceBatch b, DeviceResult out) {
 			}
 		}
 	}
-	if(tid == 0) {
-		if(out.V) out.V[(size_t)cidx * out.V_stride + N - 1] = x_tail;
-		if(out.S) out.S[(size_t)cidx * out.S_stride + N - 1] = sm.S_tail;
+	__syncthreads();   // the tail owner's last writes to sm.tail become visible
+	if(tail_owner) {
+		if(out.V) out.V[(size_t)cidx * out.V_stride + N - 1] = sm.tail.x;
+		if(out.S) out.S[(size_t)cidx * out.S_stride + N - 1] = sm.tail.S;
 		if(out.active) {
-			const double pred = AMERICAN ? (0. + 1. * x_tail) - pz_tail : 0.;
+			const double pred = AMERICAN ? (0. + 1. * sm.tail.x) - sm.tail.pz : 0.;
 			out.active[(size_t)cidx * out.active_stride + N - 1] = pred < 0. ? 1 : 0;
 		}
+	}
+	if(tid == 0) {
 		if(out.n_steps) out.n_steps[cidx] = n_steps;
 		if(out.inner_total) out.inner_total[cidx] = inner_total;
 		if(out.status) out.status[cidx] = status;
@@ -600,15 +647,15 @@ k_resident_sweep(DeviceBatch b, DeviceResult out) {
 		// PiecewiseLinear::interpolate (Core/Interpolant.hpp:153-181,331-374):
 		// the thread owning the bracketing interval writes the value
 		const double s0 = b.spot ? b.spot[cidx] : K;
-		const double Sfirst = S_at(0), Slast = sm.S_tail;
+		const double Sfirst = S_at(0), Slast = S_at(N - 1);
 #pragma unroll
 		for(int j = 0; j < M; ++j) {
 			const int i = i0 + j;
-			if(i >= n_main) continue;
+			if(i >= N - 1) continue;              // intervals [S_i, S_{i+1}), i = 0 .. N-2
 			const double Si = sm_S[j * P + tid];
-			const double Sp = i + 1 == N - 1 ? sm.S_tail : S_at(i + 1);
+			const double Sp = S_at(i + 1);
 			const double vi = x[j];
-			const double vp = i + 1 == N - 1 ? x_tail : (j == M - 1 ? x_next : x[j + 1 < M ? j + 1 : j]);
+			const double vp = i + 1 >= n_main ? sm.tail.x : (j == M - 1 ? x_next : x[j + 1 < M ? j + 1 : j]);
 			bool mine = false; double wgt = 0.;
 			if(s0 <= Sfirst) { mine = i == 0; wgt = 1.; }
 			else if(s0 >= Slast) { mine = i == N - 2; wgt = 0.; }
@@ -623,57 +670,66 @@ k_resident_sweep(DeviceBatch b, DeviceResult out) {
 	}
 }
 
-// Rows per thread for a grid of N nodes: 8 up to 2049 nodes, 9 up to 2305.
-static int rows_per_thread(int N) {
-	const int n_main = N - 1;
-	if(n_main <= 8 * MAX_THREADS) return 8;
-	if(n_main <= 9 * MAX_THREADS) return 9;
+// Geometry (rows per thread M, threads PT) for a grid of N nodes.  P M rows are
+// available; a grid of P M + 1 nodes uses the tail equation.
+//   N <=  513: M = 8, PT =  64      N <= 2049: M = 8, PT = 256 (or M = 4, PT = 512)
+//   N <= 2305: M = 9, PT = 256
+static int pick_geometry(int N, int *M, int *PT) {
+	static const char *env = getenv("QPDE_RESIDENT_GEOMETRY");   // "4x512": A/B the wide variant
+	if(N <= 8 * 64 + 1)       { *M = 8; *PT = 64;  return 1; }
+	if(N <= 8 * 256 + 1) {
+		if(env && !strcmp(env, "4x512")) { *M = 4; *PT = 512; return 1; }
+		*M = 8; *PT = 256; return 1;
+	}
+	if(N <= 9 * 256 + 1)      { *M = 9; *PT = 256; return 1; }
 	return 0;
 }
 
 bool resident_supported(const DeviceBatch &b) {
+	int M, PT;
 	if(b.N < 10) return false;
-	if(rows_per_thread(b.N) == 0) return false;
+	if(!pick_geometry(b.N, &M, &PT)) return false;
 	if(b.american && b.n_exercise > 0) return false; // penalty + events: INTERLEAVED family
 	return true;
 }
 
-template <int M, bool AMERICAN, bool BDF2, bool EVENTS>
+template <int M, int PT, bool AMERICAN, bool BDF2, bool EVENTS>
 static int launch_variant(const DeviceBatch &b, const DeviceResult &out, cudaStream_t stream) {
-	auto kern = k_resident_sweep<M, AMERICAN, BDF2, EVENTS>;
-	const int n_main = b.N - 1;
-	int threads = (n_main + M - 1) / M;
-	threads = (threads + 31) / 32 * 32;
+	auto kern = k_resident_sweep<M, PT, AMERICAN, BDF2, EVENTS>;
 	static bool configured = false;
 	if(!configured) {
 		if(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
-				(int)smem_bytes(M, MAX_THREADS)) != cudaSuccess) {
+				(int)smem_bytes(M, PT)) != cudaSuccess) {
 			return QPDE_ERR_CUDA;
 		}
 		configured = true;
 	}
-	kern<<<b.C, threads, smem_bytes(M, threads), stream>>>(b, out);
+	kern<<<b.C, PT, smem_bytes(M, PT), stream>>>(b, out);
 	return QPDE_OK;
 }
 
-template <int M>
+template <int M, int PT>
 static int launch_rows(const DeviceBatch &b, const DeviceResult &out, cudaStream_t stream) {
 	const bool bdf2 = b.scheme == QPDE_SCHEME_BDF2;
 	const bool events = b.n_exercise > 0;
-	if(b.american) return bdf2 ? launch_variant<M, true, true, false>(b, out, stream)
-	                           : launch_variant<M, true, false, false>(b, out, stream);
-	if(events)     return bdf2 ? launch_variant<M, false, true, true>(b, out, stream)
-	                           : launch_variant<M, false, false, true>(b, out, stream);
-	return bdf2 ? launch_variant<M, false, true, false>(b, out, stream)
-	            : launch_variant<M, false, false, false>(b, out, stream);
+	if(b.american) return bdf2 ? launch_variant<M, PT, true, true, false>(b, out, stream)
+	                           : launch_variant<M, PT, true, false, false>(b, out, stream);
+	if(events)     return bdf2 ? launch_variant<M, PT, false, true, true>(b, out, stream)
+	                           : launch_variant<M, PT, false, false, true>(b, out, stream);
+	return bdf2 ? launch_variant<M, PT, false, true, false>(b, out, stream)
+	            : launch_variant<M, PT, false, false, false>(b, out, stream);
 }
 
 int launch_resident(const DeviceBatch &b, const DeviceResult &out, cudaStream_t stream,
 		int sm_count, long long *launches) {
 	(void)sm_count;
-	if(!resident_supported(b)) return QPDE_ERR_UNSUPPORTED;
-	const int rc = rows_per_thread(b.N) == 8 ? launch_rows<8>(b, out, stream)
-	                                         : launch_rows<9>(b, out, stream);
+	int M = 0, PT = 0;
+	if(!resident_supported(b) || !pick_geometry(b.N, &M, &PT)) return QPDE_ERR_UNSUPPORTED;
+	int rc;
+	if(M == 8 && PT == 64)       rc = launch_rows<8, 64>(b, out, stream);
+	else if(M == 8 && PT == 256) rc = launch_rows<8, 256>(b, out, stream);
+	else if(M == 4 && PT == 512) rc = launch_rows<4, 512>(b, out, stream);
+	else                         rc = launch_rows<9, 256>(b, out, stream);
 	if(rc == QPDE_OK) *launches += 1;
 	return rc;
 }
