@@ -162,6 +162,18 @@ typedef struct {
 	 * (Core/Interpolant.hpp:153-181,331-374); NULL = strike */
 	const double *spot;
 
+	/* --- HJB control: BlackScholes1(grid, Control1(grid), v, q) under
+	 * Min/MaxPolicyIteration1_1(grid, controlGrid, bs) attached to the
+	 * ToleranceIteration (Core/PolicyIteration.hpp:54-105,
+	 * examples/unequal_borrowing_lending_rates.cpp:108-138).  The interest rate
+	 * is the control; per inner iteration every node picks the control value
+	 * that minimises (maximises) (A(q) x - b(q))_i.  Needs scheme BDF1 or BDF2,
+	 * american = 0, n_exercise = 0; tolerance / scale / max_inner apply. */
+	int32_t n_controls;      /* 0 = r is not a control; else 2 .. 8          */
+	int32_t policy_max;      /* 1: MaxPolicyIteration1_1, 0: MinPolicyIteration1_1 */
+	const double *controls;  /* [C][n_controls] ticks of the control grid, in order */
+	int64_t controls_stride; /* 0 = one control grid shared by all contracts */
+
 	int32_t kernel;          /* QPDE_KERNEL_* (AUTO picks by N)             */
 	int32_t outputs;         /* split form only: QPDE_OUT_* mask of the outputs
 	                            to keep on the device; 0 = all.  The one-shot

@@ -35,7 +35,10 @@ class Problem(C.Structure):
                 ("obstacle", C.POINTER(C.c_double)),
                 ("tolerance", C.c_double), ("scale", C.c_double),
                 ("penalty_tol", C.c_double), ("max_inner", C.c_int),
-                ("event_obstacle", C.POINTER(C.c_double)), ("solver", C.c_int)]
+                ("event_obstacle", C.POINTER(C.c_double)),
+                ("n_controls", C.c_int), ("policy_max", C.c_int),
+                ("plo", C.POINTER(C.c_double)), ("pdi", C.POINTER(C.c_double)),
+                ("pup", C.POINTER(C.c_double)), ("solver", C.c_int)]
 
 
 _lib = None
@@ -127,8 +130,10 @@ def interp(x, v, c):
 
 def sweep(S, lo, di, up, v0, T, steps, n_steps, scheme="rannacher",
           american=False, obstacle=None, event_obstacle=None,
-          tolerance=1e-6, scale=1.0, penalty_tol=1e-6, max_inner=1000, solver=0):
-    """Returns dict(V, inner, mask, status)."""
+          tolerance=1e-6, scale=1.0, penalty_tol=1e-6, max_inner=1000, solver=0,
+          policy_rows=None, policy_max=False):
+    """Returns dict(V, inner, mask, status).  policy_rows = (lo, di, up), each
+    [n_controls][n]: PolicyIteration over the controls."""
     n = len(S)
     arrs = [np.ascontiguousarray(a, dtype=np.float64) for a in (S, lo, di, up, v0)]
     p = Problem()
@@ -147,6 +152,11 @@ def sweep(S, lo, di, up, v0, T, steps, n_steps, scheme="rannacher",
         p.event_obstacle = _dp(event_obstacle)
     p.tolerance, p.scale, p.penalty_tol, p.max_inner = tolerance, scale, penalty_tol, max_inner
     p.solver = solver
+    if policy_rows is not None:
+        prs = [np.ascontiguousarray(a, dtype=np.float64) for a in policy_rows]
+        p.n_controls = prs[0].shape[0]
+        p.policy_max = int(policy_max)
+        p.plo, p.pdi, p.pup = [_dp(a) for a in prs]
     V = np.zeros(n)
     inner = np.zeros(n_steps, dtype=np.int32)
     mask = np.zeros(n, dtype=np.uint8)
@@ -181,6 +191,21 @@ def bermudan_put(K, r, alpha, T, n_steps, E, refine_times, q=0.0, scheme="bdf2")
     steps, n = schedule(T, T / n_steps, ev)
     out = sweep(S, lo, di, up, payoff, T, steps, n, scheme=scheme,
                 american=False, obstacle=payoff, event_obstacle=K - S)
+    out["S"] = S
+    out["n_steps"] = n
+    return out
+
+
+def hjb_straddle(K, r_l, r_b, vol, T, n_steps, refine_times, q=0.0, long_position=False,
+                 scheme="bdf2", solver=0):
+    """The unequal_borrowing_lending_rates.cpp wiring on the oracle."""
+    S = vanilla_grid(K, K, refine_times)
+    rows = [bs_coeffs(S, r, vol, q) for r in (r_l, r_b)]
+    plo, pdi, pup = [np.stack([rw[k] for rw in rows]) for k in range(3)]
+    payoff = np.where(S < K, K - S, S - K)
+    steps, n = schedule(T, T / n_steps)
+    out = sweep(S, rows[0][0], rows[0][1], rows[0][2], payoff, T, steps, n, scheme=scheme,
+                policy_rows=(plo, pdi, pup), policy_max=long_position, solver=solver)
     out["S"] = S
     out["n_steps"] = n
     return out

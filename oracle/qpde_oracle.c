@@ -443,9 +443,53 @@ int qpo_sweep_1d(const qpo_problem *p, double *V, int *inner,
 				}
 			}
 		}
-		(void)hA;
 
-		if(!p->american) {
+		if(p->n_controls > 0) {
+			/* ToleranceIteration over PolicyIteration<1,1,Max>
+			 * (PolicyIteration.hpp:54-105) under BDFOne / BDFTwo: the root's
+			 * A is I + hA * bs.A(control), b is the BDF right-hand side.  The
+			 * discretisation node's isATheSame() is false because its operator
+			 * (the policy node) keeps LinearSystem's default. */
+			if(use_cn) { status = 2; break; }   /* not restated: theta schemes re-evaluate A(t0) */
+			memcpy(x, v1, sizeof(double) * (size_t)n);
+			do {
+				memcpy(xprev, x, sizeof(double) * (size_t)n);
+				for(i = 0; i < n; ++i) {
+					int k, best_k = 0;
+					double best = p->policy_max ? -INFINITY : INFINITY;
+					for(k = 0; k < p->n_controls; ++k) {
+						const double *lo_k = p->plo + (size_t)k * n;
+						const double *di_k = p->pdi + (size_t)k * n;
+						const double *up_k = p->pup + (size_t)k * n;
+						/* candidate = A(q) x - b(q): SpMV row from zero in column
+						 * order over the stored entries, then minus b = 0 */
+						double acc = 0., cand;
+						if(i > 0 && i < n - 1) acc += lo_k[i] * xprev[i - 1];
+						acc += di_k[i] * xprev[i];
+						if(i > 0 && i < n - 1) acc += up_k[i] * xprev[i + 1];
+						cand = acc - 0.;
+						if(p->policy_max ? cand > best : cand < best) { best = cand; best_k = k; }
+					}
+					{
+						const double l = p->plo[(size_t)best_k * n + i];
+						const double d = p->pdi[(size_t)best_k * n + i];
+						const double u = p->pup[(size_t)best_k * n + i];
+						if(use_bdf2) { A_lo[i] = hA * l; A_di[i] = 1. + hA * d; A_up[i] = hA * u; }
+						else         { A_lo[i] = l * hA; A_di[i] = 1. + d * hA; A_up[i] = u * hA; }
+					}
+				}
+				memcpy(x, lb, sizeof(double) * (size_t)n);
+				if(p->solver) {
+					thomas_model(n, A_lo, A_di, A_up, x, P_di, rhs);
+				} else {
+					tri_factor(&lu, A_lo, A_di, A_up);
+					tri_solve(&lu, x);
+				}
+				++its;
+				notdone = relative_error(n, x, xprev, p->scale) > p->tolerance;
+				if(notdone && its >= p->max_inner) { status = 1; break; }
+			} while(notdone);
+		} else if(!p->american) {
 			/* IterativeMethod.hpp:899-917 */
 			if(!initialized || !a_same) {
 				memcpy(A_lo, M_lo, sizeof(double) * (size_t)n);

@@ -75,12 +75,16 @@ typedef struct {
 	int max_inner;         /* guard (the reference has none)               */
 	const double *event_obstacle; /* [n] or NULL: at each user event
 	                          V = max(V, event_obstacle) (tutorial.cpp:103-105) */
+	int n_controls;        /* > 0: PolicyIteration over this many control values */
+	int policy_max;        /* 1: MaxPolicyIteration, 0: MinPolicyIteration */
+	const double *plo, *pdi, *pup; /* [n_controls][n] operator rows per control */
 	int solver;            /* 0: pivoted LU (the reference's policy);
 	                          1: arithmetic model of the INTERLEAVED kernel   */
 } qpo_problem;
 
 /* Runs the sweep.  V [n] out; inner [n_steps] out (may be NULL); mask [n] out
- * (may be NULL).  Returns 0, or 1 if some step hit max_inner. */
+ * (may be NULL).  Returns 0, 1 if some step hit max_inner, 2 if the
+ * combination is not restated (policy iteration under a theta scheme). */
 int qpo_sweep_1d(const qpo_problem *p, double *V, int *inner,
 		unsigned char *mask);
 

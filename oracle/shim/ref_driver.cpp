@@ -254,12 +254,80 @@ int runBermudan(const Args &a) {
 	return 0;
 }
 
+////////////////////////////////////////////////////////////////////////////////
+// hjb: unequal borrowing / lending rates.  The interest rate is a control with
+// values {r_l, r_b}; Min/MaxPolicyIteration1_1 inside a ToleranceIteration,
+// BDF2 (or BDF1) time stepping, straddle payoff.
+////////////////////////////////////////////////////////////////////////////////
+
+int runHjb(const Args &a) {
+	const Real K = num(a, "K", 100.), S0 = num(a, "S0", K);
+	const Real r_l = num(a, "r_l", .03), r_b = num(a, "r_b", .05);
+	const Real vol = num(a, "vol", .3), q = num(a, "q", 0.), T = num(a, "T", 1.);
+	const long steps = integer(a, "steps", 12);
+	const int refine = (int) integer(a, "refine", 0);
+	const bool long_position = integer(a, "long", 0) != 0;
+	const std::string scheme = str(a, "scheme", "bdf2");
+	const int repeat = (int) integer(a, "repeat", 1);
+
+	RectilinearGrid1 coarse( baseAxis(str(a, "axis", "special"), S0, K) );
+	auto grid = coarse.refined(refine);
+	RectilinearGrid1 controls( Axis { r_l, r_b } );
+	auto payoff = straddlePayoff(K);
+
+	double seconds = 0.;
+	std::vector<double> values;
+	std::vector<long> inner;
+	long timesteps = 0;
+
+	for(int rep = 0; rep < repeat; ++rep) {
+		ReverseConstantStepper stepper(0., T, T / steps);
+		ToleranceIteration tolerance;
+		stepper.setInnerIteration(tolerance);
+
+		BlackScholes1 bs(grid, Control1(grid), vol, q);
+
+		std::unique_ptr<IterationNode> policy(long_position
+			? (IterationNode *) new MaxPolicyIteration1_1(grid, controls, bs)
+			: (IterationNode *) new MinPolicyIteration1_1(grid, controls, bs));
+		policy->setIteration(tolerance);
+
+		std::unique_ptr<IterationNode> discretization;
+		if(scheme == "bdf2") discretization.reset(new ReverseBDFTwo(grid, *policy));
+		else                 discretization.reset(new ReverseBDFOne(grid, *policy));
+		discretization->setIteration(stepper);
+
+		SparseLUSolver solver;
+
+		auto begin = std::chrono::steady_clock::now();
+		auto solution = stepper.solve(grid, payoff, *discretization, solver);
+		auto end = std::chrono::steady_clock::now();
+		seconds += std::chrono::duration<double>(end - begin).count();
+
+		if(rep == 0) {
+			values = nodeValues(grid, solution);
+			timesteps = (long) stepper.iterations()[0];
+			for(auto k : tolerance.iterations()) inner.push_back((long)k);
+			std::printf("value %a\n", (double) solution(S0));
+		}
+	}
+
+	std::printf("seconds %.9g\n", seconds / repeat);
+	std::printf("steps %ld\n", timesteps);
+	dumpReals("S", nodes(grid));
+	dumpReals("V", values);
+	dumpInts("inner", inner);
+	return 0;
+}
+
 void usage() {
 	std::fprintf(stderr,
 		"qpde_ref vanilla  K= S0= r= vol= q= T= steps= refine= american=0|1 "
 		"call=0|1 scheme=rannacher|cn|bdf1|bdf2 axis=special|tutorial repeat=\n"
 		"qpde_ref bermudan K= r= alpha= q= T= steps= E= refine= "
-		"scheme=bdf2|bdf1|rannacher|cn axis= repeat=\n");
+		"scheme=bdf2|bdf1|rannacher|cn axis= repeat=\n"
+		"qpde_ref hjb      K= S0= r_l= r_b= vol= q= T= steps= refine= long=0|1 "
+		"scheme=bdf2|bdf1 repeat=\n");
 }
 
 } // namespace
@@ -276,6 +344,7 @@ int main(int argc, char **argv) {
 	const std::string mode(argv[1]);
 	if(mode == "vanilla")  return runVanilla(a);
 	if(mode == "bermudan") return runBermudan(a);
+	if(mode == "hjb")      return runHjb(a);
 	usage();
 	return 2;
 }

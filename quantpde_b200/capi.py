@@ -52,6 +52,8 @@ class Batch(C.Structure):
         ("american", C.c_int32), ("max_inner", C.c_int32),
         ("tolerance", C.c_double), ("scale", C.c_double), ("penalty_tolerance", C.c_double),
         ("spot", _dp),
+        ("n_controls", C.c_int32), ("policy_max", C.c_int32),
+        ("controls", _dp), ("controls_stride", C.c_int64),
         ("kernel", C.c_int32), ("outputs", C.c_int32),
     ]
 
@@ -194,7 +196,7 @@ class BatchSpec:
                  obstacle_array=None, vol_model="const", sigma_nodes=None,
                  n_exercise=0, exercise="k_minus_s", spot=None, tolerance=1e-6, scale=1.0,
                  penalty_tolerance=1e-6, max_inner=100, kernel="auto", outputs=OUT_ALL,
-                 n_contracts=None):
+                 n_contracts=None, controls=None, policy_max=False):
         axis = np.ascontiguousarray(axis, dtype=np.float64)
         if n_contracts is None:
             n_contracts = axis.shape[0] if axis.ndim == 2 else len(np.atleast_1d(strike))
@@ -245,6 +247,13 @@ class BatchSpec:
         b.tolerance, b.scale, b.penalty_tolerance = tolerance, scale, penalty_tolerance
         if spot is not None:
             b.spot = vec(spot)
+        if controls is not None:
+            ctl = np.ascontiguousarray(controls, dtype=np.float64)
+            self.keep.append(ctl)
+            b.controls = ctl.ctypes.data_as(_dp)
+            b.controls_stride = ctl.shape[1] if ctl.ndim == 2 else 0
+            b.n_controls = ctl.shape[-1]
+            b.policy_max = int(bool(policy_max))
         b.kernel = KERNEL[kernel]
         b.outputs = int(outputs)
         self.struct = b

@@ -287,6 +287,18 @@ static int plan_create_impl(qpde_handle *h, const qpde_bs1d_batch *in,
 		}
 		if(in->max_inner < 1) return fail(h, QPDE_ERR_INVALID, "max_inner must be >= 1");
 	}
+	if(in->n_controls != 0) {
+		if(in->n_controls < 2 || in->n_controls > 8) return fail(h, QPDE_ERR_INVALID, "n_controls must be 0 or 2 .. 8");
+		if(!in->controls) return fail(h, QPDE_ERR_INVALID, "controls required");
+		if(in->controls_stride != 0 && in->controls_stride < in->n_controls) return fail(h, QPDE_ERR_INVALID, "controls_stride < n_controls");
+		if(in->american || in->n_exercise > 0) return fail(h, QPDE_ERR_UNSUPPORTED, "policy iteration with a penalty constraint or events is not supported");
+		if(in->scheme != QPDE_SCHEME_BDF1 && in->scheme != QPDE_SCHEME_BDF2) {
+			return fail(h, QPDE_ERR_UNSUPPORTED, "policy iteration needs scheme BDF1 or BDF2 (theta schemes re-evaluate A(t0) under the current control)");
+		}
+		if(!(in->tolerance > 0.) || !(in->scale > 0.) || in->max_inner < 1) {
+			return fail(h, QPDE_ERR_INVALID, "policy iteration: tolerance, scale > 0 and max_inner >= 1 required");
+		}
+	}
 	if(in->n_exercise < 0) return fail(h, QPDE_ERR_INVALID, "n_exercise < 0");
 	if(in->n_exercise > 0 && !is_generator(in->exercise_kind)) return fail(h, QPDE_ERR_INVALID, "exercise_kind must be a generator");
 	for(int c = 0; c < C; ++c) {
@@ -316,6 +328,7 @@ static int plan_create_impl(qpde_handle *h, const qpde_bs1d_batch *in,
 	b.max_inner = in->max_inner;
 	b.tolerance = in->tolerance; b.scale = in->scale; b.penalty_tolerance = in->penalty_tolerance;
 	b.pen = in->american ? 1. / in->penalty_tolerance : 0.;
+	b.n_controls = in->n_controls; b.policy_max = in->policy_max ? 1 : 0;
 
 	int max_steps = in->max_steps;
 	if(max_steps <= 0) {
@@ -337,6 +350,9 @@ static int plan_create_impl(qpde_handle *h, const qpde_bs1d_batch *in,
 	if(in->strike) QPDE_TRY(upload_vec(p, in->strike, C, &b.strike));
 	else           QPDE_TRY(upload_vec(p, in->spot, C, &b.strike));
 	if(in->spot) QPDE_TRY(upload_vec(p, in->spot, C, &b.spot));
+	if(in->n_controls > 0) {
+		QPDE_TRY(upload_rows(p, in->controls, in->controls_stride, C, in->n_controls, &b.controls, &b.controls_stride));
+	}
 	if(in->vol_model == QPDE_VOL_NODES) {
 		QPDE_TRY(upload_rows(p, in->sigma_nodes, in->sigma_nodes_stride ? in->sigma_nodes_stride : 0,
 			C, N, &b.sigma_nodes, &b.sigma_nodes_stride));
@@ -378,8 +394,9 @@ static int plan_create_impl(qpde_handle *h, const qpde_bs1d_batch *in,
 	if(kernel == QPDE_KERNEL_INTERLEAVED) {
 		const size_t NC = (size_t)N * C;
 		InterleavedWork &w = p->w;
-		QPDE_TRY(dev_alloc(p, &w.S, NC));  QPDE_TRY(dev_alloc(p, &w.lo, NC));
-		QPDE_TRY(dev_alloc(p, &w.di, NC)); QPDE_TRY(dev_alloc(p, &w.up, NC));
+		const size_t sets = b.n_controls > 0 ? (size_t)b.n_controls : 1;   // operator rows per control value
+		QPDE_TRY(dev_alloc(p, &w.S, NC));  QPDE_TRY(dev_alloc(p, &w.lo, NC * sets));
+		QPDE_TRY(dev_alloc(p, &w.di, NC * sets)); QPDE_TRY(dev_alloc(p, &w.up, NC * sets));
 		QPDE_TRY(dev_alloc(p, &w.x, NC));  QPDE_TRY(dev_alloc(p, &w.lb, NC));
 		QPDE_TRY(dev_alloc(p, &w.cp, NC)); QPDE_TRY(dev_alloc(p, &w.dp, NC));
 		if(b.scheme == QPDE_SCHEME_BDF2) QPDE_TRY(dev_alloc(p, &w.xprev, NC));

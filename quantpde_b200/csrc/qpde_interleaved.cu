@@ -16,6 +16,8 @@
 // Algorithmic HBM bytes per inner solve and node: reads lo, di,
 // up, lb, obstacle, x_old (48 B) + writes cp, dp (16 B) in the forward pass;
 // reads cp, dp, x_old (24 B) + writes x_new (8 B) in the backward pass.
+#include <math_constants.h>
+
 #include "qpde_kernels.cuh"
 
 namespace qpde {
@@ -40,9 +42,19 @@ __global__ void k_interleaved_setup(DeviceBatch b, InterleavedWork w) {
 		const double v_i = b.vol_model == QPDE_VOL_NODES
 			? b.sigma_nodes[(size_t)c * b.sigma_nodes_stride + i]
 			: vol_value(b.vol_model, sig, Si);
-		const Row row = bs_row(i, N, Sm, Si, Sp, r, v_i, q);
 		w.S[at] = Si;
-		w.lo[at] = row.lo; w.di[at] = row.di; w.up[at] = row.up;
+		if(b.n_controls > 0) {
+			// one set of operator rows per control value of the interest rate
+			for(int k = 0; k < b.n_controls; ++k) {
+				const double rk = b.controls[(size_t)c * b.controls_stride + k];
+				const Row row = bs_row(i, N, Sm, Si, Sp, rk, v_i, q);
+				const size_t ak = ((size_t)k * N + i) * C + c;
+				w.lo[ak] = row.lo; w.di[ak] = row.di; w.up[ak] = row.up;
+			}
+		} else {
+			const Row row = bs_row(i, N, Sm, Si, Sp, r, v_i, q);
+			w.lo[at] = row.lo; w.di[at] = row.di; w.up[at] = row.up;
+		}
 		w.x[at] = b.payoff_kind == QPDE_PAYOFF_ARRAY
 			? b.payoff[(size_t)c * b.payoff_stride + i]
 			: payoff_value(b.payoff_kind, Si, K);
@@ -74,6 +86,9 @@ k_interleaved_sweep(DeviceBatch b, InterleavedWork w, DeviceResult out) {
 	const double *ob = w.obst ? w.obst + c : nullptr;
 	const double *evob = w.evobst ? w.evobst + c : nullptr;
 
+	const bool policy = b.n_controls > 0;
+	const bool iterate = b.american || policy;   // a ToleranceIteration wraps every step
+	const size_t NC = (size_t)N * C;
 	Replay rp; rp.start(b.T[c], b.dt[c], b.n_exercise);
 	NodeState ns; ns.start(b.scheme);
 	double time1 = rp.T, time0 = rp.T; // times of iterand(0), iterand(1)
@@ -95,7 +110,8 @@ k_interleaved_sweep(DeviceBatch b, InterleavedWork w, DeviceResult out) {
 			c1 = hh0 / h1; c0 = h1 / hh0; den = hh0 - h1;
 		}
 		// IterativeMethod.hpp:906: re-assemble A unless the root says it is the same
-		if(b.american || !ns.initialized || !ns.a_same(st.same_dt)) gA = gb;
+		// (a penalty or policy node in the tree keeps LinearSystem's default: never)
+		if(iterate || !ns.initialized || !ns.a_same(st.same_dt)) gA = gb;
 
 		// ---- lb = root.b(t) of the discretisation node ------------------
 		// x holds iterand(0) = V^n, xp holds iterand(1) for BDF2.
@@ -132,11 +148,29 @@ k_interleaved_sweep(DeviceBatch b, InterleavedWork w, DeviceResult out) {
 		do {
 			// ---- forward elimination of (lA + P) x = lb + P obstacle ------
 			double cprev = 0., dprev = 0.;
+			double xm = 0., xi = x[0], xq = N > 1 ? x[C] : 0.;   // previous iterate around node i
 			for(int i = 0; i < N; ++i) {
 				const size_t at = (size_t)i * C;
-				double a_i = gA.off(lo[at]);
-				double b_i = 1. + gA.off(di[at]);
-				double c_i = gA.off(up[at]);
+				size_t rows = at;
+				if(policy) {
+					// PolicyIteration::onIterationStart (PolicyIteration.hpp:54-105):
+					// candidate = (A(q) x - b(q))_i per control value, strict order
+					double best = b.policy_max ? -CUDART_INF : CUDART_INF;
+					for(int k = 0; k < b.n_controls; ++k) {
+						const size_t ak = (size_t)k * NC + at;
+						double acc = 0.;
+						if(i > 0 && i < N - 1) acc += lo[ak] * xm;
+						acc += di[ak] * xi;
+						if(i > 0 && i < N - 1) acc += up[ak] * xq;
+						const double cand = acc - 0.;
+						if(b.policy_max ? cand > best : cand < best) { best = cand; rows = ak; }
+					}
+					xm = xi; xi = xq;
+					xq = i + 2 < N ? x[at + 2 * C] : 0.;
+				}
+				double a_i = gA.off(lo[rows]);
+				double b_i = 1. + gA.off(di[rows]);
+				double c_i = gA.off(up[rows]);
 				double rhs = lb[at];
 				if(b.american) {
 					// PenaltyMethod.hpp:45,61-68: predicate on the previous iterand
@@ -155,7 +189,7 @@ k_interleaved_sweep(DeviceBatch b, InterleavedWork w, DeviceResult out) {
 			for(int i = N - 1; i >= 0; --i) {
 				const size_t at = (size_t)i * C;
 				xn = dp[at] - cp[at] * xn;
-				if(b.american) {
+				if(iterate) {
 					const double xo = x[at];
 					const double fa = fabs(xn), fb = fabs(xo);
 					double d = fa < fb ? fb : fa;
@@ -165,7 +199,7 @@ k_interleaved_sweep(DeviceBatch b, InterleavedWork w, DeviceResult out) {
 				x[at] = xn;
 			}
 			++its;
-			again = b.american && notdone;
+			again = iterate && notdone;
 			if(again && its >= b.max_inner) { status = 1; again = false; }
 		} while(again);
 

@@ -27,6 +27,8 @@ struct DeviceBatch {
 	double tolerance, scale, penalty_tolerance;
 	double pen;   // 1 / penalty_tolerance (PenaltyMethod.hpp:85), formed on the host
 	const double *spot;
+	int n_controls, policy_max;
+	const double *controls; long long controls_stride;
 };
 
 // Device output buffers (contract-major); any pointer may be null.

@@ -34,14 +34,13 @@
 #include <cstring>
 
 #include "qpde_kernels.cuh"
+#include "qpde_partition.cuh"
 
 namespace qpde {
 
 namespace {
 
-constexpr int MAX_WARPS = 16;    // PT <= 512 threads per CTA
-constexpr unsigned FULL = 0xffffffffu;
-__host__ __device__ constexpr int ilog2_ceil(int n) { return n <= 1 ? 0 : 1 + ilog2_ceil((n + 1) / 2); }
+constexpr unsigned FULL = FULL_MASK;
 constexpr int N_ROW_ARRAYS = 11; // S, lo, di, up, a, bd, c, na, me, nc, lb
 
 // Fixed part of the shared memory of one CTA.  The per-row arrays ([M][PT]
@@ -49,11 +48,7 @@ constexpr int N_ROW_ARRAYS = 11; // S, lo, di, up, a, bd, c, na, me, nc, lb
 // touches consecutive doubles) and xlast / xfirst ([PT + 1] each) follow it in
 // dynamic shared memory.
 struct Smem {
-	// level 1/2 -> level 3 hand-over of the factorisation, one slot per warp
-	double f_Vs7[MAX_WARPS], f_Ws7[MAX_WARPS], f_V2l[MAX_WARPS], f_W2l[MAX_WARPS];
-	double f_V2f[MAX_WARPS], f_W2f[MAX_WARPS], f_a0[MAX_WARPS], f_Bp[MAX_WARPS], f_Ct[MAX_WARPS];
-	// right-hand-side hand-over
-	double s_G7[MAX_WARPS], s_G2l[MAX_WARPS], s_P0[MAX_WARPS], s_G2f[MAX_WARPS];
+	PartitionSmem ps;   // hand-over between the warps of the partition solve
 	// the scalar "tail" equation (row N-1 when N = P M + 1); touched only by
 	// its owner, the last thread
 	struct Tail { double S, di, x, pz, bd, me, lb, invb, pq, vprev, c; } tail;
@@ -62,23 +57,6 @@ struct Smem {
 
 inline size_t smem_bytes(int M, int P) {
 	return sizeof(Smem) + sizeof(double) * ((size_t)N_ROW_ARRAYS * M * P + 2 * (P + 1));
-}
-
-__device__ __forceinline__ double shfl_up(double v, int d) { return __shfl_up_sync(FULL, v, d); }
-__device__ __forceinline__ double shfl_down(double v, int d) { return __shfl_down_sync(FULL, v, d); }
-__device__ __forceinline__ double shfl_idx(double v, int l) { return __shfl_sync(FULL, v, l); }
-
-// 1 / d for the factorisation: hardware seed (MUFU.RCP64H, ~2^-22) plus two
-// Newton steps => error below one ulp.  The factors need no more: any
-// elimination order already moves the solution by a few ulp.
-__device__ __forceinline__ double rcp(double d) {
-	double y;
-	asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(d));
-	double e = fma(-d, y, 1.);
-	y = fma(y, e, y);
-	e = fma(-d, y, 1.);
-	y = fma(y, e, y);
-	return y;
 }
 
 // relativeError's per-element test  |a-b| / max(scale,|a|,|b|) > tol
@@ -112,13 +90,19 @@ struct ConvTest {
 
 } // namespace
 
-template <int M, int PT, bool AMERICAN, bool BDF2, bool EVENTS>
+enum { MODE_LINEAR = 0, MODE_PENALTY = 1, MODE_POLICY = 2 };
+
+// MODE_LINEAR : root = the discretisation node (European / Bermudan)
+// MODE_PENALTY: root = MinPenaltyMethodDifference1 under a ToleranceIteration
+// MODE_POLICY : discretisation over Min/MaxPolicyIteration1_1 (two control
+//               values of the interest rate) under a ToleranceIteration
+template <int M, int PT, int MODE, bool BDF2, bool EVENTS>
 __global__ void __launch_bounds__(PT, 1)
 k_resident_sweep(DeviceBatch b, DeviceResult out) {
+	constexpr bool AMERICAN = MODE == MODE_PENALTY;
+	constexpr bool POLICY = MODE == MODE_POLICY;
+	constexpr bool ITERATE = MODE != MODE_LINEAR;
 	constexpr int P = PT;                    // blockDim.x == PT
-	constexpr int W = PT / 32;               // warps = level-3 unknowns
-	constexpr int L3_STAGES = ilog2_ceil(W);
-	static_assert(W <= MAX_WARPS && W <= 32, "too many warps");
 	extern __shared__ __align__(16) unsigned char smem_raw[];
 	Smem &sm = *reinterpret_cast<Smem *>(smem_raw);
 
@@ -180,7 +164,17 @@ k_resident_sweep(DeviceBatch b, DeviceResult out) {
 				const double v_i = b.vol_model == QPDE_VOL_NODES
 					? b.sigma_nodes[(size_t)cidx * b.sigma_nodes_stride + i]
 					: vol_value(b.vol_model, sig, Si);
-				row = bs_row(i, N, Sm, Si, Sp, r, v_i, q);
+				if(POLICY) {
+					// control value 0 -> (lo, di, up); control value 1 -> (na, me, nc)
+					const double *ctl = b.controls + (size_t)cidx * b.controls_stride;
+					row = bs_row(i, N, Sm, Si, Sp, ctl[0], v_i, q);
+					const Row row1 = bs_row(i, N, Sm, Si, Sp, ctl[1], v_i, q);
+					if(!tail) { sm_na[j * P + tid] = row1.lo; sm_me[j * P + tid] = row1.di; sm_nc[j * P + tid] = row1.up; }
+				} else {
+					row = bs_row(i, N, Sm, Si, Sp, r, v_i, q);
+				}
+			} else if(POLICY && !tail) {
+				sm_na[j * P + tid] = 0.; sm_me[j * P + tid] = 0.; sm_nc[j * P + tid] = 0.;
 			}
 			if(tail) sm.tail.di = row.di;
 			else { sm_lo[j * P + tid] = row.lo; sm_di[j * P + tid] = row.di; sm_up[j * P + tid] = row.up; }
@@ -193,11 +187,8 @@ k_resident_sweep(DeviceBatch b, DeviceResult out) {
 	double rr[M];       // right-hand side lb + penalty terms for the current active set
 	double vprev[BDF2 ? M : 1]; // iterand(1) for BDF2
 	double x_next;      // x of the next thread's first row
-	// cached factorisation
-	double f_m[M], f_invd[M], f_u[M], f_Vs[M], f_Ws[M];   // level 1 (index 0 unused)
-	double f_a0 = 0., f_c0 = 0.;
-	double f_al[5], f_ga[5], f_invB2 = 1., f_V2 = 0., f_W2 = 0.;   // level 2
-	double f_q1 = 0., f_q2 = 0., f_q3 = 0., f_al3[L3_STAGES > 0 ? L3_STAGES : 1], f_ga3[L3_STAGES > 0 ? L3_STAGES : 1], f_invB3 = 1.; // level 3 (lanes < W)
+	PartitionSolver<M, PT> ps;   // cached factorisation (registers)
+	ps.init();
 	unsigned curmask = 0, newmask = 0;  // bit j: row j penalised; bit M: tail row
 	// row N-2 (row M-1 of the last thread) couples to the tail row; that thread
 	// owns the tail equation and folds the coupling into its rhs.
@@ -223,7 +214,6 @@ k_resident_sweep(DeviceBatch b, DeviceResult out) {
 		x[j] = real ? initial_value(i) : 0.;
 		pz[j] = real && (AMERICAN || EVENTS) ? obstacle_value(i) : -CUDART_INF;
 		if(BDF2) vprev[j] = 0.;
-		f_m[j] = 0.; f_invd[j] = 1.; f_u[j] = 0.; f_Vs[j] = 0.; f_Ws[j] = 0.;
 		rr[j] = 0.;
 	}
 	if(tail_owner) {
@@ -234,10 +224,6 @@ k_resident_sweep(DeviceBatch b, DeviceResult out) {
 	x_next = i0 + M < n_main ? initial_value(i0 + M) : 0.;
 	sm_xlast[tid + 1] = x[M - 1];
 	if(tid == 0) { sm_xlast[0] = 0.; sm.flags[0] = 0u; sm.flags[1] = 0u; }
-#pragma unroll
-	for(int s = 0; s < 5; ++s) { f_al[s] = 0.; f_ga[s] = 0.; }
-#pragma unroll
-	for(int s = 0; s < (L3_STAGES > 0 ? L3_STAGES : 1); ++s) { f_al3[s] = 0.; f_ga3[s] = 0.; }
 
 	// PenaltyMethod.hpp:45,61-66: row penalised iff (scale * (x - payoff)) < 0,
 	// i.e. iff x < payoff (scale > 0 and the difference of two distinct doubles
@@ -252,7 +238,28 @@ k_resident_sweep(DeviceBatch b, DeviceResult out) {
 		} \
 		dst = mk_; \
 	} while(0)
-	QPDE_MASK_OF(newmask);
+	// PolicyIteration::onIterationStart (Core/PolicyIteration.hpp:54-105): per row
+	// candidate_k = (A(q_k) x - b(q_k))_i, SpMV from zero in column order, b = 0;
+	// control 1 replaces control 0 only on a strict improvement.  Bit j = control
+	// index of row j.  Reads sm_xlast: call after a barrier that follows its write.
+#define QPDE_POLICY_OF(dst) \
+	do { \
+		unsigned mk_ = 0; \
+		const double xm_ = sm_xlast[tid]; \
+		_Pragma("unroll") \
+		for(int j = 0; j < M; ++j) { \
+			const int at_ = j * P + tid; \
+			const double vm_ = j == 0 ? xm_ : x[j > 0 ? j - 1 : 0]; \
+			const double vp_ = j == M - 1 ? (tail_owner ? sm.tail.x : x_next) : x[j + 1 < M ? j + 1 : j]; \
+			double c0_ = 0., c1_ = 0.; \
+			c0_ += sm_lo[at_] * vm_; c0_ += sm_di[at_] * x[j]; c0_ += sm_up[at_] * vp_; c0_ = c0_ - 0.; \
+			c1_ += sm_na[at_] * vm_; c1_ += sm_me[at_] * x[j]; c1_ += sm_nc[at_] * vp_; c1_ = c1_ - 0.; \
+			if(b.policy_max ? c1_ > c0_ : c1_ < c0_) mk_ |= 1u << j; \
+		} \
+		dst = mk_; \
+	} while(0)
+	__syncthreads();
+	if(POLICY) QPDE_POLICY_OF(newmask); else QPDE_MASK_OF(newmask);
 	__syncthreads();
 
 	// ------------------------------------------------------------------
@@ -291,6 +298,7 @@ k_resident_sweep(DeviceBatch b, DeviceResult out) {
 			cur_kind = kind; cur_h = g.h;
 #pragma unroll
 			for(int j = 0; j < M; ++j) {
+				if(POLICY) break;     // rows are scaled at factorisation time, per selected control
 				const int at = j * P + tid;
 				const double aj = g.off(sm_lo[at]), ej = g.off(sm_di[at]);
 				double cj = g.off(sm_up[at]);
@@ -356,14 +364,21 @@ k_resident_sweep(DeviceBatch b, DeviceResult out) {
 			if(refactor) {
 				refactor = false;
 				curmask = newmask;
-				double bb0, cc[M];
-				// level 1: interior rows 1 .. M-1
 				{
-					double aa[M], bb[M];
+					double aa[M], bb[M], cc[M];
 #pragma unroll
 					for(int j = 0; j < M; ++j) {
 						const int at = j * P + tid;
-						aa[j] = sm_a[at]; bb[j] = sm_bd[at]; cc[j] = sm_c[at];
+						if(POLICY) {
+							const bool sel = curmask >> j & 1u;
+							Gamma gA; gA.kind = cur_kind; gA.h = cur_h;
+							aa[j] = gA.off(sel ? sm_na[at] : sm_lo[at]);
+							bb[j] = 1. + gA.off(sel ? sm_me[at] : sm_di[at]);
+							cc[j] = gA.off(sel ? sm_nc[at] : sm_up[at]);
+							if(j == M - 1 && tail_owner) { sm.tail.c = cc[j]; cc[j] = 0.; }
+						} else {
+							aa[j] = sm_a[at]; bb[j] = sm_bd[at]; cc[j] = sm_c[at];
+						}
 						const bool act = AMERICAN && (curmask >> j & 1u);
 						if(act) bb[j] = bb[j] + b.pen * 1.;
 						const double lbj = sm_lb[at];
@@ -374,106 +389,7 @@ k_resident_sweep(DeviceBatch b, DeviceResult out) {
 						sm.tail.invb = rcp(act ? sm.tail.bd + b.pen * 1. : sm.tail.bd);
 						sm.tail.pq = act ? b.pen * sm.tail.pz : 0.;
 					}
-					bb0 = bb[0]; f_a0 = aa[0]; f_c0 = cc[0];
-					f_invd[1] = rcp(bb[1]);
-#pragma unroll
-					for(int j = 2; j < M; ++j) {
-						f_m[j] = aa[j] * f_invd[j - 1];
-						f_invd[j] = rcp(fma(-f_m[j], cc[j - 1], bb[j]));
-					}
-					double y = aa[1];
-					double yv[M];
-					yv[1] = y;
-#pragma unroll
-					for(int j = 2; j < M; ++j) { y = -f_m[j] * y; yv[j] = y; }
-#pragma unroll
-					for(int j = 1; j < M; ++j) f_u[j] = cc[j] * f_invd[j];
-					f_Vs[M - 1] = yv[M - 1] * f_invd[M - 1];
-					f_Ws[M - 1] = f_u[M - 1];
-#pragma unroll
-					for(int j = M - 2; j >= 1; --j) {
-						f_Vs[j] = fma(-f_u[j], f_Vs[j + 1], yv[j] * f_invd[j]);
-						f_Ws[j] = -f_u[j] * f_Ws[j + 1];
-					}
-				}
-				// reduced row of this thread's separator (its row 0)
-				const double Vs7p = shfl_up(f_Vs[M - 1], 1), Ws7p = shfl_up(f_Ws[M - 1], 1);
-				const bool interior = lane >= 1;
-				const double Bpart = fma(-f_c0, f_Vs[1], bb0);
-				const double Ct = -f_c0 * f_Ws[1];
-				double A2 = interior ? -f_a0 * Vs7p : 0.;
-				double B2 = interior ? fma(-f_a0, Ws7p, Bpart) : 1.;
-				double C2 = interior ? Ct : 0.;
-				// level 2: cyclic reduction over lanes 1 .. 31; the couplings of lane
-				// 1 to the warp separator and of lane 31 to the next warp's
-				// separator become two extra right-hand sides (spikes V2, W2)
-				double V2 = lane == 1 ? A2 : 0.;
-				double W2 = lane == 31 ? C2 : 0.;
-				if(lane == 1) A2 = 0.;
-				if(lane == 31) C2 = 0.;
-#pragma unroll
-				for(int s = 0; s < 5; ++s) {
-					const int dl = 1 << s;
-					const double rB = rcp(B2);
-					const double rBm = shfl_up(rB, dl), rBq = shfl_down(rB, dl);
-					const double Am = shfl_up(A2, dl), Aq = shfl_down(A2, dl);
-					const double Cm = shfl_up(C2, dl), Cq = shfl_down(C2, dl);
-					const double Vm = shfl_up(V2, dl), Vq = shfl_down(V2, dl);
-					const double Wm = shfl_up(W2, dl), Wq = shfl_down(W2, dl);
-					const bool okm = interior && lane - dl >= 1;
-					const bool okq = interior && lane + dl <= 31;
-					const double al = okm ? -A2 * rBm : 0.;
-					const double ga = okq ? -C2 * rBq : 0.;
-					f_al[s] = al; f_ga[s] = ga;
-					B2 = fma(al, Cm, fma(ga, Aq, B2));
-					V2 = fma(al, Vm, fma(ga, Vq, V2));
-					W2 = fma(al, Wm, fma(ga, Wq, W2));
-					A2 = al * Am;
-					C2 = ga * Cq;
-				}
-				f_invB2 = rcp(B2);
-				f_V2 = V2 * f_invB2;
-				f_W2 = W2 * f_invB2;
-				// hand-over to level 3
-				if(lane == 31) { sm.f_Vs7[warp] = f_Vs[M - 1]; sm.f_Ws7[warp] = f_Ws[M - 1]; sm.f_V2l[warp] = f_V2; sm.f_W2l[warp] = f_W2; }
-				if(lane == 1)  { sm.f_V2f[warp] = f_V2; sm.f_W2f[warp] = f_W2; }
-				if(lane == 0)  { sm.f_a0[warp] = f_a0; sm.f_Bp[warp] = Bpart; sm.f_Ct[warp] = Ct; }
-				__syncthreads();
-				// level 3: W x W tridiagonal over the warp separators, reduced by
-				// every warp redundantly across its lanes 0 .. W-1
-				{
-					double A3 = 0., B3 = 1., C3 = 0.;
-					f_q1 = 0.; f_q2 = 0.; f_q3 = 0.;
-					if(lane < W) {
-						const int w = lane;
-						const double a0 = sm.f_a0[w];
-						const double Vs7q = w > 0 ? sm.f_Vs7[w - 1] : 0., Ws7q = w > 0 ? sm.f_Ws7[w - 1] : 0.;
-						const double V2q = w > 0 ? sm.f_V2l[w - 1] : 0., W2q = w > 0 ? sm.f_W2l[w - 1] : 0.;
-						const double At = -a0 * Vs7q;
-						const double Bt = fma(-a0, Ws7q, sm.f_Bp[w]);
-						const double Cw = sm.f_Ct[w];
-						A3 = -At * V2q;
-						B3 = fma(-Cw, sm.f_V2f[w], fma(-At, W2q, Bt));
-						C3 = -Cw * sm.f_W2f[w];
-						f_q1 = -a0; f_q2 = -At; f_q3 = -Cw;
-					}
-#pragma unroll
-					for(int s = 0; s < L3_STAGES; ++s) {
-						const int dl = 1 << s;
-						const double rB = rcp(B3);
-						const double rBm = shfl_up(rB, dl), rBq = shfl_down(rB, dl);
-						const double Am = shfl_up(A3, dl), Aq = shfl_down(A3, dl);
-						const double Cm = shfl_up(C3, dl), Cq = shfl_down(C3, dl);
-						const bool okm = lane < W && lane - dl >= 0;
-						const bool okq = lane + dl < W;
-						const double al = okm ? -A3 * rBm : 0.;
-						const double ga = okq ? -C3 * rBq : 0.;
-						f_al3[s] = al; f_ga3[s] = ga;
-						B3 = fma(al, Cm, fma(ga, Aq, B3));
-						A3 = al * Am;
-						C3 = ga * Cq;
-					}
-					f_invB3 = rcp(B3);
+					ps.factorize(aa, bb, cc, sm.ps, lane, warp);
 				}
 			}
 
@@ -488,60 +404,14 @@ k_resident_sweep(DeviceBatch b, DeviceResult out) {
 				r_last = fma(-sm.tail.c, xt_new, r_last);
 			}
 			double G[M];
-			double r0;
 			{
 				double r[M];
 #pragma unroll
 				for(int j = 0; j < M; ++j) r[j] = j == M - 1 ? r_last : rr[j];
-				r0 = r[0];
-				// level 1: G = T^-1 r on the interior rows
-				G[1] = r[1];
-#pragma unroll
-				for(int j = 2; j < M; ++j) G[j] = fma(-f_m[j], G[j - 1], r[j]);
+				ps.solve(r, G, x_next, sm.ps, lane, warp);
 			}
-			G[M - 1] = G[M - 1] * f_invd[M - 1];
-#pragma unroll
-			for(int j = M - 2; j >= 1; --j) G[j] = fma(-f_u[j], G[j + 1], G[j] * f_invd[j]);
-			const double G7p = shfl_up(G[M - 1], 1);
-			const double P0 = fma(-f_c0, G[1], r0);
-			// level 2
-			double R2 = lane >= 1 ? fma(-f_a0, G7p, P0) : 0.;
-#pragma unroll
-			for(int s = 0; s < 5; ++s) {
-				const int dl = 1 << s;
-				const double Rm = shfl_up(R2, dl), Rq = shfl_down(R2, dl);
-				R2 = fma(f_al[s], Rm, fma(f_ga[s], Rq, R2));   // al, ga are 0 where the partner is outside
-			}
-			const double G2 = R2 * f_invB2;
-			if(lane == 31) { sm.s_G7[warp] = G[M - 1]; sm.s_G2l[warp] = G2; }
-			if(lane == 1)  sm.s_G2f[warp] = G2;
-			if(lane == 0)  sm.s_P0[warp] = P0;
-			__syncthreads();
-			// level 3 (lanes 0 .. W-1 of every warp)
-			double R3 = 0.;
-			if(lane < W) {
-				R3 = sm.s_P0[lane];
-				if(lane > 0) R3 = fma(f_q1, sm.s_G7[lane - 1], fma(f_q2, sm.s_G2l[lane - 1], R3));
-				R3 = fma(f_q3, sm.s_G2f[lane], R3);
-			}
-#pragma unroll
-			for(int s = 0; s < L3_STAGES; ++s) {
-				const int dl = 1 << s;
-				const double Rm = shfl_up(R3, dl), Rq = shfl_down(R3, dl);
-				R3 = fma(f_al3[s], Rm, fma(f_ga3[s], Rq, R3));
-			}
-			const double Y = R3 * f_invB3;            // separator of warp `lane` (0 for lanes >= W)
-			const double Yw = shfl_idx(Y, warp);
-			const double Yn = shfl_idx(Y, warp + 1);   // lane W holds 0
-			// back substitution, levels 2 and 1
-			const double ysep = lane == 0 ? Yw : fma(-Yn, f_W2, fma(-Yw, f_V2, G2));
-			double ynext = shfl_down(ysep, 1);
-			if(lane == 31) ynext = Yn;
-			G[0] = ysep;
-#pragma unroll
-			for(int j = 1; j < M; ++j) G[j] = fma(-ynext, f_Ws[j], fma(-ysep, f_Vs[j], G[j]));
 			bool nd = false;
-			if(AMERICAN) {
+			if(ITERATE) {
 				int dmax_hi = 0, xmax_hi = 0;
 #pragma unroll
 				for(int j = 0; j < M; ++j) ConvTest::track(G[j], x[j], dmax_hi, xmax_hi);
@@ -557,11 +427,15 @@ k_resident_sweep(DeviceBatch b, DeviceResult out) {
 #pragma unroll
 			for(int j = 0; j < M; ++j) x[j] = G[j];
 			if(tail_owner) sm.tail.x = xt_new;
-			x_next = ynext;
 			sm_xlast[tid + 1] = x[M - 1];
 			++its;
-			if(AMERICAN) {
-				QPDE_MASK_OF(newmask);
+			if(ITERATE) {
+				if(POLICY) {
+					__syncthreads();             // sm_xlast of the new iterate is visible
+					QPDE_POLICY_OF(newmask);
+				} else {
+					QPDE_MASK_OF(newmask);
+				}
 				// one barrier carries both block-wide flags
 				const unsigned bits = (nd ? 1u : 0u) | (newmask != curmask ? 2u : 0u);
 				const unsigned wbits = __reduce_or_sync(FULL, bits);
@@ -613,6 +487,7 @@ k_resident_sweep(DeviceBatch b, DeviceResult out) {
 		}
 	}
 #undef QPDE_MASK_OF
+#undef QPDE_POLICY_OF
 
 	// ------------------------------------------------------------------
 	// Outputs
@@ -690,12 +565,13 @@ bool resident_supported(const DeviceBatch &b) {
 	if(b.N < 10) return false;
 	if(!pick_geometry(b.N, &M, &PT)) return false;
 	if(b.american && b.n_exercise > 0) return false; // penalty + events: INTERLEAVED family
+	if(b.n_controls != 0 && b.n_controls != 2) return false; // more control values: INTERLEAVED family
 	return true;
 }
 
-template <int M, int PT, bool AMERICAN, bool BDF2, bool EVENTS>
+template <int M, int PT, int MODE, bool BDF2, bool EVENTS>
 static int launch_variant(const DeviceBatch &b, const DeviceResult &out, cudaStream_t stream) {
-	auto kern = k_resident_sweep<M, PT, AMERICAN, BDF2, EVENTS>;
+	auto kern = k_resident_sweep<M, PT, MODE, BDF2, EVENTS>;
 	static bool configured = false;
 	if(!configured) {
 		if(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -712,12 +588,14 @@ template <int M, int PT>
 static int launch_rows(const DeviceBatch &b, const DeviceResult &out, cudaStream_t stream) {
 	const bool bdf2 = b.scheme == QPDE_SCHEME_BDF2;
 	const bool events = b.n_exercise > 0;
-	if(b.american) return bdf2 ? launch_variant<M, PT, true, true, false>(b, out, stream)
-	                           : launch_variant<M, PT, true, false, false>(b, out, stream);
-	if(events)     return bdf2 ? launch_variant<M, PT, false, true, true>(b, out, stream)
-	                           : launch_variant<M, PT, false, false, true>(b, out, stream);
-	return bdf2 ? launch_variant<M, PT, false, true, false>(b, out, stream)
-	            : launch_variant<M, PT, false, false, false>(b, out, stream);
+	if(b.n_controls > 0) return bdf2 ? launch_variant<M, PT, MODE_POLICY, true, false>(b, out, stream)
+	                                 : launch_variant<M, PT, MODE_POLICY, false, false>(b, out, stream);
+	if(b.american) return bdf2 ? launch_variant<M, PT, MODE_PENALTY, true, false>(b, out, stream)
+	                           : launch_variant<M, PT, MODE_PENALTY, false, false>(b, out, stream);
+	if(events)     return bdf2 ? launch_variant<M, PT, MODE_LINEAR, true, true>(b, out, stream)
+	                           : launch_variant<M, PT, MODE_LINEAR, false, true>(b, out, stream);
+	return bdf2 ? launch_variant<M, PT, MODE_LINEAR, true, false>(b, out, stream)
+	            : launch_variant<M, PT, MODE_LINEAR, false, false>(b, out, stream);
 }
 
 int launch_resident(const DeviceBatch &b, const DeviceResult &out, cudaStream_t stream,

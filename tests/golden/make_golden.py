@@ -39,6 +39,15 @@ for sch in ("bdf2", "rannacher", "bdf1", "cn"):
         CASES.append(("bermudan_%s_k%d" % (sch, k), "bermudan",
                       dict(steps=100 * 2 ** k, refine=k, scheme=sch, K=100.0, r=0.04, alpha=20.0, T=1.0, E=10)))
 
+# examples/unequal_borrowing_lending_rates.cpp: HJB with the interest rate as a control
+for lp in (0, 1):
+    for k in (0, 1, 2):
+        CASES.append(("hjb_%s_bdf2_k%d" % ("long" if lp else "short", k), "hjb",
+                      dict(steps=12 * 2 ** k, refine=k, long=lp, scheme="bdf2", K=100.0, r_l=0.03, r_b=0.05,
+                           vol=0.3, T=1.0)))
+CASES.append(("hjb_short_bdf1_k1", "hjb",
+              dict(steps=40, refine=1, long=0, scheme="bdf1", K=90.0, r_l=0.02, r_b=0.07, vol=0.25, T=0.8)))
+
 out = {}
 names = []
 for name, mode, kw in CASES:

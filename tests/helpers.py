@@ -44,6 +44,9 @@ def run_oracle_case(po, mode, kw):
         return po.american_put(kw["K"], kw["r"], kw["vol"], kw["T"], kw["steps"], kw["refine"],
                                q=kw.get("q", 0.0), call=bool(kw.get("call", 0)),
                                american=bool(kw["american"]), scheme=kw.get("scheme", "rannacher"))
+    if mode == "hjb":
+        return po.hjb_straddle(kw["K"], kw["r_l"], kw["r_b"], kw["vol"], kw["T"], kw["steps"], kw["refine"],
+                               long_position=bool(kw["long"]), scheme=kw["scheme"])
     return po.bermudan_put(kw["K"], kw["r"], kw["alpha"], kw["T"], kw["steps"], kw["E"],
                            kw["refine"], scheme=kw["scheme"])
 
@@ -59,6 +62,14 @@ def spec_for_case(qpde, po, mode, kw, kernel="auto", copies=1):
             q=kw.get("q", 0.0), T=kw["T"], dt=kw["T"] / kw["steps"], strike=np.full(copies, K),
             scheme=kw.get("scheme", "rannacher"), american=bool(kw["american"]),
             payoff="call" if call else "put", kernel=kernel)
+    if mode == "hjb":
+        K = kw["K"]
+        axis = po.axis_union(po.special_axis() * K, po.special_axis() * K)
+        return qpde.BatchSpec(
+            axis=np.tile(axis, (copies, 1)), refine=kw["refine"], r=0.0, sigma=kw["vol"], q=0.0,
+            T=kw["T"], dt=kw["T"] / kw["steps"], strike=np.full(copies, K), scheme=kw["scheme"],
+            american=False, payoff="straddle", controls=np.array([kw["r_l"], kw["r_b"]]),
+            policy_max=bool(kw["long"]), kernel=kernel)
     K = kw["K"]
     axis = po.TUTORIAL_AXIS * (K / 100.0)
     return qpde.BatchSpec(

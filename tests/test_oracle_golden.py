@@ -12,7 +12,7 @@ from helpers import case_args, run_oracle_case
 
 def test_golden_cases_bit_exact(oracle, golden):
     names = [str(n) for n in golden["names"]]
-    assert len(names) >= 20
+    assert len(names) >= 30
     for name in names:
         mode, kw = case_args(golden, name)
         out = run_oracle_case(oracle, mode, kw)
@@ -22,6 +22,7 @@ def test_golden_cases_bit_exact(oracle, golden):
         assert np.array_equal(out["V"], golden[name + "/V"]), name
         if name + "/inner" in golden.files and len(golden[name + "/inner"]):
             assert np.array_equal(out["inner"], golden[name + "/inner"]), name
+        if name + "/mask" in golden.files and len(golden[name + "/mask"]):
             assert np.array_equal(out["mask"], golden[name + "/mask"]), name
 
 
