@@ -212,13 +212,22 @@ public:
 	virtual ~LinearSystem() {}
 };
 
+// Control1(grid): marks a coefficient as a control (Core/IterativeMethod.hpp:449-499,
+// examples/unequal_borrowing_lending_rates.cpp:108-118)
+struct Control1 {
+	explicit Control1(const RectilinearGrid1 &) {}
+};
+
 // BlackScholes1(grid, r, v, q) — Modules/Operators/BlackScholes.hpp:114-134
 class BlackScholes1 : public LinearSystem {
 public:
 	const RectilinearGrid1 &grid;
 	Real r; Volatility v; Real q;
+	bool rIsControl;
 	BlackScholes1(const RectilinearGrid1 &grid, Real r, Volatility v, Real q)
-			: grid(grid), r(r), v(std::move(v)), q(q) {}
+			: grid(grid), r(r), v(std::move(v)), q(q), rIsControl(false) {}
+	BlackScholes1(const RectilinearGrid1 &grid, Control1, Volatility v, Real q)
+			: grid(grid), r(0.), v(std::move(v)), q(q), rIsControl(true) {}
 };
 
 class Iteration {
@@ -251,25 +260,55 @@ public:
 	void setIteration(Iteration &it) { iteration = &it; }             // IterativeMethod.hpp:848
 };
 
+// Min/MaxPolicyIteration1_1(grid, controlGrid, system) — Core/PolicyIteration.hpp:109-174
+class PolicyIteration1_1 : public IterationNode {
+public:
+	const RectilinearGrid1 &grid;
+	std::vector<Real> controls;   // ticks of the control grid, in order
+	const BlackScholes1 &system;
+	bool maximise;
+	PolicyIteration1_1(const RectilinearGrid1 &g, const RectilinearGrid1 &controlGrid,
+			const BlackScholes1 &bs, bool maximise)
+			: grid(g), controls(controlGrid.nodes()), system(bs), maximise(maximise) {
+		if(!bs.rIsControl) throw std::invalid_argument("QuantPDE_B200: the operator has no Control1 coefficient");
+	}
+};
+struct MinPolicyIteration1_1 : PolicyIteration1_1 {
+	MinPolicyIteration1_1(const RectilinearGrid1 &g, const RectilinearGrid1 &c, const BlackScholes1 &bs)
+			: PolicyIteration1_1(g, c, bs, false) {}
+};
+struct MaxPolicyIteration1_1 : PolicyIteration1_1 {
+	MaxPolicyIteration1_1(const RectilinearGrid1 &g, const RectilinearGrid1 &c, const BlackScholes1 &bs)
+			: PolicyIteration1_1(g, c, bs, true) {}
+};
+
 class Discretization : public IterationNode {
 public:
 	const RectilinearGrid1 &grid;
 	const BlackScholes1 &op;
+	const PolicyIteration1_1 *policy;   // non-null when the operator is wrapped in a policy iteration
 	int scheme;
-	Discretization(const RectilinearGrid1 &g, const BlackScholes1 &o, int s) : grid(g), op(o), scheme(s) {}
+	Discretization(const RectilinearGrid1 &g, const BlackScholes1 &o, int s)
+			: grid(g), op(o), policy(nullptr), scheme(s) {}
+	Discretization(const RectilinearGrid1 &g, const PolicyIteration1_1 &p, int s)
+			: grid(g), op(p.system), policy(&p), scheme(s) {}
 };
 struct ReverseRannacher : Discretization {
 	ReverseRannacher(const RectilinearGrid1 &g, const BlackScholes1 &o) : Discretization(g, o, QPDE_SCHEME_RANNACHER) {}
+	ReverseRannacher(const RectilinearGrid1 &g, const PolicyIteration1_1 &p) : Discretization(g, p, QPDE_SCHEME_RANNACHER) {}
 };
 struct ReverseCrankNicolson : Discretization {
 	ReverseCrankNicolson(const RectilinearGrid1 &g, const BlackScholes1 &o) : Discretization(g, o, QPDE_SCHEME_CN) {}
+	ReverseCrankNicolson(const RectilinearGrid1 &g, const PolicyIteration1_1 &p) : Discretization(g, p, QPDE_SCHEME_CN) {}
 };
 struct ReverseBDFOne : Discretization {
 	ReverseBDFOne(const RectilinearGrid1 &g, const BlackScholes1 &o) : Discretization(g, o, QPDE_SCHEME_BDF1) {}
+	ReverseBDFOne(const RectilinearGrid1 &g, const PolicyIteration1_1 &p) : Discretization(g, p, QPDE_SCHEME_BDF1) {}
 };
 typedef ReverseBDFOne ReverseImplicitEuler;
 struct ReverseBDFTwo : Discretization {
 	ReverseBDFTwo(const RectilinearGrid1 &g, const BlackScholes1 &o) : Discretization(g, o, QPDE_SCHEME_BDF2) {}
+	ReverseBDFTwo(const RectilinearGrid1 &g, const PolicyIteration1_1 &p) : Discretization(g, p, QPDE_SCHEME_BDF2) {}
 };
 
 // MinPenaltyMethodDifference1(grid, constraintNode, payoff, tolerance) —
@@ -406,6 +445,10 @@ public:
 		std::vector<Real> payArr, obsArr, sigArr;
 		int payKind = items[0].payoff.kind(), obsKind = american ? p0->obstacle.kind() : QPDE_PAYOFF_PUT;
 		int volModel = d0->op.v.model();
+		const bool policy = d0->policy != nullptr;
+		const int nControls = policy ? (int)d0->policy->controls.size() : 0;
+		std::vector<Real> controls;
+		if(policy && !tol0) throw std::invalid_argument("QuantPDE_B200: policy iteration needs setInnerIteration()");
 		for(int c = 0; c < C; ++c) {
 			const Item &it = items[c];
 			const Discretization *d; MinPenaltyMethodDifference1 *p;
@@ -413,12 +456,16 @@ public:
 			if(it.grid->size() != N || it.grid->coarse().size() != nAxis || it.grid->refinement() != refine
 					|| d->scheme != d0->scheme || (p != nullptr) != american
 					|| it.stepper->exerciseDates() != nEx || d->op.v.model() != volModel
-					|| it.payoff.kind() != payKind || (american && p->obstacle.kind() != obsKind)) {
+					|| it.payoff.kind() != payKind || (american && p->obstacle.kind() != obsKind)
+					|| (d->policy != nullptr) != policy
+					|| (policy && ((int)d->policy->controls.size() != nControls
+						|| d->policy->maximise != d0->policy->maximise))) {
 				throw std::invalid_argument("QuantPDE_B200: all problems of a batch must share grid size, "
 					"scheme, constraint type, payoff kind and volatility model");
 			}
 			for(int k = 0; k < nAxis; ++k) axis[(size_t)c * nAxis + k] = it.grid->coarse()[k];
 			r[c] = d->op.r; sig[c] = d->op.v.param(); q[c] = d->op.q;
+			if(policy) controls.insert(controls.end(), d->policy->controls.begin(), d->policy->controls.end());
 			T[c] = it.stepper->expiry(); dt[c] = it.stepper->timestep();
 			K[c] = it.payoff.kind() != QPDE_PAYOFF_ARRAY ? it.payoff.strike()
 				: (american && p->obstacle.kind() != QPDE_PAYOFF_ARRAY ? p->obstacle.strike()
@@ -449,9 +496,14 @@ public:
 		if(payKind == QPDE_PAYOFF_ARRAY) { b.payoff = payArr.data(); b.payoff_stride = N; }
 		if(american && obsKind == QPDE_PAYOFF_ARRAY) { b.obstacle = obsArr.data(); b.obstacle_stride = N; }
 		b.american = american ? 1 : 0;
-		b.max_inner = american ? tol0->maxIterations : 1;
-		b.tolerance = american ? tol0->tol : tolerance;
-		b.scale = american ? tol0->scl : scale;
+		const bool iterate = american || policy;
+		b.max_inner = iterate ? tol0->maxIterations : 1;
+		b.tolerance = iterate ? tol0->tol : tolerance;
+		b.scale = iterate ? tol0->scl : scale;
+		if(policy) {
+			b.n_controls = nControls; b.policy_max = d0->policy->maximise ? 1 : 0;
+			b.controls = controls.data(); b.controls_stride = nControls;
+		}
 		b.penalty_tolerance = american ? p0->tol : tolerance;
 		b.spot = spot.data();
 		b.kernel = kernel;
@@ -484,10 +536,12 @@ public:
 			it.stepper->its.assign(1, (size_t)nSteps[c]);
 			const Discretization *d; MinPenaltyMethodDifference1 *p;
 			decode(it.root, d, p);
-			if(p) {
+			if(p || d->policy) {
 				ToleranceIteration *ti = it.stepper->innerIteration();
 				ti->its.clear();
 				for(int s = 0; s < nSteps[c]; ++s) ti->its.push_back(inner[(size_t)c * maxSteps + s]);
+			}
+			if(p) {
 				p->mask.assign(active.begin() + (size_t)c * N, active.begin() + (size_t)(c + 1) * N);
 			}
 		}

@@ -53,7 +53,7 @@ def test_golden_cases(qpde, handle, oracle, golden, kernel):
                                           case_obstacle(kw, S_ref))
                 assert hard == 0, name
             assert rel_err(res.value[c], float(golden[name + "/value"])) <= REL_TOL
-    assert ran >= (30 if kernel == "interleaved" else 1)
+    assert ran >= (28 if kernel == "interleaved" else 1)
 
 
 @pytest.mark.parametrize("kernel", KERNELS)
