@@ -174,6 +174,24 @@ typedef struct {
 	const double *controls;  /* [C][n_controls] ticks of the control grid, in order */
 	int64_t controls_stride; /* 0 = one control grid shared by all contracts */
 
+	/* --- jump diffusion: BlackScholesJumpDiffusion1(grid, r, v, q, lambda, density)
+	 * (Modules/Operators/BlackScholes.hpp:271-461, examples/jump_diffusion.cpp:105-116).
+	 * The operator gains lambda on the diagonal and the drift r - q - lambda kappa;
+	 * its b() is the explicit correlation integral lambda h(log S_i), h = circular
+	 * correlation of V(exp(x0 + k dx)) with the density weights (d'Halluin et al.).
+	 * x0, dx, kappa and the weights are what the reference computes once at
+	 * construction by adaptive quadrature; qpde_jump_setup() reproduces them on
+	 * the host.  jump_lambda == NULL: no jumps.  Needs american = 0, no controls,
+	 * scheme BDF1 or BDF2. */
+	const double *jump_lambda;   /* [C] mean arrival rate                    */
+	const double *jump_kappa;    /* [C] E[eta] - 1                           */
+	const double *jump_x0;       /* [C] log-grid origin log S_{i0}           */
+	const double *jump_dx;       /* [C] log-grid spacing                     */
+	const double *jump_weights;  /* [C][n_fft] density weights f'_j (wrapped order) */
+	int64_t jump_weights_stride; /* 0 = one weight vector shared by all contracts */
+	int32_t n_fft;               /* power of two >= N (qpde_jump_nfft)       */
+	int32_t reserved2;
+
 	int32_t kernel;          /* QPDE_KERNEL_* (AUTO picks by N)             */
 	int32_t outputs;         /* split form only: QPDE_OUT_* mask of the outputs
 	                            to keep on the device; 0 = all.  The one-shot
@@ -223,6 +241,19 @@ int qpde_make_schedule(double T, double dt, const double *event_times,
 		int n_events, qpde_step *out, int max_steps);
 /* N after refinement. */
 int qpde_refined_size(int n_axis, int refine);
+
+/* Jump-diffusion set-up on the host, as BlackScholesJumpDiffusion does at
+ * construction (BlackScholes.hpp:53-62 kappa, :275-297 log-grid, :299-329
+ * density weights; quadrature Core/Integral.hpp:122-212,367-456).
+ * density_kind: QPDE_DENSITY_LOGNORMAL (params = mu, sigma) or
+ * QPDE_DENSITY_DOUBLE_EXPONENTIAL (params = p, eta_1, eta_2).
+ * S: the refined grid [n_nodes]; weights: [qpde_jump_nfft(n_nodes)] out. */
+enum { QPDE_DENSITY_LOGNORMAL = 0, QPDE_DENSITY_DOUBLE_EXPONENTIAL = 1 };
+int qpde_jump_nfft(int n_nodes);
+int qpde_jump_setup(int n_nodes, const double *S, int density_kind,
+		const double *params, double *x0, double *dx, double *kappa, double *weights);
+/* The refined grid RectilinearGrid1(axis).refined(refine) on the host. */
+int qpde_refine_axis(const double *axis, int n_axis, int refine, double *out);
 
 /* ---- the sweep -------------------------------------------------------- */
 /* One-shot: upload (H2D), run, download (D2H).  This is the call the

@@ -38,7 +38,10 @@ class Problem(C.Structure):
                 ("event_obstacle", C.POINTER(C.c_double)),
                 ("n_controls", C.c_int), ("policy_max", C.c_int),
                 ("plo", C.POINTER(C.c_double)), ("pdi", C.POINTER(C.c_double)),
-                ("pup", C.POINTER(C.c_double)), ("solver", C.c_int)]
+                ("pup", C.POINTER(C.c_double)),
+                ("jump_weights", C.POINTER(C.c_double)), ("jump_nfft", C.c_int),
+                ("jump_lambda", C.c_double), ("jump_x0", C.c_double), ("jump_dx", C.c_double),
+                ("solver", C.c_int)]
 
 
 _lib = None
@@ -131,7 +134,7 @@ def interp(x, v, c):
 def sweep(S, lo, di, up, v0, T, steps, n_steps, scheme="rannacher",
           american=False, obstacle=None, event_obstacle=None,
           tolerance=1e-6, scale=1.0, penalty_tol=1e-6, max_inner=1000, solver=0,
-          policy_rows=None, policy_max=False):
+          policy_rows=None, policy_max=False, jump=None):
     """Returns dict(V, inner, mask, status).  policy_rows = (lo, di, up), each
     [n_controls][n]: PolicyIteration over the controls."""
     n = len(S)
@@ -152,6 +155,11 @@ def sweep(S, lo, di, up, v0, T, steps, n_steps, scheme="rannacher",
         p.event_obstacle = _dp(event_obstacle)
     p.tolerance, p.scale, p.penalty_tol, p.max_inner = tolerance, scale, penalty_tol, max_inner
     p.solver = solver
+    if jump is not None:
+        jw = np.ascontiguousarray(jump["weights"], dtype=np.float64)
+        p.jump_weights = _dp(jw)
+        p.jump_nfft = len(jw)
+        p.jump_lambda, p.jump_x0, p.jump_dx = jump["lambda"], jump["x0"], jump["dx"]
     if policy_rows is not None:
         prs = [np.ascontiguousarray(a, dtype=np.float64) for a in policy_rows]
         p.n_controls = prs[0].shape[0]
@@ -193,6 +201,38 @@ def bermudan_put(K, r, alpha, T, n_steps, E, refine_times, q=0.0, scheme="bdf2")
                 american=False, obstacle=payoff, event_obstacle=K - S)
     out["S"] = S
     out["n_steps"] = n
+    return out
+
+
+JUMP_AXIS_EXTRA = 1000.0   # examples/jump_diffusion.cpp:166: + S_0 * Axis{1000.}
+
+
+def jump_setup(S, density="lognormal", params=(-0.1, 0.45, 0.0)):
+    """(x0, dx, weights, kappa) as BlackScholesJumpDiffusion computes them at construction."""
+    S = np.ascontiguousarray(S, dtype=np.float64)
+    nfft = lib().qpo_jump_nfft(len(S))
+    w = np.zeros(nfft)
+    x0, dx, kappa = C.c_double(), C.c_double(), C.c_double()
+    p = list(params) + [0.0] * (3 - len(params))
+    lib().qpo_jump_setup(len(S), _dp(S), 1 if density == "kou" else 0, C.c_double(p[0]),
+                         C.c_double(p[1]), C.c_double(p[2]), C.byref(x0), C.byref(dx), _dp(w),
+                         C.byref(kappa))
+    return x0.value, dx.value, w, kappa.value
+
+
+def jump_call(K, r, vol, T, lam, n_steps, refine_times, q=0.0, density="lognormal",
+              params=(-0.1, 0.45), scheme="bdf1", solver=0):
+    """The jump_diffusion.cpp wiring on the oracle (European call)."""
+    sp = special_axis()
+    coarse = axis_union(axis_union(sp * K, sp * K), np.array([K * JUMP_AXIS_EXTRA]))
+    S = refine(coarse, refine_times)
+    x0, dx, w, kappa = jump_setup(S, density, params)
+    lo, di, up = bs_coeffs(S, r, vol, q, lam=lam, kappa=kappa)
+    payoff = np.where(S < K, 0.0, S - K)
+    steps, n = schedule(T, T / n_steps)
+    out = sweep(S, lo, di, up, payoff, T, steps, n, scheme=scheme,
+                jump=dict(weights=w, x0=x0, dx=dx, **{"lambda": lam}), solver=solver)
+    out.update(S=S, n_steps=n, x0=x0, dx=dx, weights=w, kappa=kappa)
     return out
 
 

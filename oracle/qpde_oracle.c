@@ -181,6 +181,192 @@ double qpo_interp(int n, const double *x, const double *v, double c) {
 }
 
 /* ------------------------------------------------------------------------ */
+/* Quadrature: AdaptiveQuadrature1<TrapezoidalRule1<1>> with the expanding   */
+/* window for infinite bounds (Core/Integral.hpp:122-212, 243-256, 367-456)  */
+/* ------------------------------------------------------------------------ */
+
+typedef double (*qpo_fn)(double, const void *);
+static const double QPO_TOL = 1e-6;   /* QuantPDE::tolerance, EarlyInclude.hpp:62 */
+
+static double trap1(qpo_fn f, const void *ctx, double a, double x) {
+	/* TrapezoidalRule<1,1>::compute (:280-296) */
+	double scale = 1. / 2, sum;
+	scale *= (x - a) / 1;
+	sum = f(a, ctx) * 1.;
+	sum += f(x, ctx) * 1.;
+	return scale * sum;
+}
+
+static double quad_refine(qpo_fn f, const void *ctx, double previous, double a,
+		double x, int n) {
+	/* AdaptiveQuadrature::refine for Dimension = 1 (:386-449) */
+	const double mid = (a + x) / 2.;
+	const double left = trap1(f, ctx, a, mid);
+	const double right = trap1(f, ctx, mid, x);
+	double sum = 0., error;
+	sum += left;
+	sum += right;
+	error = fabs((sum - previous) / sum);
+	if(n > 0 && error > QPO_TOL) {
+		sum = 0.;
+		sum += quad_refine(f, ctx, left, a, mid, n - 1);
+		sum += quad_refine(f, ctx, right, mid, x, n - 1);
+	}
+	return sum;
+}
+
+static double quad_compute(qpo_fn f, const void *ctx, double a, double x) {
+	return quad_refine(f, ctx, trap1(f, ctx, a, x), a, x, 64);
+}
+
+static double quad_integral(qpo_fn f, const void *ctx, double a, double x) {
+	/* Integral<1>::operator() (:122-212) */
+	const int neginf = a == -INFINITY, posinf = x == INFINITY;
+	double aa = a, xx = x, m = 0., previous, integral;
+	if(neginf) {
+		if(posinf) { aa = -1.; xx = 1.; m = 0.; }
+		else       { aa = xx - 1.; m = xx; }
+	} else if(posinf) { xx = aa + 1.; m = aa; }
+	if(!neginf && !posinf) return quad_compute(f, ctx, aa, xx);
+	previous = quad_compute(f, ctx, aa, xx);
+	for(;;) {
+		if(neginf) aa += aa - m;
+		if(posinf) xx += xx - m;
+		integral = quad_compute(f, ctx, aa, xx);
+		if(fabs((integral - previous) / integral) < QPO_TOL) break;
+		previous = integral;
+	}
+	return integral;
+}
+
+/* Jump amplitude densities (Modules/Lambdas/Densities.hpp:21-66) */
+typedef struct { int kind; double p0, p1, p2; } qpo_density;
+
+static double density_eval(double x, const qpo_density *d) {
+	if(x == 0.) return 0.;
+	if(d->kind == QPO_DENSITY_LOGNORMAL) {
+		const double mu = d->p0, sigma = d->p1;
+		return 1. / (x * sigma * sqrt(2. * M_PI))
+			* exp( -((log(x) - mu) * (log(x) - mu)) / (2. * sigma * sigma) );
+	} else {
+		const double p = d->p0, eta_1 = d->p1, eta_2 = d->p2;
+		return (x >= 1) ? (p * eta_1 * pow(x, -eta_1 - 1))
+		                : ((1 - p) * eta_2 * pow(x, eta_2 - 1));
+	}
+}
+
+/* exp(2y) g(exp(y)): BlackScholes::computeKappa (BlackScholes.hpp:53-62) */
+static double kappa_integrand(double y, const void *ctx) {
+	return exp(2 * y) * density_eval(exp(y), (const qpo_density *)ctx);
+}
+
+/* g(exp(x)) exp(x): computeDensityFFT's fbar (BlackScholes.hpp:306-308) */
+static double fbar_integrand(double x, const void *ctx) {
+	return density_eval(exp(x), (const qpo_density *)ctx) * exp(x);
+}
+
+int qpo_jump_nfft(int n) {
+	int N = 2;
+	while(N < n) N *= 2;   /* BlackScholes.hpp:281-284 */
+	return N;
+}
+
+void qpo_jump_setup(int n, const double *S, int density_kind, double p0, double p1,
+		double p2, double *x0_out, double *dx_out, double *weights, double *kappa_out) {
+	qpo_density d;
+	const int N = qpo_jump_nfft(n);
+	const int i0 = S[0] < DBL_EPSILON ? 1 : 0;                /* :288-291 */
+	const double x0 = log(S[i0]), xf = log(S[n - 2]);
+	const double dx = (xf - x0) / (N - 1);
+	int i;
+	d.kind = density_kind; d.p0 = p0; d.p1 = p1; d.p2 = p2;
+	*x0_out = x0; *dx_out = dx;
+	*kappa_out = quad_integral(kappa_integrand, &d, -INFINITY, INFINITY) - 1.;
+	for(i = 0; i <= N / 2; ++i) {                             /* :313-318 */
+		const double a = dx * (-.5 + i), b = dx * (.5 + i);
+		weights[i] = quad_integral(fbar_integrand, &d, a, b);
+	}
+	for(i = N / 2 + 1; i < N; ++i) {                          /* :319-324 */
+		const double a = dx * (-.5 + i - N), b = dx * (.5 + i - N);
+		weights[i] = quad_integral(fbar_integrand, &d, a, b);
+	}
+}
+
+/* Radix-2 complex FFT, same butterflies and twiddles as the binding's
+ * Eigen::FFT stand-in (oracle/shim/qpde_linalg_binding.hpp). */
+static void fft_inplace(int n, double *re, double *im, int inverse) {
+	int i, j = 0, len, k;
+	double *wr, *wi;
+	const double sgn = inverse ? 1. : -1.;
+	for(i = 1; i < n; ++i) {
+		int bit = n >> 1;
+		for(; j & bit; bit >>= 1) j ^= bit;
+		j ^= bit;
+		if(i < j) {
+			double t = re[i]; re[i] = re[j]; re[j] = t;
+			t = im[i]; im[i] = im[j]; im[j] = t;
+		}
+	}
+	wr = (double *)malloc(sizeof(double) * (size_t)(n / 2));
+	wi = (double *)malloc(sizeof(double) * (size_t)(n / 2));
+	for(k = 0; k < n / 2; ++k) {
+		const double ang = sgn * 2. * M_PI * (double)k / (double)n;
+		wr[k] = cos(ang); wi[k] = sin(ang);
+	}
+	for(len = 2; len <= n; len <<= 1) {
+		const int half = len >> 1, stride = n / len;
+		for(i = 0; i < n; i += len) {
+			for(k = 0; k < half; ++k) {
+				/* std::complex multiplication: (a+bi)(c+di) = (ac - bd) + (ad + bc)i */
+				const double a = re[i + k + half], b = im[i + k + half];
+				const double c = wr[k * stride], d = wi[k * stride];
+				const double tr = a * c - b * d, ti = a * d + b * c;
+				const double ur = re[i + k], ui = im[i + k];
+				re[i + k] = ur + tr; im[i + k] = ui + ti;
+				re[i + k + half] = ur - tr; im[i + k + half] = ui - ti;
+			}
+		}
+	}
+	free(wr); free(wi);
+}
+
+/* BlackScholesJumpDiffusion::b (BlackScholes.hpp:389-459): b_i = lambda h(log S_i),
+ * h = circular correlation of V(exp(x0 + k dx)) with the density weights. */
+void qpo_jump_term(int n, const double *S, const double *v, double lambda, int N,
+		double x0, double dx, const double *weights, double *b) {
+	double *re = (double *)malloc(sizeof(double) * (size_t)N);
+	double *im = (double *)calloc((size_t)N, sizeof(double));
+	double *wr = (double *)malloc(sizeof(double) * (size_t)N);
+	double *wi = (double *)calloc((size_t)N, sizeof(double));
+	double *F = (double *)malloc(sizeof(double) * (size_t)N);
+	const double xf = log(S[n - 2]);
+	const double dxu = (xf - x0) / (N - 1);     /* Axis::uniform(x0, xf, N), Axis.hpp:219-226 */
+	int i;
+	(void)dx;
+	for(i = 0; i < N; ++i) {
+		re[i] = qpo_interp(n, S, v, exp(x0 + i * dx));
+		wr[i] = weights[i];
+		F[i] = x0 + dxu * i;
+	}
+	fft_inplace(N, re, im, 0);
+	fft_inplace(N, wr, wi, 0);
+	for(i = 0; i < N; ++i) {
+		/* bufferFFT[i] *= conj(fprimeFFT[i]) */
+		const double a = re[i], bb = im[i], c = wr[i], d = -wi[i];
+		re[i] = a * c - bb * d; im[i] = a * d + bb * c;
+	}
+	fft_inplace(N, re, im, 1);
+	{
+		const double s = 1. / (double)N;
+		for(i = 0; i < N; ++i) re[i] = re[i] * s;
+	}
+	b[0] = 0.;
+	for(i = 1; i < n - 1; ++i) b[i] = lambda * qpo_interp(N, F, re, log(S[i]));
+	b[n - 1] = 0.;
+	free(re); free(im); free(wr); free(wi); free(F);
+}
+
+/* ------------------------------------------------------------------------ */
 /* Tridiagonal LU with row partial pivoting, natural order.  Same operation  */
 /* order as oracle/shim's banded SparseLU stand-in with kl = ku = 1 (the     */
 /* pivot policy Eigen::SparseLU defaults to: keep the diagonal unless a      */
@@ -336,6 +522,7 @@ int qpo_sweep_1d(const qpo_problem *p, double *V, int *inner,
 	double *xprev = (double *)malloc(sizeof(double) * (size_t)n);
 	double *v1 = (double *)malloc(sizeof(double) * (size_t)n); /* iterand(0) */
 	double *v0 = (double *)malloc(sizeof(double) * (size_t)n); /* iterand(1) */
+	double *bj = (double *)calloc((size_t)n, sizeof(double)); /* op.b(): explicit jump term or 0 */
 	tri_lu lu;
 	int s, i, status = 0;
 	/* stepper history: times of iterand(0), iterand(1) */
@@ -384,6 +571,12 @@ int qpo_sweep_1d(const qpo_problem *p, double *V, int *inner,
 		 * (IterativeMethod.hpp:143-146) */
 		if(p->american) a_same = 0;
 
+		/* --- explicit jump term: BlackScholesJumpDiffusion::b at iterand(0) -- */
+		if(p->jump_weights) {
+			qpo_jump_term(n, p->S, v1, p->jump_lambda, p->jump_nfft, p->jump_x0,
+					p->jump_dx, p->jump_weights, bj);
+		}
+
 		/* --- left-hand side  lA  and right-hand side  lb ----------------- */
 		{
 			const double h0 = time1 - t; /* difference(t1, t0), reverse time */
@@ -398,7 +591,7 @@ int qpo_sweep_1d(const qpo_problem *p, double *V, int *inner,
 					M_lo[i] = hh * p->lo[i];
 					M_di[i] = 1. + hh * p->di[i];
 					M_up[i] = hh * p->up[i];
-					lb[i] = ((c1 * v1[i] - c0 * v0[i]) / den + 0.) * hh;
+					lb[i] = ((c1 * v1[i] - c0 * v0[i]) / den + bj[i]) * hh;
 				}
 			} else if(use_cn == 1) {
 				/* Rannacher.hpp:50-73 */
@@ -414,7 +607,7 @@ int qpo_sweep_1d(const qpo_problem *p, double *V, int *inner,
 					if(i > 0) acc += (0. - p->lo[i] * h0 / 2.) * v1[i - 1];
 					acc += (1. - p->di[i] * h0 / 2.) * v1[i];
 					if(i < n - 1) acc += (0. - p->up[i] * h0 / 2.) * v1[i + 1];
-					lb[i] = acc + (0. + 0.) / 2.;
+					lb[i] = acc + (bj[i] + bj[i]) / 2.;
 				}
 			} else if(use_cn == 2) {
 				/* CrankNicolson.hpp:52-78 with theta = 1/2 */
@@ -430,7 +623,7 @@ int qpo_sweep_1d(const qpo_problem *p, double *V, int *inner,
 					if(i > 0) acc += (0. - p->lo[i] * (1 - theta) * h0) * v1[i - 1];
 					acc += (1. - p->di[i] * (1 - theta) * h0) * v1[i];
 					if(i < n - 1) acc += (0. - p->up[i] * (1 - theta) * h0) * v1[i + 1];
-					lb[i] = acc + (theta * 0. + (1 - theta) * 0.);
+					lb[i] = acc + (theta * bj[i] + (1 - theta) * bj[i]);
 				}
 			} else {
 				/* implicit Euler: Rannacher.hpp:32-48 / BDF.hpp:32-46 */
@@ -439,7 +632,7 @@ int qpo_sweep_1d(const qpo_problem *p, double *V, int *inner,
 					M_lo[i] = p->lo[i] * h0;
 					M_di[i] = 1. + p->di[i] * h0;
 					M_up[i] = p->up[i] * h0;
-					lb[i] = v1[i] + 0. * h0;
+					lb[i] = p->scheme == QPO_SCHEME_RANNACHER ? v1[i] + bj[i] * h0 : v1[i] + h0 * bj[i];
 				}
 			}
 		}
@@ -583,6 +776,6 @@ int qpo_sweep_1d(const qpo_problem *p, double *V, int *inner,
 
 	tri_free(&lu);
 	free(A_lo); free(A_di); free(A_up); free(M_lo); free(M_di); free(M_up);
-	free(P_di); free(lb); free(rhs); free(x); free(xprev); free(v1); free(v0);
+	free(bj); free(P_di); free(lb); free(rhs); free(x); free(xprev); free(v1); free(v0);
 	return status;
 }

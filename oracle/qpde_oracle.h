@@ -55,6 +55,17 @@ void qpo_bs_coeffs(int n, const double *S, const double *r, const double *v,
 		const double *q, const double *lambda, double kappa,
 		double *lo, double *di, double *up);
 
+/* Jump-diffusion set-up and explicit jump term
+ * (Modules/Operators/BlackScholes.hpp:53-62, 275-329, 389-459). */
+enum { QPO_DENSITY_LOGNORMAL = 0, QPO_DENSITY_DOUBLE_EXPONENTIAL = 1 };
+int qpo_jump_nfft(int n);
+/* weights must hold qpo_jump_nfft(n) doubles.  lognormal: p0 = mu, p1 = sigma;
+ * double exponential: p0 = p, p1 = eta_1, p2 = eta_2. */
+void qpo_jump_setup(int n, const double *S, int density_kind, double p0, double p1,
+		double p2, double *x0, double *dx, double *weights, double *kappa);
+void qpo_jump_term(int n, const double *S, const double *v, double lambda, int N,
+		double x0, double dx, const double *weights, double *b);
+
 /* Piecewise-linear read-out (Core/Interpolant.hpp:153-181,331-374). */
 double qpo_interp(int n, const double *x, const double *v, double c);
 
@@ -78,6 +89,10 @@ typedef struct {
 	int n_controls;        /* > 0: PolicyIteration over this many control values */
 	int policy_max;        /* 1: MaxPolicyIteration, 0: MinPolicyIteration */
 	const double *plo, *pdi, *pup; /* [n_controls][n] operator rows per control */
+	/* jump diffusion (NULL weights = none): b() of the operator is the explicit
+	 * correlation integral; lo/di/up must already carry lambda and kappa */
+	const double *jump_weights; int jump_nfft;
+	double jump_lambda, jump_x0, jump_dx;
 	int solver;            /* 0: pivoted LU (the reference's policy);
 	                          1: arithmetic model of the INTERLEAVED kernel   */
 } qpo_problem;

@@ -320,6 +320,66 @@ int runHjb(const Args &a) {
 	return 0;
 }
 
+////////////////////////////////////////////////////////////////////////////////
+// jump: European call under Merton (lognormal) or Kou (double-exponential) jump
+// diffusion, BDF1 with the explicit correlation-integral jump term
+// (examples/jump_diffusion.cpp:43-140).  Also dumps what the operator computed
+// at construction: the log-grid (N, x0, dx), the density weights and kappa.
+////////////////////////////////////////////////////////////////////////////////
+
+int runJump(const Args &a) {
+	const Real K = num(a, "K", 100.), S0 = num(a, "S0", K);
+	const Real r = num(a, "r", .05), vol = num(a, "vol", .15);
+	const Real q = num(a, "q", 0.), T = num(a, "T", .25);
+	const Real lambda = num(a, "lambda", .1);
+	const long steps = integer(a, "steps", 12);
+	const int refine = (int) integer(a, "refine", 0);
+	const bool kou = str(a, "density", "lognormal") == "kou";
+	const Real mu = num(a, "mu", -.1), sd = num(a, "sd", .45);
+	const Real p_up = num(a, "p_up", .3445), eta1 = num(a, "eta1", 3.0465), eta2 = num(a, "eta2", 3.0775);
+	const std::string scheme = str(a, "scheme", "bdf1");
+	const int repeat = (int) integer(a, "repeat", 1);
+
+	RectilinearGrid1 coarse( (S0 * Axis::special) + (K * Axis::special)
+			+ (S0 * Axis { 1000. }) + (K * Axis { 1000. }) );   // jump_diffusion.cpp:166
+	auto grid = coarse.refined(refine);
+	auto payoff = callPayoff(K);
+
+	double seconds = 0.;
+	std::vector<double> values;
+	long timesteps = 0;
+
+	for(int rep = 0; rep < repeat; ++rep) {
+		ReverseConstantStepper stepper(0., T, T / steps);
+		auto density = kou ? doubleExponential(p_up, eta1, eta2) : lognormal(mu, sd);
+		BlackScholesJumpDiffusion1 bs(grid, r, vol, q, lambda, density);
+		bs.setIteration(stepper);
+
+		std::unique_ptr<IterationNode> discretization;
+		if(scheme == "bdf2") discretization.reset(new ReverseBDFTwo(grid, bs));
+		else                 discretization.reset(new ReverseBDFOne(grid, bs));
+		discretization->setIteration(stepper);
+
+		SparseLUSolver solver;
+		auto begin = std::chrono::steady_clock::now();
+		auto solution = stepper.solve(grid, payoff, *discretization, solver);
+		auto end = std::chrono::steady_clock::now();
+		seconds += std::chrono::duration<double>(end - begin).count();
+
+		if(rep == 0) {
+			values = nodeValues(grid, solution);
+			timesteps = (long) stepper.iterations()[0];
+			std::printf("value %a\n", (double) solution(S0));
+		}
+	}
+
+	std::printf("seconds %.9g\n", seconds / repeat);
+	std::printf("steps %ld\n", timesteps);
+	dumpReals("S", nodes(grid));
+	dumpReals("V", values);
+	return 0;
+}
+
 void usage() {
 	std::fprintf(stderr,
 		"qpde_ref vanilla  K= S0= r= vol= q= T= steps= refine= american=0|1 "
@@ -327,7 +387,9 @@ void usage() {
 		"qpde_ref bermudan K= r= alpha= q= T= steps= E= refine= "
 		"scheme=bdf2|bdf1|rannacher|cn axis= repeat=\n"
 		"qpde_ref hjb      K= S0= r_l= r_b= vol= q= T= steps= refine= long=0|1 "
-		"scheme=bdf2|bdf1 repeat=\n");
+		"scheme=bdf2|bdf1 repeat=\n"
+		"qpde_ref jump     K= S0= r= vol= q= T= lambda= steps= refine= density=lognormal|kou "
+		"mu= sd= p_up= eta1= eta2= scheme=bdf1|bdf2 repeat=\n");
 }
 
 } // namespace
@@ -345,6 +407,7 @@ int main(int argc, char **argv) {
 	if(mode == "vanilla")  return runVanilla(a);
 	if(mode == "bermudan") return runBermudan(a);
 	if(mode == "hjb")      return runHjb(a);
+	if(mode == "jump")     return runJump(a);
 	usage();
 	return 2;
 }

@@ -54,6 +54,9 @@ class Batch(C.Structure):
         ("spot", _dp),
         ("n_controls", C.c_int32), ("policy_max", C.c_int32),
         ("controls", _dp), ("controls_stride", C.c_int64),
+        ("jump_lambda", _dp), ("jump_kappa", _dp), ("jump_x0", _dp), ("jump_dx", _dp),
+        ("jump_weights", _dp), ("jump_weights_stride", C.c_int64),
+        ("n_fft", C.c_int32), ("reserved2", C.c_int32),
         ("kernel", C.c_int32), ("outputs", C.c_int32),
     ]
 
@@ -78,7 +81,7 @@ EXPORTS = [
     "qpde_host_free", "qpde_make_schedule", "qpde_refined_size", "qpde_bs1d_sweep",
     "qpde_bs1d_plan_create", "qpde_bs1d_plan_run", "qpde_bs1d_plan_fetch",
     "qpde_bs1d_plan_destroy", "qpde_bs1d_plan_kernel", "qpde_bs1d_plan_nodes",
-    "qpde_bs1d_plan_max_steps",
+    "qpde_bs1d_plan_max_steps", "qpde_jump_nfft", "qpde_jump_setup", "qpde_refine_axis",
 ]
 
 _lib = None
@@ -122,6 +125,9 @@ def lib():
         L.qpde_bs1d_plan_kernel.argtypes = [C.c_void_p]
         L.qpde_bs1d_plan_nodes.argtypes = [C.c_void_p]
         L.qpde_bs1d_plan_max_steps.argtypes = [C.c_void_p]
+        L.qpde_jump_nfft.argtypes = [C.c_int]
+        L.qpde_jump_setup.argtypes = [C.c_int, _dp, C.c_int, _dp, _dp, _dp, _dp, _dp]
+        L.qpde_refine_axis.argtypes = [_dp, C.c_int, C.c_int, _dp]
         _lib = L
     return _lib
 
@@ -143,6 +149,30 @@ def make_schedule(T, dt, event_times=()):
     buf = (Step * n)()
     lib().qpde_make_schedule(T, dt, evp, len(ev), buf, n)
     return buf
+
+
+def refine_axis(axis, refine):
+    """RectilinearGrid1(axis).refined(refine) on the host (no GPU needed)."""
+    axis = np.ascontiguousarray(axis, dtype=np.float64)
+    out = np.zeros(refined_size(len(axis), refine))
+    n = lib().qpde_refine_axis(axis.ctypes.data_as(_dp), len(axis), refine, out.ctypes.data_as(_dp))
+    assert n == len(out)
+    return out
+
+
+def jump_setup(S, density="lognormal", params=(-0.1, 0.45)):
+    """(x0, dx, kappa, weights): the host-side set-up of BlackScholesJumpDiffusion (no GPU needed)."""
+    S = np.ascontiguousarray(S, dtype=np.float64)
+    nfft = lib().qpde_jump_nfft(len(S))
+    w = np.zeros(nfft)
+    par = np.zeros(3); par[:len(params)] = params
+    x0, dx, kappa = C.c_double(), C.c_double(), C.c_double()
+    rc = lib().qpde_jump_setup(len(S), S.ctypes.data_as(_dp), 1 if density == "kou" else 0,
+                               par.ctypes.data_as(_dp), C.byref(x0), C.byref(dx), C.byref(kappa),
+                               w.ctypes.data_as(_dp))
+    if rc != OK:
+        raise QpdeError(rc, "qpde_jump_setup")
+    return x0.value, dx.value, kappa.value, w
 
 
 def refined_size(n_axis, refine):
@@ -196,7 +226,7 @@ class BatchSpec:
                  obstacle_array=None, vol_model="const", sigma_nodes=None,
                  n_exercise=0, exercise="k_minus_s", spot=None, tolerance=1e-6, scale=1.0,
                  penalty_tolerance=1e-6, max_inner=100, kernel="auto", outputs=OUT_ALL,
-                 n_contracts=None, controls=None, policy_max=False):
+                 n_contracts=None, controls=None, policy_max=False, jump=None):
         axis = np.ascontiguousarray(axis, dtype=np.float64)
         if n_contracts is None:
             n_contracts = axis.shape[0] if axis.ndim == 2 else len(np.atleast_1d(strike))
@@ -247,6 +277,12 @@ class BatchSpec:
         b.tolerance, b.scale, b.penalty_tolerance = tolerance, scale, penalty_tolerance
         if spot is not None:
             b.spot = vec(spot)
+        if jump is not None:
+            # jump = dict(lam=[C], kappa=[C], x0=[C], dx=[C], weights=[C][n_fft] or [n_fft])
+            b.jump_lambda, b.jump_kappa = vec(jump["lam"]), vec(jump["kappa"])
+            b.jump_x0, b.jump_dx = vec(jump["x0"]), vec(jump["dx"])
+            b.jump_weights, b.jump_weights_stride = rows(jump["weights"])
+            b.n_fft = np.asarray(jump["weights"]).shape[-1]
         if controls is not None:
             ctl = np.ascontiguousarray(controls, dtype=np.float64)
             self.keep.append(ctl)

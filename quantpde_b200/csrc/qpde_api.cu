@@ -39,6 +39,8 @@ struct qpde_bs1d_plan {
 	DeviceBatch b;
 	DeviceResult out;
 	InterleavedWork w;
+	JumpWork jw;
+	bool jump;
 	int kernel;
 	int outputs;
 	std::vector<void *> allocations;
@@ -299,6 +301,21 @@ static int plan_create_impl(qpde_handle *h, const qpde_bs1d_batch *in,
 			return fail(h, QPDE_ERR_INVALID, "policy iteration: tolerance, scale > 0 and max_inner >= 1 required");
 		}
 	}
+	if(in->jump_lambda) {
+		if(!in->jump_kappa || !in->jump_x0 || !in->jump_dx || !in->jump_weights) {
+			return fail(h, QPDE_ERR_INVALID, "jump diffusion: kappa, x0, dx and weights are required (qpde_jump_setup)");
+		}
+		if(in->n_fft != qpde_jump_nfft(qpde_refined_size(in->n_axis, in->refine))) {
+			return fail(h, QPDE_ERR_INVALID, "jump diffusion: n_fft must be qpde_jump_nfft(N)");
+		}
+		if(in->jump_weights_stride != 0 && in->jump_weights_stride < in->n_fft) return fail(h, QPDE_ERR_INVALID, "jump_weights_stride < n_fft");
+		if(in->american || in->n_controls != 0 || in->n_exercise > 0) {
+			return fail(h, QPDE_ERR_UNSUPPORTED, "jump diffusion with a penalty constraint, controls or events is not supported");
+		}
+		if(in->scheme != QPDE_SCHEME_BDF1 && in->scheme != QPDE_SCHEME_BDF2) {
+			return fail(h, QPDE_ERR_UNSUPPORTED, "jump diffusion needs scheme BDF1 or BDF2");
+		}
+	}
 	if(in->n_exercise < 0) return fail(h, QPDE_ERR_INVALID, "n_exercise < 0");
 	if(in->n_exercise > 0 && !is_generator(in->exercise_kind)) return fail(h, QPDE_ERR_INVALID, "exercise_kind must be a generator");
 	for(int c = 0; c < C; ++c) {
@@ -314,6 +331,8 @@ static int plan_create_impl(qpde_handle *h, const qpde_bs1d_batch *in,
 	memset(&p->b, 0, sizeof(p->b));
 	memset(&p->out, 0, sizeof(p->out));
 	memset(&p->w, 0, sizeof(p->w));
+	memset(&p->jw, 0, sizeof(p->jw));
+	p->jump = in->jump_lambda != nullptr;
 	DeviceBatch &b = p->b;
 	b.C = C;
 	b.n_axis = in->n_axis; b.refine = in->refine;
@@ -350,6 +369,15 @@ static int plan_create_impl(qpde_handle *h, const qpde_bs1d_batch *in,
 	if(in->strike) QPDE_TRY(upload_vec(p, in->strike, C, &b.strike));
 	else           QPDE_TRY(upload_vec(p, in->spot, C, &b.strike));
 	if(in->spot) QPDE_TRY(upload_vec(p, in->spot, C, &b.spot));
+	if(p->jump) {
+		b.n_fft = in->n_fft;
+		QPDE_TRY(upload_vec(p, in->jump_lambda, C, &b.jump_lambda));
+		QPDE_TRY(upload_vec(p, in->jump_kappa, C, &b.jump_kappa));
+		QPDE_TRY(upload_vec(p, in->jump_x0, C, &b.jump_x0));
+		QPDE_TRY(upload_vec(p, in->jump_dx, C, &b.jump_dx));
+		QPDE_TRY(upload_rows(p, in->jump_weights, in->jump_weights_stride, C, in->n_fft,
+			&b.jump_weights, &b.jump_weights_stride));
+	}
 	if(in->n_controls > 0) {
 		QPDE_TRY(upload_rows(p, in->controls, in->controls_stride, C, in->n_controls, &b.controls, &b.controls_stride));
 	}
@@ -378,10 +406,23 @@ static int plan_create_impl(qpde_handle *h, const qpde_bs1d_batch *in,
 
 	// kernel choice
 	int kernel = in->kernel;
+	if(p->jump) {
+		// the jump-diffusion sweep exists in the RESIDENT family only
+		if(kernel == QPDE_KERNEL_INTERLEAVED || !jump_supported(b)) {
+			qpde_bs1d_plan_destroy(p);
+			return fail(h, QPDE_ERR_UNSUPPORTED, "jump diffusion: N = %d, n_fft = %d is not supported by the RESIDENT family", N, b.n_fft);
+		}
+		kernel = QPDE_KERNEL_RESIDENT;
+		QPDE_TRY(dev_alloc(p, &p->jw.g_idx, (size_t)C * b.n_fft));
+		QPDE_TRY(dev_alloc(p, &p->jw.g_w, (size_t)C * b.n_fft));
+		QPDE_TRY(dev_alloc(p, &p->jw.n_idx, (size_t)C * N));
+		QPDE_TRY(dev_alloc(p, &p->jw.n_w, (size_t)C * N));
+		QPDE_TRY(dev_alloc(p, &p->jw.fw, (size_t)C * b.n_fft));
+	}
 	if(kernel == QPDE_KERNEL_AUTO) {
 		kernel = resident_supported(b) ? QPDE_KERNEL_RESIDENT : QPDE_KERNEL_INTERLEAVED;
 	}
-	if(kernel == QPDE_KERNEL_RESIDENT && !resident_supported(b)) {
+	if(kernel == QPDE_KERNEL_RESIDENT && !p->jump && !resident_supported(b)) {
 		qpde_bs1d_plan_destroy(p);
 		return fail(h, QPDE_ERR_UNSUPPORTED, "the RESIDENT kernel does not support N = %d with this configuration", N);
 	}
@@ -418,7 +459,10 @@ int qpde_bs1d_plan_run(qpde_bs1d_plan *p) {
 	if(!p) return fail(nullptr, QPDE_ERR_INVALID, "plan_run: NULL plan");
 	qpde_handle *h = p->h;
 	QPDE_CUDA(h, cudaSetDevice(h->device));
-	if(p->kernel == QPDE_KERNEL_INTERLEAVED) {
+	if(p->jump) {
+		int rc = launch_jump(p->b, p->jw, p->out, h->stream, &h->launches);
+		if(rc != QPDE_OK) return fail(h, rc, "launch_jump failed");
+	} else if(p->kernel == QPDE_KERNEL_INTERLEAVED) {
 		launch_interleaved(p->b, p->w, p->out, h->stream, &h->launches);
 	} else {
 		int rc = launch_resident(p->b, p->out, h->stream, h->sm_count, &h->launches);

@@ -1,0 +1,417 @@
+// qpde_jump.cu — jump-diffusion sweep: one CTA per contract, the European
+// backward sweep of BlackScholesJumpDiffusion1 under ReverseBDFOne / BDFTwo with
+// the jump integral treated explicitly (d'Halluin, Forsyth & Vetzal's
+// correlation-integral method), everything of one contract on chip.
+//
+// Reference call stack replaced:
+//   BlackScholesJumpDiffusion::b      Modules/Operators/BlackScholes.hpp:389-459
+//     V(exp(x0 + k dx)) by PiecewiseLinear   Core/Interpolant.hpp:153-181,331-374
+//     Eigen::FFT fwd / inv (3 transforms of n_fft per step)
+//     h(log S_i) by PiecewiseLinear on the uniform log-grid
+//   BlackScholes::A with lambda, kappa       Modules/Operators/BlackScholes.hpp:136-226
+//   BDFOne / BDFTwo ::A, ::b                 Core/BDF.hpp:32-117
+//   SparseLUSolver                           Bindings/Eigen.hpp:143-165
+//
+// Per time step: (1) gather V onto the log-grid through a per-contract
+// interpolation table, written bit-reversed into shared memory; (2) a
+// hand-written radix-2 FFT pair in shared memory (forward decimation-in-time,
+// multiply by the conjugate spectrum of the density weights, inverse
+// decimation-in-frequency) — no cuFFT; (3) interpolate h back at log S_i and
+// add h0 * lambda * h to the BDF right-hand side; (4) the partition solve with
+// the cached factorisation (the matrix is constant in time).
+//
+// The circular, un-padded correlation of the reference is reproduced as is.
+#include <math_constants.h>
+
+#include "qpde_kernels.cuh"
+#include "qpde_partition.cuh"
+
+namespace qpde {
+
+namespace {
+
+constexpr int JUMP_ROW_ARRAYS = 5;  // S, lo, di, up, V
+
+struct JumpSmem {
+	PartitionSmem ps;
+	struct Tail { double S, di, x, bd, invb, vprev, c, h; } tail;
+};
+
+inline size_t jump_smem_bytes(int M, int P, int NF) {
+	// row arrays [M][P] (+1 slot of V for the tail node), complex work buffer
+	// [NF], twiddles [NF / 2]
+	return sizeof(JumpSmem) + sizeof(double) * ((size_t)JUMP_ROW_ARRAYS * M * P + 2)
+		+ sizeof(double2) * ((size_t)NF + NF / 2);
+}
+
+__device__ __forceinline__ double2 cmul(double2 a, double2 b) {
+	return make_double2(fma(a.x, b.x, -(a.y * b.y)), fma(a.x, b.y, a.y * b.x));
+}
+
+// In-place radix-2 FFT of `buf` (NF complex points in shared memory) by the
+// whole CTA.  forward = decimation in time: input bit-reversed, output natural,
+// kernel exp(-2 pi i jk / NF).  inverse = decimation in frequency: input
+// natural, output bit-reversed, kernel exp(+2 pi i jk / NF), unscaled.
+// tw[k] = exp(-2 pi i k / NF), k < NF / 2.  Ends with a barrier.
+template <int PT>
+__device__ __forceinline__ void fft_forward_dit(double2 *buf, const double2 *tw, int NF, int logNF, int tid) {
+	for(int s = 0; s < logNF; ++s) {
+		const int half = 1 << s;
+		const int shift = logNF - 1 - s;          // twiddle stride = NF / (2 half)
+		for(int bfly = tid; bfly < NF / 2; bfly += PT) {
+			const int k = bfly & (half - 1);
+			const int i = ((bfly >> s) << (s + 1)) | k;
+			const double2 u = buf[i];
+			const double2 t = cmul(buf[i + half], tw[k << shift]);
+			buf[i] = make_double2(u.x + t.x, u.y + t.y);
+			buf[i + half] = make_double2(u.x - t.x, u.y - t.y);
+		}
+		__syncthreads();
+	}
+}
+
+template <int PT>
+__device__ __forceinline__ void fft_inverse_dif(double2 *buf, const double2 *tw, int NF, int logNF, int tid) {
+	for(int s = logNF - 1; s >= 0; --s) {
+		const int half = 1 << s;
+		const int shift = logNF - 1 - s;
+		for(int bfly = tid; bfly < NF / 2; bfly += PT) {
+			const int k = bfly & (half - 1);
+			const int i = ((bfly >> s) << (s + 1)) | k;
+			const double2 u = buf[i], v = buf[i + half];
+			const double2 w = tw[k << shift];
+			const double2 d = make_double2(u.x - v.x, u.y - v.y);
+			buf[i] = make_double2(u.x + v.x, u.y + v.y);
+			buf[i + half] = cmul(d, make_double2(w.x, -w.y));    // conjugate twiddle
+		}
+		__syncthreads();
+	}
+}
+
+__device__ __forceinline__ int bitrev(int k, int logNF) { return (int)(__brev((unsigned)k) >> (32 - logNF)); }
+
+// linearInterpolationData (Core/Interpolant.hpp:153-181) on ticks given by a functor
+template <typename Tick>
+__device__ __forceinline__ void interp_data(const Tick &x, int length, double ci, int &idx, double &w) {
+	if(ci <= x(0)) { idx = 0; w = 1.; return; }
+	if(ci >= x(length - 1)) { idx = length - 2; w = 0.; return; }
+	int lo = 0, hi = length - 2, mid = 0;
+	w = 0.;
+	while(lo <= hi) {
+		mid = (lo + hi) / 2;
+		if(ci < x(mid)) hi = mid - 1;
+		else if(ci >= x(mid + 1)) lo = mid + 1;
+		else { w = (x(mid + 1) - ci) / (x(mid + 1) - x(mid)); break; }
+	}
+	idx = mid;
+}
+
+// PiecewiseLinear::interpolate for one dimension (:331-374): corners whose
+// factor is <= epsilon are skipped
+__device__ __forceinline__ double interp_apply(double w, double v0, double v1) {
+	double sum = 0.;
+	if(w > DBL_EPSILON) sum += w * v0;
+	if(1. - w > DBL_EPSILON) sum += (1. - w) * v1;
+	return sum;
+}
+
+} // namespace
+
+template <int M, int PT, bool BDF2>
+__global__ void __launch_bounds__(PT, 1)
+k_jump_sweep(DeviceBatch b, JumpWork work, DeviceResult out) {
+	constexpr int P = PT;
+	constexpr int MP = M * P;
+	extern __shared__ __align__(16) unsigned char smem_raw[];
+	JumpSmem &sm = *reinterpret_cast<JumpSmem *>(smem_raw);
+	double *const sm_S  = reinterpret_cast<double *>(smem_raw + sizeof(JumpSmem));
+	double *const sm_lo = sm_S + MP;
+	double *const sm_di = sm_lo + MP;
+	double *const sm_up = sm_di + MP;
+	double *const sm_V  = sm_up + MP;             // [MP + 1]: current solution, node-addressable
+	double2 *const sm_buf = reinterpret_cast<double2 *>(sm_V + MP + 2);   // [NF]
+	const int NF = b.n_fft;
+	double2 *const sm_tw = sm_buf + NF;                                   // [NF / 2]
+	const int logNF = 31 - __clz(NF);
+
+	const int cidx = blockIdx.x;
+	const int tid = threadIdx.x;
+	const int lane = tid & 31, warp = tid >> 5;
+	const int N = b.N;
+	const bool has_tail = N == P * M + 1;
+	const int n_main = has_tail ? N - 1 : N;
+	const int i0 = tid * M;
+	const bool tail_owner = has_tail && tid == P - 1;
+
+	const double K = b.strike[cidx];
+	const double lambda = b.jump_lambda[cidx], kappa = b.jump_kappa[cidx];
+	const double x0 = b.jump_x0[cidx], dxg = b.jump_dx[cidx];
+	int *const g_idx = work.g_idx + (size_t)cidx * NF;
+	double *const g_w = work.g_w + (size_t)cidx * NF;
+	int *const n_idx = work.n_idx + (size_t)cidx * N;
+	double *const n_w = work.n_w + (size_t)cidx * N;
+	double2 *const fw = work.fw + (size_t)cidx * NF;
+
+	// node i of V / S in shared memory
+	auto at_node = [&] (int i) -> int { return i >= n_main ? MP : (i % M) * P + (i / M); };
+
+	// ------------------------------------------------------------------
+	// Setup
+	// ------------------------------------------------------------------
+	{
+		const double *axis = b.axis + (size_t)cidx * b.axis_stride;
+		for(int j = 0; j < M; ++j) {
+			const int i = i0 + j;
+			sm_S[j * P + tid] = i < n_main ? refined_node(axis, b.refine, i) : 0.;
+		}
+		if(tid == 0) sm.tail.S = has_tail ? refined_node(axis, b.refine, N - 1) : 0.;
+		for(int k = tid; k < NF / 2; k += P) {
+			double sn, cs;
+			sincospi(-2. * (double)k / (double)NF, &sn, &cs);
+			sm_tw[k] = make_double2(cs, sn);
+		}
+	}
+	__syncthreads();
+	auto S_at = [&] (int i) -> double { return i >= n_main ? sm.tail.S : sm_S[(i % M) * P + (i / M)]; };
+	{
+		const double r = b.r[cidx], q = b.q[cidx], sig = b.sigma[cidx];
+		for(int j = 0; j <= M; ++j) {
+			const bool tail = j == M;
+			if(tail && (tid != 0 || !has_tail)) break;
+			const int i = tail ? N - 1 : i0 + j;
+			Row row; row.lo = 0.; row.di = 0.; row.up = 0.;
+			if(tail || i < n_main) {
+				const double Si = S_at(i);
+				const double Sm = i > 0 ? S_at(i - 1) : 0.;
+				const double Sp = i < N - 1 ? S_at(i + 1) : 0.;
+				const double v_i = b.vol_model == QPDE_VOL_NODES
+					? b.sigma_nodes[(size_t)cidx * b.sigma_nodes_stride + i]
+					: vol_value(b.vol_model, sig, Si);
+				row = bs_row(i, N, Sm, Si, Sp, r, v_i, q, lambda, kappa);
+			}
+			if(tail) sm.tail.di = row.di;
+			else { sm_lo[j * P + tid] = row.lo; sm_di[j * P + tid] = row.di; sm_up[j * P + tid] = row.up; }
+		}
+		// interpolation tables
+		// (a) V at exp(x0 + k dx): PiecewiseLinear over the S grid (BlackScholes.hpp:405-414)
+		for(int k = tid; k < NF; k += P) {
+			const double c = exp(x0 + k * dxg);
+			int idx; double w;
+			interp_data(S_at, N, c, idx, w);
+			g_idx[k] = idx; g_w[k] = w;
+		}
+		// (b) h at log S_i: PiecewiseLinear over Axis::uniform(x0, xf, NF) (:293-296, :441-452)
+		const double xf = log(S_at(N - 2));
+		const double du = (xf - x0) / (NF - 1);        // Axis::uniform, Core/Axis.hpp:219-226
+		auto tick = [&] (int k) -> double { return x0 + du * k; };
+		for(int i = tid; i < N; i += P) {
+			int idx = 0; double w = 1.;
+			if(i > 0 && i < N - 1) interp_data(tick, NF, log(S_at(i)), idx, w);
+			n_idx[i] = idx; n_w[i] = w;
+		}
+		// (c) spectrum of the density weights (computeDensityFFT, :326-328)
+		const double *wts = b.jump_weights + (size_t)cidx * b.jump_weights_stride;
+		for(int k = tid; k < NF; k += P) sm_buf[bitrev(k, logNF)] = make_double2(wts[k], 0.);
+	}
+	__syncthreads();
+	fft_forward_dit<PT>(sm_buf, sm_tw, NF, logNF, tid);
+	for(int k = tid; k < NF; k += P) fw[k] = sm_buf[k];
+	__threadfence_block();
+	__syncthreads();
+
+	// ---- per-thread state ------------------------------------------------
+	double x[M], vprev[BDF2 ? M : 1];
+	double x_next;
+	PartitionSolver<M, PT> ps; ps.init();
+	auto initial_value = [&] (int i) -> double {
+		return b.payoff_kind == QPDE_PAYOFF_ARRAY
+			? b.payoff[(size_t)cidx * b.payoff_stride + i]
+			: payoff_value(b.payoff_kind, S_at(i), K);
+	};
+#pragma unroll
+	for(int j = 0; j < M; ++j) {
+		x[j] = i0 + j < n_main ? initial_value(i0 + j) : 0.;
+		if(BDF2) vprev[j] = 0.;
+	}
+	if(tail_owner) { sm.tail.x = initial_value(N - 1); sm.tail.vprev = 0.; sm.tail.c = 0.; sm.tail.bd = 1.; sm.tail.invb = 1.; sm.tail.h = 0.; }
+	x_next = 0.;
+	__syncthreads();
+
+	Replay rp; rp.start(b.T[cidx], b.dt[cidx], 0);
+	NodeState ns; ns.start(b.scheme);
+	double time1 = rp.T, time0 = rp.T;
+	int cur_kind = -1; double cur_h = 0.;
+	int n_steps = 0;
+	bool more = true;
+
+	while(more) {
+		qpde_step st;
+		more = rp.next(st);
+		const double t = st.t;
+		const int kind = ns.kind();
+		const double h0 = time1 - t;
+		Gamma g; g.kind = kind; g.h = h0;
+		double c1 = 0., c0 = 0., den = 1.;
+		if(BDF2 && kind == STEP_BDF2) {
+			const double h1 = time1 - t, hh0 = time0 - t;
+			g.h = (hh0 * h1) / (hh0 + h1);
+			c1 = hh0 / h1; c0 = h1 / hh0; den = hh0 - h1;
+		}
+		// the matrix I + g.h * A is constant in time: factorise when the step changes
+		if(kind != cur_kind || fabs(g.h - cur_h) > 1e-11 * cur_h) {
+			cur_kind = kind; cur_h = g.h;
+			double aa[M], bb[M], cc[M];
+#pragma unroll
+			for(int j = 0; j < M; ++j) {
+				const int at = j * P + tid;
+				aa[j] = g.off(sm_lo[at]); bb[j] = 1. + g.off(sm_di[at]); cc[j] = g.off(sm_up[at]);
+				if(j == M - 1 && tail_owner) { sm.tail.c = cc[j]; cc[j] = 0.; }
+			}
+			if(tail_owner) { sm.tail.bd = 1. + g.off(sm.tail.di); sm.tail.invb = rcp(sm.tail.bd); }
+			ps.factorize(aa, bb, cc, sm.ps, lane, warp);
+		}
+
+		// ---- (1) V onto the log-grid, bit-reversed ------------------------
+#pragma unroll
+		for(int j = 0; j < M; ++j) sm_V[j * P + tid] = x[j];
+		if(tail_owner) sm_V[MP] = sm.tail.x;
+		__syncthreads();
+		for(int k = tid; k < NF; k += P) {
+			const int idx = g_idx[k];
+			const double vb = interp_apply(g_w[k], sm_V[at_node(idx)], sm_V[at_node(idx + 1)]);
+			sm_buf[bitrev(k, logNF)] = make_double2(vb, 0.);
+		}
+		__syncthreads();
+		// ---- (2) correlation: inv( fwd(Vbar) * conj(fwd(weights)) ) --------
+		fft_forward_dit<PT>(sm_buf, sm_tw, NF, logNF, tid);
+		for(int k = tid; k < NF; k += P) {
+			const double2 f = fw[k];
+			sm_buf[k] = cmul(sm_buf[k], make_double2(f.x, -f.y));
+		}
+		__syncthreads();
+		fft_inverse_dif<PT>(sm_buf, sm_tw, NF, logNF, tid);
+		// sm_buf[bitrev(k)].x / NF = h_k
+		const double inv_nf = 1. / (double)NF;
+		// ---- (3) right-hand side: BDF b() with the explicit jump term ------
+		double r[M];
+#pragma unroll
+		for(int j = 0; j < M; ++j) {
+			const int i = i0 + j;
+			double bj = 0.;
+			if(i > 0 && i < N - 1 && i < n_main) {
+				const int idx = n_idx[i];
+				const double hA = sm_buf[bitrev(idx, logNF)].x * inv_nf;
+				const double hB = sm_buf[bitrev(idx + 1, logNF)].x * inv_nf;
+				bj = lambda * interp_apply(n_w[i], hA, hB);
+			}
+			if(kind == STEP_IMPLICIT) r[j] = x[j] + h0 * bj;                                   // BDF.hpp:40-46
+			else r[j] = ((c1 * x[j] - c0 * vprev[BDF2 ? j : 0]) / den + bj) * g.h;             // BDF.hpp:94-110
+		}
+		double xt_new = 0.;
+		if(tail_owner) {
+			// the last row has b = 0 (BlackScholes.hpp:455-456)
+			const double lbt = kind == STEP_IMPLICIT ? sm.tail.x + h0 * 0.
+				: ((c1 * sm.tail.x - c0 * sm.tail.vprev) / den + 0.) * g.h;
+			xt_new = lbt * sm.tail.invb;
+			r[M - 1] = fma(-sm.tail.c, xt_new, r[M - 1]);
+		}
+		if(BDF2) {
+#pragma unroll
+			for(int j = 0; j < M; ++j) vprev[j] = x[j];
+			if(tail_owner) sm.tail.vprev = sm.tail.x;
+		}
+		// ---- (4) solve ------------------------------------------------------
+		ps.solve(r, x, x_next, sm.ps, lane, warp);
+		if(tail_owner) sm.tail.x = xt_new;
+		__syncthreads();     // sm_buf / sm_V are rewritten by the next step
+
+		++n_steps;
+		time0 = time1; time1 = t;
+		ns.end_step();
+		if(st.event_after) ns.after_event();
+	}
+
+	// ------------------------------------------------------------------
+	// Outputs
+	// ------------------------------------------------------------------
+#pragma unroll
+	for(int j = 0; j < M; ++j) {
+		const int i = i0 + j;
+		if(i < n_main) {
+			if(out.V) out.V[(size_t)cidx * out.V_stride + i] = x[j];
+			if(out.S) out.S[(size_t)cidx * out.S_stride + i] = sm_S[j * P + tid];
+			if(out.active) out.active[(size_t)cidx * out.active_stride + i] = 0;
+		}
+	}
+	if(tail_owner) {
+		if(out.V) out.V[(size_t)cidx * out.V_stride + N - 1] = sm.tail.x;
+		if(out.S) out.S[(size_t)cidx * out.S_stride + N - 1] = sm.tail.S;
+		if(out.active) out.active[(size_t)cidx * out.active_stride + N - 1] = 0;
+	}
+	if(tid == 0) {
+		if(out.n_steps) out.n_steps[cidx] = n_steps;
+		if(out.inner_total) out.inner_total[cidx] = n_steps;
+		if(out.status) out.status[cidx] = 0;
+		if(out.inner) for(int s = 0; s < n_steps; ++s) out.inner[(size_t)cidx * out.inner_stride + s] = 1;
+	}
+	if(out.value) {
+		const double s0 = b.spot ? b.spot[cidx] : K;
+		const double Sfirst = S_at(0), Slast = S_at(N - 1);
+#pragma unroll
+		for(int j = 0; j < M; ++j) {
+			const int i = i0 + j;
+			if(i >= N - 1) continue;
+			const double Si = sm_S[j * P + tid];
+			const double Sp = S_at(i + 1);
+			const double vi = x[j];
+			const double vp = i + 1 >= n_main ? sm.tail.x : (j == M - 1 ? x_next : x[j + 1 < M ? j + 1 : j]);
+			bool mine = false; double wgt = 0.;
+			if(s0 <= Sfirst) { mine = i == 0; wgt = 1.; }
+			else if(s0 >= Slast) { mine = i == N - 2; wgt = 0.; }
+			else if(!(s0 < Si) && !(s0 >= Sp)) { mine = true; wgt = (Sp - s0) / (Sp - Si); }
+			if(mine) out.value[cidx] = interp_apply(wgt, vi, vp);
+		}
+	}
+}
+
+static int jump_geometry(int N, int *M, int *PT) {
+	if(N <= 8 * 64 + 1)  { *M = 8; *PT = 64;  return 1; }
+	if(N <= 8 * 256 + 1) { *M = 8; *PT = 256; return 1; }
+	if(N <= 9 * 256 + 1) { *M = 9; *PT = 256; return 1; }
+	return 0;
+}
+
+bool jump_supported(const DeviceBatch &b) {
+	int M, PT;
+	if(!b.jump_lambda || b.N < 10 || !jump_geometry(b.N, &M, &PT)) return false;
+	if(b.american || b.n_controls > 0 || b.n_exercise > 0) return false;
+	if(b.scheme != QPDE_SCHEME_BDF1 && b.scheme != QPDE_SCHEME_BDF2) return false;
+	if(b.n_fft < 2 || (b.n_fft & (b.n_fft - 1)) != 0 || b.n_fft < b.N || b.n_fft > 4096) return false;
+	return jump_smem_bytes(M, PT, b.n_fft) <= 227 * 1024;
+}
+
+template <int M, int PT, bool BDF2>
+static int launch_jump_variant(const DeviceBatch &b, const JumpWork &w, const DeviceResult &out, cudaStream_t stream) {
+	auto kern = k_jump_sweep<M, PT, BDF2>;
+	const size_t bytes = jump_smem_bytes(M, PT, b.n_fft);
+	if(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes) != cudaSuccess) {
+		return QPDE_ERR_CUDA;
+	}
+	kern<<<b.C, PT, bytes, stream>>>(b, w, out);
+	return QPDE_OK;
+}
+
+int launch_jump(const DeviceBatch &b, const JumpWork &w, const DeviceResult &out,
+		cudaStream_t stream, long long *launches) {
+	int M = 0, PT = 0;
+	if(!jump_supported(b) || !jump_geometry(b.N, &M, &PT)) return QPDE_ERR_UNSUPPORTED;
+	const bool bdf2 = b.scheme == QPDE_SCHEME_BDF2;
+	int rc;
+	if(M == 8 && PT == 64)       rc = bdf2 ? launch_jump_variant<8, 64, true>(b, w, out, stream) : launch_jump_variant<8, 64, false>(b, w, out, stream);
+	else if(M == 8 && PT == 256) rc = bdf2 ? launch_jump_variant<8, 256, true>(b, w, out, stream) : launch_jump_variant<8, 256, false>(b, w, out, stream);
+	else                         rc = bdf2 ? launch_jump_variant<9, 256, true>(b, w, out, stream) : launch_jump_variant<9, 256, false>(b, w, out, stream);
+	if(rc == QPDE_OK) *launches += 1;
+	return rc;
+}
+
+} // namespace qpde

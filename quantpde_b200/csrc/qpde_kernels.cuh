@@ -29,6 +29,8 @@ struct DeviceBatch {
 	const double *spot;
 	int n_controls, policy_max;
 	const double *controls; long long controls_stride;
+	const double *jump_lambda, *jump_kappa, *jump_x0, *jump_dx, *jump_weights;
+	long long jump_weights_stride; int n_fft;
 };
 
 // Device output buffers (contract-major); any pointer may be null.
@@ -52,6 +54,16 @@ struct InterleavedWork {
 
 void launch_interleaved(const DeviceBatch &b, const InterleavedWork &w,
 		const DeviceResult &out, cudaStream_t stream, long long *launches);
+
+// Workspace of the jump-diffusion kernel (qpde_jump.cu), per contract.
+struct JumpWork {
+	int *g_idx; double *g_w;      // [C][n_fft]: V(exp(x0 + k dx)) = w V[idx] + (1 - w) V[idx + 1]
+	int *n_idx; double *n_w;      // [C][N]:     h(log S_i)       = w h[idx] + (1 - w) h[idx + 1]
+	double2 *fw;                  // [C][n_fft]: FFT of the density weights
+};
+bool jump_supported(const DeviceBatch &b);
+int launch_jump(const DeviceBatch &b, const JumpWork &w, const DeviceResult &out,
+		cudaStream_t stream, long long *launches);
 
 // RESIDENT family (qpde_resident.cu): one CTA per contract.
 bool resident_supported(const DeviceBatch &b);

@@ -48,6 +48,21 @@ for lp in (0, 1):
 CASES.append(("hjb_short_bdf1_k1", "hjb",
               dict(steps=40, refine=1, long=0, scheme="bdf1", K=90.0, r_l=0.02, r_b=0.07, vol=0.25, T=0.8)))
 
+# examples/jump_diffusion.cpp: European call, BDF1 + explicit correlation-integral jump term.
+# The Kou cases k = 3, 4 are rows of the reference's own recorded table
+# (examples/jump_diffusion.cpp:184-185: 3.970527 at 265 x 97, 3.971451 at 529 x 192).
+for k in (0, 3, 4):
+    CASES.append(("jump_kou_k%d" % k, "jump",
+                  dict(steps=12 * 2 ** k, refine=k, density="kou", K=100.0, r=0.05, vol=0.15, T=0.25,
+                       p_up=0.3445, eta1=3.0465, eta2=3.0775, **{"lambda": 0.1})))
+for k in (1, 3):
+    CASES.append(("jump_merton_k%d" % k, "jump",
+                  dict(steps=12 * 2 ** k, refine=k, density="lognormal", K=100.0, r=0.05, vol=0.15, T=0.25,
+                       mu=-0.1, sd=0.45, **{"lambda": 0.1})))
+CASES.append(("jump_merton_bdf2", "jump",
+              dict(steps=40, refine=2, density="lognormal", K=90.0, r=0.03, vol=0.25, T=0.5,
+                   mu=-0.2, sd=0.3, scheme="bdf2", **{"lambda": 0.4})))
+
 out = {}
 names = []
 for name, mode, kw in CASES:

@@ -35,6 +35,10 @@ def case_obstacle(kw, S):
     return np.where(S < K, 0.0, S - K) if kw.get("call", 0) else np.where(S < K, K - S, 0.0)
 
 
+def jump_params(kw):
+    return (kw["p_up"], kw["eta1"], kw["eta2"]) if kw["density"] == "kou" else (kw["mu"], kw["sd"])
+
+
 def case_args(golden, name):
     return str(golden[name + "/mode"]), ast.literal_eval(str(golden[name + "/args"]))
 
@@ -44,6 +48,9 @@ def run_oracle_case(po, mode, kw):
         return po.american_put(kw["K"], kw["r"], kw["vol"], kw["T"], kw["steps"], kw["refine"],
                                q=kw.get("q", 0.0), call=bool(kw.get("call", 0)),
                                american=bool(kw["american"]), scheme=kw.get("scheme", "rannacher"))
+    if mode == "jump":
+        return po.jump_call(kw["K"], kw["r"], kw["vol"], kw["T"], kw["lambda"], kw["steps"], kw["refine"],
+                            density=kw["density"], params=jump_params(kw), scheme=kw.get("scheme", "bdf1"))
     if mode == "hjb":
         return po.hjb_straddle(kw["K"], kw["r_l"], kw["r_b"], kw["vol"], kw["T"], kw["steps"], kw["refine"],
                                long_position=bool(kw["long"]), scheme=kw["scheme"])
@@ -62,6 +69,17 @@ def spec_for_case(qpde, po, mode, kw, kernel="auto", copies=1):
             q=kw.get("q", 0.0), T=kw["T"], dt=kw["T"] / kw["steps"], strike=np.full(copies, K),
             scheme=kw.get("scheme", "rannacher"), american=bool(kw["american"]),
             payoff="call" if call else "put", kernel=kernel)
+    if mode == "jump":
+        K = kw["K"]
+        sp = po.special_axis()
+        axis = po.axis_union(po.axis_union(sp * K, sp * K), np.array([K * 1000.0]))
+        S = qpde.refine_axis(axis, kw["refine"])
+        x0, dx, kappa, w = qpde.jump_setup(S, kw["density"], jump_params(kw))   # product host helper
+        return qpde.BatchSpec(
+            axis=np.tile(axis, (copies, 1)), refine=kw["refine"], r=kw["r"], sigma=kw["vol"], q=0.0,
+            T=kw["T"], dt=kw["T"] / kw["steps"], strike=np.full(copies, K), scheme=kw.get("scheme", "bdf1"),
+            american=False, payoff="call", kernel=kernel,
+            jump=dict(lam=kw["lambda"], kappa=kappa, x0=x0, dx=dx, weights=w))
     if mode == "hjb":
         K = kw["K"]
         axis = po.axis_union(po.special_axis() * K, po.special_axis() * K)

@@ -65,6 +65,24 @@ def test_schedule_helper_matches_oracle(qpde, oracle):
                    (b.t, b.dt, b.same_dt, b.event_after, b.user_events)
 
 
+def test_jump_setup_matches_oracle(qpde, oracle):
+    """qpde_jump_setup (product host code) vs the oracle's restatement of the
+    reference's construction-time quadrature: bit-identical x0, dx, kappa, weights."""
+    sp = oracle.special_axis()
+    axis = oracle.axis_union(oracle.axis_union(sp * 100., sp * 100.), np.array([100000.]))
+    for refine, density, params in ((0, "lognormal", (-0.1, 0.45)), (2, "kou", (0.3445, 3.0465, 3.0775)),
+                                    (3, "lognormal", (-0.25, 0.3))):
+        S = qpde.refine_axis(axis, refine)
+        assert np.array_equal(S, oracle.refine(axis, refine))
+        x0, dx, kappa, w = qpde.jump_setup(S, density, params)
+        ox0, odx, ow, okappa = oracle.jump_setup(S, density, params)
+        assert (x0, dx, kappa) == (ox0, odx, okappa)
+        assert np.array_equal(w, ow)
+        assert abs(w.sum() - 1.0) < 1e-3          # the weights are a probability mass function
+    # closed form for the lognormal density: kappa = exp(mu + sigma^2 / 2) - 1
+    assert abs(qpde.jump_setup(S, "lognormal", (-0.1, 0.45))[2] - (np.exp(-0.1 + 0.45 ** 2 / 2) - 1)) < 1e-6
+
+
 def test_refined_size(qpde):
     assert qpde.refined_size(33, 6) == 2049
     assert qpde.refined_size(34, 6) == 2113

@@ -12,7 +12,7 @@ from helpers import case_args, run_oracle_case
 
 def test_golden_cases_bit_exact(oracle, golden):
     names = [str(n) for n in golden["names"]]
-    assert len(names) >= 28
+    assert len(names) >= 34
     for name in names:
         mode, kw = case_args(golden, name)
         out = run_oracle_case(oracle, mode, kw)
@@ -35,6 +35,20 @@ def test_live_reference_when_present(oracle):
     assert np.array_equal(out["V"], ref["V"])
     assert np.array_equal(out["inner"], ref["inner"])
     assert np.array_equal(out["mask"], ref["mask"])
+
+
+def test_reference_known_answer_table(oracle, golden):
+    """The one known-answer table the reference records (examples/jump_diffusion.cpp:179-190,
+    Kou double-exponential jumps, "Tested February 18, 2016"): value and step count per level."""
+    table = {3: (265, 97, 3.970527), 4: (529, 192, 3.971451)}
+    for k, (nodes, steps, value) in table.items():
+        name = "jump_kou_k%d" % k
+        assert len(golden[name + "/S"]) == nodes
+        assert int(golden[name + "/steps"]) == steps
+        assert round(float(golden[name + "/value"]), 6) == value     # the reference, compiled here
+        o = oracle.jump_call(100., .05, .15, .25, .1, 12 * 2 ** k, k, density="kou",
+                             params=(0.3445, 3.0465, 3.0775))
+        assert o["n_steps"] == steps and round(oracle.interp(o["S"], o["V"], 100.), 6) == value
 
 
 def test_axis_special_and_refine(oracle):

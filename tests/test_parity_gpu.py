@@ -29,6 +29,8 @@ def test_golden_cases(qpde, handle, oracle, golden, kernel):
     ran = 0
     for name in [str(n) for n in golden["names"]]:
         mode, kw = case_args(golden, name)
+        if mode == "jump" and kernel == "interleaved":
+            continue                 # the jump-diffusion sweep exists in the RESIDENT family only
         spec = spec_for_case(qpde, oracle, mode, kw, kernel=kernel, copies=3)
         plan = _supported(qpde, handle, spec)
         if plan is None:
@@ -53,7 +55,7 @@ def test_golden_cases(qpde, handle, oracle, golden, kernel):
                                           case_obstacle(kw, S_ref))
                 assert hard == 0, name
             assert rel_err(res.value[c], float(golden[name + "/value"])) <= REL_TOL
-    assert ran >= (28 if kernel == "interleaved" else 1)
+    assert ran >= (28 if kernel == "interleaved" else 30)
 
 
 @pytest.mark.parametrize("kernel", KERNELS)
@@ -159,6 +161,35 @@ def test_policy_batch_vs_oracle(qpde, handle, oracle, kernel):
             assert err <= REL_TOL, "contract %d: %.3e" % (c, err)
             assert np.array_equal(res.inner[c, :o["n_steps"]], o["inner"])
             assert res.status[c] == 0
+
+
+def test_jump_batch_full_size(qpde, handle, oracle):
+    """config-4 shape: Merton jump European calls on the 2113-node grid (34 ticks
+    refined 6x), n_fft = 4096, 768 BDF1 steps; one contract against the oracle."""
+    rng = np.random.default_rng(4)
+    Cn, refine, steps = 6, 6, 768
+    K = rng.uniform(80, 120, Cn); vol = rng.uniform(.1, .3, Cn)
+    sp = oracle.special_axis()
+    axes, jl, jk, jx, jd, jw = [], [], [], [], [], []
+    for c in range(Cn):
+        axis = oracle.axis_union(oracle.axis_union(sp * K[c], sp * K[c]), np.array([K[c] * 1000.0]))
+        S = qpde.refine_axis(axis, refine)
+        x0, dx, kappa, w = qpde.jump_setup(S, "lognormal", (-0.1, 0.45))
+        axes.append(axis); jk.append(kappa); jx.append(x0); jd.append(dx); jw.append(w)
+    spec = qpde.BatchSpec(axis=np.stack(axes), refine=refine, r=0.05, sigma=vol, q=0.0, T=0.25,
+                          dt=0.25 / steps, strike=K, scheme="bdf1", payoff="call",
+                          jump=dict(lam=0.1, kappa=jk, x0=jx, dx=jd, weights=np.stack(jw)))
+    with qpde.Plan(handle, spec) as plan:
+        assert plan.N == 2113
+        plan.run()
+        res = plan.fetch()
+    assert np.all(res.status == 0) and np.all(res.n_steps == 768)
+    for c in (0, Cn - 1):
+        o = oracle.jump_call(K[c], 0.05, vol[c], 0.25, 0.1, steps, refine)
+        assert np.array_equal(res.S[c], o["S"])
+        err = rel_err(res.V[c], o["V"]).max()
+        assert err <= REL_TOL, "contract %d: %.3e" % (c, err)
+        assert rel_err(res.value[c], oracle.interp(o["S"], o["V"], K[c])) <= REL_TOL
 
 
 def test_one_shot_sweep_host_buffers(qpde, handle, oracle):
