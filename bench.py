@@ -30,15 +30,19 @@ N_STEPS = 1000
 ALG_BYTES_PER_NODE_SOLVE = 56   # 7 FP64 vectors per inner solve
 
 
-def contract_parameters(n, rank=0):
+def contract_parameters(n, rank=0, world=1):
     """default_rng(1234); K, sigma, T, r drawn in this
-    order.  Rank k > 0 draws its own disjoint batch from seed 1234 + k."""
-    rng = np.random.default_rng(1234 + rank)
-    K = rng.uniform(50, 150, n)
-    vol = rng.uniform(0.10, 0.60, n)
-    T = rng.uniform(0.25, 2.0, n)
-    r = rng.uniform(0.01, 0.08, n)
-    return K, vol, T, r
+    order for the whole job (n contracts per rank x world ranks); rank k sweeps
+    its contiguous slice (quantpde_b200.shard.contract_slice)."""
+    from quantpde_b200.shard import contract_slice
+    total = n * world
+    rng = np.random.default_rng(1234)
+    K = rng.uniform(50, 150, total)
+    vol = rng.uniform(0.10, 0.60, total)
+    T = rng.uniform(0.25, 2.0, total)
+    r = rng.uniform(0.01, 0.08, total)
+    b, e = contract_slice(total, rank, world)
+    return K[b:e], vol[b:e], T[b:e], r[b:e]
 
 
 SPECIAL = np.array([0., .1, .2, .3, .4, .5, .6, .7, .80, .84, .88, .92, .94, .96, .98, 1.,
@@ -223,7 +227,7 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
     Cn = args.contracts
-    K, vol, T, r = contract_parameters(Cn, rank)
+    K, vol, T, r = contract_parameters(Cn, rank, world)
     axis = np.ascontiguousarray(K[:, None] * SPECIAL[None, :])     # K * Axis::special (S_0 = K)
     handle = capi.Handle(local)
     outputs = capi.OUT_V | capi.OUT_VALUE | capi.OUT_INNER_TOTAL | capi.OUT_STATUS | capi.OUT_STEPS
@@ -273,12 +277,16 @@ def main():
     # ---- e2e: qpde_bs1d_sweep with host buffers, copies inside the timed region
     e2e = None
     if not args.no_e2e:
+        # One call of the reference-facing API per step: host pointers in (the
+        # contract parameters), host pointers out (V[C][N], value, inner_total,
+        # status) into page-locked buffers the caller allocated once.
         e2e_out = capi.OUT_V | capi.OUT_VALUE | capi.OUT_INNER_TOTAL | capi.OUT_STATUS
+        r2 = capi.ResultBuffers(Cn, N, capi.sweep_max_steps(spec), e2e_out, pinned=True)
         e2e_times = []
-        for i in range(1 + min(args.steps, 2)):
+        for i in range(1 + min(args.steps, 3)):
             barrier()
             t0 = time.perf_counter()
-            r2 = capi.sweep(handle, spec, outputs=e2e_out)
+            capi.sweep(handle, spec, outputs=e2e_out, result=r2)
             torch.cuda.synchronize()
             dt_s = time.perf_counter() - t0
             if i > 0:
@@ -286,7 +294,8 @@ def main():
         h2d = axis.nbytes + 6 * 8 * Cn
         d2h = r2.V.nbytes + r2.value.nbytes + r2.inner_total.nbytes + r2.status.nbytes
         e2e_ms = 1e3 * float(np.mean(e2e_times))
-        del r2
+        assert int(r2.inner_total.astype(np.int64).sum()) == inner_sum   # same work as the resident run
+        r2.close()
     if world > 1:
         tt = torch.tensor([total_ms, e2e_ms if not args.no_e2e else 0.0], device="cuda", dtype=torch.float64)
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
@@ -301,7 +310,7 @@ def main():
         e2e = {"value": Cn * world / (e2e_ms_max / 1e3), "unit": "solves/s",
                "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                "ms_per_step": e2e_ms_max,
-               "api": "qpde_bs1d_sweep (host pointers; V[C][N] + value + inner_total + status returned)"}
+               "api": "qpde_bs1d_sweep (host pointers in; V[C][N] + value + inner_total + status out into page-locked host buffers)"}
 
     ms_per_step = total_ms / args.steps
     value = Cn * world / (ms_per_step / 1e3)

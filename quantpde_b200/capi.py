@@ -298,14 +298,29 @@ class BatchSpec:
 class ResultBuffers:
     """Host output buffers for qpde_bs1d_result."""
 
-    def __init__(self, C_, N, max_steps, outputs=OUT_ALL):
+    def __init__(self, C_, N, max_steps, outputs=OUT_ALL, pinned=False):
+        """pinned=True backs the large arrays with qpde_host_alloc (page-locked
+        memory: full-rate, asynchronous D2H); call close() to release them."""
         r = Result()
         self.V = self.S = self.value = self.n_steps = self.inner_total = None
         self.inner = self.active = self.status = None
+        self._pinned = []
+
+        def big(shape):
+            if not pinned:
+                return np.zeros(shape)
+            n = int(np.prod(shape))
+            ptr = C.c_void_p()
+            check(lib().qpde_host_alloc(n * 8, C.byref(ptr)))
+            self._pinned.append(ptr)
+            arr = np.ctypeslib.as_array(C.cast(ptr, _dp), shape=(n,)).reshape(shape)
+            arr[...] = 0.0
+            return arr
+
         if outputs & OUT_V:
-            self.V = np.zeros((C_, N)); r.V = self.V.ctypes.data_as(_dp); r.V_stride = N
+            self.V = big((C_, N)); r.V = self.V.ctypes.data_as(_dp); r.V_stride = N
         if outputs & OUT_S:
-            self.S = np.zeros((C_, N)); r.S = self.S.ctypes.data_as(_dp); r.S_stride = N
+            self.S = big((C_, N)); r.S = self.S.ctypes.data_as(_dp); r.S_stride = N
         if outputs & OUT_VALUE:
             self.value = np.zeros(C_); r.value = self.value.ctypes.data_as(_dp)
         if outputs & OUT_STEPS:
@@ -324,6 +339,13 @@ class ResultBuffers:
             self.status = np.zeros(C_, dtype=np.int32)
             r.status = self.status.ctypes.data_as(C.POINTER(C.c_int32))
         self.struct = r
+
+
+    def close(self):
+        self.V = self.S = None
+        for ptr in self._pinned:
+            lib().qpde_host_free(ptr)
+        self._pinned = []
 
 
 class Plan:
@@ -358,12 +380,15 @@ class Plan:
         self.close()
 
 
-def sweep(handle, spec, outputs=OUT_ALL):
-    """qpde_bs1d_sweep: host buffers in, host buffers out."""
-    N = spec.N
+def sweep_max_steps(spec):
     Tmax = np.max(np.ctypeslib.as_array(spec.struct.T, (spec.C,)) /
                   np.ctypeslib.as_array(spec.struct.dt, (spec.C,)))
-    max_steps = int(np.floor(Tmax)) + 3 + 2 * spec.struct.n_exercise
-    res = ResultBuffers(spec.C, N, max_steps, outputs)
+    return int(np.floor(Tmax)) + 3 + 2 * spec.struct.n_exercise
+
+
+def sweep(handle, spec, outputs=OUT_ALL, result=None):
+    """qpde_bs1d_sweep: host buffers in, host buffers out.  `result` reuses a
+    ResultBuffers (e.g. page-locked) across calls."""
+    res = result if result is not None else ResultBuffers(spec.C, spec.N, sweep_max_steps(spec), outputs)
     check(lib().qpde_bs1d_sweep(handle.ptr, C.byref(spec.struct), C.byref(res.struct)), handle.ptr)
     return res

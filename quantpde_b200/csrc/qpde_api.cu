@@ -488,6 +488,9 @@ int qpde_bs1d_plan_fetch(qpde_bs1d_plan *p, qpde_bs1d_result *r) {
 	if(r->V) {
 		const long long hs = r->V_stride ? r->V_stride : N;
 		if(hs < N) return fail(h, QPDE_ERR_INVALID, "V_stride < N");
+		if(hs == N && o.V_stride == N) {
+			QPDE_CUDA(h, cudaMemcpyAsync(r->V, o.V, sizeof(double) * (size_t)N * C, cudaMemcpyDeviceToHost, h->stream));
+		} else
 		QPDE_CUDA(h, cudaMemcpy2DAsync(r->V, sizeof(double) * hs, o.V, sizeof(double) * o.V_stride,
 			sizeof(double) * N, C, cudaMemcpyDeviceToHost, h->stream));
 	}
