@@ -109,6 +109,7 @@ k_interleaved_sweep(DeviceBatch b, InterleavedWork w, DeviceResult out) {
 			gb.h = (hh0 * h1) / (hh0 + h1);
 			c1 = hh0 / h1; c0 = h1 / hh0; den = hh0 - h1;
 		}
+		const double rden = 1. / den;
 		// IterativeMethod.hpp:906: re-assemble A unless the root says it is the same
 		// (a penalty or policy node in the tree keeps LinearSystem's default: never)
 		if(iterate || !ns.initialized || !ns.a_same(st.same_dt)) gA = gb;
@@ -123,7 +124,7 @@ k_interleaved_sweep(DeviceBatch b, InterleavedWork w, DeviceResult out) {
 				if(kind == STEP_IMPLICIT) {
 					val = vi + 0. * h0;
 				} else if(kind == STEP_BDF2) {
-					val = ((c1 * vi - c0 * xp[at]) / den + 0.) * gb.h;
+					val = (div_by(c1 * vi - c0 * xp[at], den, rden) + 0.) * gb.h;
 				} else {
 					// (I - A h/2) v0, row-major SpMV from zero in column order
 					double acc = 0.;

@@ -257,6 +257,7 @@ k_jump_sweep(DeviceBatch b, JumpWork work, DeviceResult out) {
 			g.h = (hh0 * h1) / (hh0 + h1);
 			c1 = hh0 / h1; c0 = h1 / hh0; den = hh0 - h1;
 		}
+		const double rden = 1. / den;
 		// the matrix I + g.h * A is constant in time: factorise when the step changes
 		if(kind != cur_kind || fabs(g.h - cur_h) > 1e-11 * cur_h) {
 			cur_kind = kind; cur_h = g.h;
@@ -305,13 +306,13 @@ k_jump_sweep(DeviceBatch b, JumpWork work, DeviceResult out) {
 				bj = lambda * interp_apply(n_w[i], hA, hB);
 			}
 			if(kind == STEP_IMPLICIT) r[j] = x[j] + h0 * bj;                                   // BDF.hpp:40-46
-			else r[j] = ((c1 * x[j] - c0 * vprev[BDF2 ? j : 0]) / den + bj) * g.h;             // BDF.hpp:94-110
+			else r[j] = (div_by(c1 * x[j] - c0 * vprev[BDF2 ? j : 0], den, rden) + bj) * g.h;             // BDF.hpp:94-110
 		}
 		double xt_new = 0.;
 		if(tail_owner) {
 			// the last row has b = 0 (BlackScholes.hpp:455-456)
 			const double lbt = kind == STEP_IMPLICIT ? sm.tail.x + h0 * 0.
-				: ((c1 * sm.tail.x - c0 * sm.tail.vprev) / den + 0.) * g.h;
+				: (div_by(c1 * sm.tail.x - c0 * sm.tail.vprev, den, rden) + 0.) * g.h;
 			xt_new = lbt * sm.tail.invb;
 			r[M - 1] = fma(-sm.tail.c, xt_new, r[M - 1]);
 		}

@@ -287,6 +287,7 @@ k_resident_sweep(DeviceBatch b, DeviceResult out) {
 			g.h = (hh0 * h1) / (hh0 + h1);
 			c1 = hh0 / h1; c0 = h1 / hh0; den = hh0 - h1;
 		}
+		const double rden = 1. / den;
 		// (Re)build the system rows when the step kind or size changes.  h0 is a
 		// difference of accumulated times and moves in its last bits from step
 		// to step (by ulp(t) / dt, ~1e-13 relative); moves below 1e-11 relative
@@ -324,8 +325,8 @@ k_resident_sweep(DeviceBatch b, DeviceResult out) {
 				if(tail_owner) sm.tail.lb = sm.tail.x + 0. * h0;
 			} else if(BDF2 && kind == STEP_BDF2) {
 #pragma unroll
-				for(int j = 0; j < M; ++j) lb[j] = ((c1 * x[j] - c0 * vprev[j]) / den + 0.) * g.h;
-				if(tail_owner) sm.tail.lb = ((c1 * sm.tail.x - c0 * sm.tail.vprev) / den + 0.) * g.h;
+				for(int j = 0; j < M; ++j) lb[j] = (div_by(c1 * x[j] - c0 * vprev[j], den, rden) + 0.) * g.h;
+				if(tail_owner) sm.tail.lb = (div_by(c1 * sm.tail.x - c0 * sm.tail.vprev, den, rden) + 0.) * g.h;
 			} else {
 				// (I - A h/2) V^n: row-major SpMV accumulated from zero in column order
 				const double xm = sm_xlast[tid];       // x of row i0 - 1
