@@ -269,7 +269,7 @@ def run_ref(mode, **kw):
     i = 0
     while i < len(toks):
         key = toks[i]
-        if key in ("value",):
+        if key in ("value", "mean_inner", "mean_solver"):
             out[key] = float.fromhex(toks[i + 1]); i += 2
         elif key in ("seconds",):
             out[key] = float(toks[i + 1]); i += 2

@@ -19,6 +19,7 @@
 #include <QuantPDE/Core>
 #include <QuantPDE/Modules/Lambdas>
 #include <QuantPDE/Modules/Operators>
+#include <QuantPDE/Modules/HJBQVI>
 
 #include <chrono>
 #include <cstdio>
@@ -380,6 +381,72 @@ int runJump(const Args &a) {
 	return 0;
 }
 
+////////////////////////////////////////////////////////////////////////////////
+// gmwb: the 2-D (W, A) guaranteed-minimum-withdrawal-benefit HJBQVI with the
+// penalised scheme and BiCGSTAB, wired as examples/hjbqvi/gmwb.cpp:35-208.
+// Fixture generator for the row of SURVEY.md §8(a) that the device path does
+// not cover yet: dumps the solution, both control vectors and the iteration
+// statistics of HJBQVI::solve(refinement).
+////////////////////////////////////////////////////////////////////////////////
+
+int runGmwb(const Args &a) {
+	constexpr int Dimension = 2, SC = 1, IC = 1;
+	const Real T = num(a, "T", 10.), r = num(a, "r", .05), eta = num(a, "eta", 0.);
+	const Real sigma = num(a, "sigma", .2), G = num(a, "G", 10.), k = num(a, "k", .1);
+	const Real c = num(a, "c", 0.), w_0 = num(a, "w0", 100.);
+	const int timesteps = (int) integer(a, "timesteps", 32);
+	const int a_points = (int) integer(a, "a_points", 51);
+	const int control_points = (int) integer(a, "control_points", 3);
+	const int refinement = (int) integer(a, "refine", 0);
+
+	HJBQVI<Dimension, SC, IC> hjbqvi(timesteps,
+		{ (w_0 / 100.) * Axis { 0., 5., 10., 15., 20., 25., 30., 35., 40., 45., 50., 55., 60., 65., 70.,
+			72.5, 75., 77.5, 80., 82., 84., 86., 88., 90., 91., 92., 93., 94., 95., 96., 97., 98., 99.,
+			100., 101., 102., 103., 104., 105., 106., 107., 108., 109., 110., 112., 114., 116., 118., 120.,
+			123., 126., 130., 135., 140., 145., 150., 160., 175., 200., 225., 250., 300., 500., 750., 1000. },
+		  Axis::uniform(0., w_0, a_points) },
+		{ Axis { 0., G } }, { Axis::uniform(0., 1., control_points) }, T,
+		[=] (Real, Real, Real) { return r; },
+		{ [=] (Real, Real w, Real) { return sigma * w; }, [=] (Real, Real, Real) { return 0.; } },
+		{ [=] (Real, Real w, Real av, Real q) { return (r - eta) * w + ((0. < av) ? -q : 0.); },
+		  [=] (Real, Real, Real av, Real q) { return (0. < av) ? -q : 0.; } },
+		[=] (Real, Real, Real av, Real q) { return (0. < av) ? q : 0.; },
+		{ [=] (Real, Real w, Real av, Real z_frac) { const Real z = z_frac * av; return max(w - z, 0.); },
+		  [=] (Real, Real, Real av, Real z_frac) { const Real z = z_frac * av; return av - z; } },
+		[=] (Real, Real w, Real av, Real z_frac) {
+			const Real z = z_frac * av;
+			const Real w_plus = max(w - z, 0.), a_plus = av - z;
+			if( (w - w_plus) + (av - a_plus) < QuantPDE::epsilon ) {
+				return -std::numeric_limits<Real>::infinity();
+			}
+			return (1 - k) * z - c; },
+		[=] (Real, Real w, Real av) { return max(w, (1 - k) * av - c); });
+	hjbqvi.usePenalizedScheme();
+	hjbqvi.useBiCGSTABSolver();
+	hjbqvi.disableStochasticControlRefinement();
+	hjbqvi.coefficientsAreTimeIndependent();
+	hjbqvi.right_boundary(0, HJBQVILinearBoundary<Dimension, SC, IC>);
+	hjbqvi.right_boundary(1, HJBQVIZeroDiffusionRightBoundary<Dimension, SC, IC>);
+
+	auto result = hjbqvi.solve(refinement);
+	PiecewiseLinear<Dimension> u(result.spatial_grid, result.solution_vector);
+	std::printf("value %a\n", (double) u.interpolate({{ w_0, w_0 }}));
+	std::printf("seconds %.9g\n", (double) result.execution_time_seconds);
+	std::printf("steps %d\n", (int) result.timesteps);
+	std::printf("mean_inner %a\n", (double) result.mean_inner_iterations);
+	std::printf("mean_solver %a\n", (double) result.mean_solver_iterations);
+	std::vector<double> W, A, V, Q, Z;
+	for(Index i = 0; i < result.spatial_grid[0].size(); ++i) W.push_back(result.spatial_grid[0][i]);
+	for(Index i = 0; i < result.spatial_grid[1].size(); ++i) A.push_back(result.spatial_grid[1][i]);
+	for(Index i = 0; i < result.solution_vector.size(); ++i) {
+		V.push_back(result.solution_vector(i));
+		Q.push_back(result.stochastic_control_vector[0](i));
+		Z.push_back(result.impulse_control_vector[0](i));
+	}
+	dumpReals("W", W); dumpReals("A", A); dumpReals("V", V); dumpReals("Q", Q); dumpReals("Z", Z);
+	return 0;
+}
+
 void usage() {
 	std::fprintf(stderr,
 		"qpde_ref vanilla  K= S0= r= vol= q= T= steps= refine= american=0|1 "
@@ -389,7 +456,8 @@ void usage() {
 		"qpde_ref hjb      K= S0= r_l= r_b= vol= q= T= steps= refine= long=0|1 "
 		"scheme=bdf2|bdf1 repeat=\n"
 		"qpde_ref jump     K= S0= r= vol= q= T= lambda= steps= refine= density=lognormal|kou "
-		"mu= sd= p_up= eta1= eta2= scheme=bdf1|bdf2 repeat=\n");
+		"mu= sd= p_up= eta1= eta2= scheme=bdf1|bdf2 repeat=\n"
+		"qpde_ref gmwb     T= r= eta= sigma= G= k= c= w0= timesteps= a_points= control_points= refine=\n");
 }
 
 } // namespace
@@ -408,6 +476,7 @@ int main(int argc, char **argv) {
 	if(mode == "bermudan") return runBermudan(a);
 	if(mode == "hjb")      return runHjb(a);
 	if(mode == "jump")     return runJump(a);
+	if(mode == "gmwb")     return runGmwb(a);
 	usage();
 	return 2;
 }

@@ -78,3 +78,17 @@ for name, mode, kw in CASES:
     print(name, ref["steps"], ref["value"])
 out["names"] = np.array(names)
 np.savez_compressed(os.path.join(os.path.dirname(os.path.abspath(__file__)), "reference_cases.npz"), **out)
+
+# ---------------------------------------------------------------------------
+# GMWB (examples/hjbqvi/gmwb.cpp): fixtures of the reference for the §8(a) row 17
+# path that the device code does not cover yet.
+# ---------------------------------------------------------------------------
+gm = {}
+for name, kw in (("gmwb_small", dict(refine=0, a_points=11, timesteps=8, control_points=3)),
+                 ("gmwb_k0", dict(refine=0)), ("gmwb_k1", dict(refine=1))):
+    ref = po.run_ref("gmwb", **kw)
+    gm[name + "/args"] = np.array(repr(kw))
+    for key in ("W", "A", "V", "Q", "Z", "value", "steps", "mean_inner", "mean_solver"):
+        gm[name + "/" + key] = np.asarray(ref[key])
+    print(name, len(ref["W"]), len(ref["A"]), ref["steps"], ref["value"], ref["mean_inner"], ref["mean_solver"])
+np.savez_compressed(os.path.join(os.path.dirname(os.path.abspath(__file__)), "gmwb_reference.npz"), **gm)

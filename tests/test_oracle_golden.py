@@ -113,3 +113,28 @@ def test_american_table_ratio_and_properties(oracle):
     assert all(c > 0 for c in changes)
     assert 2.0 < changes[0] / changes[1] < 8.0 and 2.0 < changes[1] / changes[2] < 8.0
     assert all(1.5 < x < 3.0 for x in its)
+
+
+def test_gmwb_reference_fixture(oracle):
+    """Fixtures of the reference's GMWB example (examples/hjbqvi/gmwb.cpp) for the one
+    §8(a) row the device path does not cover yet.  Checks what can be checked without a
+    restatement: the convergence table's first two values agree with the no-fee GMWB
+    value of the literature (~107.7 at w = a = 100), the solution dominates the exit
+    payoff, controls take grid values; and — when the reference binary is present —
+    that it reproduces the fixture bit for bit."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "gmwb_reference.npz"))
+    v0, v1 = float(g["gmwb_k0/value"]), float(g["gmwb_k1/value"])
+    assert 107.5 < v0 < v1 < 107.8
+    for name in ("gmwb_small", "gmwb_k0", "gmwb_k1"):
+        W, A, V = g[name + "/W"], g[name + "/A"], g[name + "/V"].reshape(len(g[name + "/A"]), -1)
+        assert V.shape == (len(A), len(W))                     # W fastest (Domain.hpp:1416-1425)
+        payoff = np.maximum(W[None, :], 0.9 * A[:, None])      # exit function max(w, (1 - k) a - c)
+        assert np.all(V >= payoff - 1e-6 * np.maximum(1., payoff))
+        q = g[name + "/Q"]; q = q[np.isfinite(q)]              # entries no candidate claimed stay unset
+        assert set(np.unique(q)) <= {0.0, 10.0}
+        z = g[name + "/Z"]; z = z[np.isfinite(z)]
+        assert len(z) == 0 or (z.min() >= 0.0 and z.max() <= 1.0)
+    if oracle.have_ref():
+        ref = oracle.run_ref("gmwb", refine=0, a_points=11, timesteps=8, control_points=3)
+        assert np.array_equal(ref["V"], g["gmwb_small/V"]) and np.array_equal(ref["Z"], g["gmwb_small/Z"])
