@@ -175,8 +175,9 @@ k_interleaved_sweep(DeviceBatch b, InterleavedWork w, DeviceResult out) {
 				double rhs = lb[at];
 				if(b.american) {
 					// PenaltyMethod.hpp:45,61-68: predicate on the previous iterand
-					const double pred = (0. + 1. * x[at]) - ob[at];
-					if((pen * pred) < 0.) { b_i = b_i + pen * 1.; rhs = rhs + pen * ob[at]; }
+					// (scale * (x - payoff)) < 0  <=>  x < payoff
+					const double obi = ob[at];
+					if(x[at] < obi) { b_i = b_i + pen * 1.; rhs = rhs + pen * obi; }
 				}
 				const double denom = b_i - a_i * cprev;
 				const double inv = 1. / denom;
@@ -186,12 +187,13 @@ k_interleaved_sweep(DeviceBatch b, InterleavedWork w, DeviceResult out) {
 			}
 			// ---- back substitution + relativeError --------------------------
 			double xn = 0.;
-			bool notdone = false;
+			bool notdone = false, changed = !b.american;
 			for(int i = N - 1; i >= 0; --i) {
 				const size_t at = (size_t)i * C;
 				xn = dp[at] - cp[at] * xn;
 				if(iterate) {
 					const double xo = x[at];
+					if(b.american) { const double obi = ob[at]; changed = changed || ((xo < obi) != (xn < obi)); }
 					const double fa = fabs(xn), fb = fabs(xo);
 					double d = fa < fb ? fb : fa;
 					d = scale < d ? d : scale;
@@ -201,7 +203,12 @@ k_interleaved_sweep(DeviceBatch b, InterleavedWork w, DeviceResult out) {
 			}
 			++its;
 			again = iterate && notdone;
-			if(again && its >= b.max_inner) { status = 1; again = false; }
+			if(again && !changed) {
+				// Same active set => the next penalty iteration would assemble the same
+				// system and return this iterate again (relativeError == 0): count it.
+				if(its >= b.max_inner) status = 1; else ++its;
+				again = false;
+			} else if(again && its >= b.max_inner) { status = 1; again = false; }
 		} while(again);
 
 		if(out.inner) {
