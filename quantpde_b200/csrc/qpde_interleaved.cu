@@ -187,13 +187,12 @@ k_interleaved_sweep(DeviceBatch b, InterleavedWork w, DeviceResult out) {
 			}
 			// ---- back substitution + relativeError --------------------------
 			double xn = 0.;
-			bool notdone = false, changed = !b.american;
+			bool notdone = false;
 			for(int i = N - 1; i >= 0; --i) {
 				const size_t at = (size_t)i * C;
 				xn = dp[at] - cp[at] * xn;
 				if(iterate) {
 					const double xo = x[at];
-					if(b.american) { const double obi = ob[at]; changed = changed || ((xo < obi) != (xn < obi)); }
 					const double fa = fabs(xn), fb = fabs(xo);
 					double d = fa < fb ? fb : fa;
 					d = scale < d ? d : scale;
@@ -203,12 +202,7 @@ k_interleaved_sweep(DeviceBatch b, InterleavedWork w, DeviceResult out) {
 			}
 			++its;
 			again = iterate && notdone;
-			if(again && !changed) {
-				// Same active set => the next penalty iteration would assemble the same
-				// system and return this iterate again (relativeError == 0): count it.
-				if(its >= b.max_inner) status = 1; else ++its;
-				again = false;
-			} else if(again && its >= b.max_inner) { status = 1; again = false; }
+			if(again && its >= b.max_inner) { status = 1; again = false; }
 		} while(again);
 
 		if(out.inner) {
