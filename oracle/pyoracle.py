@@ -204,6 +204,47 @@ def bermudan_put(K, r, alpha, T, n_steps, E, refine_times, q=0.0, scheme="bdf2")
     return out
 
 
+class Gmwb(C.Structure):
+    _fields_ = [("n_w", C.c_int), ("n_a", C.c_int), ("W", C.POINTER(C.c_double)), ("A", C.POINTER(C.c_double)),
+                ("n_q", C.c_int), ("q", C.POINTER(C.c_double)), ("n_z", C.c_int), ("zfrac", C.POINTER(C.c_double)),
+                ("T", C.c_double), ("timesteps", C.c_int), ("r", C.c_double), ("eta", C.c_double),
+                ("sigma", C.c_double), ("kfee", C.c_double), ("c", C.c_double),
+                ("scaling_factor", C.c_double), ("tolerance", C.c_double), ("max_inner", C.c_int)]
+
+
+GMWB_W_AXIS = np.array([
+    0., 5., 10., 15., 20., 25., 30., 35., 40., 45., 50., 55., 60., 65., 70., 72.5, 75., 77.5, 80., 82., 84.,
+    86., 88., 90., 91., 92., 93., 94., 95., 96., 97., 98., 99., 100., 101., 102., 103., 104., 105., 106.,
+    107., 108., 109., 110., 112., 114., 116., 118., 120., 123., 126., 130., 135., 140., 145., 150., 160.,
+    175., 200., 225., 250., 300., 500., 750., 1000.])      # examples/hjbqvi/gmwb.cpp:92-105
+
+
+def uniform_axis(begin, end, points):
+    dx = (end - begin) / (points - 1)                          # Axis::uniform, Core/Axis.hpp:219-226
+    return np.array([begin + dx * i for i in range(points)])
+
+
+def gmwb(refine_times=0, a_points=51, timesteps=32, control_points=3, T=10., r=.05, eta=0., sigma=.2,
+         G=10., kfee=.1, c=0., w0=100., max_inner=1000):
+    """The examples/hjbqvi/gmwb.cpp wiring on the oracle; HJBQVI::solve(refinement) doubles the
+    time steps per level and refines the spatial and impulse-control grids (HJBQVI.hpp:596-634)."""
+    W = refine((w0 / 100.) * GMWB_W_AXIS, refine_times)
+    A = refine(uniform_axis(0., w0, a_points), refine_times)
+    z = refine(uniform_axis(0., 1., control_points), refine_times)
+    q = np.array([0., G])
+    p = Gmwb()
+    p.n_w, p.n_a, p.W, p.A = len(W), len(A), _dp(W), _dp(A)
+    p.n_q, p.q, p.n_z, p.zfrac = len(q), _dp(q), len(z), _dp(z)
+    p.T, p.timesteps = T, timesteps * 2 ** refine_times
+    p.r, p.eta, p.sigma, p.kfee, p.c = r, eta, sigma, kfee, c
+    p.scaling_factor, p.tolerance, p.max_inner = 1e-2, 1e-6, max_inner
+    V = np.zeros(len(W) * len(A))
+    mean_inner, n_steps = C.c_double(), C.c_int()
+    status = lib().qpo_gmwb_solve(C.byref(p), _dp(V), C.byref(mean_inner), C.byref(n_steps))
+    return dict(W=W, A=A, V=V.reshape(len(A), len(W)), mean_inner=mean_inner.value,
+                n_steps=n_steps.value, status=status)
+
+
 JUMP_AXIS_EXTRA = 1000.0   # examples/jump_diffusion.cpp:166: + S_0 * Axis{1000.}
 
 

@@ -103,6 +103,21 @@ typedef struct {
 int qpo_sweep_1d(const qpo_problem *p, double *V, int *inner,
 		unsigned char *mask);
 
+/* ---- GMWB 2-D impulse-control HJBQVI (qpde_oracle_gmwb.c) ----------------- */
+typedef struct {
+	int n_w, n_a;
+	const double *W, *A;        /* refined axes; node (iw, ia) is row iw + n_w ia   */
+	int n_q; const double *q;   /* stochastic control grid, e.g. {0, G}             */
+	int n_z; const double *zfrac; /* impulse control grid (fractions of a)          */
+	double T; int timesteps;
+	double r, eta, sigma, kfee, c;
+	double scaling_factor;      /* HJBQVI default 1e-2: penalty = 1 / (this * dt)    */
+	double tolerance;           /* iteration_tolerance, 1e-6                         */
+	int max_inner;
+} qpo_gmwb;
+/* V [n_w n_a] out.  Returns 0, 1 (max_inner hit) or 2 (linear sweeps did not settle). */
+int qpo_gmwb_solve(const qpo_gmwb *p, double *V, double *mean_inner, int *n_steps);
+
 #ifdef __cplusplus
 }
 #endif
