@@ -273,6 +273,53 @@ int qpde_bs1d_plan_nodes(const qpde_bs1d_plan *plan);
 /* Row length of the per-step `inner` output (upper bound on steps). */
 int qpde_bs1d_plan_max_steps(const qpde_bs1d_plan *plan);
 
+/* ---- GMWB: 2-D (W, A) impulse-control HJBQVI, penalised scheme ------------- */
+/* One call does what HJBQVI<2,1,1>::solve(refinement) does for the model of
+ * examples/hjbqvi/gmwb.cpp:35-208 (Modules/HJBQVI/HJBQVI.hpp:590-811 with
+ * usePenalizedScheme(), useBiCGSTABSolver(), HJBQVILinearBoundary on W and
+ * HJBQVIZeroDiffusionRightBoundary on A):
+ *   state   w = account value, a = guarantee balance; volatility sigma w in W, none in A
+ *   drift   ((r - eta) w - q 1{a>0}, -q 1{a>0}),  flow q 1{a>0},  discount r
+ *   control q in `controls` (the stochastic control grid, not refined)
+ *   impulse z = z_frac a: (w, a) -> (max(w - z, 0), a - z), reward (1 - kappa) z - c,
+ *           z_frac on `impulse_axis` refined `refine` times
+ *   exit    V(T, w, a) = max(w, (1 - kappa) a - c)
+ *   time    ReverseConstantStepper(0, T, T / timesteps), BDF1, ToleranceIteration(tolerance)
+ *   penalty 1 / (scaling_factor dt)
+ * `timesteps` is the count at this refinement (the reference doubles it per level).
+ * Grid: RectilinearGrid2(w_axis, a_axis).refined(refine); node (iw, ia) is element
+ * ia * n_w + iw of V (W fastest, Core/Domain.hpp:1408-1428). */
+typedef struct {
+	int32_t abi_version;
+	int32_t refine;
+	const double *w_axis; int32_t n_w_axis;
+	const double *a_axis; int32_t n_a_axis;
+	const double *controls; int32_t n_controls;      /* e.g. {0, G}                    */
+	const double *impulse_axis; int32_t n_impulse_axis; /* e.g. uniform(0, 1, 3)       */
+	double T; int32_t timesteps; int32_t max_inner;  /* inner-iteration guard per step  */
+	double r, eta, sigma, kappa, c;
+	double scaling_factor;   /* HJBQVI default 1e-2                                     */
+	double tolerance;        /* iteration_tolerance, 1e-6                               */
+	int32_t max_sweeps;      /* guard of the linear solve's Gauss-Seidel sweeps, e.g. 500 */
+	int32_t reserved;
+} qpde_gmwb2d;
+
+typedef struct {
+	int32_t nodes_w, nodes_a; /* refined grid sizes                                     */
+	int32_t n_steps;          /* time steps taken                                       */
+	int32_t status;           /* 0 ok, 1 max_inner hit, 2 the linear sweeps did not settle */
+	double  mean_inner;       /* "Mean Policy Iterations" of HJBQVI_main                */
+	int32_t *inner;           /* [inner_capacity] per-step inner iterations, or NULL    */
+	int32_t inner_capacity;
+	int32_t reserved;
+} qpde_gmwb2d_stats;
+
+/* Refined grid sizes for the buffers the caller allocates. */
+int qpde_gmwb2d_nodes(const qpde_gmwb2d *problem, int *nodes_w, int *nodes_a);
+/* V: HOST buffer [nodes_a][nodes_w] out; W_out / A_out: optional refined axes. */
+int qpde_gmwb2d_solve(qpde_handle *h, const qpde_gmwb2d *problem, double *V,
+		double *W_out, double *A_out, qpde_gmwb2d_stats *stats);
+
 #ifdef __cplusplus
 }
 #endif

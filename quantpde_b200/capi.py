@@ -74,6 +74,27 @@ class Result(C.Structure):
     ]
 
 
+class Gmwb2d(C.Structure):
+    _fields_ = [
+        ("abi_version", C.c_int32), ("refine", C.c_int32),
+        ("w_axis", _dp), ("n_w_axis", C.c_int32), ("a_axis", _dp), ("n_a_axis", C.c_int32),
+        ("controls", _dp), ("n_controls", C.c_int32),
+        ("impulse_axis", _dp), ("n_impulse_axis", C.c_int32),
+        ("T", C.c_double), ("timesteps", C.c_int32), ("max_inner", C.c_int32),
+        ("r", C.c_double), ("eta", C.c_double), ("sigma", C.c_double), ("kappa", C.c_double), ("c", C.c_double),
+        ("scaling_factor", C.c_double), ("tolerance", C.c_double),
+        ("max_sweeps", C.c_int32), ("reserved", C.c_int32),
+    ]
+
+
+class Gmwb2dStats(C.Structure):
+    _fields_ = [
+        ("nodes_w", C.c_int32), ("nodes_a", C.c_int32), ("n_steps", C.c_int32), ("status", C.c_int32),
+        ("mean_inner", C.c_double), ("inner", C.POINTER(C.c_int32)), ("inner_capacity", C.c_int32),
+        ("reserved", C.c_int32),
+    ]
+
+
 # every symbol include/qpde_b200.h declares
 EXPORTS = [
     "qpde_abi_version", "qpde_create", "qpde_destroy", "qpde_last_error", "qpde_stream",
@@ -82,6 +103,7 @@ EXPORTS = [
     "qpde_bs1d_plan_create", "qpde_bs1d_plan_run", "qpde_bs1d_plan_fetch",
     "qpde_bs1d_plan_destroy", "qpde_bs1d_plan_kernel", "qpde_bs1d_plan_nodes",
     "qpde_bs1d_plan_max_steps", "qpde_jump_nfft", "qpde_jump_setup", "qpde_refine_axis",
+    "qpde_gmwb2d_nodes", "qpde_gmwb2d_solve",
 ]
 
 _lib = None
@@ -128,6 +150,8 @@ def lib():
         L.qpde_jump_nfft.argtypes = [C.c_int]
         L.qpde_jump_setup.argtypes = [C.c_int, _dp, C.c_int, _dp, _dp, _dp, _dp, _dp]
         L.qpde_refine_axis.argtypes = [_dp, C.c_int, C.c_int, _dp]
+        L.qpde_gmwb2d_nodes.argtypes = [C.POINTER(Gmwb2d), C.POINTER(C.c_int), C.POINTER(C.c_int)]
+        L.qpde_gmwb2d_solve.argtypes = [C.c_void_p, C.POINTER(Gmwb2d), _dp, _dp, _dp, C.POINTER(Gmwb2dStats)]
         _lib = L
     return _lib
 
@@ -216,6 +240,31 @@ class Handle:
 def _arr(x, n, dtype=np.float64):
     a = np.ascontiguousarray(np.broadcast_to(np.asarray(x, dtype=dtype), (n,)))
     return a
+
+
+def gmwb_solve(handle, w_axis, a_axis, controls, impulse_axis, refine, timesteps, T=10., r=.05, eta=0.,
+               sigma=.2, kappa=.1, c=0., scaling_factor=1e-2, tolerance=1e-6, max_inner=200, max_sweeps=500):
+    """qpde_gmwb2d_solve: the 2-D GMWB HJBQVI (host arrays in, host arrays out)."""
+    keep = [np.ascontiguousarray(a, dtype=np.float64) for a in (w_axis, a_axis, controls, impulse_axis)]
+    g = Gmwb2d()
+    g.abi_version, g.refine = ABI_VERSION, int(refine)
+    g.w_axis, g.n_w_axis = keep[0].ctypes.data_as(_dp), len(keep[0])
+    g.a_axis, g.n_a_axis = keep[1].ctypes.data_as(_dp), len(keep[1])
+    g.controls, g.n_controls = keep[2].ctypes.data_as(_dp), len(keep[2])
+    g.impulse_axis, g.n_impulse_axis = keep[3].ctypes.data_as(_dp), len(keep[3])
+    g.T, g.timesteps, g.max_inner = T, int(timesteps), int(max_inner)
+    g.r, g.eta, g.sigma, g.kappa, g.c = r, eta, sigma, kappa, c
+    g.scaling_factor, g.tolerance, g.max_sweeps = scaling_factor, tolerance, int(max_sweeps)
+    nw, na = C.c_int(), C.c_int()
+    check(lib().qpde_gmwb2d_nodes(C.byref(g), C.byref(nw), C.byref(na)))
+    V = np.zeros((na.value, nw.value)); W = np.zeros(nw.value); A = np.zeros(na.value)
+    inner = np.zeros(int(timesteps) + 8, dtype=np.int32)
+    st = Gmwb2dStats()
+    st.inner = inner.ctypes.data_as(C.POINTER(C.c_int32)); st.inner_capacity = len(inner)
+    check(lib().qpde_gmwb2d_solve(handle.ptr, C.byref(g), V.ctypes.data_as(_dp), W.ctypes.data_as(_dp),
+                                  A.ctypes.data_as(_dp), C.byref(st)), handle.ptr)
+    return dict(V=V, W=W, A=A, n_steps=st.n_steps, mean_inner=st.mean_inner, status=st.status,
+                inner=inner[:st.n_steps].copy())
 
 
 class BatchSpec:

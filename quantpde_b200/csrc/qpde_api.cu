@@ -520,6 +520,41 @@ int qpde_bs1d_plan_fetch(qpde_bs1d_plan *p, qpde_bs1d_result *r) {
 	return QPDE_OK;
 }
 
+int qpde_gmwb2d_nodes(const qpde_gmwb2d *g, int *nodes_w, int *nodes_a) {
+	if(!g || !nodes_w || !nodes_a) return QPDE_ERR_INVALID;
+	*nodes_w = qpde_refined_size(g->n_w_axis, g->refine);
+	*nodes_a = qpde_refined_size(g->n_a_axis, g->refine);
+	return *nodes_w > 0 && *nodes_a > 0 ? QPDE_OK : QPDE_ERR_INVALID;
+}
+
+int qpde_gmwb2d_solve(qpde_handle *h, const qpde_gmwb2d *g, double *V, double *W_out, double *A_out,
+		qpde_gmwb2d_stats *stats) {
+	if(!h) return fail(nullptr, QPDE_ERR_INVALID, "qpde_gmwb2d_solve: NULL handle");
+	if(!g || !V) return fail(h, QPDE_ERR_INVALID, "qpde_gmwb2d_solve: NULL argument");
+	if(g->abi_version != QPDE_ABI_VERSION) return fail(h, QPDE_ERR_INVALID, "problem.abi_version %d != %d", g->abi_version, QPDE_ABI_VERSION);
+	if(!g->w_axis || !g->a_axis || g->n_w_axis < 3 || g->n_a_axis < 3) return fail(h, QPDE_ERR_INVALID, "gmwb: axes need >= 3 ticks");
+	if(!g->controls || g->n_controls < 1 || g->n_controls > 16) return fail(h, QPDE_ERR_INVALID, "gmwb: 1 .. 16 stochastic controls");
+	if(!g->impulse_axis || g->n_impulse_axis < 2) return fail(h, QPDE_ERR_INVALID, "gmwb: impulse axis needs >= 2 ticks");
+	if(g->refine < 0 || g->refine > 8) return fail(h, QPDE_ERR_INVALID, "gmwb: refine out of range");
+	if(!(g->T > 0.) || g->timesteps < 1 || g->max_inner < 1 || g->max_sweeps < 1) return fail(h, QPDE_ERR_INVALID, "gmwb: T, timesteps, max_inner, max_sweeps must be positive");
+	if(!(g->scaling_factor > 0.) || !(g->tolerance > 0.)) return fail(h, QPDE_ERR_INVALID, "gmwb: scaling_factor and tolerance must be > 0");
+	if(g->w_axis[0] != 0. || g->a_axis[0] != 0.) return fail(h, QPDE_ERR_INVALID, "gmwb: both axes start at 0 (no left boundary routine, as in the reference model)");
+	int nw = 0, na = 0;
+	if(qpde_gmwb2d_nodes(g, &nw, &na) != QPDE_OK) return fail(h, QPDE_ERR_INVALID, "gmwb: bad grid");
+	const int nz = qpde_refined_size(g->n_impulse_axis, g->refine);
+	std::vector<double> W((size_t)nw), A((size_t)na), Z((size_t)nz);
+	qpde_refine_axis(g->w_axis, g->n_w_axis, g->refine, W.data());
+	qpde_refine_axis(g->a_axis, g->n_a_axis, g->refine, A.data());
+	qpde_refine_axis(g->impulse_axis, g->n_impulse_axis, g->refine, Z.data());
+	QPDE_CUDA(h, cudaSetDevice(h->device));
+	std::string error;
+	const int rc = gmwb_run(g, W.data(), nw, A.data(), na, Z.data(), nz, V, stats, h->stream, &h->launches, &error);
+	if(rc != QPDE_OK) return fail(h, rc, "%s", error.c_str());
+	if(W_out) memcpy(W_out, W.data(), sizeof(double) * nw);
+	if(A_out) memcpy(A_out, A.data(), sizeof(double) * na);
+	return QPDE_OK;
+}
+
 int qpde_bs1d_plan_max_steps(const qpde_bs1d_plan *p) { return p ? p->b.max_steps : QPDE_ERR_INVALID; }
 
 int qpde_bs1d_sweep(qpde_handle *h, const qpde_bs1d_batch *batch, qpde_bs1d_result *r) {

@@ -1,0 +1,388 @@
+// qpde_gmwb.cu — the 2-D (W, A) GMWB impulse-control HJBQVI sweep with the
+// penalised scheme (BASELINE.json configs[4]).
+//
+// Reference call stack replaced:
+//   HJBQVI::solve wiring                  Modules/HJBQVI/HJBQVI.hpp:590-811
+//   ControlledOperator::A / b             :158-335   (5-point upwinded stencil)
+//   HJBQVILinearBoundary / ZeroDiffusionRightBoundary   :1285-1340
+//   MinPolicyIteration (stochastic, impulse)            Core/PolicyIteration.hpp:54-105
+//   Impulse::A / b (bilinear rows)        Core/Impulse.hpp:87-216
+//   MinPenaltyMethod (non-direct)         Core/PenaltyMethod.hpp:37-119
+//   ReverseBDFOne                         Core/BDF.hpp:32-46
+//   ToleranceIteration / relativeError    Core/IterativeMethod.hpp:1125-1254
+//   BiCGSTABSolver (ILUT)                 Bindings/Eigen.hpp:170-204
+//   model lambdas                         examples/hjbqvi/gmwb.cpp:92-176
+//
+// Per inner (policy) iteration:
+//   k_gmwb_policy  one thread per node: argmin over the stochastic controls of
+//                  (L^q x - f^q)_i, argmin over the impulse grid of
+//                  ((I - M_z) x - g_z)_i, penalty flag, and the assembled row of
+//                  (I + h L^q* + P (I - M*)) with its right-hand side;
+//   k_gmwb_solve   the linear system.  Every entry outside a W-line points to an
+//                  equal-or-lower A (upwinded drift -q <= 0, impulses with
+//                  z > 0), so the matrix is block lower-triangular by A-line:
+//                  block Gauss-Seidel over the lines in ascending A, each line a
+//                  tridiagonal solve by the partition solver of
+//                  qpde_partition.cuh; same-line impulse targets that are not
+//                  adjacent use the previous sweep, hence a few sweeps to a 1e-15
+//                  relative update (the reference iterates BiCGSTAB + ILUT to a
+//                  machine-epsilon residual);
+//   k_gmwb_relerr  relativeError(x_new, x_old) > tolerance.
+#include <math_constants.h>
+
+#include <algorithm>
+#include <string>
+#include <vector>
+
+#include "qpde_kernels.cuh"
+#include "qpde_partition.cuh"
+
+namespace qpde {
+
+struct GmwbDev {
+	int nw, na, nq, nz;
+	const double *W, *A, *q, *z;
+	double r, eta, sigma, kfee, c;
+	double pen, tol;
+};
+
+// Assembled rows: W sub / diagonal / W super, coefficient of the node below in A,
+// right-hand side, and up to four far impulse targets (index -1 = none).
+struct GmwbRows {
+	double *ra, *rb, *rc, *raa, *rhs;
+	int *tgt; double *tw;       // [4][n]
+};
+
+namespace {
+
+__device__ __forceinline__ double qmax(double x, double y) { return x > y ? x : y; }
+
+// linearInterpolationData, Core/Interpolant.hpp:153-181
+__device__ __forceinline__ void axis_interp(const double *x, int length, double ci, int &idx, double &w) {
+	if(ci <= x[0]) { idx = 0; w = 1.; return; }
+	if(ci >= x[length - 1]) { idx = length - 2; w = 0.; return; }
+	int lo = 0, hi = length - 2, mid = 0;
+	w = 0.;
+	while(lo <= hi) {
+		mid = (lo + hi) / 2;
+		if(ci < x[mid]) hi = mid - 1;
+		else if(ci >= x[mid + 1]) lo = mid + 1;
+		else { w = (x[mid + 1] - ci) / (x[mid + 1] - x[mid]); break; }
+	}
+	idx = mid;
+}
+
+struct OpRow { double aw, cw, aa, ca, diag, b; };
+
+// ControlledOperator::A / b for one node and one control value
+__device__ __forceinline__ OpRow controlled_row(const GmwbDev &d, int iw, int ia, double q) {
+	OpRow o; o.aw = o.cw = o.aa = o.ca = 0.;
+	const double w = d.W[iw], a = d.A[ia];
+	double total = 0.;
+	{   // W direction: volatility sigma w, drift (r - eta) w - q 1{a > 0}
+		const double mu = (d.r - d.eta) * w + ((0. < a) ? -q : 0.);
+		if(iw == 0) {
+		} else if(iw == d.nw - 1) {
+			total += - mu / w;                         // HJBQVILinearBoundary
+		} else {
+			const double dxb = d.W[iw] - d.W[iw - 1], dxc = d.W[iw + 1] - d.W[iw - 1], dxf = d.W[iw + 1] - d.W[iw];
+			const double v = d.sigma * w, vv = v * v;
+			const double ac = vv / dxb / dxc, bc = vv / dxf / dxc;
+			double alpha = ac - mu / dxc, beta = bc + mu / dxc;
+			if(alpha < 0.) { alpha = ac; beta = bc + mu / dxf; }
+			else if(beta < 0.) { alpha = ac - mu / dxb; beta = bc; }
+			o.aw = -alpha; o.cw = -beta;
+			total += alpha + beta;
+		}
+	}
+	{   // A direction: no diffusion, drift -q 1{a > 0}
+		const double mu = (0. < a) ? -q : 0.;
+		if(ia == 0) {
+		} else if(ia == d.na - 1) {
+			const double alpha = - mu / (d.A[ia] - d.A[ia - 1]);   // ZeroDiffusionRightBoundary
+			o.aa = -alpha;
+			total += alpha;
+		} else {
+			const double dxb = d.A[ia] - d.A[ia - 1], dxc = d.A[ia + 1] - d.A[ia - 1], dxf = d.A[ia + 1] - d.A[ia];
+			const double vv = 0. * 0.;
+			const double ac = vv / dxb / dxc, bc = vv / dxf / dxc;
+			double alpha = ac - mu / dxc, beta = bc + mu / dxc;
+			if(alpha < 0.) { alpha = ac; beta = bc + mu / dxf; }
+			else if(beta < 0.) { alpha = ac - mu / dxb; beta = bc; }
+			o.aa = -alpha; o.ca = -beta;
+			total += alpha + beta;
+		}
+	}
+	o.diag = total + d.r;
+	o.b = (0. < a) ? q : 0.;
+	return o;
+}
+
+} // namespace
+
+__global__ void k_gmwb_exit(GmwbDev d, double *x) {
+	const int row = blockIdx.x * blockDim.x + threadIdx.x;
+	if(row >= d.nw * d.na) return;
+	const double w = d.W[row % d.nw], a = d.A[row / d.nw];
+	x[row] = qmax(w, (1 - d.kfee) * a - d.c);                // gmwb.cpp:168
+}
+
+__global__ void __launch_bounds__(128)
+k_gmwb_policy(GmwbDev d, GmwbRows R, const double *x, const double *v0, double h0) {
+	const int n = d.nw * d.na;
+	const int row = blockIdx.x * blockDim.x + threadIdx.x;
+	if(row >= n) return;
+	const int nw = d.nw, iw = row % nw, ia = row / nw;
+
+	// 1. stochastic control: argmin_q (L^q x - f^q)_row, strict <, grid order
+	OpRow o; o.aw = o.cw = o.aa = o.ca = 0.; o.diag = 0.; o.b = 0.;
+	{
+		double best = CUDART_INF;
+		for(int k = 0; k < d.nq; ++k) {
+			const OpRow c = controlled_row(d, iw, ia, d.q[k]);
+			double acc = 0.;
+			if(ia > 0) acc += c.aa * x[row - nw];
+			if(iw > 0 && iw < nw - 1) acc += c.aw * x[row - 1];
+			acc += c.diag * x[row];
+			if(iw > 0 && iw < nw - 1) acc += c.cw * x[row + 1];
+			if(ia > 0 && ia < d.na - 1) acc += c.ca * x[row + nw];
+			const double cand = acc - c.b;
+			if(cand < best) { best = cand; o = c; }
+		}
+	}
+	// 2. impulse control: argmin_z ((I - M_z) x - g_z)_row
+	int t[4] = {0, 0, 0, 0}; double f[4] = {0., 0., 0., 0.}; double reward = 0.;
+	double best = CUDART_INF; bool has = false;
+	{
+		const double w = d.W[iw], a = d.A[ia];
+		for(int k = 0; k < d.nz; ++k) {
+			const double z = d.z[k] * a;
+			const double w_plus = qmax(w - z, 0.), a_plus = a - z;     // gmwb.cpp:139-148
+			int i0, i1; double f0, f1;
+			axis_interp(d.W, nw, w_plus, i0, f0);
+			axis_interp(d.A, d.na, a_plus, i1, f1);
+			const int tt[4] = { i0 + nw * i1, i0 + 1 + nw * i1, i0 + nw * (i1 + 1), i0 + 1 + nw * (i1 + 1) };
+			const double ff[4] = { 1. * f0 * f1, 1. * (-f0 + 1.) * f1, 1. * f0 * (-f1 + 1.), 1. * (-f0 + 1.) * (-f1 + 1.) };
+			const double g = (w - w_plus) + (a - a_plus) < DBL_EPSILON ? -CUDART_INF : (1 - d.kfee) * z - d.c;
+			// row of I - M_z times x, accumulated in column order
+			double acc = 0.; bool diag_done = false;
+#pragma unroll
+			for(int m = 0; m < 4; ++m) {
+				if(!diag_done && row < tt[m]) { acc += 1. * x[row]; diag_done = true; }
+				if(tt[m] == row) { acc += (1. - ff[m]) * x[row]; diag_done = true; }
+				else acc += (0. - ff[m]) * x[tt[m]];
+			}
+			if(!diag_done) acc += 1. * x[row];
+			const double cand = acc - g;
+			if(cand < best) {
+				best = cand; has = true; reward = g;
+#pragma unroll
+				for(int m = 0; m < 4; ++m) { t[m] = tt[m]; f[m] = ff[m]; }
+			}
+		}
+	}
+	// 3. penalty flag and the assembled row of I + h L^q* + P (I - M*)
+	const bool active = has && (d.pen * best) < 0.;
+	double a_ = o.aw * h0, b_ = 1. + o.diag * h0, c_ = o.cw * h0;
+	double rhs = v0[row] + h0 * o.b;
+	int tg[4] = {-1, -1, -1, -1}; double tw[4] = {0., 0., 0., 0.};
+	if(active) {
+		b_ += d.pen;
+		rhs += d.pen * reward;
+#pragma unroll
+		for(int m = 0; m < 4; ++m) {
+			const double fm = d.pen * f[m];
+			if(t[m] == row) b_ -= fm;
+			else if(t[m] == row - 1 && iw > 0 && iw < nw - 1) a_ -= fm;   // same line, adjacent; the last
+			else if(t[m] == row + 1 && iw < nw - 2) c_ -= fm;             // W row stays decoupled in W
+			else if(fm != 0.) { tg[m] = t[m]; tw[m] = fm; }
+		}
+	}
+	R.ra[row] = a_; R.rb[row] = b_; R.rc[row] = c_; R.raa[row] = o.aa * h0; R.rhs[row] = rhs;
+#pragma unroll
+	for(int m = 0; m < 4; ++m) { R.tgt[m * n + row] = tg[m]; R.tw[m * n + row] = tw[m]; }
+}
+
+// Block Gauss-Seidel over the A-lines by one CTA.  Each W-line is a tridiagonal
+// system of nw rows: M rows per thread; when nw == PT M + 1 the last row (decoupled
+// in W: HJBQVILinearBoundary contributes to the diagonal only) is a scalar "tail"
+// equation folded into row nw - 2.
+template <int M, int PT>
+__global__ void __launch_bounds__(PT, 1)
+k_gmwb_solve(GmwbDev d, GmwbRows R, double *x, int max_sweeps, int *status) {
+	__shared__ PartitionSmem sm;
+	__shared__ double s_tail;
+	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+	const int nw = d.nw, n = d.nw * d.na;
+	const bool has_tail = nw == PT * M + 1;
+	const int n_main = has_tail ? nw - 1 : nw;
+	const bool tail_owner = has_tail && tid == PT - 1;
+	PartitionSolver<M, PT> ps; ps.init();
+
+	int sweep = 0;
+	for(; sweep < max_sweeps; ++sweep) {
+		bool moved = false;
+		for(int ia = 0; ia < d.na; ++ia) {
+			const int base = ia * nw;
+			double aa[M], bb[M], cc[M], r[M], xo[M];
+#pragma unroll
+			for(int j = 0; j < M; ++j) {
+				const int iw = tid * M + j;
+				if(iw < n_main) {
+					const int row = base + iw;
+					aa[j] = R.ra[row]; bb[j] = R.rb[row]; cc[j] = R.rc[row];
+					double rr = R.rhs[row];
+					if(ia > 0) rr -= R.raa[row] * x[row - nw];
+#pragma unroll
+					for(int m = 0; m < 4; ++m) {
+						const int tk = R.tgt[m * n + row];
+						if(tk >= 0) rr += R.tw[m * n + row] * x[tk];
+					}
+					r[j] = rr; xo[j] = x[row];
+				} else { aa[j] = 0.; bb[j] = 1.; cc[j] = 0.; r[j] = 0.; xo[j] = 0.; }
+			}
+			double x_tail = 0., x_tail_old = 0.;
+			if(tail_owner) {
+				const int row = base + nw - 1;
+				double rr = R.rhs[row];
+				if(ia > 0) rr -= R.raa[row] * x[row - nw];
+#pragma unroll
+				for(int m = 0; m < 4; ++m) {
+					const int tk = R.tgt[m * n + row];
+					if(tk >= 0) rr += R.tw[m * n + row] * x[tk];
+				}
+				x_tail = rr / R.rb[row];
+				x_tail_old = x[row];
+				r[M - 1] = fma(-cc[M - 1], x_tail, r[M - 1]);   // row nw - 2 couples to the tail through its super-diagonal
+				cc[M - 1] = 0.;
+			}
+			ps.factorize(aa, bb, cc, sm, lane, warp);
+			double G[M], x_next;
+			ps.solve(r, G, x_next, sm, lane, warp);
+#pragma unroll
+			for(int j = 0; j < M; ++j) {
+				const int iw = tid * M + j;
+				if(iw < n_main) {
+					const double den = fabs(G[j]) > 1. ? fabs(G[j]) : 1.;
+					if(fabs(G[j] - xo[j]) > 1e-15 * den) moved = true;
+					x[base + iw] = G[j];
+				}
+			}
+			if(tail_owner) {
+				const double den = fabs(x_tail) > 1. ? fabs(x_tail) : 1.;
+				if(fabs(x_tail - x_tail_old) > 1e-15 * den) moved = true;
+				x[base + nw - 1] = x_tail;
+			}
+			__threadfence_block();
+			__syncthreads();      // this line's values are read by the next line
+		}
+		if(!__syncthreads_or(moved ? 1 : 0)) break;
+	}
+	(void)s_tail;
+	if(tid == 0 && sweep >= max_sweeps) *status = 2;
+}
+
+__global__ void k_gmwb_relerr(int n, const double *x, const double *xprev, double scale, double tol, int *notdone) {
+	const int i = blockIdx.x * blockDim.x + threadIdx.x;
+	bool nd = false;
+	if(i < n) {
+		const double fa = fabs(x[i]), fb = fabs(xprev[i]);
+		double den = fa < fb ? fb : fa;
+		den = scale < den ? den : scale;
+		nd = fabs(x[i] - xprev[i]) / den > tol;                 // IterativeMethod.hpp:1131-1135
+	}
+	if(__syncthreads_or(nd ? 1 : 0) && threadIdx.x == 0) atomicOr(notdone, 1);
+}
+
+template <int M, int PT>
+static void launch_solve(const GmwbDev &d, const GmwbRows &R, double *x, int max_sweeps, int *status, cudaStream_t s) {
+	k_gmwb_solve<M, PT><<<1, PT, 0, s>>>(d, R, x, max_sweeps, status);
+}
+
+// Host driver: the reference's time loop and ToleranceIteration around the kernels.
+int gmwb_run(const qpde_gmwb2d *p, const double *W, int nw, const double *A, int na, const double *z, int nz,
+		double *V_host, qpde_gmwb2d_stats *stats, cudaStream_t stream, long long *launches, std::string *error) {
+	const int n = nw * na;
+	auto fail = [&] (const char *what, cudaError_t e) { *error = std::string(what) + ": " + cudaGetErrorString(e); return QPDE_ERR_CUDA; };
+	// geometry of the line solver: 8 rows per thread
+	int PT = 32;
+	while(PT * 8 + 1 < nw && PT < 512) PT *= 2;
+	if(PT * 8 + 1 < nw) { *error = "gmwb: W axis longer than 4097 nodes is not supported"; return QPDE_ERR_UNSUPPORTED; }
+
+	std::vector<void *> allocs;
+	auto dalloc = [&] (size_t bytes) -> void * { void *ptr = nullptr; if(cudaMalloc(&ptr, bytes) != cudaSuccess) return nullptr; allocs.push_back(ptr); return ptr; };
+	auto cleanup = [&] () { for(void *ptr : allocs) cudaFree(ptr); };
+	double *dW = (double *)dalloc(sizeof(double) * nw), *dA = (double *)dalloc(sizeof(double) * na);
+	double *dq = (double *)dalloc(sizeof(double) * p->n_controls), *dz = (double *)dalloc(sizeof(double) * nz);
+	double *x = (double *)dalloc(sizeof(double) * n), *xprev = (double *)dalloc(sizeof(double) * n), *v0 = (double *)dalloc(sizeof(double) * n);
+	GmwbRows R;
+	R.ra = (double *)dalloc(sizeof(double) * n); R.rb = (double *)dalloc(sizeof(double) * n); R.rc = (double *)dalloc(sizeof(double) * n);
+	R.raa = (double *)dalloc(sizeof(double) * n); R.rhs = (double *)dalloc(sizeof(double) * n);
+	R.tgt = (int *)dalloc(sizeof(int) * 4 * (size_t)n); R.tw = (double *)dalloc(sizeof(double) * 4 * (size_t)n);
+	int *flags = (int *)dalloc(sizeof(int) * 2);
+	if(!dW || !dA || !dq || !dz || !x || !xprev || !v0 || !R.ra || !R.rb || !R.rc || !R.raa || !R.rhs || !R.tgt || !R.tw || !flags) {
+		cleanup(); *error = "gmwb: out of device memory"; return QPDE_ERR_CUDA;
+	}
+	cudaMemcpyAsync(dW, W, sizeof(double) * nw, cudaMemcpyHostToDevice, stream);
+	cudaMemcpyAsync(dA, A, sizeof(double) * na, cudaMemcpyHostToDevice, stream);
+	cudaMemcpyAsync(dq, p->controls, sizeof(double) * p->n_controls, cudaMemcpyHostToDevice, stream);
+	cudaMemcpyAsync(dz, z, sizeof(double) * nz, cudaMemcpyHostToDevice, stream);
+	cudaMemsetAsync(flags, 0, sizeof(int) * 2, stream);
+
+	const double dt_nominal = p->T / p->timesteps;
+	GmwbDev d;
+	d.nw = nw; d.na = na; d.nq = p->n_controls; d.nz = nz;
+	d.W = dW; d.A = dA; d.q = dq; d.z = dz;
+	d.r = p->r; d.eta = p->eta; d.sigma = p->sigma; d.kfee = p->kappa; d.c = p->c;
+	d.pen = 1. / (p->scaling_factor * dt_nominal);   // HJBQVI.hpp:635, PenaltyMethod.hpp:85
+	d.tol = p->tolerance;
+
+	const int threads = 128, blocks = (n + threads - 1) / threads;
+	k_gmwb_exit<<<blocks, 256, 0, stream>>>(d, x); ++*launches;
+
+	Replay rp; rp.start(p->T, dt_nominal, 0);
+	double time1 = p->T;
+	long inner_sum = 0; int n_steps = 0, status = 0;
+	bool more = true;
+	while(more) {
+		qpde_step st;
+		more = rp.next(st);
+		const double h0 = time1 - st.t;
+		cudaMemcpyAsync(v0, x, sizeof(double) * n, cudaMemcpyDeviceToDevice, stream);
+		int its = 0, notdone = 0;
+		do {
+			cudaMemcpyAsync(xprev, x, sizeof(double) * n, cudaMemcpyDeviceToDevice, stream);
+			k_gmwb_policy<<<blocks, threads, 0, stream>>>(d, R, xprev, v0, h0);
+			switch(PT) {
+			case 32:  launch_solve<8, 32>(d, R, x, p->max_sweeps, flags + 1, stream); break;
+			case 64:  launch_solve<8, 64>(d, R, x, p->max_sweeps, flags + 1, stream); break;
+			case 128: launch_solve<8, 128>(d, R, x, p->max_sweeps, flags + 1, stream); break;
+			case 256: launch_solve<8, 256>(d, R, x, p->max_sweeps, flags + 1, stream); break;
+			default:  launch_solve<8, 512>(d, R, x, p->max_sweeps, flags + 1, stream); break;
+			}
+			cudaMemsetAsync(flags, 0, sizeof(int), stream);
+			k_gmwb_relerr<<<(n + 255) / 256, 256, 0, stream>>>(n, x, xprev, 1., p->tolerance, flags);
+			*launches += 3;
+			int host_flags[2] = {0, 0};
+			cudaError_t e = cudaMemcpyAsync(host_flags, flags, sizeof(int) * 2, cudaMemcpyDeviceToHost, stream);
+			if(e == cudaSuccess) e = cudaStreamSynchronize(stream);
+			if(e != cudaSuccess) { cleanup(); return fail("gmwb iteration", e); }
+			notdone = host_flags[0];
+			if(host_flags[1]) status = 2;
+			++its;
+			if(notdone && its >= p->max_inner) { if(!status) status = 1; break; }
+		} while(notdone);
+		if(stats && stats->inner && n_steps < stats->inner_capacity) stats->inner[n_steps] = its;
+		inner_sum += its;
+		++n_steps;
+		time1 = st.t;
+	}
+	cudaError_t e = cudaMemcpyAsync(V_host, x, sizeof(double) * n, cudaMemcpyDeviceToHost, stream);
+	if(e == cudaSuccess) e = cudaStreamSynchronize(stream);
+	cleanup();
+	if(e != cudaSuccess) return fail("gmwb fetch", e);
+	if(stats) { stats->n_steps = n_steps; stats->mean_inner = (double)inner_sum / n_steps; stats->status = status; stats->nodes_w = nw; stats->nodes_a = na; }
+	return QPDE_OK;
+}
+
+} // namespace qpde

@@ -5,6 +5,8 @@
 
 #include <cuda_runtime.h>
 
+#include <string>
+
 #include "qpde_common.cuh"
 
 namespace qpde {
@@ -64,6 +66,10 @@ struct JumpWork {
 bool jump_supported(const DeviceBatch &b);
 int launch_jump(const DeviceBatch &b, const JumpWork &w, const DeviceResult &out,
 		cudaStream_t stream, long long *launches);
+
+// GMWB 2-D sweep (qpde_gmwb.cu): host-driven loop over the kernels.
+int gmwb_run(const qpde_gmwb2d *p, const double *W, int nw, const double *A, int na, const double *z, int nz,
+		double *V_host, qpde_gmwb2d_stats *stats, cudaStream_t stream, long long *launches, std::string *error);
 
 // RESIDENT family (qpde_resident.cu): one CTA per contract.
 bool resident_supported(const DeviceBatch &b);
