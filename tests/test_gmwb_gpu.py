@@ -43,10 +43,12 @@ def test_gmwb_refinement_two_against_oracle(qpde, handle, oracle):
 
 
 def test_gmwb_properties_and_errors(qpde, handle, oracle):
-    res = _solve(qpde, handle, oracle, refine=1, eta=0.01, sigma=0.3)
+    res = _solve(qpde, handle, oracle, refine=1, sigma=0.3)
     payoff = np.maximum(res["W"][None, :], 0.9 * res["A"][:, None])
-    assert np.all(res["V"] >= payoff - 1e-6 * np.maximum(1., payoff))      # V dominates the exit payoff
+    assert np.all(res["V"] >= payoff - 1e-6 * np.maximum(1., payoff))      # no fee: V dominates the exit payoff
     assert np.all(np.diff(res["V"], axis=1) >= -1e-9)                      # increasing in the account value
+    fee = _solve(qpde, handle, oracle, refine=1, sigma=0.3, eta=0.01)
+    assert np.all(fee["V"] <= res["V"] + 1e-9)                             # a fee can only lower the value
     with pytest.raises(qpde.QpdeError):
         qpde.gmwb_solve(handle, oracle.GMWB_W_AXIS + 1.0, oracle.uniform_axis(0., 100., 11), [0., 10.],
                         oracle.uniform_axis(0., 1., 3), 0, 8)
