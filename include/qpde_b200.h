@@ -320,6 +320,29 @@ int qpde_gmwb2d_nodes(const qpde_gmwb2d *problem, int *nodes_w, int *nodes_a);
 int qpde_gmwb2d_solve(qpde_handle *h, const qpde_gmwb2d *problem, double *V,
 		double *W_out, double *A_out, qpde_gmwb2d_stats *stats);
 
+/* ---- GMWB sharded by the A-axis (one shard per rank / GPU) ------------------ */
+/* The pieces of one inner iteration restricted to the refined A-lines
+ * [a_begin, a_end) a rank owns.  x, v0, xprev are DEVICE pointers to full-grid
+ * vectors [nodes_a][nodes_w] replicated on every rank (e.g. torch tensors); the
+ * caller moves the owned lines between ranks (NCCL broadcast / all-gather of the
+ * iterate: the impulse targets (w - z, a - z) live on arbitrary lower A) and
+ * reduces the two flags.  The lines are swept in ascending A across the ranks
+ * (block Gauss-Seidel: rank k sweeps after rank k-1 has published its lines).
+ * quantpde_b200/gmwb_sharded.py is the driver; see DESIGN.md §5. */
+typedef struct qpde_gmwb2d_shard qpde_gmwb2d_shard;
+int qpde_gmwb2d_shard_create(qpde_handle *h, const qpde_gmwb2d *problem, int a_begin, int a_end,
+		qpde_gmwb2d_shard **out);
+int qpde_gmwb2d_shard_destroy(qpde_gmwb2d_shard *shard);
+/* V(T) on the owned lines */
+int qpde_gmwb2d_shard_exit(qpde_gmwb2d_shard *shard, double *x_dev);
+/* control searches + row assembly of the owned lines from the full previous iterate */
+int qpde_gmwb2d_shard_policy(qpde_gmwb2d_shard *shard, const double *x_dev, const double *v0_dev, double h0);
+/* one Gauss-Seidel sweep over the owned lines; *moved_dev (device int) |= 1 if a value moved */
+int qpde_gmwb2d_shard_sweep(qpde_gmwb2d_shard *shard, double *x_dev, int *moved_dev);
+/* relativeError(x, xprev) > tolerance on the owned lines; *notdone_dev (device int) |= 1 */
+int qpde_gmwb2d_shard_relerr(qpde_gmwb2d_shard *shard, const double *x_dev, const double *xprev_dev,
+		int *notdone_dev);
+
 #ifdef __cplusplus
 }
 #endif

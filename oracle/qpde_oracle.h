@@ -117,6 +117,14 @@ typedef struct {
 } qpo_gmwb;
 /* V [n_w n_a] out.  Returns 0, 1 (max_inner hit) or 2 (linear sweeps did not settle). */
 int qpo_gmwb_solve(const qpo_gmwb *p, double *V, double *mean_inner, int *n_steps);
+/* The same, cut into the pieces an A-axis shard owns: lines [lo, hi). */
+typedef struct qpo_gmwb_state qpo_gmwb_state;
+qpo_gmwb_state *qpo_gmwb_state_new(const qpo_gmwb *p);
+void qpo_gmwb_state_free(qpo_gmwb_state *s);
+void qpo_gmwb_exit(const qpo_gmwb *p, int lo, int hi, double *x);
+void qpo_gmwb_policy(qpo_gmwb_state *s, const double *xprev, int lo, int hi);
+double qpo_gmwb_sweep(qpo_gmwb_state *s, double *x, const double *v0, double h0, int lo, int hi);
+double qpo_gmwb_relerr(const qpo_gmwb *p, const double *x, const double *xprev, int lo, int hi);
 
 #ifdef __cplusplus
 }

@@ -162,112 +162,161 @@ static void line_solve(int n, const double *a, const double *b, const double *c,
 	for(i = n - 1; i >= 0; --i) { xn = dp[i] - cp[i] * xn; x[i] = xn; }
 }
 
+/* ------------------------------------------------------------------------ */
+/* The pieces of one inner iteration, restricted to the A-lines [lo, hi): the  */
+/* unit an A-axis shard owns.  The monolithic solve below    */
+/* calls them with [0, n_a).                                                   */
+/* ------------------------------------------------------------------------ */
+
+struct qpo_gmwb_state {
+	const qpo_gmwb *p;
+	op_row *rows; impulse_row *imp; unsigned char *active;
+	double *la, *lb, *lc, *lr, *cp, *dp, *xl;
+	double pen;
+};
+
+qpo_gmwb_state *qpo_gmwb_state_new(const qpo_gmwb *p) {
+	const int n = p->n_w * p->n_a, nw = p->n_w;
+	qpo_gmwb_state *s = (qpo_gmwb_state *)malloc(sizeof(qpo_gmwb_state));
+	s->p = p;
+	s->rows = (op_row *)malloc(sizeof(op_row) * n);
+	s->imp = (impulse_row *)malloc(sizeof(impulse_row) * n);
+	s->active = (unsigned char *)calloc(n, 1);
+	s->la = (double *)malloc(sizeof(double) * nw); s->lb = (double *)malloc(sizeof(double) * nw);
+	s->lc = (double *)malloc(sizeof(double) * nw); s->lr = (double *)malloc(sizeof(double) * nw);
+	s->cp = (double *)malloc(sizeof(double) * nw); s->dp = (double *)malloc(sizeof(double) * nw);
+	s->xl = (double *)malloc(sizeof(double) * nw);
+	s->pen = 1. / (p->scaling_factor * (p->T / p->timesteps));   /* HJBQVI.hpp:635, PenaltyMethod.hpp:85 */
+	return s;
+}
+
+void qpo_gmwb_state_free(qpo_gmwb_state *s) {
+	free(s->rows); free(s->imp); free(s->active);
+	free(s->la); free(s->lb); free(s->lc); free(s->lr); free(s->cp); free(s->dp); free(s->xl);
+	free(s);
+}
+
+/* exit values V(T) on the lines [lo, hi) (gmwb.cpp:168) */
+void qpo_gmwb_exit(const qpo_gmwb *p, int lo, int hi, double *x) {
+	int i;
+	for(i = lo * p->n_w; i < hi * p->n_w; ++i) {
+		const double w = p->W[i % p->n_w], a = p->A[i / p->n_w];
+		x[i] = qmax(w, (1 - p->kfee) * a - p->c);
+	}
+}
+
+/* steps 1-3: control searches and penalty flags for the rows of lines [lo, hi),
+ * reading the whole previous iterate */
+void qpo_gmwb_policy(qpo_gmwb_state *s, const double *xprev, int lo, int hi) {
+	const qpo_gmwb *p = s->p;
+	const int nw = p->n_w, na = p->n_a;
+	int i;
+	for(i = lo * nw; i < hi * nw; ++i) {
+		const int iw = i % nw, ia = i / nw;
+		double best = INFINITY; int k, has = 0;
+		/* 1. stochastic policy: argmin_q (A(q) x - b(q))_i, strict < */
+		for(k = 0; k < p->n_q; ++k) {
+			const op_row o = controlled_row(p, iw, ia, p->q[k]);
+			double acc = 0., cand;
+			/* row entries in column order: A-sub, W-sub, diag, W-super, A-super;
+			 * interior A rows carry both A entries even when they are zero */
+			if(ia > 0) acc += o.aa * xprev[i - nw];
+			if(iw > 0 && iw < nw - 1) acc += o.aw * xprev[i - 1];
+			acc += o.diag * xprev[i];
+			if(iw > 0 && iw < nw - 1) acc += o.cw * xprev[i + 1];
+			if(ia > 0 && ia < na - 1) acc += o.ca * xprev[i + nw];
+			cand = acc - o.b;
+			if(cand < best) { best = cand; s->rows[i] = o; }
+		}
+		/* 2. impulse policy: argmin_z ((I - M_z) x - reward_z)_i, strict < */
+		best = INFINITY;
+		for(k = 0; k < p->n_z; ++k) {
+			const impulse_row m = impulse_of(p, iw, ia, p->zfrac[k]);
+			const double cand = impulse_candidate(&m, i, xprev);
+			if(cand < best) { best = cand; s->imp[i] = m; has = 1; }
+		}
+		/* 3. penalty: active iff scale * ((I - M*) x - reward*) < 0 */
+		s->active[i] = has && (s->pen * best) < 0.;
+	}
+}
+
+/* step 4, one block Gauss-Seidel sweep over the lines [lo, hi) of
+ * (I + h0 L^q + P (I - M*)) x = v0 + h0 b^q + P reward*; lines below lo must
+ * already hold this sweep's values.  Returns the largest relative update. */
+double qpo_gmwb_sweep(qpo_gmwb_state *s, double *x, const double *v0, double h0, int lo, int hi) {
+	const qpo_gmwb *p = s->p;
+	const int nw = p->n_w, na = p->n_a;
+	const double pen = s->pen;
+	double worst = 0.;
+	int ia;
+	for(ia = lo; ia < hi; ++ia) {
+		int iw;
+		for(iw = 0; iw < nw; ++iw) {
+			const int row = iw + nw * ia;
+			const op_row *o = &s->rows[row];
+			double a_ = o->aw * h0, b_ = 1. + o->diag * h0, c_ = o->cw * h0;
+			double r_ = v0[row] + h0 * o->b;
+			if(ia > 0) r_ -= (o->aa * h0) * x[row - nw];
+			if(ia < na - 1) r_ -= (o->ca * h0) * x[row + nw];
+			if(s->active[row]) {
+				int k;
+				b_ += pen;
+				r_ += pen * s->imp[row].reward;
+				for(k = 0; k < 4; ++k) {
+					const int tk = s->imp[row].t[k];
+					const double f = pen * s->imp[row].f[k];
+					if(tk == row) b_ -= f;
+					else if(tk == row - 1) a_ -= f;
+					else if(tk == row + 1) c_ -= f;
+					else r_ += f * x[tk];
+				}
+			}
+			s->la[iw] = a_; s->lb[iw] = b_; s->lc[iw] = c_; s->lr[iw] = r_;
+		}
+		line_solve(nw, s->la, s->lb, s->lc, s->lr, s->xl, s->cp, s->dp);
+		for(iw = 0; iw < nw; ++iw) {
+			const int row = iw + nw * ia;
+			const double d = fabs(s->xl[iw] - x[row]);
+			const double den = fabs(s->xl[iw]) > 1. ? fabs(s->xl[iw]) : 1.;
+			if(d / den > worst) worst = d / den;
+			x[row] = s->xl[iw];
+		}
+	}
+	return worst;
+}
+
+/* relativeError over the lines [lo, hi) (Core/IterativeMethod.hpp:1125-1137) */
+double qpo_gmwb_relerr(const qpo_gmwb *p, const double *x, const double *xprev, int lo, int hi) {
+	const int first = lo * p->n_w, count = (hi - lo) * p->n_w;
+	return count > 0 ? relative_error2(count, x + first, xprev + first, 1.) : 0.;
+}
+
 int qpo_gmwb_solve(const qpo_gmwb *p, double *V, double *mean_inner, int *n_steps_out) {
 	const int nw = p->n_w, na = p->n_a, n = nw * na;
 	const double dt_nominal = p->T / p->timesteps;
-	const double pen = 1. / (p->scaling_factor * dt_nominal);    /* HJBQVI.hpp:635, PenaltyMethod.hpp:85 */
 	double *x = (double *)malloc(sizeof(double) * n), *xprev = (double *)malloc(sizeof(double) * n);
 	double *v0 = (double *)malloc(sizeof(double) * n);
-	op_row *rows = (op_row *)malloc(sizeof(op_row) * n);
-	impulse_row *imp = (impulse_row *)malloc(sizeof(impulse_row) * n);
-	unsigned char *active = (unsigned char *)malloc(n), *has_imp = (unsigned char *)malloc(n);
-	double *la = (double *)malloc(sizeof(double) * nw), *lbb = (double *)malloc(sizeof(double) * nw);
-	double *lc = (double *)malloc(sizeof(double) * nw), *lr = (double *)malloc(sizeof(double) * nw);
-	double *cp = (double *)malloc(sizeof(double) * nw), *dp = (double *)malloc(sizeof(double) * nw);
-	double *xl = (double *)malloc(sizeof(double) * nw);
+	qpo_gmwb_state *st = qpo_gmwb_state_new(p);
 	qpo_step *steps = (qpo_step *)malloc(sizeof(qpo_step) * (size_t)(p->timesteps + 8));
 	const int n_steps = qpo_schedule(p->T, dt_nominal, NULL, 0, steps, p->timesteps + 8);
-	int s, i, status = 0; long inner_sum = 0;
+	int s, status = 0; long inner_sum = 0;
 	double time1 = p->T;
 
-	for(i = 0; i < n; ++i) {
-		const double w = p->W[i % nw], a = p->A[i / nw];
-		v0[i] = qmax(w, (1 - p->kfee) * a - p->c);                       /* gmwb.cpp:168 */
-	}
-
+	qpo_gmwb_exit(p, 0, na, v0);
 	for(s = 0; s < n_steps; ++s) {
 		const double t = steps[s].t, h0 = time1 - t;
 		int its = 0, notdone;
 		memcpy(x, v0, sizeof(double) * n);
 		do {
+			int sweep;
 			memcpy(xprev, x, sizeof(double) * n);
-			/* 1. stochastic policy: argmin_q (A(q) x - b(q))_i, strict < */
-			for(i = 0; i < n; ++i) {
-				const int iw = i % nw, ia = i / nw;
-				double best = INFINITY; int k;
-				for(k = 0; k < p->n_q; ++k) {
-					const op_row o = controlled_row(p, iw, ia, p->q[k]);
-					double acc = 0., cand;
-					/* row entries in column order: A-sub, W-sub, diag, W-super, A-super;
-					 * interior A rows carry both A entries even when they are zero */
-					if(ia > 0) acc += o.aa * xprev[i - nw];
-					if(iw > 0 && iw < nw - 1) acc += o.aw * xprev[i - 1];
-					acc += o.diag * xprev[i];
-					if(iw > 0 && iw < nw - 1) acc += o.cw * xprev[i + 1];
-					if(ia > 0 && ia < na - 1) acc += o.ca * xprev[i + nw];
-					cand = acc - o.b;
-					if(cand < best) { best = cand; rows[i] = o; }
-				}
+			qpo_gmwb_policy(st, xprev, 0, na);
+			for(sweep = 0; sweep < 500; ++sweep) {
+				if(qpo_gmwb_sweep(st, x, v0, h0, 0, na) <= 1e-15) break;
 			}
-			/* 2. impulse policy: argmin_z ((I - M_z) x - reward_z)_i, strict < */
-			for(i = 0; i < n; ++i) {
-				const int iw = i % nw, ia = i / nw;
-				double best = INFINITY; int k;
-				has_imp[i] = 0;
-				for(k = 0; k < p->n_z; ++k) {
-					const impulse_row m = impulse_of(p, iw, ia, p->zfrac[k]);
-					const double cand = impulse_candidate(&m, i, xprev);
-					if(cand < best) { best = cand; imp[i] = m; has_imp[i] = 1; }
-				}
-				/* 3. penalty: active iff scale * ((I - M*) x - reward*) < 0 */
-				active[i] = has_imp[i] && (pen * best) < 0.;
-			}
-			/* 4. solve (I + h0 L^q + P (I - M*)) x = v0 + h0 b^q + P reward*
-			 *    by block Gauss-Seidel over the A-lines, to a 1e-15 relative update */
-			{
-				int sweep;
-				for(sweep = 0; sweep < 500; ++sweep) {
-					double worst = 0.;
-					int ia;
-					for(ia = 0; ia < na; ++ia) {
-						int iw;
-						for(iw = 0; iw < nw; ++iw) {
-							const int row = iw + nw * ia;
-							const op_row *o = &rows[row];
-							double a_ = o->aw * h0, b_ = 1. + o->diag * h0, c_ = o->cw * h0;
-							double r_ = v0[row] + h0 * o->b;
-							if(ia > 0) r_ -= (o->aa * h0) * x[row - nw];
-							if(ia < na - 1) r_ -= (o->ca * h0) * x[row + nw];
-							if(active[row]) {
-								int k;
-								b_ += pen;
-								r_ += pen * imp[row].reward;
-								for(k = 0; k < 4; ++k) {
-									const int tk = imp[row].t[k];
-									const double f = pen * imp[row].f[k];
-									if(tk == row) b_ -= f;
-									else if(tk == row - 1) a_ -= f;
-									else if(tk == row + 1) c_ -= f;
-									else r_ += f * x[tk];
-								}
-							}
-							la[iw] = a_; lbb[iw] = b_; lc[iw] = c_; lr[iw] = r_;
-						}
-						line_solve(nw, la, lbb, lc, lr, xl, cp, dp);
-						for(iw = 0; iw < nw; ++iw) {
-							const int row = iw + nw * ia;
-							const double d = fabs(xl[iw] - x[row]);
-							const double den = fabs(xl[iw]) > 1. ? fabs(xl[iw]) : 1.;
-							if(d / den > worst) worst = d / den;
-							x[row] = xl[iw];
-						}
-					}
-					if(worst <= 1e-15) break;
-				}
-				if(sweep >= 500) status = 2;
-			}
+			if(sweep >= 500) status = 2;
 			++its;
-			notdone = relative_error2(n, x, xprev, 1.) > p->tolerance;
+			notdone = qpo_gmwb_relerr(p, x, xprev, 0, na) > p->tolerance;
 			if(notdone && its >= p->max_inner) { status = status ? status : 1; break; }
 		} while(notdone);
 		inner_sum += its;
@@ -277,7 +326,7 @@ int qpo_gmwb_solve(const qpo_gmwb *p, double *V, double *mean_inner, int *n_step
 	memcpy(V, v0, sizeof(double) * n);
 	if(mean_inner) *mean_inner = (double)inner_sum / n_steps;
 	if(n_steps_out) *n_steps_out = n_steps;
-	free(x); free(xprev); free(v0); free(rows); free(imp); free(active); free(has_imp);
-	free(la); free(lbb); free(lc); free(lr); free(cp); free(dp); free(xl); free(steps);
+	free(x); free(xprev); free(v0); free(steps);
+	qpo_gmwb_state_free(st);
 	return status;
 }

@@ -103,7 +103,8 @@ EXPORTS = [
     "qpde_bs1d_plan_create", "qpde_bs1d_plan_run", "qpde_bs1d_plan_fetch",
     "qpde_bs1d_plan_destroy", "qpde_bs1d_plan_kernel", "qpde_bs1d_plan_nodes",
     "qpde_bs1d_plan_max_steps", "qpde_jump_nfft", "qpde_jump_setup", "qpde_refine_axis",
-    "qpde_gmwb2d_nodes", "qpde_gmwb2d_solve",
+    "qpde_gmwb2d_nodes", "qpde_gmwb2d_solve", "qpde_gmwb2d_shard_create", "qpde_gmwb2d_shard_destroy",
+    "qpde_gmwb2d_shard_exit", "qpde_gmwb2d_shard_policy", "qpde_gmwb2d_shard_sweep", "qpde_gmwb2d_shard_relerr",
 ]
 
 _lib = None
@@ -152,6 +153,12 @@ def lib():
         L.qpde_refine_axis.argtypes = [_dp, C.c_int, C.c_int, _dp]
         L.qpde_gmwb2d_nodes.argtypes = [C.POINTER(Gmwb2d), C.POINTER(C.c_int), C.POINTER(C.c_int)]
         L.qpde_gmwb2d_solve.argtypes = [C.c_void_p, C.POINTER(Gmwb2d), _dp, _dp, _dp, C.POINTER(Gmwb2dStats)]
+        L.qpde_gmwb2d_shard_create.argtypes = [C.c_void_p, C.POINTER(Gmwb2d), C.c_int, C.c_int, C.POINTER(C.c_void_p)]
+        L.qpde_gmwb2d_shard_destroy.argtypes = [C.c_void_p]
+        L.qpde_gmwb2d_shard_exit.argtypes = [C.c_void_p, C.c_void_p]
+        L.qpde_gmwb2d_shard_policy.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_double]
+        L.qpde_gmwb2d_shard_sweep.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        L.qpde_gmwb2d_shard_relerr.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         _lib = L
     return _lib
 
@@ -240,6 +247,59 @@ class Handle:
 def _arr(x, n, dtype=np.float64):
     a = np.ascontiguousarray(np.broadcast_to(np.asarray(x, dtype=dtype), (n,)))
     return a
+
+
+class GmwbProblem:
+    """Keeps the arrays a qpde_gmwb2d points into alive."""
+
+    def __init__(self, w_axis, a_axis, controls, impulse_axis, refine, timesteps, T=10., r=.05, eta=0.,
+                 sigma=.2, kappa=.1, c=0., scaling_factor=1e-2, tolerance=1e-6, max_inner=200, max_sweeps=500):
+        self.keep = [np.ascontiguousarray(a, dtype=np.float64) for a in (w_axis, a_axis, controls, impulse_axis)]
+        keep = self.keep
+        g = Gmwb2d()
+        g.abi_version, g.refine = ABI_VERSION, int(refine)
+        g.w_axis, g.n_w_axis = keep[0].ctypes.data_as(_dp), len(keep[0])
+        g.a_axis, g.n_a_axis = keep[1].ctypes.data_as(_dp), len(keep[1])
+        g.controls, g.n_controls = keep[2].ctypes.data_as(_dp), len(keep[2])
+        g.impulse_axis, g.n_impulse_axis = keep[3].ctypes.data_as(_dp), len(keep[3])
+        g.T, g.timesteps, g.max_inner = T, int(timesteps), int(max_inner)
+        g.r, g.eta, g.sigma, g.kappa, g.c = r, eta, sigma, kappa, c
+        g.scaling_factor, g.tolerance, g.max_sweeps = scaling_factor, tolerance, int(max_sweeps)
+        self.struct = g
+        nw, na = C.c_int(), C.c_int()
+        check(lib().qpde_gmwb2d_nodes(C.byref(g), C.byref(nw), C.byref(na)))
+        self.nw, self.na = nw.value, na.value
+        self.W = refine_axis(keep[0], refine)
+        self.A = refine_axis(keep[1], refine)
+
+
+class GmwbShard:
+    """qpde_gmwb2d_shard_*: one rank's A-lines [a_begin, a_end); the vectors are device
+    pointers (torch CUDA tensors of the full grid)."""
+
+    def __init__(self, handle, problem, a_begin, a_end):
+        self.handle, self.problem = handle, problem
+        self.ptr = C.c_void_p()
+        check(lib().qpde_gmwb2d_shard_create(handle.ptr, C.byref(problem.struct), int(a_begin), int(a_end),
+                                             C.byref(self.ptr)), handle.ptr)
+
+    def exit_values(self, x):
+        check(lib().qpde_gmwb2d_shard_exit(self.ptr, x.data_ptr()), self.handle.ptr)
+
+    def policy(self, x, v0, h0):
+        check(lib().qpde_gmwb2d_shard_policy(self.ptr, x.data_ptr(), v0.data_ptr(), float(h0)), self.handle.ptr)
+
+    def sweep(self, x, moved):
+        check(lib().qpde_gmwb2d_shard_sweep(self.ptr, x.data_ptr(), moved.data_ptr()), self.handle.ptr)
+
+    def relerr(self, x, xprev, notdone):
+        check(lib().qpde_gmwb2d_shard_relerr(self.ptr, x.data_ptr(), xprev.data_ptr(), notdone.data_ptr()),
+              self.handle.ptr)
+
+    def close(self):
+        if self.ptr:
+            lib().qpde_gmwb2d_shard_destroy(self.ptr)
+            self.ptr = C.c_void_p()
 
 
 def gmwb_solve(handle, w_axis, a_axis, controls, impulse_axis, refine, timesteps, T=10., r=.05, eta=0.,

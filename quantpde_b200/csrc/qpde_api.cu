@@ -555,6 +555,66 @@ int qpde_gmwb2d_solve(qpde_handle *h, const qpde_gmwb2d *g, double *V, double *W
 	return QPDE_OK;
 }
 
+} // extern "C" (reopened below)
+
+struct qpde_gmwb2d_shard { qpde_handle *h; GmwbShard *impl; };
+
+extern "C" {
+
+int qpde_gmwb2d_shard_create(qpde_handle *h, const qpde_gmwb2d *g, int a_begin, int a_end, qpde_gmwb2d_shard **out) {
+	if(!h) return fail(nullptr, QPDE_ERR_INVALID, "qpde_gmwb2d_shard_create: NULL handle");
+	if(!g || !out) return fail(h, QPDE_ERR_INVALID, "qpde_gmwb2d_shard_create: NULL argument");
+	*out = nullptr;
+	if(g->abi_version != QPDE_ABI_VERSION) return fail(h, QPDE_ERR_INVALID, "problem.abi_version %d != %d", g->abi_version, QPDE_ABI_VERSION);
+	int nw = 0, na = 0;
+	if(!g->w_axis || !g->a_axis || !g->controls || !g->impulse_axis || g->n_controls < 1 || g->n_impulse_axis < 2
+			|| qpde_gmwb2d_nodes(g, &nw, &na) != QPDE_OK || !(g->T > 0.) || g->timesteps < 1
+			|| !(g->scaling_factor > 0.) || !(g->tolerance > 0.)) {
+		return fail(h, QPDE_ERR_INVALID, "gmwb shard: bad problem description");
+	}
+	const int nz = qpde_refined_size(g->n_impulse_axis, g->refine);
+	std::vector<double> W((size_t)nw), A((size_t)na), Z((size_t)nz);
+	qpde_refine_axis(g->w_axis, g->n_w_axis, g->refine, W.data());
+	qpde_refine_axis(g->a_axis, g->n_a_axis, g->refine, A.data());
+	qpde_refine_axis(g->impulse_axis, g->n_impulse_axis, g->refine, Z.data());
+	QPDE_CUDA(h, cudaSetDevice(h->device));
+	std::string error;
+	GmwbShard *impl = nullptr;
+	const int rc = gmwb_shard_create(g, W.data(), nw, A.data(), na, Z.data(), nz, a_begin, a_end, h->stream,
+		&h->launches, &impl, &error);
+	if(rc != QPDE_OK) return fail(h, rc, "%s", error.c_str());
+	*out = new qpde_gmwb2d_shard{h, impl};
+	return QPDE_OK;
+}
+
+int qpde_gmwb2d_shard_destroy(qpde_gmwb2d_shard *s) {
+	if(!s) return QPDE_OK;
+	cudaSetDevice(s->h->device);
+	cudaStreamSynchronize(s->h->stream);
+	gmwb_shard_destroy(s->impl);
+	delete s;
+	return QPDE_OK;
+}
+
+#define QPDE_SHARD_CALL(call) \
+	if(!s) return fail(nullptr, QPDE_ERR_INVALID, "gmwb shard: NULL shard"); \
+	QPDE_CUDA(s->h, cudaSetDevice(s->h->device)); \
+	call; \
+	QPDE_CUDA(s->h, cudaGetLastError()); \
+	return QPDE_OK
+
+int qpde_gmwb2d_shard_exit(qpde_gmwb2d_shard *s, double *x_dev) { QPDE_SHARD_CALL(gmwb_shard_exit(s->impl, x_dev)); }
+int qpde_gmwb2d_shard_policy(qpde_gmwb2d_shard *s, const double *x_dev, const double *v0_dev, double h0) {
+	QPDE_SHARD_CALL(gmwb_shard_policy(s->impl, x_dev, v0_dev, h0));
+}
+int qpde_gmwb2d_shard_sweep(qpde_gmwb2d_shard *s, double *x_dev, int *moved_dev) {
+	QPDE_SHARD_CALL(gmwb_shard_sweep(s->impl, x_dev, moved_dev));
+}
+int qpde_gmwb2d_shard_relerr(qpde_gmwb2d_shard *s, const double *x_dev, const double *xprev_dev, int *notdone_dev) {
+	QPDE_SHARD_CALL(gmwb_shard_relerr(s->impl, x_dev, xprev_dev, notdone_dev));
+}
+#undef QPDE_SHARD_CALL
+
 int qpde_bs1d_plan_max_steps(const qpde_bs1d_plan *p) { return p ? p->b.max_steps : QPDE_ERR_INVALID; }
 
 int qpde_bs1d_sweep(qpde_handle *h, const qpde_bs1d_batch *batch, qpde_bs1d_result *r) {

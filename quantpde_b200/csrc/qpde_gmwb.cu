@@ -120,18 +120,18 @@ __device__ __forceinline__ OpRow controlled_row(const GmwbDev &d, int iw, int ia
 
 } // namespace
 
-__global__ void k_gmwb_exit(GmwbDev d, double *x) {
-	const int row = blockIdx.x * blockDim.x + threadIdx.x;
-	if(row >= d.nw * d.na) return;
+__global__ void k_gmwb_exit(GmwbDev d, double *x, int row_begin, int row_end) {
+	const int row = row_begin + blockIdx.x * blockDim.x + threadIdx.x;
+	if(row >= row_end) return;
 	const double w = d.W[row % d.nw], a = d.A[row / d.nw];
 	x[row] = qmax(w, (1 - d.kfee) * a - d.c);                // gmwb.cpp:168
 }
 
 __global__ void __launch_bounds__(128)
-k_gmwb_policy(GmwbDev d, GmwbRows R, const double *x, const double *v0, double h0) {
+k_gmwb_policy(GmwbDev d, GmwbRows R, const double *x, const double *v0, double h0, int row_begin, int row_end) {
 	const int n = d.nw * d.na;
-	const int row = blockIdx.x * blockDim.x + threadIdx.x;
-	if(row >= n) return;
+	const int row = row_begin + blockIdx.x * blockDim.x + threadIdx.x;
+	if(row >= row_end) return;
 	const int nw = d.nw, iw = row % nw, ia = row / nw;
 
 	// 1. stochastic control: argmin_q (L^q x - f^q)_row, strict <, grid order
@@ -209,7 +209,7 @@ k_gmwb_policy(GmwbDev d, GmwbRows R, const double *x, const double *v0, double h
 // equation folded into row nw - 2.
 template <int M, int PT>
 __global__ void __launch_bounds__(PT, 1)
-k_gmwb_solve(GmwbDev d, GmwbRows R, double *x, int max_sweeps, int *status) {
+k_gmwb_solve(GmwbDev d, GmwbRows R, double *x, int ia_begin, int ia_end, int max_sweeps, int *moved_out, int *status) {
 	__shared__ PartitionSmem sm;
 	__shared__ double s_tail;
 	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -222,7 +222,7 @@ k_gmwb_solve(GmwbDev d, GmwbRows R, double *x, int max_sweeps, int *status) {
 	int sweep = 0;
 	for(; sweep < max_sweeps; ++sweep) {
 		bool moved = false;
-		for(int ia = 0; ia < d.na; ++ia) {
+		for(int ia = ia_begin; ia < ia_end; ++ia) {
 			const int base = ia * nw;
 			double aa[M], bb[M], cc[M], r[M], xo[M];
 #pragma unroll
@@ -276,16 +276,18 @@ k_gmwb_solve(GmwbDev d, GmwbRows R, double *x, int max_sweeps, int *status) {
 			__threadfence_block();
 			__syncthreads();      // this line's values are read by the next line
 		}
-		if(!__syncthreads_or(moved ? 1 : 0)) break;
+		const int any = __syncthreads_or(moved ? 1 : 0);
+		if(any && moved_out && tid == 0) *moved_out = 1;
+		if(!any) break;
 	}
 	(void)s_tail;
-	if(tid == 0 && sweep >= max_sweeps) *status = 2;
+	if(tid == 0 && status && sweep >= max_sweeps) *status = 2;
 }
 
-__global__ void k_gmwb_relerr(int n, const double *x, const double *xprev, double scale, double tol, int *notdone) {
-	const int i = blockIdx.x * blockDim.x + threadIdx.x;
+__global__ void k_gmwb_relerr(int row_begin, int row_end, const double *x, const double *xprev, double scale, double tol, int *notdone) {
+	const int i = row_begin + blockIdx.x * blockDim.x + threadIdx.x;
 	bool nd = false;
-	if(i < n) {
+	if(i < row_end) {
 		const double fa = fabs(x[i]), fb = fabs(xprev[i]);
 		double den = fa < fb ? fb : fa;
 		den = scale < den ? den : scale;
@@ -294,53 +296,121 @@ __global__ void k_gmwb_relerr(int n, const double *x, const double *xprev, doubl
 	if(__syncthreads_or(nd ? 1 : 0) && threadIdx.x == 0) atomicOr(notdone, 1);
 }
 
-template <int M, int PT>
-static void launch_solve(const GmwbDev &d, const GmwbRows &R, double *x, int max_sweeps, int *status, cudaStream_t s) {
-	k_gmwb_solve<M, PT><<<1, PT, 0, s>>>(d, R, x, max_sweeps, status);
+// One rank's share of the problem: the A-lines [a_begin, a_end);
+// the single-GPU solve is the shard [0, n_a).
+struct GmwbShard {
+	cudaStream_t stream;
+	long long *launches;
+	GmwbDev d;
+	GmwbRows R;
+	int a_begin, a_end, PT;
+	int *flags;                 // [0] not converged, [1] solve status, [2] moved
+	std::vector<void *> allocs;
+};
+
+static void launch_solve(GmwbShard &sh, double *x, int ia0, int ia1, int max_sweeps, int *moved, int *status) {
+	switch(sh.PT) {
+	case 32:  k_gmwb_solve<8, 32><<<1, 32, 0, sh.stream>>>(sh.d, sh.R, x, ia0, ia1, max_sweeps, moved, status); break;
+	case 64:  k_gmwb_solve<8, 64><<<1, 64, 0, sh.stream>>>(sh.d, sh.R, x, ia0, ia1, max_sweeps, moved, status); break;
+	case 128: k_gmwb_solve<8, 128><<<1, 128, 0, sh.stream>>>(sh.d, sh.R, x, ia0, ia1, max_sweeps, moved, status); break;
+	case 256: k_gmwb_solve<8, 256><<<1, 256, 0, sh.stream>>>(sh.d, sh.R, x, ia0, ia1, max_sweeps, moved, status); break;
+	default:  k_gmwb_solve<8, 512><<<1, 512, 0, sh.stream>>>(sh.d, sh.R, x, ia0, ia1, max_sweeps, moved, status); break;
+	}
+	++*sh.launches;
 }
 
-// Host driver: the reference's time loop and ToleranceIteration around the kernels.
-int gmwb_run(const qpde_gmwb2d *p, const double *W, int nw, const double *A, int na, const double *z, int nz,
-		double *V_host, qpde_gmwb2d_stats *stats, cudaStream_t stream, long long *launches, std::string *error) {
+void gmwb_shard_destroy(GmwbShard *sh) {
+	if(!sh) return;
+	for(void *ptr : sh->allocs) cudaFree(ptr);
+	delete sh;
+}
+
+int gmwb_shard_create(const qpde_gmwb2d *p, const double *W, int nw, const double *A, int na, const double *z, int nz,
+		int a_begin, int a_end, cudaStream_t stream, long long *launches, GmwbShard **out, std::string *error) {
 	const int n = nw * na;
-	auto fail = [&] (const char *what, cudaError_t e) { *error = std::string(what) + ": " + cudaGetErrorString(e); return QPDE_ERR_CUDA; };
-	// geometry of the line solver: 8 rows per thread
 	int PT = 32;
 	while(PT * 8 + 1 < nw && PT < 512) PT *= 2;
 	if(PT * 8 + 1 < nw) { *error = "gmwb: W axis longer than 4097 nodes is not supported"; return QPDE_ERR_UNSUPPORTED; }
-
-	std::vector<void *> allocs;
-	auto dalloc = [&] (size_t bytes) -> void * { void *ptr = nullptr; if(cudaMalloc(&ptr, bytes) != cudaSuccess) return nullptr; allocs.push_back(ptr); return ptr; };
-	auto cleanup = [&] () { for(void *ptr : allocs) cudaFree(ptr); };
+	if(a_begin < 0 || a_end > na || a_begin > a_end) { *error = "gmwb: bad A-line range"; return QPDE_ERR_INVALID; }
+	GmwbShard *sh = new GmwbShard();
+	sh->stream = stream; sh->launches = launches; sh->a_begin = a_begin; sh->a_end = a_end; sh->PT = PT;
+	bool ok = true;
+	auto dalloc = [&] (size_t bytes) -> void * {
+		void *ptr = nullptr;
+		if(cudaMalloc(&ptr, bytes ? bytes : 8) != cudaSuccess) { ok = false; return nullptr; }
+		sh->allocs.push_back(ptr);
+		return ptr;
+	};
 	double *dW = (double *)dalloc(sizeof(double) * nw), *dA = (double *)dalloc(sizeof(double) * na);
 	double *dq = (double *)dalloc(sizeof(double) * p->n_controls), *dz = (double *)dalloc(sizeof(double) * nz);
-	double *x = (double *)dalloc(sizeof(double) * n), *xprev = (double *)dalloc(sizeof(double) * n), *v0 = (double *)dalloc(sizeof(double) * n);
-	GmwbRows R;
+	GmwbRows &R = sh->R;
 	R.ra = (double *)dalloc(sizeof(double) * n); R.rb = (double *)dalloc(sizeof(double) * n); R.rc = (double *)dalloc(sizeof(double) * n);
 	R.raa = (double *)dalloc(sizeof(double) * n); R.rhs = (double *)dalloc(sizeof(double) * n);
 	R.tgt = (int *)dalloc(sizeof(int) * 4 * (size_t)n); R.tw = (double *)dalloc(sizeof(double) * 4 * (size_t)n);
-	int *flags = (int *)dalloc(sizeof(int) * 2);
-	if(!dW || !dA || !dq || !dz || !x || !xprev || !v0 || !R.ra || !R.rb || !R.rc || !R.raa || !R.rhs || !R.tgt || !R.tw || !flags) {
-		cleanup(); *error = "gmwb: out of device memory"; return QPDE_ERR_CUDA;
-	}
+	sh->flags = (int *)dalloc(sizeof(int) * 4);
+	if(!ok) { gmwb_shard_destroy(sh); *error = "gmwb: out of device memory"; return QPDE_ERR_CUDA; }
 	cudaMemcpyAsync(dW, W, sizeof(double) * nw, cudaMemcpyHostToDevice, stream);
 	cudaMemcpyAsync(dA, A, sizeof(double) * na, cudaMemcpyHostToDevice, stream);
 	cudaMemcpyAsync(dq, p->controls, sizeof(double) * p->n_controls, cudaMemcpyHostToDevice, stream);
 	cudaMemcpyAsync(dz, z, sizeof(double) * nz, cudaMemcpyHostToDevice, stream);
-	cudaMemsetAsync(flags, 0, sizeof(int) * 2, stream);
-
-	const double dt_nominal = p->T / p->timesteps;
-	GmwbDev d;
+	cudaMemsetAsync(sh->flags, 0, sizeof(int) * 4, stream);
+	cudaStreamSynchronize(stream);      // the host arrays may go away
+	GmwbDev &d = sh->d;
 	d.nw = nw; d.na = na; d.nq = p->n_controls; d.nz = nz;
 	d.W = dW; d.A = dA; d.q = dq; d.z = dz;
 	d.r = p->r; d.eta = p->eta; d.sigma = p->sigma; d.kfee = p->kappa; d.c = p->c;
-	d.pen = 1. / (p->scaling_factor * dt_nominal);   // HJBQVI.hpp:635, PenaltyMethod.hpp:85
+	d.pen = 1. / (p->scaling_factor * (p->T / p->timesteps));   // HJBQVI.hpp:635, PenaltyMethod.hpp:85
 	d.tol = p->tolerance;
+	*out = sh;
+	return QPDE_OK;
+}
 
-	const int threads = 128, blocks = (n + threads - 1) / threads;
-	k_gmwb_exit<<<blocks, 256, 0, stream>>>(d, x); ++*launches;
+// exit values V(T) on the shard's lines, written into the full-grid vector x
+void gmwb_shard_exit(GmwbShard *sh, double *x) {
+	const int r0 = sh->a_begin * sh->d.nw, r1 = sh->a_end * sh->d.nw;
+	if(r1 > r0) { k_gmwb_exit<<<(r1 - r0 + 255) / 256, 256, 0, sh->stream>>>(sh->d, x, r0, r1); ++*sh->launches; }
+}
 
-	Replay rp; rp.start(p->T, dt_nominal, 0);
+// control searches + row assembly for the shard's lines, from the full previous iterate
+void gmwb_shard_policy(GmwbShard *sh, const double *x, const double *v0, double h0) {
+	const int r0 = sh->a_begin * sh->d.nw, r1 = sh->a_end * sh->d.nw;
+	if(r1 > r0) { k_gmwb_policy<<<(r1 - r0 + 127) / 128, 128, 0, sh->stream>>>(sh->d, sh->R, x, v0, h0, r0, r1); ++*sh->launches; }
+}
+
+// one block Gauss-Seidel sweep over the shard's lines; *moved_dev |= 1 if any value moved
+void gmwb_shard_sweep(GmwbShard *sh, double *x, int *moved_dev) {
+	if(sh->a_end > sh->a_begin) launch_solve(*sh, x, sh->a_begin, sh->a_end, 1, moved_dev, nullptr);
+}
+
+// relativeError(x, xprev) > tolerance on the shard's lines; *notdone_dev |= 1
+void gmwb_shard_relerr(GmwbShard *sh, const double *x, const double *xprev, int *notdone_dev) {
+	const int r0 = sh->a_begin * sh->d.nw, r1 = sh->a_end * sh->d.nw;
+	if(r1 > r0) {
+		k_gmwb_relerr<<<(r1 - r0 + 255) / 256, 256, 0, sh->stream>>>(r0, r1, x, xprev, 1., sh->d.tol, notdone_dev);
+		++*sh->launches;
+	}
+}
+
+// Host driver of the single-GPU solve: the reference's time loop and
+// ToleranceIteration around the kernels, on the shard [0, n_a).
+int gmwb_run(const qpde_gmwb2d *p, const double *W, int nw, const double *A, int na, const double *z, int nz,
+		double *V_host, qpde_gmwb2d_stats *stats, cudaStream_t stream, long long *launches, std::string *error) {
+	const int n = nw * na;
+	GmwbShard *sh = nullptr;
+	int rc = gmwb_shard_create(p, W, nw, A, na, z, nz, 0, na, stream, launches, &sh, error);
+	if(rc != QPDE_OK) return rc;
+	auto dalloc = [&] (size_t bytes) -> double * {
+		void *ptr = nullptr;
+		if(cudaMalloc(&ptr, bytes) != cudaSuccess) return nullptr;
+		sh->allocs.push_back(ptr);
+		return (double *)ptr;
+	};
+	double *x = dalloc(sizeof(double) * n), *xprev = dalloc(sizeof(double) * n), *v0 = dalloc(sizeof(double) * n);
+	if(!x || !xprev || !v0) { gmwb_shard_destroy(sh); *error = "gmwb: out of device memory"; return QPDE_ERR_CUDA; }
+	int *flags = sh->flags;
+	gmwb_shard_exit(sh, x);
+
+	Replay rp; rp.start(p->T, p->T / p->timesteps, 0);
 	double time1 = p->T;
 	long inner_sum = 0; int n_steps = 0, status = 0;
 	bool more = true;
@@ -352,21 +422,18 @@ int gmwb_run(const qpde_gmwb2d *p, const double *W, int nw, const double *A, int
 		int its = 0, notdone = 0;
 		do {
 			cudaMemcpyAsync(xprev, x, sizeof(double) * n, cudaMemcpyDeviceToDevice, stream);
-			k_gmwb_policy<<<blocks, threads, 0, stream>>>(d, R, xprev, v0, h0);
-			switch(PT) {
-			case 32:  launch_solve<8, 32>(d, R, x, p->max_sweeps, flags + 1, stream); break;
-			case 64:  launch_solve<8, 64>(d, R, x, p->max_sweeps, flags + 1, stream); break;
-			case 128: launch_solve<8, 128>(d, R, x, p->max_sweeps, flags + 1, stream); break;
-			case 256: launch_solve<8, 256>(d, R, x, p->max_sweeps, flags + 1, stream); break;
-			default:  launch_solve<8, 512>(d, R, x, p->max_sweeps, flags + 1, stream); break;
-			}
+			gmwb_shard_policy(sh, xprev, v0, h0);
+			launch_solve(*sh, x, 0, na, p->max_sweeps, nullptr, flags + 1);
 			cudaMemsetAsync(flags, 0, sizeof(int), stream);
-			k_gmwb_relerr<<<(n + 255) / 256, 256, 0, stream>>>(n, x, xprev, 1., p->tolerance, flags);
-			*launches += 3;
+			gmwb_shard_relerr(sh, x, xprev, flags);
 			int host_flags[2] = {0, 0};
 			cudaError_t e = cudaMemcpyAsync(host_flags, flags, sizeof(int) * 2, cudaMemcpyDeviceToHost, stream);
 			if(e == cudaSuccess) e = cudaStreamSynchronize(stream);
-			if(e != cudaSuccess) { cleanup(); return fail("gmwb iteration", e); }
+			if(e != cudaSuccess) {
+				gmwb_shard_destroy(sh);
+				*error = std::string("gmwb iteration: ") + cudaGetErrorString(e);
+				return QPDE_ERR_CUDA;
+			}
 			notdone = host_flags[0];
 			if(host_flags[1]) status = 2;
 			++its;
@@ -379,8 +446,8 @@ int gmwb_run(const qpde_gmwb2d *p, const double *W, int nw, const double *A, int
 	}
 	cudaError_t e = cudaMemcpyAsync(V_host, x, sizeof(double) * n, cudaMemcpyDeviceToHost, stream);
 	if(e == cudaSuccess) e = cudaStreamSynchronize(stream);
-	cleanup();
-	if(e != cudaSuccess) return fail("gmwb fetch", e);
+	gmwb_shard_destroy(sh);
+	if(e != cudaSuccess) { *error = std::string("gmwb fetch: ") + cudaGetErrorString(e); return QPDE_ERR_CUDA; }
 	if(stats) { stats->n_steps = n_steps; stats->mean_inner = (double)inner_sum / n_steps; stats->status = status; stats->nodes_w = nw; stats->nodes_a = na; }
 	return QPDE_OK;
 }

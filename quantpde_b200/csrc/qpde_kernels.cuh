@@ -71,6 +71,15 @@ int launch_jump(const DeviceBatch &b, const JumpWork &w, const DeviceResult &out
 int gmwb_run(const qpde_gmwb2d *p, const double *W, int nw, const double *A, int na, const double *z, int nz,
 		double *V_host, qpde_gmwb2d_stats *stats, cudaStream_t stream, long long *launches, std::string *error);
 
+struct GmwbShard;
+int gmwb_shard_create(const qpde_gmwb2d *p, const double *W, int nw, const double *A, int na, const double *z, int nz,
+		int a_begin, int a_end, cudaStream_t stream, long long *launches, GmwbShard **out, std::string *error);
+void gmwb_shard_destroy(GmwbShard *sh);
+void gmwb_shard_exit(GmwbShard *sh, double *x);
+void gmwb_shard_policy(GmwbShard *sh, const double *x, const double *v0, double h0);
+void gmwb_shard_sweep(GmwbShard *sh, double *x, int *moved_dev);
+void gmwb_shard_relerr(GmwbShard *sh, const double *x, const double *xprev, int *notdone_dev);
+
 // RESIDENT family (qpde_resident.cu): one CTA per contract.
 bool resident_supported(const DeviceBatch &b);
 int launch_resident(const DeviceBatch &b, const DeviceResult &out,
