@@ -289,8 +289,8 @@ class GmwbShard:
     def policy(self, x, v0, h0):
         check(lib().qpde_gmwb2d_shard_policy(self.ptr, x.data_ptr(), v0.data_ptr(), float(h0)), self.handle.ptr)
 
-    def sweep(self, x, moved):
-        check(lib().qpde_gmwb2d_shard_sweep(self.ptr, x.data_ptr(), moved.data_ptr()), self.handle.ptr)
+    def sweep(self, x, status):
+        check(lib().qpde_gmwb2d_shard_sweep(self.ptr, x.data_ptr(), status.data_ptr()), self.handle.ptr)
 
     def relerr(self, x, xprev, notdone):
         check(lib().qpde_gmwb2d_shard_relerr(self.ptr, x.data_ptr(), xprev.data_ptr(), notdone.data_ptr()),

@@ -28,6 +28,7 @@
 //                  relative update (the reference iterates BiCGSTAB + ILUT to a
 //                  machine-epsilon residual);
 //   k_gmwb_relerr  relativeError(x_new, x_old) > tolerance.
+#include <cooperative_groups.h>
 #include <math_constants.h>
 
 #include <algorithm>
@@ -36,6 +37,8 @@
 
 #include "qpde_kernels.cuh"
 #include "qpde_partition.cuh"
+
+namespace cg = cooperative_groups;
 
 namespace qpde {
 
@@ -203,85 +206,194 @@ k_gmwb_policy(GmwbDev d, GmwbRows R, const double *x, const double *v0, double h
 	for(int m = 0; m < 4; ++m) { R.tgt[m * n + row] = tg[m]; R.tw[m * n + row] = tw[m]; }
 }
 
-// Block Gauss-Seidel over the A-lines by one CTA.  Each W-line is a tridiagonal
-// system of nw rows: M rows per thread; when nw == PT M + 1 the last row (decoupled
-// in W: HJBQVILinearBoundary contributes to the diagonal only) is a scalar "tail"
-// equation folded into row nw - 2.
+// ---- the line solves -------------------------------------------------------
+// The system of one policy iteration is block lower-triangular by A-line: every
+// entry outside a W-line points to an equal-or-lower A (drift in A is -q <= 0,
+// impulses take z >= 0 out of a).  One ascending pass of line solves is therefore
+// a direct solve; the only lagged entries are same-line impulse targets that are
+// not W-neighbours (lines next to a = 0), and those lines are iterated in place
+// until their update is below 1e-15 before the pass moves on.
+//
+// The lines are a serial chain, so the pass is latency-bound.  It runs on ONE
+// thread-block cluster of G CTAs that take the lines round-robin: while line a - 1
+// is being solved, the CTA that owns line a has already loaded its rows, folded in
+// every target that lies G or more lines below (final, visible), and factorised
+// its tridiagonal matrix; on the chain are only the hand-over, one fused
+// multiply-add per row and the solve with the cached factors.  The hand-over is
+// through distributed shared memory: the finishing CTA writes its line into the
+// successor's `xin` (st.shared::cluster) and arrives on the successor's mbarrier
+// (release.cluster); the global copy of the line (for far targets, later kernels
+// and the other ranks) is stored before that arrive.
+namespace {
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, int count) {
+	asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(bar)), "r"(count) : "memory");
+	asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+
+__device__ __forceinline__ void mbar_arrive_cluster(const uint64_t *bar, int cta) {
+	uint32_t remote;
+	asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(smem_u32(bar)), "r"(cta));
+	asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" :: "r"(remote) : "memory");
+}
+
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t *bar, int parity) {
+	uint32_t done;
+	do {
+		asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+			: "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+	} while(!done);
+}
+
+} // namespace
+
+// Each W-line is a tridiagonal system of nw rows: M rows per thread; when
+// nw == PT M + 1 the last row (decoupled in W: HJBQVILinearBoundary contributes to
+// the diagonal only) is a scalar "tail" equation folded into row nw - 2.
 template <int M, int PT>
 __global__ void __launch_bounds__(PT, 1)
-k_gmwb_solve(GmwbDev d, GmwbRows R, double *x, int ia_begin, int ia_end, int max_sweeps, int *moved_out, int *status) {
+k_gmwb_lines(GmwbDev d, GmwbRows R, double *x, int ia_begin, int ia_end, int max_local, int *status) {
+	extern __shared__ __align__(16) double xin[];      // [PT M + 2] the line below, written by the predecessor CTA
 	__shared__ PartitionSmem sm;
-	__shared__ double s_tail;
+	__shared__ __align__(8) uint64_t full;
+	cg::cluster_group cluster = cg::this_cluster();
+	const int G = (int)cluster.num_blocks(), me = (int)cluster.block_rank(), next = (me + 1) % G;
 	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 	const int nw = d.nw, n = d.nw * d.na;
 	const bool has_tail = nw == PT * M + 1;
 	const int n_main = has_tail ? nw - 1 : nw;
 	const bool tail_owner = has_tail && tid == PT - 1;
+	if(tid == 0) mbar_init(&full, PT);
+	cluster.sync();
+	double *xnext = cluster.map_shared_rank(xin, next);
 	PartitionSolver<M, PT> ps; ps.init();
+	int received = 0;
+	bool failed = false;
 
-	int sweep = 0;
-	for(; sweep < max_sweeps; ++sweep) {
-		bool moved = false;
-		for(int ia = ia_begin; ia < ia_end; ++ia) {
-			const int base = ia * nw;
-			double aa[M], bb[M], cc[M], r[M], xo[M];
+	for(int ia = ia_begin + me; ia < ia_end; ia += G) {
+		const int base = ia * nw;
+		const int far_end = (ia - G + 1) * nw;       // rows of lines <= ia - G: final, and visible through the chain
+		const bool handed = ia > ia_begin;            // the line below arrives in xin (else it is final in x)
+		// ---- off the chain: rows, far targets, factorisation
+		double rr0[M], raa[M];
+		unsigned near = 0, near_tail = 0;
+		bool same_line = false;
+		double rr0_t = 0., raa_t = 0., rb_t = 1., cc_t = 0.;
+		{
+			double aa[M], bb[M], cc[M];
 #pragma unroll
 			for(int j = 0; j < M; ++j) {
 				const int iw = tid * M + j;
 				if(iw < n_main) {
 					const int row = base + iw;
 					aa[j] = R.ra[row]; bb[j] = R.rb[row]; cc[j] = R.rc[row];
+					raa[j] = ia > 0 ? R.raa[row] : 0.;
 					double rr = R.rhs[row];
-					if(ia > 0) rr -= R.raa[row] * x[row - nw];
 #pragma unroll
 					for(int m = 0; m < 4; ++m) {
 						const int tk = R.tgt[m * n + row];
-						if(tk >= 0) rr += R.tw[m * n + row] * x[tk];
+						if(tk >= 0) {
+							if(tk < far_end) rr += R.tw[m * n + row] * __ldcg(x + tk);
+							else { near |= 1u << (4 * j + m); same_line |= tk >= base; }
+						}
 					}
-					r[j] = rr; xo[j] = x[row];
-				} else { aa[j] = 0.; bb[j] = 1.; cc[j] = 0.; r[j] = 0.; xo[j] = 0.; }
+					rr0[j] = rr;
+				} else { aa[j] = 0.; bb[j] = 1.; cc[j] = 0.; rr0[j] = 0.; raa[j] = 0.; }
 			}
-			double x_tail = 0., x_tail_old = 0.;
 			if(tail_owner) {
 				const int row = base + nw - 1;
+				raa_t = ia > 0 ? R.raa[row] : 0.; rb_t = R.rb[row];
 				double rr = R.rhs[row];
-				if(ia > 0) rr -= R.raa[row] * x[row - nw];
 #pragma unroll
 				for(int m = 0; m < 4; ++m) {
 					const int tk = R.tgt[m * n + row];
-					if(tk >= 0) rr += R.tw[m * n + row] * x[tk];
+					if(tk >= 0) {
+						if(tk < far_end) rr += R.tw[m * n + row] * __ldcg(x + tk);
+						else { near_tail |= 1u << m; same_line |= tk >= base; }
+					}
 				}
-				x_tail = rr / R.rb[row];
-				x_tail_old = x[row];
-				r[M - 1] = fma(-cc[M - 1], x_tail, r[M - 1]);   // row nw - 2 couples to the tail through its super-diagonal
-				cc[M - 1] = 0.;
+				rr0_t = rr;
+				cc_t = cc[M - 1]; cc[M - 1] = 0.;     // row nw - 2 couples to the tail through its super-diagonal
 			}
 			ps.factorize(aa, bb, cc, sm, lane, warp);
-			double G[M], x_next;
-			ps.solve(r, G, x_next, sm, lane, warp);
+		}
+		const bool iterate = __syncthreads_or(same_line ? 1 : 0) != 0;
+		// ---- on the chain
+		if(handed) { mbar_wait_cluster(&full, received & 1); ++received; }
+		auto value_of = [&] (int tk) -> double {      // a near target: the line below, or x (own line / lines above far_end)
+			return (handed && tk >= base - nw && tk < base) ? xin[tk - (base - nw)] : __ldcg(x + tk);
+		};
+		double Gs[M], x_tail = 0.;
+		for(int it = 0;; ++it) {
+			double r[M];
 #pragma unroll
 			for(int j = 0; j < M; ++j) {
 				const int iw = tid * M + j;
-				if(iw < n_main) {
-					const double den = fabs(G[j]) > 1. ? fabs(G[j]) : 1.;
-					if(fabs(G[j] - xo[j]) > 1e-15 * den) moved = true;
-					x[base + iw] = G[j];
+				double rr = rr0[j];
+				if(ia > 0 && iw < n_main) rr -= raa[j] * (handed ? xin[iw] : __ldcg(x + base - nw + iw));
+				if((near >> (4 * j)) & 15u) {
+#pragma unroll
+					for(int m = 0; m < 4; ++m) if((near >> (4 * j + m)) & 1u) {
+						const int row = base + iw;
+						rr += R.tw[m * n + row] * value_of(R.tgt[m * n + row]);
+					}
+				}
+				r[j] = rr;
+			}
+			double x_tail_old = x_tail;
+			if(tail_owner) {
+				const int row = base + nw - 1;
+				double rr = rr0_t;
+				if(ia > 0) rr -= raa_t * (handed ? xin[nw - 1] : __ldcg(x + row - nw));
+#pragma unroll
+				for(int m = 0; m < 4; ++m) if((near_tail >> m) & 1u) rr += R.tw[m * n + row] * value_of(R.tgt[m * n + row]);
+				if(it == 0 && iterate) x_tail_old = __ldcg(x + row);
+				x_tail = rr / rb_t;
+				r[M - 1] = fma(-cc_t, x_tail, r[M - 1]);
+			}
+			double Gn[M], x_next;
+			ps.solve(r, Gn, x_next, sm, lane, warp);
+			bool moved = false;
+			if(iterate) {                               // rare: compare with the previous iterate of this line
+#pragma unroll
+				for(int j = 0; j < M; ++j) {
+					const int iw = tid * M + j;
+					if(iw < n_main) {
+						const double old = it == 0 ? __ldcg(x + base + iw) : Gs[j];
+						const double den = fabs(Gn[j]) > 1. ? fabs(Gn[j]) : 1.;
+						moved |= fabs(Gn[j] - old) > 1e-15 * den;
+					}
+				}
+				if(tail_owner) {
+					const double den = fabs(x_tail) > 1. ? fabs(x_tail) : 1.;
+					moved |= fabs(x_tail - x_tail_old) > 1e-15 * den;
 				}
 			}
-			if(tail_owner) {
-				const double den = fabs(x_tail) > 1. ? fabs(x_tail) : 1.;
-				if(fabs(x_tail - x_tail_old) > 1e-15 * den) moved = true;
-				x[base + nw - 1] = x_tail;
+#pragma unroll
+			for(int j = 0; j < M; ++j) {
+				const int iw = tid * M + j;
+				Gs[j] = Gn[j];
+				if(iw < n_main) x[base + iw] = Gn[j];
 			}
+			if(tail_owner) x[base + nw - 1] = x_tail;
+			if(!iterate) break;
 			__threadfence_block();
-			__syncthreads();      // this line's values are read by the next line
+			if(!__syncthreads_or(moved ? 1 : 0)) break;
+			if(it + 1 >= max_local) { failed = true; break; }
 		}
-		const int any = __syncthreads_or(moved ? 1 : 0);
-		if(any && moved_out && tid == 0) *moved_out = 1;
-		if(!any) break;
+		// ---- hand the line to the CTA that owns the next one
+		if(ia + 1 < ia_end) {
+			double2 *dst = reinterpret_cast<double2 *>(xnext + tid * M);
+#pragma unroll
+			for(int j = 0; j < M; j += 2) dst[j / 2] = make_double2(Gs[j], Gs[j + 1]);
+			if(tail_owner) xnext[nw - 1] = x_tail;
+			mbar_arrive_cluster(&full, next);
+		}
 	}
-	(void)s_tail;
-	if(tid == 0 && status && sweep >= max_sweeps) *status = 2;
+	if(failed && tid == 0 && status) atomicOr(status, 2);
+	cluster.sync();                                     // nobody leaves while a peer may still write into its xin
 }
 
 __global__ void k_gmwb_relerr(int row_begin, int row_end, const double *x, const double *xprev, double scale, double tol, int *notdone) {
@@ -303,20 +415,36 @@ struct GmwbShard {
 	long long *launches;
 	GmwbDev d;
 	GmwbRows R;
-	int a_begin, a_end, PT;
-	int *flags;                 // [0] not converged, [1] solve status, [2] moved
+	int a_begin, a_end, PT, max_local;
+	int *flags;                 // [0] not converged, [1] solve status
 	std::vector<void *> allocs;
 };
 
-static void launch_solve(GmwbShard &sh, double *x, int ia0, int ia1, int max_sweeps, int *moved, int *status) {
-	switch(sh.PT) {
-	case 32:  k_gmwb_solve<8, 32><<<1, 32, 0, sh.stream>>>(sh.d, sh.R, x, ia0, ia1, max_sweeps, moved, status); break;
-	case 64:  k_gmwb_solve<8, 64><<<1, 64, 0, sh.stream>>>(sh.d, sh.R, x, ia0, ia1, max_sweeps, moved, status); break;
-	case 128: k_gmwb_solve<8, 128><<<1, 128, 0, sh.stream>>>(sh.d, sh.R, x, ia0, ia1, max_sweeps, moved, status); break;
-	case 256: k_gmwb_solve<8, 256><<<1, 256, 0, sh.stream>>>(sh.d, sh.R, x, ia0, ia1, max_sweeps, moved, status); break;
-	default:  k_gmwb_solve<8, 512><<<1, 512, 0, sh.stream>>>(sh.d, sh.R, x, ia0, ia1, max_sweeps, moved, status); break;
-	}
+static const int GMWB_CLUSTER = 8;       // CTAs in the cluster (portable maximum): depth of the line pipeline
+
+template <int PT>
+static cudaError_t launch_lines_t(GmwbShard &sh, double *x, int ia0, int ia1, int max_local, int *status) {
+	const size_t smem = sizeof(double) * (PT * 8 + 2);
+	cudaError_t e = cudaFuncSetAttribute(k_gmwb_lines<8, PT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+	if(e != cudaSuccess) return e;
+	cudaLaunchConfig_t cfg = {};
+	cfg.gridDim = dim3(GMWB_CLUSTER); cfg.blockDim = dim3(PT); cfg.dynamicSmemBytes = smem; cfg.stream = sh.stream;
+	cudaLaunchAttribute attr[1];
+	attr[0].id = cudaLaunchAttributeClusterDimension;
+	attr[0].val.clusterDim.x = GMWB_CLUSTER; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+	cfg.attrs = attr; cfg.numAttrs = 1;
+	return cudaLaunchKernelEx(&cfg, k_gmwb_lines<8, PT>, sh.d, sh.R, x, ia0, ia1, max_local, status);
+}
+
+static cudaError_t launch_lines(GmwbShard &sh, double *x, int ia0, int ia1, int *status) {
 	++*sh.launches;
+	switch(sh.PT) {
+	case 32:  return launch_lines_t<32>(sh, x, ia0, ia1, sh.max_local, status);
+	case 64:  return launch_lines_t<64>(sh, x, ia0, ia1, sh.max_local, status);
+	case 128: return launch_lines_t<128>(sh, x, ia0, ia1, sh.max_local, status);
+	case 256: return launch_lines_t<256>(sh, x, ia0, ia1, sh.max_local, status);
+	default:  return launch_lines_t<512>(sh, x, ia0, ia1, sh.max_local, status);
+	}
 }
 
 void gmwb_shard_destroy(GmwbShard *sh) {
@@ -332,8 +460,11 @@ int gmwb_shard_create(const qpde_gmwb2d *p, const double *W, int nw, const doubl
 	while(PT * 8 + 1 < nw && PT < 512) PT *= 2;
 	if(PT * 8 + 1 < nw) { *error = "gmwb: W axis longer than 4097 nodes is not supported"; return QPDE_ERR_UNSUPPORTED; }
 	if(a_begin < 0 || a_end > na || a_begin > a_end) { *error = "gmwb: bad A-line range"; return QPDE_ERR_INVALID; }
+	// the block-triangular structure the line pass relies on
+	for(int k = 0; k < p->n_controls; ++k) if(!(p->controls[k] >= 0.)) { *error = "gmwb: withdrawal rates must be >= 0"; return QPDE_ERR_INVALID; }
+	for(int k = 0; k < nz; ++k) if(!(z[k] >= 0. && z[k] <= 1.)) { *error = "gmwb: impulse fractions must lie in [0, 1]"; return QPDE_ERR_INVALID; }
 	GmwbShard *sh = new GmwbShard();
-	sh->stream = stream; sh->launches = launches; sh->a_begin = a_begin; sh->a_end = a_end; sh->PT = PT;
+	sh->stream = stream; sh->launches = launches; sh->a_begin = a_begin; sh->a_end = a_end; sh->PT = PT; sh->max_local = p->max_sweeps > 0 ? p->max_sweeps : 500;
 	bool ok = true;
 	auto dalloc = [&] (size_t bytes) -> void * {
 		void *ptr = nullptr;
@@ -377,9 +508,11 @@ void gmwb_shard_policy(GmwbShard *sh, const double *x, const double *v0, double 
 	if(r1 > r0) { k_gmwb_policy<<<(r1 - r0 + 127) / 128, 128, 0, sh->stream>>>(sh->d, sh->R, x, v0, h0, r0, r1); ++*sh->launches; }
 }
 
-// one block Gauss-Seidel sweep over the shard's lines; *moved_dev |= 1 if any value moved
-void gmwb_shard_sweep(GmwbShard *sh, double *x, int *moved_dev) {
-	if(sh->a_end > sh->a_begin) launch_solve(*sh, x, sh->a_begin, sh->a_end, 1, moved_dev, nullptr);
+// the shard's line solves in ascending A (exact given final lines below a_begin);
+// *status_dev |= 2 if a line's in-place iteration did not settle
+cudaError_t gmwb_shard_sweep(GmwbShard *sh, double *x, int *status_dev) {
+	if(sh->a_end > sh->a_begin) return launch_lines(*sh, x, sh->a_begin, sh->a_end, status_dev);
+	return cudaSuccess;
 }
 
 // relativeError(x, xprev) > tolerance on the shard's lines; *notdone_dev |= 1
@@ -423,11 +556,11 @@ int gmwb_run(const qpde_gmwb2d *p, const double *W, int nw, const double *A, int
 		do {
 			cudaMemcpyAsync(xprev, x, sizeof(double) * n, cudaMemcpyDeviceToDevice, stream);
 			gmwb_shard_policy(sh, xprev, v0, h0);
-			launch_solve(*sh, x, 0, na, p->max_sweeps, nullptr, flags + 1);
+			cudaError_t le = launch_lines(*sh, x, 0, na, flags + 1);
 			cudaMemsetAsync(flags, 0, sizeof(int), stream);
 			gmwb_shard_relerr(sh, x, xprev, flags);
 			int host_flags[2] = {0, 0};
-			cudaError_t e = cudaMemcpyAsync(host_flags, flags, sizeof(int) * 2, cudaMemcpyDeviceToHost, stream);
+			cudaError_t e = le != cudaSuccess ? le : cudaMemcpyAsync(host_flags, flags, sizeof(int) * 2, cudaMemcpyDeviceToHost, stream);
 			if(e == cudaSuccess) e = cudaStreamSynchronize(stream);
 			if(e != cudaSuccess) {
 				gmwb_shard_destroy(sh);

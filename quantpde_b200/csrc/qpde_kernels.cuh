@@ -77,7 +77,7 @@ int gmwb_shard_create(const qpde_gmwb2d *p, const double *W, int nw, const doubl
 void gmwb_shard_destroy(GmwbShard *sh);
 void gmwb_shard_exit(GmwbShard *sh, double *x);
 void gmwb_shard_policy(GmwbShard *sh, const double *x, const double *v0, double h0);
-void gmwb_shard_sweep(GmwbShard *sh, double *x, int *moved_dev);
+cudaError_t gmwb_shard_sweep(GmwbShard *sh, double *x, int *status_dev);
 void gmwb_shard_relerr(GmwbShard *sh, const double *x, const double *xprev, int *notdone_dev);
 
 // RESIDENT family (qpde_resident.cu): one CTA per contract.

@@ -6,10 +6,12 @@ of its lines.  Per inner iteration:
   * control searches + row assembly of the owned lines      (parallel over ranks;
     reads the whole previous iterate: the impulse targets (w - z, a - z) live on
     arbitrary lower A-lines)
-  * block Gauss-Seidel sweeps in ascending A: rank k sweeps its lines after ranks
-    < k have published theirs, then broadcasts its block — the "halo" for the
-    upwinded a-1 coupling and the all-gather for the impulse step in one exchange
-  * MAX-reduction of the two flags (a value moved / relativeError > tolerance).
+  * the line solves in ascending A: rank k solves its lines after ranks < k have
+    published theirs, then broadcasts its block — the "halo" for the upwinded a-1
+    coupling and the all-gather for the impulse step in one exchange.  The system
+    is block lower-triangular by A-line, so one round is a direct solve (a backend
+    without that guarantee, `exact_pass = False`, is swept until nothing moves)
+  * MAX-reduction of the stopping flag (relativeError > tolerance).
 The collectives are torch.distributed's (NCCL on GPUs, gloo in the CPU test); the
 per-rank work goes through the C ABI (qpde_gmwb2d_shard_*).  The `backend` object
 supplies the per-rank work, so the same driver runs the CPU test with a stand-in.
@@ -21,6 +23,8 @@ from .shard import contract_slice
 
 class CudaBackend:
     """The product path: libqpde_b200 through the C ABI, tensors on the rank's GPU."""
+
+    exact_pass = True       # qpde_gmwb2d_shard_sweep is a direct solve of the owned lines
 
     def __init__(self, handle, problem, a_begin, a_end):
         import torch
@@ -39,7 +43,7 @@ class CudaBackend:
 
     def exit_values(self, x): self.shard.exit_values(x)
     def policy(self, x, v0, h0): self.shard.policy(x, v0, h0)
-    def sweep(self, x, v0, h0, moved): self.shard.sweep(x, moved)
+    def sweep(self, x, v0, h0, status): self.shard.sweep(x, status)
     def relerr(self, x, xprev, notdone): self.shard.relerr(x, xprev, notdone)
     def close(self): self.shard.close()
 
@@ -58,7 +62,8 @@ def solve(problem, backend, rank, world, max_inner=200, max_sweeps=500, group=No
     ctx = torch.cuda.stream(backend.stream) if hasattr(backend, "stream") else _Null()
     with ctx:
         x, xprev, v0 = backend.empty(nw * na), backend.empty(nw * na), backend.empty(nw * na)
-        moved, notdone = backend.flag(), backend.flag()
+        moved, notdone, failed = backend.flag(), backend.flag(), backend.flag()
+        exact = getattr(backend, "exact_pass", False)
 
         def publish(r):
             lo, hi = blocks[r]
@@ -79,10 +84,12 @@ def solve(problem, backend, rank, world, max_inner=200, max_sweeps=500, group=No
                 backend.policy(xprev, v0, h0)
                 for sweep in range(max_sweeps):
                     moved.zero_()
-                    for r in range(world):                 # ascending A: block Gauss-Seidel across ranks
+                    for r in range(world):                 # ascending A across the ranks
                         if r == rank:
-                            backend.sweep(x, v0, h0, moved)
+                            backend.sweep(x, v0, h0, failed if exact else moved)
                         publish(r)
+                    if exact:
+                        break
                     if world > 1:
                         dist.all_reduce(moved, op=dist.ReduceOp.MAX, group=group)
                     if int(moved.item()) == 0:
@@ -101,6 +108,10 @@ def solve(problem, backend, rank, world, max_inner=200, max_sweeps=500, group=No
                     break
             inner_sum += its
             time1 = st.t
+        if exact:
+            if world > 1:
+                dist.all_reduce(failed, op=dist.ReduceOp.MAX, group=group)
+            status = status or int(failed.item())
         V = x.cpu().numpy().reshape(na, nw).copy()
     return dict(V=V, n_steps=len(steps), mean_inner=inner_sum / len(steps), status=status)
 

@@ -52,3 +52,56 @@ def test_gmwb_properties_and_errors(qpde, handle, oracle):
     with pytest.raises(qpde.QpdeError):
         qpde.gmwb_solve(handle, oracle.GMWB_W_AXIS + 1.0, oracle.uniform_axis(0., 100., 11), [0., 10.],
                         oracle.uniform_axis(0., 1., 3), 0, 8)
+
+
+class _TwoShards:
+    """Two A-blocks on one GPU, swept in ascending A as two ranks would."""
+
+    def __init__(self, handle, problem):
+        from quantpde_b200 import gmwb_sharded
+        mid = problem.na // 2
+        self.parts = [gmwb_sharded.CudaBackend(handle, problem, 0, mid),
+                      gmwb_sharded.CudaBackend(handle, problem, mid, problem.na)]
+        self.stream = self.parts[0].stream
+        self.empty, self.flag = self.parts[0].empty, self.parts[0].flag
+
+    def exit_values(self, x): [p.exit_values(x) for p in self.parts]
+    def policy(self, x, v0, h0): [p.policy(x, v0, h0) for p in self.parts]
+    def sweep(self, x, v0, h0, moved): [p.sweep(x, v0, h0, moved) for p in self.parts]
+    def relerr(self, x, xprev, notdone): [p.relerr(x, xprev, notdone) for p in self.parts]
+    def close(self): [p.close() for p in self.parts]
+
+
+def test_gmwb_shard_api_two_blocks_equal_whole(qpde, handle, oracle):
+    """qpde_gmwb2d_shard_*: the grid split in two A-blocks and driven by gmwb_sharded.solve gives
+    the bits of qpde_gmwb2d_solve (same sweep order), for one block and for two."""
+    from quantpde_b200 import gmwb_sharded
+    args = (oracle.GMWB_W_AXIS, oracle.uniform_axis(0., 100., 51), [0., 10.], oracle.uniform_axis(0., 1., 3), 1, 64)
+    whole = qpde.gmwb_solve(handle, *args)
+    prob = qpde.GmwbProblem(*args)
+    one = gmwb_sharded.CudaBackend(handle, prob, 0, prob.na)
+    two = _TwoShards(handle, prob)
+    for backend in (one, two):
+        res = gmwb_sharded.solve(prob, backend, 0, 1)
+        backend.close()
+        assert res["status"] == 0 and res["n_steps"] == whole["n_steps"] and res["mean_inner"] == whole["mean_inner"]
+        assert np.array_equal(res["V"], whole["V"])
+
+
+def test_gmwb_two_ranks_nccl(qpde, oracle, tmp_path):
+    """World size 2 over NCCL (needs two GPUs; the driver's scaling run has them)."""
+    import subprocess
+    import sys
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("one GPU visible")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = str(tmp_path / "sharded.npz")
+    subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                    "--master-addr", "127.0.0.1", "--master-port", "29631",
+                    os.path.join(root, "tools", "gmwb_sharded_run.py"), "--refine", "1", "--out", out],
+                   check=True, cwd=root, timeout=900)
+    got = np.load(out)
+    with qpde.Handle(0) as h:
+        whole = _solve(qpde, h, oracle, refine=1)
+    assert np.array_equal(got["V"], whole["V"]) and float(got["mean_inner"]) == whole["mean_inner"]
