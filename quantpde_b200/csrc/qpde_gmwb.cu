@@ -32,6 +32,7 @@
 #include <math_constants.h>
 
 #include <algorithm>
+#include <cstdlib>
 #include <string>
 #include <vector>
 
@@ -215,15 +216,30 @@ k_gmwb_policy(GmwbDev d, GmwbRows R, const double *x, const double *v0, double h
 // until their update is below 1e-15 before the pass moves on.
 //
 // The lines are a serial chain, so the pass is latency-bound.  It runs on ONE
-// thread-block cluster of G CTAs that take the lines round-robin: while line a - 1
-// is being solved, the CTA that owns line a has already loaded its rows, folded in
-// every target that lies G or more lines below (final, visible), and factorised
-// its tridiagonal matrix; on the chain are only the hand-over, one fused
-// multiply-add per row and the solve with the cached factors.  The hand-over is
-// through distributed shared memory: the finishing CTA writes its line into the
-// successor's `xin` (st.shared::cluster) and arrives on the successor's mbarrier
-// (release.cluster); the global copy of the line (for far targets, later kernels
-// and the other ranks) is stored before that arrive.
+// thread-block cluster of G CTAs that take the lines round-robin, and everything
+// that does not need the two lines below is done before they are finished:
+//   stage 1  rows of line a, targets on lines <= a - G - 3 (visible since this
+//            CTA's previous line), factorisation of the tridiagonal matrix;
+//   stage 2  after the `pre` barrier (lines <= a - 3 are in x and visible): the
+//            remaining targets on those lines;
+//   chain    wait for lines a - 1 and a - 2 in shared memory (`full_a`, `full_b`),
+//            one multiply-add per row (plus the rare targets on those two lines),
+//            the solve with the cached factors, hand-over.
+// Hand-over through distributed shared memory: the finishing CTA stores its line
+// into `xa` of the next CTA and `xb` of the one after it (st.shared::cluster) and
+// arrives once per warp on their barriers (release.cluster) — no global memory on
+// the chain.  Afterwards, off the chain, the line is written to x and released to
+// the CTA three lines up (`pre`); thread 0 of every CTA forwards its own `pre` to
+// its successor, so that by induction `pre`(a) covers every line <= a - 3.
+//
+// Two things ptxas / the hardware punish in this kernel, both measured:
+//  * a warp that reaches a shuffle while diverged (an `if(tid == ...)` block in
+//    front of the solver is enough) runs every shuffle of the solver on the
+//    WARPSYNC slow path — 10x on the factorisation.  All single-thread work here
+//    is predicated instead of branched, and the tail row is formed by every thread.
+//  * a predicate that lives across a gather load makes ptxas issue the loads one
+//    after the other (seven predicate registers).  Targets that are not wanted
+//    read x[0] with weight 0 instead.
 namespace {
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -233,10 +249,21 @@ __device__ __forceinline__ void mbar_init(uint64_t *bar, int count) {
 	asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 }
 
-__device__ __forceinline__ void mbar_arrive_cluster(const uint64_t *bar, int cta) {
+__device__ __forceinline__ uint32_t cluster_addr(const void *p, int cta) {
 	uint32_t remote;
-	asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(smem_u32(bar)), "r"(cta));
-	asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" :: "r"(remote) : "memory");
+	asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(smem_u32(p)), "r"(cta));
+	return remote;
+}
+
+// `elected` is a predicate, not a branch (see above)
+__device__ __forceinline__ void mbar_arrive_cluster(const uint64_t *bar, int cta, bool elected = true) {
+	const uint32_t remote = cluster_addr(bar, cta);
+	asm volatile("{\n .reg .pred p;\n setp.ne.u32 p, %1, 0;\n @p mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];\n}"
+		:: "r"(remote), "r"((unsigned)elected) : "memory");
+}
+
+__device__ __forceinline__ void mbar_arrive_local(uint64_t *bar) {
+	asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(smem_u32(bar)) : "memory");
 }
 
 __device__ __forceinline__ void mbar_wait_cluster(uint64_t *bar, int parity) {
@@ -247,7 +274,14 @@ __device__ __forceinline__ void mbar_wait_cluster(uint64_t *bar, int parity) {
 	} while(!done);
 }
 
+// store into a peer's shared memory
+__device__ __forceinline__ void st_cluster_f64(uint32_t remote_addr, double v) {
+	asm volatile("st.shared::cluster.f64 [%0], %1;" :: "r"(remote_addr), "d"(v) : "memory");
+}
+
 } // namespace
+
+__host__ __device__ constexpr int gmwb_near_k(int PT) { return PT > 256 ? 4 : 8; }   // listed targets per thread (shared-memory budget)
 
 // Each W-line is a tridiagonal system of nw rows: M rows per thread; when
 // nw == PT M + 1 the last row (decoupled in W: HJBQVILinearBoundary contributes to
@@ -255,75 +289,156 @@ __device__ __forceinline__ void mbar_wait_cluster(uint64_t *bar, int parity) {
 template <int M, int PT>
 __global__ void __launch_bounds__(PT, 1)
 k_gmwb_lines(GmwbDev d, GmwbRows R, double *x, int ia_begin, int ia_end, int max_local, int *status) {
-	extern __shared__ __align__(16) double xin[];      // [PT M + 2] the line below, written by the predecessor CTA
+	// dynamic shared memory, each line buffer [M PT + 2]: row iw = tid M + j at j PT + tid, the
+	// tail row at M PT.  xa / xb: lines ia - 1 / ia - 2, written by the CTAs that solved them;
+	// rhs: the right-hand side under construction; then this thread's list of targets that
+	// stage 1 could not fold in
+	constexpr int LINE = M * PT + 2, NEAR_K = gmwb_near_k(PT), TK_BITS = 27, TK_MASK = (1 << TK_BITS) - 1;
+	extern __shared__ __align__(16) unsigned char dyn_smem[];
+	double *xa = reinterpret_cast<double *>(dyn_smem), *xb = xa + LINE, *rhs = xb + LINE;
+	double *nl_tw = rhs + LINE;                                         // [NEAR_K][PT] weight
+	int *nl_tk = reinterpret_cast<int *>(nl_tw + NEAR_K * PT);        // [NEAR_K][PT] target row | row slot j << 27
 	__shared__ PartitionSmem sm;
-	__shared__ __align__(8) uint64_t full;
+	__shared__ __align__(8) uint64_t full_a, full_b, pre;
 	cg::cluster_group cluster = cg::this_cluster();
-	const int G = (int)cluster.num_blocks(), me = (int)cluster.block_rank(), next = (me + 1) % G;
+	const int G = (int)cluster.num_blocks(), me = (int)cluster.block_rank();
 	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 	const int nw = d.nw, n = d.nw * d.na;
 	const bool has_tail = nw == PT * M + 1;
 	const int n_main = has_tail ? nw - 1 : nw;
 	const bool tail_owner = has_tail && tid == PT - 1;
-	if(tid == 0) mbar_init(&full, PT);
+	if(tid == 0) { mbar_init(&full_a, PT / 32); mbar_init(&full_b, PT / 32); mbar_init(&pre, PT + 1); }
 	cluster.sync();
-	double *xnext = cluster.map_shared_rank(xin, next);
+	const uint32_t xa_next = cluster_addr(xa, (me + 1) % G), xb_next2 = cluster_addr(xb, (me + 2) % G);
 	PartitionSolver<M, PT> ps; ps.init();
-	int received = 0;
+	int n_full_a = 0, n_full_b = 0, n_pre = 0;
 	bool failed = false;
+	auto slot = [&] (int iw) -> int { return iw == M * PT ? M * PT : (iw % M) * PT + iw / M; };
 
 	for(int ia = ia_begin + me; ia < ia_end; ia += G) {
 		const int base = ia * nw;
-		const int far_end = (ia - G + 1) * nw;       // rows of lines <= ia - G: final, and visible through the chain
-		const bool handed = ia > ia_begin;            // the line below arrives in xin (else it is final in x)
-		// ---- off the chain: rows, far targets, factorisation
-		double rr0[M], raa[M];
-		unsigned near = 0, near_tail = 0;
-		bool same_line = false;
-		double rr0_t = 0., raa_t = 0., rb_t = 1., cc_t = 0.;
+		const int far_end = (ia - G - 2) * nw;       // rows of lines <= ia - G - 3: visible since this CTA's previous line
+		const int lower_end = base - 2 * nw;          // rows of lines <= ia - 3: visible after `pre`
+		const bool has_a = ia - 1 >= ia_begin;        // line ia - 1 arrives in xa (else it is final in x)
+		const bool has_b = ia - 2 >= ia_begin;        // line ia - 2 arrives in xb (else it is final in x)
+		// ---- stage 1: rows, far targets, factorisation
+		double raa[M];
+		unsigned later = 0, later_tail = 0;           // bit 4 j + m: target m of row j is not folded in yet
+		double raa_t = 0., rb_t = 1., rinv_t = 1., cc_t = 0.;
 		{
 			double aa[M], bb[M], cc[M];
 #pragma unroll
-			for(int j = 0; j < M; ++j) {
-				const int iw = tid * M + j;
-				if(iw < n_main) {
-					const int row = base + iw;
-					aa[j] = R.ra[row]; bb[j] = R.rb[row]; cc[j] = R.rc[row];
-					raa[j] = ia > 0 ? R.raa[row] : 0.;
-					double rr = R.rhs[row];
+			for(int j0 = 0; j0 < M; j0 += 4) {
+				int tk[16]; double tw[16], xv[16], rr[4];
 #pragma unroll
-					for(int m = 0; m < 4; ++m) {
-						const int tk = R.tgt[m * n + row];
-						if(tk >= 0) {
-							if(tk < far_end) rr += R.tw[m * n + row] * __ldcg(x + tk);
-							else { near |= 1u << (4 * j + m); same_line |= tk >= base; }
-						}
-					}
-					rr0[j] = rr;
-				} else { aa[j] = 0.; bb[j] = 1.; cc[j] = 0.; rr0[j] = 0.; raa[j] = 0.; }
+				for(int jj = 0; jj < 4; ++jj) {
+					const int j = j0 + jj, iw = tid * M + j, row = base + (iw < n_main ? iw : 0);
+					aa[j] = R.ra[row]; bb[j] = R.rb[row]; cc[j] = R.rc[row]; raa[j] = R.raa[row]; rr[jj] = R.rhs[row];
+#pragma unroll
+					for(int m = 0; m < 4; ++m) { tk[4 * jj + m] = R.tgt[m * n + row]; tw[4 * jj + m] = R.tw[m * n + row]; }
+				}
+#pragma unroll
+				for(int e = 0; e < 16; ++e) {
+					const bool real = tid * M + j0 + e / 4 < n_main;
+					const bool far = tk[e] >= 0 && tk[e] < far_end;
+					later |= real && tk[e] >= far_end && tk[e] >= 0 ? 1u << (4 * j0 + e) : 0u;
+					tk[e] = far ? tk[e] : 0;
+					tw[e] = far ? tw[e] : 0.;
+				}
+				// published before the acquire at this CTA's previous `pre`: ordinary loads (ptxas
+				// never overlaps ld.cg loads)
+#pragma unroll
+				for(int e = 0; e < 16; ++e) xv[e] = x[tk[e]];
+#pragma unroll
+				for(int jj = 0; jj < 4; ++jj) {
+					const int j = j0 + jj;
+					const bool real = tid * M + j < n_main;
+#pragma unroll
+					for(int m = 0; m < 4; ++m) rr[jj] += tw[4 * jj + m] * xv[4 * jj + m];
+					aa[j] = real ? aa[j] : 0.; bb[j] = real ? bb[j] : 1.; cc[j] = real ? cc[j] : 0.;
+					raa[j] = real && ia > 0 ? raa[j] : 0.;
+					rhs[j * PT + tid] = real ? rr[jj] : 0.;
+				}
 			}
-			if(tail_owner) {
+			if(has_tail) {       // uniform: every thread forms the tail row (broadcast loads), its owner uses it
 				const int row = base + nw - 1;
-				raa_t = ia > 0 ? R.raa[row] : 0.; rb_t = R.rb[row];
+				raa_t = ia > 0 ? R.raa[row] : 0.; rb_t = R.rb[row]; rinv_t = 1. / rb_t;
 				double rr = R.rhs[row];
+				int tk[4]; double tw[4], xv[4];
+#pragma unroll
+				for(int m = 0; m < 4; ++m) { tk[m] = R.tgt[m * n + row]; tw[m] = R.tw[m * n + row]; }
 #pragma unroll
 				for(int m = 0; m < 4; ++m) {
-					const int tk = R.tgt[m * n + row];
-					if(tk >= 0) {
-						if(tk < far_end) rr += R.tw[m * n + row] * __ldcg(x + tk);
-						else { near_tail |= 1u << m; same_line |= tk >= base; }
-					}
+					const bool far = tk[m] >= 0 && tk[m] < far_end;
+					later_tail |= tail_owner && tk[m] >= far_end && tk[m] >= 0 ? 1u << m : 0u;
+					tk[m] = far ? tk[m] : 0; tw[m] = far ? tw[m] : 0.;
 				}
-				rr0_t = rr;
-				cc_t = cc[M - 1]; cc[M - 1] = 0.;     // row nw - 2 couples to the tail through its super-diagonal
+#pragma unroll
+				for(int m = 0; m < 4; ++m) xv[m] = x[tk[m]];
+#pragma unroll
+				for(int m = 0; m < 4; ++m) rr += tw[m] * xv[m];
+				rhs[M * PT] = rr;                              // every thread writes the same value
+				cc_t = tail_owner ? cc[M - 1] : 0.;
+				cc[M - 1] = tail_owner ? 0. : cc[M - 1];     // row nw - 2 couples to the tail through its super-diagonal
 			}
 			ps.factorize(aa, bb, cc, sm, lane, warp);
 		}
+		// the marked targets go to this thread's list: (row slot in rhs, target, weight), in (j, m) order
+		int n_list = 0; unsigned over = 0, over_tail = 0; bool same_line = false;
+#pragma unroll 1
+		for(unsigned bits = later; bits; bits &= bits - 1) {
+			const int b = __ffs(bits) - 1, row = base + tid * M + (b >> 2);
+			const int tk = R.tgt[(b & 3) * n + row];
+			same_line |= tk >= base;
+			if(n_list < NEAR_K) { nl_tk[n_list * PT + tid] = tk | ((b >> 2) << TK_BITS); nl_tw[n_list * PT + tid] = R.tw[(b & 3) * n + row]; ++n_list; }
+			else over |= 1u << b;
+		}
+#pragma unroll 1
+		for(unsigned bits = later_tail; bits; bits &= bits - 1) {
+			const int b = __ffs(bits) - 1, row = base + nw - 1;
+			const int tk = R.tgt[b * n + row];
+			same_line |= tk >= base;
+			if(n_list < NEAR_K) { nl_tk[n_list * PT + tid] = tk | (M << TK_BITS); nl_tw[n_list * PT + tid] = R.tw[b * n + row]; ++n_list; }
+			else over_tail |= 1u << b;
+		}
 		const bool iterate = __syncthreads_or(same_line ? 1 : 0) != 0;
+		// ---- stage 2: lines <= ia - 3 are published
+		if(has_a) {
+			if(ia - 3 < ia_begin) mbar_arrive_local(&pre);         // nobody owns line ia - 3 in this pass
+			mbar_wait_cluster(&pre, n_pre & 1); ++n_pre;
+		}
+		mbar_arrive_cluster(&pre, (me + 1) % G, tid == 0 && ia + 1 < ia_end);   // forwards what this CTA has seen
+		{
+			// fold the listed targets on lines <= ia - 3 into rhs; keep the rest, in order
+			int kept = 0;
+#pragma unroll 1
+			for(int e0 = 0; e0 < n_list; e0 += 4) {
+				int tk[4], t[4]; double p[4], xv[4];
+#pragma unroll
+				for(int k = 0; k < 4; ++k) {
+					const bool live = e0 + k < n_list;
+					tk[k] = live ? nl_tk[(e0 + k) * PT + tid] : base;
+					p[k] = live ? nl_tw[(e0 + k) * PT + tid] : 0.;
+					t[k] = tk[k] & TK_MASK;
+				}
+#pragma unroll
+				for(int k = 0; k < 4; ++k) xv[k] = x[t[k] < lower_end ? t[k] : 0];
+#pragma unroll
+				for(int k = 0; k < 4; ++k) if(e0 + k < n_list) {
+					const int j = tk[k] >> TK_BITS;
+					if(t[k] < lower_end) rhs[(j == M ? M * PT : j * PT + tid)] += p[k] * xv[k];
+					else { nl_tk[kept * PT + tid] = tk[k]; nl_tw[kept * PT + tid] = p[k]; ++kept; }
+				}
+			}
+			n_list = kept;
+		}
 		// ---- on the chain
-		if(handed) { mbar_wait_cluster(&full, received & 1); ++received; }
-		auto value_of = [&] (int tk) -> double {      // a near target: the line below, or x (own line / lines above far_end)
-			return (handed && tk >= base - nw && tk < base) ? xin[tk - (base - nw)] : __ldcg(x + tk);
+		if(has_b) { mbar_wait_cluster(&full_b, n_full_b & 1); ++n_full_b; }
+		if(has_a) { mbar_wait_cluster(&full_a, n_full_a & 1); ++n_full_a; }
+		auto value_of = [&] (int t) -> double {       // a target on line ia - 2, ia - 1 or ia
+			if(t >= base) return __ldcg(x + t);
+			if(t >= base - nw) return has_a ? xa[slot(t - (base - nw))] : __ldcg(x + t);
+			return has_b ? xb[slot(t - lower_end)] : __ldcg(x + t);
 		};
 		double Gs[M], x_tail = 0.;
 		for(int it = 0;; ++it) {
@@ -331,28 +446,45 @@ k_gmwb_lines(GmwbDev d, GmwbRows R, double *x, int ia_begin, int ia_end, int max
 #pragma unroll
 			for(int j = 0; j < M; ++j) {
 				const int iw = tid * M + j;
-				double rr = rr0[j];
-				if(ia > 0 && iw < n_main) rr -= raa[j] * (handed ? xin[iw] : __ldcg(x + base - nw + iw));
-				if((near >> (4 * j)) & 15u) {
+				const double below = has_a ? xa[j * PT + tid] : __ldcg(x + (ia > 0 && iw < n_main ? base - nw + iw : 0));
+				r[j] = rhs[j * PT + tid] - raa[j] * below;
+			}
+			double r_t = rhs[M * PT] - raa_t * (has_a ? xa[M * PT] : __ldcg(x + (ia > 0 ? base - 1 : 0)));   // uniform; used by the tail owner
+			if(__any_sync(0xffffffffu, (n_list > 0) | (over != 0) | (over_tail != 0))) {
+				double add[M + 1];
 #pragma unroll
-					for(int m = 0; m < 4; ++m) if((near >> (4 * j + m)) & 1u) {
-						const int row = base + iw;
-						rr += R.tw[m * n + row] * value_of(R.tgt[m * n + row]);
-					}
+				for(int j = 0; j <= M; ++j) add[j] = 0.;
+#pragma unroll 1
+				for(int e = 0; e < n_list; ++e) {
+					const int t = nl_tk[e * PT + tid] & TK_MASK, je = nl_tk[e * PT + tid] >> TK_BITS;
+					const double p = nl_tw[e * PT + tid] * value_of(t);
+#pragma unroll
+					for(int j = 0; j <= M; ++j) add[j] += je == j ? p : 0.;
 				}
-				r[j] = rr;
+#pragma unroll 1
+				for(unsigned bits = over; bits; bits &= bits - 1) {      // beyond the list: re-read the row
+					const int b = __ffs(bits) - 1, row = base + tid * M + (b >> 2);
+					const int t = R.tgt[(b & 3) * n + row];
+					const double p = R.tw[(b & 3) * n + row] * (t < lower_end ? __ldcg(x + t) : value_of(t));
+#pragma unroll
+					for(int j = 0; j < M; ++j) add[j] += (b >> 2) == j ? p : 0.;
+				}
+#pragma unroll 1
+				for(unsigned bits = over_tail; bits; bits &= bits - 1) {
+					const int b = __ffs(bits) - 1, row = base + nw - 1;
+					const int t = R.tgt[b * n + row];
+					add[M] += R.tw[b * n + row] * (t < lower_end ? __ldcg(x + t) : value_of(t));
+				}
+#pragma unroll
+				for(int j = 0; j < M; ++j) r[j] += add[j];
+				r_t += add[M];
+				__syncwarp();
 			}
 			double x_tail_old = x_tail;
-			if(tail_owner) {
-				const int row = base + nw - 1;
-				double rr = rr0_t;
-				if(ia > 0) rr -= raa_t * (handed ? xin[nw - 1] : __ldcg(x + row - nw));
-#pragma unroll
-				for(int m = 0; m < 4; ++m) if((near_tail >> m) & 1u) rr += R.tw[m * n + row] * value_of(R.tgt[m * n + row]);
-				if(it == 0 && iterate) x_tail_old = __ldcg(x + row);
-				x_tail = rr / rb_t;
-				r[M - 1] = fma(-cc_t, x_tail, r[M - 1]);
-			}
+			if(it == 0 && iterate && tail_owner) x_tail_old = __ldcg(x + base + nw - 1);
+			x_tail = r_t * rinv_t;
+			x_tail = fma(fma(-rb_t, x_tail, r_t), rinv_t, x_tail);       // r_t / rb_t to the last bit or so, without the division
+			r[M - 1] = tail_owner ? fma(-cc_t, x_tail, r[M - 1]) : r[M - 1];
 			double Gn[M], x_next;
 			ps.solve(r, Gn, x_next, sm, lane, warp);
 			bool moved = false;
@@ -372,28 +504,38 @@ k_gmwb_lines(GmwbDev d, GmwbRows R, double *x, int ia_begin, int ia_end, int max
 				}
 			}
 #pragma unroll
-			for(int j = 0; j < M; ++j) {
-				const int iw = tid * M + j;
-				Gs[j] = Gn[j];
-				if(iw < n_main) x[base + iw] = Gn[j];
-			}
-			if(tail_owner) x[base + nw - 1] = x_tail;
+			for(int j = 0; j < M; ++j) Gs[j] = Gn[j];
 			if(!iterate) break;
+#pragma unroll
+			for(int j = 0; j < M; ++j) if(tid * M + j < n_main) x[base + tid * M + j] = Gs[j];
+			if(tail_owner) x[base + nw - 1] = x_tail;
 			__threadfence_block();
 			if(!__syncthreads_or(moved ? 1 : 0)) break;
 			if(it + 1 >= max_local) { failed = true; break; }
 		}
-		// ---- hand the line to the CTA that owns the next one
+		// ---- hand the line to the CTA that owns the next one, then to the one after it
 		if(ia + 1 < ia_end) {
-			double2 *dst = reinterpret_cast<double2 *>(xnext + tid * M);
 #pragma unroll
-			for(int j = 0; j < M; j += 2) dst[j / 2] = make_double2(Gs[j], Gs[j + 1]);
-			if(tail_owner) xnext[nw - 1] = x_tail;
-			mbar_arrive_cluster(&full, next);
+			for(int j = 0; j < M; ++j) st_cluster_f64(xa_next + 8u * (j * PT + tid), Gs[j]);
+			st_cluster_f64(xa_next + 8u * (M * PT + (tail_owner ? 0 : 1)), x_tail);   // slot M PT + 1 is scratch
 		}
+		__syncwarp();
+		mbar_arrive_cluster(&full_a, (me + 1) % G, lane == 0 && ia + 1 < ia_end);
+		if(ia + 2 < ia_end) {
+#pragma unroll
+			for(int j = 0; j < M; ++j) st_cluster_f64(xb_next2 + 8u * (j * PT + tid), Gs[j]);
+			st_cluster_f64(xb_next2 + 8u * (M * PT + (tail_owner ? 0 : 1)), x_tail);
+		}
+		__syncwarp();
+		mbar_arrive_cluster(&full_b, (me + 2) % G, lane == 0 && ia + 2 < ia_end);
+		// ---- off the chain again: publish the line in x, release it to the CTA three lines up
+#pragma unroll
+		for(int j = 0; j < M; ++j) if(tid * M + j < n_main) x[base + tid * M + j] = Gs[j];
+		if(tail_owner) x[base + nw - 1] = x_tail;
+		mbar_arrive_cluster(&pre, (me + 3) % G, ia + 3 < ia_end);
 	}
 	if(failed && tid == 0 && status) atomicOr(status, 2);
-	cluster.sync();                                     // nobody leaves while a peer may still write into its xin
+	cluster.sync();                                     // nobody leaves while a peer may still write into its buffers
 }
 
 __global__ void k_gmwb_relerr(int row_begin, int row_end, const double *x, const double *xprev, double scale, double tol, int *notdone) {
@@ -420,18 +562,24 @@ struct GmwbShard {
 	std::vector<void *> allocs;
 };
 
-static const int GMWB_CLUSTER = 8;       // CTAs in the cluster (portable maximum): depth of the line pipeline
+static int gmwb_cluster() {                // CTAs in the cluster: depth of the line pipeline
+	static int g = 0;
+	if(!g) { const char *e = getenv("QPDE_GMWB_CLUSTER"); g = e ? atoi(e) : 8; if(g < 4 || g > 16) g = 8; }
+	return g;
+}
 
 template <int PT>
 static cudaError_t launch_lines_t(GmwbShard &sh, double *x, int ia0, int ia1, int max_local, int *status) {
-	const size_t smem = sizeof(double) * (PT * 8 + 2);
+	const size_t smem = sizeof(double) * 3 * (PT * 8 + 2) + (sizeof(double) + sizeof(int)) * gmwb_near_k(PT) * PT;
 	cudaError_t e = cudaFuncSetAttribute(k_gmwb_lines<8, PT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
 	if(e != cudaSuccess) return e;
 	cudaLaunchConfig_t cfg = {};
-	cfg.gridDim = dim3(GMWB_CLUSTER); cfg.blockDim = dim3(PT); cfg.dynamicSmemBytes = smem; cfg.stream = sh.stream;
+	const int G = gmwb_cluster();
+	if(G > 8) { e = cudaFuncSetAttribute(k_gmwb_lines<8, PT>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1); if(e != cudaSuccess) return e; }
+	cfg.gridDim = dim3(G); cfg.blockDim = dim3(PT); cfg.dynamicSmemBytes = smem; cfg.stream = sh.stream;
 	cudaLaunchAttribute attr[1];
 	attr[0].id = cudaLaunchAttributeClusterDimension;
-	attr[0].val.clusterDim.x = GMWB_CLUSTER; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+	attr[0].val.clusterDim.x = G; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
 	cfg.attrs = attr; cfg.numAttrs = 1;
 	return cudaLaunchKernelEx(&cfg, k_gmwb_lines<8, PT>, sh.d, sh.R, x, ia0, ia1, max_local, status);
 }
