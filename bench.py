@@ -57,12 +57,14 @@ def load_peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def load_traffic(kernel):
-    """dram bytes per launch from the committed ncu --set full capture, if any."""
+def load_traffic(kernel, contracts):
+    """dram__bytes_read + write per launch of the dominant kernel, from the committed ncu
+    capture (profiles/traffic.json), scaled to this launch's contract count."""
     path = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(path):
-        d = json.load(open(path))
-        return d.get(kernel)
+        d = json.load(open(path)).get(kernel)
+        if d:
+            return d["bytes_per_contract"] * contracts
     return None
 
 
@@ -318,7 +320,7 @@ def main():
     peak, peak_src = load_peaks()
     alg_bytes = ALG_BYTES_PER_NODE_SOLVE * N * (inner_sum_all / world)   # per launch (one rank's batch)
     achieved = alg_bytes / (ms_per_step / 1e3) / 1e9
-    traffic = load_traffic(plan.kernel)
+    traffic = load_traffic(plan.kernel, Cn)
     line = {
         "metric": "option PDE solves/sec (N=2049, 1000 CN steps)", "value": value, "unit": "solves/s",
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,

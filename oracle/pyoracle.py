@@ -41,7 +41,11 @@ class Problem(C.Structure):
                 ("pup", C.POINTER(C.c_double)),
                 ("jump_weights", C.POINTER(C.c_double)), ("jump_nfft", C.c_int),
                 ("jump_lambda", C.c_double), ("jump_x0", C.c_double), ("jump_dx", C.c_double),
-                ("solver", C.c_int)]
+                ("solver", C.c_int),
+                ("dividend_kind", C.c_int), ("dividend_first", C.c_int), ("dividend", C.c_double)]
+
+
+DIVIDENDS = {None: 0, "none": 0, "cash": 1, "proportional": 2}
 
 
 _lib = None
@@ -134,8 +138,8 @@ def interp(x, v, c):
 def sweep(S, lo, di, up, v0, T, steps, n_steps, scheme="rannacher",
           american=False, obstacle=None, event_obstacle=None,
           tolerance=1e-6, scale=1.0, penalty_tol=1e-6, max_inner=1000, solver=0,
-          policy_rows=None, policy_max=False, jump=None):
-    """Returns dict(V, inner, mask, status).  policy_rows = (lo, di, up), each
+          policy_rows=None, policy_max=False, jump=None, dividend=None):
+    """Returns dict(V, inner, mask, status).  dividend = (kind, D, first).  policy_rows = (lo, di, up), each
     [n_controls][n]: PolicyIteration over the controls."""
     n = len(S)
     arrs = [np.ascontiguousarray(a, dtype=np.float64) for a in (S, lo, di, up, v0)]
@@ -155,6 +159,8 @@ def sweep(S, lo, di, up, v0, T, steps, n_steps, scheme="rannacher",
         p.event_obstacle = _dp(event_obstacle)
     p.tolerance, p.scale, p.penalty_tol, p.max_inner = tolerance, scale, penalty_tol, max_inner
     p.solver = solver
+    if dividend is not None:
+        p.dividend_kind, p.dividend, p.dividend_first = DIVIDENDS[dividend[0]], float(dividend[1]), int(dividend[2])
     if jump is not None:
         jw = np.ascontiguousarray(jump["weights"], dtype=np.float64)
         p.jump_weights = _dp(jw)
@@ -188,8 +194,10 @@ def american_put(K, r, vol, T, n_steps, refine_times, q=0.0, S0=None, call=False
     return out
 
 
-def bermudan_put(K, r, alpha, T, n_steps, E, refine_times, q=0.0, scheme="bdf2"):
-    """The tutorial.cpp wiring on the oracle (local volatility alpha / S)."""
+def bermudan_put(K, r, alpha, T, n_steps, E, refine_times, q=0.0, scheme="bdf2",
+                 dividend=None, dividend_kind="cash", dividend_first=False, exercise=True):
+    """The tutorial.cpp wiring on the oracle (local volatility alpha / S); optionally with
+    the README's discrete dividends at the exercise dates."""
     S = refine(TUTORIAL_AXIS * (K / 100.0), refine_times)
     with np.errstate(divide="ignore"):
         vol = alpha / S
@@ -198,7 +206,8 @@ def bermudan_put(K, r, alpha, T, n_steps, E, refine_times, q=0.0, scheme="bdf2")
     ev = [T / E * e for e in range(E)]
     steps, n = schedule(T, T / n_steps, ev)
     out = sweep(S, lo, di, up, payoff, T, steps, n, scheme=scheme,
-                american=False, obstacle=payoff, event_obstacle=K - S)
+                american=False, obstacle=payoff, event_obstacle=(K - S) if exercise else None,
+                dividend=None if dividend is None else (dividend_kind, dividend, dividend_first))
     out["S"] = S
     out["n_steps"] = n
     return out

@@ -524,7 +524,7 @@ int qpo_sweep_1d(const qpo_problem *p, double *V, int *inner,
 	double *v0 = (double *)malloc(sizeof(double) * (size_t)n); /* iterand(1) */
 	double *bj = (double *)calloc((size_t)n, sizeof(double)); /* op.b(): explicit jump term or 0 */
 	tri_lu lu;
-	int s, i, status = 0;
+	int s, i, k, status = 0;
 	/* stepper history: times of iterand(0), iterand(1) */
 	double time1 = 0., time0 = 0.;
 	int hist = 0;          /* number of iterands in the stepper's ring */
@@ -747,13 +747,32 @@ int qpo_sweep_1d(const qpo_problem *p, double *V, int *inner,
 
 		if(st->event_after) {
 			/* IterativeMethod.hpp:1279-1295 */
-			if(p->event_obstacle && st->user_events > 0) {
-				/* Event.hpp:100-112 with the exercise transform
-				 * max(V(S), K - S) (QuantPDE::max, EarlyInclude.hpp:48);
-				 * applying it user_events times is idempotent */
-				for(i = 0; i < n; ++i) {
-					const double ex = p->event_obstacle[i];
-					v1[i] = v1[i] > ex ? v1[i] : ex;
+			/* Events at one time are popped in descending id (TimeOrder,
+			 * IterativeMethod.hpp:1340-1352): the event add()ed last goes first. */
+			for(k = 0; k < st->user_events; ++k) {
+				int op;
+				for(op = 0; op < 2; ++op) {
+					const int is_dividend = (op == 0) == (p->dividend_first != 0);
+					if(is_dividend && p->dividend_kind != QPO_DIVIDEND_NONE) {
+						/* Event.hpp:100-112 with V(max(S - D, 0)) (README.md:361-363)
+						 * or V((1 - D) S); PointwiseMap evaluates it at every node */
+						for(i = 0; i < n; ++i) {
+							const double Si = p->S[i];
+							const double at = p->dividend_kind == QPO_DIVIDEND_CASH
+								? (Si - p->dividend > 0. ? Si - p->dividend : 0.)
+								: (1. - p->dividend) * Si;
+							x[i] = qpo_interp(n, p->S, v1, at);
+						}
+						memcpy(v1, x, sizeof(double) * (size_t)n);
+					}
+					if(!is_dividend && p->event_obstacle) {
+						/* the exercise transform max(V(S), K - S)
+						 * (QuantPDE::max, EarlyInclude.hpp:48) */
+						for(i = 0; i < n; ++i) {
+							const double ex = p->event_obstacle[i];
+							v1[i] = v1[i] > ex ? v1[i] : ex;
+						}
+					}
 				}
 			}
 			/* afterEvent(): default IterationNode::onAfterEvent -> clear()

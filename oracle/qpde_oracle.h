@@ -95,7 +95,16 @@ typedef struct {
 	double jump_lambda, jump_x0, jump_dx;
 	int solver;            /* 0: pivoted LU (the reference's policy);
 	                          1: arithmetic model of the INTERLEAVED kernel   */
+	/* discrete dividends at the user event times (README.md:357-375):
+	 * V(S) <- V(max(S - D, 0)) [cash] or V((1 - D) S) [proportional] through the
+	 * grid's piecewise-linear interpolant (Event.hpp:100-112).  dividend_first = 0:
+	 * at one event time the reverse sweep applies the exercise transform, then the
+	 * dividend transform (the dividend events were add()ed first); 1: the reverse. */
+	int dividend_kind;     /* QPO_DIVIDEND_* */
+	int dividend_first;
+	double dividend;
 } qpo_problem;
+enum { QPO_DIVIDEND_NONE = 0, QPO_DIVIDEND_CASH = 1, QPO_DIVIDEND_PROPORTIONAL = 2 };
 
 /* Runs the sweep.  V [n] out; inner [n_steps] out (may be NULL); mask [n] out
  * (may be NULL).  Returns 0, 1 if some step hit max_inner, 2 if the

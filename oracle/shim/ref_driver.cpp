@@ -200,6 +200,11 @@ int runBermudan(const Args &a) {
 	const int refine = (int) integer(a, "refine", 0);
 	const std::string scheme = str(a, "scheme", "bdf2");
 	const int repeat = (int) integer(a, "repeat", 1);
+	// README.md:357-375: discrete dividends at the event times
+	const Real D = num(a, "dividend", 0.);
+	const std::string dividendKind = str(a, "dividend_kind", "none");
+	const bool dividendFirst = integer(a, "dividend_first", 0) != 0;  // first in the reverse sweep = add()ed last
+	const bool withExercise = integer(a, "exercise", 1) != 0;
 
 	RectilinearGrid1 coarse( baseAxis(str(a, "axis", "tutorial"), K, K) );
 	auto grid = coarse.refined(refine);
@@ -207,6 +212,12 @@ int runBermudan(const Args &a) {
 	auto payoff = [K] (Real S) { return max(K - S, 0.); };
 	auto exercise = [K] (const Interpolant1 &V, Real S) {
 		return max(V(S), K - S);
+	};
+	auto cashDividend = [D] (const Interpolant1 &V, Real S) {
+		return V( max( S - D, 0. ) );
+	};
+	auto proportionalDividend = [D] (const Interpolant1 &V, Real S) {
+		return V( (1. - D) * S );
 	};
 	auto localVol = [alpha] (Real S) { return alpha / S; };
 
@@ -216,9 +227,17 @@ int runBermudan(const Args &a) {
 
 	for(int rep = 0; rep < repeat; ++rep) {
 		ReverseConstantStepper stepper(0., T, T / steps);
-		for(int e = 0; e < E; ++e) {
+		auto addDividends = [&] () {
+			for(int e = 0; e < E; ++e) {
+				if(dividendKind == "cash") stepper.add(T / E * e, cashDividend, grid);
+				else if(dividendKind == "proportional") stepper.add(T / E * e, proportionalDividend, grid);
+			}
+		};
+		if(!dividendFirst) addDividends();
+		if(withExercise) for(int e = 0; e < E; ++e) {
 			stepper.add(T / E * e, exercise, grid);
 		}
+		if(dividendFirst) addDividends();
 
 		BlackScholes1 bs(grid, r, localVol, q);
 
