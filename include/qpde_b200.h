@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define QPDE_ABI_VERSION 1
+#define QPDE_ABI_VERSION 2
 
 /* ---- status codes ----------------------------------------------------- */
 enum {
@@ -63,8 +63,12 @@ enum {
 	QPDE_PAYOFF_DIGITAL_PUT  = 3, /* S > K ? 0 : 1              :20-22      */
 	QPDE_PAYOFF_DIGITAL_CALL = 4, /* S < K ? 0 : 1              :13-15      */
 	QPDE_PAYOFF_STRADDLE     = 5, /* S < K ? K - S : S - K      :47-49      */
-	QPDE_PAYOFF_K_MINUS_S    = 6  /* K - S (exercise value of tutorial.cpp:103-105) */
+	QPDE_PAYOFF_K_MINUS_S    = 6, /* K - S (exercise value of tutorial.cpp:103-105) */
+	QPDE_EXERCISE_NONE       = -1 /* exercise_kind only: the event times carry no exercise transform */
 };
+
+/* ---- discrete dividend events (qpde_bs1d_batch.dividend_kind) ----------- */
+enum { QPDE_DIVIDEND_NONE = 0, QPDE_DIVIDEND_CASH = 1, QPDE_DIVIDEND_PROPORTIONAL = 2 };
 
 /* ---- volatility model of BlackScholes1's `v` argument ----------------- */
 enum {
@@ -139,7 +143,20 @@ typedef struct {
 	/* --- events: stepper.add(te, exerciseEvent, grid), te = T e / E for
 	 * e = 0 .. n_exercise-1 (tutorial.cpp:108-114); 0 = none */
 	int32_t n_exercise;
-	int32_t exercise_kind;   /* QPDE_PAYOFF_* generator of the exercise value */
+	int32_t exercise_kind;   /* QPDE_PAYOFF_* generator of the exercise value, or QPDE_EXERCISE_NONE */
+
+	/* --- discrete dividends at the same event times: stepper.add(te, dividendEvent, grid)
+	 * with  V(S) <- V(max(S - D, 0))  (cash; README.md:357-375, tutorial.cpp:82-99) or
+	 * V(S) <- V((1 - D) S)  (proportional), V evaluated through the grid's piecewise-
+	 * linear interpolant and mapped back pointwise (Core/Event.hpp:100-112,153-163,
+	 * Core/Interpolant.hpp:153-181,331-374).  Events at one time are applied in
+	 * descending add() order in a reverse sweep (IterativeMethod.hpp:1340-1352):
+	 * dividend_first = 0: exercise transform, then dividend transform (the dividend
+	 * events were add()ed before the exercise events — the dividend is paid before
+	 * the holder's right to exercise); 1: the other way round. */
+	int32_t dividend_kind;   /* QPDE_DIVIDEND_*                             */
+	int32_t dividend_first;
+	const double *dividend;  /* [C] D (cash amount >= 0, or proportion in [0, 1)) */
 
 	/* --- initial condition and obstacle */
 	const double *strike;    /* [C] K for the generators                    */

@@ -13,13 +13,14 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "lib", "libqpde_b200.so")
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 OK, ERR_INVALID, ERR_CUDA, ERR_NO_DEVICE, ERR_NOT_CONVERGED, ERR_UNSUPPORTED = 0, -1, -2, -3, -4, -5
 
 SCHEME = {"rannacher": 0, "cn": 1, "bdf1": 2, "bdf2": 3}
 PAYOFF = {"array": 0, "put": 1, "call": 2, "digital_put": 3, "digital_call": 4,
-          "straddle": 5, "k_minus_s": 6}
+          "straddle": 5, "k_minus_s": 6, "none": -1}
+DIVIDEND = {None: 0, "none": 0, "cash": 1, "proportional": 2}
 VOL = {"const": 0, "inverse_s": 1, "nodes": 2}
 KERNEL = {"auto": 0, "interleaved": 1, "resident": 2}
 KERNEL_NAME = {v: k for k, v in KERNEL.items()}
@@ -46,6 +47,7 @@ class Batch(C.Structure):
         ("sigma_nodes", _dp), ("sigma_nodes_stride", C.c_int64),
         ("T", _dp), ("dt", _dp), ("scheme", C.c_int32), ("max_steps", C.c_int32),
         ("n_exercise", C.c_int32), ("exercise_kind", C.c_int32),
+        ("dividend_kind", C.c_int32), ("dividend_first", C.c_int32), ("dividend", _dp),
         ("strike", _dp), ("payoff_kind", C.c_int32), ("obstacle_kind", C.c_int32),
         ("payoff", _dp), ("payoff_stride", C.c_int64),
         ("obstacle", _dp), ("obstacle_stride", C.c_int64),
@@ -335,7 +337,7 @@ class BatchSpec:
                  obstacle_array=None, vol_model="const", sigma_nodes=None,
                  n_exercise=0, exercise="k_minus_s", spot=None, tolerance=1e-6, scale=1.0,
                  penalty_tolerance=1e-6, max_inner=100, kernel="auto", outputs=OUT_ALL,
-                 n_contracts=None, controls=None, policy_max=False, jump=None):
+                 n_contracts=None, controls=None, policy_max=False, jump=None, dividend=None):
         axis = np.ascontiguousarray(axis, dtype=np.float64)
         if n_contracts is None:
             n_contracts = axis.shape[0] if axis.ndim == 2 else len(np.atleast_1d(strike))
@@ -372,6 +374,11 @@ class BatchSpec:
         b.max_steps = 0
         b.n_exercise = int(n_exercise)
         b.exercise_kind = PAYOFF[exercise]
+        if dividend is not None:
+            # dividend = dict(kind="cash" | "proportional", amount=[C] or scalar, first=bool)
+            b.dividend_kind = DIVIDEND[dividend["kind"]]
+            b.dividend_first = int(bool(dividend.get("first", False)))
+            b.dividend = vec(dividend["amount"])
         b.strike = vec(strike)
         b.payoff_kind = PAYOFF["array"] if payoff_array is not None else PAYOFF[payoff]
         if payoff_array is not None:

@@ -317,7 +317,20 @@ static int plan_create_impl(qpde_handle *h, const qpde_bs1d_batch *in,
 		}
 	}
 	if(in->n_exercise < 0) return fail(h, QPDE_ERR_INVALID, "n_exercise < 0");
-	if(in->n_exercise > 0 && !is_generator(in->exercise_kind)) return fail(h, QPDE_ERR_INVALID, "exercise_kind must be a generator");
+	if(in->n_exercise > 0 && in->exercise_kind != QPDE_EXERCISE_NONE && !is_generator(in->exercise_kind)) {
+		return fail(h, QPDE_ERR_INVALID, "exercise_kind must be a generator or QPDE_EXERCISE_NONE");
+	}
+	if(in->dividend_kind != QPDE_DIVIDEND_NONE) {
+		if(in->dividend_kind != QPDE_DIVIDEND_CASH && in->dividend_kind != QPDE_DIVIDEND_PROPORTIONAL) return fail(h, QPDE_ERR_INVALID, "unknown dividend_kind");
+		if(!in->dividend || in->n_exercise < 1) return fail(h, QPDE_ERR_INVALID, "dividends need the amounts and n_exercise >= 1 event times");
+		if(in->n_controls != 0) return fail(h, QPDE_ERR_UNSUPPORTED, "policy iteration with events is not supported");
+		for(int c = 0; c < C; ++c) {
+			const double D = in->dividend[c];
+			if(!(D >= 0.) || (in->dividend_kind == QPDE_DIVIDEND_PROPORTIONAL && !(D < 1.))) {
+				return fail(h, QPDE_ERR_INVALID, "contract %d: dividend must be >= 0 (and < 1 when proportional)", c);
+			}
+		}
+	}
 	for(int c = 0; c < C; ++c) {
 		if(!(in->T[c] > 0.) || !(in->dt[c] > DBL_EPSILON) || in->dt[c] > in->T[c]) {
 			return fail(h, QPDE_ERR_INVALID, "contract %d: need 0 < dt <= T", c);
@@ -341,6 +354,7 @@ static int plan_create_impl(qpde_handle *h, const qpde_bs1d_batch *in,
 	b.vol_model = in->vol_model;
 	b.scheme = in->scheme;
 	b.n_exercise = in->n_exercise; b.exercise_kind = in->exercise_kind;
+	b.dividend_kind = in->dividend_kind; b.dividend_first = in->dividend_first ? 1 : 0;
 	b.payoff_kind = in->payoff_kind;
 	b.obstacle_kind = in->american ? in->obstacle_kind : 0;
 	b.american = in->american ? 1 : 0;
@@ -369,6 +383,7 @@ static int plan_create_impl(qpde_handle *h, const qpde_bs1d_batch *in,
 	if(in->strike) QPDE_TRY(upload_vec(p, in->strike, C, &b.strike));
 	else           QPDE_TRY(upload_vec(p, in->spot, C, &b.strike));
 	if(in->spot) QPDE_TRY(upload_vec(p, in->spot, C, &b.spot));
+	if(in->dividend_kind != QPDE_DIVIDEND_NONE) QPDE_TRY(upload_vec(p, in->dividend, C, &b.dividend));
 	if(p->jump) {
 		b.n_fft = in->n_fft;
 		QPDE_TRY(upload_vec(p, in->jump_lambda, C, &b.jump_lambda));
@@ -443,7 +458,7 @@ static int plan_create_impl(qpde_handle *h, const qpde_bs1d_batch *in,
 		if(b.scheme == QPDE_SCHEME_BDF2) QPDE_TRY(dev_alloc(p, &w.xprev, NC));
 		else w.xprev = w.x;
 		if(b.american) QPDE_TRY(dev_alloc(p, &w.obst, NC));
-		if(b.n_exercise > 0) QPDE_TRY(dev_alloc(p, &w.evobst, NC));
+		if(b.n_exercise > 0 && b.exercise_kind != QPDE_EXERCISE_NONE) QPDE_TRY(dev_alloc(p, &w.evobst, NC));
 	}
 #undef QPDE_TRY
 	*out = p;

@@ -63,7 +63,7 @@ __global__ void k_interleaved_setup(DeviceBatch b, InterleavedWork w) {
 				? b.obstacle[(size_t)c * b.obstacle_stride + i]
 				: payoff_value(b.obstacle_kind, Si, K);
 		}
-		if(w.evobst) w.evobst[at] = payoff_value(b.exercise_kind, Si, K);
+		if(w.evobst) w.evobst[at] = payoff_value(b.exercise_kind, Si, K);   // allocated only with an exercise transform
 		Sm = Si; Si = Sp;
 		Sp = i + 2 < N ? refined_node(axis, b.refine, i + 2) : Sp;
 	}
@@ -214,11 +214,43 @@ k_interleaved_sweep(DeviceBatch b, InterleavedWork w, DeviceResult out) {
 		ns.end_step();
 
 		if(st.event_after) {
-			if(st.user_events > 0 && evob) {
-				for(int i = 0; i < N; ++i) {
-					const size_t at = (size_t)i * C;
-					const double ex = evob[at], v = x[at];
-					x[at] = v > ex ? v : ex;       // QuantPDE::max, EarlyInclude.hpp:48
+			// Events at one time go in descending add() order (IterativeMethod.hpp:1340-1352)
+			for(int ue = 0; ue < st.user_events; ++ue) {
+				for(int op = 0; op < 2; ++op) {
+					const bool is_dividend = (op == 0) == (b.dividend_first != 0);
+					if(is_dividend && b.dividend_kind != QPDE_DIVIDEND_NONE) {
+						// Event<1>::_doEvent with V(max(S - D, 0)) or V((1 - D) S) through the
+						// piecewise-linear interpolant (Core/Event.hpp:100-112, Interpolant.hpp:153-181,
+						// 331-374).  The shifted price never exceeds S_i, so the nodes are updated in
+						// place from the top down, and the bracketing interval only moves down.
+						const double D = b.dividend[c];
+						const double *S = w.S + c;
+						const double Sfirst = S[0], Slast = S[(size_t)(N - 1) * C];
+						int idx = N - 2;
+						for(int i = N - 1; i >= 0; --i) {
+							const double Si = S[(size_t)i * C];
+							const double at = b.dividend_kind == QPDE_DIVIDEND_CASH ? (Si - D > 0. ? Si - D : 0.) : (1. - D) * Si;
+							int k; double wgt;
+							if(at <= Sfirst) { k = 0; wgt = 1.; }
+							else if(at >= Slast) { k = N - 2; wgt = 0.; }
+							else {
+								while(idx > 0 && S[(size_t)idx * C] > at) --idx;      // S[idx] <= at < S[idx + 1]
+								k = idx;
+								wgt = (S[(size_t)(k + 1) * C] - at) / (S[(size_t)(k + 1) * C] - S[(size_t)k * C]);
+							}
+							double sum = 0.;
+							if(wgt > DBL_EPSILON) sum += wgt * x[(size_t)k * C];
+							if(1. - wgt > DBL_EPSILON) sum += (1. - wgt) * x[(size_t)(k + 1) * C];
+							x[(size_t)i * C] = sum;
+						}
+					}
+					if(!is_dividend && evob) {
+						for(int i = 0; i < N; ++i) {
+							const size_t at = (size_t)i * C;
+							const double ex = evob[at], v = x[at];
+							x[at] = v > ex ? v : ex;       // QuantPDE::max, EarlyInclude.hpp:48
+						}
+					}
 				}
 			}
 			ns.after_event();

@@ -21,6 +21,8 @@ struct DeviceBatch {
 	const double *T, *dt;
 	int scheme, max_steps;
 	int n_exercise, exercise_kind;
+	int dividend_kind, dividend_first;
+	const double *dividend;
 	const double *strike;
 	int payoff_kind, obstacle_kind;
 	const double *payoff; long long payoff_stride;

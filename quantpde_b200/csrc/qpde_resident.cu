@@ -205,7 +205,7 @@ k_resident_sweep(DeviceBatch b, DeviceResult out) {
 				? b.obstacle[(size_t)cidx * b.obstacle_stride + i]
 				: payoff_value(b.obstacle_kind, S_at(i), K);
 		}
-		return payoff_value(b.exercise_kind, S_at(i), K);
+		return b.exercise_kind == QPDE_EXERCISE_NONE ? -CUDART_INF : payoff_value(b.exercise_kind, S_at(i), K);
 	};
 #pragma unroll
 	for(int j = 0; j < M; ++j) {
@@ -474,10 +474,56 @@ k_resident_sweep(DeviceBatch b, DeviceResult out) {
 
 		if(st.event_after) {
 			if(EVENTS && st.user_events > 0) {
-				// Event<1>::_doEvent with max(V(S), K - S): Core/Event.hpp:100-112
+				// Events at one time go in descending add() order (IterativeMethod.hpp:1340-1352)
+				for(int ue = 0; ue < st.user_events; ++ue) {
+					for(int op = 0; op < 2; ++op) {
+						const bool is_dividend = (op == 0) == (b.dividend_first != 0);
+						if(is_dividend && b.dividend_kind != QPDE_DIVIDEND_NONE) {
+							// Event<1>::_doEvent with V(max(S - D, 0)) or V((1 - D) S): the solution goes to
+							// shared memory (sm_lb is free between steps), every node reads its two
+							// neighbours of the shifted price (Core/Interpolant.hpp:153-181,331-374).
+							// Fixed-trip bisection: no divergence in front of the solver's shuffles.
+							const double D = b.dividend[cidx];
 #pragma unroll
-				for(int j = 0; j < M; ++j) x[j] = x[j] > pz[j] ? x[j] : pz[j];
-				if(tail_owner) sm.tail.x = sm.tail.x > sm.tail.pz ? sm.tail.x : sm.tail.pz;
+							for(int j = 0; j < M; ++j) sm_lb[j * P + tid] = x[j];
+							__syncthreads();
+							auto V_at = [&] (int i) -> double { return i >= n_main ? sm.tail.x : sm_lb[(i % M) * P + (i / M)]; };
+							const double Sfirst = S_at(0), Slast = S_at(N - 1);
+							auto shifted = [&] (double Si) -> double {
+								double at = b.dividend_kind == QPDE_DIVIDEND_CASH ? (Si - D > 0. ? Si - D : 0.) : (1. - D) * Si;
+								int lo = 0, hi = N - 2;
+								for(int it = 0; it < 13; ++it) {          // 2^13 > any supported N
+									const int mid = (lo + hi + 1) >> 1;
+									const bool up = S_at(mid) <= at;
+									lo = up ? mid : lo; hi = up ? hi : mid - 1;
+								}
+								double wgt = (S_at(lo + 1) - at) / (S_at(lo + 1) - S_at(lo));
+								int idx = lo;
+								if(at <= Sfirst) { idx = 0; wgt = 1.; }
+								if(at >= Slast) { idx = N - 2; wgt = 0.; }
+								double sum = 0.;
+								if(wgt > DBL_EPSILON) sum += wgt * V_at(idx);
+								if(1. - wgt > DBL_EPSILON) sum += (1. - wgt) * V_at(idx + 1);
+								return sum;
+							};
+							double xn[M];
+#pragma unroll
+							for(int j = 0; j < M; ++j) xn[j] = i0 + j < n_main ? shifted(sm_S[j * P + tid]) : 0.;
+							const double xt = has_tail ? shifted(Slast) : 0.;   // uniform: every thread
+							__syncthreads();
+#pragma unroll
+							for(int j = 0; j < M; ++j) x[j] = xn[j];
+							if(tail_owner) sm.tail.x = xt;
+						}
+						if(!is_dividend && b.exercise_kind != QPDE_EXERCISE_NONE) {
+							// Event<1>::_doEvent with max(V(S), K - S): Core/Event.hpp:100-112
+#pragma unroll
+							for(int j = 0; j < M; ++j) x[j] = x[j] > pz[j] ? x[j] : pz[j];
+							if(tail_owner) sm.tail.x = sm.tail.x > sm.tail.pz ? sm.tail.x : sm.tail.pz;
+						}
+					}
+				}
+				__syncthreads();
 				sm_xfirst[tid] = x[0];
 				sm_xlast[tid + 1] = x[M - 1];
 				if(tid == 0) sm_xfirst[P] = 0.;

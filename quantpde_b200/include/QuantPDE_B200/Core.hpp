@@ -379,25 +379,55 @@ public:
 	}
 };
 
+// The tagged forms of the README's dividend event  [D] (const Interpolant1 &V, Real S) { return
+// V( max( S - D, 0. ) ); }  (README.md:357-375, tutorial.cpp:82-99) and its proportional sibling
+// V( (1. - D) * S ): an arbitrary Event<1> lambda cannot cross the C ABI.
+struct Dividend {
+	int kind; Real amount;
+	Dividend() : kind(QPDE_DIVIDEND_NONE), amount(0.) {}
+	Dividend(int kind, Real amount) : kind(kind), amount(amount) {}
+	static Dividend cash(Real D) { return Dividend(QPDE_DIVIDEND_CASH, D); }
+	static Dividend proportional(Real D) { return Dividend(QPDE_DIVIDEND_PROPORTIONAL, D); }
+};
+
 // ReverseConstantStepper(t0, T, dt) — Core/Stepper.hpp:27-36
 class ReverseConstantStepper : public Iteration {
 	Real t0, T, dt;
 	ToleranceIteration *inner;
-	int nExercise;
+	int nExercise, nDividend;
 	Payoff exercise;
+	Dividend dividend_;
+	bool dividendAddedFirst;
 public:
 	ReverseConstantStepper(Real startTime, Real endTime, Real dt)
-			: t0(startTime), T(endTime), dt(dt), inner(nullptr), nExercise(0) {
+			: t0(startTime), T(endTime), dt(dt), inner(nullptr), nExercise(0), nDividend(0),
+			  dividendAddedFirst(false) {
 		if(startTime != 0.) throw std::invalid_argument("QuantPDE_B200: startTime must be 0");
 	}
 	void setInnerIteration(ToleranceIteration &it) { inner = &it; }   // IterativeMethod.hpp:977
 	// stepper.add(T / E * e, exerciseEvent, grid) for e = 0 .. E-1 (tutorial.cpp:103-114)
-	void addExerciseDates(int E, Payoff exerciseValue) { nExercise = E; exercise = std::move(exerciseValue); }
+	void addExerciseDates(int E, Payoff exerciseValue) {
+		if(nDividend > 0 && nDividend != E) throw std::invalid_argument("QuantPDE_B200: exercise and dividend dates must coincide");
+		nExercise = E; exercise = std::move(exerciseValue);
+	}
+	// stepper.add(T / E * e, dividendEvent, grid) for e = 0 .. E-1 (README.md:357-375).  As in the
+	// reference the order of the add() calls matters: events at one time are applied in descending
+	// add() order by the reverse sweep (IterativeMethod.hpp:1340-1352), so calling this BEFORE
+	// addExerciseDates models a dividend paid before the holder's right to exercise.
+	void addDividendDates(int E, Dividend d) {
+		if(nExercise > 0 && nExercise != E) throw std::invalid_argument("QuantPDE_B200: exercise and dividend dates must coincide");
+		nDividend = E; dividend_ = d; dividendAddedFirst = nExercise == 0;
+	}
 
 	Real expiry() const { return T; }
 	Real timestep() const { return dt; }
 	int exerciseDates() const { return nExercise; }
 	const Payoff &exercisePayoff() const { return exercise; }
+	int eventDates() const { return nExercise > 0 ? nExercise : nDividend; }
+	const Dividend &dividend() const { return dividend_; }
+	bool hasDividends() const { return nDividend > 0 && dividend_.kind != QPDE_DIVIDEND_NONE; }
+	// the dividend transform goes first in the reverse sweep iff its events were add()ed last
+	bool dividendFirstInSweep() const { return hasDividends() && nExercise > 0 && !dividendAddedFirst; }
 	ToleranceIteration *innerIteration() const { return inner; }
 
 	// Iteration::solve(domain, initialCondition, root, solver) — IterativeMethod.hpp:1065-1079
@@ -437,7 +467,11 @@ public:
 		const int N = items[0].grid->size(), nAxis = items[0].grid->coarse().size();
 		const int refine = items[0].grid->refinement();
 		const bool american = p0 != nullptr;
-		const int nEx = items[0].stepper->exerciseDates();
+		const int nEx = items[0].stepper->exerciseDates(), nEv = items[0].stepper->eventDates();
+		const bool dividends = items[0].stepper->hasDividends();
+		const int divKind = items[0].stepper->dividend().kind;
+		const bool divFirst = items[0].stepper->dividendFirstInSweep();
+		std::vector<Real> divAmount;
 		ToleranceIteration *tol0 = items[0].stepper->innerIteration();
 		if(american && !tol0) throw std::invalid_argument("QuantPDE_B200: penalty root needs setInnerIteration()");
 
@@ -455,7 +489,10 @@ public:
 			decode(it.root, d, p);
 			if(it.grid->size() != N || it.grid->coarse().size() != nAxis || it.grid->refinement() != refine
 					|| d->scheme != d0->scheme || (p != nullptr) != american
-					|| it.stepper->exerciseDates() != nEx || d->op.v.model() != volModel
+					|| it.stepper->exerciseDates() != nEx || it.stepper->eventDates() != nEv
+					|| it.stepper->hasDividends() != dividends
+					|| (dividends && (it.stepper->dividend().kind != divKind || it.stepper->dividendFirstInSweep() != divFirst))
+					|| d->op.v.model() != volModel
 					|| it.payoff.kind() != payKind || (american && p->obstacle.kind() != obsKind)
 					|| (d->policy != nullptr) != policy
 					|| (policy && ((int)d->policy->controls.size() != nControls
@@ -467,6 +504,7 @@ public:
 			r[c] = d->op.r; sig[c] = d->op.v.param(); q[c] = d->op.q;
 			if(policy) controls.insert(controls.end(), d->policy->controls.begin(), d->policy->controls.end());
 			T[c] = it.stepper->expiry(); dt[c] = it.stepper->timestep();
+			if(dividends) divAmount.push_back(it.stepper->dividend().amount);
 			K[c] = it.payoff.kind() != QPDE_PAYOFF_ARRAY ? it.payoff.strike()
 				: (american && p->obstacle.kind() != QPDE_PAYOFF_ARRAY ? p->obstacle.strike()
 				: (nEx > 0 ? it.stepper->exercisePayoff().strike() : 0.));
@@ -489,8 +527,9 @@ public:
 		b.vol_model = volModel;
 		if(volModel == QPDE_VOL_NODES) { b.sigma_nodes = sigArr.data(); b.sigma_nodes_stride = N; }
 		b.T = T.data(); b.dt = dt.data(); b.scheme = d0->scheme; b.max_steps = 0;
-		b.n_exercise = nEx;
-		b.exercise_kind = nEx > 0 ? items[0].stepper->exercisePayoff().kind() : QPDE_PAYOFF_K_MINUS_S;
+		b.n_exercise = nEv;
+		b.exercise_kind = nEx > 0 ? items[0].stepper->exercisePayoff().kind() : QPDE_EXERCISE_NONE;
+		if(dividends) { b.dividend_kind = divKind; b.dividend_first = divFirst ? 1 : 0; b.dividend = divAmount.data(); }
 		b.strike = K.data();
 		b.payoff_kind = payKind; b.obstacle_kind = obsKind;
 		if(payKind == QPDE_PAYOFF_ARRAY) { b.payoff = payArr.data(); b.payoff_stride = N; }

@@ -39,6 +39,24 @@ for sch in ("bdf2", "rannacher", "bdf1", "cn"):
         CASES.append(("bermudan_%s_k%d" % (sch, k), "bermudan",
                       dict(steps=100 * 2 ** k, refine=k, scheme=sch, K=100.0, r=0.04, alpha=20.0, T=1.0, E=10)))
 
+# README.md:357-375: discrete dividends at the event times (general interpolating events,
+# Event.hpp:100-112); dividend_first = which transform the reverse sweep applies first
+CASES.append(("dividend_cash_bdf2_k1", "bermudan",
+              dict(steps=200, refine=1, scheme="bdf2", K=100.0, r=0.04, alpha=20.0, T=1.0, E=10,
+                   dividend=1.0, dividend_kind="cash", dividend_first=0)))
+CASES.append(("dividend_cash_first_rannacher_k0", "bermudan",
+              dict(steps=100, refine=0, scheme="rannacher", K=100.0, r=0.04, alpha=20.0, T=1.0, E=10,
+                   dividend=1.0, dividend_kind="cash", dividend_first=1)))
+CASES.append(("dividend_proportional_bdf2_k0", "bermudan",
+              dict(steps=100, refine=0, scheme="bdf2", K=110.0, r=0.03, alpha=25.0, T=0.75, E=4,
+                   dividend=0.02, dividend_kind="proportional", dividend_first=0)))
+CASES.append(("dividend_cash_european_cn_k2", "bermudan",
+              dict(steps=80, refine=2, scheme="cn", K=100.0, r=0.04, alpha=20.0, T=1.0, E=10,
+                   dividend=2.5, dividend_kind="cash", dividend_first=0, exercise=0)))
+CASES.append(("dividend_cash_bdf1_k1", "bermudan",
+              dict(steps=60, refine=1, scheme="bdf1", K=95.0, r=0.05, alpha=18.0, T=0.5, E=3,
+                   dividend=0.7, dividend_kind="cash", dividend_first=1)))
+
 # examples/unequal_borrowing_lending_rates.cpp: HJB with the interest rate as a control
 for lp in (0, 1):
     for k in (0, 1, 2):

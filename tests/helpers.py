@@ -55,7 +55,9 @@ def run_oracle_case(po, mode, kw):
         return po.hjb_straddle(kw["K"], kw["r_l"], kw["r_b"], kw["vol"], kw["T"], kw["steps"], kw["refine"],
                                long_position=bool(kw["long"]), scheme=kw["scheme"])
     return po.bermudan_put(kw["K"], kw["r"], kw["alpha"], kw["T"], kw["steps"], kw["E"],
-                           kw["refine"], scheme=kw["scheme"])
+                           kw["refine"], scheme=kw["scheme"], dividend=kw.get("dividend"),
+                           dividend_kind=kw.get("dividend_kind", "cash"),
+                           dividend_first=bool(kw.get("dividend_first", 0)), exercise=bool(kw.get("exercise", 1)))
 
 
 def spec_for_case(qpde, po, mode, kw, kernel="auto", copies=1):
@@ -94,4 +96,6 @@ def spec_for_case(qpde, po, mode, kw, kernel="auto", copies=1):
         axis=np.tile(axis, (copies, 1)), refine=kw["refine"], r=kw["r"], sigma=kw["alpha"], q=0.0,
         T=kw["T"], dt=kw["T"] / kw["steps"], strike=np.full(copies, K), scheme=kw["scheme"],
         american=False, payoff="put", vol_model="inverse_s", n_exercise=kw["E"],
-        exercise="k_minus_s", kernel=kernel)
+        exercise="k_minus_s" if kw.get("exercise", 1) else "none", kernel=kernel,
+        dividend=None if "dividend" not in kw else dict(kind=kw["dividend_kind"], amount=kw["dividend"],
+                                                      first=bool(kw.get("dividend_first", 0))))
