@@ -8,7 +8,9 @@
 // All refinement levels are put into ONE batch and swept in one device call.
 //
 //   vanilla_options_b200 [american=1] [call=0] [kn=5] [k0=0] [K=100] [S0=100]
-//                        [r=.04] [vol=.2] [q=0] [T=1] [N=12] [device=0]
+//                        [r=.04] [vol=.2] [q=0] [T=1] [N=12] [variable=0] [device=0]
+// variable=1: use_variable_timestepping of vanilla_options.cpp:52-58 (ReverseVariableStepper,
+// target 1 / factor)
 #include <QuantPDE_B200/Core.hpp>
 
 #include <chrono>
@@ -41,6 +43,7 @@ int main(int argc, char **argv) {
 	const Real r = arg(a, "r", .04), vol = arg(a, "vol", .2), divs = arg(a, "q", 0.);
 	const Real T = arg(a, "T", 1.);
 	const int N = (int) arg(a, "N", 12);
+	const bool variable = arg(a, "variable", 0) != 0;
 
 	RectilinearGrid1 grid( (S_0 * Axis::special()) + (K * Axis::special()) );
 	const Payoff payoff = call ? callPayoff(K) : putPayoff(K);
@@ -75,7 +78,8 @@ int main(int argc, char **argv) {
 			unique_ptr<Level> L(new Level());
 			L->refined_grid = grid.refined(k);
 			L->bs.reset(new BlackScholes1(L->refined_grid, r, vol, divs));
-			L->stepper.reset(new ReverseConstantStepper(0., T, T / N2k));
+			if(variable) L->stepper.reset(new ReverseVariableStepper(0., T, T / N2k, 1. / factor));
+			else L->stepper.reset(new ReverseConstantStepper(0., T, T / N2k));
 			L->discretization.reset(new ReverseRannacher(L->refined_grid, *L->bs));
 			L->discretization->setIteration(*L->stepper);
 			L->root = L->discretization.get();

@@ -138,7 +138,17 @@ typedef struct {
 	const double *dt;        /* [C] step size (e.g. T / 1000)               */
 	int32_t scheme;          /* QPDE_SCHEME_*                               */
 	int32_t max_steps;       /* upper bound on replayed steps per contract;
-	                            0 = derive (the library replays the loop)   */
+	                            0 = derive (the library replays the loop);
+	                            required (> 0) with variable_target          */
+	/* --- ReverseVariableStepper(0, T, dt, target, scale) instead of the constant
+	 * stepper (Core/Stepper.hpp:60-126, examples/vanilla_options.cpp:52-58): dt[c]
+	 * is the first step, afterwards dt *= target / (relativeError(V^{n+1}, V^n,
+	 * scale) + epsilon) before the usual clamp at the terminal time.  NULL =
+	 * constant steps.  No events (the reference's stepper reads an emptied history
+	 * slot after one), no jump term.  A contract that would need more than
+	 * max_steps steps stops with status 3. */
+	const double *variable_target; /* [C] */
+	double variable_scale;   /* relativeError scale of the stepper, 1 (EarlyInclude.hpp:63) */
 
 	/* --- events: stepper.add(te, exerciseEvent, grid), te = T e / E for
 	 * e = 0 .. n_exercise-1 (tutorial.cpp:108-114); 0 = none */
@@ -230,7 +240,7 @@ typedef struct {
 	uint8_t *active;      /* [C][N] final penalty active set, 0/1
 	                         (PenaltyMethod::constraintMask, PenaltyMethod.hpp:127-139) */
 	int64_t  active_stride;
-	int32_t *status;      /* [C] 0 ok, 1 = some step hit max_inner          */
+	int32_t *status;      /* [C] 0 ok, 1 = some step hit max_inner, 3 = max_steps exhausted (variable steps) */
 } qpde_bs1d_result;
 
 /* ---- context ---------------------------------------------------------- */

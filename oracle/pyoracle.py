@@ -42,7 +42,9 @@ class Problem(C.Structure):
                 ("jump_weights", C.POINTER(C.c_double)), ("jump_nfft", C.c_int),
                 ("jump_lambda", C.c_double), ("jump_x0", C.c_double), ("jump_dx", C.c_double),
                 ("solver", C.c_int),
-                ("dividend_kind", C.c_int), ("dividend_first", C.c_int), ("dividend", C.c_double)]
+                ("dividend_kind", C.c_int), ("dividend_first", C.c_int), ("dividend", C.c_double),
+                ("variable_target", C.c_double), ("variable_scale", C.c_double), ("variable_dt0", C.c_double),
+                ("steps_taken", C.POINTER(C.c_int))]
 
 
 DIVIDENDS = {None: 0, "none": 0, "cash": 1, "proportional": 2}
@@ -138,8 +140,9 @@ def interp(x, v, c):
 def sweep(S, lo, di, up, v0, T, steps, n_steps, scheme="rannacher",
           american=False, obstacle=None, event_obstacle=None,
           tolerance=1e-6, scale=1.0, penalty_tol=1e-6, max_inner=1000, solver=0,
-          policy_rows=None, policy_max=False, jump=None, dividend=None):
-    """Returns dict(V, inner, mask, status).  dividend = (kind, D, first).  policy_rows = (lo, di, up), each
+          policy_rows=None, policy_max=False, jump=None, dividend=None, variable=None):
+    """Returns dict(V, inner, mask, status).  dividend = (kind, D, first); variable = (dt0, target,
+    scale): ReverseVariableStepper, `steps` ignored, n_steps = capacity, out['n_steps'] = steps taken.  policy_rows = (lo, di, up), each
     [n_controls][n]: PolicyIteration over the controls."""
     n = len(S)
     arrs = [np.ascontiguousarray(a, dtype=np.float64) for a in (S, lo, di, up, v0)]
@@ -149,7 +152,12 @@ def sweep(S, lo, di, up, v0, T, steps, n_steps, scheme="rannacher",
     p.S, p.lo, p.di, p.up, p.v0 = [_dp(a) for a in arrs]
     p.scheme = SCHEMES[scheme]
     p.n_steps = n_steps
-    p.steps = C.cast(steps, C.POINTER(Step))
+    if steps is not None:
+        p.steps = C.cast(steps, C.POINTER(Step))
+    taken = C.c_int(n_steps)
+    if variable is not None:
+        p.variable_dt0, p.variable_target, p.variable_scale = float(variable[0]), float(variable[1]), float(variable[2])
+        p.steps_taken = C.pointer(taken)
     p.american = int(american)
     if obstacle is not None:
         obstacle = np.ascontiguousarray(obstacle, dtype=np.float64)
@@ -177,15 +185,23 @@ def sweep(S, lo, di, up, v0, T, steps, n_steps, scheme="rannacher",
     status = lib().qpo_sweep_1d(C.byref(p), _dp(V),
                                 inner.ctypes.data_as(C.POINTER(C.c_int)),
                                 mask.ctypes.data_as(C.POINTER(C.c_ubyte)))
-    return dict(V=V, inner=inner, mask=mask, status=status)
+    if variable is not None:
+        inner = inner[:taken.value]
+    return dict(V=V, inner=inner, mask=mask, status=status, n_steps=taken.value)
 
 
 def american_put(K, r, vol, T, n_steps, refine_times, q=0.0, S0=None, call=False,
-                 american=True, scheme="rannacher", solver=0):
-    """The vanilla_options.cpp wiring on the oracle."""
+                 american=True, scheme="rannacher", solver=0, variable_target=None, max_steps=100000):
+    """The vanilla_options.cpp wiring on the oracle.  variable_target: ReverseVariableStepper(0, T,
+    T / n_steps, target) as vanilla_options.cpp:52-58 builds it."""
     S = vanilla_grid(K, S0, refine_times)
     lo, di, up = bs_coeffs(S, r, vol, q)
     payoff = np.where(S < K, 0.0, S - K) if call else np.where(S < K, K - S, 0.0)
+    if variable_target:
+        out = sweep(S, lo, di, up, payoff, T, None, max_steps, scheme=scheme, american=american, obstacle=payoff,
+                    solver=solver, variable=(T / n_steps, variable_target, 1.0))
+        out["S"] = S
+        return out
     steps, n = schedule(T, T / n_steps)
     out = sweep(S, lo, di, up, payoff, T, steps, n, scheme=scheme,
                 american=american, obstacle=payoff, solver=solver)

@@ -525,6 +525,10 @@ int qpo_sweep_1d(const qpo_problem *p, double *V, int *inner,
 	double *bj = (double *)calloc((size_t)n, sizeof(double)); /* op.b(): explicit jump term or 0 */
 	tri_lu lu;
 	int s, i, k, status = 0;
+	const int variable = p->variable_target > 0.;
+	qpo_step vstep;
+	double vdt = p->variable_dt0, vt_t = p->T, vt_dt = -1., vt_dtPrevious = -1.;
+	int vt_done = 0;
 	/* stepper history: times of iterand(0), iterand(1) */
 	double time1 = 0., time0 = 0.;
 	int hist = 0;          /* number of iterands in the stepper's ring */
@@ -541,10 +545,44 @@ int qpo_sweep_1d(const qpo_problem *p, double *V, int *inner,
 	time1 = p->T;
 	hist = 1;
 
-	for(s = 0; s < p->n_steps; ++s) {
-		const qpo_step *st = &p->steps[s];
-		const double t = st->t;
+	for(s = 0; ; ++s) {
+		const qpo_step *st;
+		double t;
 		int a_same, its = 0, notdone = 0;
+		if(variable) {
+			/* VariableStepper::timestep (Stepper.hpp:63-83) inside
+			 * QUANT_PDE_TMP_TIMESTEP (IterativeMethod.hpp:1296-1308); the only event
+			 * is the NullEvent at 0 */
+			double tmp, dt;
+			if(vt_done) break;
+			if(s >= p->n_steps) { status = 3; break; }   /* capacity exceeded */
+			if(s > 0) {
+				double err = 0.;
+				for(i = 0; i < n; ++i) {
+					/* relativeError(v1, v0, scale), IterativeMethod.hpp:1125-1137 */
+					const double fa = fabs(v1[i]), fb = fabs(v0[i]);
+					double den = fa < fb ? fb : fa, e;
+					den = p->variable_scale < den ? den : p->variable_scale;
+					e = fabs(v1[i] - v0[i]) / den;
+					if(e > err) err = e;
+				}
+				vdt *= p->variable_target / (err + DBL_EPSILON);
+			}
+			vt_dtPrevious = vt_dt;
+			dt = vdt;
+			tmp = vt_t + -1. * dt;
+			if(fabs(tmp - 0.) < DBL_EPSILON) tmp = 0.;
+			else if(tmp < 0.) { tmp = 0.; dt = -1. * (0. - vt_t); }
+			vt_t = tmp; vt_dt = dt;
+			vstep.t = tmp; vstep.dt = dt; vstep.same_dt = (dt == vt_dtPrevious);
+			vt_done = !(0. < tmp + -1. * DBL_EPSILON);
+			vstep.event_after = vt_done; vstep.user_events = 0;
+			st = &vstep;
+		} else {
+			if(s >= p->n_steps) break;
+			st = &p->steps[s];
+		}
+		t = st->t;
 		int use_cn = 0, use_bdf2 = 0;
 		double hA = 0.;
 
@@ -783,6 +821,7 @@ int qpo_sweep_1d(const qpo_problem *p, double *V, int *inner,
 		}
 	}
 
+	if(p->steps_taken) *p->steps_taken = s;
 	if(mask) {
 		/* PenaltyMethod::constraintMask (PenaltyMethod.hpp:127-139) on the
 		 * tolerance iteration's last iterand */

@@ -103,6 +103,13 @@ typedef struct {
 	int dividend_kind;     /* QPO_DIVIDEND_* */
 	int dividend_first;
 	double dividend;
+	/* ReverseVariableStepper(0, T, variable_dt0, variable_target, variable_scale)
+	 * (Core/Stepper.hpp:60-126, examples/vanilla_options.cpp:52-64) when
+	 * variable_target > 0: `steps` is ignored, n_steps is the capacity of `inner`,
+	 * *steps_taken the number of steps taken.  No user events (after an event the
+	 * reference's stepper reads a history slot that clear() has emptied). */
+	double variable_target, variable_scale, variable_dt0;
+	int *steps_taken;
 } qpo_problem;
 enum { QPO_DIVIDEND_NONE = 0, QPO_DIVIDEND_CASH = 1, QPO_DIVIDEND_PROPORTIONAL = 2 };
 

@@ -129,9 +129,16 @@ int runVanilla(const Args &a) {
 	std::vector<long> inner, mask;
 	long timesteps = 0;
 
+	// examples/vanilla_options.cpp:52-64: ReverseVariableStepper(0, T, T / N2k, 1 / factor)
+	const Real variableTarget = num(a, "variable_target", 0.);
+
 	for(int rep = 0; rep < repeat; ++rep) {
 		BlackScholes1 bs(grid, r, vol, q);
-		ReverseConstantStepper stepper(0., T, T / steps);
+		std::unique_ptr<ReverseConstantStepper> constantStepper;
+		std::unique_ptr<ReverseVariableStepper> variableStepper;
+		if(variableTarget > 0.) variableStepper.reset(new ReverseVariableStepper(0., T, T / steps, variableTarget));
+		else constantStepper.reset(new ReverseConstantStepper(0., T, T / steps));
+		Iteration &stepper = variableTarget > 0. ? (Iteration &) *variableStepper : (Iteration &) *constantStepper;
 
 		std::unique_ptr<IterationNode> discretization;
 		if(scheme == "rannacher") {

@@ -46,6 +46,7 @@ class Batch(C.Structure):
         ("vol_model", C.c_int32), ("reserved0", C.c_int32),
         ("sigma_nodes", _dp), ("sigma_nodes_stride", C.c_int64),
         ("T", _dp), ("dt", _dp), ("scheme", C.c_int32), ("max_steps", C.c_int32),
+        ("variable_target", _dp), ("variable_scale", C.c_double),
         ("n_exercise", C.c_int32), ("exercise_kind", C.c_int32),
         ("dividend_kind", C.c_int32), ("dividend_first", C.c_int32), ("dividend", _dp),
         ("strike", _dp), ("payoff_kind", C.c_int32), ("obstacle_kind", C.c_int32),
@@ -337,7 +338,8 @@ class BatchSpec:
                  obstacle_array=None, vol_model="const", sigma_nodes=None,
                  n_exercise=0, exercise="k_minus_s", spot=None, tolerance=1e-6, scale=1.0,
                  penalty_tolerance=1e-6, max_inner=100, kernel="auto", outputs=OUT_ALL,
-                 n_contracts=None, controls=None, policy_max=False, jump=None, dividend=None):
+                 n_contracts=None, controls=None, policy_max=False, jump=None, dividend=None,
+                 variable_target=None, variable_scale=1.0, max_steps=0):
         axis = np.ascontiguousarray(axis, dtype=np.float64)
         if n_contracts is None:
             n_contracts = axis.shape[0] if axis.ndim == 2 else len(np.atleast_1d(strike))
@@ -371,7 +373,10 @@ class BatchSpec:
             b.sigma_nodes, b.sigma_nodes_stride = rows(sigma_nodes)
         b.T, b.dt = vec(T), vec(dt)
         b.scheme = SCHEME[scheme]
-        b.max_steps = 0
+        b.max_steps = int(max_steps)
+        if variable_target is not None:
+            b.variable_target = vec(variable_target)
+            b.variable_scale = float(variable_scale)
         b.n_exercise = int(n_exercise)
         b.exercise_kind = PAYOFF[exercise]
         if dividend is not None:
@@ -497,6 +502,8 @@ class Plan:
 
 
 def sweep_max_steps(spec):
+    if spec.struct.max_steps > 0:
+        return int(spec.struct.max_steps)
     Tmax = np.max(np.ctypeslib.as_array(spec.struct.T, (spec.C,)) /
                   np.ctypeslib.as_array(spec.struct.dt, (spec.C,)))
     return int(np.floor(Tmax)) + 3 + 2 * spec.struct.n_exercise

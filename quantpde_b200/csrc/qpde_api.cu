@@ -316,6 +316,12 @@ static int plan_create_impl(qpde_handle *h, const qpde_bs1d_batch *in,
 			return fail(h, QPDE_ERR_UNSUPPORTED, "jump diffusion needs scheme BDF1 or BDF2");
 		}
 	}
+	if(in->variable_target) {
+		if(in->max_steps < 1) return fail(h, QPDE_ERR_INVALID, "variable time steps need max_steps > 0");
+		if(!(in->variable_scale > 0.)) return fail(h, QPDE_ERR_INVALID, "variable_scale must be > 0");
+		if(in->n_exercise > 0 || in->jump_lambda) return fail(h, QPDE_ERR_UNSUPPORTED, "variable time steps with events or a jump term are not supported");
+		for(int c = 0; c < C; ++c) if(!(in->variable_target[c] > 0.)) return fail(h, QPDE_ERR_INVALID, "contract %d: variable_target must be > 0", c);
+	}
 	if(in->n_exercise < 0) return fail(h, QPDE_ERR_INVALID, "n_exercise < 0");
 	if(in->n_exercise > 0 && in->exercise_kind != QPDE_EXERCISE_NONE && !is_generator(in->exercise_kind)) {
 		return fail(h, QPDE_ERR_INVALID, "exercise_kind must be a generator or QPDE_EXERCISE_NONE");
@@ -383,6 +389,7 @@ static int plan_create_impl(qpde_handle *h, const qpde_bs1d_batch *in,
 	if(in->strike) QPDE_TRY(upload_vec(p, in->strike, C, &b.strike));
 	else           QPDE_TRY(upload_vec(p, in->spot, C, &b.strike));
 	if(in->spot) QPDE_TRY(upload_vec(p, in->spot, C, &b.spot));
+	if(in->variable_target) { QPDE_TRY(upload_vec(p, in->variable_target, C, &b.variable_target)); b.variable_scale = in->variable_scale; }
 	if(in->dividend_kind != QPDE_DIVIDEND_NONE) QPDE_TRY(upload_vec(p, in->dividend, C, &b.dividend));
 	if(p->jump) {
 		b.n_fft = in->n_fft;
@@ -455,7 +462,7 @@ static int plan_create_impl(qpde_handle *h, const qpde_bs1d_batch *in,
 		QPDE_TRY(dev_alloc(p, &w.di, NC * sets)); QPDE_TRY(dev_alloc(p, &w.up, NC * sets));
 		QPDE_TRY(dev_alloc(p, &w.x, NC));  QPDE_TRY(dev_alloc(p, &w.lb, NC));
 		QPDE_TRY(dev_alloc(p, &w.cp, NC)); QPDE_TRY(dev_alloc(p, &w.dp, NC));
-		if(b.scheme == QPDE_SCHEME_BDF2) QPDE_TRY(dev_alloc(p, &w.xprev, NC));
+		if(b.scheme == QPDE_SCHEME_BDF2 || b.variable_target) QPDE_TRY(dev_alloc(p, &w.xprev, NC));
 		else w.xprev = w.x;
 		if(b.american) QPDE_TRY(dev_alloc(p, &w.obst, NC));
 		if(b.n_exercise > 0 && b.exercise_kind != QPDE_EXERCISE_NONE) QPDE_TRY(dev_alloc(p, &w.evobst, NC));

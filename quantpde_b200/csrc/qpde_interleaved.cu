@@ -96,8 +96,17 @@ k_interleaved_sweep(DeviceBatch b, InterleavedWork w, DeviceResult out) {
 	int n_steps = 0, inner_total = 0, status = 0;
 	bool more = true;
 
+	// ReverseVariableStepper (Core/Stepper.hpp:60-126)
+	const bool variable = b.variable_target != nullptr;
+	const double vtarget = variable ? b.variable_target[c] : 0.;
+	double vdt = b.dt[c];
+
 	while(more) {
 		qpde_step st;
+		if(variable) {
+			if(n_steps >= b.max_steps) { status = 3; break; }      // output capacity
+			rp.dt_const = vdt;                                      // VariableStepper::timestep()
+		}
 		more = rp.next(st);
 		const double t = st.t;
 		const int kind = ns.kind();
@@ -140,7 +149,7 @@ k_interleaved_sweep(DeviceBatch b, InterleavedWork w, DeviceResult out) {
 		}
 		// history push: iterand(1) <- iterand(0).  For BDF2 the previous
 		// iterand must survive the solve, so copy it before x is overwritten.
-		if(b.scheme == QPDE_SCHEME_BDF2) {
+		if(b.scheme == QPDE_SCHEME_BDF2 || variable) {   // the variable stepper needs V^n after the solve, too
 			for(int i = 0; i < N; ++i) xp[(size_t)i * C] = x[(size_t)i * C];
 		}
 
@@ -212,6 +221,20 @@ k_interleaved_sweep(DeviceBatch b, InterleavedWork w, DeviceResult out) {
 		++n_steps;
 		time0 = time1; time1 = t;
 		ns.end_step();
+
+		if(variable && more) {
+			// dt *= target / (relativeError(iterand(0), iterand(1), scale) + epsilon), Stepper.hpp:68-82
+			double err = 0.;
+			for(int i = 0; i < N; ++i) {
+				const double a = x[(size_t)i * C], v = xp[(size_t)i * C];
+				const double fa = fabs(a), fb = fabs(v);
+				double dn = fa < fb ? fb : fa;
+				dn = b.variable_scale < dn ? dn : b.variable_scale;
+				const double e = fabs(a - v) / dn;
+				err = e > err ? e : err;
+			}
+			vdt *= vtarget / (err + DBL_EPSILON);
+		}
 
 		if(st.event_after) {
 			// Events at one time go in descending add() order (IterativeMethod.hpp:1340-1352)

@@ -20,6 +20,7 @@ struct DeviceBatch {
 	const double *sigma_nodes; long long sigma_nodes_stride;
 	const double *T, *dt;
 	int scheme, max_steps;
+	const double *variable_target; double variable_scale;
 	int n_exercise, exercise_kind;
 	int dividend_kind, dividend_first;
 	const double *dividend;

@@ -34,6 +34,7 @@ __host__ __device__ constexpr int ilog2_ceil(int n) { return n <= 1 ? 0 : 1 + il
 __device__ __forceinline__ double shfl_up(double v, int d) { return __shfl_up_sync(FULL_MASK, v, d); }
 __device__ __forceinline__ double shfl_down(double v, int d) { return __shfl_down_sync(FULL_MASK, v, d); }
 __device__ __forceinline__ double shfl_idx(double v, int l) { return __shfl_sync(FULL_MASK, v, l); }
+__device__ __forceinline__ double shfl_xor(double v, int m) { return __shfl_xor_sync(FULL_MASK, v, m); }
 
 // 1 / d for the factorisation: hardware seed (MUFU.RCP64H, ~2^-22) plus two
 // Newton steps => error below one ulp.  The factors need no more: any

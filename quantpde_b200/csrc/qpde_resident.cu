@@ -51,12 +51,14 @@ struct Smem {
 	PartitionSmem ps;   // hand-over between the warps of the partition solve
 	// the scalar "tail" equation (row N-1 when N = P M + 1); touched only by
 	// its owner, the last thread
-	struct Tail { double S, di, x, pz, bd, me, lb, invb, pq, vprev, c; } tail;
+	struct Tail { double S, di, x, pz, bd, me, lb, invb, pq, vprev, c, vn; } tail;
 	unsigned flags[2];
+	double red[PS_MAX_WARPS];   // max-reduction of the variable stepper's relativeError
 };
 
-inline size_t smem_bytes(int M, int P) {
-	return sizeof(Smem) + sizeof(double) * ((size_t)N_ROW_ARRAYS * M * P + 2 * (P + 1));
+// `variable`: one more row array, V^n of the running step (ReverseVariableStepper)
+inline size_t smem_bytes(int M, int P, bool variable = false) {
+	return sizeof(Smem) + sizeof(double) * ((size_t)(N_ROW_ARRAYS + (variable ? 1 : 0)) * M * P + 2 * (P + 1));
 }
 
 // relativeError's per-element test  |a-b| / max(scale,|a|,|b|) > tol
@@ -96,12 +98,17 @@ enum { MODE_LINEAR = 0, MODE_PENALTY = 1, MODE_POLICY = 2 };
 // MODE_PENALTY: root = MinPenaltyMethodDifference1 under a ToleranceIteration
 // MODE_POLICY : discretisation over Min/MaxPolicyIteration1_1 (two control
 //               values of the interest rate) under a ToleranceIteration
-template <int M, int PT, int MODE, bool BDF2, bool EVENTS>
+// EXTRA: what the time loop carries besides the steps — user events, or the variable stepper
+// (mutually exclusive at the boundary); compile-time so that the plain sweep pays for neither
+enum { EXTRA_NONE = 0, EXTRA_EVENTS = 1, EXTRA_VARIABLE = 2 };
+
+template <int M, int PT, int MODE, bool BDF2, int EXTRA>
 __global__ void __launch_bounds__(PT, 1)
 k_resident_sweep(DeviceBatch b, DeviceResult out) {
 	constexpr bool AMERICAN = MODE == MODE_PENALTY;
 	constexpr bool POLICY = MODE == MODE_POLICY;
 	constexpr bool ITERATE = MODE != MODE_LINEAR;
+	constexpr bool EVENTS = EXTRA == EXTRA_EVENTS, VARIABLE = EXTRA == EXTRA_VARIABLE;
 	constexpr int P = PT;                    // blockDim.x == PT
 	extern __shared__ __align__(16) unsigned char smem_raw[];
 	Smem &sm = *reinterpret_cast<Smem *>(smem_raw);
@@ -132,6 +139,7 @@ k_resident_sweep(DeviceBatch b, DeviceResult out) {
 	double *const sm_lb = sm_nc + MP;  // right-hand side of the discretisation node (without penalty terms)
 	double *const sm_xlast = sm_lb + MP;        // [P + 1]: x of each thread's last row, shifted by one
 	double *const sm_xfirst = sm_xlast + P + 1; // [P + 1]: x of each thread's first row
+	double *const sm_vn = sm_xfirst + P + 1;    // [MP], variable steps only: V^n of the running step
 
 	const double K = b.strike[cidx];
 
@@ -267,6 +275,11 @@ k_resident_sweep(DeviceBatch b, DeviceResult out) {
 	// ------------------------------------------------------------------
 	Replay rp; rp.start(b.T[cidx], b.dt[cidx], b.n_exercise);
 	NodeState ns; ns.start(b.scheme);
+	// ReverseVariableStepper (Core/Stepper.hpp:60-126): dt of the next step from the
+	// relative change over the last one
+	constexpr bool variable = VARIABLE;
+	const double vtarget = variable ? b.variable_target[cidx] : 0.;
+	double vdt = b.dt[cidx];
 	double time1 = rp.T, time0 = rp.T;
 	int cur_kind = -1; double cur_h = 0.;
 	int n_steps = 0, inner_total = 0, status = 0;
@@ -276,6 +289,10 @@ k_resident_sweep(DeviceBatch b, DeviceResult out) {
 
 	while(more) {
 		qpde_step st;
+		if(variable) {
+			if(n_steps >= b.max_steps) { status = 3; break; }      // output capacity
+			rp.dt_const = vdt;                                      // VariableStepper::timestep()
+		}
 		more = rp.next(st);
 		const double t = st.t;
 		const int kind = ns.kind();
@@ -354,6 +371,11 @@ k_resident_sweep(DeviceBatch b, DeviceResult out) {
 #pragma unroll
 			for(int j = 0; j < M; ++j) vprev[j] = x[j];
 			if(tail_owner) sm.tail.vprev = sm.tail.x;
+		}
+		if(variable) {
+#pragma unroll
+			for(int j = 0; j < M; ++j) sm_vn[j * P + tid] = x[j];
+			if(tail_owner) sm.tail.vn = sm.tail.x;
 		}
 
 		int its = 0;
@@ -471,6 +493,35 @@ k_resident_sweep(DeviceBatch b, DeviceResult out) {
 		++n_steps;
 		time0 = time1; time1 = t;
 		ns.end_step();
+
+		if(variable && more) {
+			// dt *= target / (relativeError(iterand(0), iterand(1), scale) + epsilon), Stepper.hpp:68-82;
+			// relativeError = max_i |a - b| / max(scale, |a|, |b|), IterativeMethod.hpp:1125-1137
+			double err = 0.;
+#pragma unroll
+			for(int j = 0; j < M; ++j) {
+				const double vn = sm_vn[j * P + tid];
+				const double fa = fabs(x[j]), fb = fabs(vn);
+				double dn = fa < fb ? fb : fa;
+				dn = b.variable_scale < dn ? dn : b.variable_scale;
+				const double e = i0 + j < n_main ? fabs(x[j] - vn) / dn : 0.;
+				err = e > err ? e : err;
+			}
+			{   // the tail row: formed by every thread (no branch in front of the shuffles), used by its owner
+				const double fa = fabs(sm.tail.x), fb = fabs(sm.tail.vn);
+				double dn = fa < fb ? fb : fa;
+				dn = b.variable_scale < dn ? dn : b.variable_scale;
+				const double e = fabs(sm.tail.x - sm.tail.vn) / dn;
+				err = tail_owner && e > err ? e : err;
+			}
+#pragma unroll
+			for(int dl = 16; dl >= 1; dl >>= 1) { const double o = shfl_xor(err, dl); err = o > err ? o : err; }
+			if(lane == 0) sm.red[warp] = err;
+			__syncthreads();
+			err = 0.;
+			for(int wv = 0; wv < P / 32; ++wv) err = sm.red[wv] > err ? sm.red[wv] : err;
+			vdt *= vtarget / (err + DBL_EPSILON);
+		}
 
 		if(st.event_after) {
 			if(EVENTS && st.user_events > 0) {
@@ -613,36 +664,51 @@ bool resident_supported(const DeviceBatch &b) {
 	if(!pick_geometry(b.N, &M, &PT)) return false;
 	if(b.american && b.n_exercise > 0) return false; // penalty + events: INTERLEAVED family
 	if(b.n_controls != 0 && b.n_controls != 2) return false; // more control values: INTERLEAVED family
+	if(b.variable_target && !((M == 8 && PT == 64) || (M == 8 && PT == 256))) return false; // no room for V^n: INTERLEAVED family
 	return true;
 }
 
-template <int M, int PT, int MODE, bool BDF2, bool EVENTS>
+template <int M, int PT, int MODE, bool BDF2, int EXTRA>
 static int launch_variant(const DeviceBatch &b, const DeviceResult &out, cudaStream_t stream) {
-	auto kern = k_resident_sweep<M, PT, MODE, BDF2, EVENTS>;
+	auto kern = k_resident_sweep<M, PT, MODE, BDF2, EXTRA>;
 	static bool configured = false;
+	constexpr bool VARIABLE = EXTRA == EXTRA_VARIABLE;        // one more row array: V^n
 	if(!configured) {
 		if(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
-				(int)smem_bytes(M, PT)) != cudaSuccess) {
+				(int)smem_bytes(M, PT, VARIABLE)) != cudaSuccess) {
 			return QPDE_ERR_CUDA;
 		}
 		configured = true;
 	}
-	kern<<<b.C, PT, smem_bytes(M, PT), stream>>>(b, out);
+	kern<<<b.C, PT, smem_bytes(M, PT, VARIABLE), stream>>>(b, out);
 	return QPDE_OK;
 }
 
-template <int M, int PT>
+template <int M, int PT, int EXTRA>
+static int launch_extra(const DeviceBatch &b, const DeviceResult &out, cudaStream_t stream) {
+	const bool bdf2 = b.scheme == QPDE_SCHEME_BDF2;
+	if(b.n_controls > 0) return bdf2 ? launch_variant<M, PT, MODE_POLICY, true, EXTRA>(b, out, stream)
+	                                 : launch_variant<M, PT, MODE_POLICY, false, EXTRA>(b, out, stream);
+	if(b.american) return bdf2 ? launch_variant<M, PT, MODE_PENALTY, true, EXTRA>(b, out, stream)
+	                           : launch_variant<M, PT, MODE_PENALTY, false, EXTRA>(b, out, stream);
+	return bdf2 ? launch_variant<M, PT, MODE_LINEAR, true, EXTRA>(b, out, stream)
+	            : launch_variant<M, PT, MODE_LINEAR, false, EXTRA>(b, out, stream);
+}
+
+// VARIABLE_OK: the geometry has room for the variable stepper's V^n array (and is worth the
+// extra instantiations)
+template <int M, int PT, bool VARIABLE_OK>
 static int launch_rows(const DeviceBatch &b, const DeviceResult &out, cudaStream_t stream) {
 	const bool bdf2 = b.scheme == QPDE_SCHEME_BDF2;
-	const bool events = b.n_exercise > 0;
-	if(b.n_controls > 0) return bdf2 ? launch_variant<M, PT, MODE_POLICY, true, false>(b, out, stream)
-	                                 : launch_variant<M, PT, MODE_POLICY, false, false>(b, out, stream);
-	if(b.american) return bdf2 ? launch_variant<M, PT, MODE_PENALTY, true, false>(b, out, stream)
-	                           : launch_variant<M, PT, MODE_PENALTY, false, false>(b, out, stream);
-	if(events)     return bdf2 ? launch_variant<M, PT, MODE_LINEAR, true, true>(b, out, stream)
-	                           : launch_variant<M, PT, MODE_LINEAR, false, true>(b, out, stream);
-	return bdf2 ? launch_variant<M, PT, MODE_LINEAR, true, false>(b, out, stream)
-	            : launch_variant<M, PT, MODE_LINEAR, false, false>(b, out, stream);
+	if(b.variable_target) {
+		if(VARIABLE_OK) return launch_extra<M, PT, VARIABLE_OK ? EXTRA_VARIABLE : EXTRA_NONE>(b, out, stream);
+		return QPDE_ERR_UNSUPPORTED;
+	}
+	if(b.n_exercise > 0) {      // events: linear sweeps only (penalty + events: INTERLEAVED family)
+		return bdf2 ? launch_variant<M, PT, MODE_LINEAR, true, EXTRA_EVENTS>(b, out, stream)
+		            : launch_variant<M, PT, MODE_LINEAR, false, EXTRA_EVENTS>(b, out, stream);
+	}
+	return launch_extra<M, PT, EXTRA_NONE>(b, out, stream);
 }
 
 int launch_resident(const DeviceBatch &b, const DeviceResult &out, cudaStream_t stream,
@@ -651,10 +717,10 @@ int launch_resident(const DeviceBatch &b, const DeviceResult &out, cudaStream_t 
 	int M = 0, PT = 0;
 	if(!resident_supported(b) || !pick_geometry(b.N, &M, &PT)) return QPDE_ERR_UNSUPPORTED;
 	int rc;
-	if(M == 8 && PT == 64)       rc = launch_rows<8, 64>(b, out, stream);
-	else if(M == 8 && PT == 256) rc = launch_rows<8, 256>(b, out, stream);
-	else if(M == 4 && PT == 512) rc = launch_rows<4, 512>(b, out, stream);
-	else                         rc = launch_rows<9, 256>(b, out, stream);
+	if(M == 8 && PT == 64)       rc = launch_rows<8, 64, true>(b, out, stream);
+	else if(M == 8 && PT == 256) rc = launch_rows<8, 256, true>(b, out, stream);
+	else if(M == 4 && PT == 512) rc = launch_rows<4, 512, false>(b, out, stream);
+	else                         rc = launch_rows<9, 256, false>(b, out, stream);
 	if(rc == QPDE_OK) *launches += 1;
 	return rc;
 }

@@ -398,10 +398,13 @@ class ReverseConstantStepper : public Iteration {
 	Payoff exercise;
 	Dividend dividend_;
 	bool dividendAddedFirst;
+protected:
+	Real vTarget, vScale;      // > 0: ReverseVariableStepper
+	int stepLimit_;
 public:
 	ReverseConstantStepper(Real startTime, Real endTime, Real dt)
 			: t0(startTime), T(endTime), dt(dt), inner(nullptr), nExercise(0), nDividend(0),
-			  dividendAddedFirst(false) {
+			  dividendAddedFirst(false), vTarget(0.), vScale(1.), stepLimit_(0) {
 		if(startTime != 0.) throw std::invalid_argument("QuantPDE_B200: startTime must be 0");
 	}
 	void setInnerIteration(ToleranceIteration &it) { inner = &it; }   // IterativeMethod.hpp:977
@@ -423,6 +426,9 @@ public:
 	Real timestep() const { return dt; }
 	int exerciseDates() const { return nExercise; }
 	const Payoff &exercisePayoff() const { return exercise; }
+	Real variableTarget() const { return vTarget; }
+	Real variableScale() const { return vScale; }
+	int stepLimit() const { return stepLimit_ > 0 ? stepLimit_ : 16 * (int)std::ceil(T / dt) + 64; }
 	int eventDates() const { return nExercise > 0 ? nExercise : nDividend; }
 	const Dividend &dividend() const { return dividend_; }
 	bool hasDividends() const { return nDividend > 0 && dividend_.kind != QPDE_DIVIDEND_NONE; }
@@ -434,6 +440,20 @@ public:
 	inline Solution solve(const RectilinearGrid1 &grid, const Payoff &payoff, IterationNode &root,
 			B200Solver &solver);
 	friend class Batch;
+};
+
+// ReverseVariableStepper(t0, T, dt, target, scale) — Core/Stepper.hpp:60-126: dt is the first
+// step; afterwards dt *= target / (relativeError(V^{n+1}, V^n, scale) + epsilon).  The number
+// of steps is data dependent: setStepLimit bounds it (iterations()[0] reports what was taken;
+// solve() throws if the limit was hit).
+class ReverseVariableStepper : public ReverseConstantStepper {
+public:
+	ReverseVariableStepper(Real startTime, Real endTime, Real dt, Real target, Real scale_ = scale)
+			: ReverseConstantStepper(startTime, endTime, dt) {
+		if(!(target > 0.) || !(scale_ > 0.)) throw std::invalid_argument("QuantPDE_B200: target and scale must be > 0");
+		vTarget = target; vScale = scale_;
+	}
+	void setStepLimit(int limit) { stepLimit_ = limit; }
 };
 
 ////////////////////////////////////////////////////////////////////////////////
@@ -468,6 +488,8 @@ public:
 		const int refine = items[0].grid->refinement();
 		const bool american = p0 != nullptr;
 		const int nEx = items[0].stepper->exerciseDates(), nEv = items[0].stepper->eventDates();
+		const bool variableSteps = items[0].stepper->variableTarget() > 0.;
+		std::vector<Real> vTargets;
 		const bool dividends = items[0].stepper->hasDividends();
 		const int divKind = items[0].stepper->dividend().kind;
 		const bool divFirst = items[0].stepper->dividendFirstInSweep();
@@ -491,6 +513,8 @@ public:
 					|| d->scheme != d0->scheme || (p != nullptr) != american
 					|| it.stepper->exerciseDates() != nEx || it.stepper->eventDates() != nEv
 					|| it.stepper->hasDividends() != dividends
+					|| (it.stepper->variableTarget() > 0.) != variableSteps
+					|| (variableSteps && it.stepper->variableScale() != items[0].stepper->variableScale())
 					|| (dividends && (it.stepper->dividend().kind != divKind || it.stepper->dividendFirstInSweep() != divFirst))
 					|| d->op.v.model() != volModel
 					|| it.payoff.kind() != payKind || (american && p->obstacle.kind() != obsKind)
@@ -505,6 +529,7 @@ public:
 			if(policy) controls.insert(controls.end(), d->policy->controls.begin(), d->policy->controls.end());
 			T[c] = it.stepper->expiry(); dt[c] = it.stepper->timestep();
 			if(dividends) divAmount.push_back(it.stepper->dividend().amount);
+			if(variableSteps) vTargets.push_back(it.stepper->variableTarget());
 			K[c] = it.payoff.kind() != QPDE_PAYOFF_ARRAY ? it.payoff.strike()
 				: (american && p->obstacle.kind() != QPDE_PAYOFF_ARRAY ? p->obstacle.strike()
 				: (nEx > 0 ? it.stepper->exercisePayoff().strike() : 0.));
@@ -549,8 +574,12 @@ public:
 
 		int maxSteps = 0;
 		for(int c = 0; c < C; ++c) {
-			const int bound = (int)std::floor(T[c] / dt[c]) + 3 + 2 * nEx;
+			const int bound = variableSteps ? items[c].stepper->stepLimit() : (int)std::floor(T[c] / dt[c]) + 3 + 2 * nEv;
 			if(bound > maxSteps) maxSteps = bound;
+		}
+		if(variableSteps) {
+			b.variable_target = vTargets.data(); b.variable_scale = items[0].stepper->variableScale();
+			b.max_steps = maxSteps;
 		}
 		std::vector<Real> V((size_t)C * N), S((size_t)C * N);
 		std::vector<int32_t> nSteps(C), status(C);
@@ -565,6 +594,10 @@ public:
 		std::vector<Solution> out;
 		for(int c = 0; c < C; ++c) {
 			const Item &it = items[c];
+			if(status[c] == 3) {
+				throw std::runtime_error("QuantPDE_B200: contract " + std::to_string(c)
+					+ " needs more time steps than ReverseVariableStepper::setStepLimit allows");
+			}
 			if(status[c] != 0) {
 				throw std::runtime_error("QuantPDE_B200: the penalty iteration of contract "
 					+ std::to_string(c) + " hit ToleranceIteration::maxIterations (the reference would not terminate)");

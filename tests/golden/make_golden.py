@@ -39,6 +39,18 @@ for sch in ("bdf2", "rannacher", "bdf1", "cn"):
         CASES.append(("bermudan_%s_k%d" % (sch, k), "bermudan",
                       dict(steps=100 * 2 ** k, refine=k, scheme=sch, K=100.0, r=0.04, alpha=20.0, T=1.0, E=10)))
 
+# ReverseVariableStepper (Core/Stepper.hpp:60-126) as examples/vanilla_options.cpp:52-58 builds it:
+# dt0 = T / steps, target = 1 / factor
+for name, kw in (("variable_american_k1", dict(american=1, steps=48, refine=1, variable_target=0.25)),
+                 ("variable_american_k2", dict(american=1, steps=192, refine=2, variable_target=1.0 / 16)),
+                 ("variable_american_k3", dict(american=1, steps=768, refine=3, variable_target=1.0 / 64)),
+                 ("variable_european_k2", dict(american=0, steps=48, refine=2, variable_target=0.25)),
+                 ("variable_american_bdf2", dict(american=1, steps=40, refine=1, variable_target=0.3, scheme="bdf2")),
+                 ("variable_european_cn", dict(american=0, steps=40, refine=1, variable_target=0.3, scheme="cn")),
+                 ("variable_american_bdf1", dict(american=1, steps=40, refine=2, variable_target=0.2, scheme="bdf1"))):
+    kw.update(K=100.0, r=0.04, vol=0.2, T=1.0)
+    CASES.append((name, "vanilla", kw))
+
 # README.md:357-375: discrete dividends at the event times (general interpolating events,
 # Event.hpp:100-112); dividend_first = which transform the reverse sweep applies first
 CASES.append(("dividend_cash_bdf2_k1", "bermudan",

@@ -47,7 +47,8 @@ def run_oracle_case(po, mode, kw):
     if mode == "vanilla":
         return po.american_put(kw["K"], kw["r"], kw["vol"], kw["T"], kw["steps"], kw["refine"],
                                q=kw.get("q", 0.0), call=bool(kw.get("call", 0)),
-                               american=bool(kw["american"]), scheme=kw.get("scheme", "rannacher"))
+                               american=bool(kw["american"]), scheme=kw.get("scheme", "rannacher"),
+                               variable_target=kw.get("variable_target"))
     if mode == "jump":
         return po.jump_call(kw["K"], kw["r"], kw["vol"], kw["T"], kw["lambda"], kw["steps"], kw["refine"],
                             density=kw["density"], params=jump_params(kw), scheme=kw.get("scheme", "bdf1"))
@@ -70,7 +71,8 @@ def spec_for_case(qpde, po, mode, kw, kernel="auto", copies=1):
             axis=np.tile(axis, (copies, 1)), refine=kw["refine"], r=kw["r"], sigma=kw["vol"],
             q=kw.get("q", 0.0), T=kw["T"], dt=kw["T"] / kw["steps"], strike=np.full(copies, K),
             scheme=kw.get("scheme", "rannacher"), american=bool(kw["american"]),
-            payoff="call" if call else "put", kernel=kernel)
+            payoff="call" if call else "put", kernel=kernel,
+            variable_target=kw.get("variable_target"), max_steps=4000 if "variable_target" in kw else 0)
     if mode == "jump":
         K = kw["K"]
         sp = po.special_axis()

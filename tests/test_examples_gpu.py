@@ -50,3 +50,17 @@ def test_vanilla_options_example_table(examples, golden):
         assert int(float(cols[0])) == len(golden[name + "/S"])
         assert int(float(cols[1])) == int(golden[name + "/steps"])
         assert rel_err(float(cols[3]), float(golden[name + "/value"])) <= 1e-6   # printed with 6 digits
+
+
+def test_vanilla_options_example_variable_timestepping(examples, golden):
+    """use_variable_timestepping of vanilla_options.cpp:52-58 through ReverseVariableStepper."""
+    out = subprocess.run([os.path.join(examples, "vanilla_options_b200"), "k0=1", "kn=3", "variable=1"], check=True,
+                         capture_output=True, text=True)
+    rows = out.stdout.strip().splitlines()[1:]
+    assert len(rows) == 3
+    for k, row in zip((1, 2, 3), rows):
+        cols = row.split()
+        name = "variable_american_k%d" % k
+        assert int(float(cols[0])) == len(golden[name + "/S"])
+        assert int(float(cols[1])) == int(golden[name + "/steps"])
+        assert rel_err(float(cols[3]), float(golden[name + "/value"])) <= 1e-6   # printed with 6 digits

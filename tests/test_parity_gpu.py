@@ -55,7 +55,7 @@ def test_golden_cases(qpde, handle, oracle, golden, kernel):
                                           case_obstacle(kw, S_ref))
                 assert hard == 0, name
             assert rel_err(res.value[c], float(golden[name + "/value"])) <= REL_TOL
-    assert ran >= (33 if kernel == "interleaved" else 35)
+    assert ran >= (40 if kernel == "interleaved" else 42)
 
 
 @pytest.mark.parametrize("kernel", KERNELS)
