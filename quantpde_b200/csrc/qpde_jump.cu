@@ -37,11 +37,15 @@ struct JumpSmem {
 	struct Tail { double S, di, x, bd, invb, vprev, c, h; } tail;
 };
 
+// padded sizes of the complex work buffer and of the twiddle table (pad_buf, pad_tw below)
+inline int pad_buf_size(int NF) { return NF + (NF >> 3) + 1; }
+inline int pad_tw_size(int NF) { const int h = NF / 2; return h + (h >> 3) + (h >> 6) + (h >> 9) + 1; }
+
 inline size_t jump_smem_bytes(int M, int P, int NF) {
 	// row arrays [M][P] (+1 slot of V for the tail node), complex work buffer
 	// [NF], twiddles [NF / 2]
 	return sizeof(JumpSmem) + sizeof(double) * ((size_t)JUMP_ROW_ARRAYS * M * P + 2)
-		+ sizeof(double2) * ((size_t)NF + NF / 2);
+		+ sizeof(double2) * ((size_t)pad_buf_size(NF) + pad_tw_size(NF));
 }
 
 __device__ __forceinline__ double2 cmul(double2 a, double2 b) {
@@ -53,39 +57,73 @@ __device__ __forceinline__ double2 cmul(double2 a, double2 b) {
 // kernel exp(-2 pi i jk / NF).  inverse = decimation in frequency: input
 // natural, output bit-reversed, kernel exp(+2 pi i jk / NF), unscaled.
 // tw[k] = exp(-2 pi i k / NF), k < NF / 2.  Ends with a barrier.
+//
+// Three consecutive radix-2 stages are fused into one pass: a thread loads the
+// 2^3 points that these stages connect (stride 2^s0), runs the butterflies in
+// registers — the very operations of the one-stage-per-barrier form, in the same
+// order, so the result is bit-identical to it — and stores them back: a third of
+// the shared-memory traffic and of the barriers.  Both arrays are padded against
+// bank conflicts (16-byte elements: a quarter-warp must hit 8 distinct 4-bank
+// groups): the data by one element per 8 (the stride-1 pass), the twiddles by
+// the base-8 digit sum of the index (8 threads read tw[j << t], j consecutive).
+__device__ __forceinline__ int pad_buf(int i) { return i + (i >> 3); }
+__device__ __forceinline__ int pad_tw(int k) { return k + (k >> 3) + (k >> 6) + (k >> 9); }
+
+template <int U, int PT, bool INVERSE>
+__device__ __forceinline__ void fft_pass(double2 *buf, const double2 *tw, int NF, int logNF, int s0, int tid) {
+	constexpr int R = 1 << U;
+	const int stride = 1 << s0;
+	for(int g = tid; g < (NF >> U); g += PT) {
+		const int low = g & (stride - 1);
+		const int base = ((g >> s0) << (s0 + U)) | low;
+		double2 v[R];
+#pragma unroll
+		for(int m = 0; m < R; ++m) v[m] = buf[pad_buf(base + m * stride)];
+#pragma unroll
+		for(int uu = 0; uu < U; ++uu) {
+			const int u = INVERSE ? U - 1 - uu : uu;      // DIF runs the stages downwards
+			const int half = 1 << u;
+			const int shift = logNF - 1 - (s0 + u);
+#pragma unroll
+			for(int m = 0; m < R; ++m) {
+				if(m & half) continue;
+				// the pair (i, i + 2^s) of stage s = s0 + u with i = base + m stride; k = i mod 2^s
+				const int k = low + (m & (half - 1)) * stride;
+				const double2 w = tw[pad_tw(k << shift)];
+				if(!INVERSE) {
+					const double2 a = v[m];
+					const double2 t = cmul(v[m + half], w);
+					v[m] = make_double2(a.x + t.x, a.y + t.y);
+					v[m + half] = make_double2(a.x - t.x, a.y - t.y);
+				} else {
+					const double2 a = v[m], c = v[m + half];
+					const double2 d = make_double2(a.x - c.x, a.y - c.y);
+					v[m] = make_double2(a.x + c.x, a.y + c.y);
+					v[m + half] = cmul(d, make_double2(w.x, -w.y));    // conjugate twiddle
+				}
+			}
+		}
+#pragma unroll
+		for(int m = 0; m < R; ++m) buf[pad_buf(base + m * stride)] = v[m];
+	}
+	__syncthreads();
+}
+
+template <int PT, bool INVERSE>
+__device__ __forceinline__ void fft_pass_any(double2 *buf, const double2 *tw, int NF, int logNF, int s0, int U, int tid) {
+	if(U == 3) fft_pass<3, PT, INVERSE>(buf, tw, NF, logNF, s0, tid);
+	else if(U == 2) fft_pass<2, PT, INVERSE>(buf, tw, NF, logNF, s0, tid);
+	else fft_pass<1, PT, INVERSE>(buf, tw, NF, logNF, s0, tid);
+}
+
 template <int PT>
 __device__ __forceinline__ void fft_forward_dit(double2 *buf, const double2 *tw, int NF, int logNF, int tid) {
-	for(int s = 0; s < logNF; ++s) {
-		const int half = 1 << s;
-		const int shift = logNF - 1 - s;          // twiddle stride = NF / (2 half)
-		for(int bfly = tid; bfly < NF / 2; bfly += PT) {
-			const int k = bfly & (half - 1);
-			const int i = ((bfly >> s) << (s + 1)) | k;
-			const double2 u = buf[i];
-			const double2 t = cmul(buf[i + half], tw[k << shift]);
-			buf[i] = make_double2(u.x + t.x, u.y + t.y);
-			buf[i + half] = make_double2(u.x - t.x, u.y - t.y);
-		}
-		__syncthreads();
-	}
+	for(int s0 = 0; s0 < logNF; s0 += 3) fft_pass_any<PT, false>(buf, tw, NF, logNF, s0, logNF - s0 < 3 ? logNF - s0 : 3, tid);
 }
 
 template <int PT>
 __device__ __forceinline__ void fft_inverse_dif(double2 *buf, const double2 *tw, int NF, int logNF, int tid) {
-	for(int s = logNF - 1; s >= 0; --s) {
-		const int half = 1 << s;
-		const int shift = logNF - 1 - s;
-		for(int bfly = tid; bfly < NF / 2; bfly += PT) {
-			const int k = bfly & (half - 1);
-			const int i = ((bfly >> s) << (s + 1)) | k;
-			const double2 u = buf[i], v = buf[i + half];
-			const double2 w = tw[k << shift];
-			const double2 d = make_double2(u.x - v.x, u.y - v.y);
-			buf[i] = make_double2(u.x + v.x, u.y + v.y);
-			buf[i + half] = cmul(d, make_double2(w.x, -w.y));    // conjugate twiddle
-		}
-		__syncthreads();
-	}
+	for(int s0 = 3 * ((logNF - 1) / 3); s0 >= 0; s0 -= 3) fft_pass_any<PT, true>(buf, tw, NF, logNF, s0, logNF - s0 < 3 ? logNF - s0 : 3, tid);
 }
 
 __device__ __forceinline__ int bitrev(int k, int logNF) { return (int)(__brev((unsigned)k) >> (32 - logNF)); }
@@ -131,7 +169,7 @@ k_jump_sweep(DeviceBatch b, JumpWork work, DeviceResult out) {
 	double *const sm_V  = sm_up + MP;             // [MP + 1]: current solution, node-addressable
 	double2 *const sm_buf = reinterpret_cast<double2 *>(sm_V + MP + 2);   // [NF]
 	const int NF = b.n_fft;
-	double2 *const sm_tw = sm_buf + NF;                                   // [NF / 2]
+	double2 *const sm_tw = sm_buf + (NF + (NF >> 3) + 1);                 // [NF / 2], padded (pad_tw)
 	const int logNF = 31 - __clz(NF);
 
 	const int cidx = blockIdx.x;
@@ -168,7 +206,7 @@ k_jump_sweep(DeviceBatch b, JumpWork work, DeviceResult out) {
 		for(int k = tid; k < NF / 2; k += P) {
 			double sn, cs;
 			sincospi(-2. * (double)k / (double)NF, &sn, &cs);
-			sm_tw[k] = make_double2(cs, sn);
+			sm_tw[pad_tw(k)] = make_double2(cs, sn);
 		}
 	}
 	__syncthreads();
@@ -211,11 +249,11 @@ k_jump_sweep(DeviceBatch b, JumpWork work, DeviceResult out) {
 		}
 		// (c) spectrum of the density weights (computeDensityFFT, :326-328)
 		const double *wts = b.jump_weights + (size_t)cidx * b.jump_weights_stride;
-		for(int k = tid; k < NF; k += P) sm_buf[bitrev(k, logNF)] = make_double2(wts[k], 0.);
+		for(int k = tid; k < NF; k += P) sm_buf[pad_buf(bitrev(k, logNF))] = make_double2(wts[k], 0.);
 	}
 	__syncthreads();
 	fft_forward_dit<PT>(sm_buf, sm_tw, NF, logNF, tid);
-	for(int k = tid; k < NF; k += P) fw[k] = sm_buf[k];
+	for(int k = tid; k < NF; k += P) fw[k] = sm_buf[pad_buf(k)];
 	__threadfence_block();
 	__syncthreads();
 
@@ -280,14 +318,14 @@ k_jump_sweep(DeviceBatch b, JumpWork work, DeviceResult out) {
 		for(int k = tid; k < NF; k += P) {
 			const int idx = g_idx[k];
 			const double vb = interp_apply(g_w[k], sm_V[at_node(idx)], sm_V[at_node(idx + 1)]);
-			sm_buf[bitrev(k, logNF)] = make_double2(vb, 0.);
+			sm_buf[pad_buf(bitrev(k, logNF))] = make_double2(vb, 0.);
 		}
 		__syncthreads();
 		// ---- (2) correlation: inv( fwd(Vbar) * conj(fwd(weights)) ) --------
 		fft_forward_dit<PT>(sm_buf, sm_tw, NF, logNF, tid);
 		for(int k = tid; k < NF; k += P) {
 			const double2 f = fw[k];
-			sm_buf[k] = cmul(sm_buf[k], make_double2(f.x, -f.y));
+			sm_buf[pad_buf(k)] = cmul(sm_buf[pad_buf(k)], make_double2(f.x, -f.y));
 		}
 		__syncthreads();
 		fft_inverse_dif<PT>(sm_buf, sm_tw, NF, logNF, tid);
@@ -301,8 +339,8 @@ k_jump_sweep(DeviceBatch b, JumpWork work, DeviceResult out) {
 			double bj = 0.;
 			if(i > 0 && i < N - 1 && i < n_main) {
 				const int idx = n_idx[i];
-				const double hA = sm_buf[bitrev(idx, logNF)].x * inv_nf;
-				const double hB = sm_buf[bitrev(idx + 1, logNF)].x * inv_nf;
+				const double hA = sm_buf[pad_buf(bitrev(idx, logNF))].x * inv_nf;
+				const double hB = sm_buf[pad_buf(bitrev(idx + 1, logNF))].x * inv_nf;
 				bj = lambda * interp_apply(n_w[i], hA, hB);
 			}
 			if(kind == STEP_IMPLICIT) r[j] = x[j] + h0 * bj;                                   // BDF.hpp:40-46
