@@ -19,8 +19,11 @@
 #include <math_constants.h>
 
 #include "qpde_kernels.cuh"
+#include "qpde_partition.cuh"   // rcp()
 
 namespace qpde {
+
+constexpr int ROWS = 8;   // rows whose loads are in flight together in the per-thread elimination loops
 
 // ---------------------------------------------------------------------------
 // Setup: refined grid, operator rows, initial condition, obstacles.
@@ -126,25 +129,40 @@ k_interleaved_sweep(DeviceBatch b, InterleavedWork w, DeviceResult out) {
 		// ---- lb = root.b(t) of the discretisation node ------------------
 		// x holds iterand(0) = V^n, xp holds iterand(1) for BDF2.
 		{
-			double vm = 0., vi = x[0], vp = N > 1 ? x[C] : 0.;
-			for(int i = 0; i < N; ++i) {
-				const size_t at = (size_t)i * C;
-				double val;
-				if(kind == STEP_IMPLICIT) {
-					val = vi + 0. * h0;
-				} else if(kind == STEP_BDF2) {
-					val = (div_by(c1 * vi - c0 * xp[at], den, rden) + 0.) * gb.h;
-				} else {
-					// (I - A h/2) v0, row-major SpMV from zero in column order
-					double acc = 0.;
-					if(i > 0) acc += (0. - gb.off(lo[at])) * vm;
-					acc += (1. - gb.off(di[at])) * vi;
-					if(i < N - 1) acc += (0. - gb.off(up[at])) * vp;
-					val = acc + 0.;
+			// blocks of ROWS rows with all loads issued first (see the elimination loop)
+			double vm = 0.;
+			for(int ib = 0; ib < N; ib += ROWS) {
+				double vx[ROWS + 1], vlo[ROWS], vdi[ROWS], vup[ROWS], vxp[ROWS];
+#pragma unroll
+				for(int u = 0; u < ROWS; ++u) {
+					const size_t at = (size_t)(ib + u < N ? ib + u : N - 1) * C;
+					vx[u] = x[at];
+					vxp[u] = kind == STEP_BDF2 ? xp[at] : 0.;
+					const bool cn = kind != STEP_IMPLICIT && kind != STEP_BDF2;
+					vlo[u] = cn ? lo[at] : 0.; vdi[u] = cn ? di[at] : 0.; vup[u] = cn ? up[at] : 0.;
 				}
-				lb[at] = val;
-				vm = vi; vi = vp;
-				vp = i + 2 < N ? x[at + 2 * C] : 0.;
+				vx[ROWS] = ib + ROWS < N ? x[(size_t)(ib + ROWS) * C] : 0.;
+#pragma unroll
+				for(int u = 0; u < ROWS; ++u) {
+					const int i = ib + u;
+					if(i >= N) break;
+					const double vi = vx[u], vp = i + 1 < N ? vx[u + 1] : 0.;
+					double val;
+					if(kind == STEP_IMPLICIT) {
+						val = vi + 0. * h0;
+					} else if(kind == STEP_BDF2) {
+						val = (div_by(c1 * vi - c0 * vxp[u], den, rden) + 0.) * gb.h;
+					} else {
+						// (I - A h/2) v0, row-major SpMV from zero in column order
+						double acc = 0.;
+						if(i > 0) acc += (0. - gb.off(vlo[u])) * vm;
+						acc += (1. - gb.off(vdi[u])) * vi;
+						if(i < N - 1) acc += (0. - gb.off(vup[u])) * vp;
+						val = acc + 0.;
+					}
+					lb[(size_t)i * C] = val;
+					vm = vi;
+				}
 			}
 		}
 		// history push: iterand(1) <- iterand(0).  For BDF2 the previous
@@ -158,56 +176,100 @@ k_interleaved_sweep(DeviceBatch b, InterleavedWork w, DeviceResult out) {
 		do {
 			// ---- forward elimination of (lA + P) x = lb + P obstacle ------
 			double cprev = 0., dprev = 0.;
-			double xm = 0., xi = x[0], xq = N > 1 ? x[C] : 0.;   // previous iterate around node i
-			for(int i = 0; i < N; ++i) {
-				const size_t at = (size_t)i * C;
-				size_t rows = at;
-				if(policy) {
-					// PolicyIteration::onIterationStart (PolicyIteration.hpp:54-105):
-					// candidate = (A(q) x - b(q))_i per control value, strict order
-					double best = b.policy_max ? -CUDART_INF : CUDART_INF;
-					for(int k = 0; k < b.n_controls; ++k) {
-						const size_t ak = (size_t)k * NC + at;
-						double acc = 0.;
-						if(i > 0 && i < N - 1) acc += lo[ak] * xm;
-						acc += di[ak] * xi;
-						if(i > 0 && i < N - 1) acc += up[ak] * xq;
-						const double cand = acc - 0.;
-						if(b.policy_max ? cand > best : cand < best) { best = cand; rows = ak; }
+			if(!policy) {
+				// Every thread walks its own contract: the rows form a serial chain, and a load per
+				// row would expose the full HBM latency 2 N times per solve.  The rows are taken in
+				// blocks of ROWS: all loads of a block are issued first, then the chain runs on registers.
+				for(int ib = 0; ib < N; ib += ROWS) {
+					double vlo[ROWS], vdi[ROWS], vup[ROWS], vlb[ROWS], vob[ROWS], vx[ROWS];
+#pragma unroll
+					for(int u = 0; u < ROWS; ++u) {
+						const size_t at = (size_t)(ib + u < N ? ib + u : N - 1) * C;
+						vlo[u] = lo[at]; vdi[u] = di[at]; vup[u] = up[at]; vlb[u] = lb[at];
+						vob[u] = b.american ? ob[at] : 0.; vx[u] = b.american ? x[at] : 0.;
 					}
-					xm = xi; xi = xq;
-					xq = i + 2 < N ? x[at + 2 * C] : 0.;
+#pragma unroll
+					for(int u = 0; u < ROWS; ++u) {
+						if(ib + u >= N) break;
+						const size_t at = (size_t)(ib + u) * C;
+						double a_i = gA.off(vlo[u]);
+						double b_i = 1. + gA.off(vdi[u]);
+						double c_i = gA.off(vup[u]);
+						double rhs = vlb[u];
+						if(b.american) {
+							// PenaltyMethod.hpp:45,61-68: predicate on the previous iterand
+							// (scale * (x - payoff)) < 0  <=>  x < payoff
+							if(vx[u] < vob[u]) { b_i = b_i + pen * 1.; rhs = rhs + pen * vob[u]; }
+						}
+						const double denom = b_i - a_i * cprev;
+						const double inv = rcp(denom);        // < 1 ulp; no division sequence on the serial chain
+						cprev = c_i * inv;
+						dprev = (rhs - a_i * dprev) * inv;
+						cp[at] = cprev; dp[at] = dprev;
+					}
 				}
-				double a_i = gA.off(lo[rows]);
-				double b_i = 1. + gA.off(di[rows]);
-				double c_i = gA.off(up[rows]);
-				double rhs = lb[at];
-				if(b.american) {
-					// PenaltyMethod.hpp:45,61-68: predicate on the previous iterand
-					// (scale * (x - payoff)) < 0  <=>  x < payoff
-					const double obi = ob[at];
-					if(x[at] < obi) { b_i = b_i + pen * 1.; rhs = rhs + pen * obi; }
+			} else {
+				double xm = 0., xi = x[0], xq = N > 1 ? x[C] : 0.;   // previous iterate around node i
+				for(int i = 0; i < N; ++i) {
+					const size_t at = (size_t)i * C;
+					size_t rows = at;
+					if(policy) {
+						// PolicyIteration::onIterationStart (PolicyIteration.hpp:54-105):
+						// candidate = (A(q) x - b(q))_i per control value, strict order
+						double best = b.policy_max ? -CUDART_INF : CUDART_INF;
+						for(int k = 0; k < b.n_controls; ++k) {
+							const size_t ak = (size_t)k * NC + at;
+							double acc = 0.;
+							if(i > 0 && i < N - 1) acc += lo[ak] * xm;
+							acc += di[ak] * xi;
+							if(i > 0 && i < N - 1) acc += up[ak] * xq;
+							const double cand = acc - 0.;
+							if(b.policy_max ? cand > best : cand < best) { best = cand; rows = ak; }
+						}
+						xm = xi; xi = xq;
+						xq = i + 2 < N ? x[at + 2 * C] : 0.;
+					}
+					double a_i = gA.off(lo[rows]);
+					double b_i = 1. + gA.off(di[rows]);
+					double c_i = gA.off(up[rows]);
+					double rhs = lb[at];
+					if(b.american) {
+						// PenaltyMethod.hpp:45,61-68: predicate on the previous iterand
+						// (scale * (x - payoff)) < 0  <=>  x < payoff
+						const double obi = ob[at];
+						if(x[at] < obi) { b_i = b_i + pen * 1.; rhs = rhs + pen * obi; }
+					}
+					const double denom = b_i - a_i * cprev;
+					const double inv = 1. / denom;
+					cprev = c_i * inv;
+					dprev = (rhs - a_i * dprev) * inv;
+					cp[at] = cprev; dp[at] = dprev;
 				}
-				const double denom = b_i - a_i * cprev;
-				const double inv = 1. / denom;
-				cprev = c_i * inv;
-				dprev = (rhs - a_i * dprev) * inv;
-				cp[at] = cprev; dp[at] = dprev;
 			}
 			// ---- back substitution + relativeError --------------------------
 			double xn = 0.;
 			bool notdone = false;
-			for(int i = N - 1; i >= 0; --i) {
-				const size_t at = (size_t)i * C;
-				xn = dp[at] - cp[at] * xn;
-				if(iterate) {
-					const double xo = x[at];
-					const double fa = fabs(xn), fb = fabs(xo);
-					double d = fa < fb ? fb : fa;
-					d = scale < d ? d : scale;
-					if(fabs(xn - xo) / d > tol) notdone = true;  // IterativeMethod.hpp:1131-1135
+			for(int ib = N - 1; ib >= 0; ib -= ROWS) {
+				double vcp[ROWS], vdp[ROWS], vxo[ROWS];
+#pragma unroll
+				for(int u = 0; u < ROWS; ++u) {
+					const size_t at = (size_t)(ib - u >= 0 ? ib - u : 0) * C;
+					vcp[u] = cp[at]; vdp[u] = dp[at]; vxo[u] = iterate ? x[at] : 0.;
 				}
-				x[at] = xn;
+#pragma unroll
+				for(int u = 0; u < ROWS; ++u) {
+					if(ib - u < 0) break;
+					const size_t at = (size_t)(ib - u) * C;
+					xn = vdp[u] - vcp[u] * xn;
+					if(iterate) {
+						const double xo = vxo[u];
+						const double fa = fabs(xn), fb = fabs(xo);
+						double d = fa < fb ? fb : fa;
+						d = scale < d ? d : scale;
+						if(fabs(xn - xo) / d > tol) notdone = true;  // IterativeMethod.hpp:1131-1135
+					}
+					x[at] = xn;
+				}
 			}
 			++its;
 			again = iterate && notdone;
@@ -322,7 +384,8 @@ k_interleaved_sweep(DeviceBatch b, InterleavedWork w, DeviceResult out) {
 
 void launch_interleaved(const DeviceBatch &b, const InterleavedWork &w,
 		const DeviceResult &out, cudaStream_t stream, long long *launches) {
-	const int threads = 128;
+	// small CTAs: a batch of a few thousand contracts still reaches every SM
+	const int threads = b.C >= 148 * 512 ? 128 : (b.C >= 148 * 128 ? 64 : 32);
 	const int blocks = (b.C + threads - 1) / threads;
 	k_interleaved_setup<<<blocks, threads, 0, stream>>>(b, w);
 	k_interleaved_sweep<<<blocks, threads, 0, stream>>>(b, w, out);

@@ -236,7 +236,8 @@ k_jump_sweep(DeviceBatch b, JumpWork work, DeviceResult out) {
 			const double c = exp(x0 + k * dxg);
 			int idx; double w;
 			interp_data(S_at, N, c, idx, w);
-			g_idx[k] = idx; g_w[k] = w;
+			g_idx[k] = at_node(idx) | (at_node(idx + 1) << 16);      // both shared-memory slots (< 2^16), no division per step
+			g_w[k] = w;
 		}
 		// (b) h at log S_i: PiecewiseLinear over Axis::uniform(x0, xf, NF) (:293-296, :441-452)
 		const double xf = log(S_at(N - 2));
@@ -245,7 +246,8 @@ k_jump_sweep(DeviceBatch b, JumpWork work, DeviceResult out) {
 		for(int i = tid; i < N; i += P) {
 			int idx = 0; double w = 1.;
 			if(i > 0 && i < N - 1) interp_data(tick, NF, log(S_at(i)), idx, w);
-			n_idx[i] = idx; n_w[i] = w;
+			n_idx[i] = pad_buf(bitrev(idx, logNF)) | (pad_buf(bitrev(idx + 1, logNF)) << 16);   // slots of h_idx, h_idx+1 in sm_buf
+			n_w[i] = i > 0 && i < N - 1 ? w : 0.;                     // rows 0 and N - 1 have b = 0
 		}
 		// (c) spectrum of the density weights (computeDensityFFT, :326-328)
 		const double *wts = b.jump_weights + (size_t)cidx * b.jump_weights_stride;
@@ -315,19 +317,42 @@ k_jump_sweep(DeviceBatch b, JumpWork work, DeviceResult out) {
 		for(int j = 0; j < M; ++j) sm_V[j * P + tid] = x[j];
 		if(tail_owner) sm_V[MP] = sm.tail.x;
 		__syncthreads();
-		for(int k = tid; k < NF; k += P) {
-			const int idx = g_idx[k];
-			const double vb = interp_apply(g_w[k], sm_V[at_node(idx)], sm_V[at_node(idx + 1)]);
-			sm_buf[pad_buf(bitrev(k, logNF))] = make_double2(vb, 0.);
+		// the table loads of four points are issued together (latency of L2, not of four round trips)
+		for(int k0 = tid; k0 < NF; k0 += 4 * P) {
+			int slots[4]; double wk[4];
+#pragma unroll
+			for(int u = 0; u < 4; ++u) {
+				const int k = k0 + u * P < NF ? k0 + u * P : k0;
+				slots[u] = g_idx[k]; wk[u] = g_w[k];
+			}
+#pragma unroll
+			for(int u = 0; u < 4; ++u) {
+				const int k = k0 + u * P;
+				const double vb = interp_apply(wk[u], sm_V[slots[u] & 0xffff], sm_V[slots[u] >> 16]);
+				if(k < NF) sm_buf[pad_buf(bitrev(k, logNF))] = make_double2(vb, 0.);
+			}
 		}
 		__syncthreads();
 		// ---- (2) correlation: inv( fwd(Vbar) * conj(fwd(weights)) ) --------
 		fft_forward_dit<PT>(sm_buf, sm_tw, NF, logNF, tid);
-		for(int k = tid; k < NF; k += P) {
-			const double2 f = fw[k];
-			sm_buf[pad_buf(k)] = cmul(sm_buf[pad_buf(k)], make_double2(f.x, -f.y));
+		for(int k0 = tid; k0 < NF; k0 += 4 * P) {
+			double2 f[4];
+#pragma unroll
+			for(int u = 0; u < 4; ++u) f[u] = fw[k0 + u * P < NF ? k0 + u * P : k0];
+#pragma unroll
+			for(int u = 0; u < 4; ++u) {
+				const int k = k0 + u * P;
+				if(k < NF) sm_buf[pad_buf(k)] = cmul(sm_buf[pad_buf(k)], make_double2(f[u].x, -f[u].y));
+			}
 		}
 		__syncthreads();
+		// the read-out table of step (3): loaded here so that the inverse transform hides the latency
+		int nslot[M]; double nw[M];
+#pragma unroll
+		for(int j = 0; j < M; ++j) {
+			const int i = i0 + j < N ? i0 + j : 0;
+			nslot[j] = n_idx[i]; nw[j] = n_w[i];
+		}
 		fft_inverse_dif<PT>(sm_buf, sm_tw, NF, logNF, tid);
 		// sm_buf[bitrev(k)].x / NF = h_k
 		const double inv_nf = 1. / (double)NF;
@@ -336,13 +361,11 @@ k_jump_sweep(DeviceBatch b, JumpWork work, DeviceResult out) {
 #pragma unroll
 		for(int j = 0; j < M; ++j) {
 			const int i = i0 + j;
-			double bj = 0.;
-			if(i > 0 && i < N - 1 && i < n_main) {
-				const int idx = n_idx[i];
-				const double hA = sm_buf[pad_buf(bitrev(idx, logNF))].x * inv_nf;
-				const double hB = sm_buf[pad_buf(bitrev(idx + 1, logNF))].x * inv_nf;
-				bj = lambda * interp_apply(n_w[i], hA, hB);
-			}
+			// no predicate across the loads: rows without a jump term have weight and slots 0
+			const int slots = nslot[j];
+			const double hA = sm_buf[slots & 0xffff].x * inv_nf;
+			const double hB = sm_buf[slots >> 16].x * inv_nf;
+			const double bj = i > 0 && i < N - 1 && i < n_main ? lambda * interp_apply(nw[j], hA, hB) : 0.;
 			if(kind == STEP_IMPLICIT) r[j] = x[j] + h0 * bj;                                   // BDF.hpp:40-46
 			else r[j] = (div_by(c1 * x[j] - c0 * vprev[BDF2 ? j : 0], den, rden) + bj) * g.h;             // BDF.hpp:94-110
 		}
