@@ -58,9 +58,24 @@ struct PartitionSmem {
 	double s_G7[PS_MAX_WARPS], s_G2l[PS_MAX_WARPS], s_P0[PS_MAX_WARPS], s_G2f[PS_MAX_WARPS];
 };
 
-template <int M, int PT>
+// The CTAs whose warps together hold ONE tridiagonal system: a single CTA, or the CL CTAs of
+// a thread-block cluster (each warp publishes its separator data in the shared memory of every
+// CTA of the cluster — distributed shared memory — and the barrier is the cluster's).
+template <int CL>
+struct PartitionTeam {
+	PartitionSmem *peer[CL];   // PartitionSmem of CTA q of the cluster, own included (generic pointers)
+	int rank;                  // this CTA
+};
+
+template <int CL>
+__device__ __forceinline__ void team_sync() {
+	if(CL == 1) __syncthreads();
+	else asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
+template <int M, int PT, int CL = 1>
 struct PartitionSolver {
-	static constexpr int W = PT / 32;
+	static constexpr int W = CL * (PT / 32);     // warps of the whole system
 	static constexpr int L3_STAGES = ilog2_ceil(W);
 	static constexpr int L3_ALLOC = L3_STAGES > 0 ? L3_STAGES : 1;
 	static_assert(W <= PS_MAX_WARPS && W <= 32, "too many warps");
@@ -86,6 +101,13 @@ struct PartitionSolver {
 	// (0, 1, 0).  Contains one __syncthreads().
 	__device__ __forceinline__ void factorize(const double (&aa)[M], const double (&bb)[M],
 			const double (&cc)[M], PartitionSmem &sm, int lane, int warp) {
+		PartitionTeam<1> team; team.peer[0] = &sm; team.rank = 0;
+		factorize(aa, bb, cc, team, lane, warp);
+	}
+	// `warp` is the index of this warp in the whole system (rank * PT / 32 + warp of the CTA)
+	__device__ __forceinline__ void factorize(const double (&aa)[M], const double (&bb)[M],
+			const double (&cc)[M], const PartitionTeam<CL> &team, int lane, int warp) {
+		PartitionSmem &sm = *team.peer[team.rank];
 		f_a0 = aa[0]; f_c0 = cc[0];
 		// level 1
 		f_invd[1] = rcp(bb[1]);
@@ -146,10 +168,14 @@ struct PartitionSolver {
 		f_V2 = V2 * f_invB2;
 		f_W2 = W2 * f_invB2;
 		// hand-over to level 3
-		if(lane == 31) { sm.f_Vs7[warp] = f_Vs[M - 1]; sm.f_Ws7[warp] = f_Ws[M - 1]; sm.f_V2l[warp] = f_V2; sm.f_W2l[warp] = f_W2; }
-		if(lane == 1)  { sm.f_V2f[warp] = f_V2; sm.f_W2f[warp] = f_W2; }
-		if(lane == 0)  { sm.f_a0[warp] = f_a0; sm.f_Bp[warp] = Bpart; sm.f_Ct[warp] = Ct; }
-		__syncthreads();
+#pragma unroll
+		for(int q = 0; q < CL; ++q) {
+			PartitionSmem &to = *team.peer[q];
+			if(lane == 31) { to.f_Vs7[warp] = f_Vs[M - 1]; to.f_Ws7[warp] = f_Ws[M - 1]; to.f_V2l[warp] = f_V2; to.f_W2l[warp] = f_W2; }
+			if(lane == 1)  { to.f_V2f[warp] = f_V2; to.f_W2f[warp] = f_W2; }
+			if(lane == 0)  { to.f_a0[warp] = f_a0; to.f_Bp[warp] = Bpart; to.f_Ct[warp] = Ct; }
+		}
+		team_sync<CL>();
 		// level 3: W x W tridiagonal over the warp separators, reduced by every
 		// warp redundantly across its lanes 0 .. W-1
 		double A3 = 0., B3 = 1., C3 = 0.;
@@ -192,6 +218,12 @@ struct PartitionSolver {
 	// __syncthreads().
 	__device__ __forceinline__ void solve(const double (&r)[M], double (&G)[M], double &x_next,
 			PartitionSmem &sm, int lane, int warp) const {
+		PartitionTeam<1> team; team.peer[0] = &sm; team.rank = 0;
+		solve(r, G, x_next, team, lane, warp);
+	}
+	__device__ __forceinline__ void solve(const double (&r)[M], double (&G)[M], double &x_next,
+			const PartitionTeam<CL> &team, int lane, int warp) const {
+		PartitionSmem &sm = *team.peer[team.rank];
 		// level 1: G = T^-1 r on the interior rows
 		G[1] = r[1];
 #pragma unroll
@@ -210,10 +242,14 @@ struct PartitionSolver {
 			R2 = fma(f_al[s], Rm, fma(f_ga[s], Rq, R2));   // al, ga are 0 where the partner is outside
 		}
 		const double G2 = R2 * f_invB2;
-		if(lane == 31) { sm.s_G7[warp] = G[M - 1]; sm.s_G2l[warp] = G2; }
-		if(lane == 1)  sm.s_G2f[warp] = G2;
-		if(lane == 0)  sm.s_P0[warp] = P0;
-		__syncthreads();
+#pragma unroll
+		for(int q = 0; q < CL; ++q) {
+			PartitionSmem &to = *team.peer[q];
+			if(lane == 31) { to.s_G7[warp] = G[M - 1]; to.s_G2l[warp] = G2; }
+			if(lane == 1)  to.s_G2f[warp] = G2;
+			if(lane == 0)  to.s_P0[warp] = P0;
+		}
+		team_sync<CL>();
 		// level 3 (lanes 0 .. W-1 of every warp)
 		double R3 = 0.;
 		if(lane < W) {

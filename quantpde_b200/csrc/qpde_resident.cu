@@ -34,7 +34,11 @@
 #include <cstring>
 
 #include "qpde_kernels.cuh"
+#include <cooperative_groups.h>
+
 #include "qpde_partition.cuh"
+
+namespace cg = cooperative_groups;
 
 namespace qpde {
 
@@ -102,7 +106,10 @@ enum { MODE_LINEAR = 0, MODE_PENALTY = 1, MODE_POLICY = 2 };
 // (mutually exclusive at the boundary); compile-time so that the plain sweep pays for neither
 enum { EXTRA_NONE = 0, EXTRA_EVENTS = 1, EXTRA_VARIABLE = 2 };
 
-template <int M, int PT, int MODE, bool BDF2, int EXTRA>
+// CL: CTAs per contract.  CL = 2 is a thread-block cluster: the two CTAs hold the lower and the
+// upper half of the rows (N up to 2 PT M + 1 = 4097), exchange the row at their boundary and the
+// warps' separator data through distributed shared memory, and every barrier is the cluster's.
+template <int M, int PT, int MODE, bool BDF2, int EXTRA, int CL>
 __global__ void __launch_bounds__(PT, 1)
 k_resident_sweep(DeviceBatch b, DeviceResult out) {
 	constexpr bool AMERICAN = MODE == MODE_PENALTY;
@@ -113,17 +120,19 @@ k_resident_sweep(DeviceBatch b, DeviceResult out) {
 	extern __shared__ __align__(16) unsigned char smem_raw[];
 	Smem &sm = *reinterpret_cast<Smem *>(smem_raw);
 
-	const int cidx = blockIdx.x;
+	const int cidx = blockIdx.x / CL;
+	const int rank = CL == 1 ? 0 : (int)(blockIdx.x % CL);      // == %cluster_ctarank for a 1-D cluster
 	const int tid = threadIdx.x;
-	const int lane = tid & 31, warp = tid >> 5;
+	const int lane = tid & 31, warp = rank * (PT / 32) + (tid >> 5);   // warp: index in the whole system
 	const int N = b.N;
 	// P M rows are available.  A grid of exactly P M + 1 nodes (2049 = 256 * 8 + 1)
 	// keeps its last row — diagonal-only in BlackScholes::A, BlackScholes.hpp:177-180 —
 	// as a scalar "tail" equation folded into row N-2 (last row of the last thread);
 	// smaller grids fit entirely and have no tail.
-	const bool has_tail = N == P * M + 1;
+	const bool has_tail = N == CL * P * M + 1;
 	const int n_main = has_tail ? N - 1 : N;
-	const int i0 = tid * M;
+	const int i0 = (rank * P + tid) * M;       // first row of this thread
+	const int row0 = rank * P * M;             // first row of this CTA
 	constexpr int MP = M * P;
 
 	double *const sm_S  = reinterpret_cast<double *>(smem_raw + sizeof(Smem));
@@ -142,21 +151,46 @@ k_resident_sweep(DeviceBatch b, DeviceResult out) {
 	double *const sm_vn = sm_xfirst + P + 1;    // [MP], variable steps only: V^n of the running step
 
 	const double K = b.strike[cidx];
+	const double *const axis = b.axis + (size_t)cidx * b.axis_stride;
+
+	// the other CTAs of the cluster: their Smem (solver hand-over, flags) and boundary slots
+	PartitionTeam<CL> team; team.rank = rank; team.peer[0] = &sm.ps;
+	Smem *peer_sm[CL]; peer_sm[0] = &sm;
+	double *xlast_of_next = nullptr, *xfirst_of_prev = nullptr;
+	if(CL > 1) {
+		cg::cluster_group cluster = cg::this_cluster();
+#pragma unroll
+		for(int q = 0; q < CL; ++q) { peer_sm[q] = cluster.map_shared_rank(&sm, q); team.peer[q] = &peer_sm[q]->ps; }
+		if(rank + 1 < CL) xlast_of_next = cluster.map_shared_rank(sm_xlast, rank + 1);
+		if(rank > 0) xfirst_of_prev = cluster.map_shared_rank(sm_xfirst, rank - 1);
+	}
+	// x of a thread's last / first row goes to the neighbour thread; across the CTA boundary
+	// the slot lives in the neighbour CTA's shared memory
+	auto publish_last = [&] (double v) {
+		sm_xlast[tid + 1] = v;
+		if(CL > 1 && tid == P - 1 && rank + 1 < CL) xlast_of_next[0] = v;
+	};
+	auto publish_first = [&] (double v) {
+		sm_xfirst[tid] = v;
+		if(CL > 1 && tid == 0 && rank > 0) xfirst_of_prev[P] = v;
+	};
 
 	// ------------------------------------------------------------------
 	// Setup: refined grid -> shared memory, operator rows, payoff, obstacle
 	// ------------------------------------------------------------------
 	{
-		const double *axis = b.axis + (size_t)cidx * b.axis_stride;
 		for(int j = 0; j < M; ++j) {
 			const int i = i0 + j;
 			sm_S[j * P + tid] = i < n_main ? refined_node(axis, b.refine, i) : 0.;
 		}
 		if(tid == 0) sm.tail.S = has_tail ? refined_node(axis, b.refine, N - 1) : 0.;
 	}
-	__syncthreads();
+	team_sync<CL>();
 	auto S_at = [&] (int i) -> double {       // node i of the refined grid, 0 <= i < N
-		return i >= n_main ? sm.tail.S : sm_S[(i % M) * P + (i / M)];
+		if(i >= n_main) return sm.tail.S;
+		const int l = i - row0;               // rows of this CTA are in shared memory
+		if(CL > 1 && (l < 0 || l >= MP)) return refined_node(axis, b.refine, i);
+		return sm_S[(l % M) * P + (l / M)];
 	};
 	{
 		const double r = b.r[cidx], q = b.q[cidx], sig = b.sigma[cidx];
@@ -195,12 +229,12 @@ k_resident_sweep(DeviceBatch b, DeviceResult out) {
 	double rr[M];       // right-hand side lb + penalty terms for the current active set
 	double vprev[BDF2 ? M : 1]; // iterand(1) for BDF2
 	double x_next;      // x of the next thread's first row
-	PartitionSolver<M, PT> ps;   // cached factorisation (registers)
+	PartitionSolver<M, PT, CL> ps;   // cached factorisation (registers)
 	ps.init();
 	unsigned curmask = 0, newmask = 0;  // bit j: row j penalised; bit M: tail row
 	// row N-2 (row M-1 of the last thread) couples to the tail row; that thread
 	// owns the tail equation and folds the coupling into its rhs.
-	const bool tail_owner = has_tail && tid == P - 1;
+	const bool tail_owner = has_tail && rank == CL - 1 && tid == P - 1;
 
 	auto initial_value = [&] (int i) -> double {
 		return b.payoff_kind == QPDE_PAYOFF_ARRAY
@@ -230,8 +264,8 @@ k_resident_sweep(DeviceBatch b, DeviceResult out) {
 		sm.tail.vprev = 0.; sm.tail.c = 0.; sm.tail.bd = 1.; sm.tail.me = 1.; sm.tail.invb = 1.; sm.tail.pq = 0.;
 	}
 	x_next = i0 + M < n_main ? initial_value(i0 + M) : 0.;
-	sm_xlast[tid + 1] = x[M - 1];
-	if(tid == 0) { sm_xlast[0] = 0.; sm.flags[0] = 0u; sm.flags[1] = 0u; }
+	publish_last(x[M - 1]);
+	if(tid == 0) { if(rank == 0) sm_xlast[0] = 0.; sm.flags[0] = 0u; sm.flags[1] = 0u; }
 
 	// PenaltyMethod.hpp:45,61-66: row penalised iff (scale * (x - payoff)) < 0,
 	// i.e. iff x < payoff (scale > 0 and the difference of two distinct doubles
@@ -266,9 +300,9 @@ k_resident_sweep(DeviceBatch b, DeviceResult out) {
 		} \
 		dst = mk_; \
 	} while(0)
-	__syncthreads();
+	team_sync<CL>();
 	if(POLICY) QPDE_POLICY_OF(newmask); else QPDE_MASK_OF(newmask);
-	__syncthreads();
+	team_sync<CL>();
 
 	// ------------------------------------------------------------------
 	// Time loop
@@ -412,7 +446,7 @@ k_resident_sweep(DeviceBatch b, DeviceResult out) {
 						sm.tail.invb = rcp(act ? sm.tail.bd + b.pen * 1. : sm.tail.bd);
 						sm.tail.pq = act ? b.pen * sm.tail.pz : 0.;
 					}
-					ps.factorize(aa, bb, cc, sm.ps, lane, warp);
+					ps.factorize(aa, bb, cc, team, lane, warp);
 				}
 			}
 
@@ -431,7 +465,7 @@ k_resident_sweep(DeviceBatch b, DeviceResult out) {
 				double r[M];
 #pragma unroll
 				for(int j = 0; j < M; ++j) r[j] = j == M - 1 ? r_last : rr[j];
-				ps.solve(r, G, x_next, sm.ps, lane, warp);
+				ps.solve(r, G, x_next, team, lane, warp);
 			}
 			bool nd = false;
 			if(ITERATE) {
@@ -450,11 +484,11 @@ k_resident_sweep(DeviceBatch b, DeviceResult out) {
 #pragma unroll
 			for(int j = 0; j < M; ++j) x[j] = G[j];
 			if(tail_owner) sm.tail.x = xt_new;
-			sm_xlast[tid + 1] = x[M - 1];
+			publish_last(x[M - 1]);
 			++its;
 			if(ITERATE) {
 				if(POLICY) {
-					__syncthreads();             // sm_xlast of the new iterate is visible
+					team_sync<CL>();             // sm_xlast of the new iterate is visible
 					QPDE_POLICY_OF(newmask);
 				} else {
 					QPDE_MASK_OF(newmask);
@@ -464,8 +498,11 @@ k_resident_sweep(DeviceBatch b, DeviceResult out) {
 				const unsigned wbits = __reduce_or_sync(FULL, bits);
 				const unsigned slot = flip & 1u;   // two slots used alternately
 				++flip;
-				if(lane == 0 && wbits) atomicOr(&sm.flags[slot], wbits);
-				__syncthreads();
+				if(lane == 0 && wbits) {
+#pragma unroll
+					for(int q = 0; q < CL; ++q) atomicOr(&peer_sm[q]->flags[slot], wbits);   // every CTA sees every flag
+				}
+				team_sync<CL>();
 				const unsigned all = *(volatile unsigned *)&sm.flags[slot];
 				if(tid == 0) sm.flags[slot ^ 1u] = 0u;       // ordered by the barrier inside the next solve
 				const bool notdone = (all & 1u) != 0, changed = (all & 2u) != 0;
@@ -481,12 +518,12 @@ k_resident_sweep(DeviceBatch b, DeviceResult out) {
 					status = 1; again = false;
 				}
 			} else {
-				__syncthreads();
+				team_sync<CL>();
 				again = false;
 			}
 		} while(again);
 
-		if(tid == 0 && out.inner) {
+		if(rank == 0 && tid == 0 && out.inner) {
 			out.inner[(size_t)cidx * out.inner_stride + n_steps] = (unsigned char)(its > 255 ? 255 : its);
 		}
 		inner_total += its;
@@ -529,7 +566,7 @@ k_resident_sweep(DeviceBatch b, DeviceResult out) {
 				for(int ue = 0; ue < st.user_events; ++ue) {
 					for(int op = 0; op < 2; ++op) {
 						const bool is_dividend = (op == 0) == (b.dividend_first != 0);
-						if(is_dividend && b.dividend_kind != QPDE_DIVIDEND_NONE) {
+						if(CL == 1 && is_dividend && b.dividend_kind != QPDE_DIVIDEND_NONE) {   // reads any node: one CTA only
 							// Event<1>::_doEvent with V(max(S - D, 0)) or V((1 - D) S): the solution goes to
 							// shared memory (sm_lb is free between steps), every node reads its two
 							// neighbours of the shifted price (Core/Interpolant.hpp:153-181,331-374).
@@ -574,11 +611,11 @@ k_resident_sweep(DeviceBatch b, DeviceResult out) {
 						}
 					}
 				}
-				__syncthreads();
-				sm_xfirst[tid] = x[0];
-				sm_xlast[tid + 1] = x[M - 1];
-				if(tid == 0) sm_xfirst[P] = 0.;
-				__syncthreads();
+				team_sync<CL>();
+				publish_first(x[0]);
+				publish_last(x[M - 1]);
+				if(tid == 0 && rank == CL - 1) sm_xfirst[P] = 0.;
+				team_sync<CL>();
 				x_next = sm_xfirst[tid + 1];
 			}
 			ns.after_event();
@@ -602,7 +639,7 @@ k_resident_sweep(DeviceBatch b, DeviceResult out) {
 			}
 		}
 	}
-	__syncthreads();   // the tail owner's last writes to sm.tail become visible
+	team_sync<CL>();   // the tail owner's last writes to sm.tail become visible; no CTA leaves while a peer may still write into it
 	if(tail_owner) {
 		if(out.V) out.V[(size_t)cidx * out.V_stride + N - 1] = sm.tail.x;
 		if(out.S) out.S[(size_t)cidx * out.S_stride + N - 1] = sm.tail.S;
@@ -611,7 +648,7 @@ k_resident_sweep(DeviceBatch b, DeviceResult out) {
 			out.active[(size_t)cidx * out.active_stride + N - 1] = pred < 0. ? 1 : 0;
 		}
 	}
-	if(tid == 0) {
+	if(rank == 0 && tid == 0) {
 		if(out.n_steps) out.n_steps[cidx] = n_steps;
 		if(out.inner_total) out.inner_total[cidx] = inner_total;
 		if(out.status) out.status[cidx] = status;
@@ -647,80 +684,95 @@ k_resident_sweep(DeviceBatch b, DeviceResult out) {
 // available; a grid of P M + 1 nodes uses the tail equation.
 //   N <=  513: M = 8, PT =  64      N <= 2049: M = 8, PT = 256 (or M = 4, PT = 512)
 //   N <= 2305: M = 9, PT = 256
-static int pick_geometry(int N, int *M, int *PT) {
+//   N <= 4097: M = 8, PT = 256, CL = 2 (a cluster of two CTAs per contract)
+static int pick_geometry(int N, int *M, int *PT, int *CL = nullptr) {
 	static const char *env = getenv("QPDE_RESIDENT_GEOMETRY");   // "4x512": A/B the wide variant
+	if(CL) *CL = 1;
 	if(N <= 8 * 64 + 1)       { *M = 8; *PT = 64;  return 1; }
 	if(N <= 8 * 256 + 1) {
 		if(env && !strcmp(env, "4x512")) { *M = 4; *PT = 512; return 1; }
 		*M = 8; *PT = 256; return 1;
 	}
 	if(N <= 9 * 256 + 1)      { *M = 9; *PT = 256; return 1; }
+	if(N <= 2 * 8 * 256 + 1)  { *M = 8; *PT = 256; if(CL) *CL = 2; return 1; }
 	return 0;
 }
 
 bool resident_supported(const DeviceBatch &b) {
-	int M, PT;
+	int M, PT, CL;
 	if(b.N < 10) return false;
-	if(!pick_geometry(b.N, &M, &PT)) return false;
+	if(!pick_geometry(b.N, &M, &PT, &CL)) return false;
+	if(CL > 1 && (b.variable_target || b.dividend_kind != QPDE_DIVIDEND_NONE)) return false; // one-CTA features
 	if(b.american && b.n_exercise > 0) return false; // penalty + events: INTERLEAVED family
 	if(b.n_controls != 0 && b.n_controls != 2) return false; // more control values: INTERLEAVED family
 	if(b.variable_target && !((M == 8 && PT == 64) || (M == 8 && PT == 256))) return false; // no room for V^n: INTERLEAVED family
 	return true;
 }
 
-template <int M, int PT, int MODE, bool BDF2, int EXTRA>
+template <int M, int PT, int MODE, bool BDF2, int EXTRA, int CL>
 static int launch_variant(const DeviceBatch &b, const DeviceResult &out, cudaStream_t stream) {
-	auto kern = k_resident_sweep<M, PT, MODE, BDF2, EXTRA>;
+	auto kern = k_resident_sweep<M, PT, MODE, BDF2, EXTRA, CL>;
 	static bool configured = false;
 	constexpr bool VARIABLE = EXTRA == EXTRA_VARIABLE;        // one more row array: V^n
+	const size_t smem = smem_bytes(M, PT, VARIABLE);
 	if(!configured) {
-		if(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
-				(int)smem_bytes(M, PT, VARIABLE)) != cudaSuccess) {
+		if(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
 			return QPDE_ERR_CUDA;
 		}
 		configured = true;
 	}
-	kern<<<b.C, PT, smem_bytes(M, PT, VARIABLE), stream>>>(b, out);
-	return QPDE_OK;
+	if(CL == 1) {
+		kern<<<b.C, PT, smem, stream>>>(b, out);
+		return QPDE_OK;
+	}
+	// CL CTAs per contract as one thread-block cluster
+	cudaLaunchConfig_t cfg = {};
+	cfg.gridDim = dim3((unsigned)b.C * CL); cfg.blockDim = dim3(PT); cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+	cudaLaunchAttribute attr[1];
+	attr[0].id = cudaLaunchAttributeClusterDimension;
+	attr[0].val.clusterDim.x = CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+	cfg.attrs = attr; cfg.numAttrs = 1;
+	return cudaLaunchKernelEx(&cfg, kern, b, out) == cudaSuccess ? QPDE_OK : QPDE_ERR_CUDA;
 }
 
-template <int M, int PT, int EXTRA>
+template <int M, int PT, int EXTRA, int CL>
 static int launch_extra(const DeviceBatch &b, const DeviceResult &out, cudaStream_t stream) {
 	const bool bdf2 = b.scheme == QPDE_SCHEME_BDF2;
-	if(b.n_controls > 0) return bdf2 ? launch_variant<M, PT, MODE_POLICY, true, EXTRA>(b, out, stream)
-	                                 : launch_variant<M, PT, MODE_POLICY, false, EXTRA>(b, out, stream);
-	if(b.american) return bdf2 ? launch_variant<M, PT, MODE_PENALTY, true, EXTRA>(b, out, stream)
-	                           : launch_variant<M, PT, MODE_PENALTY, false, EXTRA>(b, out, stream);
-	return bdf2 ? launch_variant<M, PT, MODE_LINEAR, true, EXTRA>(b, out, stream)
-	            : launch_variant<M, PT, MODE_LINEAR, false, EXTRA>(b, out, stream);
+	if(b.n_controls > 0) return bdf2 ? launch_variant<M, PT, MODE_POLICY, true, EXTRA, CL>(b, out, stream)
+	                                 : launch_variant<M, PT, MODE_POLICY, false, EXTRA, CL>(b, out, stream);
+	if(b.american) return bdf2 ? launch_variant<M, PT, MODE_PENALTY, true, EXTRA, CL>(b, out, stream)
+	                           : launch_variant<M, PT, MODE_PENALTY, false, EXTRA, CL>(b, out, stream);
+	return bdf2 ? launch_variant<M, PT, MODE_LINEAR, true, EXTRA, CL>(b, out, stream)
+	            : launch_variant<M, PT, MODE_LINEAR, false, EXTRA, CL>(b, out, stream);
 }
 
 // VARIABLE_OK: the geometry has room for the variable stepper's V^n array (and is worth the
 // extra instantiations)
-template <int M, int PT, bool VARIABLE_OK>
+template <int M, int PT, bool VARIABLE_OK, int CL>
 static int launch_rows(const DeviceBatch &b, const DeviceResult &out, cudaStream_t stream) {
 	const bool bdf2 = b.scheme == QPDE_SCHEME_BDF2;
 	if(b.variable_target) {
-		if(VARIABLE_OK) return launch_extra<M, PT, VARIABLE_OK ? EXTRA_VARIABLE : EXTRA_NONE>(b, out, stream);
+		if(VARIABLE_OK) return launch_extra<M, PT, VARIABLE_OK ? EXTRA_VARIABLE : EXTRA_NONE, CL>(b, out, stream);
 		return QPDE_ERR_UNSUPPORTED;
 	}
 	if(b.n_exercise > 0) {      // events: linear sweeps only (penalty + events: INTERLEAVED family)
-		return bdf2 ? launch_variant<M, PT, MODE_LINEAR, true, EXTRA_EVENTS>(b, out, stream)
-		            : launch_variant<M, PT, MODE_LINEAR, false, EXTRA_EVENTS>(b, out, stream);
+		return bdf2 ? launch_variant<M, PT, MODE_LINEAR, true, EXTRA_EVENTS, CL>(b, out, stream)
+		            : launch_variant<M, PT, MODE_LINEAR, false, EXTRA_EVENTS, CL>(b, out, stream);
 	}
-	return launch_extra<M, PT, EXTRA_NONE>(b, out, stream);
+	return launch_extra<M, PT, EXTRA_NONE, CL>(b, out, stream);
 }
 
 int launch_resident(const DeviceBatch &b, const DeviceResult &out, cudaStream_t stream,
 		int sm_count, long long *launches) {
 	(void)sm_count;
-	int M = 0, PT = 0;
-	if(!resident_supported(b) || !pick_geometry(b.N, &M, &PT)) return QPDE_ERR_UNSUPPORTED;
+	int M = 0, PT = 0, CL = 1;
+	if(!resident_supported(b) || !pick_geometry(b.N, &M, &PT, &CL)) return QPDE_ERR_UNSUPPORTED;
 	int rc;
-	if(M == 8 && PT == 64)       rc = launch_rows<8, 64, true>(b, out, stream);
-	else if(M == 8 && PT == 256) rc = launch_rows<8, 256, true>(b, out, stream);
-	else if(M == 4 && PT == 512) rc = launch_rows<4, 512, false>(b, out, stream);
-	else                         rc = launch_rows<9, 256, false>(b, out, stream);
+	if(CL == 2)                  rc = launch_rows<8, 256, false, 2>(b, out, stream);
+	else if(M == 8 && PT == 64)  rc = launch_rows<8, 64, true, 1>(b, out, stream);
+	else if(M == 8 && PT == 256) rc = launch_rows<8, 256, true, 1>(b, out, stream);
+	else if(M == 4 && PT == 512) rc = launch_rows<4, 512, false, 1>(b, out, stream);
+	else                         rc = launch_rows<9, 256, false, 1>(b, out, stream);
 	if(rc == QPDE_OK) *launches += 1;
 	return rc;
 }

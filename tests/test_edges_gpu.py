@@ -26,19 +26,81 @@ def test_single_contract_smallest_grid(qpde, handle, oracle):
         assert np.array_equal(res.inner[0, :12], o["inner"])
 
 
-def test_auto_picks_resident_up_to_2305_nodes_then_interleaved(qpde, handle, oracle):
-    # 2049 nodes: RESIDENT with the tail equation; 4097 nodes (refine 7): INTERLEAVED
+def test_auto_picks_resident_up_to_4097_nodes_then_interleaved(qpde, handle, oracle):
+    # 2049 nodes: RESIDENT with the tail equation; 4097 nodes (refine 7): RESIDENT on a cluster of two
+    # CTAs per contract (tail equation in the second CTA); 8193 nodes: INTERLEAVED
     o6 = oracle.american_put(100., .04, .2, 1., 40, 6)
     kernel, res = _american(qpde, handle, oracle, 100., .04, .2, 1., 40, 6)
     assert kernel == "resident" and rel_err(res.V[0], o6["V"]).max() <= REL_TOL
     assert np.array_equal(res.inner[0, :o6["n_steps"]], o6["inner"])
     o7 = oracle.american_put(100., .04, .2, 1., 20, 7)
-    kernel, res = _american(qpde, handle, oracle, 100., .04, .2, 1., 20, 7)
-    assert kernel == "interleaved" and len(o7["S"]) == 4097
-    assert rel_err(res.V[0], o7["V"]).max() <= REL_TOL
+    for forced in ("auto", "interleaved"):
+        kernel, res = _american(qpde, handle, oracle, 100., .04, .2, 1., 20, 7, kernel=forced)
+        assert kernel == ("resident" if forced == "auto" else "interleaved") and len(o7["S"]) == 4097
+        assert rel_err(res.V[0], o7["V"]).max() <= REL_TOL
+        assert np.array_equal(res.inner[0, :o7["n_steps"]], o7["inner"])
+    o8 = oracle.american_put(100., .04, .2, 1., 10, 8)
+    kernel, res = _american(qpde, handle, oracle, 100., .04, .2, 1., 10, 8)
+    assert kernel == "interleaved" and len(o8["S"]) == 8193
+    assert rel_err(res.V[0], o8["V"]).max() <= REL_TOL
     with pytest.raises(qpde.QpdeError) as e:
-        _american(qpde, handle, oracle, 100., .04, .2, 1., 20, 7, kernel="resident")
+        _american(qpde, handle, oracle, 100., .04, .2, 1., 10, 8, kernel="resident")
     assert e.value.code == qpde.ERR_UNSUPPORTED
+
+
+@pytest.mark.parametrize("nodes_extra", [0, 3])
+@pytest.mark.parametrize("case", ["american_rannacher", "american_bdf2", "european_cn", "bermudan_bdf2", "hjb_bdf2"])
+def test_cluster_of_two_ctas_per_contract(qpde, handle, oracle, case, nodes_extra):
+    """2305 < N <= 4097: the rows of one contract are split over the two CTAs of a thread-block
+    cluster.  With extra ticks the grid has no tail equation (N = 4481 would not fit; 3 extra ticks
+    at refine 6 give 2241 + ... nodes, still two CTAs)."""
+    base = oracle.special_axis() * 100.
+    if nodes_extra:
+        S0 = np.concatenate([base, [20000., 40000., 80000.]]); refine = 6     # 36 ticks -> 2241 nodes: one CTA, 9 rows
+        S0 = np.concatenate([S0, [160000., 320000., 640000.]])               # 39 ticks -> 2433 nodes: two CTAs, no tail
+    else:
+        S0 = base; refine = 7                                                  # 33 ticks -> 4097 nodes: two CTAs + tail
+    S = oracle.refine(S0, refine)
+    K, r, vol, T, steps = 100., .04, .25, 1., 30
+    Cn = 3
+    common = dict(axis=np.tile(S0, (Cn, 1)), refine=refine, q=0., T=T, dt=T / steps, strike=np.full(Cn, K), kernel="resident")
+    if case.startswith("american") or case == "european_cn":
+        scheme = {"american_rannacher": "rannacher", "american_bdf2": "bdf2", "european_cn": "cn"}[case]
+        american = case.startswith("american")
+        lo, di, up = oracle.bs_coeffs(S, r, vol, 0.)
+        payoff = np.where(S < K, K - S, 0.)
+        st, n = oracle.schedule(T, T / steps)
+        o = oracle.sweep(S, lo, di, up, payoff, T, st, n, scheme=scheme, american=american, obstacle=payoff)
+        spec = qpde.BatchSpec(r=r, sigma=vol, scheme=scheme, american=american, payoff="put", **common)
+    elif case == "bermudan_bdf2":
+        with np.errstate(divide="ignore"):
+            lo, di, up = oracle.bs_coeffs(S, r, 20. / S, 0.)
+        payoff = np.maximum(K - S, 0.)
+        st, n = oracle.schedule(T, T / steps, [T / 5 * e for e in range(5)])
+        o = oracle.sweep(S, lo, di, up, payoff, T, st, n, scheme="bdf2", american=False, obstacle=payoff, event_obstacle=K - S)
+        spec = qpde.BatchSpec(r=r, sigma=20., scheme="bdf2", american=False, payoff="put", vol_model="inverse_s",
+                              n_exercise=5, exercise="k_minus_s", **common)
+    else:
+        rows = [oracle.bs_coeffs(S, rr, vol, 0.) for rr in (.03, .05)]
+        prs = tuple(np.stack([rw[k] for rw in rows]) for k in range(3))
+        payoff = np.where(S < K, K - S, S - K)
+        st, n = oracle.schedule(T, T / steps)
+        o = oracle.sweep(S, rows[0][0], rows[0][1], rows[0][2], payoff, T, st, n, scheme="bdf2", american=False,
+                         obstacle=payoff, policy_rows=prs, policy_max=False)
+        spec = qpde.BatchSpec(r=0., sigma=vol, scheme="bdf2", american=False, payoff="straddle",
+                              controls=np.array([.03, .05]), policy_max=False, **common)
+    with qpde.Plan(handle, spec) as plan:
+        assert plan.kernel == "resident" and plan.N == len(S) and 2305 < plan.N <= 4097
+        plan.run(); res = plan.fetch()
+    for c in range(Cn):
+        assert res.status[c] == 0 and res.n_steps[c] == n
+        assert np.array_equal(res.S[c], S)
+        err = rel_err(res.V[c], o["V"]).max()
+        assert err <= REL_TOL, "%s: %.3e" % (case, err)
+        if case.startswith("american") or case == "hjb_bdf2":
+            assert np.array_equal(res.inner[c, :n], o["inner"]), case
+        assert rel_err(res.value[c], oracle.lib().qpo_interp(len(S), oracle._dp(np.ascontiguousarray(S)),
+                                                             oracle._dp(np.ascontiguousarray(o["V"])), K)) <= REL_TOL
 
 
 def test_largest_resident_grid_nine_rows_per_thread(qpde, handle, oracle):

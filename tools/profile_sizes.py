@@ -12,7 +12,7 @@ import bench  # noqa: E402
 from quantpde_b200 import capi  # noqa: E402
 
 with capi.Handle(0) as h:
-    for refine, kernel, Cn, steps in ((6, "resident", 4736, 1000), (6, "interleaved", 16384, 1000), (7, "auto", 16384, 1000),
+    for refine, kernel, Cn, steps in ((6, "resident", 4736, 1000), (6, "interleaved", 16384, 1000), (7, "auto", 4736, 1000), (7, "interleaved", 16384, 1000),
                                       (4, "resident", 37888, 1000), (4, "interleaved", 65536, 1000), (2, "auto", 65536, 1000)):
         K, vol, T, r = bench.contract_parameters(Cn)
         axis = np.ascontiguousarray(K[:, None] * bench.SPECIAL[None, :])
