@@ -48,7 +48,12 @@ struct GmwbDev {
 	const double *W, *A, *q, *z;
 	double r, eta, sigma, kfee, c;
 	double pen, tol;
+	// bucket tables for the interpolation searches of the impulse step: lutW[b] = largest node
+	// index i with W[i] <= b / invhW (same for A); GMWB_LUT buckets over [0, axis end]
+	const int *lutW, *lutA;
+	double invhW, invhA;
 };
+constexpr int GMWB_LUT = 1 << 16;
 
 // Assembled rows: W sub / diagonal / W super, coefficient of the node below in A,
 // right-hand side, and up to four far impulse targets (index -1 = none).
@@ -62,6 +67,20 @@ namespace {
 __device__ __forceinline__ double qmax(double x, double y) { return x > y ? x : y; }
 
 // linearInterpolationData, Core/Interpolant.hpp:153-181
+// The same through a bucket table: a start index not above the bracket, then a walk of a few
+// nodes instead of a bisection (same idx, same weight).  Needs x[0] == 0 and lut from make_lut().
+__device__ __forceinline__ void axis_interp_lut(const double *x, int length, const int *lut, double invh,
+		double ci, int &idx, double &w) {
+	if(ci <= x[0]) { idx = 0; w = 1.; return; }
+	if(ci >= x[length - 1]) { idx = length - 2; w = 0.; return; }
+	int bkt = (int)(ci * invh);
+	bkt = bkt < GMWB_LUT - 1 ? bkt : GMWB_LUT - 1;
+	int i = lut[bkt];
+	while(x[i + 1] <= ci) ++i;            // x[i] <= ci < x[i + 1]; terminates: ci < x[length - 1]
+	idx = i;
+	w = (x[i + 1] - ci) / (x[i + 1] - x[i]);
+}
+
 __device__ __forceinline__ void axis_interp(const double *x, int length, double ci, int &idx, double &w) {
 	if(ci <= x[0]) { idx = 0; w = 1.; return; }
 	if(ci >= x[length - 1]) { idx = length - 2; w = 0.; return; }
@@ -163,8 +182,8 @@ k_gmwb_policy(GmwbDev d, GmwbRows R, const double *x, const double *v0, double h
 			const double z = d.z[k] * a;
 			const double w_plus = qmax(w - z, 0.), a_plus = a - z;     // gmwb.cpp:139-148
 			int i0, i1; double f0, f1;
-			axis_interp(d.W, nw, w_plus, i0, f0);
-			axis_interp(d.A, d.na, a_plus, i1, f1);
+			axis_interp_lut(d.W, nw, d.lutW, d.invhW, w_plus, i0, f0);
+			axis_interp_lut(d.A, d.na, d.lutA, d.invhA, a_plus, i1, f1);
 			const int tt[4] = { i0 + nw * i1, i0 + 1 + nw * i1, i0 + nw * (i1 + 1), i0 + 1 + nw * (i1 + 1) };
 			const double ff[4] = { 1. * f0 * f1, 1. * (-f0 + 1.) * f1, 1. * f0 * (-f1 + 1.), 1. * (-f0 + 1.) * (-f1 + 1.) };
 			const double g = (w - w_plus) + (a - a_plus) < DBL_EPSILON ? -CUDART_INF : (1 - d.kfee) * z - d.c;
@@ -595,6 +614,22 @@ static cudaError_t launch_lines(GmwbShard &sh, double *x, int ia0, int ia1, int 
 	}
 }
 
+// lut[b] = largest i with x[i] <= b h, h = x[n - 1] / GMWB_LUT; returns 1 / h.  A value ci in
+// bucket b = floor(ci / h) has its bracket at or above lut[b] whatever the rounding of ci / h does
+// to the bucket (a bucket too low only lengthens the walk; too high cannot happen by more than
+// one, which is guarded by taking the entry of the bucket below).
+static double make_lut(const double *x, int n, std::vector<int> &lut) {
+	const double h = x[n - 1] / GMWB_LUT, invh = 1. / h;
+	lut.assign(GMWB_LUT, 0);
+	int i = 0;
+	for(int bkt = 0; bkt < GMWB_LUT; ++bkt) {
+		const double edge = (bkt > 0 ? bkt - 1 : 0) * h;      // one bucket of slack against rounding
+		while(i + 1 < n - 1 && x[i + 1] <= edge) ++i;
+		lut[bkt] = i;
+	}
+	return invh;
+}
+
 void gmwb_shard_destroy(GmwbShard *sh) {
 	if(!sh) return;
 	for(void *ptr : sh->allocs) cudaFree(ptr);
@@ -627,16 +662,22 @@ int gmwb_shard_create(const qpde_gmwb2d *p, const double *W, int nw, const doubl
 	R.raa = (double *)dalloc(sizeof(double) * n); R.rhs = (double *)dalloc(sizeof(double) * n);
 	R.tgt = (int *)dalloc(sizeof(int) * 4 * (size_t)n); R.tw = (double *)dalloc(sizeof(double) * 4 * (size_t)n);
 	sh->flags = (int *)dalloc(sizeof(int) * 4);
+	int *dlutW = (int *)dalloc(sizeof(int) * GMWB_LUT), *dlutA = (int *)dalloc(sizeof(int) * GMWB_LUT);
+	std::vector<int> lutW, lutA;
+	const double invhW = make_lut(W, nw, lutW), invhA = make_lut(A, na, lutA);
 	if(!ok) { gmwb_shard_destroy(sh); *error = "gmwb: out of device memory"; return QPDE_ERR_CUDA; }
 	cudaMemcpyAsync(dW, W, sizeof(double) * nw, cudaMemcpyHostToDevice, stream);
 	cudaMemcpyAsync(dA, A, sizeof(double) * na, cudaMemcpyHostToDevice, stream);
 	cudaMemcpyAsync(dq, p->controls, sizeof(double) * p->n_controls, cudaMemcpyHostToDevice, stream);
 	cudaMemcpyAsync(dz, z, sizeof(double) * nz, cudaMemcpyHostToDevice, stream);
+	cudaMemcpyAsync(dlutW, lutW.data(), sizeof(int) * GMWB_LUT, cudaMemcpyHostToDevice, stream);
+	cudaMemcpyAsync(dlutA, lutA.data(), sizeof(int) * GMWB_LUT, cudaMemcpyHostToDevice, stream);
 	cudaMemsetAsync(sh->flags, 0, sizeof(int) * 4, stream);
 	cudaStreamSynchronize(stream);      // the host arrays may go away
 	GmwbDev &d = sh->d;
 	d.nw = nw; d.na = na; d.nq = p->n_controls; d.nz = nz;
 	d.W = dW; d.A = dA; d.q = dq; d.z = dz;
+	d.lutW = dlutW; d.lutA = dlutA; d.invhW = invhW; d.invhA = invhA;
 	d.r = p->r; d.eta = p->eta; d.sigma = p->sigma; d.kfee = p->kappa; d.c = p->c;
 	d.pen = 1. / (p->scaling_factor * (p->T / p->timesteps));   // HJBQVI.hpp:635, PenaltyMethod.hpp:85
 	d.tol = p->tolerance;
