@@ -154,8 +154,28 @@ __global__ void __launch_bounds__(128)
 k_gmwb_policy(GmwbDev d, GmwbRows R, const double *x, const double *v0, double h0, int row_begin, int row_end) {
 	const int n = d.nw * d.na;
 	const int row = row_begin + blockIdx.x * blockDim.x + threadIdx.x;
+	const int nw = d.nw;
+	// The A-direction half of every impulse candidate — z = z_k a, a - z and its bracket on the A
+	// axis — depends on (line, k) only: formed once per CTA for the lines its rows touch.
+	extern __shared__ __align__(16) unsigned char pol_smem[];
+	const int lines = blockDim.x / nw + 2;
+	double *const tab_z = reinterpret_cast<double *>(pol_smem);        // [lines][nz]
+	double *const tab_f1 = tab_z + lines * d.nz;
+	int *const tab_i1 = reinterpret_cast<int *>(tab_f1 + lines * d.nz);
+	const int ia_first = (row_begin + blockIdx.x * blockDim.x) / nw;
+	for(int e = threadIdx.x; e < lines * d.nz; e += blockDim.x) {
+		const int ial = ia_first + e / d.nz, k = e % d.nz;
+		if(ial < d.na) {
+			const double a = d.A[ial], z = d.z[k] * a;
+			int i1; double f1;
+			axis_interp_lut(d.A, d.na, d.lutA, d.invhA, a - z, i1, f1);
+			tab_z[e] = z; tab_f1[e] = f1; tab_i1[e] = i1;
+		}
+	}
+	__syncthreads();
 	if(row >= row_end) return;
-	const int nw = d.nw, iw = row % nw, ia = row / nw;
+	const int iw = row % nw, ia = row / nw;
+	const int tab0 = (ia - ia_first) * d.nz;
 
 	// 1. stochastic control: argmin_q (L^q x - f^q)_row, strict <, grid order
 	OpRow o; o.aw = o.cw = o.aa = o.ca = 0.; o.diag = 0.; o.b = 0.;
@@ -179,11 +199,11 @@ k_gmwb_policy(GmwbDev d, GmwbRows R, const double *x, const double *v0, double h
 	{
 		const double w = d.W[iw], a = d.A[ia];
 		for(int k = 0; k < d.nz; ++k) {
-			const double z = d.z[k] * a;
+			const double z = tab_z[tab0 + k];
 			const double w_plus = qmax(w - z, 0.), a_plus = a - z;     // gmwb.cpp:139-148
-			int i0, i1; double f0, f1;
+			int i0; double f0;
+			const int i1 = tab_i1[tab0 + k]; const double f1 = tab_f1[tab0 + k];
 			axis_interp_lut(d.W, nw, d.lutW, d.invhW, w_plus, i0, f0);
-			axis_interp_lut(d.A, d.na, d.lutA, d.invhA, a_plus, i1, f1);
 			const int tt[4] = { i0 + nw * i1, i0 + 1 + nw * i1, i0 + nw * (i1 + 1), i0 + 1 + nw * (i1 + 1) };
 			const double ff[4] = { 1. * f0 * f1, 1. * (-f0 + 1.) * f1, 1. * f0 * (-f1 + 1.), 1. * (-f0 + 1.) * (-f1 + 1.) };
 			const double g = (w - w_plus) + (a - a_plus) < DBL_EPSILON ? -CUDART_INF : (1 - d.kfee) * z - d.c;
@@ -694,7 +714,11 @@ void gmwb_shard_exit(GmwbShard *sh, double *x) {
 // control searches + row assembly for the shard's lines, from the full previous iterate
 void gmwb_shard_policy(GmwbShard *sh, const double *x, const double *v0, double h0) {
 	const int r0 = sh->a_begin * sh->d.nw, r1 = sh->a_end * sh->d.nw;
-	if(r1 > r0) { k_gmwb_policy<<<(r1 - r0 + 127) / 128, 128, 0, sh->stream>>>(sh->d, sh->R, x, v0, h0, r0, r1); ++*sh->launches; }
+	if(r1 > r0) {
+		const size_t smem = (size_t)(128 / sh->d.nw + 2) * sh->d.nz * (2 * sizeof(double) + sizeof(int));
+		k_gmwb_policy<<<(r1 - r0 + 127) / 128, 128, smem, sh->stream>>>(sh->d, sh->R, x, v0, h0, r0, r1);
+		++*sh->launches;
+	}
 }
 
 // the shard's line solves in ascending A (exact given final lines below a_begin);
