@@ -27,7 +27,7 @@
 namespace qpde {
 
 constexpr unsigned FULL_MASK = 0xffffffffu;
-constexpr int PS_MAX_WARPS = 16;    // PT <= 512 threads per CTA
+constexpr int PS_MAX_WARPS = 32;    // warps of one system: PT <= 512 threads per CTA, or a cluster of 4 x 256
 
 __host__ __device__ constexpr int ilog2_ceil(int n) { return n <= 1 ? 0 : 1 + ilog2_ceil((n + 1) / 2); }
 
@@ -265,7 +265,7 @@ struct PartitionSolver {
 		}
 		const double Y = R3 * f_invB3;            // separator of warp `lane` (0 for lanes >= W)
 		const double Yw = shfl_idx(Y, warp);
-		const double Yn = shfl_idx(Y, warp + 1);   // lane W holds 0
+		const double Yn = warp + 1 < 32 ? shfl_idx(Y, warp + 1) : 0.;   // lane W holds 0; W == 32 has no such lane
 		// back substitution, levels 2 and 1
 		const double ysep = lane == 0 ? Yw : fma(-Yn, f_W2, fma(-Yw, f_V2, G2));
 		double ynext = shfl_down(ysep, 1);

@@ -684,7 +684,7 @@ k_resident_sweep(DeviceBatch b, DeviceResult out) {
 // available; a grid of P M + 1 nodes uses the tail equation.
 //   N <=  513: M = 8, PT =  64      N <= 2049: M = 8, PT = 256 (or M = 4, PT = 512)
 //   N <= 2305: M = 9, PT = 256
-//   N <= 4097: M = 8, PT = 256, CL = 2 (a cluster of two CTAs per contract)
+//   N <= 4097: M = 8, PT = 256, CL = 2 (a cluster of two CTAs per contract); N <= 8193: CL = 4
 static int pick_geometry(int N, int *M, int *PT, int *CL = nullptr) {
 	static const char *env = getenv("QPDE_RESIDENT_GEOMETRY");   // "4x512": A/B the wide variant
 	if(CL) *CL = 1;
@@ -695,6 +695,7 @@ static int pick_geometry(int N, int *M, int *PT, int *CL = nullptr) {
 	}
 	if(N <= 9 * 256 + 1)      { *M = 9; *PT = 256; return 1; }
 	if(N <= 2 * 8 * 256 + 1)  { *M = 8; *PT = 256; if(CL) *CL = 2; return 1; }
+	if(N <= 4 * 8 * 256 + 1)  { *M = 8; *PT = 256; if(CL) *CL = 4; return 1; }
 	return 0;
 }
 
@@ -768,7 +769,8 @@ int launch_resident(const DeviceBatch &b, const DeviceResult &out, cudaStream_t 
 	int M = 0, PT = 0, CL = 1;
 	if(!resident_supported(b) || !pick_geometry(b.N, &M, &PT, &CL)) return QPDE_ERR_UNSUPPORTED;
 	int rc;
-	if(CL == 2)                  rc = launch_rows<8, 256, false, 2>(b, out, stream);
+	if(CL == 4)                  rc = launch_rows<8, 256, false, 4>(b, out, stream);
+	else if(CL == 2)             rc = launch_rows<8, 256, false, 2>(b, out, stream);
 	else if(M == 8 && PT == 64)  rc = launch_rows<8, 64, true, 1>(b, out, stream);
 	else if(M == 8 && PT == 256) rc = launch_rows<8, 256, true, 1>(b, out, stream);
 	else if(M == 4 && PT == 512) rc = launch_rows<4, 512, false, 1>(b, out, stream);

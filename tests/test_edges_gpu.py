@@ -26,9 +26,9 @@ def test_single_contract_smallest_grid(qpde, handle, oracle):
         assert np.array_equal(res.inner[0, :12], o["inner"])
 
 
-def test_auto_picks_resident_up_to_4097_nodes_then_interleaved(qpde, handle, oracle):
-    # 2049 nodes: RESIDENT with the tail equation; 4097 nodes (refine 7): RESIDENT on a cluster of two
-    # CTAs per contract (tail equation in the second CTA); 8193 nodes: INTERLEAVED
+def test_auto_picks_resident_up_to_8193_nodes_then_interleaved(qpde, handle, oracle):
+    # 2049 nodes: RESIDENT with the tail equation; 4097 / 8193 nodes (refine 7 / 8): RESIDENT on a cluster
+    # of two / four CTAs per contract (tail equation in the last CTA); 16385 nodes: INTERLEAVED
     o6 = oracle.american_put(100., .04, .2, 1., 40, 6)
     kernel, res = _american(qpde, handle, oracle, 100., .04, .2, 1., 40, 6)
     assert kernel == "resident" and rel_err(res.V[0], o6["V"]).max() <= REL_TOL
@@ -41,25 +41,31 @@ def test_auto_picks_resident_up_to_4097_nodes_then_interleaved(qpde, handle, ora
         assert np.array_equal(res.inner[0, :o7["n_steps"]], o7["inner"])
     o8 = oracle.american_put(100., .04, .2, 1., 10, 8)
     kernel, res = _american(qpde, handle, oracle, 100., .04, .2, 1., 10, 8)
-    assert kernel == "interleaved" and len(o8["S"]) == 8193
+    assert kernel == "resident" and len(o8["S"]) == 8193
     assert rel_err(res.V[0], o8["V"]).max() <= REL_TOL
+    assert np.array_equal(res.inner[0, :o8["n_steps"]], o8["inner"])
+    o9 = oracle.american_put(100., .04, .2, 1., 20, 9)                # up to ~80 penalty iterations per step here
+    kernel, res = _american(qpde, handle, oracle, 100., .04, .2, 1., 20, 9, max_inner=1000)
+    assert kernel == "interleaved" and len(o9["S"]) == 16385 and res.status[0] == 0
+    assert rel_err(res.V[0], o9["V"]).max() <= REL_TOL
+    assert np.array_equal(res.inner[0, :20], np.minimum(o9["inner"], 255))
     with pytest.raises(qpde.QpdeError) as e:
-        _american(qpde, handle, oracle, 100., .04, .2, 1., 10, 8, kernel="resident")
+        _american(qpde, handle, oracle, 100., .04, .2, 1., 20, 9, kernel="resident")
     assert e.value.code == qpde.ERR_UNSUPPORTED
 
 
-@pytest.mark.parametrize("nodes_extra", [0, 3])
+@pytest.mark.parametrize("nodes_extra", [0, 3, 8])
 @pytest.mark.parametrize("case", ["american_rannacher", "american_bdf2", "european_cn", "bermudan_bdf2", "hjb_bdf2"])
-def test_cluster_of_two_ctas_per_contract(qpde, handle, oracle, case, nodes_extra):
-    """2305 < N <= 4097: the rows of one contract are split over the two CTAs of a thread-block
-    cluster.  With extra ticks the grid has no tail equation (N = 4481 would not fit; 3 extra ticks
-    at refine 6 give 2241 + ... nodes, still two CTAs)."""
+def test_cluster_of_ctas_per_contract(qpde, handle, oracle, case, nodes_extra):
+    """2305 < N <= 8193: the rows of one contract are split over the two or four CTAs of a
+    thread-block cluster, with (4097, 8193 nodes) and without (2433 nodes) the tail equation."""
     base = oracle.special_axis() * 100.
-    if nodes_extra:
-        S0 = np.concatenate([base, [20000., 40000., 80000.]]); refine = 6     # 36 ticks -> 2241 nodes: one CTA, 9 rows
-        S0 = np.concatenate([S0, [160000., 320000., 640000.]])               # 39 ticks -> 2433 nodes: two CTAs, no tail
+    if nodes_extra == 3:
+        S0 = np.concatenate([base, [20000., 40000., 80000., 160000., 320000., 640000.]]); refine = 6   # 39 ticks -> 2433 nodes
+    elif nodes_extra == 8:
+        S0 = base; refine = 8                                                  # 8193 nodes: four CTAs + tail
     else:
-        S0 = base; refine = 7                                                  # 33 ticks -> 4097 nodes: two CTAs + tail
+        S0 = base; refine = 7                                                  # 4097 nodes: two CTAs + tail
     S = oracle.refine(S0, refine)
     K, r, vol, T, steps = 100., .04, .25, 1., 30
     Cn = 3
@@ -90,7 +96,7 @@ def test_cluster_of_two_ctas_per_contract(qpde, handle, oracle, case, nodes_extr
         spec = qpde.BatchSpec(r=0., sigma=vol, scheme="bdf2", american=False, payoff="straddle",
                               controls=np.array([.03, .05]), policy_max=False, **common)
     with qpde.Plan(handle, spec) as plan:
-        assert plan.kernel == "resident" and plan.N == len(S) and 2305 < plan.N <= 4097
+        assert plan.kernel == "resident" and plan.N == len(S) and 2305 < plan.N <= 8193
         plan.run(); res = plan.fetch()
     for c in range(Cn):
         assert res.status[c] == 0 and res.n_steps[c] == n
