@@ -439,7 +439,6 @@ static int plan_create_impl(qpde_handle *h, const qpde_bs1d_batch *in,
 		QPDE_TRY(dev_alloc(p, &p->jw.g_w, (size_t)C * b.n_fft));
 		QPDE_TRY(dev_alloc(p, &p->jw.n_idx, (size_t)C * N));
 		QPDE_TRY(dev_alloc(p, &p->jw.n_w, (size_t)C * N));
-		QPDE_TRY(dev_alloc(p, &p->jw.fw, (size_t)C * b.n_fft));
 	}
 	if(kernel == QPDE_KERNEL_AUTO) {
 		kernel = resident_supported(b) ? QPDE_KERNEL_RESIDENT : QPDE_KERNEL_INTERLEAVED;

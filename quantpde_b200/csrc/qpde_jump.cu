@@ -13,9 +13,11 @@
 //   SparseLUSolver                           Bindings/Eigen.hpp:143-165
 //
 // Per time step: (1) gather V onto the log-grid through a per-contract
-// interpolation table, written bit-reversed into shared memory; (2) a
-// hand-written radix-2 FFT pair in shared memory (forward decimation-in-time,
-// multiply by the conjugate spectrum of the density weights, inverse
+// interpolation table, written bit-reversed into shared memory, two real points
+// per complex element; (2) a hand-written radix-2 FFT pair of n_fft / 2 complex
+// points in shared memory (forward decimation-in-time, one pass that unpacks the
+// real-data spectrum, multiplies by the conjugate spectrum of the density weights
+// — kept in shared memory — and packs for the way back, inverse
 // decimation-in-frequency) — no cuFFT; (3) interpolate h back at log S_i and
 // add h0 * lambda * h to the BDF right-hand side; (4) the partition solve with
 // the cached factorisation (the matrix is constant in time).
@@ -38,14 +40,16 @@ struct JumpSmem {
 };
 
 // padded sizes of the complex work buffer and of the twiddle table (pad_buf, pad_tw below)
-inline int pad_buf_size(int NF) { return NF + (NF >> 3) + 1; }
-inline int pad_tw_size(int NF) { const int h = NF / 2; return h + (h >> 3) + (h >> 6) + (h >> 9) + 1; }
+__host__ __device__ inline int pad_buf_size(int NF) { return NF + (NF >> 3) + 1; }
+__host__ __device__ inline int pad_tw_size(int NF) { const int h = NF / 2; return h + (h >> 3) + (h >> 6) + (h >> 9) + 1; }
 
 inline size_t jump_smem_bytes(int M, int P, int NF) {
-	// row arrays [M][P] (+1 slot of V for the tail node), complex work buffer
-	// [NF], twiddles [NF / 2]
+	// row arrays [M][P] (+1 slot of V for the tail node); the transforms are of NF / 2 complex
+	// points (real data, see below): work buffer, twiddles of the half-size transform,
+	// exp(-2 pi i k / NF) for k <= NF / 4, spectrum of the density weights for k <= NF / 2
+	const int NH = NF / 2;
 	return sizeof(JumpSmem) + sizeof(double) * ((size_t)JUMP_ROW_ARRAYS * M * P + 2)
-		+ sizeof(double2) * ((size_t)pad_buf_size(NF) + pad_tw_size(NF));
+		+ sizeof(double2) * ((size_t)pad_buf_size(NH) + pad_tw_size(NH) + (NH / 2 + 1) + (NH + 1));
 }
 
 __device__ __forceinline__ double2 cmul(double2 a, double2 b) {
@@ -126,6 +130,43 @@ __device__ __forceinline__ void fft_inverse_dif(double2 *buf, const double2 *tw,
 	for(int s0 = 3 * ((logNF - 1) / 3); s0 >= 0; s0 -= 3) fft_pass_any<PT, true>(buf, tw, NF, logNF, s0, logNF - s0 < 3 ? logNF - s0 : 3, tid);
 }
 
+// The data are real: the NF real points x_n are transformed as NH = NF / 2 complex points
+// z_m = x_2m + i x_2m+1.  With Z = DFT_NH(z), E / O the transforms of the even / odd samples and
+// q_k = exp(-2 pi i k / NF):  E_k = (Z_k + conj Z_{NH-k}) / 2,  O_k = (Z_k - conj Z_{NH-k}) / (2 i),
+// X_k = E_k + q_k O_k,  X_{NH-k} = conj(E_k - q_k O_k)  (k = 0 .. NH / 2; X_NH is the Nyquist term).
+// The inverse of a Hermitian spectrum Y goes the same way back:  Z'_k = A_k + i B_k with
+// A_k = Y_k + conj Y_{NH-k},  B_k = (Y_k - conj Y_{NH-k}) conj q_k,  Z'_{NH-k} = conj A_k + i conj B_k;
+// the unscaled inverse DFT_NH of Z' is NF (y_2m + i y_2m+1).
+// spectral_pass does, for the pair (k, NH - k) in place in `buf` (natural order):
+//   STORE:   F_k, F_{NH-k} <- X_k, X_{NH-k}                       (set-up: spectrum of the weights)
+//   else:    Y = X conj F, then Z' into buf                       (every step: the correlation)
+template <int PT, bool STORE>
+__device__ __forceinline__ void spectral_pass(double2 *buf, const double2 *tq, double2 *F, int NH, int tid) {
+	for(int k = tid; k <= NH / 2; k += PT) {
+		const int km = k == 0 ? 0 : NH - k;
+		const double2 Zk = buf[pad_buf(k)], Zm = buf[pad_buf(km)];
+		const double2 E = make_double2(.5 * (Zk.x + Zm.x), .5 * (Zk.y - Zm.y));
+		const double2 O = make_double2(.5 * (Zk.y + Zm.y), -.5 * (Zk.x - Zm.x));
+		const double2 q = tq[k];
+		const double2 T = cmul(q, O);
+		const double2 Xk = make_double2(E.x + T.x, E.y + T.y);
+		const double2 Xm = make_double2(E.x - T.x, -(E.y - T.y));
+		if(STORE) {
+			F[k] = Xk; F[NH - k] = Xm;
+		} else {
+			const double2 Fk = F[k], Fm = F[NH - k];
+			const double2 Yk = cmul(Xk, make_double2(Fk.x, -Fk.y));
+			const double2 Ym = cmul(Xm, make_double2(Fm.x, -Fm.y));
+			const double2 A = make_double2(Yk.x + Ym.x, Yk.y - Ym.y);
+			const double2 D = make_double2(Yk.x - Ym.x, Yk.y + Ym.y);
+			const double2 B = cmul(D, make_double2(q.x, -q.y));
+			buf[pad_buf(k)] = make_double2(A.x - B.y, A.y + B.x);              // A + i B
+			if(km != k && k != 0) buf[pad_buf(km)] = make_double2(A.x + B.y, -A.y + B.x);   // conj A + i conj B
+		}
+	}
+	__syncthreads();
+}
+
 __device__ __forceinline__ int bitrev(int k, int logNF) { return (int)(__brev((unsigned)k) >> (32 - logNF)); }
 
 // linearInterpolationData (Core/Interpolant.hpp:153-181) on ticks given by a functor
@@ -167,10 +208,12 @@ k_jump_sweep(DeviceBatch b, JumpWork work, DeviceResult out) {
 	double *const sm_di = sm_lo + MP;
 	double *const sm_up = sm_di + MP;
 	double *const sm_V  = sm_up + MP;             // [MP + 1]: current solution, node-addressable
-	double2 *const sm_buf = reinterpret_cast<double2 *>(sm_V + MP + 2);   // [NF]
-	const int NF = b.n_fft;
-	double2 *const sm_tw = sm_buf + (NF + (NF >> 3) + 1);                 // [NF / 2], padded (pad_tw)
-	const int logNF = 31 - __clz(NF);
+	const int NF = b.n_fft, NH = NF / 2;          // NF real points = NH complex points (spectral_pass)
+	const int logNH = 31 - __clz(NH);
+	double2 *const sm_buf = reinterpret_cast<double2 *>(sm_V + MP + 2);   // [NH], padded (pad_buf)
+	double2 *const sm_tw = sm_buf + pad_buf_size(NH);                     // [NH / 2], padded (pad_tw): exp(-2 pi i k / NH)
+	double2 *const sm_tq = sm_tw + pad_tw_size(NH);                       // [NH / 2 + 1]: exp(-2 pi i k / NF)
+	double2 *const sm_F = sm_tq + (NH / 2 + 1);                           // [NH + 1]: spectrum of the density weights
 
 	const int cidx = blockIdx.x;
 	const int tid = threadIdx.x;
@@ -188,7 +231,6 @@ k_jump_sweep(DeviceBatch b, JumpWork work, DeviceResult out) {
 	double *const g_w = work.g_w + (size_t)cidx * NF;
 	int *const n_idx = work.n_idx + (size_t)cidx * N;
 	double *const n_w = work.n_w + (size_t)cidx * N;
-	double2 *const fw = work.fw + (size_t)cidx * NF;
 
 	// node i of V / S in shared memory
 	auto at_node = [&] (int i) -> int { return i >= n_main ? MP : (i % M) * P + (i / M); };
@@ -203,10 +245,14 @@ k_jump_sweep(DeviceBatch b, JumpWork work, DeviceResult out) {
 			sm_S[j * P + tid] = i < n_main ? refined_node(axis, b.refine, i) : 0.;
 		}
 		if(tid == 0) sm.tail.S = has_tail ? refined_node(axis, b.refine, N - 1) : 0.;
-		for(int k = tid; k < NF / 2; k += P) {
+		for(int k = tid; k <= NH / 2; k += P) {
 			double sn, cs;
 			sincospi(-2. * (double)k / (double)NF, &sn, &cs);
-			sm_tw[pad_tw(k)] = make_double2(cs, sn);
+			sm_tq[k] = make_double2(cs, sn);
+			if(k < NH / 2) {
+				sincospi(-2. * (double)k / (double)NH, &sn, &cs);
+				sm_tw[pad_tw(k)] = make_double2(cs, sn);
+			}
 		}
 	}
 	__syncthreads();
@@ -246,18 +292,19 @@ k_jump_sweep(DeviceBatch b, JumpWork work, DeviceResult out) {
 		for(int i = tid; i < N; i += P) {
 			int idx = 0; double w = 1.;
 			if(i > 0 && i < N - 1) interp_data(tick, NF, log(S_at(i)), idx, w);
-			n_idx[i] = pad_buf(bitrev(idx, logNF)) | (pad_buf(bitrev(idx + 1, logNF)) << 16);   // slots of h_idx, h_idx+1 in sm_buf
+			// h_k is the real (k even) or imaginary (k odd) part of element bitrev(k / 2) of sm_buf:
+			// slots in sm_buf viewed as doubles, for idx and idx + 1
+			n_idx[i] = (2 * pad_buf(bitrev(idx >> 1, logNH)) + (idx & 1))
+				| ((2 * pad_buf(bitrev((idx + 1) >> 1, logNH)) + ((idx + 1) & 1)) << 16);
 			n_w[i] = i > 0 && i < N - 1 ? w : 0.;                     // rows 0 and N - 1 have b = 0
 		}
 		// (c) spectrum of the density weights (computeDensityFFT, :326-328)
 		const double *wts = b.jump_weights + (size_t)cidx * b.jump_weights_stride;
-		for(int k = tid; k < NF; k += P) sm_buf[pad_buf(bitrev(k, logNF))] = make_double2(wts[k], 0.);
+		for(int m = tid; m < NH; m += P) sm_buf[pad_buf(bitrev(m, logNH))] = make_double2(wts[2 * m], wts[2 * m + 1]);
 	}
 	__syncthreads();
-	fft_forward_dit<PT>(sm_buf, sm_tw, NF, logNF, tid);
-	for(int k = tid; k < NF; k += P) fw[k] = sm_buf[pad_buf(k)];
-	__threadfence_block();
-	__syncthreads();
+	fft_forward_dit<PT>(sm_buf, sm_tw, NH, logNH, tid);
+	spectral_pass<PT, true>(sm_buf, sm_tq, sm_F, NH, tid);     // ends with a barrier
 
 	// ---- per-thread state ------------------------------------------------
 	double x[M], vprev[BDF2 ? M : 1];
@@ -317,35 +364,27 @@ k_jump_sweep(DeviceBatch b, JumpWork work, DeviceResult out) {
 		for(int j = 0; j < M; ++j) sm_V[j * P + tid] = x[j];
 		if(tail_owner) sm_V[MP] = sm.tail.x;
 		__syncthreads();
-		// the table loads of four points are issued together (latency of L2, not of four round trips)
-		for(int k0 = tid; k0 < NF; k0 += 4 * P) {
-			int slots[4]; double wk[4];
+		// two real points per complex element; the table loads of two elements are issued together
+		for(int m0 = tid; m0 < NH; m0 += 2 * P) {
+			int2 slots[2]; double2 wk[2];
 #pragma unroll
-			for(int u = 0; u < 4; ++u) {
-				const int k = k0 + u * P < NF ? k0 + u * P : k0;
-				slots[u] = g_idx[k]; wk[u] = g_w[k];
+			for(int u = 0; u < 2; ++u) {
+				const int m = m0 + u * P < NH ? m0 + u * P : m0;
+				slots[u] = reinterpret_cast<const int2 *>(g_idx)[m];
+				wk[u] = reinterpret_cast<const double2 *>(g_w)[m];
 			}
 #pragma unroll
-			for(int u = 0; u < 4; ++u) {
-				const int k = k0 + u * P;
-				const double vb = interp_apply(wk[u], sm_V[slots[u] & 0xffff], sm_V[slots[u] >> 16]);
-				if(k < NF) sm_buf[pad_buf(bitrev(k, logNF))] = make_double2(vb, 0.);
-			}
-		}
-		__syncthreads();
-		// ---- (2) correlation: inv( fwd(Vbar) * conj(fwd(weights)) ) --------
-		fft_forward_dit<PT>(sm_buf, sm_tw, NF, logNF, tid);
-		for(int k0 = tid; k0 < NF; k0 += 4 * P) {
-			double2 f[4];
-#pragma unroll
-			for(int u = 0; u < 4; ++u) f[u] = fw[k0 + u * P < NF ? k0 + u * P : k0];
-#pragma unroll
-			for(int u = 0; u < 4; ++u) {
-				const int k = k0 + u * P;
-				if(k < NF) sm_buf[pad_buf(k)] = cmul(sm_buf[pad_buf(k)], make_double2(f[u].x, -f[u].y));
+			for(int u = 0; u < 2; ++u) {
+				const int m = m0 + u * P;
+				const double v0 = interp_apply(wk[u].x, sm_V[slots[u].x & 0xffff], sm_V[slots[u].x >> 16]);
+				const double v1 = interp_apply(wk[u].y, sm_V[slots[u].y & 0xffff], sm_V[slots[u].y >> 16]);
+				if(m < NH) sm_buf[pad_buf(bitrev(m, logNH))] = make_double2(v0, v1);
 			}
 		}
 		__syncthreads();
+		// ---- (2) correlation: inv( fwd(Vbar) * conj(fwd(weights)) ), real data on half-size transforms
+		fft_forward_dit<PT>(sm_buf, sm_tw, NH, logNH, tid);
+		spectral_pass<PT, false>(sm_buf, sm_tq, sm_F, NH, tid);    // ends with a barrier
 		// the read-out table of step (3): loaded here so that the inverse transform hides the latency
 		int nslot[M]; double nw[M];
 #pragma unroll
@@ -353,8 +392,9 @@ k_jump_sweep(DeviceBatch b, JumpWork work, DeviceResult out) {
 			const int i = i0 + j < N ? i0 + j : 0;
 			nslot[j] = n_idx[i]; nw[j] = n_w[i];
 		}
-		fft_inverse_dif<PT>(sm_buf, sm_tw, NF, logNF, tid);
-		// sm_buf[bitrev(k)].x / NF = h_k
+		fft_inverse_dif<PT>(sm_buf, sm_tw, NH, logNH, tid);
+		// h_k / NF: real / imaginary part of element bitrev(k / 2)
+		const double *const sm_h = reinterpret_cast<const double *>(sm_buf);
 		const double inv_nf = 1. / (double)NF;
 		// ---- (3) right-hand side: BDF b() with the explicit jump term ------
 		double r[M];
@@ -363,8 +403,8 @@ k_jump_sweep(DeviceBatch b, JumpWork work, DeviceResult out) {
 			const int i = i0 + j;
 			// no predicate across the loads: rows without a jump term have weight and slots 0
 			const int slots = nslot[j];
-			const double hA = sm_buf[slots & 0xffff].x * inv_nf;
-			const double hB = sm_buf[slots >> 16].x * inv_nf;
+			const double hA = sm_h[slots & 0xffff] * inv_nf;
+			const double hB = sm_h[slots >> 16] * inv_nf;
 			const double bj = i > 0 && i < N - 1 && i < n_main ? lambda * interp_apply(nw[j], hA, hB) : 0.;
 			if(kind == STEP_IMPLICIT) r[j] = x[j] + h0 * bj;                                   // BDF.hpp:40-46
 			else r[j] = (div_by(c1 * x[j] - c0 * vprev[BDF2 ? j : 0], den, rden) + bj) * g.h;             // BDF.hpp:94-110

@@ -64,7 +64,6 @@ void launch_interleaved(const DeviceBatch &b, const InterleavedWork &w,
 struct JumpWork {
 	int *g_idx; double *g_w;      // [C][n_fft]: V(exp(x0 + k dx)) = w V[idx] + (1 - w) V[idx + 1]
 	int *n_idx; double *n_w;      // [C][N]:     h(log S_i)       = w h[idx] + (1 - w) h[idx + 1]
-	double2 *fw;                  // [C][n_fft]: FFT of the density weights
 };
 bool jump_supported(const DeviceBatch &b);
 int launch_jump(const DeviceBatch &b, const JumpWork &w, const DeviceResult &out,
