@@ -204,6 +204,31 @@ def test_one_shot_sweep_host_buffers(qpde, handle, oracle):
     assert res.S is None and res.active is None
 
 
+def test_one_shot_sweep_of_a_large_batch_matches_the_plan(qpde, handle, oracle):
+    """qpde_bs1d_sweep on a batch of many waves (5,000 contracts on 148 SMs): every output equals
+    the plan path bit for bit, also into strided host buffers."""
+    Cn = 5000
+    rng = np.random.default_rng(7)
+    K = rng.uniform(50., 150., Cn); vol = rng.uniform(.1, .6, Cn); T = rng.uniform(.25, 2., Cn)
+    r = rng.uniform(.01, .08, Cn)
+    special = oracle.special_axis()
+    spec = qpde.BatchSpec(axis=K[:, None] * special[None, :], refine=1, r=r, sigma=vol, q=0., T=T,
+                          dt=T / 20, strike=K, american=True, payoff="put", kernel="resident")
+    with qpde.Plan(handle, spec) as plan:
+        plan.run()
+        ref = plan.fetch()
+    res = qpde.sweep(handle, spec)
+    for name in ("V", "S", "value", "n_steps", "inner_total", "active", "status"):
+        assert np.array_equal(getattr(res, name), getattr(ref, name)), name
+    w = min(res.inner.shape[1], ref.inner.shape[1])
+    assert np.array_equal(res.inner[:, :w], ref.inner[:, :w]) and np.all(ref.n_steps <= w)
+    # strided host buffers (a wider V row than N)
+    wide = qpde.ResultBuffers(Cn, spec.N + 5, qpde.sweep_max_steps(spec), qpde.OUT_V | qpde.OUT_VALUE)
+    wide.struct.V_stride = spec.N + 5
+    qpde.sweep(handle, spec, result=wide)
+    assert np.array_equal(wide.V[:, :spec.N], ref.V) and np.array_equal(wide.value, ref.value)
+
+
 def test_payoff_and_sigma_arrays(qpde, handle, oracle):
     """explicit [C][N] initial condition / obstacle / per-node volatility."""
     K, refine, steps = 100., 2, 80
