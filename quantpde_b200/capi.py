@@ -104,7 +104,7 @@ EXPORTS = [
     "qpde_synchronize", "qpde_launch_count", "qpde_sm_count", "qpde_host_alloc",
     "qpde_host_free", "qpde_make_schedule", "qpde_refined_size", "qpde_bs1d_sweep",
     "qpde_bs1d_plan_create", "qpde_bs1d_plan_run", "qpde_bs1d_plan_fetch",
-    "qpde_bs1d_plan_destroy", "qpde_bs1d_plan_kernel", "qpde_bs1d_plan_nodes",
+    "qpde_bs1d_plan_destroy", "qpde_bs1d_plan_kernel", "qpde_bs1d_plan_nodes", "qpde_bs1d_plan_tma_staged",
     "qpde_bs1d_plan_max_steps", "qpde_jump_nfft", "qpde_jump_setup", "qpde_refine_axis",
     "qpde_gmwb2d_nodes", "qpde_gmwb2d_solve", "qpde_gmwb2d_shard_create", "qpde_gmwb2d_shard_destroy",
     "qpde_gmwb2d_shard_exit", "qpde_gmwb2d_shard_policy", "qpde_gmwb2d_shard_sweep", "qpde_gmwb2d_shard_relerr",
@@ -150,6 +150,7 @@ def lib():
         L.qpde_bs1d_plan_destroy.argtypes = [C.c_void_p]
         L.qpde_bs1d_plan_kernel.argtypes = [C.c_void_p]
         L.qpde_bs1d_plan_nodes.argtypes = [C.c_void_p]
+        L.qpde_bs1d_plan_tma_staged.argtypes = [C.c_void_p]
         L.qpde_bs1d_plan_max_steps.argtypes = [C.c_void_p]
         L.qpde_jump_nfft.argtypes = [C.c_int]
         L.qpde_jump_setup.argtypes = [C.c_int, _dp, C.c_int, _dp, _dp, _dp, _dp, _dp]
@@ -479,6 +480,7 @@ class Plan:
         self.N = lib().qpde_bs1d_plan_nodes(self.ptr)
         self.max_steps = lib().qpde_bs1d_plan_max_steps(self.ptr)
         self.kernel = KERNEL_NAME[lib().qpde_bs1d_plan_kernel(self.ptr)]
+        self.tma_staged = bool(lib().qpde_bs1d_plan_tma_staged(self.ptr))
 
     def run(self):
         check(lib().qpde_bs1d_plan_run(self.ptr), self.handle.ptr)

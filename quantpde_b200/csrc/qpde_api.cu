@@ -4,6 +4,7 @@
 // sm_100 device qpde_create() fails with QPDE_ERR_NO_DEVICE.
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <algorithm>
 #include <mutex>
@@ -39,6 +40,8 @@ struct qpde_bs1d_plan {
 	DeviceBatch b;
 	DeviceResult out;
 	InterleavedWork w;
+	InterleavedTma tma;
+	double *wblock;   // the one allocation behind the INTERLEAVED arrays when the TMA-staged sweep is used
 	JumpWork jw;
 	bool jump;
 	int kernel;
@@ -253,6 +256,7 @@ int qpde_bs1d_plan_destroy(qpde_bs1d_plan *p) {
 
 int qpde_bs1d_plan_kernel(const qpde_bs1d_plan *p) { return p ? p->kernel : QPDE_ERR_INVALID; }
 int qpde_bs1d_plan_nodes(const qpde_bs1d_plan *p) { return p ? p->b.N : QPDE_ERR_INVALID; }
+int qpde_bs1d_plan_tma_staged(const qpde_bs1d_plan *p) { return p ? (p->kernel == QPDE_KERNEL_INTERLEAVED && p->tma.enabled ? 1 : 0) : QPDE_ERR_INVALID; }
 
 static int plan_create_impl(qpde_handle *h, const qpde_bs1d_batch *in,
 		int outputs, qpde_bs1d_plan **out) {
@@ -454,17 +458,42 @@ static int plan_create_impl(qpde_handle *h, const qpde_bs1d_batch *in,
 	p->kernel = kernel;
 
 	if(kernel == QPDE_KERNEL_INTERLEAVED) {
-		const size_t NC = (size_t)N * C;
 		InterleavedWork &w = p->w;
+		w.ld = ((long long)C + 31) / 32 * 32;                 // a warp of contracts per 256-byte row segment
+		const size_t NC = (size_t)N * (size_t)w.ld;
 		const size_t sets = b.n_controls > 0 ? (size_t)b.n_controls : 1;   // operator rows per control value
-		QPDE_TRY(dev_alloc(p, &w.S, NC));  QPDE_TRY(dev_alloc(p, &w.lo, NC * sets));
-		QPDE_TRY(dev_alloc(p, &w.di, NC * sets)); QPDE_TRY(dev_alloc(p, &w.up, NC * sets));
-		QPDE_TRY(dev_alloc(p, &w.x, NC));  QPDE_TRY(dev_alloc(p, &w.lb, NC));
-		QPDE_TRY(dev_alloc(p, &w.cp, NC)); QPDE_TRY(dev_alloc(p, &w.dp, NC));
-		if(b.scheme == QPDE_SCHEME_BDF2 || b.variable_target) QPDE_TRY(dev_alloc(p, &w.xprev, NC));
-		else w.xprev = w.x;
-		if(b.american) QPDE_TRY(dev_alloc(p, &w.obst, NC));
-		if(b.n_exercise > 0 && b.exercise_kind != QPDE_EXERCISE_NONE) QPDE_TRY(dev_alloc(p, &w.evobst, NC));
+		const bool need_xprev = b.scheme == QPDE_SCHEME_BDF2 || b.variable_target;
+		const bool need_evobst = b.n_exercise > 0 && b.exercise_kind != QPDE_EXERCISE_NONE;
+		p->tma.enabled = false;
+		p->wblock = nullptr;
+		const char *no_tma = getenv("QPDE_INTERLEAVED_NO_TMA");  // tuning / A-B switch: the plain-load sweep
+		if(interleaved_tma_supported(b) && !(no_tma && no_tma[0] == '1')) {
+			// one block, arrays stacked: a single tensor map over [rows][32] serves every array
+			const size_t arrays = 8 + (need_xprev ? 1 : 0) + (b.american ? 1 : 0) + (need_evobst ? 1 : 0);
+			QPDE_TRY(dev_alloc(p, &p->wblock, NC * arrays));
+			double *at = p->wblock;
+			auto take = [&](double **ptr) { *ptr = at; at += NC; };
+			take(&w.S); take(&w.lo); take(&w.di); take(&w.up); take(&w.x); take(&w.lb); take(&w.cp); take(&w.dp);
+			if(need_xprev) take(&w.xprev); else w.xprev = w.x;
+			if(b.american) take(&w.obst);
+			if(need_evobst) take(&w.evobst);
+			// lanes past C in the last warp of contracts are loaded (never stored): keep them finite
+			QPDE_CUDA(h, cudaMemsetAsync(p->wblock, 0, NC * arrays * sizeof(double), h->stream));
+			std::string err;
+			if(!interleaved_tma_prepare(&p->tma, p->wblock, (long long)(arrays * NC / QPDE_WARP_ROW), &err)) {
+				qpde_bs1d_plan_destroy(p);
+				return fail(h, QPDE_ERR_CUDA, "INTERLEAVED (TMA): %s", err.c_str());
+			}
+		} else {
+			QPDE_TRY(dev_alloc(p, &w.S, NC));  QPDE_TRY(dev_alloc(p, &w.lo, NC * sets));
+			QPDE_TRY(dev_alloc(p, &w.di, NC * sets)); QPDE_TRY(dev_alloc(p, &w.up, NC * sets));
+			QPDE_TRY(dev_alloc(p, &w.x, NC));  QPDE_TRY(dev_alloc(p, &w.lb, NC));
+			QPDE_TRY(dev_alloc(p, &w.cp, NC)); QPDE_TRY(dev_alloc(p, &w.dp, NC));
+			if(need_xprev) QPDE_TRY(dev_alloc(p, &w.xprev, NC));
+			else w.xprev = w.x;
+			if(b.american) QPDE_TRY(dev_alloc(p, &w.obst, NC));
+			if(need_evobst) QPDE_TRY(dev_alloc(p, &w.evobst, NC));
+		}
 	}
 #undef QPDE_TRY
 	*out = p;
@@ -484,7 +513,8 @@ int qpde_bs1d_plan_run(qpde_bs1d_plan *p) {
 		int rc = launch_jump(p->b, p->jw, p->out, h->stream, &h->launches);
 		if(rc != QPDE_OK) return fail(h, rc, "launch_jump failed");
 	} else if(p->kernel == QPDE_KERNEL_INTERLEAVED) {
-		launch_interleaved(p->b, p->w, p->out, h->stream, &h->launches);
+		if(p->tma.enabled) launch_interleaved_tma(p->b, p->w, p->tma, p->wblock, p->out, h->stream, &h->launches);
+		else launch_interleaved(p->b, p->w, p->out, h->stream, &h->launches);
 	} else {
 		int rc = launch_resident(p->b, p->out, h->stream, h->sm_count, &h->launches);
 		if(rc != QPDE_OK) return fail(h, rc, "launch_resident failed");

@@ -1,6 +1,8 @@
 // qpde_interleaved.cu — kernel family "INTERLEAVED": one thread per contract,
-// every per-node array stored node-major / contract-minor ([N][C]) in HBM so
-// that the 32 lanes of a warp touch 32 consecutive doubles at every node.
+// every per-node array stored as [C / 32][N][32] in HBM (node-major inside a
+// block of 32 contracts): the 32 lanes of a warp touch 32 consecutive doubles
+// at every node, and the rows a warp walks are one sequential stream per array
+// (a [N][C] layout made every 256-byte row segment its own DRAM page visit).
 // The whole sweep (all time steps, all penalty iterations) is one launch;
 // nothing returns to the host in between.
 //
@@ -33,7 +35,9 @@ __global__ void k_interleaved_setup(DeviceBatch b, InterleavedWork w) {
 	const int c = blockIdx.x * blockDim.x + threadIdx.x;
 	if(c >= b.C) return;
 	const int N = b.N;
-	const size_t C = (size_t)b.C;
+	constexpr size_t C = QPDE_WARP_ROW;                       // row stride inside a warp's block of contracts
+	const size_t base = interleaved_base(c, N);               // [C / 32][N][32] layout
+	const size_t NC = (size_t)N * (size_t)w.ld;               // one array
 	const double *axis = b.axis + (size_t)c * b.axis_stride;
 	const double K = b.strike[c];
 	const double r = b.r[c], q = b.q[c], sig = b.sigma[c];
@@ -41,7 +45,7 @@ __global__ void k_interleaved_setup(DeviceBatch b, InterleavedWork w) {
 	double Sm = 0., Si = refined_node(axis, b.refine, 0);
 	double Sp = N > 1 ? refined_node(axis, b.refine, 1) : Si;
 	for(int i = 0; i < N; ++i) {
-		const size_t at = (size_t)i * C + c;
+		const size_t at = (size_t)i * C + base;
 		const double v_i = b.vol_model == QPDE_VOL_NODES
 			? b.sigma_nodes[(size_t)c * b.sigma_nodes_stride + i]
 			: vol_value(b.vol_model, sig, Si);
@@ -51,7 +55,7 @@ __global__ void k_interleaved_setup(DeviceBatch b, InterleavedWork w) {
 			for(int k = 0; k < b.n_controls; ++k) {
 				const double rk = b.controls[(size_t)c * b.controls_stride + k];
 				const Row row = bs_row(i, N, Sm, Si, Sp, rk, v_i, q);
-				const size_t ak = ((size_t)k * N + i) * C + c;
+				const size_t ak = (size_t)k * NC + at;
 				w.lo[ak] = row.lo; w.di[ak] = row.di; w.up[ak] = row.up;
 			}
 		} else {
@@ -80,18 +84,19 @@ k_interleaved_sweep(DeviceBatch b, InterleavedWork w, DeviceResult out) {
 	const int c = blockIdx.x * blockDim.x + threadIdx.x;
 	if(c >= b.C) return;
 	const int N = b.N;
-	const size_t C = (size_t)b.C;
+	constexpr size_t C = QPDE_WARP_ROW;                       // row stride inside a warp's block of contracts
+	const size_t base = interleaved_base(c, N);               // [C / 32][N][32] layout
 	const double tol = b.tolerance, scale = b.scale;
 	const double pen = 1. / b.penalty_tolerance; // PenaltyMethod.hpp:85
-	const double *lo = w.lo + c, *di = w.di + c, *up = w.up + c;
-	double *x = w.x + c, *xp = w.xprev + c, *lb = w.lb + c;
-	double *cp = w.cp + c, *dp = w.dp + c;
-	const double *ob = w.obst ? w.obst + c : nullptr;
-	const double *evob = w.evobst ? w.evobst + c : nullptr;
+	const double *lo = w.lo + base, *di = w.di + base, *up = w.up + base;
+	double *x = w.x + base, *xp = w.xprev + base, *lb = w.lb + base;
+	double *cp = w.cp + base, *dp = w.dp + base;
+	const double *ob = w.obst ? w.obst + base : nullptr;
+	const double *evob = w.evobst ? w.evobst + base : nullptr;
 
 	const bool policy = b.n_controls > 0;
 	const bool iterate = b.american || policy;   // a ToleranceIteration wraps every step
-	const size_t NC = (size_t)N * C;
+	const size_t NC = (size_t)N * (size_t)w.ld;               // one array (one set of operator rows)
 	Replay rp; rp.start(b.T[c], b.dt[c], b.n_exercise);
 	NodeState ns; ns.start(b.scheme);
 	double time1 = rp.T, time0 = rp.T; // times of iterand(0), iterand(1)
@@ -309,7 +314,7 @@ k_interleaved_sweep(DeviceBatch b, InterleavedWork w, DeviceResult out) {
 						// 331-374).  The shifted price never exceeds S_i, so the nodes are updated in
 						// place from the top down, and the bracketing interval only moves down.
 						const double D = b.dividend[c];
-						const double *S = w.S + c;
+						const double *S = w.S + base;
 						const double Sfirst = S[0], Slast = S[(size_t)(N - 1) * C];
 						int idx = N - 2;
 						for(int i = N - 1; i >= 0; --i) {
@@ -344,7 +349,7 @@ k_interleaved_sweep(DeviceBatch b, InterleavedWork w, DeviceResult out) {
 
 	// ---- outputs (contract-major) ------------------------------------------
 	if(out.V) for(int i = 0; i < N; ++i) out.V[(size_t)c * out.V_stride + i] = x[(size_t)i * C];
-	if(out.S) for(int i = 0; i < N; ++i) out.S[(size_t)c * out.S_stride + i] = w.S[(size_t)i * C + c];
+	if(out.S) for(int i = 0; i < N; ++i) out.S[(size_t)c * out.S_stride + i] = w.S[(size_t)i * C + base];
 	if(out.active) {
 		for(int i = 0; i < N; ++i) {
 			const double pred = ob ? (0. + 1. * x[(size_t)i * C]) - ob[(size_t)i * C] : 0.;
@@ -353,7 +358,7 @@ k_interleaved_sweep(DeviceBatch b, InterleavedWork w, DeviceResult out) {
 	}
 	if(out.value) {
 		// PiecewiseLinear::interpolate (Core/Interpolant.hpp:153-181,331-374)
-		const double *S = w.S + c;
+		const double *S = w.S + base;
 		const double s0 = b.spot ? b.spot[c] : b.strike[c];
 		int idx; double wgt;
 		if(s0 <= S[0]) { idx = 0; wgt = 1.; }
@@ -382,14 +387,21 @@ k_interleaved_sweep(DeviceBatch b, InterleavedWork w, DeviceResult out) {
 	if(out.status) out.status[c] = status;
 }
 
+void launch_interleaved_setup(const DeviceBatch &b, const InterleavedWork &w, cudaStream_t stream, long long *launches) {
+	const int threads = b.C >= 148 * 512 ? 128 : (b.C >= 148 * 128 ? 64 : 32);
+	const int blocks = (b.C + threads - 1) / threads;
+	k_interleaved_setup<<<blocks, threads, 0, stream>>>(b, w);
+	*launches += 1;
+}
+
 void launch_interleaved(const DeviceBatch &b, const InterleavedWork &w,
 		const DeviceResult &out, cudaStream_t stream, long long *launches) {
 	// small CTAs: a batch of a few thousand contracts still reaches every SM
 	const int threads = b.C >= 148 * 512 ? 128 : (b.C >= 148 * 128 ? 64 : 32);
 	const int blocks = (b.C + threads - 1) / threads;
-	k_interleaved_setup<<<blocks, threads, 0, stream>>>(b, w);
+	launch_interleaved_setup(b, w, stream, launches);
 	k_interleaved_sweep<<<blocks, threads, 0, stream>>>(b, w, out);
-	*launches += 2;
+	*launches += 1;
 }
 
 } // namespace qpde

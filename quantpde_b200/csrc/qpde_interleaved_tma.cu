@@ -1,0 +1,467 @@
+// qpde_interleaved_tma.cu — the INTERLEAVED family with its HBM streams staged by TMA.
+//
+// Same algorithm, same arithmetic and same [C / 32][N][32] workspace as qpde_interleaved.cu (one
+// thread per contract, Thomas elimination, the whole sweep in one launch), i.e. the same
+// replacement of the reference call stack
+//   TimeIteration<false>::iterateUntilDone     Core/IterativeMethod.hpp:1163-1204,1259-1317
+//   ToleranceIteration + relativeError         Core/IterativeMethod.hpp:1125-1137,1211-1254
+//   PenaltyMethodDifference::onIterationStart  Core/PenaltyMethod.hpp:37-69,96-119
+//   Rannacher / CrankNicolson / BDFOne / BDFTwo A(), b()
+//   SparseLUSolver::initialize/solve           Bindings/Eigen.hpp:143-165
+// What changes is how the rows reach the serial chain.  A thread that loads its own rows
+// pays the HBM latency once per block of rows and needs registers for everything in
+// flight; here a warp of 32 contracts owns a ring of shared-memory stages that the TMA
+// unit fills with tiles of 32 contracts x 4 node rows per array (1 KB, contiguous; one
+// cp.async.bulk.tensor per array and tile, issued by lane 0, completion on an mbarrier),
+// so that `stages` tiles are in flight per warp while the chain runs, at no register
+// cost.  All control flow that surrounds a tile is warp-uniform (votes); what differs
+// per contract (step kind, number of penalty iterations, number of steps) is a
+// predicate on the stores.
+//
+// Passes per time step: right-hand side (reads x [+ xprev | lo, di, up], writes lb
+// [+ xprev]), then per penalty iteration a forward elimination (reads lo, di, up, lb
+// [+ obstacle, x], writes cp, dp) and a back substitution (reads cp, dp [+ x], writes x).
+// Results written with ordinary stores are read by later TMA loads: every pass starts
+// with a device-scope fence + fence.proxy.async.
+#include <cuda.h>
+#include <math_constants.h>
+
+#include <cstdlib>
+
+#include "qpde_kernels.cuh"
+#include "qpde_partition.cuh"   // rcp()
+
+namespace qpde {
+
+namespace {
+
+constexpr int TR = QPDE_TMA_TILE_ROWS;
+constexpr int SLOT_DOUBLES = TR * 32;            // one array's tile: TR rows x 32 contracts
+constexpr int MAX_SLOTS = 6;
+constexpr int STAGE_DOUBLES = MAX_SLOTS * SLOT_DOUBLES;
+constexpr int STAGE_BYTES = STAGE_DOUBLES * 8;   // 6 KB
+constexpr unsigned FULL = 0xffffffffu;
+
+// rows of the arrays inside the workspace block (tensor-map coordinates)
+struct TmaRows { int lo, di, up, x, xp, lb, cp, dp, ob; };
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, int count) {
+	asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(bar), "r"(count) : "memory");
+}
+
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+	asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(bytes) : "memory");
+}
+
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+	uint32_t done;
+	do {
+		asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+			: "=r"(done) : "r"(bar), "r"(parity) : "memory");
+	} while(!done);
+}
+
+// one tile: box {32 contracts, TR rows} at row `row` of the workspace block seen as [rows][32]
+__device__ __forceinline__ void tma_tile(uint32_t dst, const CUtensorMap *map, int row, uint32_t bar) {
+	asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+		:: "r"(dst), "l"((unsigned long long)map), "r"(0), "r"(row), "r"(bar) : "memory");
+}
+
+// The ring of one warp.  Every pass issues and consumes the same number of tiles, in the
+// same order, so one stage cursor per side and one parity bit per stage are all the state.
+struct Ring {
+	uint32_t data, bars;   // shared-memory addresses of stage 0 / barrier 0
+	int ns;                // stages
+	int is, cs;            // stage of the next issue / of the next wait
+	uint32_t parity;       // bit s: parity the next wait on stage s looks for
+};
+
+// Issues one tile per array named in `arow` (slots 0 .. NA-1; a negative row = slot unused).
+template <int NA>
+__device__ __forceinline__ void ring_issue(Ring &r, const CUtensorMap *map, int blk0, const int (&arow)[NA], int row, int lane) {
+	if(lane == 0) {
+		const uint32_t bar = r.bars + 8u * r.is;
+		const uint32_t dst = r.data + (uint32_t)STAGE_BYTES * r.is;
+		int used = 0;
+#pragma unroll
+		for(int a = 0; a < NA; ++a) used += arow[a] >= 0 ? 1 : 0;
+		mbar_expect_tx(bar, (uint32_t)(used * SLOT_DOUBLES * 8));
+#pragma unroll
+		for(int a = 0; a < NA; ++a) {
+			if(arow[a] >= 0) tma_tile(dst + (uint32_t)(a * SLOT_DOUBLES * 8), map, arow[a] + blk0 + row, bar);
+		}
+	}
+	r.is = r.is + 1 == r.ns ? 0 : r.is + 1;
+}
+
+// Waits for the next tile; returns its stage.
+__device__ __forceinline__ int ring_wait(Ring &r) {
+	const int s = r.cs;
+	mbar_wait(r.bars + 8u * s, (r.parity >> s) & 1u);
+	r.parity ^= 1u << s;
+	r.cs = s + 1 == r.ns ? 0 : s + 1;
+	return s;
+}
+
+// Ordinary stores of this warp (and of earlier kernels) become visible to the TMA loads
+// that follow.
+__device__ __forceinline__ void pass_begin() {
+	__threadfence();
+	asm volatile("fence.proxy.async;" ::: "memory");
+	__syncwarp();
+}
+
+__global__ void __launch_bounds__(32)
+k_interleaved_sweep_tma(const __grid_constant__ CUtensorMap map, DeviceBatch b, InterleavedWork w, DeviceResult out,
+		TmaRows tr, int stages) {
+	extern __shared__ __align__(128) unsigned char smem_raw[];
+	const int lane = threadIdx.x;
+	const int c = blockIdx.x * 32 + lane;
+	const int blk0 = blockIdx.x * b.N;        // first tensor-map row of this warp's block of contracts inside an array
+	const bool valid = c < b.C;
+	const int cc = valid ? c : b.C - 1;       // lanes past the batch read a real contract's parameters and store nothing
+	const int N = b.N;
+	constexpr size_t ld = QPDE_WARP_ROW;      // row stride inside the block ([C / 32][N][32] layout)
+	const size_t base = interleaved_base(c, N);
+	const double tol = b.tolerance, scale = b.scale;
+	const double pen = 1. / b.penalty_tolerance; // PenaltyMethod.hpp:85
+	double *x = w.x + base, *xp = w.xprev + base, *lb = w.lb + base;
+	double *cp = w.cp + base, *dp = w.dp + base;
+	const double *ob = w.obst ? w.obst + base : nullptr;
+	const double *evob = w.evobst ? w.evobst + base : nullptr;
+	const double *sm = reinterpret_cast<const double *>(smem_raw) + lane;
+
+	Ring ring;
+	ring.data = smem_u32(smem_raw);
+	ring.bars = ring.data + (uint32_t)(STAGE_BYTES * stages);
+	ring.ns = stages; ring.is = 0; ring.cs = 0; ring.parity = 0u;
+	if(lane == 0) {
+		for(int s = 0; s < stages; ++s) mbar_init(ring.bars + 8u * s, 1);
+		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+	}
+	__syncwarp();
+
+	const bool american = b.american != 0;
+	const bool iterate = american;               // a ToleranceIteration wraps every step
+	const bool copy_xp = b.scheme == QPDE_SCHEME_BDF2;
+	const int nb = (N + TR - 1) / TR;            // tiles per pass
+	const int lead = nb < stages ? nb : stages;
+
+	Replay rp; rp.start(b.T[cc], b.dt[cc], b.n_exercise);
+	NodeState ns; ns.start(b.scheme);
+	double time1 = rp.T, time0 = rp.T; // times of iterand(0), iterand(1)
+	Gamma gA; gA.kind = STEP_IMPLICIT; gA.h = 0.; // what the factorised A was built with
+	int n_steps = 0, inner_total = 0, status = 0;
+	bool more = valid;
+
+	while(__any_sync(FULL, more)) {
+		const bool act = more;                   // this contract takes a step in this trip
+		qpde_step st; st.t = 0.; st.dt = 0.; st.same_dt = 0; st.event_after = 0; st.user_events = 0; st.reserved = 0;
+		int kind = STEP_IMPLICIT;
+		double t = 0., h0 = 0., c1 = 0., c0 = 0., den = 1.;
+		Gamma gb; gb.kind = STEP_IMPLICIT; gb.h = 0.;
+		if(act) {
+			more = rp.next(st);
+			t = st.t;
+			kind = ns.kind();
+			h0 = time1 - t;
+			gb.kind = kind; gb.h = h0;
+			if(kind == STEP_BDF2) {
+				const double h1 = time1 - t, hh0 = time0 - t;     // BDF.hpp:68-73
+				gb.h = (hh0 * h1) / (hh0 + h1);
+				c1 = hh0 / h1; c0 = h1 / hh0; den = hh0 - h1;
+			}
+			// IterativeMethod.hpp:906: re-assemble A unless the root says it is the same
+			// (a penalty node in the tree keeps LinearSystem's default: never)
+			if(iterate || !ns.initialized || !ns.a_same(st.same_dt)) gA = gb;
+		}
+		const double rden = 1. / den;
+		const bool is_cn = kind == STEP_CN_R || kind == STEP_CN_T;
+
+		// ---- lb = root.b(t) of the discretisation node; iterand(1) <- iterand(0) for BDF2 ----
+		{
+			const bool any_cn = __any_sync(FULL, act && is_cn);
+			const bool any_b2 = __any_sync(FULL, act && kind == STEP_BDF2);
+			const int arow[5] = { tr.x, any_b2 ? tr.xp : -1, any_cn ? tr.lo : -1, any_cn ? tr.di : -1, any_cn ? tr.up : -1 };
+			pass_begin();
+			for(int j = 0; j < lead; ++j) ring_issue(ring, &map, blk0, arow, j * TR, lane);
+			// row i is finished when x[i + 1] arrives: one row of delay
+			double xm = 0., xc = 0., pxp = 0., plo = 0., pdi = 0., pup = 0.;
+			auto emit = [&](int i, double vp) {
+				double val;
+				if(kind == STEP_IMPLICIT) {
+					val = xc + 0. * h0;
+				} else if(kind == STEP_BDF2) {
+					val = (div_by(c1 * xc - c0 * pxp, den, rden) + 0.) * gb.h;
+				} else {
+					// (I - A h/2) v0, row-major SpMV from zero in column order
+					double acc = 0.;
+					if(i > 0) acc += (0. - gb.off(plo)) * xm;
+					acc += (1. - gb.off(pdi)) * xc;
+					if(i < N - 1) acc += (0. - gb.off(pup)) * vp;
+					val = acc + 0.;
+				}
+				if(act) {
+					lb[(size_t)i * ld] = val;
+					if(copy_xp) xp[(size_t)i * ld] = xc;
+				}
+			};
+			for(int j = 0; j < nb; ++j) {
+				const int s = ring_wait(ring);
+				const double *tile = sm + s * STAGE_DOUBLES;
+				double vx[TR], vxp[TR], vlo[TR], vdi[TR], vup[TR];
+#pragma unroll
+				for(int u = 0; u < TR; ++u) {
+					vx[u] = tile[u * 32];
+					vxp[u] = any_b2 ? tile[SLOT_DOUBLES + u * 32] : 0.;
+					vlo[u] = any_cn ? tile[2 * SLOT_DOUBLES + u * 32] : 0.;
+					vdi[u] = any_cn ? tile[3 * SLOT_DOUBLES + u * 32] : 0.;
+					vup[u] = any_cn ? tile[4 * SLOT_DOUBLES + u * 32] : 0.;
+				}
+				__syncwarp();
+				if(j + stages < nb) ring_issue(ring, &map, blk0, arow, (j + stages) * TR, lane);
+#pragma unroll
+				for(int u = 0; u < TR; ++u) {
+					const int i = j * TR + u;
+					if(i >= 1 && i <= N) emit(i - 1, vx[u]);
+					xm = xc; xc = vx[u]; pxp = vxp[u]; plo = vlo[u]; pdi = vdi[u]; pup = vup[u];
+				}
+			}
+			if(nb * TR == N) emit(N - 1, 0.);
+		}
+
+		int its = 0;
+		bool again = act;
+		do {
+			// ---- forward elimination of (lA + P) x = lb + P obstacle ------
+			{
+				const int arow[6] = { tr.lo, tr.di, tr.up, tr.lb, american ? tr.ob : -1, american ? tr.x : -1 };
+				pass_begin();
+				for(int j = 0; j < lead; ++j) ring_issue(ring, &map, blk0, arow, j * TR, lane);
+				double cprev = 0., dprev = 0.;
+				for(int j = 0; j < nb; ++j) {
+					const int s = ring_wait(ring);
+					const double *tile = sm + s * STAGE_DOUBLES;
+					double vlo[TR], vdi[TR], vup[TR], vlb[TR], vob[TR], vx[TR];
+#pragma unroll
+					for(int u = 0; u < TR; ++u) {
+						vlo[u] = tile[u * 32]; vdi[u] = tile[SLOT_DOUBLES + u * 32]; vup[u] = tile[2 * SLOT_DOUBLES + u * 32];
+						vlb[u] = tile[3 * SLOT_DOUBLES + u * 32];
+						vob[u] = american ? tile[4 * SLOT_DOUBLES + u * 32] : 0.;
+						vx[u] = american ? tile[5 * SLOT_DOUBLES + u * 32] : 0.;
+					}
+					__syncwarp();
+					if(j + stages < nb) ring_issue(ring, &map, blk0, arow, (j + stages) * TR, lane);
+#pragma unroll
+					for(int u = 0; u < TR; ++u) {
+						const int i = j * TR + u;
+						if(i >= N) break;
+						const size_t at = (size_t)i * ld;
+						double a_i = gA.off(vlo[u]);
+						double b_i = 1. + gA.off(vdi[u]);
+						double c_i = gA.off(vup[u]);
+						double rhs = vlb[u];
+						if(american) {
+							// PenaltyMethod.hpp:45,61-68: predicate on the previous iterand
+							// (scale * (x - payoff)) < 0  <=>  x < payoff
+							if(vx[u] < vob[u]) { b_i = b_i + pen * 1.; rhs = rhs + pen * vob[u]; }
+						}
+						const double denom = b_i - a_i * cprev;
+						const double inv = rcp(denom);        // < 1 ulp; no division sequence on the serial chain
+						cprev = c_i * inv;
+						dprev = (rhs - a_i * dprev) * inv;
+						if(again) { cp[at] = cprev; dp[at] = dprev; }
+					}
+				}
+			}
+			// ---- back substitution + relativeError --------------------------
+			bool notdone = false;
+			{
+				const int arow[3] = { tr.cp, tr.dp, iterate ? tr.x : -1 };
+				pass_begin();
+				for(int j = 0; j < lead; ++j) ring_issue(ring, &map, blk0, arow, N - (j + 1) * TR, lane);
+				double xn = 0.;
+				for(int j = 0; j < nb; ++j) {
+					const int r0 = N - (j + 1) * TR;      // first row of the tile (negative in the last one: those rows are skipped)
+					const int s = ring_wait(ring);
+					const double *tile = sm + s * STAGE_DOUBLES;
+					double vcp[TR], vdp[TR], vxo[TR];
+#pragma unroll
+					for(int u = 0; u < TR; ++u) {
+						vcp[u] = tile[u * 32]; vdp[u] = tile[SLOT_DOUBLES + u * 32];
+						vxo[u] = iterate ? tile[2 * SLOT_DOUBLES + u * 32] : 0.;
+					}
+					__syncwarp();
+					if(j + stages < nb) ring_issue(ring, &map, blk0, arow, N - (j + stages + 1) * TR, lane);
+#pragma unroll
+					for(int u = TR - 1; u >= 0; --u) {
+						const int i = r0 + u;
+						if(i < 0) break;
+						xn = vdp[u] - vcp[u] * xn;
+						if(iterate) {
+							const double xo = vxo[u];
+							const double fa = fabs(xn), fb = fabs(xo);
+							double d = fa < fb ? fb : fa;
+							d = scale < d ? d : scale;
+							if(fabs(xn - xo) / d > tol) notdone = true;  // IterativeMethod.hpp:1131-1135
+						}
+						if(again) x[(size_t)i * ld] = xn;
+					}
+				}
+			}
+			if(again) {
+				++its;
+				again = iterate && notdone;
+				if(again && its >= b.max_inner) { status = 1; again = false; }
+			}
+		} while(__any_sync(FULL, again));
+
+		if(act) {
+			if(out.inner) {
+				out.inner[(size_t)c * out.inner_stride + n_steps] = (uint8_t)(its > 255 ? 255 : its);
+			}
+			inner_total += its;
+			++n_steps;
+			time0 = time1; time1 = t;
+			ns.end_step();
+
+			if(st.event_after) {
+				// Events at one time go in descending add() order (IterativeMethod.hpp:1340-1352);
+				// the exercise transform max(V, K - S) is idempotent.  Rare (E times per sweep):
+				// ordinary loads.
+				if(evob && st.user_events > 0) {
+					for(int i = 0; i < N; ++i) {
+						const size_t at = (size_t)i * ld;
+						const double ex = evob[at], v = x[at];
+						x[at] = v > ex ? v : ex;       // QuantPDE::max, EarlyInclude.hpp:48
+					}
+				}
+				ns.after_event();
+			}
+		}
+	}
+
+	if(!valid) return;
+	// ---- outputs (contract-major) ------------------------------------------
+	if(out.V) for(int i = 0; i < N; ++i) out.V[(size_t)c * out.V_stride + i] = x[(size_t)i * ld];
+	if(out.S) for(int i = 0; i < N; ++i) out.S[(size_t)c * out.S_stride + i] = w.S[(size_t)i * ld + base];
+	if(out.active) {
+		for(int i = 0; i < N; ++i) {
+			const double pred = ob ? (0. + 1. * x[(size_t)i * ld]) - ob[(size_t)i * ld] : 0.;
+			out.active[(size_t)c * out.active_stride + i] = pred < 0. ? 1 : 0;
+		}
+	}
+	if(out.value) {
+		// PiecewiseLinear::interpolate (Core/Interpolant.hpp:153-181,331-374)
+		const double *S = w.S + base;
+		const double s0 = b.spot ? b.spot[c] : b.strike[c];
+		int idx; double wgt;
+		if(s0 <= S[0]) { idx = 0; wgt = 1.; }
+		else if(s0 >= S[(size_t)(N - 1) * ld]) { idx = N - 2; wgt = 0.; }
+		else {
+			int l = 0, hgh = N - 2, mid = 0; wgt = 0.;
+			while(l <= hgh) {
+				mid = (l + hgh) / 2;
+				if(s0 < S[(size_t)mid * ld]) hgh = mid - 1;
+				else if(s0 >= S[(size_t)(mid + 1) * ld]) l = mid + 1;
+				else {
+					wgt = (S[(size_t)(mid + 1) * ld] - s0)
+						/ (S[(size_t)(mid + 1) * ld] - S[(size_t)mid * ld]);
+					break;
+				}
+			}
+			idx = mid;
+		}
+		double sum = 0.;
+		if(wgt > DBL_EPSILON) sum += wgt * x[(size_t)idx * ld];
+		if(1. - wgt > DBL_EPSILON) sum += (1. - wgt) * x[(size_t)(idx + 1) * ld];
+		out.value[c] = sum;
+	}
+	if(out.n_steps) out.n_steps[c] = n_steps;
+	if(out.inner_total) out.inner_total[c] = inner_total;
+	if(out.status) out.status[c] = status;
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+	const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+	CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_tiled_entry() {
+	static EncodeTiledFn fn = [] {
+		void *p = nullptr;
+		cudaDriverEntryPointQueryResult q;
+		if(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess
+				|| q != cudaDriverEntryPointSuccess) p = nullptr;
+		return (EncodeTiledFn)p;
+	}();
+	return fn;
+}
+
+} // namespace
+
+bool interleaved_tma_supported(const DeviceBatch &b) {
+	// policy iteration walks several sets of operator rows, the variable stepper and the
+	// dividend transform make extra passes with per-contract control flow: those batches
+	// stay on k_interleaved_sweep
+	// Below ~256 nodes a pass is a few dozen tiles: the ring drains and refills three times per
+	// inner solve and the plain-load sweep, whose back substitution still finds cp / dp in L2,
+	// is faster (measured at 129 nodes: 2.35 against 2.0 TB/s algorithmic; at 513: 1.67 against 2.13).
+	return b.n_controls == 0 && b.variable_target == nullptr && b.dividend_kind == QPDE_DIVIDEND_NONE && b.N >= 256;
+}
+
+bool interleaved_tma_prepare(InterleavedTma *t, double *block, long long rows, std::string *error) {
+	static_assert(sizeof(CUtensorMap) <= sizeof(t->map), "CUtensorMap does not fit InterleavedTma::map");
+	t->enabled = false;
+	EncodeTiledFn encode = encode_tiled_entry();
+	if(!encode) { if(error) *error = "cuTensorMapEncodeTiled is not available from this driver"; return false; }
+	const cuuint64_t dims[2] = { (cuuint64_t)QPDE_WARP_ROW, (cuuint64_t)rows };
+	const cuuint64_t strides[1] = { (cuuint64_t)QPDE_WARP_ROW * sizeof(double) };
+	const cuuint32_t box[2] = { 32u, (cuuint32_t)TR };
+	const cuuint32_t estr[2] = { 1u, 1u };
+	const CUresult rc = encode(reinterpret_cast<CUtensorMap *>(t->map), CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, block,
+		dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+		CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+	if(rc != CUDA_SUCCESS) {
+		if(error) *error = "cuTensorMapEncodeTiled failed with CUresult " + std::to_string((int)rc);
+		return false;
+	}
+	t->stages = 0;   // chosen per launch
+	t->enabled = true;
+	return true;
+}
+
+// Ring depth.  A stage is 6 KB per warp; what hides the HBM latency is the number of bytes in
+// flight per SM, (warps per SM) x stages x 6 KB.  Up to seven warps per SM the whole batch is
+// resident at once and the shared memory is split between the warps there are; beyond that,
+// seven warps with five stages each (fewer, deeper rings would add a wave of CTAs).
+static int tma_stages(int C, int sm_count) {
+	if(const char *e = std::getenv("QPDE_TMA_STAGES")) { const int v = std::atoi(e); if(v >= 1 && v <= 32) return v; }
+	const int warps = (C + 31) / 32;
+	int per_sm = (warps + sm_count - 1) / sm_count;
+	if(per_sm > 7) per_sm = 7;
+	int stages = (225 * 1024 / per_sm - 1024) / (STAGE_BYTES + 8);
+	return stages > 16 ? 16 : (stages < 2 ? 2 : stages);
+}
+
+void launch_interleaved_tma(const DeviceBatch &b, const InterleavedWork &w, const InterleavedTma &t, double *block,
+		const DeviceResult &out, cudaStream_t stream, long long *launches) {
+	launch_interleaved_setup(b, w, stream, launches);
+	auto row_of = [&](const double *p) { return p ? (int)((p - block) / QPDE_WARP_ROW) : -1; };
+	TmaRows tr;
+	tr.lo = row_of(w.lo); tr.di = row_of(w.di); tr.up = row_of(w.up);
+	tr.x = row_of(w.x); tr.xp = row_of(w.xprev); tr.lb = row_of(w.lb);
+	tr.cp = row_of(w.cp); tr.dp = row_of(w.dp); tr.ob = row_of(w.obst);
+	int device = 0, sm_count = 148;
+	cudaGetDevice(&device);
+	cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, device);
+	const int stages = t.stages > 0 ? t.stages : tma_stages(b.C, sm_count);
+	const int smem = stages * STAGE_BYTES + stages * 8;
+	cudaFuncSetAttribute(k_interleaved_sweep_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+	const int blocks = (b.C + 31) / 32;
+	k_interleaved_sweep_tma<<<blocks, 32, smem, stream>>>(*reinterpret_cast<const CUtensorMap *>(t.map), b, w, out, tr, stages);
+	*launches += 1;
+}
+
+} // namespace qpde

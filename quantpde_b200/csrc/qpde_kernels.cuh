@@ -50,12 +50,33 @@ struct DeviceResult {
 	int *status;
 };
 
-// Workspace of the INTERLEAVED family: [N][C] arrays.
+// Workspace of the INTERLEAVED family: arrays of N x ld doubles, ld = C rounded up to a warp of
+// contracts, laid out [ld / 32][N][32]: contract c, node i lives at ((c / 32) N + i) 32 + c % 32.
+constexpr int QPDE_WARP_ROW = 32;
+QPDE_HD size_t interleaved_base(int c, int N) { return (size_t)(c >> 5) * (size_t)N * QPDE_WARP_ROW + (size_t)(c & 31); }
 struct InterleavedWork {
 	double *S, *lo, *di, *up;
 	double *x, *xprev, *lb, *cp, *dp;
 	double *obst, *evobst; // null when unused
+	long long ld;          // contracts incl. padding (an array is N x ld doubles)
 };
+
+// The TMA-staged sweep (qpde_interleaved_tma.cu) reads every array through ONE tiled tensor map
+// over the workspace block seen as [rows][32].
+struct InterleavedTma {
+	alignas(64) unsigned char map[128];   // CUtensorMap (opaque here; cuda.h stays out of this header)
+	bool enabled;
+	int stages;                           // ring depth (tiles in flight per warp)
+};
+constexpr int QPDE_TMA_TILE_ROWS = 4;     // node rows per TMA tile (box = 32 contracts x 4 rows = 1 KB)
+
+// true if the TMA-staged sweep covers this batch (no policy iteration, variable steps or dividends)
+bool interleaved_tma_supported(const DeviceBatch &b);
+// encodes the tensor map over `block` ([rows][32] doubles); false if the driver entry point is missing
+bool interleaved_tma_prepare(InterleavedTma *t, double *block, long long rows, std::string *error);
+void launch_interleaved_tma(const DeviceBatch &b, const InterleavedWork &w, const InterleavedTma &t, double *block,
+		const DeviceResult &out, cudaStream_t stream, long long *launches);
+void launch_interleaved_setup(const DeviceBatch &b, const InterleavedWork &w, cudaStream_t stream, long long *launches);
 
 void launch_interleaved(const DeviceBatch &b, const InterleavedWork &w,
 		const DeviceResult &out, cudaStream_t stream, long long *launches);

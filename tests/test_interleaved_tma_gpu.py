@@ -1,0 +1,97 @@
+"""GPU: the TMA-staged sweep of the INTERLEAVED family (qpde_interleaved_tma.cu) against the
+plain-load sweep (bit for bit: same arithmetic, different staging) and against the oracle,
+on ragged batches (last warp of contracts partly empty, last tile of rows partly empty),
+every scheme, with and without the penalty iteration, with exercise events."""
+import os
+
+import numpy as np
+import pytest
+
+from helpers import REL_TOL, rel_err
+
+pytestmark = pytest.mark.gpu
+
+FIELDS = ("V", "S", "value", "n_steps", "inner_total", "inner", "active", "status")
+
+
+def _run(qpde, handle, spec, tma):
+    old = os.environ.get("QPDE_INTERLEAVED_NO_TMA")
+    os.environ["QPDE_INTERLEAVED_NO_TMA"] = "0" if tma else "1"      # read at plan creation
+    try:
+        with qpde.Plan(handle, spec) as plan:
+            assert plan.kernel == "interleaved" and plan.tma_staged == tma
+            plan.run()
+            return plan.fetch()
+    finally:
+        if old is None:
+            del os.environ["QPDE_INTERLEAVED_NO_TMA"]
+        else:
+            os.environ["QPDE_INTERLEAVED_NO_TMA"] = old
+
+
+def _batch(oracle, Cn, seed):
+    rng = np.random.default_rng(seed)
+    K = rng.uniform(50, 150, Cn); vol = rng.uniform(.1, .6, Cn)
+    T = rng.uniform(.25, 2., Cn); r = rng.uniform(.01, .08, Cn)
+    sp = oracle.special_axis()
+    axis = np.stack([oracle.axis_union(sp * k, sp * k) for k in K])
+    return K, vol, T, r, axis
+
+
+@pytest.mark.parametrize("scheme", ["rannacher", "cn", "bdf1", "bdf2"])
+@pytest.mark.parametrize("american", [True, False])
+def test_tma_staging_is_bit_identical_to_plain_loads(qpde, handle, oracle, scheme, american):
+    Cn, refine, steps = 70, 3, 40                   # 257 nodes = 64 tiles + 1 row; 70 = 2 warps + 6 contracts
+    K, vol, T, r, axis = _batch(oracle, Cn, 11)
+    spec = qpde.BatchSpec(axis=axis, refine=refine, r=r, sigma=vol, q=0.01, T=T, dt=T / steps, strike=K,
+                          scheme=scheme, american=american, payoff="put", kernel="interleaved")
+    a = _run(qpde, handle, spec, True)
+    p = _run(qpde, handle, spec, False)
+    for name in FIELDS:
+        assert np.array_equal(getattr(a, name), getattr(p, name)), name
+    assert np.all(a.status == 0)
+    c = Cn - 1                                      # a contract of the ragged last warp against the oracle
+    o = oracle.american_put(K[c], r[c], vol[c], T[c], steps, refine, q=0.01, american=american, scheme=scheme)
+    assert np.array_equal(a.S[c], o["S"]) and a.n_steps[c] == o["n_steps"]
+    assert rel_err(a.V[c], o["V"]).max() <= REL_TOL
+    assert np.array_equal(a.inner[c, :o["n_steps"]], o["inner"])
+
+
+@pytest.mark.parametrize("scheme", ["bdf2", "rannacher"])
+def test_tma_bermudan_events(qpde, handle, oracle, scheme):
+    """exercise dates (events between steps, BDF restart) on the tutorial grid, local volatility:
+    260 nodes = exactly 65 tiles; contracts of one warp hit their events at the same steps"""
+    Cn, refine, steps, E = 33, 3, 60, 5
+    rng = np.random.default_rng(5)
+    K = rng.uniform(80., 120., Cn); alpha = rng.uniform(10., 30., Cn); r = rng.uniform(.01, .08, Cn)
+    axis = np.stack([oracle.TUTORIAL_AXIS * (k / 100.) for k in K])
+    spec = qpde.BatchSpec(axis=axis, refine=refine, r=r, sigma=alpha, q=0., T=1., dt=1. / steps, strike=K,
+                          scheme=scheme, american=False, payoff="put", vol_model="inverse_s", n_exercise=E,
+                          exercise="k_minus_s", kernel="interleaved")
+    a = _run(qpde, handle, spec, True)
+    p = _run(qpde, handle, spec, False)
+    for name in FIELDS:
+        assert np.array_equal(getattr(a, name), getattr(p, name)), name
+    for c in (0, Cn - 1):
+        o = oracle.bermudan_put(K[c], r[c], alpha[c], 1., steps, E, refine, scheme=scheme)
+        assert a.n_steps[c] == o["n_steps"]
+        assert rel_err(a.V[c], o["V"]).max() <= REL_TOL
+
+
+def test_tma_contracts_with_different_step_counts_share_a_warp(qpde, handle, oracle):
+    """T / dt differs per contract: lanes of one warp finish after different numbers of steps and
+    penalty iterations; the finished lanes ride along without storing."""
+    Cn, refine = 40, 4                              # 513 nodes
+    K, vol, T, r, axis = _batch(oracle, Cn, 3)
+    steps = np.random.default_rng(3).integers(10, 60, Cn)
+    spec = qpde.BatchSpec(axis=axis, refine=refine, r=r, sigma=vol, q=0., T=T, dt=T / steps, strike=K,
+                          american=True, payoff="put", kernel="interleaved")
+    a = _run(qpde, handle, spec, True)
+    p = _run(qpde, handle, spec, False)
+    for name in FIELDS:
+        assert np.array_equal(getattr(a, name), getattr(p, name)), name
+    assert np.all(a.n_steps >= steps) and np.all(a.n_steps <= steps + 1)
+    for c in (int(np.argmin(steps)), int(np.argmax(steps))):
+        o = oracle.american_put(K[c], r[c], vol[c], T[c], int(steps[c]), refine)
+        assert rel_err(a.V[c], o["V"]).max() <= REL_TOL
+        assert np.array_equal(a.inner[c, :o["n_steps"]], o["inner"])
