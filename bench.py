@@ -208,6 +208,8 @@ def main():
     ap.add_argument("--cpu-sample", type=int, default=0)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-streaming", action="store_true",
+                    help="skip the bounded sample of the HBM-streaming (INTERLEAVED, TMA-staged) family")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -317,6 +319,37 @@ def main():
     ms_per_step = total_ms / args.steps
     value = Cn * world / (ms_per_step / 1e3)
 
+    # ---- the HBM-streaming family on a bounded sample of the same workload (rank 0, N = 1):
+    # same contracts and grid, 50 time steps instead of 1000, INTERLEAVED kernel (TMA ring).
+    streaming = None
+    if rank == 0 and world == 1 and not args.no_streaming:
+        s_steps = 50
+        sspec = capi.BatchSpec(axis=axis, refine=N_NODES_REFINE, r=r, sigma=vol, q=0.0, T=T, dt=T / s_steps,
+                               strike=K, american=True, payoff="put", kernel="interleaved",
+                               outputs=capi.OUT_VALUE | capi.OUT_INNER_TOTAL | capi.OUT_STATUS)
+        with capi.Plan(handle, sspec) as splan:
+            splan.run(); handle.synchronize()                      # warm-up
+            flush_l2()
+            e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+            l0 = handle.launches
+            e0.record(stream); splan.run(); e1.record(stream); e1.synchronize()
+            s_ms = e0.elapsed_time(e1)
+            sres = splan.fetch(capi.OUT_INNER_TOTAL | capi.OUT_STATUS)
+            s_inner = int(sres.inner_total.astype(np.int64).sum())
+            s_alg = ALG_BYTES_PER_NODE_SOLVE * N * s_inner
+            s_real = (96 * s_inner + 40 * Cn * s_steps) * N        # cp / dp round trip + rhs pass
+            speak, _ = load_peaks()
+            streaming = {"kernel": "interleaved (TMA-staged)" if splan.tma_staged else "interleaved (plain loads)",
+                         "sample": "%d contracts x %d nodes x %d steps (setup + sweep launch)" % (Cn, N, s_steps),
+                         "ms": s_ms, "gpu_launches": int(handle.launches - l0),
+                         "achieved": s_alg / (s_ms / 1e3) / 1e9, "peak": speak, "unit": "GB/s",
+                         "frac": s_alg / (s_ms / 1e3) / 1e9 / speak,
+                         "kernel_traffic_model_gbs": s_real / (s_ms / 1e3) / 1e9,
+                         "not_converged": int((sres.status != 0).sum()),
+                         "note": "achieved = 56 B x nodes x inner solves / time (SURVEY.md 8d); the kernel's own "
+                                 "traffic model is 96 B per inner solve + 40 B per step and node; ncu DRAM "
+                                 "bytes: profiles/r1_interleaved_tma_ncu_raw_subset.csv"}
+
     peak, peak_src = load_peaks()
     alg_bytes = ALG_BYTES_PER_NODE_SOLVE * N * (inner_sum_all / world)   # per launch (one rank's batch)
     achieved = alg_bytes / (ms_per_step / 1e3) / 1e9
@@ -340,7 +373,9 @@ def main():
                               "keeps state on chip, so frac > 1 means it has left the HBM roofline"},
         "clocks": clocks, "gpu_launches": int(launches), "e2e": e2e,
     }
-    if rank == 0 and not args.no_cpu:
+    if streaming is not None:
+        line["roofline_streaming_family"] = streaming
+    if rank == 0 and world == 1 and not args.no_cpu:    # the CPU baseline is an N = 1 leg
         cores = os.cpu_count() or 1
         line["cpu_baseline"] = {k: v for k, v in cpu_baseline(args.cpu_sample or max(cores, 8)).items()
                                 if k in ("value", "unit", "cores", "kind", "sample")}
