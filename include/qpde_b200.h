@@ -52,7 +52,13 @@ enum {
 	QPDE_SCHEME_RANNACHER = 0, /* ReverseRannacher,      Core/Rannacher.hpp:23-135   */
 	QPDE_SCHEME_CN        = 1, /* ReverseCrankNicolson,  Core/CrankNicolson.hpp:52-105 */
 	QPDE_SCHEME_BDF1      = 2, /* ReverseBDFOne,         Core/BDF.hpp:484-517        */
-	QPDE_SCHEME_BDF2      = 3  /* ReverseBDFTwo,         Core/BDF.hpp:522-590        */
+	QPDE_SCHEME_BDF2      = 3, /* ReverseBDFTwo,         Core/BDF.hpp:522-590        */
+	/* Higher-order BDF (variable-step formulas, start-up through the lower orders, restart after
+	 * every event): INTERLEAVED family, linear and penalised sweeps with constant steps. */
+	QPDE_SCHEME_BDF3      = 4, /* ReverseBDFThree,       Core/BDF.hpp:139-192,595-668 */
+	QPDE_SCHEME_BDF4      = 5, /* ReverseBDFFour,        Core/BDF.hpp:213-279,674-753 */
+	QPDE_SCHEME_BDF5      = 6, /* ReverseBDFFive,        Core/BDF.hpp:299-373,759-844 */
+	QPDE_SCHEME_BDF6      = 7  /* ReverseBDFSix,         Core/BDF.hpp:391-470,850-942 */
 };
 
 /* ---- initial condition / obstacle generators (Modules/Lambdas/Payoffs.hpp:13-51) */

@@ -15,7 +15,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "_ref", "liboracle.so")
 REF_PATH = os.path.join(HERE, "_ref", "qpde_ref")
 
-SCHEMES = {"rannacher": 0, "cn": 1, "bdf1": 2, "bdf2": 3}
+SCHEMES = {"rannacher": 0, "cn": 1, "bdf1": 2, "bdf2": 3, "bdf3": 4, "bdf4": 5, "bdf5": 6, "bdf6": 7}
 
 
 class Step(C.Structure):

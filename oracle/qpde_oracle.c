@@ -501,6 +501,44 @@ static void tri_spmv(int n, const double *lo, const double *di,
 	}
 }
 
+/* Variable-step BDF formulas of order k = 3 .. 6 (Core/BDF.hpp:139-470): g[m] = time(m) - t
+ * (reverse time, m = 0 the newest iterand); the reference names them h_{k-1} .. h_0.  On
+ * return c[m] multiplies iterand(m) in b (signs alternate, + for m = 0) and *hh scales A and b.
+ * Every expression is written as the reference writes it, so that it rounds the same way. */
+static void bdf_coefficients(int k, const double *g, double *c, double *hh) {
+	if(k == 3) {
+		const double h2 = g[0], h1 = g[1], h0 = g[2];
+		*hh = (h0*h1*h2)/(h0*h1 + h0*h2 + h1*h2);
+		c[0] = (h0*h1)/(h2*(h0 - h2)*(h1 - h2));
+		c[1] = (h0*h2)/(h1*(h0 - h1)*(h1 - h2));
+		c[2] = (h1*h2)/(h0*(h0 - h1)*(h0 - h2));
+	} else if(k == 4) {
+		const double h3 = g[0], h2 = g[1], h1 = g[2], h0 = g[3];
+		*hh = (h0*h1*h2*h3)/(h0*h1*h2 + h0*h1*h3 + h0*h2*h3 + h1*h2*h3);
+		c[0] = (h0*h1*h2)/(h3*(h0 - h3)*(h1 - h3)*(h2 - h3));
+		c[1] = (h0*h1*h3)/(h2*(h0 - h2)*(h1 - h2)*(h2 - h3));
+		c[2] = (h0*h2*h3)/(h1*(h0 - h1)*(h1 - h2)*(h1 - h3));
+		c[3] = (h1*h2*h3)/(h0*(h0 - h1)*(h0 - h2)*(h0 - h3));
+	} else if(k == 5) {
+		const double h4 = g[0], h3 = g[1], h2 = g[2], h1 = g[3], h0 = g[4];
+		*hh = (h0*h1*h2*h3*h4)/(h0*h1*h2*h3 + h0*h1*h2*h4 + h0*h1*h3*h4 + h0*h2*h3*h4 + h1*h2*h3*h4);
+		c[0] = (h0*h1*h2*h3)/(h4*(h0 - h4)*(h1 - h4)*(h2 - h4)*(h3 - h4));
+		c[1] = (h0*h1*h2*h4)/(h3*(h0 - h3)*(h1 - h3)*(h2 - h3)*(h3 - h4));
+		c[2] = (h0*h1*h3*h4)/(h2*(h0 - h2)*(h1 - h2)*(h2 - h3)*(h2 - h4));
+		c[3] = (h0*h2*h3*h4)/(h1*(h0 - h1)*(h1 - h2)*(h1 - h3)*(h1 - h4));
+		c[4] = (h1*h2*h3*h4)/(h0*(h0 - h1)*(h0 - h2)*(h0 - h3)*(h0 - h4));
+	} else {
+		const double h5 = g[0], h4 = g[1], h3 = g[2], h2 = g[3], h1 = g[4], h0 = g[5];
+		*hh = (h0*h1*h2*h3*h4*h5)/(h0*h1*h2*h3*h4 + h0*h1*h2*h3*h5 + h0*h1*h2*h4*h5 + h0*h1*h3*h4*h5 + h0*h2*h3*h4*h5 + h1*h2*h3*h4*h5);
+		c[0] = (h0*h1*h2*h3*h4)/(h5*(h0 - h5)*(h1 - h5)*(h2 - h5)*(h3 - h5)*(h4 - h5));
+		c[1] = (h0*h1*h2*h3*h5)/(h4*(h0 - h4)*(h1 - h4)*(h2 - h4)*(h3 - h4)*(h4 - h5));
+		c[2] = (h0*h1*h2*h4*h5)/(h3*(h0 - h3)*(h1 - h3)*(h2 - h3)*(h3 - h4)*(h3 - h5));
+		c[3] = (h0*h1*h3*h4*h5)/(h2*(h0 - h2)*(h1 - h2)*(h2 - h3)*(h2 - h4)*(h2 - h5));
+		c[4] = (h0*h2*h3*h4*h5)/(h1*(h0 - h1)*(h1 - h2)*(h1 - h3)*(h1 - h4)*(h1 - h5));
+		c[5] = (h1*h2*h3*h4*h5)/(h0*(h0 - h1)*(h0 - h2)*(h0 - h3)*(h0 - h4)*(h0 - h5));
+	}
+}
+
 /* diagnostics: number of inner solves of the last sweep and how many of them
  * saw an active set different from the one of the previous solve */
 long qpo_diag_solves = 0, qpo_diag_mask_changes = 0;
@@ -523,6 +561,10 @@ int qpo_sweep_1d(const qpo_problem *p, double *V, int *inner,
 	double *v1 = (double *)malloc(sizeof(double) * (size_t)n); /* iterand(0) */
 	double *v0 = (double *)malloc(sizeof(double) * (size_t)n); /* iterand(1) */
 	double *bj = (double *)calloc((size_t)n, sizeof(double)); /* op.b(): explicit jump term or 0 */
+	/* BDF3 .. BDF6: iterand(2) .. iterand(5) and their times */
+	const int order = p->scheme >= QPO_SCHEME_BDF2 ? p->scheme - QPO_SCHEME_BDF2 + 2 : 1;
+	double *vh[4] = { NULL, NULL, NULL, NULL };
+	double th[4] = { 0., 0., 0., 0. };
 	tri_lu lu;
 	int s, i, k, status = 0;
 	const int variable = p->variable_target > 0.;
@@ -535,8 +577,9 @@ int qpo_sweep_1d(const qpo_problem *p, double *V, int *inner,
 	int initialized = 0;   /* IterativeMethod.hpp:1150-1157 */
 	/* node state machines */
 	int ran_phase = 1;     /* Rannacher: 1,2 = implicit steps, 3 = first CN, 4 = CN */
-	int bdf_phase = 1;     /* BDFTwo: 1 = BDF1 step, 2 = first BDF2, 3 = BDF2 */
+	int bdf_phase = 1;     /* BDFTwo: 1 = BDF1 step, 2 = first BDF2, 3 = BDF2; BDFk: up to k + 1 */
 
+	for(i = 0; i + 2 < order; ++i) vh[i] = (double *)calloc((size_t)n, sizeof(double));
 	tri_alloc(&lu, n);
 	qpo_diag_solves = 0; qpo_diag_mask_changes = 0;
 	for(i = 0; i < n; ++i) P_di[i] = 0.;
@@ -583,7 +626,7 @@ int qpo_sweep_1d(const qpo_problem *p, double *V, int *inner,
 			st = &p->steps[s];
 		}
 		t = st->t;
-		int use_cn = 0, use_bdf2 = 0;
+		int use_cn = 0, use_bdf2 = 0, use_bdfk = 0;
 		double hA = 0.;
 
 		/* --- which A / b formulas apply at this step ------------------- */
@@ -600,10 +643,14 @@ int qpo_sweep_1d(const qpo_problem *p, double *V, int *inner,
 		case QPO_SCHEME_BDF1:
 			a_same = st->same_dt; /* BDF.hpp:511-513 */
 			break;
-		default:
-			use_bdf2 = bdf_phase >= 2;
-			a_same = (bdf_phase <= 2) ? 0 : st->same_dt; /* BDF.hpp:20-26,531-550 */
+		default: {
+			/* BDFk: steps 1 .. k - 1 after clear() use the lower orders (BDF.hpp:601-627,856-900) */
+			const int use = bdf_phase < order ? bdf_phase : order;
+			use_bdf2 = use == 2;
+			use_bdfk = use >= 3 ? use : 0;
+			a_same = (bdf_phase <= order) ? 0 : st->same_dt; /* BDF.hpp:20-26,531-550,615-619 */
 			break;
+		}
 		}
 		/* PenaltyMethod keeps LinearSystem's default isATheSame() == false
 		 * (IterativeMethod.hpp:143-146) */
@@ -618,7 +665,26 @@ int qpo_sweep_1d(const qpo_problem *p, double *V, int *inner,
 		/* --- left-hand side  lA  and right-hand side  lb ----------------- */
 		{
 			const double h0 = time1 - t; /* difference(t1, t0), reverse time */
-			if(use_bdf2) {
+			if(use_bdfk) {
+				/* BDF.hpp:139-470: A = I + hh op.A, b = (c v_new - c' v' + ... + op.b) hh */
+				double g[6], c[6], hh;
+				g[0] = time1 - t; g[1] = time0 - t;
+				for(k = 2; k < use_bdfk; ++k) g[k] = th[k - 2] - t;
+				bdf_coefficients(use_bdfk, g, c, &hh);
+				hA = hh;
+				for(i = 0; i < n; ++i) {
+					double acc = c[0] * v1[i];
+					acc = acc - c[1] * v0[i];
+					for(k = 2; k < use_bdfk; ++k) {
+						if(k & 1) acc = acc - c[k] * vh[k - 2][i];
+						else      acc = acc + c[k] * vh[k - 2][i];
+					}
+					M_lo[i] = hh * p->lo[i];
+					M_di[i] = 1. + hh * p->di[i];
+					M_up[i] = hh * p->up[i];
+					lb[i] = (acc + bj[i]) * hh;
+				}
+			} else if(use_bdf2) {
 				/* BDF.hpp:68-117 */
 				const double h1 = time1 - t;
 				const double hh0 = time0 - t;
@@ -705,7 +771,7 @@ int qpo_sweep_1d(const qpo_problem *p, double *V, int *inner,
 						const double l = p->plo[(size_t)best_k * n + i];
 						const double d = p->pdi[(size_t)best_k * n + i];
 						const double u = p->pup[(size_t)best_k * n + i];
-						if(use_bdf2) { A_lo[i] = hA * l; A_di[i] = 1. + hA * d; A_up[i] = hA * u; }
+						if(use_bdf2 || use_bdfk) { A_lo[i] = hA * l; A_di[i] = 1. + hA * d; A_up[i] = hA * u; }
 						else         { A_lo[i] = l * hA; A_di[i] = 1. + d * hA; A_up[i] = u * hA; }
 					}
 				}
@@ -772,7 +838,11 @@ int qpo_sweep_1d(const qpo_problem *p, double *V, int *inner,
 		initialized = 1;
 		if(inner) inner[s] = its;
 
-		/* stepper history push (lookback 2 when BDF2, else >= 1) */
+		/* stepper history push (lookback = the BDF order, else >= 1) */
+		for(k = order - 3; k >= 0; --k) {
+			memcpy(vh[k], k > 0 ? vh[k - 1] : v0, sizeof(double) * (size_t)n);
+			th[k] = k > 0 ? th[k - 1] : time0;
+		}
 		memcpy(v0, v1, sizeof(double) * (size_t)n);
 		time0 = time1;
 		memcpy(v1, x, sizeof(double) * (size_t)n);
@@ -781,7 +851,7 @@ int qpo_sweep_1d(const qpo_problem *p, double *V, int *inner,
 
 		/* node onIterationEnd (called by the stepper's endNodes) */
 		if(ran_phase < 4) ++ran_phase;  /* Rannacher.hpp:75-92 */
-		if(bdf_phase < 3) ++bdf_phase;  /* BDF.hpp:531-545 */
+		if(bdf_phase < order + 1) ++bdf_phase;  /* BDF.hpp:531-545,601-621 */
 
 		if(st->event_after) {
 			/* IterativeMethod.hpp:1279-1295 */
@@ -835,5 +905,6 @@ int qpo_sweep_1d(const qpo_problem *p, double *V, int *inner,
 	tri_free(&lu);
 	free(A_lo); free(A_di); free(A_up); free(M_lo); free(M_di); free(M_up);
 	free(bj); free(P_di); free(lb); free(rhs); free(x); free(xprev); free(v1); free(v0);
+	for(i = 0; i < 4; ++i) free(vh[i]);
 	return status;
 }

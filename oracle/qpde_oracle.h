@@ -22,7 +22,11 @@ enum {
 	QPO_SCHEME_RANNACHER = 0, /* Core/Rannacher.hpp:23-121 */
 	QPO_SCHEME_CN        = 1, /* Core/CrankNicolson.hpp:52-78, theta = 1/2 */
 	QPO_SCHEME_BDF1      = 2, /* Core/BDF.hpp:32-46,484-517 */
-	QPO_SCHEME_BDF2      = 3  /* Core/BDF.hpp:68-117,522-590 */
+	QPO_SCHEME_BDF2      = 3, /* Core/BDF.hpp:68-117,522-590 */
+	QPO_SCHEME_BDF3      = 4, /* Core/BDF.hpp:139-192,595-668: BDF1, BDF2, then BDF3 steps */
+	QPO_SCHEME_BDF4      = 5, /* Core/BDF.hpp:213-279,674-753 */
+	QPO_SCHEME_BDF5      = 6, /* Core/BDF.hpp:299-373,759-844 */
+	QPO_SCHEME_BDF6      = 7  /* Core/BDF.hpp:391-470,850-942 */
 };
 
 /* One entry of the replayed time loop (Core/IterativeMethod.hpp:1259-1317). */

@@ -149,6 +149,14 @@ int runVanilla(const Args &a) {
 			discretization.reset(new ReverseBDFOne(grid, bs));
 		} else if(scheme == "bdf2") {
 			discretization.reset(new ReverseBDFTwo(grid, bs));
+		} else if(scheme == "bdf3") {
+			discretization.reset(new ReverseBDFThree(grid, bs));
+		} else if(scheme == "bdf4") {
+			discretization.reset(new ReverseBDFFour(grid, bs));
+		} else if(scheme == "bdf5") {
+			discretization.reset(new ReverseBDFFive(grid, bs));
+		} else if(scheme == "bdf6") {
+			discretization.reset(new ReverseBDFSix(grid, bs));
 		} else {
 			std::fprintf(stderr, "unknown scheme\n");
 			return 2;
@@ -251,6 +259,14 @@ int runBermudan(const Args &a) {
 		std::unique_ptr<IterationNode> discretization;
 		if(scheme == "bdf2") {
 			discretization.reset(new ReverseBDFTwo(grid, bs));
+		} else if(scheme == "bdf3") {
+			discretization.reset(new ReverseBDFThree(grid, bs));
+		} else if(scheme == "bdf4") {
+			discretization.reset(new ReverseBDFFour(grid, bs));
+		} else if(scheme == "bdf5") {
+			discretization.reset(new ReverseBDFFive(grid, bs));
+		} else if(scheme == "bdf6") {
+			discretization.reset(new ReverseBDFSix(grid, bs));
 		} else if(scheme == "bdf1") {
 			discretization.reset(new ReverseBDFOne(grid, bs));
 		} else if(scheme == "rannacher") {
@@ -320,8 +336,12 @@ int runHjb(const Args &a) {
 		policy->setIteration(tolerance);
 
 		std::unique_ptr<IterationNode> discretization;
-		if(scheme == "bdf2") discretization.reset(new ReverseBDFTwo(grid, *policy));
-		else                 discretization.reset(new ReverseBDFOne(grid, *policy));
+		if(scheme == "bdf2")      discretization.reset(new ReverseBDFTwo(grid, *policy));
+		else if(scheme == "bdf3") discretization.reset(new ReverseBDFThree(grid, *policy));
+		else if(scheme == "bdf4") discretization.reset(new ReverseBDFFour(grid, *policy));
+		else if(scheme == "bdf5") discretization.reset(new ReverseBDFFive(grid, *policy));
+		else if(scheme == "bdf6") discretization.reset(new ReverseBDFSix(grid, *policy));
+		else                      discretization.reset(new ReverseBDFOne(grid, *policy));
 		discretization->setIteration(stepper);
 
 		SparseLUSolver solver;
@@ -476,9 +496,9 @@ int runGmwb(const Args &a) {
 void usage() {
 	std::fprintf(stderr,
 		"qpde_ref vanilla  K= S0= r= vol= q= T= steps= refine= american=0|1 "
-		"call=0|1 scheme=rannacher|cn|bdf1|bdf2 axis=special|tutorial repeat=\n"
+		"call=0|1 scheme=rannacher|cn|bdf1|bdf2|...|bdf6 axis=special|tutorial repeat=\n"
 		"qpde_ref bermudan K= r= alpha= q= T= steps= E= refine= "
-		"scheme=bdf2|bdf1|rannacher|cn axis= repeat=\n"
+		"scheme=bdf2|...|bdf6|bdf1|rannacher|cn axis= repeat=\n"
 		"qpde_ref hjb      K= S0= r_l= r_b= vol= q= T= steps= refine= long=0|1 "
 		"scheme=bdf2|bdf1 repeat=\n"
 		"qpde_ref jump     K= S0= r= vol= q= T= lambda= steps= refine= density=lognormal|kou "

@@ -17,7 +17,7 @@ ABI_VERSION = 2
 
 OK, ERR_INVALID, ERR_CUDA, ERR_NO_DEVICE, ERR_NOT_CONVERGED, ERR_UNSUPPORTED = 0, -1, -2, -3, -4, -5
 
-SCHEME = {"rannacher": 0, "cn": 1, "bdf1": 2, "bdf2": 3}
+SCHEME = {"rannacher": 0, "cn": 1, "bdf1": 2, "bdf2": 3, "bdf3": 4, "bdf4": 5, "bdf5": 6, "bdf6": 7}
 PAYOFF = {"array": 0, "put": 1, "call": 2, "digital_put": 3, "digital_call": 4,
           "straddle": 5, "k_minus_s": 6, "none": -1}
 DIVIDEND = {None: 0, "none": 0, "cash": 1, "proportional": 2}

@@ -274,7 +274,7 @@ static int plan_create_impl(qpde_handle *h, const qpde_bs1d_batch *in,
 	if(!in->r || !in->sigma || !in->q || !in->T || !in->dt) {
 		return fail(h, QPDE_ERR_INVALID, "r, sigma, q, T and dt are required");
 	}
-	if(in->scheme < QPDE_SCHEME_RANNACHER || in->scheme > QPDE_SCHEME_BDF2) return fail(h, QPDE_ERR_INVALID, "unknown scheme");
+	if(in->scheme < QPDE_SCHEME_RANNACHER || in->scheme > QPDE_SCHEME_BDF6) return fail(h, QPDE_ERR_INVALID, "unknown scheme");
 	if(in->vol_model < QPDE_VOL_CONST || in->vol_model > QPDE_VOL_NODES) return fail(h, QPDE_ERR_INVALID, "unknown vol_model");
 	if(in->vol_model == QPDE_VOL_NODES && !in->sigma_nodes) return fail(h, QPDE_ERR_INVALID, "sigma_nodes required");
 	if(in->payoff_kind == QPDE_PAYOFF_ARRAY ? !in->payoff : !is_generator(in->payoff_kind)) {
@@ -298,8 +298,8 @@ static int plan_create_impl(qpde_handle *h, const qpde_bs1d_batch *in,
 		if(!in->controls) return fail(h, QPDE_ERR_INVALID, "controls required");
 		if(in->controls_stride != 0 && in->controls_stride < in->n_controls) return fail(h, QPDE_ERR_INVALID, "controls_stride < n_controls");
 		if(in->american || in->n_exercise > 0) return fail(h, QPDE_ERR_UNSUPPORTED, "policy iteration with a penalty constraint or events is not supported");
-		if(in->scheme != QPDE_SCHEME_BDF1 && in->scheme != QPDE_SCHEME_BDF2) {
-			return fail(h, QPDE_ERR_UNSUPPORTED, "policy iteration needs scheme BDF1 or BDF2 (theta schemes re-evaluate A(t0) under the current control)");
+		if(bdf_order(in->scheme) == 0) {
+			return fail(h, QPDE_ERR_UNSUPPORTED, "policy iteration needs a BDF scheme (theta schemes re-evaluate A(t0) under the current control)");
 		}
 		if(!(in->tolerance > 0.) || !(in->scale > 0.) || in->max_inner < 1) {
 			return fail(h, QPDE_ERR_INVALID, "policy iteration: tolerance, scale > 0 and max_inner >= 1 required");
@@ -462,7 +462,8 @@ static int plan_create_impl(qpde_handle *h, const qpde_bs1d_batch *in,
 		w.ld = ((long long)C + 31) / 32 * 32;                 // a warp of contracts per 256-byte row segment
 		const size_t NC = (size_t)N * (size_t)w.ld;
 		const size_t sets = b.n_controls > 0 ? (size_t)b.n_controls : 1;   // operator rows per control value
-		const bool need_xprev = b.scheme == QPDE_SCHEME_BDF2 || b.variable_target;
+		const bool need_xprev = bdf_order(b.scheme) >= 2 || b.variable_target;
+		const size_t hist_slots = bdf_order(b.scheme) > 2 ? (size_t)bdf_order(b.scheme) - 1 : 1;   // iterand(1) .. iterand(order - 1)
 		const bool need_evobst = b.n_exercise > 0 && b.exercise_kind != QPDE_EXERCISE_NONE;
 		p->tma.enabled = false;
 		p->wblock = nullptr;
@@ -489,7 +490,7 @@ static int plan_create_impl(qpde_handle *h, const qpde_bs1d_batch *in,
 			QPDE_TRY(dev_alloc(p, &w.di, NC * sets)); QPDE_TRY(dev_alloc(p, &w.up, NC * sets));
 			QPDE_TRY(dev_alloc(p, &w.x, NC));  QPDE_TRY(dev_alloc(p, &w.lb, NC));
 			QPDE_TRY(dev_alloc(p, &w.cp, NC)); QPDE_TRY(dev_alloc(p, &w.dp, NC));
-			if(need_xprev) QPDE_TRY(dev_alloc(p, &w.xprev, NC));
+			if(need_xprev) QPDE_TRY(dev_alloc(p, &w.xprev, NC * hist_slots));
 			else w.xprev = w.x;
 			if(b.american) QPDE_TRY(dev_alloc(p, &w.obst, NC));
 			if(need_evobst) QPDE_TRY(dev_alloc(p, &w.evobst, NC));

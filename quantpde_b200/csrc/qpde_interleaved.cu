@@ -77,6 +77,37 @@ __global__ void k_interleaved_setup(DeviceBatch b, InterleavedWork w) {
 }
 
 // ---------------------------------------------------------------------------
+// BDF3 .. BDF6 (BDF.hpp:139-470), kept out of line so that the sweep's hot path keeps its
+// registers: coefficients of one step, and the right-hand side
+//   b = (c0 iterand(0) - c1 iterand(1) + c2 iterand(2) - ... + op.b) hh
+// with iterand(m >= 1) in slot (head + m - 1) % slots of the history ring behind xp.
+// ---------------------------------------------------------------------------
+struct BdfHigh { double c[6]; double hh; };
+
+__device__ __noinline__ BdfHigh bdf_high_setup(int k, double t, double time1, double time0,
+		double th0, double th1, double th2, double th3) {
+	BdfHigh f;
+	double g[6] = { time1 - t, time0 - t, th0 - t, th1 - t, th2 - t, th3 - t };
+	for(int m = 0; m < 6; ++m) f.c[m] = 0.;
+	bdf_coefficients(k, g, f.c, &f.hh);
+	return f;
+}
+
+__device__ __noinline__ void bdf_high_rhs(int k, BdfHigh f, int N, size_t NC, const double *x, const double *xp,
+		int head, int slots, double *lb) {
+	constexpr size_t C = QPDE_WARP_ROW;
+	for(int i = 0; i < N; ++i) {
+		const size_t at = (size_t)i * C;
+		double acc = f.c[0] * x[at];
+		for(int m = 1; m < k; ++m) {
+			const double term = f.c[m] * xp[(size_t)((head + m - 1) % slots) * NC + at];
+			acc = (m & 1) ? acc - term : acc + term;
+		}
+		lb[at] = (acc + 0.) * f.hh;
+	}
+}
+
+// ---------------------------------------------------------------------------
 // The sweep.
 // ---------------------------------------------------------------------------
 __global__ void __launch_bounds__(128)
@@ -103,6 +134,12 @@ k_interleaved_sweep(DeviceBatch b, InterleavedWork w, DeviceResult out) {
 	Gamma gA; gA.kind = STEP_IMPLICIT; gA.h = 0.; // what the factorised A was built with
 	int n_steps = 0, inner_total = 0, status = 0;
 	bool more = true;
+	// BDF3 .. BDF6: iterand(1) .. iterand(order - 1) live in a ring of order - 1 arrays behind
+	// w.xprev; iterand(m) is slot (head + m - 1) % slots.  th[] = times of iterand(2) .. iterand(5).
+	const int order = bdf_order(b.scheme);
+	const int slots = order > 2 ? order - 1 : 1;
+	int head = 0;
+	double th0 = rp.T, th1 = rp.T, th2 = rp.T, th3 = rp.T;
 
 	// ReverseVariableStepper (Core/Stepper.hpp:60-126)
 	const bool variable = b.variable_target != nullptr;
@@ -127,13 +164,20 @@ k_interleaved_sweep(DeviceBatch b, InterleavedWork w, DeviceResult out) {
 			c1 = hh0 / h1; c0 = h1 / hh0; den = hh0 - h1;
 		}
 		const double rden = 1. / den;
+		if(kind >= STEP_BDF3) {
+			// BDF.hpp:139-470: A = I + hh op.A; the right-hand side goes to lb here
+			const BdfHigh f = bdf_high_setup(kind - STEP_BDF3 + 3, t, time1, time0, th0, th1, th2, th3);
+			gb.h = f.hh;
+			bdf_high_rhs(kind - STEP_BDF3 + 3, f, N, NC, x, xp, head, slots, lb);
+		}
 		// IterativeMethod.hpp:906: re-assemble A unless the root says it is the same
 		// (a penalty or policy node in the tree keeps LinearSystem's default: never)
 		if(iterate || !ns.initialized || !ns.a_same(st.same_dt)) gA = gb;
+		double *it1 = xp + (size_t)head * NC;       // iterand(1)
 
 		// ---- lb = root.b(t) of the discretisation node ------------------
 		// x holds iterand(0) = V^n, xp holds iterand(1) for BDF2.
-		{
+		if(kind < STEP_BDF3) {
 			// blocks of ROWS rows with all loads issued first (see the elimination loop)
 			double vm = 0.;
 			for(int ib = 0; ib < N; ib += ROWS) {
@@ -142,7 +186,7 @@ k_interleaved_sweep(DeviceBatch b, InterleavedWork w, DeviceResult out) {
 				for(int u = 0; u < ROWS; ++u) {
 					const size_t at = (size_t)(ib + u < N ? ib + u : N - 1) * C;
 					vx[u] = x[at];
-					vxp[u] = kind == STEP_BDF2 ? xp[at] : 0.;
+					vxp[u] = kind == STEP_BDF2 ? it1[at] : 0.;
 					const bool cn = kind != STEP_IMPLICIT && kind != STEP_BDF2;
 					vlo[u] = cn ? lo[at] : 0.; vdi[u] = cn ? di[at] : 0.; vup[u] = cn ? up[at] : 0.;
 				}
@@ -172,8 +216,10 @@ k_interleaved_sweep(DeviceBatch b, InterleavedWork w, DeviceResult out) {
 		}
 		// history push: iterand(1) <- iterand(0).  For BDF2 the previous
 		// iterand must survive the solve, so copy it before x is overwritten.
-		if(b.scheme == QPDE_SCHEME_BDF2 || variable) {   // the variable stepper needs V^n after the solve, too
-			for(int i = 0; i < N; ++i) xp[(size_t)i * C] = x[(size_t)i * C];
+		if(order >= 2 || variable) {   // the variable stepper needs V^n after the solve, too
+			head = head == 0 ? slots - 1 : head - 1;    // the oldest slot becomes iterand(1)
+			it1 = xp + (size_t)head * NC;
+			for(int i = 0; i < N; ++i) it1[(size_t)i * C] = x[(size_t)i * C];
 		}
 
 		int its = 0;
@@ -286,6 +332,7 @@ k_interleaved_sweep(DeviceBatch b, InterleavedWork w, DeviceResult out) {
 		}
 		inner_total += its;
 		++n_steps;
+		th3 = th2; th2 = th1; th1 = th0; th0 = time0;
 		time0 = time1; time1 = t;
 		ns.end_step();
 
@@ -293,7 +340,7 @@ k_interleaved_sweep(DeviceBatch b, InterleavedWork w, DeviceResult out) {
 			// dt *= target / (relativeError(iterand(0), iterand(1), scale) + epsilon), Stepper.hpp:68-82
 			double err = 0.;
 			for(int i = 0; i < N; ++i) {
-				const double a = x[(size_t)i * C], v = xp[(size_t)i * C];
+				const double a = x[(size_t)i * C], v = it1[(size_t)i * C];
 				const double fa = fabs(a), fb = fabs(v);
 				double dn = fa < fb ? fb : fa;
 				dn = b.variable_scale < dn ? dn : b.variable_scale;

@@ -408,7 +408,8 @@ bool interleaved_tma_supported(const DeviceBatch &b) {
 	// Below ~256 nodes a pass is a few dozen tiles: the ring drains and refills three times per
 	// inner solve and the plain-load sweep, whose back substitution still finds cp / dp in L2,
 	// is faster (measured at 129 nodes: 2.35 against 2.0 TB/s algorithmic; at 513: 1.67 against 2.13).
-	return b.n_controls == 0 && b.variable_target == nullptr && b.dividend_kind == QPDE_DIVIDEND_NONE && b.N >= 256;
+	return b.n_controls == 0 && b.variable_target == nullptr && b.dividend_kind == QPDE_DIVIDEND_NONE && b.N >= 256
+		&& b.scheme <= QPDE_SCHEME_BDF2;   // BDF3 .. BDF6 keep a ring of history arrays: plain-load sweep
 }
 
 bool interleaved_tma_prepare(InterleavedTma *t, double *block, long long rows, std::string *error) {

@@ -702,6 +702,7 @@ static int pick_geometry(int N, int *M, int *PT, int *CL = nullptr) {
 bool resident_supported(const DeviceBatch &b) {
 	int M, PT, CL;
 	if(b.N < 10) return false;
+	if(b.scheme > QPDE_SCHEME_BDF2) return false;   // BDF3 .. BDF6: INTERLEAVED family
 	if(!pick_geometry(b.N, &M, &PT, &CL)) return false;
 	if(CL > 1 && (b.variable_target || b.dividend_kind != QPDE_DIVIDEND_NONE)) return false; // one-CTA features
 	if(b.american && b.n_exercise > 0) return false; // penalty + events: INTERLEAVED family

@@ -13,7 +13,7 @@
 //   Core/IterativeMethod.hpp:1243 ToleranceIteration       ToleranceIteration(tolerance, scale)
 //   Core/Rannacher.hpp:123  CrankNicolson.hpp:97  BDF.hpp:496,570
 //                                                          ReverseRannacher / ReverseCrankNicolson /
-//                                                          ReverseBDFOne / ReverseBDFTwo (grid, op)
+//                                                          ReverseBDFOne / ReverseBDFTwo / ... / ReverseBDFSix (grid, op)
 //   Core/PenaltyMethod.hpp:281-301                         MinPenaltyMethodDifference1(grid, node, payoff, tol)
 //   Bindings/Eigen.hpp:143-165  SparseLUSolver             B200Solver (owns the device context)
 //   Core/IterativeMethod.hpp:1065-1079 Iteration::solve    stepper.solve(grid, payoff, root, solver)
@@ -310,6 +310,17 @@ struct ReverseBDFTwo : Discretization {
 	ReverseBDFTwo(const RectilinearGrid1 &g, const BlackScholes1 &o) : Discretization(g, o, QPDE_SCHEME_BDF2) {}
 	ReverseBDFTwo(const RectilinearGrid1 &g, const PolicyIteration1_1 &p) : Discretization(g, p, QPDE_SCHEME_BDF2) {}
 };
+// Core/BDF.hpp:595-942 (start-up through the lower orders, restart after every event)
+#define QPDE_B200_BDF_CLASS(NAME, SCHEME) \
+struct NAME : Discretization { \
+	NAME(const RectilinearGrid1 &g, const BlackScholes1 &o) : Discretization(g, o, SCHEME) {} \
+	NAME(const RectilinearGrid1 &g, const PolicyIteration1_1 &p) : Discretization(g, p, SCHEME) {} \
+};
+QPDE_B200_BDF_CLASS(ReverseBDFThree, QPDE_SCHEME_BDF3)
+QPDE_B200_BDF_CLASS(ReverseBDFFour,  QPDE_SCHEME_BDF4)
+QPDE_B200_BDF_CLASS(ReverseBDFFive,  QPDE_SCHEME_BDF5)
+QPDE_B200_BDF_CLASS(ReverseBDFSix,   QPDE_SCHEME_BDF6)
+#undef QPDE_B200_BDF_CLASS
 
 // MinPenaltyMethodDifference1(grid, constraintNode, payoff, tolerance) —
 // Core/PenaltyMethod.hpp:281-301

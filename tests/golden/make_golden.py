@@ -93,9 +93,39 @@ CASES.append(("jump_merton_bdf2", "jump",
               dict(steps=40, refine=2, density="lognormal", K=90.0, r=0.03, vol=0.25, T=0.5,
                    mu=-0.2, sd=0.3, scheme="bdf2", **{"lambda": 0.4})))
 
+# ReverseBDFThree .. ReverseBDFSix (Core/BDF.hpp:139-470,595-942): start-up through the lower
+# orders, restart after every event, variable-step coefficients when the last step is clipped
+for order in (3, 4, 5, 6):
+    sch = "bdf%d" % order
+    CASES.append(("european_%s" % sch, "vanilla",
+                  dict(american=0, steps=100, refine=2, K=100.0, r=0.04, vol=0.2, T=1.0, scheme=sch)))
+    CASES.append(("bermudan_%s_k1" % sch, "bermudan",
+                  dict(steps=200, refine=1, scheme=sch, K=100.0, r=0.04, alpha=20.0, T=1.0, E=10)))
+CASES.append(("american_bdf3", "vanilla",
+              dict(american=1, steps=60, refine=2, K=100.0, r=0.04, vol=0.2, T=1.0, scheme="bdf3")))
+CASES.append(("american_bdf6_varied", "vanilla",
+              dict(american=1, steps=90, refine=3, K=83.0, r=0.06, vol=0.45, T=1.7, scheme="bdf6")))
+CASES.append(("dividend_cash_bdf4_k1", "bermudan",
+              dict(steps=120, refine=1, scheme="bdf4", K=100.0, r=0.04, alpha=20.0, T=1.0, E=6,
+                   dividend=1.0, dividend_kind="cash", dividend_first=0)))
+
+CASES.append(("hjb_short_bdf4_k2", "hjb",
+              dict(steps=48, refine=2, long=0, scheme="bdf4", K=100.0, r_l=0.03, r_b=0.05, vol=0.3, T=1.0)))
+CASES.append(("variable_american_bdf4", "vanilla",
+              dict(american=1, steps=40, refine=2, variable_target=0.3, scheme="bdf4", K=100.0, r=0.04, vol=0.2, T=1.0)))
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "reference_cases.npz")
+# cases already in the file with the same arguments are kept (pass --all to re-run everything)
+have = np.load(GOLDEN, allow_pickle=False) if os.path.exists(GOLDEN) and "--all" not in sys.argv else None
 out = {}
 names = []
 for name, mode, kw in CASES:
+    if have is not None and name + "/args" in have.files and str(have[name + "/args"]) == repr(kw):
+        names.append(name)
+        for key in have.files:
+            if key.startswith(name + "/"):
+                out[key] = have[key]
+        continue
     ref = po.run_ref(mode, **kw)
     names.append(name)
     out[name + "/mode"] = np.array(mode)
@@ -107,7 +137,9 @@ for name, mode, kw in CASES:
     out[name + "/value"] = np.array(ref["value"])
     print(name, ref["steps"], ref["value"])
 out["names"] = np.array(names)
-np.savez_compressed(os.path.join(os.path.dirname(os.path.abspath(__file__)), "reference_cases.npz"), **out)
+np.savez_compressed(GOLDEN, **out)
+if "--no-gmwb" in sys.argv:
+    sys.exit(0)
 
 # ---------------------------------------------------------------------------
 # GMWB (examples/hjbqvi/gmwb.cpp): fixtures of the reference for the §8(a) row 17
