@@ -226,6 +226,11 @@ def main():
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback")
+    # stdout carries exactly one line, the result: anything a library prints on the way (NCCL
+    # announces its version on fd 1 at the first collective) goes to stderr
+    sys.stdout.flush()
+    result_fd = os.dup(1)
+    os.dup2(2, 1)
     torch.cuda.set_device(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
@@ -381,10 +386,14 @@ def main():
                                 if k in ("value", "unit", "cores", "kind", "sample")}
     plan.close()
     handle.close()
-    if rank == 0:
-        print(json.dumps(line))
     if world > 1:
+        dist.barrier()
         dist.destroy_process_group()
+    sys.stdout.flush()
+    os.dup2(result_fd, 1)
+    os.close(result_fd)
+    if rank == 0:
+        print(json.dumps(line), flush=True)
 
 
 if __name__ == "__main__":

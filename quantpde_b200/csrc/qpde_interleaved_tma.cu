@@ -20,7 +20,7 @@
 //
 // Passes per time step: right-hand side (reads x [+ xprev | lo, di, up], writes lb
 // [+ xprev]), then per penalty iteration a forward elimination (reads lo, di, up, lb
-// [+ obstacle, x], writes cp, dp) and a back substitution (reads cp, dp [+ x], writes x).
+// [+ obstacle, x], writes cp, dp) and a back substitution (reads cp, dp [+ x, obstacle], writes x).
 // Results written with ordinary stores are read by later TMA loads: every pass starts
 // with a device-scope fence + fence.proxy.async.
 #include <cuda.h>
@@ -277,9 +277,16 @@ k_interleaved_sweep_tma(const __grid_constant__ CUtensorMap map, DeviceBatch b, 
 				}
 			}
 			// ---- back substitution + relativeError --------------------------
-			bool notdone = false;
+			// With the penalty iteration the pass also reads the obstacle and compares the active
+			// set of the new iterate with the one this solve was assembled with: if nothing
+			// changed, the next iteration would assemble the same matrix and right-hand side and
+			// return this iterate bit for bit (relativeError == 0) — it is counted, not computed.
+			// A warp makes as many passes as its slowest contract needs, and nearly every step
+			// has some contract whose free boundary has just crossed a node (three iterations
+			// instead of two): without the shortcut every warp would take three solves per step.
+			bool notdone = false, changed = false;
 			{
-				const int arow[3] = { tr.cp, tr.dp, iterate ? tr.x : -1 };
+				const int arow[4] = { tr.cp, tr.dp, iterate ? tr.x : -1, american ? tr.ob : -1 };
 				pass_begin();
 				for(int j = 0; j < lead; ++j) ring_issue(ring, &map, blk0, arow, N - (j + 1) * TR, lane);
 				double xn = 0.;
@@ -287,11 +294,12 @@ k_interleaved_sweep_tma(const __grid_constant__ CUtensorMap map, DeviceBatch b, 
 					const int r0 = N - (j + 1) * TR;      // first row of the tile (negative in the last one: those rows are skipped)
 					const int s = ring_wait(ring);
 					const double *tile = sm + s * STAGE_DOUBLES;
-					double vcp[TR], vdp[TR], vxo[TR];
+					double vcp[TR], vdp[TR], vxo[TR], vob[TR];
 #pragma unroll
 					for(int u = 0; u < TR; ++u) {
 						vcp[u] = tile[u * 32]; vdp[u] = tile[SLOT_DOUBLES + u * 32];
 						vxo[u] = iterate ? tile[2 * SLOT_DOUBLES + u * 32] : 0.;
+						vob[u] = american ? tile[3 * SLOT_DOUBLES + u * 32] : 0.;
 					}
 					__syncwarp();
 					if(j + stages < nb) ring_issue(ring, &map, blk0, arow, N - (j + stages + 1) * TR, lane);
@@ -306,6 +314,7 @@ k_interleaved_sweep_tma(const __grid_constant__ CUtensorMap map, DeviceBatch b, 
 							double d = fa < fb ? fb : fa;
 							d = scale < d ? d : scale;
 							if(fabs(xn - xo) / d > tol) notdone = true;  // IterativeMethod.hpp:1131-1135
+							if(american && ((xn < vob[u]) != (xo < vob[u]))) changed = true;
 						}
 						if(again) x[(size_t)i * ld] = xn;
 					}
@@ -314,7 +323,11 @@ k_interleaved_sweep_tma(const __grid_constant__ CUtensorMap map, DeviceBatch b, 
 			if(again) {
 				++its;
 				again = iterate && notdone;
-				if(again && its >= b.max_inner) { status = 1; again = false; }
+				if(again && !changed) {
+					// same active set: the confirming iteration is counted (see above)
+					if(its >= b.max_inner) status = 1; else ++its;
+					again = false;
+				} else if(again && its >= b.max_inner) { status = 1; again = false; }
 			}
 		} while(__any_sync(FULL, again));
 
