@@ -325,10 +325,10 @@ def main():
     value = Cn * world / (ms_per_step / 1e3)
 
     # ---- the HBM-streaming family on a bounded sample of the same workload (rank 0, N = 1):
-    # same contracts and grid, 50 time steps instead of 1000, INTERLEAVED kernel (TMA ring).
+    # same contracts and grid, 200 time steps instead of 1000, INTERLEAVED kernel (TMA ring).
     streaming = None
     if rank == 0 and world == 1 and not args.no_streaming:
-        s_steps = 50
+        s_steps = 200
         sspec = capi.BatchSpec(axis=axis, refine=N_NODES_REFINE, r=r, sigma=vol, q=0.0, T=T, dt=T / s_steps,
                                strike=K, american=True, payoff="put", kernel="interleaved",
                                outputs=capi.OUT_VALUE | capi.OUT_INNER_TOTAL | capi.OUT_STATUS)

@@ -18,8 +18,9 @@
 // per contract (step kind, number of penalty iterations, number of steps) is a
 // predicate on the stores.
 //
-// Passes per time step: right-hand side (reads x [+ xprev | lo, di, up], writes lb
-// [+ xprev]), then per penalty iteration a forward elimination (reads lo, di, up, lb
+// Passes per time step: the first solve forms the right-hand side on the way (reads lo, di,
+// up, x [+ obstacle, xprev], writes lb, cp, dp [+ xprev]), every further penalty iteration
+// has a forward elimination (reads lo, di, up, lb
 // [+ obstacle, x], writes cp, dp) and a back substitution (reads cp, dp [+ x, obstacle], writes x).
 // Results written with ordinary stores are read by later TMA loads: every pass starts
 // with a device-scope fence + fence.proxy.async.
@@ -180,67 +181,88 @@ k_interleaved_sweep_tma(const __grid_constant__ CUtensorMap map, DeviceBatch b, 
 		const double rden = 1. / den;
 		const bool is_cn = kind == STEP_CN_R || kind == STEP_CN_T;
 
-		// ---- lb = root.b(t) of the discretisation node; iterand(1) <- iterand(0) for BDF2 ----
-		{
-			const bool any_cn = __any_sync(FULL, act && is_cn);
-			const bool any_b2 = __any_sync(FULL, act && kind == STEP_BDF2);
-			const int arow[5] = { tr.x, any_b2 ? tr.xp : -1, any_cn ? tr.lo : -1, any_cn ? tr.di : -1, any_cn ? tr.up : -1 };
-			pass_begin();
-			for(int j = 0; j < lead; ++j) ring_issue(ring, &map, blk0, arow, j * TR, lane);
-			// row i is finished when x[i + 1] arrives: one row of delay
-			double xm = 0., xc = 0., pxp = 0., plo = 0., pdi = 0., pup = 0.;
-			auto emit = [&](int i, double vp) {
-				double val;
-				if(kind == STEP_IMPLICIT) {
-					val = xc + 0. * h0;
-				} else if(kind == STEP_BDF2) {
-					val = (div_by(c1 * xc - c0 * pxp, den, rden) + 0.) * gb.h;
-				} else {
-					// (I - A h/2) v0, row-major SpMV from zero in column order
-					double acc = 0.;
-					if(i > 0) acc += (0. - gb.off(plo)) * xm;
-					acc += (1. - gb.off(pdi)) * xc;
-					if(i < N - 1) acc += (0. - gb.off(pup)) * vp;
-					val = acc + 0.;
-				}
-				if(act) {
-					lb[(size_t)i * ld] = val;
-					if(copy_xp) xp[(size_t)i * ld] = xc;
-				}
-			};
-			for(int j = 0; j < nb; ++j) {
-				const int s = ring_wait(ring);
-				const double *tile = sm + s * STAGE_DOUBLES;
-				double vx[TR], vxp[TR], vlo[TR], vdi[TR], vup[TR];
-#pragma unroll
-				for(int u = 0; u < TR; ++u) {
-					vx[u] = tile[u * 32];
-					vxp[u] = any_b2 ? tile[SLOT_DOUBLES + u * 32] : 0.;
-					vlo[u] = any_cn ? tile[2 * SLOT_DOUBLES + u * 32] : 0.;
-					vdi[u] = any_cn ? tile[3 * SLOT_DOUBLES + u * 32] : 0.;
-					vup[u] = any_cn ? tile[4 * SLOT_DOUBLES + u * 32] : 0.;
-				}
-				__syncwarp();
-				if(j + stages < nb) ring_issue(ring, &map, blk0, arow, (j + stages) * TR, lane);
-#pragma unroll
-				for(int u = 0; u < TR; ++u) {
-					const int i = j * TR + u;
-					if(i >= 1 && i <= N) emit(i - 1, vx[u]);
-					xm = xc; xc = vx[u]; pxp = vxp[u]; plo = vlo[u]; pdi = vdi[u]; pup = vup[u];
-				}
+		// One row of the elimination of (lA + P) x = lb + P obstacle (the serial chain)
+		double cprev = 0., dprev = 0.;
+		auto eliminate = [&](int i, double vlo, double vdi, double vup, double rhs, double vob, double vx, bool store) {
+			double a_i = gA.off(vlo);
+			double b_i = 1. + gA.off(vdi);
+			double c_i = gA.off(vup);
+			if(american) {
+				// PenaltyMethod.hpp:45,61-68: predicate on the previous iterand
+				// (scale * (x - payoff)) < 0  <=>  x < payoff
+				if(vx < vob) { b_i = b_i + pen * 1.; rhs = rhs + pen * vob; }
 			}
-			if(nb * TR == N) emit(N - 1, 0.);
-		}
+			const double denom = b_i - a_i * cprev;
+			const double inv = rcp(denom);        // < 1 ulp; no division sequence on the serial chain
+			cprev = c_i * inv;
+			dprev = (rhs - a_i * dprev) * inv;
+			if(store) { cp[(size_t)i * ld] = cprev; dp[(size_t)i * ld] = dprev; }
+		};
 
 		int its = 0;
 		bool again = act;
+		bool first = true;
 		do {
+			if(first) {
+				// ---- first solve of the step: lb = root.b(t) of the discretisation node is formed
+				// on the way (and kept for the later penalty iterations), iterand(1) <- iterand(0)
+				// for BDF2, and the forward elimination runs in the same pass.  Row i of lb needs
+				// x[i + 1]: the chain runs one row behind the tiles.
+				first = false;
+				const bool any_b2 = __any_sync(FULL, act && kind == STEP_BDF2);
+				const int arow[6] = { tr.lo, tr.di, tr.up, tr.x, american ? tr.ob : -1, any_b2 ? tr.xp : -1 };
+				pass_begin();
+				for(int j = 0; j < lead; ++j) ring_issue(ring, &map, blk0, arow, j * TR, lane);
+				double xm = 0., xc = 0., pxp = 0., plo = 0., pdi = 0., pup = 0., pob = 0.;
+				cprev = 0.; dprev = 0.;
+				auto finish_row = [&](int i, double vp) {
+					double val;
+					if(kind == STEP_IMPLICIT) {
+						val = xc + 0. * h0;
+					} else if(kind == STEP_BDF2) {
+						val = (div_by(c1 * xc - c0 * pxp, den, rden) + 0.) * gb.h;
+					} else {
+						// (I - A h/2) v0, row-major SpMV from zero in column order
+						double acc = 0.;
+						if(i > 0) acc += (0. - gb.off(plo)) * xm;
+						acc += (1. - gb.off(pdi)) * xc;
+						if(i < N - 1) acc += (0. - gb.off(pup)) * vp;
+						val = acc + 0.;
+					}
+					if(act) {
+						lb[(size_t)i * ld] = val;
+						if(copy_xp) xp[(size_t)i * ld] = xc;
+					}
+					eliminate(i, plo, pdi, pup, val, pob, xc, again);
+				};
+				for(int j = 0; j < nb; ++j) {
+					const int s = ring_wait(ring);
+					const double *tile = sm + s * STAGE_DOUBLES;
+					double vlo[TR], vdi[TR], vup[TR], vx[TR], vob[TR], vxp[TR];
+#pragma unroll
+					for(int u = 0; u < TR; ++u) {
+						vlo[u] = tile[u * 32]; vdi[u] = tile[SLOT_DOUBLES + u * 32]; vup[u] = tile[2 * SLOT_DOUBLES + u * 32];
+						vx[u] = tile[3 * SLOT_DOUBLES + u * 32];
+						vob[u] = american ? tile[4 * SLOT_DOUBLES + u * 32] : 0.;
+						vxp[u] = any_b2 ? tile[5 * SLOT_DOUBLES + u * 32] : 0.;
+					}
+					__syncwarp();
+					if(j + stages < nb) ring_issue(ring, &map, blk0, arow, (j + stages) * TR, lane);
+#pragma unroll
+					for(int u = 0; u < TR; ++u) {
+						const int i = j * TR + u;
+						if(i >= 1 && i <= N) finish_row(i - 1, vx[u]);
+						xm = xc; xc = vx[u]; pxp = vxp[u]; plo = vlo[u]; pdi = vdi[u]; pup = vup[u]; pob = vob[u];
+					}
+				}
+				if(nb * TR == N) finish_row(N - 1, 0.);
+			} else {
 			// ---- forward elimination of (lA + P) x = lb + P obstacle ------
 			{
 				const int arow[6] = { tr.lo, tr.di, tr.up, tr.lb, american ? tr.ob : -1, american ? tr.x : -1 };
 				pass_begin();
 				for(int j = 0; j < lead; ++j) ring_issue(ring, &map, blk0, arow, j * TR, lane);
-				double cprev = 0., dprev = 0.;
+				cprev = 0.; dprev = 0.;
 				for(int j = 0; j < nb; ++j) {
 					const int s = ring_wait(ring);
 					const double *tile = sm + s * STAGE_DOUBLES;
@@ -258,23 +280,10 @@ k_interleaved_sweep_tma(const __grid_constant__ CUtensorMap map, DeviceBatch b, 
 					for(int u = 0; u < TR; ++u) {
 						const int i = j * TR + u;
 						if(i >= N) break;
-						const size_t at = (size_t)i * ld;
-						double a_i = gA.off(vlo[u]);
-						double b_i = 1. + gA.off(vdi[u]);
-						double c_i = gA.off(vup[u]);
-						double rhs = vlb[u];
-						if(american) {
-							// PenaltyMethod.hpp:45,61-68: predicate on the previous iterand
-							// (scale * (x - payoff)) < 0  <=>  x < payoff
-							if(vx[u] < vob[u]) { b_i = b_i + pen * 1.; rhs = rhs + pen * vob[u]; }
-						}
-						const double denom = b_i - a_i * cprev;
-						const double inv = rcp(denom);        // < 1 ulp; no division sequence on the serial chain
-						cprev = c_i * inv;
-						dprev = (rhs - a_i * dprev) * inv;
-						if(again) { cp[at] = cprev; dp[at] = dprev; }
+						eliminate(i, vlo[u], vdi[u], vup[u], vlb[u], vob[u], vx[u], again);
 					}
 				}
+			}
 			}
 			// ---- back substitution + relativeError --------------------------
 			// With the penalty iteration the pass also reads the obstacle and compares the active
