@@ -114,7 +114,7 @@ __device__ __forceinline__ void pass_begin() {
 	__syncwarp();
 }
 
-__global__ void __launch_bounds__(32)
+__global__ void __launch_bounds__(32, 8)
 k_interleaved_sweep_tma(const __grid_constant__ CUtensorMap map, DeviceBatch b, InterleavedWork w, DeviceResult out,
 		TmaRows tr, int stages) {
 	extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -146,7 +146,7 @@ k_interleaved_sweep_tma(const __grid_constant__ CUtensorMap map, DeviceBatch b, 
 
 	const bool american = b.american != 0;
 	const bool iterate = american;               // a ToleranceIteration wraps every step
-	const bool copy_xp = b.scheme == QPDE_SCHEME_BDF2;
+	const bool copy_xp = b.scheme == QPDE_SCHEME_BDF2 || b.variable_target != nullptr;   // iterand(1) <- iterand(0)
 	const int nb = (N + TR - 1) / TR;            // tiles per pass
 	const int lead = nb < stages ? nb : stages;
 
@@ -156,8 +156,17 @@ k_interleaved_sweep_tma(const __grid_constant__ CUtensorMap map, DeviceBatch b, 
 	Gamma gA; gA.kind = STEP_IMPLICIT; gA.h = 0.; // what the factorised A was built with
 	int n_steps = 0, inner_total = 0, status = 0;
 	bool more = valid;
+	// ReverseVariableStepper (Core/Stepper.hpp:60-126): every contract has its own step sizes
+	// and its own number of steps; V^n is kept in xprev for the relative change over a step
+	const bool variable = b.variable_target != nullptr;
+	const double vtarget = variable ? b.variable_target[cc] : 0.;
+	double vdt = b.dt[cc];
 
 	while(__any_sync(FULL, more)) {
+		if(variable && more) {
+			if(n_steps >= b.max_steps) { status = 3; more = false; }     // output capacity
+			rp.dt_const = vdt;                                            // VariableStepper::timestep()
+		}
 		const bool act = more;                   // this contract takes a step in this trip
 		qpde_step st; st.t = 0.; st.dt = 0.; st.same_dt = 0; st.event_after = 0; st.user_events = 0; st.reserved = 0;
 		int kind = STEP_IMPLICIT;
@@ -349,15 +358,60 @@ k_interleaved_sweep_tma(const __grid_constant__ CUtensorMap map, DeviceBatch b, 
 			time0 = time1; time1 = t;
 			ns.end_step();
 
+			if(variable && more) {
+				// dt *= target / (relativeError(iterand(0), iterand(1), scale) + epsilon), Stepper.hpp:68-82
+				// (once per step, ordinary loads: independent, so they stream)
+				double err = 0.;
+				for(int i = 0; i < N; ++i) {
+					const double a = x[(size_t)i * ld], v = xp[(size_t)i * ld];
+					const double fa = fabs(a), fb = fabs(v);
+					double dn = fa < fb ? fb : fa;
+					dn = b.variable_scale < dn ? dn : b.variable_scale;
+					const double e = fabs(a - v) / dn;
+					err = e > err ? e : err;
+				}
+				vdt *= vtarget / (err + DBL_EPSILON);
+			}
+
 			if(st.event_after) {
-				// Events at one time go in descending add() order (IterativeMethod.hpp:1340-1352);
-				// the exercise transform max(V, K - S) is idempotent.  Rare (E times per sweep):
-				// ordinary loads.
-				if(evob && st.user_events > 0) {
-					for(int i = 0; i < N; ++i) {
-						const size_t at = (size_t)i * ld;
-						const double ex = evob[at], v = x[at];
-						x[at] = v > ex ? v : ex;       // QuantPDE::max, EarlyInclude.hpp:48
+				// Events at one time go in descending add() order (IterativeMethod.hpp:1340-1352).
+				// Rare (E times per sweep): ordinary loads and stores.
+				for(int ue = 0; ue < st.user_events; ++ue) {
+					for(int op = 0; op < 2; ++op) {
+						const bool is_dividend = (op == 0) == (b.dividend_first != 0);
+						if(is_dividend && b.dividend_kind != QPDE_DIVIDEND_NONE) {
+							// Event<1>::_doEvent with V(max(S - D, 0)) or V((1 - D) S) through the
+							// piecewise-linear interpolant (Core/Event.hpp:100-112, Interpolant.hpp:153-181,
+							// 331-374).  The shifted price never exceeds S_i, so the nodes are updated in
+							// place from the top down, and the bracketing interval only moves down.
+							const double D = b.dividend[c];
+							const double *S = w.S + base;
+							const double Sfirst = S[0], Slast = S[(size_t)(N - 1) * ld];
+							int idx = N - 2;
+							for(int i = N - 1; i >= 0; --i) {
+								const double Si = S[(size_t)i * ld];
+								const double at = b.dividend_kind == QPDE_DIVIDEND_CASH ? (Si - D > 0. ? Si - D : 0.) : (1. - D) * Si;
+								int k; double wgt;
+								if(at <= Sfirst) { k = 0; wgt = 1.; }
+								else if(at >= Slast) { k = N - 2; wgt = 0.; }
+								else {
+									while(idx > 0 && S[(size_t)idx * ld] > at) --idx;      // S[idx] <= at < S[idx + 1]
+									k = idx;
+									wgt = (S[(size_t)(k + 1) * ld] - at) / (S[(size_t)(k + 1) * ld] - S[(size_t)k * ld]);
+								}
+								double sum = 0.;
+								if(wgt > DBL_EPSILON) sum += wgt * x[(size_t)k * ld];
+								if(1. - wgt > DBL_EPSILON) sum += (1. - wgt) * x[(size_t)(k + 1) * ld];
+								x[(size_t)i * ld] = sum;
+							}
+						}
+						if(!is_dividend && evob) {
+							for(int i = 0; i < N; ++i) {
+								const size_t at = (size_t)i * ld;
+								const double ex = evob[at], v = x[at];
+								x[at] = v > ex ? v : ex;       // QuantPDE::max, EarlyInclude.hpp:48
+							}
+						}
 					}
 				}
 				ns.after_event();
@@ -424,14 +478,12 @@ EncodeTiledFn encode_tiled_entry() {
 } // namespace
 
 bool interleaved_tma_supported(const DeviceBatch &b) {
-	// policy iteration walks several sets of operator rows, the variable stepper and the
-	// dividend transform make extra passes with per-contract control flow: those batches
-	// stay on k_interleaved_sweep
+	// policy iteration walks several sets of operator rows and BDF3 .. BDF6 a ring of history
+	// arrays: those batches stay on k_interleaved_sweep
 	// Below ~256 nodes a pass is a few dozen tiles: the ring drains and refills three times per
 	// inner solve and the plain-load sweep, whose back substitution still finds cp / dp in L2,
 	// is faster (measured at 129 nodes: 2.35 against 2.0 TB/s algorithmic; at 513: 1.67 against 2.13).
-	return b.n_controls == 0 && b.variable_target == nullptr && b.dividend_kind == QPDE_DIVIDEND_NONE && b.N >= 256
-		&& b.scheme <= QPDE_SCHEME_BDF2;   // BDF3 .. BDF6 keep a ring of history arrays: plain-load sweep
+	return b.n_controls == 0 && b.N >= 256 && b.scheme <= QPDE_SCHEME_BDF2;
 }
 
 bool interleaved_tma_prepare(InterleavedTma *t, double *block, long long rows, std::string *error) {

@@ -95,3 +95,46 @@ def test_tma_contracts_with_different_step_counts_share_a_warp(qpde, handle, ora
         o = oracle.american_put(K[c], r[c], vol[c], T[c], int(steps[c]), refine)
         assert rel_err(a.V[c], o["V"]).max() <= REL_TOL
         assert np.array_equal(a.inner[c, :o["n_steps"]], o["inner"])
+
+
+@pytest.mark.parametrize("kind,first", [("cash", False), ("cash", True), ("proportional", False)])
+def test_tma_dividend_events(qpde, handle, oracle, kind, first):
+    """discrete dividends at the exercise dates (interpolating events, ordinary loads inside the
+    TMA-staged sweep), per-contract amounts, both orders relative to the exercise transform"""
+    Cn, refine, steps, E = 35, 3, 60, 4
+    rng = np.random.default_rng(21)
+    K = rng.uniform(80., 120., Cn); alpha = rng.uniform(10., 30., Cn); r = rng.uniform(.01, .08, Cn)
+    D = rng.uniform(.2, 2., Cn) if kind == "cash" else rng.uniform(.005, .03, Cn)
+    axis = np.stack([oracle.TUTORIAL_AXIS * (k / 100.) for k in K])
+    spec = qpde.BatchSpec(axis=axis, refine=refine, r=r, sigma=alpha, q=0., T=1., dt=1. / steps, strike=K,
+                          scheme="bdf2", american=False, payoff="put", vol_model="inverse_s", n_exercise=E,
+                          exercise="k_minus_s", kernel="interleaved",
+                          dividend=dict(kind=kind, amount=D, first=first))
+    a = _run(qpde, handle, spec, True)
+    p = _run(qpde, handle, spec, False)
+    for name in FIELDS:
+        assert np.array_equal(getattr(a, name), getattr(p, name)), name
+    c = Cn - 1
+    o = oracle.bermudan_put(K[c], r[c], alpha[c], 1., steps, E, refine, scheme="bdf2", dividend=D[c],
+                            dividend_kind=kind, dividend_first=first)
+    assert a.n_steps[c] == o["n_steps"] and rel_err(a.V[c], o["V"]).max() <= REL_TOL
+
+
+@pytest.mark.parametrize("scheme", ["rannacher", "bdf2"])
+def test_tma_variable_stepper(qpde, handle, oracle, scheme):
+    """ReverseVariableStepper: every contract of a warp has its own step sizes and step count"""
+    Cn, refine = 36, 3
+    K, vol, T, r, axis = _batch(oracle, Cn, 9)
+    target = np.random.default_rng(9).uniform(.1, .4, Cn)
+    spec = qpde.BatchSpec(axis=axis, refine=refine, r=r, sigma=vol, q=0., T=T, dt=T / 30, strike=K, scheme=scheme,
+                          american=True, payoff="put", kernel="interleaved", variable_target=target, max_steps=600)
+    a = _run(qpde, handle, spec, True)
+    p = _run(qpde, handle, spec, False)
+    for name in FIELDS:
+        assert np.array_equal(getattr(a, name), getattr(p, name)), name
+    assert np.all(a.status == 0) and len(set(a.n_steps.tolist())) > 3
+    for c in (0, Cn - 1):
+        o = oracle.american_put(K[c], r[c], vol[c], T[c], 30, refine, scheme=scheme, variable_target=target[c])
+        assert a.n_steps[c] == o["n_steps"]
+        assert rel_err(a.V[c], o["V"]).max() <= REL_TOL
+        assert np.array_equal(a.inner[c, :o["n_steps"]], o["inner"])
