@@ -304,7 +304,7 @@ int qpde_bs1d_plan_destroy(qpde_bs1d_plan *plan);
 int qpde_bs1d_plan_kernel(const qpde_bs1d_plan *plan);
 int qpde_bs1d_plan_nodes(const qpde_bs1d_plan *plan);
 /* 1 if the plan's sweep stages its HBM streams through TMA (the INTERLEAVED family at
- * N >= 256 without policy iteration / variable steps / dividends), else 0. */
+ * N >= 32 without policy iteration, up to BDF2), else 0. */
 int qpde_bs1d_plan_tma_staged(const qpde_bs1d_plan *plan);
 /* Row length of the per-step `inner` output (upper bound on steps). */
 int qpde_bs1d_plan_max_steps(const qpde_bs1d_plan *plan);

@@ -480,10 +480,12 @@ EncodeTiledFn encode_tiled_entry() {
 bool interleaved_tma_supported(const DeviceBatch &b) {
 	// policy iteration walks several sets of operator rows and BDF3 .. BDF6 a ring of history
 	// arrays: those batches stay on k_interleaved_sweep
-	// Below ~256 nodes a pass is a few dozen tiles: the ring drains and refills three times per
-	// inner solve and the plain-load sweep, whose back substitution still finds cp / dp in L2,
-	// is faster (measured at 129 nodes: 2.35 against 2.0 TB/s algorithmic; at 513: 1.67 against 2.13).
-	return b.n_controls == 0 && b.N >= 256 && b.scheme <= QPDE_SCHEME_BDF2;
+	// With the confirming iteration counted and the right-hand side fused into the first solve the
+	// ring also wins on small systems (measured at 65 / 129 / 257 nodes: 2.9 against 2.0 - 2.3 TB/s
+	// algorithmic for the plain-load sweep); below a few tiles per pass it is all prologue.
+	int min_nodes = 32;
+	if(const char *e = std::getenv("QPDE_TMA_MIN_NODES")) { const int v = std::atoi(e); if(v >= 2) min_nodes = v; }   // tuning knob
+	return b.n_controls == 0 && b.N >= min_nodes && b.scheme <= QPDE_SCHEME_BDF2;
 }
 
 bool interleaved_tma_prepare(InterleavedTma *t, double *block, long long rows, std::string *error) {
