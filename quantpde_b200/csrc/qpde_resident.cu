@@ -682,12 +682,16 @@ k_resident_sweep(DeviceBatch b, DeviceResult out) {
 
 // Geometry (rows per thread M, threads PT) for a grid of N nodes.  P M rows are
 // available; a grid of P M + 1 nodes uses the tail equation.
+//   N <=  257: M = 8, PT =  32 (one warp per contract: no idle second warp, eight contracts per SM;
+//              2.1x over 8 x 64 at 33 .. 257 nodes.  A 4 x 32 variant for N <= 129 measured +11 % at
+//              33 / 65 nodes and -1 % at 129: not kept)
 //   N <=  513: M = 8, PT =  64      N <= 2049: M = 8, PT = 256 (or M = 4, PT = 512)
 //   N <= 2305: M = 9, PT = 256
 //   N <= 4097: M = 8, PT = 256, CL = 2 (a cluster of two CTAs per contract); N <= 8193: CL = 4
 static int pick_geometry(int N, int *M, int *PT, int *CL = nullptr) {
 	static const char *env = getenv("QPDE_RESIDENT_GEOMETRY");   // "4x512": A/B the wide variant
 	if(CL) *CL = 1;
+	if(N <= 8 * 32 + 1 && !(env && !strcmp(env, "no32"))) { *M = 8; *PT = 32; return 1; }
 	if(N <= 8 * 64 + 1)       { *M = 8; *PT = 64;  return 1; }
 	if(N <= 8 * 256 + 1) {
 		if(env && !strcmp(env, "4x512")) { *M = 4; *PT = 512; return 1; }
@@ -707,7 +711,7 @@ bool resident_supported(const DeviceBatch &b) {
 	if(CL > 1 && (b.variable_target || b.dividend_kind != QPDE_DIVIDEND_NONE)) return false; // one-CTA features
 	if(b.american && b.n_exercise > 0) return false; // penalty + events: INTERLEAVED family
 	if(b.n_controls != 0 && b.n_controls != 2) return false; // more control values: INTERLEAVED family
-	if(b.variable_target && !((M == 8 && PT == 64) || (M == 8 && PT == 256))) return false; // no room for V^n: INTERLEAVED family
+	if(b.variable_target && !((M == 8 && PT == 32) || (M == 8 && PT == 64) || (M == 8 && PT == 256))) return false; // no room for V^n: INTERLEAVED family
 	return true;
 }
 
@@ -772,6 +776,7 @@ int launch_resident(const DeviceBatch &b, const DeviceResult &out, cudaStream_t 
 	int rc;
 	if(CL == 4)                  rc = launch_rows<8, 256, false, 4>(b, out, stream);
 	else if(CL == 2)             rc = launch_rows<8, 256, false, 2>(b, out, stream);
+	else if(M == 8 && PT == 32)  rc = launch_rows<8, 32, true, 1>(b, out, stream);
 	else if(M == 8 && PT == 64)  rc = launch_rows<8, 64, true, 1>(b, out, stream);
 	else if(M == 8 && PT == 256) rc = launch_rows<8, 256, true, 1>(b, out, stream);
 	else if(M == 4 && PT == 512) rc = launch_rows<4, 512, false, 1>(b, out, stream);
