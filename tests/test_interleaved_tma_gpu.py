@@ -138,3 +138,21 @@ def test_tma_variable_stepper(qpde, handle, oracle, scheme):
         assert a.n_steps[c] == o["n_steps"]
         assert rel_err(a.V[c], o["V"]).max() <= REL_TOL
         assert np.array_equal(a.inner[c, :o["n_steps"]], o["inner"])
+
+
+def test_tma_full_occupancy_is_bit_identical(qpde, handle):
+    """Many waves of warps (seven CTAs per SM, every SM busy, HBM saturated): the ordering between the
+    ordinary stores of one pass and the TMA loads of the next must hold under load, not only in a
+    quiet machine.  20,011 contracts x 513 nodes x 60 steps, every output against the plain-load sweep."""
+    Cn, refine, steps = 20011, 4, 60
+    rng = np.random.default_rng(77)
+    K = rng.uniform(50, 150, Cn); vol = rng.uniform(.1, .6, Cn); T = rng.uniform(.25, 2., Cn); r = rng.uniform(.01, .08, Cn)
+    from bench import SPECIAL
+    spec = qpde.BatchSpec(axis=np.ascontiguousarray(K[:, None] * SPECIAL[None, :]), refine=refine, r=r, sigma=vol, q=0., T=T,
+                          dt=T / steps, strike=K, american=True, payoff="put", kernel="interleaved",
+                          outputs=qpde.OUT_V | qpde.OUT_VALUE | qpde.OUT_INNER_TOTAL | qpde.OUT_STATUS | qpde.OUT_STEPS)
+    a = _run(qpde, handle, spec, True)
+    p = _run(qpde, handle, spec, False)
+    for name in ("V", "value", "n_steps", "inner_total", "status"):
+        assert np.array_equal(getattr(a, name), getattr(p, name)), name
+    assert np.all(a.status == 0) and a.inner_total.min() >= steps
