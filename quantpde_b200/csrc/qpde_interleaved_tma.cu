@@ -191,11 +191,12 @@ k_interleaved_sweep_tma(const __grid_constant__ CUtensorMap map, DeviceBatch b, 
 		const bool is_cn = kind == STEP_CN_R || kind == STEP_CN_T;
 
 		// One row of the elimination of (lA + P) x = lb + P obstacle (the serial chain)
+		const double hsA = gA.factor(), hsb = gb.factor();   // Gamma::off(l) == l * factor(), without the switch
 		double cprev = 0., dprev = 0.;
 		auto eliminate = [&](int i, double vlo, double vdi, double vup, double rhs, double vob, double vx, bool store) {
-			double a_i = gA.off(vlo);
-			double b_i = 1. + gA.off(vdi);
-			double c_i = gA.off(vup);
+			double a_i = vlo * hsA;
+			double b_i = 1. + vdi * hsA;
+			double c_i = vup * hsA;
 			if(american) {
 				// PenaltyMethod.hpp:45,61-68: predicate on the previous iterand
 				// (scale * (x - payoff)) < 0  <=>  x < payoff
@@ -233,9 +234,9 @@ k_interleaved_sweep_tma(const __grid_constant__ CUtensorMap map, DeviceBatch b, 
 					} else {
 						// (I - A h/2) v0, row-major SpMV from zero in column order
 						double acc = 0.;
-						if(i > 0) acc += (0. - gb.off(plo)) * xm;
-						acc += (1. - gb.off(pdi)) * xc;
-						if(i < N - 1) acc += (0. - gb.off(pup)) * vp;
+						if(i > 0) acc += (0. - plo * hsb) * xm;
+						acc += (1. - pdi * hsb) * xc;
+						if(i < N - 1) acc += (0. - pup * hsb) * vp;
 						val = acc + 0.;
 					}
 					if(act) {
