@@ -332,7 +332,12 @@ k_interleaved_sweep_tma(const __grid_constant__ CUtensorMap map, DeviceBatch b, 
 							const double fa = fabs(xn), fb = fabs(xo);
 							double d = fa < fb ? fb : fa;
 							d = scale < d ? d : scale;
-							if(fabs(xn - xo) / d > tol) notdone = true;  // IterativeMethod.hpp:1131-1135
+							// IterativeMethod.hpp:1131-1135: |a - b| / max(scale, |a|, |b|) > tol.  The quotient is
+							// formed only in the rounding band around the threshold (never in practice); outside
+							// it the product form gives the same decision without a division per row.
+							const double diff = fabs(xn - xo), bound = tol * d;
+							if(diff > bound * (1. + 8e-15)) notdone = true;
+							else if(diff >= bound * (1. - 8e-15) && diff / d > tol) notdone = true;
 							if(american && ((xn < vob[u]) != (xo < vob[u]))) changed = true;
 						}
 						if(again) x[(size_t)i * ld] = xn;
