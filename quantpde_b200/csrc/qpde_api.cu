@@ -469,19 +469,22 @@ static int plan_create_impl(qpde_handle *h, const qpde_bs1d_batch *in,
 		p->wblock = nullptr;
 		const char *no_tma = getenv("QPDE_INTERLEAVED_NO_TMA");  // tuning / A-B switch: the plain-load sweep
 		if(interleaved_tma_supported(b) && !(no_tma && no_tma[0] == '1')) {
-			// one block, arrays stacked: a single tensor map over [rows][32] serves every array
+			// one block, arrays stacked: tensor maps over [array][rows][32] serve every array
 			const size_t arrays = 8 + (need_xprev ? 1 : 0) + (b.american ? 1 : 0) + (need_evobst ? 1 : 0);
 			QPDE_TRY(dev_alloc(p, &p->wblock, NC * arrays));
 			double *at = p->wblock;
 			auto take = [&](double **ptr) { *ptr = at; at += NC; };
-			take(&w.S); take(&w.lo); take(&w.di); take(&w.up); take(&w.x); take(&w.lb); take(&w.cp); take(&w.dp);
-			if(need_xprev) take(&w.xprev); else w.xprev = w.x;
+			// arrays that a pass reads together are adjacent: (lo, di, up), (obstacle, x), (cp, dp) each
+			// arrive with one TMA box
+			take(&w.S); take(&w.lo); take(&w.di); take(&w.up); take(&w.lb);
 			if(b.american) take(&w.obst);
+			take(&w.x); take(&w.cp); take(&w.dp);
+			if(need_xprev) take(&w.xprev); else w.xprev = w.x;
 			if(need_evobst) take(&w.evobst);
 			// lanes past C in the last warp of contracts are loaded (never stored): keep them finite
 			QPDE_CUDA(h, cudaMemsetAsync(p->wblock, 0, NC * arrays * sizeof(double), h->stream));
 			std::string err;
-			if(!interleaved_tma_prepare(&p->tma, p->wblock, (long long)(arrays * NC / QPDE_WARP_ROW), &err)) {
+			if(!interleaved_tma_prepare(&p->tma, p->wblock, (long long)(NC / QPDE_WARP_ROW), (int)arrays, &err)) {
 				qpde_bs1d_plan_destroy(p);
 				return fail(h, QPDE_ERR_CUDA, "INTERLEAVED (TMA): %s", err.c_str());
 			}

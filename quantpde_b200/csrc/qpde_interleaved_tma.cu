@@ -43,8 +43,13 @@ constexpr int STAGE_DOUBLES = MAX_SLOTS * SLOT_DOUBLES;
 constexpr int STAGE_BYTES = STAGE_DOUBLES * 8;   // 6 KB
 constexpr unsigned FULL = 0xffffffffu;
 
-// rows of the arrays inside the workspace block (tensor-map coordinates)
-struct TmaRows { int lo, di, up, x, xp, lb, cp, dp, ob; };
+// The workspace block is a stack of arrays; the tensor maps see it as [array][rows][32] with
+// boxes of 32 contracts x TR rows x K arrays (K = 1, 2, 3): arrays that a pass reads together are
+// adjacent in the stack — (lo, di, up), (obstacle, x), (cp, dp) — and arrive with ONE
+// cp.async.bulk.tensor instead of one per array (the issue by lane 0 costs every lane's slots).
+// These are the positions in the stack (-1 = not allocated).
+struct TmaArrays { int coef, lb, obx, x, cpdp, xp; };
+struct TmaMaps { CUtensorMap k[3]; };
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -64,11 +69,15 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
 	} while(!done);
 }
 
-// one tile: box {32 contracts, TR rows} at row `row` of the workspace block seen as [rows][32]
-__device__ __forceinline__ void tma_tile(uint32_t dst, const CUtensorMap *map, int row, uint32_t bar) {
-	asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
-		:: "r"(dst), "l"((unsigned long long)map), "r"(0), "r"(row), "r"(bar) : "memory");
+// one tile: box {32 contracts, TR rows, K arrays} at (row, array) of the workspace block
+__device__ __forceinline__ void tma_tile(uint32_t dst, const CUtensorMap *map, int row, int array, uint32_t bar) {
+	asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+		:: "r"(dst), "l"((unsigned long long)map), "r"(0), "r"(row), "r"(array), "r"(bar) : "memory");
 }
+
+// A pass reads up to three groups of adjacent arrays: group g = K arrays from stack position
+// `array` into slots slot .. slot + K - 1 of the stage (K = 0: unused).
+struct Boxes { int k[3], array[3], slot[3]; };
 
 // The ring of one warp.  Every pass issues and consumes the same number of tiles, in the
 // same order, so one stage cursor per side and one parity bit per stage are all the state.
@@ -79,19 +88,15 @@ struct Ring {
 	uint32_t parity;       // bit s: parity the next wait on stage s looks for
 };
 
-// Issues one tile per array named in `arow` (slots 0 .. NA-1; a negative row = slot unused).
-template <int NA>
-__device__ __forceinline__ void ring_issue(Ring &r, const CUtensorMap *map, int blk0, const int (&arow)[NA], int row, int lane) {
+// Issues the tile at `row` (relative to this warp's block of contracts) for every group of `bx`.
+__device__ __forceinline__ void ring_issue(Ring &r, const TmaMaps &maps, int blk0, const Boxes &bx, int row, int lane) {
 	if(lane == 0) {
 		const uint32_t bar = r.bars + 8u * r.is;
 		const uint32_t dst = r.data + (uint32_t)STAGE_BYTES * r.is;
-		int used = 0;
+		mbar_expect_tx(bar, (uint32_t)((bx.k[0] + bx.k[1] + bx.k[2]) * SLOT_DOUBLES * 8));
 #pragma unroll
-		for(int a = 0; a < NA; ++a) used += arow[a] >= 0 ? 1 : 0;
-		mbar_expect_tx(bar, (uint32_t)(used * SLOT_DOUBLES * 8));
-#pragma unroll
-		for(int a = 0; a < NA; ++a) {
-			if(arow[a] >= 0) tma_tile(dst + (uint32_t)(a * SLOT_DOUBLES * 8), map, arow[a] + blk0 + row, bar);
+		for(int g = 0; g < 3; ++g) {
+			if(bx.k[g] > 0) tma_tile(dst + (uint32_t)(bx.slot[g] * SLOT_DOUBLES * 8), &maps.k[bx.k[g] - 1], blk0 + row, bx.array[g], bar);
 		}
 	}
 	r.is = r.is + 1 == r.ns ? 0 : r.is + 1;
@@ -115,8 +120,8 @@ __device__ __forceinline__ void pass_begin() {
 }
 
 __global__ void __launch_bounds__(32, 8)
-k_interleaved_sweep_tma(const __grid_constant__ CUtensorMap map, DeviceBatch b, InterleavedWork w, DeviceResult out,
-		TmaRows tr, int stages) {
+k_interleaved_sweep_tma(const __grid_constant__ TmaMaps maps, DeviceBatch b, InterleavedWork w, DeviceResult out,
+		TmaArrays ta, int stages) {
 	extern __shared__ __align__(128) unsigned char smem_raw[];
 	const int lane = threadIdx.x;
 	const int c = blockIdx.x * 32 + lane;
@@ -220,9 +225,10 @@ k_interleaved_sweep_tma(const __grid_constant__ CUtensorMap map, DeviceBatch b, 
 				// x[i + 1]: the chain runs one row behind the tiles.
 				first = false;
 				const bool any_b2 = __any_sync(FULL, act && kind == STEP_BDF2);
-				const int arow[6] = { tr.lo, tr.di, tr.up, tr.x, american ? tr.ob : -1, any_b2 ? tr.xp : -1 };
+				// slots: lo di up | obstacle x | xprev
+				const Boxes bx = { { 3, american ? 2 : 1, any_b2 ? 1 : 0 }, { ta.coef, american ? ta.obx : ta.x, ta.xp }, { 0, american ? 3 : 4, 5 } };
 				pass_begin();
-				for(int j = 0; j < lead; ++j) ring_issue(ring, &map, blk0, arow, j * TR, lane);
+				for(int j = 0; j < lead; ++j) ring_issue(ring, maps, blk0, bx, j * TR, lane);
 				double xm = 0., xc = 0., pxp = 0., plo = 0., pdi = 0., pup = 0., pob = 0.;
 				cprev = 0.; dprev = 0.;
 				auto finish_row = [&](int i, double vp) {
@@ -252,12 +258,12 @@ k_interleaved_sweep_tma(const __grid_constant__ CUtensorMap map, DeviceBatch b, 
 #pragma unroll
 					for(int u = 0; u < TR; ++u) {
 						vlo[u] = tile[u * 32]; vdi[u] = tile[SLOT_DOUBLES + u * 32]; vup[u] = tile[2 * SLOT_DOUBLES + u * 32];
-						vx[u] = tile[3 * SLOT_DOUBLES + u * 32];
-						vob[u] = american ? tile[4 * SLOT_DOUBLES + u * 32] : 0.;
+						vob[u] = american ? tile[3 * SLOT_DOUBLES + u * 32] : 0.;
+						vx[u] = tile[4 * SLOT_DOUBLES + u * 32];
 						vxp[u] = any_b2 ? tile[5 * SLOT_DOUBLES + u * 32] : 0.;
 					}
 					__syncwarp();
-					if(j + stages < nb) ring_issue(ring, &map, blk0, arow, (j + stages) * TR, lane);
+					if(j + stages < nb) ring_issue(ring, maps, blk0, bx, (j + stages) * TR, lane);
 #pragma unroll
 					for(int u = 0; u < TR; ++u) {
 						const int i = j * TR + u;
@@ -269,9 +275,10 @@ k_interleaved_sweep_tma(const __grid_constant__ CUtensorMap map, DeviceBatch b, 
 			} else {
 			// ---- forward elimination of (lA + P) x = lb + P obstacle ------
 			{
-				const int arow[6] = { tr.lo, tr.di, tr.up, tr.lb, american ? tr.ob : -1, american ? tr.x : -1 };
+				// slots: lo di up | lb | obstacle x
+				const Boxes bx = { { 3, 1, american ? 2 : 0 }, { ta.coef, ta.lb, ta.obx }, { 0, 3, 4 } };
 				pass_begin();
-				for(int j = 0; j < lead; ++j) ring_issue(ring, &map, blk0, arow, j * TR, lane);
+				for(int j = 0; j < lead; ++j) ring_issue(ring, maps, blk0, bx, j * TR, lane);
 				cprev = 0.; dprev = 0.;
 				for(int j = 0; j < nb; ++j) {
 					const int s = ring_wait(ring);
@@ -285,7 +292,7 @@ k_interleaved_sweep_tma(const __grid_constant__ CUtensorMap map, DeviceBatch b, 
 						vx[u] = american ? tile[5 * SLOT_DOUBLES + u * 32] : 0.;
 					}
 					__syncwarp();
-					if(j + stages < nb) ring_issue(ring, &map, blk0, arow, (j + stages) * TR, lane);
+					if(j + stages < nb) ring_issue(ring, maps, blk0, bx, (j + stages) * TR, lane);
 #pragma unroll
 					for(int u = 0; u < TR; ++u) {
 						const int i = j * TR + u;
@@ -305,9 +312,10 @@ k_interleaved_sweep_tma(const __grid_constant__ CUtensorMap map, DeviceBatch b, 
 			// instead of two): without the shortcut every warp would take three solves per step.
 			bool notdone = false, changed = false;
 			{
-				const int arow[4] = { tr.cp, tr.dp, iterate ? tr.x : -1, american ? tr.ob : -1 };
+				// slots: cp dp | obstacle x   (iterate == american in this kernel)
+				const Boxes bx = { { 2, american ? 2 : 0, 0 }, { ta.cpdp, ta.obx, -1 }, { 0, 2, 0 } };
 				pass_begin();
-				for(int j = 0; j < lead; ++j) ring_issue(ring, &map, blk0, arow, N - (j + 1) * TR, lane);
+				for(int j = 0; j < lead; ++j) ring_issue(ring, maps, blk0, bx, N - (j + 1) * TR, lane);
 				double xn = 0.;
 				for(int j = 0; j < nb; ++j) {
 					const int r0 = N - (j + 1) * TR;      // first row of the tile (negative in the last one: those rows are skipped)
@@ -317,11 +325,11 @@ k_interleaved_sweep_tma(const __grid_constant__ CUtensorMap map, DeviceBatch b, 
 #pragma unroll
 					for(int u = 0; u < TR; ++u) {
 						vcp[u] = tile[u * 32]; vdp[u] = tile[SLOT_DOUBLES + u * 32];
-						vxo[u] = iterate ? tile[2 * SLOT_DOUBLES + u * 32] : 0.;
-						vob[u] = american ? tile[3 * SLOT_DOUBLES + u * 32] : 0.;
+						vob[u] = american ? tile[2 * SLOT_DOUBLES + u * 32] : 0.;
+						vxo[u] = iterate ? tile[3 * SLOT_DOUBLES + u * 32] : 0.;
 					}
 					__syncwarp();
-					if(j + stages < nb) ring_issue(ring, &map, blk0, arow, N - (j + stages + 1) * TR, lane);
+					if(j + stages < nb) ring_issue(ring, maps, blk0, bx, N - (j + stages + 1) * TR, lane);
 #pragma unroll
 					for(int u = TR - 1; u >= 0; --u) {
 						const int i = r0 + u;
@@ -494,21 +502,23 @@ bool interleaved_tma_supported(const DeviceBatch &b) {
 	return b.n_controls == 0 && b.N >= min_nodes && b.scheme <= QPDE_SCHEME_BDF2;
 }
 
-bool interleaved_tma_prepare(InterleavedTma *t, double *block, long long rows, std::string *error) {
-	static_assert(sizeof(CUtensorMap) <= sizeof(t->map), "CUtensorMap does not fit InterleavedTma::map");
+bool interleaved_tma_prepare(InterleavedTma *t, double *block, long long rows, int arrays, std::string *error) {
+	static_assert(sizeof(CUtensorMap) <= sizeof(t->map[0]), "CUtensorMap does not fit InterleavedTma::map");
 	t->enabled = false;
 	EncodeTiledFn encode = encode_tiled_entry();
 	if(!encode) { if(error) *error = "cuTensorMapEncodeTiled is not available from this driver"; return false; }
-	const cuuint64_t dims[2] = { (cuuint64_t)QPDE_WARP_ROW, (cuuint64_t)rows };
-	const cuuint64_t strides[1] = { (cuuint64_t)QPDE_WARP_ROW * sizeof(double) };
-	const cuuint32_t box[2] = { 32u, (cuuint32_t)TR };
-	const cuuint32_t estr[2] = { 1u, 1u };
-	const CUresult rc = encode(reinterpret_cast<CUtensorMap *>(t->map), CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, block,
-		dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
-		CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-	if(rc != CUDA_SUCCESS) {
-		if(error) *error = "cuTensorMapEncodeTiled failed with CUresult " + std::to_string((int)rc);
-		return false;
+	const cuuint64_t dims[3] = { (cuuint64_t)QPDE_WARP_ROW, (cuuint64_t)rows, (cuuint64_t)arrays };
+	const cuuint64_t strides[2] = { (cuuint64_t)QPDE_WARP_ROW * sizeof(double), (cuuint64_t)rows * QPDE_WARP_ROW * sizeof(double) };
+	const cuuint32_t estr[3] = { 1u, 1u, 1u };
+	for(int k = 1; k <= 3; ++k) {
+		const cuuint32_t box[3] = { 32u, (cuuint32_t)TR, (cuuint32_t)k };
+		const CUresult rc = encode(reinterpret_cast<CUtensorMap *>(t->map[k - 1]), CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, block,
+			dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+			CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+		if(rc != CUDA_SUCCESS) {
+			if(error) *error = "cuTensorMapEncodeTiled failed with CUresult " + std::to_string((int)rc);
+			return false;
+		}
 	}
 	t->stages = 0;   // chosen per launch
 	t->enabled = true;
@@ -531,11 +541,12 @@ static int tma_stages(int C, int sm_count) {
 void launch_interleaved_tma(const DeviceBatch &b, const InterleavedWork &w, const InterleavedTma &t, double *block,
 		const DeviceResult &out, cudaStream_t stream, long long *launches) {
 	launch_interleaved_setup(b, w, stream, launches);
-	auto row_of = [&](const double *p) { return p ? (int)((p - block) / QPDE_WARP_ROW) : -1; };
-	TmaRows tr;
-	tr.lo = row_of(w.lo); tr.di = row_of(w.di); tr.up = row_of(w.up);
-	tr.x = row_of(w.x); tr.xp = row_of(w.xprev); tr.lb = row_of(w.lb);
-	tr.cp = row_of(w.cp); tr.dp = row_of(w.dp); tr.ob = row_of(w.obst);
+	// positions in the stack of arrays (qpde_api.cu lays it out S, lo, di, up, lb, [obstacle], x, cp, dp, ...)
+	const long long per_array = (long long)b.N * w.ld;
+	auto index_of = [&](const double *p) { return p ? (int)((p - block) / per_array) : -1; };
+	TmaArrays ta;
+	ta.coef = index_of(w.lo); ta.lb = index_of(w.lb); ta.obx = index_of(w.obst); ta.x = index_of(w.x);
+	ta.cpdp = index_of(w.cp); ta.xp = index_of(w.xprev);
 	int device = 0, sm_count = 148;
 	cudaGetDevice(&device);
 	cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, device);
@@ -543,7 +554,9 @@ void launch_interleaved_tma(const DeviceBatch &b, const InterleavedWork &w, cons
 	const int smem = stages * STAGE_BYTES + stages * 8;
 	cudaFuncSetAttribute(k_interleaved_sweep_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
 	const int blocks = (b.C + 31) / 32;
-	k_interleaved_sweep_tma<<<blocks, 32, smem, stream>>>(*reinterpret_cast<const CUtensorMap *>(t.map), b, w, out, tr, stages);
+	TmaMaps maps;
+	for(int k = 0; k < 3; ++k) maps.k[k] = *reinterpret_cast<const CUtensorMap *>(t.map[k]);
+	k_interleaved_sweep_tma<<<blocks, 32, smem, stream>>>(maps, b, w, out, ta, stages);
 	*launches += 1;
 }
 

@@ -61,10 +61,10 @@ struct InterleavedWork {
 	long long ld;          // contracts incl. padding (an array is N x ld doubles)
 };
 
-// The TMA-staged sweep (qpde_interleaved_tma.cu) reads every array through ONE tiled tensor map
-// over the workspace block seen as [rows][32].
+// The TMA-staged sweep (qpde_interleaved_tma.cu) reads every array through tiled tensor maps over the
+// workspace block seen as [array][rows][32]: one map per box depth (1, 2 or 3 adjacent arrays).
 struct InterleavedTma {
-	alignas(64) unsigned char map[128];   // CUtensorMap (opaque here; cuda.h stays out of this header)
+	alignas(64) unsigned char map[3][128];   // CUtensorMap x 3 (opaque here; cuda.h stays out of this header)
 	bool enabled;
 	int stages;                           // ring depth (tiles in flight per warp)
 };
@@ -72,8 +72,9 @@ constexpr int QPDE_TMA_TILE_ROWS = 4;     // node rows per TMA tile (box = 32 co
 
 // true if the TMA-staged sweep covers this batch (no policy iteration, variable steps or dividends)
 bool interleaved_tma_supported(const DeviceBatch &b);
-// encodes the tensor map over `block` ([rows][32] doubles); false if the driver entry point is missing
-bool interleaved_tma_prepare(InterleavedTma *t, double *block, long long rows, std::string *error);
+// encodes the tensor maps over `block` (`arrays` arrays of `rows` x 32 doubles); false if the driver
+// entry point is missing
+bool interleaved_tma_prepare(InterleavedTma *t, double *block, long long rows, int arrays, std::string *error);
 void launch_interleaved_tma(const DeviceBatch &b, const InterleavedWork &w, const InterleavedTma &t, double *block,
 		const DeviceResult &out, cudaStream_t stream, long long *launches);
 void launch_interleaved_setup(const DeviceBatch &b, const InterleavedWork &w, cudaStream_t stream, long long *launches);
