@@ -119,6 +119,9 @@ __device__ __forceinline__ void pass_begin() {
 	__syncwarp();
 }
 
+// AMERICAN (the penalty iteration) is a compile-time variant: the box depths of every pass are then
+// constants, and the linear sweep carries none of the obstacle code.
+template <bool AMERICAN>
 __global__ void __launch_bounds__(32, 8)
 k_interleaved_sweep_tma(const __grid_constant__ TmaMaps maps, DeviceBatch b, InterleavedWork w, DeviceResult out,
 		TmaArrays ta, int stages) {
@@ -149,8 +152,8 @@ k_interleaved_sweep_tma(const __grid_constant__ TmaMaps maps, DeviceBatch b, Int
 	}
 	__syncwarp();
 
-	const bool american = b.american != 0;
-	const bool iterate = american;               // a ToleranceIteration wraps every step
+	constexpr bool american = AMERICAN;
+	constexpr bool iterate = american;             // a ToleranceIteration wraps every step
 	const bool copy_xp = b.scheme == QPDE_SCHEME_BDF2 || b.variable_target != nullptr;   // iterand(1) <- iterand(0)
 	const int nb = (N + TR - 1) / TR;            // tiles per pass
 	const int lead = nb < stages ? nb : stages;
@@ -552,11 +555,16 @@ void launch_interleaved_tma(const DeviceBatch &b, const InterleavedWork &w, cons
 	cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, device);
 	const int stages = t.stages > 0 ? t.stages : tma_stages(b.C, sm_count);
 	const int smem = stages * STAGE_BYTES + stages * 8;
-	cudaFuncSetAttribute(k_interleaved_sweep_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
 	const int blocks = (b.C + 31) / 32;
 	TmaMaps maps;
 	for(int k = 0; k < 3; ++k) maps.k[k] = *reinterpret_cast<const CUtensorMap *>(t.map[k]);
-	k_interleaved_sweep_tma<<<blocks, 32, smem, stream>>>(maps, b, w, out, ta, stages);
+	if(b.american) {
+		cudaFuncSetAttribute(k_interleaved_sweep_tma<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+		k_interleaved_sweep_tma<true><<<blocks, 32, smem, stream>>>(maps, b, w, out, ta, stages);
+	} else {
+		cudaFuncSetAttribute(k_interleaved_sweep_tma<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+		k_interleaved_sweep_tma<false><<<blocks, 32, smem, stream>>>(maps, b, w, out, ta, stages);
+	}
 	*launches += 1;
 }
 
