@@ -350,8 +350,8 @@ def main():
                          "frac": s_alg / (s_ms / 1e3) / 1e9 / speak,
                          "not_converged": int((sres.status != 0).sum()),
                          "note": "achieved = 56 B x nodes x inner solves / time (SURVEY.md 8d); the kernel itself moves "
-                                 "104 B per computed inner solve and node (DESIGN.md 4.1); ncu on the 100-step "
-                                 "capture: 5.27 TB/s of DRAM traffic = 81 % of the measured peak "
+                                 "104 B per computed inner solve and node (DESIGN.md 4.1); ncu capture of the same "
+                                 "batch at 20 steps: 6.10 TB/s of DRAM traffic = 93 % of the measured peak "
                                  "(profiles/r1_interleaved_tma_ncu_raw_subset.csv)"}
 
     peak, peak_src = load_peaks()
