@@ -31,6 +31,7 @@
 #define QUANT_PDE_B200_CORE_HPP
 
 #include <cfloat>
+#include <algorithm>
 #include <cmath>
 #include <cstdint>
 #include <functional>
@@ -228,6 +229,31 @@ public:
 			: grid(grid), r(r), v(std::move(v)), q(q), rIsControl(false) {}
 	BlackScholes1(const RectilinearGrid1 &grid, Control1, Volatility v, Real q)
 			: grid(grid), r(0.), v(std::move(v)), q(q), rIsControl(true) {}
+};
+
+// Jump amplitude densities — Modules/Lambdas/Densities (lognormal, doubleExponential) as
+// examples/jump_diffusion.cpp:88-99 builds them.  Tagged forms: the density weights and kappa are
+// produced by qpde_jump_setup(), which reproduces the reference's adaptive quadrature.
+struct JumpDensity {
+	int kind;        // 0 lognormal (Merton), 1 double exponential (Kou)
+	Real params[3];
+};
+inline JumpDensity lognormal(Real mean, Real deviation) { return JumpDensity{0, {mean, deviation, 0.}}; }
+inline JumpDensity doubleExponential(Real upProbability, Real upMeanReciprocal, Real downMeanReciprocal) {
+	return JumpDensity{1, {upProbability, upMeanReciprocal, downMeanReciprocal}};
+}
+
+// BlackScholesJumpDiffusion1(grid, r, v, q, lambda, density) — Modules/Operators/BlackScholes.hpp:271-461:
+// the jump term is explicit (the d'Halluin correlation integral of the previous iterand); runs in the
+// jump-diffusion sweep (BDF1 / BDF2, no penalty, no controls).
+class BlackScholesJumpDiffusion1 : public BlackScholes1 {
+public:
+	Real lambda; JumpDensity density;
+	BlackScholesJumpDiffusion1(const RectilinearGrid1 &grid, Real r, Volatility v, Real q, Real lambda,
+			JumpDensity density) : BlackScholes1(grid, r, std::move(v), q), lambda(lambda), density(density) {}
+	// the reference's operator reads the stepper's iterand to form its right-hand side
+	// (examples/jump_diffusion.cpp:113); here the sweep owns the iterand, so this only keeps the call shape
+	template <typename I> void setIteration(I &) {}
 };
 
 class Iteration {
@@ -516,6 +542,14 @@ public:
 		const int nControls = policy ? (int)d0->policy->controls.size() : 0;
 		std::vector<Real> controls;
 		if(policy && !tol0) throw std::invalid_argument("QuantPDE_B200: policy iteration needs setInnerIteration()");
+		// jump diffusion: density weights / kappa / log-grid per distinct (grid, density)
+		const BlackScholesJumpDiffusion1 *j0 = dynamic_cast<const BlackScholesJumpDiffusion1 *>(&d0->op);
+		const bool jump = j0 != nullptr;
+		const int nfft = jump ? qpde_jump_nfft(N) : 0;
+		std::vector<Real> jLambda, jKappa, jX0, jDx, jWeights;
+		struct JumpKey { std::vector<Real> axis; JumpDensity density; size_t at; Real x0, dx, kappa; };
+		std::vector<JumpKey> jumpKeys;
+		std::vector<int> jIndex;        // weight vector of contract c
 		for(int c = 0; c < C; ++c) {
 			const Item &it = items[c];
 			const Discretization *d; MinPenaltyMethodDifference1 *p;
@@ -529,6 +563,7 @@ public:
 					|| (dividends && (it.stepper->dividend().kind != divKind || it.stepper->dividendFirstInSweep() != divFirst))
 					|| d->op.v.model() != volModel
 					|| it.payoff.kind() != payKind || (american && p->obstacle.kind() != obsKind)
+					|| (dynamic_cast<const BlackScholesJumpDiffusion1 *>(&d->op) != nullptr) != jump
 					|| (d->policy != nullptr) != policy
 					|| (policy && ((int)d->policy->controls.size() != nControls
 						|| d->policy->maximise != d0->policy->maximise))) {
@@ -538,6 +573,31 @@ public:
 			for(int k = 0; k < nAxis; ++k) axis[(size_t)c * nAxis + k] = it.grid->coarse()[k];
 			r[c] = d->op.r; sig[c] = d->op.v.param(); q[c] = d->op.q;
 			if(policy) controls.insert(controls.end(), d->policy->controls.begin(), d->policy->controls.end());
+			if(jump) {
+				const BlackScholesJumpDiffusion1 &j = static_cast<const BlackScholesJumpDiffusion1 &>(d->op);
+				const Axis &ax = it.grid->coarse();
+				const std::vector<Real> coarse(ax.data(), ax.data() + ax.size());
+				size_t k = 0;
+				for(; k < jumpKeys.size(); ++k) {
+					const JumpKey &key = jumpKeys[k];
+					if(key.axis == coarse && key.density.kind == j.density.kind
+							&& key.density.params[0] == j.density.params[0] && key.density.params[1] == j.density.params[1]
+							&& key.density.params[2] == j.density.params[2]) break;
+				}
+				if(k == jumpKeys.size()) {
+					JumpKey key; key.axis = coarse; key.density = j.density; key.at = jumpKeys.size();
+					const std::vector<Real> S = it.grid->nodes();
+					std::vector<Real> wts((size_t)nfft);
+					const int rc = qpde_jump_setup(N, S.data(), j.density.kind, j.density.params,
+						&key.x0, &key.dx, &key.kappa, wts.data());
+					if(rc != QPDE_OK) throw std::runtime_error(std::string("QuantPDE_B200: qpde_jump_setup: ") + qpde_last_error(nullptr));
+					jumpKeys.push_back(key);
+					jWeights.insert(jWeights.end(), wts.begin(), wts.end());
+				}
+				jLambda.push_back(j.lambda); jKappa.push_back(jumpKeys[k].kappa);
+				jX0.push_back(jumpKeys[k].x0); jDx.push_back(jumpKeys[k].dx);
+				jIndex.push_back((int)k);
+			}
 			T[c] = it.stepper->expiry(); dt[c] = it.stepper->timestep();
 			if(dividends) divAmount.push_back(it.stepper->dividend().amount);
 			if(variableSteps) vTargets.push_back(it.stepper->variableTarget());
@@ -578,6 +638,22 @@ public:
 		if(policy) {
 			b.n_controls = nControls; b.policy_max = d0->policy->maximise ? 1 : 0;
 			b.controls = controls.data(); b.controls_stride = nControls;
+		}
+		std::vector<Real> jPerContract;
+		if(jump) {
+			if(american || policy) throw std::invalid_argument("QuantPDE_B200: jump diffusion takes no penalty or policy node");
+			b.jump_lambda = jLambda.data(); b.jump_kappa = jKappa.data(); b.jump_x0 = jX0.data(); b.jump_dx = jDx.data();
+			b.n_fft = nfft;
+			if(jumpKeys.size() == 1) {
+				b.jump_weights = jWeights.data(); b.jump_weights_stride = 0;      // one vector shared by the batch
+			} else {
+				jPerContract.resize((size_t)C * nfft);
+				for(int c = 0; c < C; ++c) {
+					std::copy(jWeights.begin() + (size_t)jIndex[c] * nfft, jWeights.begin() + (size_t)(jIndex[c] + 1) * nfft,
+						jPerContract.begin() + (size_t)c * nfft);
+				}
+				b.jump_weights = jPerContract.data(); b.jump_weights_stride = nfft;
+			}
 		}
 		b.penalty_tolerance = american ? p0->tol : tolerance;
 		b.spot = spot.data();
@@ -629,6 +705,93 @@ public:
 			}
 		}
 		return out;
+	}
+};
+
+////////////////////////////////////////////////////////////////////////////////
+// GMWB — the 2-D (W, A) impulse-control HJBQVI of examples/hjbqvi/gmwb.cpp.  The reference's
+// HJBQVI<2,1,1> takes the model as lambdas (Modules/HJBQVI/HJBQVI.hpp:590-754); a C ABI cannot, so
+// the model's functional forms are fixed (include/qpde_b200.h, qpde_gmwb2d) and its parameters are
+// the members below, with the example's values as defaults.  solve(refinement) does what
+// HJBQVI::solve(refinement) does with usePenalizedScheme() and HJBQVILinearBoundary /
+// HJBQVIZeroDiffusionRightBoundary: `timesteps`, the W / A axes and the impulse grid are refined
+// `refinement` times (gmwb.cpp:61-64, HJBQVI.hpp:1285-1340).
+////////////////////////////////////////////////////////////////////////////////
+class GMWB {
+public:
+	Real T, r, eta, sigma, G, kappa, c;      // gmwb.cpp:41-59 (kappa: "penalty rate k")
+	Real w_0;
+	int timesteps, controlPoints;
+	Axis wAxis, aAxis;
+	Real scalingFactor, iterationTolerance;  // HJBQVI defaults: 1e-2, 1e-6
+	int maxIterations, maxSweeps;            // guards (the reference has none)
+
+	GMWB() : T(10.), r(.05), eta(0.), sigma(.2), G(10.), kappa(.1), c(0.), w_0(100.), timesteps(32),
+			controlPoints(3),
+			wAxis({0., 5., 10., 15., 20., 25., 30., 35., 40., 45., 50., 55., 60., 65., 70., 72.5, 75., 77.5, 80.,
+				82., 84., 86., 88., 90., 91., 92., 93., 94., 95., 96., 97., 98., 99., 100., 101., 102., 103., 104.,
+				105., 106., 107., 108., 109., 110., 112., 114., 116., 118., 120., 123., 126., 130., 135., 140.,
+				145., 150., 160., 175., 200., 225., 250., 300., 500., 750., 1000.}),    // gmwb.cpp:92-105
+			aAxis(Axis::uniform(0., 100., 51)),                                          // gmwb.cpp:108
+			scalingFactor(1e-2), iterationTolerance(1e-6), maxIterations(200), maxSweeps(500) {}
+
+	struct Result {
+		std::vector<Real> W, A, V;   // V[ia * W.size() + iw] (W fastest, Core/Domain.hpp:1416-1425)
+		int steps; Real meanPolicyIterations;
+		// PiecewiseLinear<2>::interpolate (Core/Interpolant.hpp:153-181,331-374): clamped, terms with
+		// weight <= epsilon skipped
+		Real operator()(Real w, Real a) const {
+			auto bracket = [] (const std::vector<Real> &x, Real c, int &i, Real &wt) {
+				const int n = (int)x.size();
+				if(c <= x[0]) { i = 0; wt = 1.; return; }
+				if(c >= x[n - 1]) { i = n - 2; wt = 0.; return; }
+				int lo = 0, hi = n - 2, mid = 0; wt = 0.;
+				while(lo <= hi) {
+					mid = (lo + hi) / 2;
+					if(c < x[mid]) hi = mid - 1;
+					else if(c >= x[mid + 1]) lo = mid + 1;
+					else { wt = (x[mid + 1] - c) / (x[mid + 1] - x[mid]); break; }
+				}
+				i = mid;
+			};
+			int iw, ia; Real fw, fa;
+			bracket(W, w, iw, fw); bracket(A, a, ia, fa);
+			const size_t nw = W.size();
+			const Real wt[4] = { fw * fa, (1. - fw) * fa, fw * (1. - fa), (1. - fw) * (1. - fa) };
+			const size_t at[4] = { ia * nw + iw, ia * nw + iw + 1, (ia + 1) * nw + iw, (ia + 1) * nw + iw + 1 };
+			Real sum = 0.;
+			for(int m = 0; m < 4; ++m) if(wt[m] > epsilon) sum += wt[m] * V[at[m]];
+			return sum;
+		}
+	};
+
+	Result solve(B200Solver &solver, int refinement) const {
+		const Real controls[2] = { 0., G };                     // gmwb.cpp:111-114
+		const Axis impulse = Axis::uniform(0., 1., controlPoints);
+		qpde_gmwb2d g = qpde_gmwb2d();
+		g.abi_version = QPDE_ABI_VERSION; g.refine = refinement;
+		g.w_axis = wAxis.data(); g.n_w_axis = wAxis.size();
+		g.a_axis = aAxis.data(); g.n_a_axis = aAxis.size();
+		g.controls = controls; g.n_controls = 2;
+		g.impulse_axis = impulse.data(); g.n_impulse_axis = impulse.size();
+		g.T = T;
+		g.timesteps = timesteps;
+		for(int k = 0; k < refinement; ++k) g.timesteps *= 2;
+		g.max_inner = maxIterations;
+		g.r = r; g.eta = eta; g.sigma = sigma; g.kappa = kappa; g.c = c;
+		g.scaling_factor = scalingFactor; g.tolerance = iterationTolerance; g.max_sweeps = maxSweeps;
+		int nw = 0, na = 0;
+		solver.check(qpde_gmwb2d_nodes(&g, &nw, &na));
+		Result res;
+		res.W.resize(nw); res.A.resize(na); res.V.resize((size_t)nw * na);
+		qpde_gmwb2d_stats st = qpde_gmwb2d_stats();
+		solver.check(qpde_gmwb2d_solve(solver.handle(), &g, res.V.data(), res.W.data(), res.A.data(), &st));
+		if(st.status != 0) {
+			throw std::runtime_error(st.status == 1 ? "QuantPDE_B200: GMWB policy iteration hit maxIterations"
+				: "QuantPDE_B200: GMWB line sweeps did not settle");
+		}
+		res.steps = st.n_steps; res.meanPolicyIterations = st.mean_inner;
+		return res;
 	}
 };
 

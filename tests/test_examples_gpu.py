@@ -64,3 +64,51 @@ def test_vanilla_options_example_variable_timestepping(examples, golden):
         assert int(float(cols[0])) == len(golden[name + "/S"])
         assert int(float(cols[1])) == int(golden[name + "/steps"])
         assert rel_err(float(cols[3]), float(golden[name + "/value"])) <= 1e-6   # printed with 6 digits
+
+
+def test_jump_diffusion_example_reproduces_the_reference_table(examples, golden):
+    """examples/jump_diffusion.cpp:179-190 records this table for the Kou model (the only known-answer
+    table in the reference): 3.970527 at 265 nodes x 97 steps, 3.971451 at 529 x 192."""
+    out = subprocess.run([os.path.join(examples, "jump_diffusion_b200"), "jump_type=double_exponential", "k0=3", "kn=4"],
+                         check=True, capture_output=True, text=True)
+    rows = [r.split() for r in out.stdout.strip().splitlines()[1:]]
+    assert len(rows) == 2
+    for row, (nodes, steps, value, k) in zip(rows, ((265, 97, 3.970527, 3), (529, 192, 3.971451, 4))):
+        assert int(float(row[0])) == nodes and int(float(row[1])) == steps
+        assert abs(float(row[2]) - value) <= 1e-6                                  # the recorded 7 digits
+        assert rel_err(float(row[2]), float(golden["jump_kou_k%d/value" % k])) <= 1e-6   # printed with 6 digits
+    assert abs(float(rows[1][3]) - 9.242709e-04) <= 2e-9                           # the recorded "Change"
+    out = subprocess.run([os.path.join(examples, "jump_diffusion_b200"), "k0=1", "kn=3"], check=True,
+                         capture_output=True, text=True)                          # Merton (the example's default)
+    rows = [r.split() for r in out.stdout.strip().splitlines()[1:]]
+    for row, k in ((rows[0], 1), (rows[2], 3)):
+        assert int(float(row[1])) == int(golden["jump_merton_k%d/steps" % k])
+        assert rel_err(float(row[2]), float(golden["jump_merton_k%d/value" % k])) <= 1e-6
+
+
+@pytest.mark.parametrize("position", ["short", "long"])
+def test_unequal_borrowing_lending_rates_example(examples, golden, position):
+    out = subprocess.run([os.path.join(examples, "unequal_borrowing_lending_rates_b200"), "kn=2",
+                          "long_position=%d" % (position == "long")], check=True, capture_output=True, text=True)
+    rows = [r.split() for r in out.stdout.strip().splitlines()[1:]]
+    assert len(rows) == 3
+    for k, row in enumerate(rows):
+        name = "hjb_%s_bdf2_k%d" % (position, k)       # outputs of the reference's own example wiring
+        inner = golden[name + "/inner"]
+        assert int(float(row[0])) == len(golden[name + "/S"]) and int(float(row[1])) == int(golden[name + "/steps"])
+        assert abs(float(row[2]) - inner.mean()) <= 1e-6 * max(1., inner.mean())   # "Mean Policy Iterations"
+        assert rel_err(float(row[3]), float(golden[name + "/value"])) <= 1e-6
+
+
+def test_gmwb_example_table(examples):
+    """examples/hjbqvi/gmwb.cpp through QuantPDE_B200::GMWB: values and "Mean Policy Iterations" of the
+    reference's own runs (tests/golden/gmwb_reference.npz) at refinements 0 and 1."""
+    g = np.load(os.path.join(ROOT, "tests", "golden", "gmwb_reference.npz"), allow_pickle=False)
+    out = subprocess.run([os.path.join(examples, "gmwb_b200"), "max_refinement=1"], check=True,
+                         capture_output=True, text=True)
+    rows = [r.split() for r in out.stdout.strip().splitlines()[1:]]
+    assert len(rows) == 2
+    for row, name in zip(rows, ("gmwb_k0", "gmwb_k1")):
+        assert int(row[0]) == g[name + "/V"].size and int(row[3]) == int(g[name + "/steps"])
+        assert abs(float(row[6]) - float(g[name + "/mean_inner"])) <= 1e-12       # identical policy iteration counts
+        assert rel_err(float(row[8]), float(g[name + "/value"])) <= REL_TOL
