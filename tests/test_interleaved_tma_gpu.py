@@ -156,3 +156,21 @@ def test_tma_full_occupancy_is_bit_identical(qpde, handle):
     for name in ("V", "value", "n_steps", "inner_total", "status"):
         assert np.array_equal(getattr(a, name), getattr(p, name)), name
     assert np.all(a.status == 0) and a.inner_total.min() >= steps
+
+
+@pytest.mark.parametrize("n_nodes", [32, 33, 34, 35, 37, 63])
+@pytest.mark.parametrize("Cn", [1, 31, 33])
+def test_tma_ragged_tiles_and_warps(qpde, handle, n_nodes, Cn):
+    """every residue of N modulo the 4-row tile (incl. the smallest grid the ring takes, 32 nodes) and
+    batches below / above one warp of contracts: equal to the plain-load sweep bit for bit"""
+    rng = np.random.default_rng(1000 * n_nodes + Cn)
+    K = rng.uniform(80., 120., Cn)
+    base = np.concatenate([[0.], np.sort(rng.uniform(.3, 2.5, n_nodes - 2)), [6.]])
+    axis = K[:, None] * base[None, :]
+    spec = qpde.BatchSpec(axis=axis, refine=0, r=.04, sigma=rng.uniform(.15, .4, Cn), q=0., T=1., dt=1. / 25, strike=K,
+                          scheme="rannacher", american=True, payoff="put", kernel="interleaved")
+    a = _run(qpde, handle, spec, True)
+    p = _run(qpde, handle, spec, False)
+    for name in FIELDS:
+        assert np.array_equal(getattr(a, name), getattr(p, name)), name
+    assert np.all(a.status == 0) and np.all(np.isfinite(a.V))
