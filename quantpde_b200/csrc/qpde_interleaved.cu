@@ -174,6 +174,7 @@ k_interleaved_sweep(DeviceBatch b, InterleavedWork w, DeviceResult out) {
 		// (a penalty or policy node in the tree keeps LinearSystem's default: never)
 		if(iterate || !ns.initialized || !ns.a_same(st.same_dt)) gA = gb;
 		double *it1 = xp + (size_t)head * NC;       // iterand(1)
+		const double hsA = gA.factor(), hsb = gb.factor();
 
 		// ---- lb = root.b(t) of the discretisation node ------------------
 		// x holds iterand(0) = V^n, xp holds iterand(1) for BDF2.
@@ -204,9 +205,9 @@ k_interleaved_sweep(DeviceBatch b, InterleavedWork w, DeviceResult out) {
 					} else {
 						// (I - A h/2) v0, row-major SpMV from zero in column order
 						double acc = 0.;
-						if(i > 0) acc += (0. - gb.off(vlo[u])) * vm;
-						acc += (1. - gb.off(vdi[u])) * vi;
-						if(i < N - 1) acc += (0. - gb.off(vup[u])) * vp;
+						if(i > 0) acc += (0. - vlo[u] * hsb) * vm;
+						acc += (1. - vdi[u] * hsb) * vi;
+						if(i < N - 1) acc += (0. - vup[u] * hsb) * vp;
 						val = acc + 0.;
 					}
 					lb[(size_t)i * C] = val;
@@ -243,9 +244,9 @@ k_interleaved_sweep(DeviceBatch b, InterleavedWork w, DeviceResult out) {
 					for(int u = 0; u < ROWS; ++u) {
 						if(ib + u >= N) break;
 						const size_t at = (size_t)(ib + u) * C;
-						double a_i = gA.off(vlo[u]);
-						double b_i = 1. + gA.off(vdi[u]);
-						double c_i = gA.off(vup[u]);
+						double a_i = vlo[u] * hsA;            // Gamma::off(l) == l * factor(), without the switch per row
+						double b_i = 1. + vdi[u] * hsA;
+						double c_i = vup[u] * hsA;
 						double rhs = vlb[u];
 						if(b.american) {
 							// PenaltyMethod.hpp:45,61-68: predicate on the previous iterand
@@ -317,7 +318,11 @@ k_interleaved_sweep(DeviceBatch b, InterleavedWork w, DeviceResult out) {
 						const double fa = fabs(xn), fb = fabs(xo);
 						double d = fa < fb ? fb : fa;
 						d = scale < d ? d : scale;
-						if(fabs(xn - xo) / d > tol) notdone = true;  // IterativeMethod.hpp:1131-1135
+						// IterativeMethod.hpp:1131-1135, decided in product form; the quotient is formed only
+						// in the rounding band around the threshold (same decisions, no division per row)
+						const double diff = fabs(xn - xo), bound = tol * d;
+						if(diff > bound * (1. + 8e-15)) notdone = true;
+						else if(diff >= bound * (1. - 8e-15) && diff / d > tol) notdone = true;
 					}
 					x[at] = xn;
 				}
