@@ -12,16 +12,17 @@
 // pays the HBM latency once per block of rows and needs registers for everything in
 // flight; here a warp of 32 contracts owns a ring of shared-memory stages that the TMA
 // unit fills with tiles of 32 contracts x 4 node rows per array (1 KB, contiguous; one
-// cp.async.bulk.tensor per array and tile, issued by lane 0, completion on an mbarrier),
-// so that `stages` tiles are in flight per warp while the chain runs, at no register
-// cost.  All control flow that surrounds a tile is warp-uniform (votes); what differs
+// cp.async.bulk.tensor per group of adjacent arrays and tile, issued by lane 0, completion
+// on an mbarrier), so that `stages` tiles are in flight per warp while the chain runs, at
+// no register cost.  All control flow that surrounds a tile is warp-uniform (votes); what differs
 // per contract (step kind, number of penalty iterations, number of steps) is a
 // predicate on the stores.
 //
 // Passes per time step: the first solve forms the right-hand side on the way (reads lo, di,
 // up, x [+ obstacle, xprev], writes lb, cp, dp [+ xprev]), every further penalty iteration
-// has a forward elimination (reads lo, di, up, lb
-// [+ obstacle, x], writes cp, dp) and a back substitution (reads cp, dp [+ x, obstacle], writes x).
+// has a forward elimination (reads lo, di, up, lb [+ obstacle, x], writes cp, dp), and every
+// solve a back substitution (reads cp, dp [+ obstacle, x], writes x).  A penalty iteration
+// whose active set equals the previous one's is counted, not computed.
 // Results written with ordinary stores are read by later TMA loads: every pass starts
 // with a device-scope fence + fence.proxy.async.
 #include <cuda.h>
@@ -196,7 +197,6 @@ k_interleaved_sweep_tma(const __grid_constant__ TmaMaps maps, DeviceBatch b, Int
 			if(iterate || !ns.initialized || !ns.a_same(st.same_dt)) gA = gb;
 		}
 		const double rden = 1. / den;
-		const bool is_cn = kind == STEP_CN_R || kind == STEP_CN_T;
 
 		// One row of the elimination of (lA + P) x = lb + P obstacle (the serial chain)
 		const double hsA = gA.factor(), hsb = gb.factor();   // Gamma::off(l) == l * factor(), without the switch
