@@ -252,6 +252,9 @@ typedef struct {
 /* ---- context ---------------------------------------------------------- */
 int qpde_abi_version(void);
 int qpde_create(int device, qpde_handle **out);
+/* A handle keeps device blocks of destroyed plans (up to 2 GB each, 6 GB in all) for its next plan,
+ * so that back-to-back qpde_bs1d_sweep() calls do not pay cudaMalloc / cudaFree; qpde_destroy()
+ * releases them. */
 int qpde_destroy(qpde_handle *h);
 const char *qpde_last_error(const qpde_handle *h); /* h may be NULL: global */
 /* The CUDA stream (cudaStream_t) every launch of this handle goes to, for

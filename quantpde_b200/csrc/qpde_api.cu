@@ -27,12 +27,45 @@ void set_global_error(const std::string &s) {
 
 } // namespace
 
+// Device blocks of destroyed plans, kept for the next plan of this handle: qpde_bs1d_sweep() makes a
+// plan per call, and cudaMalloc / cudaFree of its gigabyte-sized outputs cost 15 - 180 ms per call
+// (cudaFree also waits for the device).  Everything on a handle runs on its one stream, so a recycled
+// block is ordered behind its last use.  Only blocks up to POOL_MAX_BLOCK are kept, up to
+// POOL_MAX_TOTAL in all (the multi-gigabyte INTERLEAVED workspaces go back to the driver).
+struct DevicePool {
+	static constexpr size_t POOL_MAX_BLOCK = (size_t)2 << 30, POOL_MAX_TOTAL = (size_t)6 << 30;
+	std::vector<std::pair<size_t, void *>> blocks;   // (bytes, pointer)
+	size_t bytes = 0;
+	void *take(size_t want) {
+		size_t best = blocks.size();
+		for(size_t k = 0; k < blocks.size(); ++k) {
+			const size_t have = blocks[k].first;
+			if(have >= want && have <= want + want / 8 + 4096 && (best == blocks.size() || have < blocks[best].first)) best = k;
+		}
+		if(best == blocks.size()) return nullptr;
+		void *ptr = blocks[best].second;
+		bytes -= blocks[best].first;
+		blocks.erase(blocks.begin() + (long)best);
+		return ptr;
+	}
+	void give(size_t size, void *ptr) {
+		if(size > POOL_MAX_BLOCK || bytes + size > POOL_MAX_TOTAL) { cudaFree(ptr); return; }
+		blocks.emplace_back(size, ptr);
+		bytes += size;
+	}
+	void release() {
+		for(auto &blk : blocks) cudaFree(blk.second);
+		blocks.clear(); bytes = 0;
+	}
+};
+
 struct qpde_handle {
 	int device;
 	int sm_count;
 	cudaStream_t stream;
 	long long launches;
 	std::string error;
+	DevicePool pool;
 };
 
 struct qpde_bs1d_plan {
@@ -46,7 +79,7 @@ struct qpde_bs1d_plan {
 	bool jump;
 	int kernel;
 	int outputs;
-	std::vector<void *> allocations;
+	std::vector<std::pair<size_t, void *>> allocations;   // (bytes, pointer)
 };
 
 namespace {
@@ -73,9 +106,20 @@ int fail(qpde_handle *h, int code, const char *fmt, ...) {
 
 template <typename T>
 int dev_alloc(qpde_bs1d_plan *p, T **out, size_t count) {
-	void *ptr = nullptr;
-	QPDE_CUDA(p->h, cudaMalloc(&ptr, count * sizeof(T) > 0 ? count * sizeof(T) : 8));
-	p->allocations.push_back(ptr);
+	size_t bytes = count * sizeof(T) > 0 ? count * sizeof(T) : 8;
+	bytes = (bytes + 255) / 256 * 256;
+	void *ptr = p->h->pool.take(bytes);
+	if(!ptr) {
+		cudaError_t err = cudaMalloc(&ptr, bytes);
+		if(err != cudaSuccess && !p->h->pool.blocks.empty()) {
+			// out of memory with blocks parked in the pool: give them back and try again
+			(void)cudaGetLastError();
+			p->h->pool.release();
+			err = cudaMalloc(&ptr, bytes);
+		}
+		QPDE_CUDA(p->h, err);
+	}
+	p->allocations.emplace_back(bytes, ptr);
 	*out = (T *)ptr;
 	return QPDE_OK;
 }
@@ -170,6 +214,7 @@ int qpde_destroy(qpde_handle *h) {
 	if(!h) return QPDE_OK;
 	cudaSetDevice(h->device);
 	cudaStreamSynchronize(h->stream);
+	h->pool.release();
 	cudaStreamDestroy(h->stream);
 	delete h;
 	return QPDE_OK;
@@ -249,7 +294,7 @@ int qpde_bs1d_plan_destroy(qpde_bs1d_plan *p) {
 	if(!p) return QPDE_OK;
 	cudaSetDevice(p->h->device);
 	cudaStreamSynchronize(p->h->stream);
-	for(void *ptr : p->allocations) cudaFree(ptr);
+	for(auto &blk : p->allocations) p->h->pool.give(blk.first, blk.second);
 	delete p;
 	return QPDE_OK;
 }
