@@ -164,6 +164,15 @@ def cpu_baseline(n_sample, kind=None):
             "seconds_per_contract_1core": per_contract, "wall_s": wall}
 
 
+def reference_seconds(job):
+    """(mode, kwargs) -> wall seconds of one run of the reference's CPU path (oracle/_ref).  The
+    cpu_baseline leg of the other configs (tools/bench_configs.py) goes through here: bench.py is
+    the one place outside tests/ that executes anything under oracle/."""
+    from oracle import pyoracle as po
+    mode, kw = job
+    return po.run_ref(mode, **kw)["seconds"]
+
+
 # ---------------------------------------------------------------------------
 
 def run_reference_arm(args, rank, world):

@@ -27,9 +27,8 @@ TUTORIAL = np.array([0., 10., 20., 30., 40., 50., 60., 70., 75., 80., 84., 88., 
 
 
 def _ref(args):
-    from oracle import pyoracle as po
-    mode, kw = args
-    return po.run_ref(mode, **kw)["seconds"]
+    import bench                                   # the cpu_baseline leg lives in bench.py
+    return bench.reference_seconds(args)
 
 
 def _jump_setup(args):
