@@ -138,9 +138,14 @@ int upload_rows(qpde_bs1d_plan *p, const double *host, long long stride,
 	} else {
 		int rc = dev_alloc(p, &d, (size_t)rows * cols);
 		if(rc) return rc;
-		QPDE_CUDA(p->h, cudaMemcpy2DAsync(d, sizeof(double) * cols, host,
-			sizeof(double) * stride, sizeof(double) * cols, rows,
-			cudaMemcpyHostToDevice, p->h->stream));
+		if(stride == cols) {
+			QPDE_CUDA(p->h, cudaMemcpyAsync(d, host, sizeof(double) * (size_t)rows * cols,
+				cudaMemcpyHostToDevice, p->h->stream));      // dense: one copy, not a pitched one
+		} else {
+			QPDE_CUDA(p->h, cudaMemcpy2DAsync(d, sizeof(double) * cols, host,
+				sizeof(double) * stride, sizeof(double) * cols, rows,
+				cudaMemcpyHostToDevice, p->h->stream));
+		}
 		*dstride = cols;
 	}
 	*dev = d;
