@@ -142,8 +142,8 @@ if "--no-gmwb" in sys.argv:
     sys.exit(0)
 
 # ---------------------------------------------------------------------------
-# GMWB (examples/hjbqvi/gmwb.cpp): fixtures of the reference for the §8(a) row 17
-# path that the device code does not cover yet.
+# GMWB (examples/hjbqvi/gmwb.cpp): fixtures of the reference for the §8(a) row 17 path
+# (qpde_gmwb2d_solve, oracle/qpde_oracle_gmwb.c).
 # ---------------------------------------------------------------------------
 gm = {}
 for name, kw in (("gmwb_small", dict(refine=0, a_points=11, timesteps=8, control_points=3)),
