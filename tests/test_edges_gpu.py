@@ -169,3 +169,23 @@ def test_american_call_with_dividends_both_kernels(qpde, handle, oracle):
         assert np.array_equal(res.inner[0, :o["n_steps"]], o["inner"])
         payoff = np.where(o["S"] < 100., 0., o["S"] - 100.)
         assert mask_mismatches(res.active[0], o["mask"], o["V"], payoff)[0] == 0
+
+
+def test_tiny_grids_stay_on_the_plain_load_sweep(qpde, handle, oracle):
+    """fewer than 32 nodes: the INTERLEAVED family keeps its plain-load sweep (a TMA pass would be all
+    prologue); 12 and 31 nodes against the oracle"""
+    for n_nodes in (12, 31):
+        S = np.concatenate([[0.], np.linspace(40., 160., n_nodes - 2), [400.]])
+        K, r, vol, T, steps = 100., .04, .3, 1., 20
+        lo, di, up = oracle.bs_coeffs(S, r, vol, 0.)
+        payoff = np.where(S < K, K - S, 0.)
+        st, n = oracle.schedule(T, T / steps)
+        o = oracle.sweep(S, lo, di, up, payoff, T, st, n, american=True, obstacle=payoff)
+        spec = qpde.BatchSpec(axis=np.tile(S, (3, 1)), refine=0, r=r, sigma=vol, q=0., T=T, dt=T / steps,
+                              strike=np.full(3, K), american=True, payoff="put", kernel="interleaved")
+        with qpde.Plan(handle, spec) as plan:
+            assert plan.kernel == "interleaved" and not plan.tma_staged
+            plan.run()
+            res = plan.fetch()
+        assert rel_err(res.V[2], o["V"]).max() <= REL_TOL
+        assert np.array_equal(res.inner[2, :n], o["inner"])
