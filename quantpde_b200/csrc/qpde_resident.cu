@@ -56,7 +56,10 @@ struct Smem {
 	// the scalar "tail" equation (row N-1 when N = P M + 1); touched only by
 	// its owner, the last thread
 	struct Tail { double S, di, x, pz, bd, me, lb, invb, pq, vprev, c, vn; } tail;
-	unsigned flags[2];
+	// block-wide flags of one inner iteration (not converged / active set changed): one byte per warp
+	// of the system, written with a plain store before the barrier and OR-ed by every thread after it
+	// (an atomicOr here put its round trip in front of the barrier); two slots used alternately
+	alignas(8) unsigned char wflags[2][PS_MAX_WARPS];
 	double red[PS_MAX_WARPS];   // max-reduction of the variable stepper's relativeError
 };
 
@@ -265,7 +268,7 @@ k_resident_sweep(DeviceBatch b, DeviceResult out) {
 	}
 	x_next = i0 + M < n_main ? initial_value(i0 + M) : 0.;
 	publish_last(x[M - 1]);
-	if(tid == 0) { if(rank == 0) sm_xlast[0] = 0.; sm.flags[0] = 0u; sm.flags[1] = 0u; }
+	if(tid == 0 && rank == 0) sm_xlast[0] = 0.;
 
 	// PenaltyMethod.hpp:45,61-66: row penalised iff (scale * (x - payoff)) < 0,
 	// i.e. iff x < payoff (scale > 0 and the difference of two distinct doubles
@@ -498,13 +501,26 @@ k_resident_sweep(DeviceBatch b, DeviceResult out) {
 				const unsigned wbits = __reduce_or_sync(FULL, bits);
 				const unsigned slot = flip & 1u;   // two slots used alternately
 				++flip;
-				if(lane == 0 && wbits) {
+				if(lane == 0) {
 #pragma unroll
-					for(int q = 0; q < CL; ++q) atomicOr(&peer_sm[q]->flags[slot], wbits);   // every CTA sees every flag
+					for(int q = 0; q < CL; ++q) peer_sm[q]->wflags[slot][warp] = (unsigned char)wbits;   // every CTA sees every flag
 				}
 				team_sync<CL>();
-				const unsigned all = *(volatile unsigned *)&sm.flags[slot];
-				if(tid == 0) sm.flags[slot ^ 1u] = 0u;       // ordered by the barrier inside the next solve
+				unsigned all = 0u;
+				{
+					constexpr int W = CL * (PT / 32);          // warps of the whole system
+					if(W % 8 == 0) {
+						const unsigned long long *words = reinterpret_cast<const unsigned long long *>(sm.wflags[slot]);
+						unsigned long long acc = 0ull;
+#pragma unroll
+						for(int k = 0; k < W / 8; ++k) acc |= words[k];
+						acc |= acc >> 32; acc |= acc >> 16; acc |= acc >> 8;
+						all = (unsigned)acc & 3u;
+					} else {
+#pragma unroll
+						for(int k = 0; k < W; ++k) all |= sm.wflags[slot][k];
+					}
+				}
 				const bool notdone = (all & 1u) != 0, changed = (all & 2u) != 0;
 				refactor = changed;
 				again = notdone;
