@@ -97,6 +97,18 @@ def test_european_converges_to_black_scholes(oracle):
     assert all(r > 3.0 for r in ratios)            # second order: ratio -> 4
 
 
+@pytest.mark.parametrize("scheme", ["bdf3", "bdf4", "bdf5", "bdf6"])
+def test_high_order_bdf_converges_to_black_scholes(oracle, scheme):
+    """closed-form anchor for the BDF3 .. BDF6 restatement (the spatial error, second order, dominates)"""
+    exact = _bs_put(100., 100., .04, .2, 1.)
+    errs = []
+    for k in range(4):
+        out = oracle.american_put(100., .04, .2, 1., 12 * 2 ** k, k, american=False, scheme=scheme)
+        errs.append(abs(oracle.interp(out["S"], out["V"], 100.) - exact))
+    assert errs[-1] < 2e-3
+    assert all(errs[i] / errs[i + 1] > 3.0 for i in range(len(errs) - 1))
+
+
 def test_american_table_ratio_and_properties(oracle):
     vals, its = [], []
     for k in range(4):
