@@ -112,3 +112,20 @@ def test_gmwb_example_table(examples):
         assert int(row[0]) == g[name + "/V"].size and int(row[3]) == int(g[name + "/steps"])
         assert abs(float(row[6]) - float(g[name + "/mean_inner"])) <= 1e-12       # identical policy iteration counts
         assert rel_err(float(row[8]), float(g[name + "/value"])) <= REL_TOL
+
+
+def test_batch_example_many_contracts_in_one_sweep(examples, oracle):
+    """QuantPDE_B200::Batch from C++: 200 American puts in one device sweep; the printed contracts
+    against the oracle"""
+    out = subprocess.run([os.path.join(examples, "batch_american_b200"), "contracts=200", "refine=3", "steps=100"],
+                         check=True, capture_output=True, text=True)
+    lines = out.stdout.strip().splitlines()
+    head = lines[0].split()
+    assert int(head[1]) == 200 and int(head[3]) == 257
+    assert 1.5 < float(head[9]) < 4.0                                   # mean penalty iterations per step
+    assert len(lines) == 4
+    for ln in lines[1:]:
+        t = ln.split()
+        K, vol, T, r, V = (float(t[i]) for i in (3, 5, 7, 9, 11))
+        o = oracle.american_put(K, r, vol, T, 100, 3)
+        assert rel_err(V, oracle.interp(o["S"], o["V"], K)) <= REL_TOL
