@@ -423,10 +423,16 @@ static int plan_create_impl(qpde_handle *h, const qpde_bs1d_batch *in,
 	b.pen = in->american ? 1. / in->penalty_tolerance : 0.;
 	b.n_controls = in->n_controls; b.policy_max = in->policy_max ? 1 : 0;
 
-	int max_steps = in->max_steps;
-	if(max_steps <= 0) {
+	// Row length of the per-step outputs.  Constant steps: at least the bound of the replayed loop (a
+	// smaller caller value would put inner[] out of bounds); variable steps: the caller's capacity.
+	int max_steps = in->max_steps > 0 ? in->max_steps : 0;
+	if(!in->variable_target) {
 		for(int c = 0; c < C; ++c) {
 			const int bound = replay_step_bound(in->T[c], in->dt[c], in->n_exercise);
+			if(bound < 0) {
+				delete p;
+				return fail(h, QPDE_ERR_INVALID, "contract %d: T / dt is too large (more than 2^30 steps)", c);
+			}
 			if(bound > max_steps) max_steps = bound;
 		}
 	}
@@ -478,7 +484,10 @@ static int plan_create_impl(qpde_handle *h, const qpde_bs1d_batch *in,
 	if(outputs & QPDE_OUT_INNER)  { QPDE_TRY(dev_alloc(p, &o.inner, (size_t)C * max_steps)); o.inner_stride = max_steps; }
 	if(outputs & QPDE_OUT_ACTIVE) { QPDE_TRY(dev_alloc(p, &o.active, (size_t)C * N)); o.active_stride = N; }
 	if(outputs & QPDE_OUT_STATUS) QPDE_TRY(dev_alloc(p, &o.status, (size_t)C));
-	if(o.inner) QPDE_CUDA(h, cudaMemsetAsync(o.inner, 0, (size_t)C * max_steps, h->stream));
+	if(o.inner && cudaMemsetAsync(o.inner, 0, (size_t)C * max_steps, h->stream) != cudaSuccess) {
+		qpde_bs1d_plan_destroy(p);
+		return fail(h, QPDE_ERR_CUDA, "cudaMemsetAsync(inner) failed: %s", cudaGetErrorString(cudaGetLastError()));
+	}
 
 	// kernel choice
 	int kernel = in->kernel;
@@ -532,7 +541,10 @@ static int plan_create_impl(qpde_handle *h, const qpde_bs1d_batch *in,
 			if(need_xprev) take(&w.xprev); else w.xprev = w.x;
 			if(need_evobst) take(&w.evobst);
 			// lanes past C in the last warp of contracts are loaded (never stored): keep them finite
-			QPDE_CUDA(h, cudaMemsetAsync(p->wblock, 0, NC * arrays * sizeof(double), h->stream));
+			if(cudaMemsetAsync(p->wblock, 0, NC * arrays * sizeof(double), h->stream) != cudaSuccess) {
+				qpde_bs1d_plan_destroy(p);
+				return fail(h, QPDE_ERR_CUDA, "cudaMemsetAsync(workspace) failed: %s", cudaGetErrorString(cudaGetLastError()));
+			}
 			std::string err;
 			if(!interleaved_tma_prepare(&p->tma, p->wblock, (long long)(NC / QPDE_WARP_ROW), (int)arrays, &err)) {
 				qpde_bs1d_plan_destroy(p);
@@ -625,6 +637,23 @@ int qpde_bs1d_plan_fetch(qpde_bs1d_plan *p, qpde_bs1d_result *r) {
 	return QPDE_OK;
 }
 
+} // extern "C" (reopened below)
+
+// One validation for the single-GPU solve and the sharded entry points.
+static int gmwb_validate(qpde_handle *h, const qpde_gmwb2d *g) {
+	if(g->abi_version != QPDE_ABI_VERSION) return fail(h, QPDE_ERR_INVALID, "problem.abi_version %d != %d", g->abi_version, QPDE_ABI_VERSION);
+	if(!g->w_axis || !g->a_axis || g->n_w_axis < 3 || g->n_a_axis < 3) return fail(h, QPDE_ERR_INVALID, "gmwb: axes need >= 3 ticks");
+	if(!g->controls || g->n_controls < 1 || g->n_controls > 16) return fail(h, QPDE_ERR_INVALID, "gmwb: 1 .. 16 stochastic controls");
+	if(!g->impulse_axis || g->n_impulse_axis < 2) return fail(h, QPDE_ERR_INVALID, "gmwb: impulse axis needs >= 2 ticks");
+	if(g->refine < 0 || g->refine > 8) return fail(h, QPDE_ERR_INVALID, "gmwb: refine out of range");
+	if(!(g->T > 0.) || g->timesteps < 1 || g->max_inner < 1 || g->max_sweeps < 1) return fail(h, QPDE_ERR_INVALID, "gmwb: T, timesteps, max_inner, max_sweeps must be positive");
+	if(!(g->scaling_factor > 0.) || !(g->tolerance > 0.)) return fail(h, QPDE_ERR_INVALID, "gmwb: scaling_factor and tolerance must be > 0");
+	if(g->w_axis[0] != 0. || g->a_axis[0] != 0.) return fail(h, QPDE_ERR_INVALID, "gmwb: both axes start at 0 (no left boundary routine, as in the reference model)");
+	return QPDE_OK;
+}
+
+extern "C" {
+
 int qpde_gmwb2d_nodes(const qpde_gmwb2d *g, int *nodes_w, int *nodes_a) {
 	if(!g || !nodes_w || !nodes_a) return QPDE_ERR_INVALID;
 	*nodes_w = qpde_refined_size(g->n_w_axis, g->refine);
@@ -636,14 +665,7 @@ int qpde_gmwb2d_solve(qpde_handle *h, const qpde_gmwb2d *g, double *V, double *W
 		qpde_gmwb2d_stats *stats) {
 	if(!h) return fail(nullptr, QPDE_ERR_INVALID, "qpde_gmwb2d_solve: NULL handle");
 	if(!g || !V) return fail(h, QPDE_ERR_INVALID, "qpde_gmwb2d_solve: NULL argument");
-	if(g->abi_version != QPDE_ABI_VERSION) return fail(h, QPDE_ERR_INVALID, "problem.abi_version %d != %d", g->abi_version, QPDE_ABI_VERSION);
-	if(!g->w_axis || !g->a_axis || g->n_w_axis < 3 || g->n_a_axis < 3) return fail(h, QPDE_ERR_INVALID, "gmwb: axes need >= 3 ticks");
-	if(!g->controls || g->n_controls < 1 || g->n_controls > 16) return fail(h, QPDE_ERR_INVALID, "gmwb: 1 .. 16 stochastic controls");
-	if(!g->impulse_axis || g->n_impulse_axis < 2) return fail(h, QPDE_ERR_INVALID, "gmwb: impulse axis needs >= 2 ticks");
-	if(g->refine < 0 || g->refine > 8) return fail(h, QPDE_ERR_INVALID, "gmwb: refine out of range");
-	if(!(g->T > 0.) || g->timesteps < 1 || g->max_inner < 1 || g->max_sweeps < 1) return fail(h, QPDE_ERR_INVALID, "gmwb: T, timesteps, max_inner, max_sweeps must be positive");
-	if(!(g->scaling_factor > 0.) || !(g->tolerance > 0.)) return fail(h, QPDE_ERR_INVALID, "gmwb: scaling_factor and tolerance must be > 0");
-	if(g->w_axis[0] != 0. || g->a_axis[0] != 0.) return fail(h, QPDE_ERR_INVALID, "gmwb: both axes start at 0 (no left boundary routine, as in the reference model)");
+	{ const int vrc = gmwb_validate(h, g); if(vrc != QPDE_OK) return vrc; }
 	int nw = 0, na = 0;
 	if(qpde_gmwb2d_nodes(g, &nw, &na) != QPDE_OK) return fail(h, QPDE_ERR_INVALID, "gmwb: bad grid");
 	const int nz = qpde_refined_size(g->n_impulse_axis, g->refine);
@@ -670,13 +692,10 @@ int qpde_gmwb2d_shard_create(qpde_handle *h, const qpde_gmwb2d *g, int a_begin, 
 	if(!h) return fail(nullptr, QPDE_ERR_INVALID, "qpde_gmwb2d_shard_create: NULL handle");
 	if(!g || !out) return fail(h, QPDE_ERR_INVALID, "qpde_gmwb2d_shard_create: NULL argument");
 	*out = nullptr;
-	if(g->abi_version != QPDE_ABI_VERSION) return fail(h, QPDE_ERR_INVALID, "problem.abi_version %d != %d", g->abi_version, QPDE_ABI_VERSION);
+	{ const int vrc = gmwb_validate(h, g); if(vrc != QPDE_OK) return vrc; }
 	int nw = 0, na = 0;
-	if(!g->w_axis || !g->a_axis || !g->controls || !g->impulse_axis || g->n_controls < 1 || g->n_impulse_axis < 2
-			|| qpde_gmwb2d_nodes(g, &nw, &na) != QPDE_OK || !(g->T > 0.) || g->timesteps < 1
-			|| !(g->scaling_factor > 0.) || !(g->tolerance > 0.)) {
-		return fail(h, QPDE_ERR_INVALID, "gmwb shard: bad problem description");
-	}
+	if(qpde_gmwb2d_nodes(g, &nw, &na) != QPDE_OK) return fail(h, QPDE_ERR_INVALID, "gmwb: bad grid");
+	if(a_begin < 0 || a_end > na || a_begin > a_end) return fail(h, QPDE_ERR_INVALID, "gmwb shard: lines [%d, %d) outside [0, %d)", a_begin, a_end, na);
 	const int nz = qpde_refined_size(g->n_impulse_axis, g->refine);
 	std::vector<double> W((size_t)nw), A((size_t)na), Z((size_t)nz);
 	qpde_refine_axis(g->w_axis, g->n_w_axis, g->refine, W.data());

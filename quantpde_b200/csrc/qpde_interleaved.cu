@@ -332,7 +332,7 @@ k_interleaved_sweep(DeviceBatch b, InterleavedWork w, DeviceResult out) {
 			if(again && its >= b.max_inner) { status = 1; again = false; }
 		} while(again);
 
-		if(out.inner) {
+		if(out.inner && n_steps < b.max_steps) {
 			out.inner[(size_t)c * out.inner_stride + n_steps] = (uint8_t)(its > 255 ? 255 : its);
 		}
 		inner_total += its;

@@ -367,7 +367,7 @@ k_interleaved_sweep_tma(const __grid_constant__ TmaMaps maps, DeviceBatch b, Int
 		} while(__any_sync(FULL, again));
 
 		if(act) {
-			if(out.inner) {
+			if(out.inner && n_steps < b.max_steps) {
 				out.inner[(size_t)c * out.inner_stride + n_steps] = (uint8_t)(its > 255 ? 255 : its);
 			}
 			inner_total += its;

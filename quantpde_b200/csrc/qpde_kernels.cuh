@@ -70,7 +70,8 @@ struct InterleavedTma {
 };
 constexpr int QPDE_TMA_TILE_ROWS = 4;     // node rows per TMA tile (box = 32 contracts x 4 rows = 1 KB)
 
-// true if the TMA-staged sweep covers this batch (no policy iteration, variable steps or dividends)
+// true if the TMA-staged sweep covers this batch (N >= 32, schemes up to BDF2, no policy iteration; dividend
+// events and the variable stepper run inside it with ordinary loads)
 bool interleaved_tma_supported(const DeviceBatch &b);
 // encodes the tensor maps over `block` (`arrays` arrays of `rows` x 32 doubles); false if the driver
 // entry point is missing

@@ -539,7 +539,7 @@ k_resident_sweep(DeviceBatch b, DeviceResult out) {
 			}
 		} while(again);
 
-		if(rank == 0 && tid == 0 && out.inner) {
+		if(rank == 0 && tid == 0 && out.inner && n_steps < b.max_steps) {
 			out.inner[(size_t)cidx * out.inner_stride + n_steps] = (unsigned char)(its > 255 ? 255 : its);
 		}
 		inner_total += its;
@@ -734,14 +734,11 @@ bool resident_supported(const DeviceBatch &b) {
 template <int M, int PT, int MODE, bool BDF2, int EXTRA, int CL>
 static int launch_variant(const DeviceBatch &b, const DeviceResult &out, cudaStream_t stream) {
 	auto kern = k_resident_sweep<M, PT, MODE, BDF2, EXTRA, CL>;
-	static bool configured = false;
 	constexpr bool VARIABLE = EXTRA == EXTRA_VARIABLE;        // one more row array: V^n
 	const size_t smem = smem_bytes(M, PT, VARIABLE);
-	if(!configured) {
-		if(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
-			return QPDE_ERR_CUDA;
-		}
-		configured = true;
+	// per device / context, and a handle may live on any device: set on every launch (as the other families do)
+	if(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
+		return QPDE_ERR_CUDA;
 	}
 	if(CL == 1) {
 		kern<<<b.C, PT, smem, stream>>>(b, out);

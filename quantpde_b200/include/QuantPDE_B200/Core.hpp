@@ -604,6 +604,19 @@ public:
 			K[c] = it.payoff.kind() != QPDE_PAYOFF_ARRAY ? it.payoff.strike()
 				: (american && p->obstacle.kind() != QPDE_PAYOFF_ARRAY ? p->obstacle.strike()
 				: (nEx > 0 ? it.stepper->exercisePayoff().strike() : 0.));
+			// one strike per contract crosses the C ABI: every generator of the tree must use it
+			if(it.payoff.kind() != QPDE_PAYOFF_ARRAY) {
+				if((american && p->obstacle.kind() != QPDE_PAYOFF_ARRAY && p->obstacle.strike() != K[c])
+						|| (nEx > 0 && it.stepper->exercisePayoff().kind() != QPDE_PAYOFF_ARRAY
+							&& it.stepper->exercisePayoff().strike() != K[c])) {
+					throw std::invalid_argument("QuantPDE_B200: payoff, obstacle and exercise generators of one "
+						"problem must share their strike (pass the obstacle as an array otherwise)");
+				}
+			} else if(american && p->obstacle.kind() != QPDE_PAYOFF_ARRAY && nEx > 0
+					&& it.stepper->exercisePayoff().kind() != QPDE_PAYOFF_ARRAY
+					&& it.stepper->exercisePayoff().strike() != K[c]) {
+				throw std::invalid_argument("QuantPDE_B200: obstacle and exercise generators of one problem must share their strike");
+			}
 			spot[c] = K[c];
 			const bool needNodes = payKind == QPDE_PAYOFF_ARRAY || (american && obsKind == QPDE_PAYOFF_ARRAY)
 				|| volModel == QPDE_VOL_NODES;
