@@ -45,6 +45,71 @@ def contract_parameters(n, rank=0, world=1):
     return K[b:e], vol[b:e], T[b:e], r[b:e]
 
 
+def parity_sample_indices(n_total, K, vol, T, r, n_sample=256, wave=148):
+    """A stratified sample of the batch for the node-level parity check:
+    the first and the last contracts (first / last wave of CTAs), the extremes of every parameter,
+    and an evenly spaced remainder.  Deterministic."""
+    n_sample = min(n_sample, n_total)
+    picks = []
+    edge = min(wave // 4, max(1, n_sample // 8))
+    picks += list(range(edge)) + list(range(n_total - edge, n_total))
+    for arr in (K, vol, T, r):
+        order = np.argsort(arr, kind="stable")
+        picks += [int(order[0]), int(order[1 % n_total]), int(order[-1]), int(order[-2 % n_total])]
+    seen, out = set(), []
+    for i in picks:
+        if i not in seen and 0 <= i < n_total:
+            seen.add(i); out.append(i)
+    k = 0
+    rest = np.linspace(0, n_total - 1, num=4 * n_sample).astype(np.int64)
+    while len(out) < n_sample and k < len(rest):
+        i = int(rest[k]); k += 1
+        if i not in seen:
+            seen.add(i); out.append(i)
+    return np.array(sorted(out[:n_sample]), dtype=np.int64)
+
+
+def _oracle_one(args):
+    """One contract of configs[1] on the oracle (the CPU checker): V, per-step inner counts, mask."""
+    K, vol, T, r = args
+    from oracle import pyoracle as po
+    o = po.american_put(float(K), float(r), float(vol), float(T), N_STEPS, N_NODES_REFINE)
+    return o["V"], o["inner"], o["mask"], o["S"], o["n_steps"]
+
+
+def parity_sample(idx, K, vol, T, r, V, inner_total, n_steps, active=None):
+    """Node-for-node comparison of the sampled contracts with the oracle (which is bit-identical to the
+    reference on the golden cases): worst relative error (|a-b| / max(1,|a|,|b|)), inner-iteration totals,
+    step counts, and — when the active sets were fetched — mismatches outside / inside the tie band
+    (DESIGN.md §6)."""
+    from concurrent.futures import ProcessPoolExecutor
+    from oracle import pyoracle as po
+    po.lib()
+    jobs = [(K[i], vol[i], T[i], r[i]) for i in idx]
+    with ProcessPoolExecutor(max_workers=os.cpu_count() or 1) as ex:
+        ref = list(ex.map(_oracle_one, jobs, chunksize=4))
+    worst, inner_equal, steps_equal, hard, ties, tied_contracts = 0.0, 0, 0, 0, 0, 0
+    eps = np.finfo(np.float64).eps
+    for k, i in enumerate(idx):
+        Vr, inr, mr, Sr, ns = ref[k]
+        err = np.abs(V[k] - Vr) / np.maximum(1.0, np.maximum(np.abs(V[k]), np.abs(Vr)))
+        worst = max(worst, float(err.max()))
+        inner_equal += int(int(inr.sum()) == int(inner_total[k]))
+        steps_equal += int(ns == int(n_steps[k]))
+        if active is not None:
+            obst = np.maximum(K[i] - Sr, 0.0)
+            diff = active[k].astype(bool) != mr.astype(bool)
+            tie = np.abs(Vr - obst) <= 64 * eps * np.maximum(1.0, np.abs(obst))
+            hard += int(np.sum(diff & ~tie)); t = int(np.sum(diff & tie)); ties += t
+            tied_contracts += int(t > 0)
+    out = {"n": int(len(idx)), "worst_rel_err": worst, "tolerance": 1e-9,
+           "inner_totals_equal": inner_equal, "step_counts_equal": steps_equal,
+           "against": "oracle/qpde_oracle.c (bit-identical to the reference headers on tests/golden)"}
+    if active is not None:
+        out.update({"active_set_mismatches": hard, "ties": ties, "contracts_with_ties": tied_contracts})
+    return out
+
+
 SPECIAL = np.array([0., .1, .2, .3, .4, .5, .6, .7, .80, .84, .88, .92, .94, .96, .98, 1.,
                     1.02, 1.04, 1.06, 1.08, 1.10, 1.14, 1.18, 1.23, 1.30, 1.40, 1.50, 1.75,
                     2.25, 3.00, 7.50, 20., 100.])   # Axis::special, Core/Axis.hpp:445-459
@@ -217,6 +282,8 @@ def main():
     ap.add_argument("--cpu-sample", type=int, default=0)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-parity", action="store_true", help="skip the node-level parity sample against the oracle")
+    ap.add_argument("--parity-sample", type=int, default=256)
     ap.add_argument("--no-streaming", action="store_true",
                     help="skip the bounded sample of the HBM-streaming (INTERLEAVED, TMA-staged) family")
     args = ap.parse_args()
@@ -292,6 +359,24 @@ def main():
     inner_sum = int(res.inner_total.astype(np.int64).sum())
     not_converged = int((res.status != 0).sum())
 
+    # ---- parity of the batch that was just timed (rank 0): a stratified sample of its contracts,
+    # node for node against the oracle; active sets and per-step counts from a second plan of the
+    # sampled contracts alone, whose V must equal the full batch's bit for bit.
+    parity = None
+    if rank == 0 and not args.no_parity:
+        idx = parity_sample_indices(Cn, K, vol, T, r, args.parity_sample)
+        full = plan.fetch(capi.OUT_V)
+        Vs = np.ascontiguousarray(full.V[idx]); del full
+        sub = capi.BatchSpec(axis=axis[idx], refine=N_NODES_REFINE, r=r[idx], sigma=vol[idx], q=0.0, T=T[idx],
+                             dt=T[idx] / N_STEPS, strike=K[idx], american=True, payoff="put", kernel=args.kernel)
+        with capi.Plan(handle, sub) as splan:
+            splan.run()
+            sres = splan.fetch()
+        parity = parity_sample(idx, K, vol, T, r, Vs, res.inner_total[idx], res.n_steps[idx], active=sres.active)
+        parity["sample_plan_bits_equal_batch"] = bool(np.array_equal(sres.V, Vs))
+        parity["drawn_from"] = "the timed %d-contract batch: first/last contracts, extremes of K, sigma, T, r, evenly spaced rest" % Cn
+        del Vs, sres
+
     # ---- e2e: qpde_bs1d_sweep with host buffers, copies inside the timed region
     e2e = None
     if not args.no_e2e:
@@ -301,7 +386,7 @@ def main():
         e2e_out = capi.OUT_V | capi.OUT_VALUE | capi.OUT_INNER_TOTAL | capi.OUT_STATUS
         r2 = capi.ResultBuffers(Cn, N, capi.sweep_max_steps(spec), e2e_out, pinned=True)
         e2e_times = []
-        for i in range(1 + min(args.steps, 3)):
+        for i in range(1 + args.steps):            # one untimed call, then --steps timed ones
             barrier()
             t0 = time.perf_counter()
             capi.sweep(handle, spec, outputs=e2e_out, result=r2)
@@ -386,6 +471,8 @@ def main():
                               "keeps state on chip, so frac > 1 means it has left the HBM roofline"},
         "clocks": clocks, "gpu_launches": int(launches), "e2e": e2e,
     }
+    if parity is not None:
+        line["parity_sample"] = parity
     if streaming is not None:
         line["roofline_streaming_family"] = streaming
     if rank == 0 and world == 1 and not args.no_cpu:    # the CPU baseline is an N = 1 leg

@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define QPDE_ABI_VERSION 2
+#define QPDE_ABI_VERSION 3
 
 /* ---- status codes ----------------------------------------------------- */
 enum {
@@ -100,7 +100,8 @@ enum {
 	QPDE_OUT_INNER       = 32,
 	QPDE_OUT_ACTIVE      = 64,
 	QPDE_OUT_STATUS      = 128,
-	QPDE_OUT_ALL         = 255
+	QPDE_OUT_COMPUTED    = 256,
+	QPDE_OUT_ALL         = 511
 };
 
 typedef struct qpde_handle qpde_handle;       /* device context + stream   */
@@ -247,6 +248,10 @@ typedef struct {
 	                         (PenaltyMethod::constraintMask, PenaltyMethod.hpp:127-139) */
 	int64_t  active_stride;
 	int32_t *status;      /* [C] 0 ok, 1 = some step hit max_inner, 3 = max_steps exhausted (variable steps) */
+	int32_t *solves_computed; /* [C] linear solves the device actually ran.  inner_total is the reference's
+	                         count (ToleranceIteration::iterations()); an inner iteration whose active set
+	                         equals the previous one's would reproduce that iterate bit for bit and is
+	                         counted, not run — the difference is work the reference does and the device skips */
 } qpde_bs1d_result;
 
 /* ---- context ---------------------------------------------------------- */

@@ -13,7 +13,7 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "lib", "libqpde_b200.so")
 
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 OK, ERR_INVALID, ERR_CUDA, ERR_NO_DEVICE, ERR_NOT_CONVERGED, ERR_UNSUPPORTED = 0, -1, -2, -3, -4, -5
 
@@ -27,7 +27,8 @@ KERNEL_NAME = {v: k for k, v in KERNEL.items()}
 
 OUT_V, OUT_S, OUT_VALUE, OUT_STEPS, OUT_INNER_TOTAL, OUT_INNER, OUT_ACTIVE, OUT_STATUS = (
     1, 2, 4, 8, 16, 32, 64, 128)
-OUT_ALL = 255
+OUT_COMPUTED = 256
+OUT_ALL = 511
 
 _dp = C.POINTER(C.c_double)
 
@@ -74,6 +75,7 @@ class Result(C.Structure):
         ("inner", C.POINTER(C.c_uint8)), ("inner_stride", C.c_int64),
         ("active", C.POINTER(C.c_uint8)), ("active_stride", C.c_int64),
         ("status", C.POINTER(C.c_int32)),
+        ("solves_computed", C.POINTER(C.c_int32)),
     ]
 
 
@@ -425,7 +427,7 @@ class ResultBuffers:
         memory: full-rate, asynchronous D2H); call close() to release them."""
         r = Result()
         self.V = self.S = self.value = self.n_steps = self.inner_total = None
-        self.inner = self.active = self.status = None
+        self.inner = self.active = self.status = self.computed = None
         self._pinned = []
 
         def big(shape):
@@ -460,6 +462,9 @@ class ResultBuffers:
         if outputs & OUT_STATUS:
             self.status = np.zeros(C_, dtype=np.int32)
             r.status = self.status.ctypes.data_as(C.POINTER(C.c_int32))
+        if outputs & OUT_COMPUTED:
+            self.computed = np.zeros(C_, dtype=np.int32)
+            r.solves_computed = self.computed.ctypes.data_as(C.POINTER(C.c_int32))
         self.struct = r
 
 

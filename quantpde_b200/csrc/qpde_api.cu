@@ -481,6 +481,7 @@ static int plan_create_impl(qpde_handle *h, const qpde_bs1d_batch *in,
 	if(outputs & QPDE_OUT_VALUE)  QPDE_TRY(dev_alloc(p, &o.value, (size_t)C));
 	if(outputs & QPDE_OUT_STEPS)  QPDE_TRY(dev_alloc(p, &o.n_steps, (size_t)C));
 	if(outputs & QPDE_OUT_INNER_TOTAL) QPDE_TRY(dev_alloc(p, &o.inner_total, (size_t)C));
+	if(outputs & QPDE_OUT_COMPUTED) QPDE_TRY(dev_alloc(p, &o.computed, (size_t)C));
 	if(outputs & QPDE_OUT_INNER)  { QPDE_TRY(dev_alloc(p, &o.inner, (size_t)C * max_steps)); o.inner_stride = max_steps; }
 	if(outputs & QPDE_OUT_ACTIVE) { QPDE_TRY(dev_alloc(p, &o.active, (size_t)C * N)); o.active_stride = N; }
 	if(outputs & QPDE_OUT_STATUS) QPDE_TRY(dev_alloc(p, &o.status, (size_t)C));
@@ -600,7 +601,7 @@ int qpde_bs1d_plan_fetch(qpde_bs1d_plan *p, qpde_bs1d_result *r) {
 	QPDE_NEED(r->V, o.V, "V"); QPDE_NEED(r->S, o.S, "S"); QPDE_NEED(r->value, o.value, "value");
 	QPDE_NEED(r->n_steps, o.n_steps, "n_steps"); QPDE_NEED(r->inner_total, o.inner_total, "inner_total");
 	QPDE_NEED(r->inner, o.inner, "inner"); QPDE_NEED(r->active, o.active, "active");
-	QPDE_NEED(r->status, o.status, "status");
+	QPDE_NEED(r->status, o.status, "status"); QPDE_NEED(r->solves_computed, o.computed, "solves_computed");
 #undef QPDE_NEED
 	if(r->V) {
 		const long long hs = r->V_stride ? r->V_stride : N;
@@ -633,6 +634,7 @@ int qpde_bs1d_plan_fetch(qpde_bs1d_plan *p, qpde_bs1d_result *r) {
 			(size_t)N, C, cudaMemcpyDeviceToHost, h->stream));
 	}
 	if(r->status) QPDE_CUDA(h, cudaMemcpyAsync(r->status, o.status, sizeof(int) * C, cudaMemcpyDeviceToHost, h->stream));
+	if(r->solves_computed) QPDE_CUDA(h, cudaMemcpyAsync(r->solves_computed, o.computed, sizeof(int) * C, cudaMemcpyDeviceToHost, h->stream));
 	QPDE_CUDA(h, cudaStreamSynchronize(h->stream));
 	return QPDE_OK;
 }
@@ -752,6 +754,7 @@ int qpde_bs1d_sweep(qpde_handle *h, const qpde_bs1d_batch *batch, qpde_bs1d_resu
 	if(r->inner) outputs |= QPDE_OUT_INNER;
 	if(r->active) outputs |= QPDE_OUT_ACTIVE;
 	if(r->status) outputs |= QPDE_OUT_STATUS;
+	if(r->solves_computed) outputs |= QPDE_OUT_COMPUTED;
 	qpde_bs1d_plan *p = nullptr;
 	int rc = plan_create_impl(h, batch, outputs, &p);
 	if(rc != QPDE_OK) return rc;

@@ -436,6 +436,7 @@ k_interleaved_sweep(DeviceBatch b, InterleavedWork w, DeviceResult out) {
 	}
 	if(out.n_steps) out.n_steps[c] = n_steps;
 	if(out.inner_total) out.inner_total[c] = inner_total;
+	if(out.computed) out.computed[c] = inner_total;          // this sweep runs every inner iteration it counts
 	if(out.status) out.status[c] = status;
 }
 

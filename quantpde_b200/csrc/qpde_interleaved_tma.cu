@@ -163,7 +163,7 @@ k_interleaved_sweep_tma(const __grid_constant__ TmaMaps maps, DeviceBatch b, Int
 	NodeState ns; ns.start(b.scheme);
 	double time1 = rp.T, time0 = rp.T; // times of iterand(0), iterand(1)
 	Gamma gA; gA.kind = STEP_IMPLICIT; gA.h = 0.; // what the factorised A was built with
-	int n_steps = 0, inner_total = 0, status = 0;
+	int n_steps = 0, inner_total = 0, computed = 0, status = 0;
 	bool more = valid;
 	// ReverseVariableStepper (Core/Stepper.hpp:60-126): every contract has its own step sizes
 	// and its own number of steps; V^n is kept in xprev for the relative change over a step
@@ -356,7 +356,7 @@ k_interleaved_sweep_tma(const __grid_constant__ TmaMaps maps, DeviceBatch b, Int
 				}
 			}
 			if(again) {
-				++its;
+				++its; ++computed;
 				again = iterate && notdone;
 				if(again && !changed) {
 					// same active set: the confirming iteration is counted (see above)
@@ -474,6 +474,7 @@ k_interleaved_sweep_tma(const __grid_constant__ TmaMaps maps, DeviceBatch b, Int
 	}
 	if(out.n_steps) out.n_steps[c] = n_steps;
 	if(out.inner_total) out.inner_total[c] = inner_total;
+	if(out.computed) out.computed[c] = computed;
 	if(out.status) out.status[c] = status;
 }
 

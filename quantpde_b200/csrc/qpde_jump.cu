@@ -453,6 +453,7 @@ k_jump_sweep(DeviceBatch b, JumpWork work, DeviceResult out) {
 	if(tid == 0) {
 		if(out.n_steps) out.n_steps[cidx] = n_steps;
 		if(out.inner_total) out.inner_total[cidx] = n_steps;
+		if(out.computed) out.computed[cidx] = n_steps;
 		if(out.status) out.status[cidx] = 0;
 		if(out.inner) for(int s = 0; s < n_steps && s < b.max_steps; ++s) out.inner[(size_t)cidx * out.inner_stride + s] = 1;
 	}

@@ -45,6 +45,7 @@ struct DeviceResult {
 	double *value;
 	int *n_steps;
 	int *inner_total;
+	int *computed;         // inner solves actually executed (inner_total also counts the confirming ones)
 	unsigned char *inner; long long inner_stride;
 	unsigned char *active; long long active_stride;
 	int *status;
@@ -104,6 +105,10 @@ void gmwb_shard_exit(GmwbShard *sh, double *x);
 void gmwb_shard_policy(GmwbShard *sh, const double *x, const double *v0, double h0);
 cudaError_t gmwb_shard_sweep(GmwbShard *sh, double *x, int *status_dev);
 void gmwb_shard_relerr(GmwbShard *sh, const double *x, const double *xprev, int *notdone_dev);
+
+// RESIDENT family at two contracts per SM (qpde_lean.cu): American sweeps on 513 < N <= 2049 nodes.
+bool lean_supported(const DeviceBatch &b);
+int launch_lean(const DeviceBatch &b, const DeviceResult &out, cudaStream_t stream, long long *launches);
 
 // RESIDENT family (qpde_resident.cu): one CTA per contract.
 bool resident_supported(const DeviceBatch &b);

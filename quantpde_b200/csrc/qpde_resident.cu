@@ -319,7 +319,7 @@ k_resident_sweep(DeviceBatch b, DeviceResult out) {
 	double vdt = b.dt[cidx];
 	double time1 = rp.T, time0 = rp.T;
 	int cur_kind = -1; double cur_h = 0.;
-	int n_steps = 0, inner_total = 0, status = 0;
+	int n_steps = 0, inner_total = 0, computed = 0, status = 0;
 	bool more = true;
 	bool refactor = true;        // block-uniform: the cached factorisation is stale
 	unsigned flip = 0;           // block-uniform: which flag slot the next reduction uses
@@ -488,7 +488,7 @@ k_resident_sweep(DeviceBatch b, DeviceResult out) {
 			for(int j = 0; j < M; ++j) x[j] = G[j];
 			if(tail_owner) sm.tail.x = xt_new;
 			publish_last(x[M - 1]);
-			++its;
+			++its; ++computed;
 			if(ITERATE) {
 				if(POLICY) {
 					team_sync<CL>();             // sm_xlast of the new iterate is visible
@@ -667,6 +667,7 @@ k_resident_sweep(DeviceBatch b, DeviceResult out) {
 	if(rank == 0 && tid == 0) {
 		if(out.n_steps) out.n_steps[cidx] = n_steps;
 		if(out.inner_total) out.inner_total[cidx] = inner_total;
+		if(out.computed) out.computed[cidx] = computed;
 		if(out.status) out.status[cidx] = status;
 	}
 	if(out.value) {
@@ -786,6 +787,7 @@ int launch_resident(const DeviceBatch &b, const DeviceResult &out, cudaStream_t 
 	(void)sm_count;
 	int M = 0, PT = 0, CL = 1;
 	if(!resident_supported(b) || !pick_geometry(b.N, &M, &PT, &CL)) return QPDE_ERR_UNSUPPORTED;
+	if(lean_supported(b)) return launch_lean(b, out, stream, launches);      // two contracts per SM (qpde_lean.cu)
 	int rc;
 	if(CL == 4)                  rc = launch_rows<8, 256, false, 4>(b, out, stream);
 	else if(CL == 2)             rc = launch_rows<8, 256, false, 2>(b, out, stream);

@@ -114,6 +114,25 @@ CASES.append(("hjb_short_bdf4_k2", "hjb",
 CASES.append(("variable_american_bdf4", "vanilla",
               dict(american=1, steps=40, refine=2, variable_target=0.3, scheme="bdf4", K=100.0, r=0.04, vol=0.2, T=1.0)))
 
+# ---- round 2: the BASELINE.json config sizes themselves -----------------------------------
+# configs[0]: the rest of the reference's default table (examples/vanilla_options.cpp:36-42,139:
+# maximum_refinement 5 -> k = 0 .. 5; k = 6 = 2049 x 49,152 is checked against the oracle live)
+for k in (4, 5):
+    CASES.append(("american_table_k%d" % k, "vanilla",
+                  dict(american=1, steps=12 * 4 ** k, refine=k, K=100.0, r=0.04, vol=0.2, T=1.0)))
+# configs[2] at size: tutorial.cpp Bermudan put, local volatility, 2113 nodes x 6400 steps x 10 exercise dates
+for sch in ("bdf2", "rannacher"):
+    CASES.append(("bermudan_%s_k6_6400" % sch, "bermudan",
+                  dict(steps=6400, refine=6, scheme=sch, K=100.0, r=0.04, alpha=20.0, T=1.0, E=10)))
+# configs[3] grid: the rows 1057 x 385 and 2113 x 768 of the reference's recorded Kou table
+# (examples/jump_diffusion.cpp:186-187: 3.972397, 3.972930)
+for k in (5, 6):
+    CASES.append(("jump_kou_k%d" % k, "jump",
+                  dict(steps=12 * 2 ** k, refine=k, density="kou", K=100.0, r=0.05, vol=0.15, T=0.25,
+                       p_up=0.3445, eta1=3.0465, eta2=3.0775, **{"lambda": 0.1})))
+CASES.append(("jump_merton_k6", "jump",
+              dict(steps=768, refine=6, density="lognormal", K=100.0, r=0.05, vol=0.15, T=0.25,
+                   mu=-0.1, sd=0.45, **{"lambda": 0.1})))
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "reference_cases.npz")
 # cases already in the file with the same arguments are kept (pass --all to re-run everything)
 have = np.load(GOLDEN, allow_pickle=False) if os.path.exists(GOLDEN) and "--all" not in sys.argv else None

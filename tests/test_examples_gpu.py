@@ -68,16 +68,20 @@ def test_vanilla_options_example_variable_timestepping(examples, golden):
 
 def test_jump_diffusion_example_reproduces_the_reference_table(examples, golden):
     """examples/jump_diffusion.cpp:179-190 records this table for the Kou model (the only known-answer
-    table in the reference): 3.970527 at 265 nodes x 97 steps, 3.971451 at 529 x 192."""
-    out = subprocess.run([os.path.join(examples, "jump_diffusion_b200"), "jump_type=double_exponential", "k0=3", "kn=4"],
+    table in the reference): 3.970527 at 265 nodes x 97 steps, 3.971451 at 529 x 192, 3.972397 at
+    1057 x 385, 3.972930 at 2113 x 768 (the grid of BASELINE.json configs[3])."""
+    out = subprocess.run([os.path.join(examples, "jump_diffusion_b200"), "jump_type=double_exponential", "k0=3", "kn=6"],
                          check=True, capture_output=True, text=True)
     rows = [r.split() for r in out.stdout.strip().splitlines()[1:]]
-    assert len(rows) == 2
-    for row, (nodes, steps, value, k) in zip(rows, ((265, 97, 3.970527, 3), (529, 192, 3.971451, 4))):
+    assert len(rows) == 4
+    for row, (nodes, steps, value, k) in zip(rows, ((265, 97, 3.970527, 3), (529, 192, 3.971451, 4),
+                                                    (1057, 385, 3.972397, 5), (2113, 768, 3.972930, 6))):
         assert int(float(row[0])) == nodes and int(float(row[1])) == steps
         assert abs(float(row[2]) - value) <= 1e-6                                  # the recorded 7 digits
         assert rel_err(float(row[2]), float(golden["jump_kou_k%d/value" % k])) <= 1e-6   # printed with 6 digits
     assert abs(float(rows[1][3]) - 9.242709e-04) <= 2e-9                           # the recorded "Change"
+    assert abs(float(rows[2][3]) - 9.454750e-04) <= 2e-9 and abs(float(rows[3][3]) - 5.331950e-04) <= 2e-9
+    assert abs(float(rows[3][4]) - 1.773226e+00) <= 2e-5                           # the recorded "Ratio"
     out = subprocess.run([os.path.join(examples, "jump_diffusion_b200"), "k0=1", "kn=3"], check=True,
                          capture_output=True, text=True)                          # Merton (the example's default)
     rows = [r.split() for r in out.stdout.strip().splitlines()[1:]]

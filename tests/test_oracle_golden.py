@@ -12,7 +12,7 @@ from helpers import case_args, run_oracle_case
 
 def test_golden_cases_bit_exact(oracle, golden):
     names = [str(n) for n in golden["names"]]
-    assert len(names) >= 47
+    assert len(names) >= 54
     for name in names:
         mode, kw = case_args(golden, name)
         out = run_oracle_case(oracle, mode, kw)
@@ -40,7 +40,7 @@ def test_live_reference_when_present(oracle):
 def test_reference_known_answer_table(oracle, golden):
     """The one known-answer table the reference records (examples/jump_diffusion.cpp:179-190,
     Kou double-exponential jumps, "Tested February 18, 2016"): value and step count per level."""
-    table = {3: (265, 97, 3.970527), 4: (529, 192, 3.971451)}
+    table = {3: (265, 97, 3.970527), 4: (529, 192, 3.971451), 5: (1057, 385, 3.972397), 6: (2113, 768, 3.972930)}
     for k, (nodes, steps, value) in table.items():
         name = "jump_kou_k%d" % k
         assert len(golden[name + "/S"]) == nodes
