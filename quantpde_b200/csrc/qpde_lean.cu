@@ -6,14 +6,16 @@
 // round 1: issue slots 30 % busy, FP64 pipe 18 %).  This variant holds the same state in half
 // the space so that two independent contracts share an SM and fill each other's stalls:
 //
-//   registers (<= 128)  : the iterate x, the Thomas multipliers m, u of the thread's rows,
-//                         three scalars of the warp-level reduction
-//   shared memory       : system rows a, e, c (the diagonal is 1 + e, the Crank-Nicolson
-//   (106 KB)              right-hand-side rows are 0 - a, 1 - e, 0 - c), the right-hand side lb,
-//                         the reciprocal pivots, the coefficients of the warp-level cyclic
-//                         reduction, the level-3 factors
-//   recomputed          : the operator rows of BlackScholes::A at the (rare) re-scalings, the
-//                         grid nodes and the obstacle from the coarse axis (two multiply-adds)
+//   registers (<= 128)  : the iterate x, the reciprocal pivots and the back-substitution
+//                         multipliers u of the thread's rows, three scalars of the warp-level
+//                         reduction
+//   shared memory       : system rows a, me, c (me = 1 - e is the Crank-Nicolson right-hand-side
+//   (106 KB)              diagonal; the system diagonal 1 + e is re-formed as 2 - me, within one
+//                         ulp, when a factorisation needs it; the off-diagonal rows of the
+//                         right-hand side are 0 - a, 0 - c), the right-hand side lb, the obstacle,
+//                         the coefficients of the warp-level cyclic reduction, the level-3 factors
+//   recomputed          : the operator rows of BlackScholes::A at the (rare) re-scalings; the
+//                         forward multipliers a_j / d_{j-1} on the way (one product per row)
 //
 // and the partition solve needs no spike vectors: once the separator unknowns are known
 // (levels 2 and 3, as in qpde_partition.cuh) every thread solves its interior rows again with
@@ -51,9 +53,10 @@ struct LeanShared {
 	double q1[LW], q2[LW], q3[LW], al3[3][LW], ga3[3][LW], invB3[LW];
 	LeanTail tail;
 	alignas(8) unsigned char wflags[2][LW];
+	int n_steps, inner_total, computed, status;   // kept by thread 0
 	double xlast[LP + 1];         // x of each thread's last row, shifted by one
 	// row arrays, [j][thread]
-	double a[M * LP], e[M * LP], c[M * LP], lb[M * LP], invd[M * LP];
+	double a[M * LP], me[M * LP], c[M * LP], lb[M * LP], pz[M * LP];
 	// warp-level cyclic reduction, [stage][thread]
 	double al[5 * LP], ga[5 * LP];
 };
@@ -79,8 +82,10 @@ __device__ __forceinline__ bool conv_exact(double xn, double xo, double tol, dou
 
 } // namespace
 
-// One CTA of 256 threads per contract, two CTAs per SM.
-template <int M>
+// One CTA of 256 threads per contract, two CTAs per SM.  OBST: the obstacle generator
+// (QPDE_PAYOFF_PUT or QPDE_PAYOFF_CALL), compile-time so that the per-row obstacle is three
+// branch-free instructions.
+template <int M, int OBST>
 __global__ void __launch_bounds__(LP, 2)
 k_lean_sweep(DeviceBatch b, DeviceResult out) {
 	extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -98,27 +103,6 @@ k_lean_sweep(DeviceBatch b, DeviceResult out) {
 	const double K = b.strike[cidx];
 	const double *const axis = b.axis + (size_t)cidx * b.axis_stride;
 	const double pen = b.pen;
-
-	// ---- the thread's grid nodes from the coarse axis: row i0 + j is tick (k0 + j) of 2^refine in
-	// the coarse interval `seg` (refine >= 3: the M = 8 rows of a thread never cross a coarse tick,
-	// RectilinearGrid::refined, Core/Domain.hpp:1092-1151; refined_node() in closed form)
-	double g_left = 0., g_dx = 0., g_k0 = 0.;
-	if(i0 < n_main) {
-		const int tmp = 1 << b.refine;
-		const int seg = i0 >> b.refine;
-		const int k0 = i0 & (tmp - 1);
-		if(seg < b.n_axis - 1) {
-			g_left = axis[seg];
-			g_dx = (axis[seg + 1] - g_left) / (double)tmp;
-			g_k0 = (double)k0;
-		} else {
-			g_left = axis[b.n_axis - 1];      // i0 == N - 1 on a grid without a tail: the last node is this thread's row 0
-		}
-	}
-	auto S_row = [&] (int j) -> double { return (g_k0 + (double)j) * g_dx + g_left; };
-	auto pz_row = [&] (int j) -> double {
-		return i0 + j < n_main ? payoff_value(b.obstacle_kind, S_row(j), K) : -CUDART_INF;
-	};
 
 	// ---- system rows for one step kind / size: BlackScholes::A rows recomputed, then scaled
 	// (Rannacher.hpp:32-58, CrankNicolson.hpp:59-62, BDF.hpp:32-46)
@@ -139,7 +123,7 @@ k_lean_sweep(DeviceBatch b, DeviceResult out) {
 				aj = g.off(row.lo); ej = g.off(row.di); cj = g.off(row.up);
 			}
 			if(j == M - 1 && tail_owner) { sm.tail.c = cj; cj = 0.; }
-			sm.a[at] = aj; sm.e[at] = ej; sm.c[at] = cj;
+			sm.a[at] = aj; sm.me[at] = 1. - ej; sm.c[at] = cj;
 		}
 		if(tail_owner) {
 			const double et = g.off(sm.tail.di);
@@ -149,12 +133,12 @@ k_lean_sweep(DeviceBatch b, DeviceResult out) {
 
 	// ---- per-thread state
 	double x[M];
-	double f_m[M], f_u[M];            // Thomas multipliers of rows 2 .. M-1 / 1 .. M-1 (index 0, 1 unused)
+	double f_invd[M], f_u[M];         // reciprocal pivots and back-substitution multipliers of rows 1 .. M-1 (index 0 unused)
 	double f_invB2 = 1., f_V2 = 0., f_W2 = 0.;
 	double x_next;
 	unsigned curmask = 0, newmask = 0;
 #pragma unroll
-	for(int j = 0; j < M; ++j) { f_m[j] = 0.; f_u[j] = 0.; }
+	for(int j = 0; j < M; ++j) { f_invd[j] = 1.; f_u[j] = 0.; }
 
 	auto initial_value = [&] (int i) -> double {
 		return b.payoff_kind == QPDE_PAYOFF_ARRAY
@@ -162,12 +146,17 @@ k_lean_sweep(DeviceBatch b, DeviceResult out) {
 			: payoff_value(b.payoff_kind, refined_node(axis, b.refine, i), K);
 	};
 #pragma unroll
-	for(int j = 0; j < M; ++j) x[j] = i0 + j < n_main ? initial_value(i0 + j) : 0.;
+	for(int j = 0; j < M; ++j) {
+		const int i = i0 + j;
+		x[j] = i < n_main ? initial_value(i) : 0.;
+		// Modules/Lambdas/Payoffs.hpp:29-31,38-40; rows past the grid never bind
+		sm.pz[j * LP + tid] = i < n_main ? payoff_value(OBST, refined_node(axis, b.refine, i), K) : -CUDART_INF;
+	}
 	if(tail_owner) {
 		sm.tail.S = refined_node(axis, b.refine, N - 1);
 		sm.tail.di = q_c;                                   // row N-1 of BlackScholes::A: [q] (BlackScholes.hpp:177-180)
 		sm.tail.x = initial_value(N - 1);
-		sm.tail.pz = payoff_value(b.obstacle_kind, sm.tail.S, K);
+		sm.tail.pz = payoff_value(OBST, sm.tail.S, K);
 		sm.tail.c = 0.; sm.tail.bd = 1.; sm.tail.me = 1.; sm.tail.invb = 1.; sm.tail.pq = 0.; sm.tail.lb = 0.;
 	}
 	x_next = i0 + M < n_main ? initial_value(i0 + M) : 0.;
@@ -179,7 +168,7 @@ k_lean_sweep(DeviceBatch b, DeviceResult out) {
 	do { \
 		unsigned mk_ = 0; \
 		_Pragma("unroll") \
-		for(int j = 0; j < M; ++j) if(x[j] < pz_row(j)) mk_ |= 1u << j; \
+		for(int j = 0; j < M; ++j) if(x[j] < sm.pz[j * LP + tid]) mk_ |= 1u << j; \
 		if(tail_owner && sm.tail.x < sm.tail.pz) mk_ |= 1u << M; \
 		dst = mk_; \
 	} while(0)
@@ -187,20 +176,23 @@ k_lean_sweep(DeviceBatch b, DeviceResult out) {
 	QPDE_LEAN_MASK(newmask);
 
 	// ---- time loop (TimeIteration<false>, Core/IterativeMethod.hpp:1259-1317)
-	Replay rp; rp.start(b.T[cidx], b.dt[cidx], 0);
-	NodeState ns; ns.start(b.scheme);
-	double time1 = rp.T;
+	// Replay::next (qpde_common.cuh) without user events: the only event is the NullEvent at 0
+	const double dt_c = b.dt[cidx];
+	double time1 = b.T[cidx];
+	int phase = 1;                    // steps since the start, saturating at 3 (NodeState)
 	int cur_kind = -1; double cur_h = 0.;
-	int n_steps = 0, inner_total = 0, computed = 0, status = 0;
+	if(tid == 0) { sm.n_steps = 0; sm.inner_total = 0; sm.computed = 0; sm.status = 0; }
 	bool more = true;
 	bool refactor = true;
 	unsigned flip = 0;
 
 	while(more) {
-		qpde_step st;
-		more = rp.next(st);
-		const double t = st.t;
-		const int kind = ns.kind();
+		double t = time1 + -1. * dt_c;
+		if(fabs(t - 0.) < DBL_EPSILON) t = 0.;
+		else if(t < 0.) t = 0.;
+		more = 0. < t + -1. * DBL_EPSILON;
+		const int kind = b.scheme == QPDE_SCHEME_RANNACHER ? (phase >= 3 ? STEP_CN_R : STEP_IMPLICIT)
+			: (b.scheme == QPDE_SCHEME_CN ? STEP_CN_T : STEP_IMPLICIT);
 		const double h0 = time1 - t;
 		Gamma g; g.kind = kind; g.h = h0;
 		// the rows are rebuilt when the step kind changes or the step size moves by more than
@@ -224,7 +216,7 @@ k_lean_sweep(DeviceBatch b, DeviceResult out) {
 				const int at = j * LP + tid;
 				const double vm = j == 0 ? xm : x[j > 0 ? j - 1 : 0];
 				const double vp = j == M - 1 ? x_next : x[j + 1 < M ? j + 1 : j];
-				const double na = 0. - sm.a[at], me = 1. - sm.e[at], nc = 0. - sm.c[at];
+				const double na = 0. - sm.a[at], me = sm.me[at], nc = 0. - sm.c[at];
 				double acc = 0.;
 				acc += na * vm;
 				acc += me * x[j];
@@ -246,32 +238,32 @@ k_lean_sweep(DeviceBatch b, DeviceResult out) {
 				curmask = newmask;
 				double Vs1, Ws1, Vs7, Ws7, a0, c0, b0;
 				{
-					double aa[M], bb[M], cc[M], invd[M];
+					double aa[M], bb[M], cc[M], fm[M];
 #pragma unroll
 					for(int j = 0; j < M; ++j) {
 						const int at = j * LP + tid;
-						aa[j] = sm.a[at]; bb[j] = 1. + sm.e[at]; cc[j] = sm.c[at];
+						aa[j] = sm.a[at]; bb[j] = 2. - sm.me[at]; cc[j] = sm.c[at];     // 1 + e within one ulp
 						if(curmask >> j & 1u) bb[j] = bb[j] + pen * 1.;      // PenaltyMethod.hpp:96-119
 					}
 					a0 = aa[0]; c0 = cc[0]; b0 = bb[0];
-					invd[1] = rcp(bb[1]);
+					f_invd[1] = rcp(bb[1]);
 #pragma unroll
 					for(int j = 2; j < M; ++j) {
-						f_m[j] = aa[j] * invd[j - 1];
-						invd[j] = rcp(fma(-f_m[j], cc[j - 1], bb[j]));
+						fm[j] = aa[j] * f_invd[j - 1];
+						f_invd[j] = rcp(fma(-fm[j], cc[j - 1], bb[j]));
 					}
 					double yv[M];
 					yv[1] = aa[1];
 #pragma unroll
-					for(int j = 2; j < M; ++j) yv[j] = -f_m[j] * yv[j - 1];
+					for(int j = 2; j < M; ++j) yv[j] = -fm[j] * yv[j - 1];
 #pragma unroll
-					for(int j = 1; j < M; ++j) { f_u[j] = cc[j] * invd[j]; sm.invd[j * LP + tid] = invd[j]; }
+					for(int j = 1; j < M; ++j) f_u[j] = cc[j] * f_invd[j];
 					// spikes of the interior block: only their first and last entries are needed
-					double Vs = yv[M - 1] * invd[M - 1], Ws = f_u[M - 1];
+					double Vs = yv[M - 1] * f_invd[M - 1], Ws = f_u[M - 1];
 					Vs7 = Vs; Ws7 = Ws;
 #pragma unroll
 					for(int j = M - 2; j >= 1; --j) {
-						Vs = fma(-f_u[j], Vs, yv[j] * invd[j]);
+						Vs = fma(-f_u[j], Vs, yv[j] * f_invd[j]);
 						Ws = -f_u[j] * Ws;
 					}
 					Vs1 = Vs; Ws1 = Ws;
@@ -362,14 +354,15 @@ k_lean_sweep(DeviceBatch b, DeviceResult out) {
 			// ==========================================================
 			// one solve with the cached factorisation
 			// ==========================================================
-			double xt_new = 0.;
-			if(tail_owner) xt_new = (sm.tail.lb + sm.tail.pq) * sm.tail.invb;
+			double xt_new = 0., tail_c = 0.;
+			if(tail_owner) { xt_new = (sm.tail.lb + sm.tail.pq) * sm.tail.invb; tail_c = sm.tail.c; }
 			// right-hand side with penalty terms (PenaltyMethod.hpp:96-119); the tail row is a scalar
 			// equation folded into row N-2
 			auto rhs = [&] (int j) -> double {
 				const double lbj = sm.lb[j * LP + tid];
-				double v = (curmask >> j & 1u) ? lbj + pen * pz_row(j) : lbj;
-				if(j == M - 1 && tail_owner) v = fma(-sm.tail.c, xt_new, v);
+				const double pj = lbj + pen * sm.pz[j * LP + tid];      // formed for every row, selected below: no branch
+				double v = (curmask >> j & 1u) ? pj : lbj;
+				if(j == M - 1) v = fma(-tail_c, xt_new, v);       // both 0 except for the tail owner
 				return v;
 			};
 			double G1, G7, P0;
@@ -378,11 +371,11 @@ k_lean_sweep(DeviceBatch b, DeviceResult out) {
 				double z[M];
 				z[1] = rhs(1);
 #pragma unroll
-				for(int j = 2; j < M; ++j) z[j] = fma(-f_m[j], z[j - 1], rhs(j));
-				double G = z[M - 1] * sm.invd[(M - 1) * LP + tid];
+				for(int j = 2; j < M; ++j) z[j] = fma(-(sm.a[j * LP + tid] * f_invd[j - 1]), z[j - 1], rhs(j));
+				double G = z[M - 1] * f_invd[M - 1];
 				G7 = G;
 #pragma unroll
-				for(int j = M - 2; j >= 1; --j) G = fma(-f_u[j], G, z[j] * sm.invd[j * LP + tid]);
+				for(int j = M - 2; j >= 1; --j) G = fma(-f_u[j], G, z[j] * f_invd[j]);
 				G1 = G;
 			}
 			const double a0 = sm.a[tid], c0 = sm.c[tid];
@@ -426,15 +419,14 @@ k_lean_sweep(DeviceBatch b, DeviceResult out) {
 				double z[M];
 				z[1] = fma(-sm.a[1 * LP + tid], ysep, rhs(1));
 #pragma unroll
-				for(int j = 2; j < M; ++j) z[j] = fma(-f_m[j], z[j - 1], rhs(j));
+				for(int j = 2; j < M; ++j) z[j] = fma(-(sm.a[j * LP + tid] * f_invd[j - 1]), z[j - 1], rhs(j));
 				// sm.c of the last row is 0 for the tail owner (the coupling went to tail.c) and ynext is 0 there
-				y[M - 1] = fma(-sm.c[(M - 1) * LP + tid], ynext, z[M - 1]) * sm.invd[(M - 1) * LP + tid];
+				y[M - 1] = fma(-sm.c[(M - 1) * LP + tid], ynext, z[M - 1]) * f_invd[M - 1];
 #pragma unroll
-				for(int j = M - 2; j >= 1; --j) y[j] = fma(-f_u[j], y[j + 1], z[j] * sm.invd[j * LP + tid]);
+				for(int j = M - 2; j >= 1; --j) y[j] = fma(-f_u[j], y[j + 1], z[j] * f_invd[j]);
 				y[0] = ysep;
 			}
 			x_next = ynext;
-			++computed;
 
 			bool nd = false;
 			{
@@ -469,24 +461,26 @@ k_lean_sweep(DeviceBatch b, DeviceResult out) {
 			const bool notdone = (all & 1u) != 0, changed = (all & 2u) != 0;
 			refactor = changed;
 			again = notdone;
+			if(tid == 0) ++sm.computed;
 			if(notdone && !changed) {
 				// same active set => the next inner iteration would return this iterate again
 				// (relativeError == 0): counted, not recomputed
-				if(its >= b.max_inner) status = 1; else ++its;
+				if(its >= b.max_inner) { if(tid == 0) sm.status = 1; } else ++its;
 				again = false;
 			} else if(again && its >= b.max_inner) {
-				status = 1; again = false;
+				if(tid == 0) sm.status = 1;
+				again = false;
 			}
 		} while(again);
 
-		if(tid == 0 && out.inner && n_steps < b.max_steps) {
-			out.inner[(size_t)cidx * out.inner_stride + n_steps] = (unsigned char)(its > 255 ? 255 : its);
+		if(tid == 0) {
+			const int n = sm.n_steps;
+			if(out.inner && n < b.max_steps) out.inner[(size_t)cidx * out.inner_stride + n] = (unsigned char)(its > 255 ? 255 : its);
+			sm.inner_total += its;
+			sm.n_steps = n + 1;
 		}
-		inner_total += its;
-		++n_steps;
 		time1 = t;
-		ns.end_step();
-		if(st.event_after) ns.after_event();
+		if(phase < 3) ++phase;
 	}
 #undef QPDE_LEAN_MASK
 
@@ -496,9 +490,9 @@ k_lean_sweep(DeviceBatch b, DeviceResult out) {
 		const int i = i0 + j;
 		if(i < n_main) {
 			if(out.V) out.V[(size_t)cidx * out.V_stride + i] = x[j];
-			if(out.S) out.S[(size_t)cidx * out.S_stride + i] = S_row(j);
+			if(out.S) out.S[(size_t)cidx * out.S_stride + i] = refined_node(axis, b.refine, i);
 			if(out.active) {
-				const double pred = (0. + 1. * x[j]) - pz_row(j);
+				const double pred = (0. + 1. * x[j]) - sm.pz[j * LP + tid];
 				out.active[(size_t)cidx * out.active_stride + i] = pred < 0. ? 1 : 0;
 			}
 		}
@@ -513,10 +507,10 @@ k_lean_sweep(DeviceBatch b, DeviceResult out) {
 		}
 	}
 	if(tid == 0) {
-		if(out.n_steps) out.n_steps[cidx] = n_steps;
-		if(out.inner_total) out.inner_total[cidx] = inner_total;
-		if(out.computed) out.computed[cidx] = computed;
-		if(out.status) out.status[cidx] = status;
+		if(out.n_steps) out.n_steps[cidx] = sm.n_steps;
+		if(out.inner_total) out.inner_total[cidx] = sm.inner_total;
+		if(out.computed) out.computed[cidx] = sm.computed;
+		if(out.status) out.status[cidx] = sm.status;
 	}
 	if(out.value) {
 		// PiecewiseLinear::interpolate (Core/Interpolant.hpp:153-181,331-374): the thread owning
@@ -527,7 +521,7 @@ k_lean_sweep(DeviceBatch b, DeviceResult out) {
 		for(int j = 0; j < M; ++j) {
 			const int i = i0 + j;
 			if(i >= N - 1) continue;
-			const double Si = S_row(j);
+			const double Si = refined_node(axis, b.refine, i);
 			const double Sp = refined_node(axis, b.refine, i + 1);
 			const double vi = x[j];
 			const double vp = i + 1 >= n_main ? sm.tail.x : (j == M - 1 ? x_next : x[j + 1 < M ? j + 1 : j]);
@@ -546,23 +540,23 @@ k_lean_sweep(DeviceBatch b, DeviceResult out) {
 }
 
 // American sweeps with constant steps, theta schemes or BDF1, a generated obstacle, on grids of
-// 513 < N <= 2049 nodes refined at least three times (the rows of a thread stay inside one
-// coarse interval).  Everything else: k_resident_sweep.
+// 513 < N <= 2049 nodes.  Everything else: k_resident_sweep.
 bool lean_supported(const DeviceBatch &b) {
 	const char *env = getenv("QPDE_RESIDENT_LEAN");             // "0": A/B against k_resident_sweep (read per call)
 	if(env && env[0] == '0') return false;
 	if(!b.american || b.n_controls != 0 || b.n_exercise > 0 || b.variable_target) return false;
 	if(b.scheme != QPDE_SCHEME_RANNACHER && b.scheme != QPDE_SCHEME_CN && b.scheme != QPDE_SCHEME_BDF1) return false;
-	if(b.obstacle_kind == QPDE_PAYOFF_ARRAY) return false;
+	if(b.obstacle_kind != QPDE_PAYOFF_PUT && b.obstacle_kind != QPDE_PAYOFF_CALL) return false;
 	if(b.N <= 8 * 64 + 1 || b.N > 8 * LP + 1) return false;
-	if(b.refine < 3 || ((b.N - 1) & 7) != 0) return false;
 	return true;
 }
 
 int launch_lean(const DeviceBatch &b, const DeviceResult &out, cudaStream_t stream, long long *launches) {
 	if(!lean_supported(b)) return QPDE_ERR_UNSUPPORTED;
-	auto kern = k_lean_sweep<8>;
-	const size_t smem = sizeof(LeanShared<8>);
+	auto kern = b.obstacle_kind == QPDE_PAYOFF_PUT ? k_lean_sweep<8, QPDE_PAYOFF_PUT> : k_lean_sweep<8, QPDE_PAYOFF_CALL>;
+	size_t smem = sizeof(LeanShared<8>);
+	const char *one = getenv("QPDE_LEAN_ONE_PER_SM");          // tuning: pad the request so that only one CTA fits an SM
+	if(one && one[0] == '1') smem = 120 * 1024;
 	if(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return QPDE_ERR_CUDA;
 	if(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared) != cudaSuccess) return QPDE_ERR_CUDA;
 	kern<<<b.C, LP, smem, stream>>>(b, out);
