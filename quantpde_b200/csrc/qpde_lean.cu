@@ -29,6 +29,7 @@
 
 #include <cstdlib>
 #include <cstring>
+#include <type_traits>
 
 #include "qpde_kernels.cuh"
 #include "qpde_partition.cuh"
@@ -52,11 +53,13 @@ struct LeanShared {
 	// level-3 factors (one entry per warp separator; written by warp 0, read by every warp)
 	double q1[LW], q2[LW], q3[LW], al3[3][LW], ga3[3][LW], invB3[LW];
 	LeanTail tail;
-	alignas(8) unsigned char wflags[2][LW];
 	int n_steps, inner_total, computed, status;   // kept by thread 0
 	double xlast[LP + 1];         // x of each thread's last row, shifted by one
-	// row arrays, [j][thread]
-	double a[M * LP], me[M * LP], c[M * LP], lb[M * LP], pz[M * LP];
+	// row arrays: rows (2p, 2p + 1) of thread t as one double2 at [p][t] — every access is a full
+	// 16-byte one (half the load / store instructions of an [j][t] layout, no bank conflicts)
+	double2 a2[M / 2 * LP], me2[M / 2 * LP], c2[M / 2 * LP];
+	double2 lb2[M / 2 * LP];       // right-hand side lb of the discretisation node
+	double2 pz2[M / 2 * LP];       // obstacle
 	// warp-level cyclic reduction, [stage][thread]
 	double al[5 * LP], ga[5 * LP];
 };
@@ -108,22 +111,28 @@ k_lean_sweep(DeviceBatch b, DeviceResult out) {
 	// (Rannacher.hpp:32-58, CrankNicolson.hpp:59-62, BDF.hpp:32-46)
 	const double r_c = b.r[cidx], q_c = b.q[cidx], sig_c = b.sigma[cidx];
 	auto rescale = [&] (const Gamma &g) {
-		for(int j = 0; j < M; ++j) {
-			const int i = i0 + j;
-			const int at = j * LP + tid;
-			double aj = 0., ej = 0., cj = 0.;
-			if(i < n_main) {
-				const double Si = refined_node(axis, b.refine, i);
-				const double Sm = i > 0 ? refined_node(axis, b.refine, i - 1) : 0.;
-				const double Sp = i < N - 1 ? refined_node(axis, b.refine, i + 1) : 0.;
-				const double v_i = b.vol_model == QPDE_VOL_NODES
-					? b.sigma_nodes[(size_t)cidx * b.sigma_nodes_stride + i]
-					: vol_value(b.vol_model, sig_c, Si);
-				const Row row = bs_row(i, N, Sm, Si, Sp, r_c, v_i, q_c);
-				aj = g.off(row.lo); ej = g.off(row.di); cj = g.off(row.up);
+		for(int p2 = 0; p2 < M / 2; ++p2) {
+			double ra[2], rme[2], rc[2];
+#pragma unroll
+			for(int k = 0; k < 2; ++k) {
+				const int j = 2 * p2 + k;
+				const int i = i0 + j;
+				double aj = 0., ej = 0., cj = 0.;
+				if(i < n_main) {
+					const double Si = refined_node(axis, b.refine, i);
+					const double Sm = i > 0 ? refined_node(axis, b.refine, i - 1) : 0.;
+					const double Sp = i < N - 1 ? refined_node(axis, b.refine, i + 1) : 0.;
+					const double v_i = b.vol_model == QPDE_VOL_NODES
+						? b.sigma_nodes[(size_t)cidx * b.sigma_nodes_stride + i]
+						: vol_value(b.vol_model, sig_c, Si);
+					const Row row = bs_row(i, N, Sm, Si, Sp, r_c, v_i, q_c);
+					aj = g.off(row.lo); ej = g.off(row.di); cj = g.off(row.up);
+				}
+				if(j == M - 1 && tail_owner) { sm.tail.c = cj; cj = 0.; }
+				ra[k] = aj; rme[k] = 1. - ej; rc[k] = cj;
 			}
-			if(j == M - 1 && tail_owner) { sm.tail.c = cj; cj = 0.; }
-			sm.a[at] = aj; sm.me[at] = 1. - ej; sm.c[at] = cj;
+			const int at = p2 * LP + tid;
+			sm.a2[at] = make_double2(ra[0], ra[1]); sm.me2[at] = make_double2(rme[0], rme[1]); sm.c2[at] = make_double2(rc[0], rc[1]);
 		}
 		if(tail_owner) {
 			const double et = g.off(sm.tail.di);
@@ -146,11 +155,16 @@ k_lean_sweep(DeviceBatch b, DeviceResult out) {
 			: payoff_value(b.payoff_kind, refined_node(axis, b.refine, i), K);
 	};
 #pragma unroll
-	for(int j = 0; j < M; ++j) {
-		const int i = i0 + j;
-		x[j] = i < n_main ? initial_value(i) : 0.;
+	for(int j = 0; j < M; ++j) x[j] = i0 + j < n_main ? initial_value(i0 + j) : 0.;
+	bool z0 = true;                   // every obstacle value of this thread is <= 0
+#pragma unroll
+	for(int p2 = 0; p2 < M / 2; ++p2) {
 		// Modules/Lambdas/Payoffs.hpp:29-31,38-40; rows past the grid never bind
-		sm.pz[j * LP + tid] = i < n_main ? payoff_value(OBST, refined_node(axis, b.refine, i), K) : -CUDART_INF;
+		double2 q;
+		q.x = i0 + 2 * p2 < n_main ? payoff_value(OBST, refined_node(axis, b.refine, i0 + 2 * p2), K) : -CUDART_INF;
+		q.y = i0 + 2 * p2 + 1 < n_main ? payoff_value(OBST, refined_node(axis, b.refine, i0 + 2 * p2 + 1), K) : -CUDART_INF;
+		sm.pz2[p2 * LP + tid] = q;
+		z0 = z0 && !(q.x > 0.) && !(q.y > 0.);
 	}
 	if(tail_owner) {
 		sm.tail.S = refined_node(axis, b.refine, N - 1);
@@ -168,10 +182,18 @@ k_lean_sweep(DeviceBatch b, DeviceResult out) {
 	do { \
 		unsigned mk_ = 0; \
 		_Pragma("unroll") \
-		for(int j = 0; j < M; ++j) if(x[j] < sm.pz[j * LP + tid]) mk_ |= 1u << j; \
+		for(int p2 = 0; p2 < M / 2; ++p2) { \
+			const double2 q_ = wpz0 ? make_double2(0., 0.) : sm.pz2[p2 * LP + tid]; \
+			if(x[2 * p2] < q_.x) mk_ |= 1u << (2 * p2); \
+			if(x[2 * p2 + 1] < q_.y) mk_ |= 1u << (2 * p2 + 1); \
+		} \
 		if(tail_owner && sm.tail.x < sm.tail.pz) mk_ |= 1u << M; \
 		dst = mk_; \
 	} while(0)
+	// warps whose rows all have a zero obstacle (out of the money) test x < 0 and never load it
+	if(tail_owner) z0 = z0 && !(sm.tail.pz > 0.);
+	const bool wpz0 = __all_sync(FULL, z0);
+	bool wpen = true;                 // some row of this warp is penalised (set at every factorisation)
 	__syncthreads();
 	QPDE_LEAN_MASK(newmask);
 
@@ -184,7 +206,6 @@ k_lean_sweep(DeviceBatch b, DeviceResult out) {
 	if(tid == 0) { sm.n_steps = 0; sm.inner_total = 0; sm.computed = 0; sm.status = 0; }
 	bool more = true;
 	bool refactor = true;
-	unsigned flip = 0;
 
 	while(more) {
 		double t = time1 + -1. * dt_c;
@@ -206,23 +227,30 @@ k_lean_sweep(DeviceBatch b, DeviceResult out) {
 		// ---- lb = b(t) of the discretisation node (V^n = x)
 		if(kind == STEP_IMPLICIT) {
 #pragma unroll
-			for(int j = 0; j < M; ++j) sm.lb[j * LP + tid] = x[j] + 0. * h0;
+			for(int p2 = 0; p2 < M / 2; ++p2) sm.lb2[p2 * LP + tid] = make_double2(x[2 * p2] + 0. * h0, x[2 * p2 + 1] + 0. * h0);
 			if(tail_owner) sm.tail.lb = sm.tail.x + 0. * h0;
 		} else {
 			// (I - A h/2) V^n: row-major SpMV accumulated from zero in column order (Rannacher.hpp:60-73)
 			const double xm = sm.xlast[tid];
 #pragma unroll
-			for(int j = 0; j < M; ++j) {
-				const int at = j * LP + tid;
-				const double vm = j == 0 ? xm : x[j > 0 ? j - 1 : 0];
-				const double vp = j == M - 1 ? x_next : x[j + 1 < M ? j + 1 : j];
-				const double na = 0. - sm.a[at], me = sm.me[at], nc = 0. - sm.c[at];
-				double acc = 0.;
-				acc += na * vm;
-				acc += me * x[j];
-				acc += nc * vp;
-				if(j == M - 1 && tail_owner) acc += (0. - sm.tail.c) * sm.tail.x;
-				sm.lb[at] = acc + 0.;
+			for(int p2 = 0; p2 < M / 2; ++p2) {
+				const int at = p2 * LP + tid;
+				const double2 a2 = sm.a2[at], me2 = sm.me2[at], c2 = sm.c2[at];
+				double lbv[2];
+#pragma unroll
+				for(int k = 0; k < 2; ++k) {
+					const int j = 2 * p2 + k;
+					const double vm = j == 0 ? xm : x[j > 0 ? j - 1 : 0];
+					const double vp = j == M - 1 ? x_next : x[j + 1 < M ? j + 1 : j];
+					const double na = 0. - (k ? a2.y : a2.x), me = k ? me2.y : me2.x, nc = 0. - (k ? c2.y : c2.x);
+					double acc = 0.;
+					acc += na * vm;
+					acc += me * x[j];
+					acc += nc * vp;
+					if(j == M - 1 && tail_owner) acc += (0. - sm.tail.c) * sm.tail.x;
+					lbv[k] = acc + 0.;
+				}
+				sm.lb2[at] = make_double2(lbv[0], lbv[1]);
 			}
 			if(tail_owner) sm.tail.lb = (0. + sm.tail.me * sm.tail.x) + 0.;
 		}
@@ -236,13 +264,19 @@ k_lean_sweep(DeviceBatch b, DeviceResult out) {
 			if(refactor) {
 				refactor = false;
 				curmask = newmask;
+				wpen = __any_sync(FULL, curmask != 0u);
 				double Vs1, Ws1, Vs7, Ws7, a0, c0, b0;
 				{
 					double aa[M], bb[M], cc[M], fm[M];
 #pragma unroll
+					for(int p2 = 0; p2 < M / 2; ++p2) {
+						const int at = p2 * LP + tid;
+						const double2 a2 = sm.a2[at], me2 = sm.me2[at], c2 = sm.c2[at];
+						aa[2 * p2] = a2.x; aa[2 * p2 + 1] = a2.y; cc[2 * p2] = c2.x; cc[2 * p2 + 1] = c2.y;
+						bb[2 * p2] = 2. - me2.x; bb[2 * p2 + 1] = 2. - me2.y;          // 1 + e within one ulp
+					}
+#pragma unroll
 					for(int j = 0; j < M; ++j) {
-						const int at = j * LP + tid;
-						aa[j] = sm.a[at]; bb[j] = 2. - sm.me[at]; cc[j] = sm.c[at];     // 1 + e within one ulp
 						if(curmask >> j & 1u) bb[j] = bb[j] + pen * 1.;      // PenaltyMethod.hpp:96-119
 					}
 					a0 = aa[0]; c0 = cc[0]; b0 = bb[0];
@@ -358,29 +392,44 @@ k_lean_sweep(DeviceBatch b, DeviceResult out) {
 			if(tail_owner) { xt_new = (sm.tail.lb + sm.tail.pq) * sm.tail.invb; tail_c = sm.tail.c; }
 			// right-hand side with penalty terms (PenaltyMethod.hpp:96-119); the tail row is a scalar
 			// equation folded into row N-2
-			auto rhs = [&] (int j) -> double {
-				const double lbj = sm.lb[j * LP + tid];
-				const double pj = lbj + pen * sm.pz[j * LP + tid];      // formed for every row, selected below: no branch
-				double v = (curmask >> j & 1u) ? pj : lbj;
-				if(j == M - 1) v = fma(-tail_c, xt_new, v);       // both 0 except for the tail owner
-				return v;
+			// (a warp without penalised rows takes lb as it is: `pen_tag` is a compile-time tag)
+			// rows (2p, 2p + 1): one 16-byte load of lb, one of the obstacle
+			auto rhs2 = [&] (auto pen_tag, int p2, double &re, double &ro) {
+				const double2 l2 = sm.lb2[p2 * LP + tid];
+				re = l2.x; ro = l2.y;
+				if(decltype(pen_tag)::value) {
+					const double2 q2 = sm.pz2[p2 * LP + tid];
+					const double pe = l2.x + pen * q2.x, po = l2.y + pen * q2.y;   // formed for every row, selected below: no branch
+					re = (curmask >> (2 * p2) & 1u) ? pe : l2.x;
+					ro = (curmask >> (2 * p2 + 1) & 1u) ? po : l2.y;
+				}
+				if(p2 == M / 2 - 1) ro = fma(-tail_c, xt_new, ro);      // both 0 except for the tail owner
 			};
-			double G1, G7, P0;
-			{
+			double G1, G7, r0, a0, a1;
+			auto pass1 = [&] (auto pen_tag) {
 				// pass 1: interior rows with zero boundary values; only the first and last are kept
 				double z[M];
-				z[1] = rhs(1);
 #pragma unroll
-				for(int j = 2; j < M; ++j) z[j] = fma(-(sm.a[j * LP + tid] * f_invd[j - 1]), z[j - 1], rhs(j));
+				for(int p2 = 0; p2 < M / 2; ++p2) {
+					double re, ro;
+					rhs2(pen_tag, p2, re, ro);
+					const double2 a2 = sm.a2[p2 * LP + tid];
+					if(p2 == 0) { r0 = re; z[1] = ro; a0 = a2.x; a1 = a2.y; }
+					else {
+						z[2 * p2] = fma(-(a2.x * f_invd[2 * p2 - 1]), z[2 * p2 - 1], re);
+						z[2 * p2 + 1] = fma(-(a2.y * f_invd[2 * p2]), z[2 * p2], ro);
+					}
+				}
 				double G = z[M - 1] * f_invd[M - 1];
 				G7 = G;
 #pragma unroll
 				for(int j = M - 2; j >= 1; --j) G = fma(-f_u[j], G, z[j] * f_invd[j]);
 				G1 = G;
-			}
-			const double a0 = sm.a[tid], c0 = sm.c[tid];
+			};
+			if(wpen) pass1(std::true_type()); else pass1(std::false_type());
+			const double c0 = sm.c2[tid].x;
 			const double G7p = shfl_up(G7, 1);
-			P0 = fma(-c0, G1, rhs(0));
+			const double P0 = fma(-c0, G1, r0);
 			double R2 = lane >= 1 ? fma(-a0, G7p, P0) : 0.;
 #pragma unroll
 			for(int s = 0; s < 5; ++s) {
@@ -415,17 +464,26 @@ k_lean_sweep(DeviceBatch b, DeviceResult out) {
 			if(lane == 31) ynext = Yn;
 			// pass 2: the interior rows again, boundary values on the right-hand side
 			double y[M];
-			{
+			auto pass2 = [&] (auto pen_tag) {
 				double z[M];
-				z[1] = fma(-sm.a[1 * LP + tid], ysep, rhs(1));
 #pragma unroll
-				for(int j = 2; j < M; ++j) z[j] = fma(-(sm.a[j * LP + tid] * f_invd[j - 1]), z[j - 1], rhs(j));
-				// sm.c of the last row is 0 for the tail owner (the coupling went to tail.c) and ynext is 0 there
-				y[M - 1] = fma(-sm.c[(M - 1) * LP + tid], ynext, z[M - 1]) * f_invd[M - 1];
+				for(int p2 = 0; p2 < M / 2; ++p2) {
+					double re, ro;
+					rhs2(pen_tag, p2, re, ro);
+					if(p2 == 0) z[1] = fma(-a1, ysep, ro);
+					else {
+						const double2 a2 = sm.a2[p2 * LP + tid];
+						z[2 * p2] = fma(-(a2.x * f_invd[2 * p2 - 1]), z[2 * p2 - 1], re);
+						z[2 * p2 + 1] = fma(-(a2.y * f_invd[2 * p2]), z[2 * p2], ro);
+					}
+				}
+				// c of the last row is 0 for the tail owner (the coupling went to tail.c) and ynext is 0 there
+				y[M - 1] = fma(-sm.c2[(M / 2 - 1) * LP + tid].y, ynext, z[M - 1]) * f_invd[M - 1];
 #pragma unroll
 				for(int j = M - 2; j >= 1; --j) y[j] = fma(-f_u[j], y[j + 1], z[j] * f_invd[j]);
 				y[0] = ysep;
-			}
+			};
+			if(wpen) pass2(std::true_type()); else pass2(std::false_type());
 			x_next = ynext;
 
 			bool nd = false;
@@ -448,17 +506,13 @@ k_lean_sweep(DeviceBatch b, DeviceResult out) {
 			sm.xlast[tid + 1] = x[M - 1];
 			++its;
 			QPDE_LEAN_MASK(newmask);
-			// one barrier carries both block-wide flags (one byte per warp, two slots used alternately)
+			// one barrier carries both block-wide flags: lanes 0 .. 30 of a warp vote "active set changed",
+			// lane 31 votes "not converged"; the barrier's population count is 31 x (warps changed) +
+			// (warps not converged), and both are at most 8
 			const unsigned bits = (nd ? 1u : 0u) | (newmask != curmask ? 2u : 0u);
 			const unsigned wbits = __reduce_or_sync(FULL, bits);
-			const unsigned slot = flip & 1u;
-			++flip;
-			if(lane == 0) sm.wflags[slot][warp] = (unsigned char)wbits;
-			__syncthreads();
-			unsigned long long acc = *reinterpret_cast<const unsigned long long *>(sm.wflags[slot]);
-			acc |= acc >> 32; acc |= acc >> 16; acc |= acc >> 8;
-			const unsigned all = (unsigned)acc & 3u;
-			const bool notdone = (all & 1u) != 0, changed = (all & 2u) != 0;
+			const int votes = __syncthreads_count(lane == 31 ? (wbits & 1u) : (wbits >> 1 & 1u));
+			const bool notdone = votes % 31 != 0, changed = votes >= 31;
 			refactor = changed;
 			again = notdone;
 			if(tid == 0) ++sm.computed;
@@ -492,7 +546,8 @@ k_lean_sweep(DeviceBatch b, DeviceResult out) {
 			if(out.V) out.V[(size_t)cidx * out.V_stride + i] = x[j];
 			if(out.S) out.S[(size_t)cidx * out.S_stride + i] = refined_node(axis, b.refine, i);
 			if(out.active) {
-				const double pred = (0. + 1. * x[j]) - sm.pz[j * LP + tid];
+				const double2 q2 = sm.pz2[(j >> 1) * LP + tid];
+				const double pred = (0. + 1. * x[j]) - ((j & 1) ? q2.y : q2.x);
 				out.active[(size_t)cidx * out.active_stride + i] = pred < 0. ? 1 : 0;
 			}
 		}
