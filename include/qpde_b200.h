@@ -271,6 +271,10 @@ int64_t qpde_launch_count(const qpde_handle *h);
 /* Multiprocessor count of the device (grid sizing / reporting). */
 int qpde_sm_count(const qpde_handle *h);
 
+/* Measured FP64 rate of the device in TFLOP/s (a chain of independent fused multiply-adds, 2 flops
+ * each): the denominator of the "fp64" rooflines bench.py reports for the control and jump kernels. */
+int qpde_measure_fp64_peak(qpde_handle *h, double *tflops);
+
 /* Pinned host memory for callers that want asynchronous, full-rate copies. */
 int qpde_host_alloc(size_t bytes, void **out);
 int qpde_host_free(void *p);

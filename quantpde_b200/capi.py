@@ -103,7 +103,7 @@ class Gmwb2dStats(C.Structure):
 # every symbol include/qpde_b200.h declares
 EXPORTS = [
     "qpde_abi_version", "qpde_create", "qpde_destroy", "qpde_last_error", "qpde_stream",
-    "qpde_synchronize", "qpde_launch_count", "qpde_sm_count", "qpde_host_alloc",
+    "qpde_synchronize", "qpde_launch_count", "qpde_sm_count", "qpde_measure_fp64_peak", "qpde_host_alloc",
     "qpde_host_free", "qpde_make_schedule", "qpde_refined_size", "qpde_bs1d_sweep",
     "qpde_bs1d_plan_create", "qpde_bs1d_plan_run", "qpde_bs1d_plan_fetch",
     "qpde_bs1d_plan_destroy", "qpde_bs1d_plan_kernel", "qpde_bs1d_plan_nodes", "qpde_bs1d_plan_tma_staged",
@@ -248,6 +248,12 @@ class Handle:
     @property
     def sm_count(self):
         return lib().qpde_sm_count(self.ptr)
+
+    def fp64_peak_tflops(self):
+        """Measured FP64 rate of the device (qpde_measure_fp64_peak)."""
+        v = C.c_double()
+        check(lib().qpde_measure_fp64_peak(self.ptr, C.byref(v)), self.ptr)
+        return v.value
 
 
 def _arr(x, n, dtype=np.float64):

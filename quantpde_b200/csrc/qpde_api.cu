@@ -63,6 +63,7 @@ struct qpde_handle {
 	int device;
 	int sm_count;
 	cudaStream_t stream;
+	cudaStream_t copy_stream;   // device-to-host copies of finished contract ranges, behind the sweep of the next range
 	long long launches;
 	std::string error;
 	DevicePool pool;
@@ -211,6 +212,11 @@ int qpde_create(int device, qpde_handle **out) {
 		delete h;
 		return fail(nullptr, QPDE_ERR_CUDA, "cudaStreamCreate failed: %s", cudaGetErrorString(serr));
 	}
+	if(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking) != cudaSuccess) {
+		cudaStreamDestroy(h->stream);
+		delete h;
+		return fail(nullptr, QPDE_ERR_CUDA, "cudaStreamCreate failed");
+	}
 	*out = h;
 	return QPDE_OK;
 }
@@ -219,7 +225,9 @@ int qpde_destroy(qpde_handle *h) {
 	if(!h) return QPDE_OK;
 	cudaSetDevice(h->device);
 	cudaStreamSynchronize(h->stream);
+	cudaStreamSynchronize(h->copy_stream);
 	h->pool.release();
+	cudaStreamDestroy(h->copy_stream);
 	cudaStreamDestroy(h->stream);
 	delete h;
 	return QPDE_OK;
@@ -236,6 +244,14 @@ int qpde_synchronize(qpde_handle *h) {
 
 int64_t qpde_launch_count(const qpde_handle *h) { return h ? h->launches : 0; }
 int qpde_sm_count(const qpde_handle *h) { return h ? h->sm_count : 0; }
+
+int qpde_measure_fp64_peak(qpde_handle *h, double *tflops) {
+	if(!h || !tflops) return fail(h, QPDE_ERR_INVALID, "qpde_measure_fp64_peak: NULL argument");
+	QPDE_CUDA(h, cudaSetDevice(h->device));
+	const int rc = measure_fp64_peak(h->sm_count, h->stream, tflops, &h->launches);
+	if(rc != QPDE_OK) return fail(h, rc, "qpde_measure_fp64_peak failed");
+	return QPDE_OK;
+}
 
 int qpde_host_alloc(size_t bytes, void **out) {
 	if(!out) return fail(nullptr, QPDE_ERR_INVALID, "qpde_host_alloc: out is NULL");
@@ -590,10 +606,50 @@ int qpde_bs1d_plan_run(qpde_bs1d_plan *p) {
 	return QPDE_OK;
 }
 
+// Copies the outputs of contracts [c0, c1) to the host buffers on `stream` (no synchronisation).
+static int fetch_range(qpde_bs1d_plan *p, qpde_bs1d_result *r, int c0, int c1, cudaStream_t stream) {
+	qpde_handle *h = p->h;
+	const int N = p->b.N;
+	const size_t n = (size_t)(c1 - c0);
+	const DeviceResult &o = p->out;
+	if(r->V) {
+		const long long hs = r->V_stride ? r->V_stride : N;
+		if(hs < N) return fail(h, QPDE_ERR_INVALID, "V_stride < N");
+		if(hs == N && o.V_stride == N) {
+			QPDE_CUDA(h, cudaMemcpyAsync(r->V + (size_t)c0 * N, o.V + (size_t)c0 * N, sizeof(double) * (size_t)N * n, cudaMemcpyDeviceToHost, stream));
+		} else
+		QPDE_CUDA(h, cudaMemcpy2DAsync(r->V + (size_t)c0 * hs, sizeof(double) * hs, o.V + (size_t)c0 * o.V_stride, sizeof(double) * o.V_stride,
+			sizeof(double) * N, n, cudaMemcpyDeviceToHost, stream));
+	}
+	if(r->S) {
+		const long long hs = r->S_stride ? r->S_stride : N;
+		if(hs < N) return fail(h, QPDE_ERR_INVALID, "S_stride < N");
+		QPDE_CUDA(h, cudaMemcpy2DAsync(r->S + (size_t)c0 * hs, sizeof(double) * hs, o.S + (size_t)c0 * o.S_stride, sizeof(double) * o.S_stride,
+			sizeof(double) * N, n, cudaMemcpyDeviceToHost, stream));
+	}
+	if(r->value) QPDE_CUDA(h, cudaMemcpyAsync(r->value + c0, o.value + c0, sizeof(double) * n, cudaMemcpyDeviceToHost, stream));
+	if(r->n_steps) QPDE_CUDA(h, cudaMemcpyAsync(r->n_steps + c0, o.n_steps + c0, sizeof(int) * n, cudaMemcpyDeviceToHost, stream));
+	if(r->inner_total) QPDE_CUDA(h, cudaMemcpyAsync(r->inner_total + c0, o.inner_total + c0, sizeof(int) * n, cudaMemcpyDeviceToHost, stream));
+	if(r->inner) {
+		const long long hs = r->inner_stride ? r->inner_stride : p->b.max_steps;
+		const long long width = hs < o.inner_stride ? hs : o.inner_stride;
+		QPDE_CUDA(h, cudaMemcpy2DAsync(r->inner + (size_t)c0 * hs, (size_t)hs, o.inner + (size_t)c0 * o.inner_stride, (size_t)o.inner_stride,
+			(size_t)width, n, cudaMemcpyDeviceToHost, stream));
+	}
+	if(r->active) {
+		const long long hs = r->active_stride ? r->active_stride : N;
+		if(hs < N) return fail(h, QPDE_ERR_INVALID, "active_stride < N");
+		QPDE_CUDA(h, cudaMemcpy2DAsync(r->active + (size_t)c0 * hs, (size_t)hs, o.active + (size_t)c0 * o.active_stride, (size_t)o.active_stride,
+			(size_t)N, n, cudaMemcpyDeviceToHost, stream));
+	}
+	if(r->status) QPDE_CUDA(h, cudaMemcpyAsync(r->status + c0, o.status + c0, sizeof(int) * n, cudaMemcpyDeviceToHost, stream));
+	if(r->solves_computed) QPDE_CUDA(h, cudaMemcpyAsync(r->solves_computed + c0, o.computed + c0, sizeof(int) * n, cudaMemcpyDeviceToHost, stream));
+	return QPDE_OK;
+}
+
 int qpde_bs1d_plan_fetch(qpde_bs1d_plan *p, qpde_bs1d_result *r) {
 	if(!p || !r) return fail(nullptr, QPDE_ERR_INVALID, "plan_fetch: NULL argument");
 	qpde_handle *h = p->h;
-	const int C = p->b.C, N = p->b.N;
 	const DeviceResult &o = p->out;
 	QPDE_CUDA(h, cudaSetDevice(h->device));
 #define QPDE_NEED(hostptr, devptr, name) \
@@ -603,39 +659,43 @@ int qpde_bs1d_plan_fetch(qpde_bs1d_plan *p, qpde_bs1d_result *r) {
 	QPDE_NEED(r->inner, o.inner, "inner"); QPDE_NEED(r->active, o.active, "active");
 	QPDE_NEED(r->status, o.status, "status"); QPDE_NEED(r->solves_computed, o.computed, "solves_computed");
 #undef QPDE_NEED
-	if(r->V) {
-		const long long hs = r->V_stride ? r->V_stride : N;
-		if(hs < N) return fail(h, QPDE_ERR_INVALID, "V_stride < N");
-		if(hs == N && o.V_stride == N) {
-			QPDE_CUDA(h, cudaMemcpyAsync(r->V, o.V, sizeof(double) * (size_t)N * C, cudaMemcpyDeviceToHost, h->stream));
-		} else
-		QPDE_CUDA(h, cudaMemcpy2DAsync(r->V, sizeof(double) * hs, o.V, sizeof(double) * o.V_stride,
-			sizeof(double) * N, C, cudaMemcpyDeviceToHost, h->stream));
-	}
-	if(r->S) {
-		const long long hs = r->S_stride ? r->S_stride : N;
-		if(hs < N) return fail(h, QPDE_ERR_INVALID, "S_stride < N");
-		QPDE_CUDA(h, cudaMemcpy2DAsync(r->S, sizeof(double) * hs, o.S, sizeof(double) * o.S_stride,
-			sizeof(double) * N, C, cudaMemcpyDeviceToHost, h->stream));
-	}
-	if(r->value) QPDE_CUDA(h, cudaMemcpyAsync(r->value, o.value, sizeof(double) * C, cudaMemcpyDeviceToHost, h->stream));
-	if(r->n_steps) QPDE_CUDA(h, cudaMemcpyAsync(r->n_steps, o.n_steps, sizeof(int) * C, cudaMemcpyDeviceToHost, h->stream));
-	if(r->inner_total) QPDE_CUDA(h, cudaMemcpyAsync(r->inner_total, o.inner_total, sizeof(int) * C, cudaMemcpyDeviceToHost, h->stream));
-	if(r->inner) {
-		const long long hs = r->inner_stride ? r->inner_stride : p->b.max_steps;
-		const long long width = hs < o.inner_stride ? hs : o.inner_stride;
-		QPDE_CUDA(h, cudaMemcpy2DAsync(r->inner, (size_t)hs, o.inner, (size_t)o.inner_stride,
-			(size_t)width, C, cudaMemcpyDeviceToHost, h->stream));
-	}
-	if(r->active) {
-		const long long hs = r->active_stride ? r->active_stride : N;
-		if(hs < N) return fail(h, QPDE_ERR_INVALID, "active_stride < N");
-		QPDE_CUDA(h, cudaMemcpy2DAsync(r->active, (size_t)hs, o.active, (size_t)o.active_stride,
-			(size_t)N, C, cudaMemcpyDeviceToHost, h->stream));
-	}
-	if(r->status) QPDE_CUDA(h, cudaMemcpyAsync(r->status, o.status, sizeof(int) * C, cudaMemcpyDeviceToHost, h->stream));
-	if(r->solves_computed) QPDE_CUDA(h, cudaMemcpyAsync(r->solves_computed, o.computed, sizeof(int) * C, cudaMemcpyDeviceToHost, h->stream));
+	const int rc = fetch_range(p, r, 0, p->b.C, h->stream);
+	if(rc != QPDE_OK) return rc;
 	QPDE_CUDA(h, cudaStreamSynchronize(h->stream));
+	return QPDE_OK;
+}
+
+// The one-shot call on a large RESIDENT batch: the contracts are swept in a few ranges, and the
+// results of a finished range travel to the host (second stream, ordered by an event) while the
+// next range is being swept — end to end the call costs the sweep plus the copy of the last range.
+static int run_and_fetch_ranges(qpde_bs1d_plan *p, qpde_bs1d_result *r) {
+	qpde_handle *h = p->h;
+	const int C = p->b.C;
+	// whole waves per range: two resident contracts per SM at most
+	const int wave = 2 * h->sm_count;
+	int per = ((C + 3) / 4 + wave - 1) / wave * wave;
+	if(per < 8 * wave) per = 8 * wave;
+	const int ranges = (C + per - 1) / per;
+	std::vector<cudaEvent_t> done((size_t)ranges);
+	int rc = QPDE_OK;
+	int made = 0;
+	for(; made < ranges; ++made) if(cudaEventCreateWithFlags(&done[made], cudaEventDisableTiming) != cudaSuccess) { rc = QPDE_ERR_CUDA; break; }
+	for(int k = 0; rc == QPDE_OK && k < ranges; ++k) {
+		DeviceBatch b = p->b;
+		b.c0 = k * per;
+		b.C = C - b.c0 < per ? C - b.c0 : per;
+		rc = launch_resident(b, p->out, h->stream, h->sm_count, &h->launches);
+		if(rc == QPDE_OK && cudaEventRecord(done[k], h->stream) != cudaSuccess) rc = QPDE_ERR_CUDA;
+	}
+	for(int k = 0; rc == QPDE_OK && k < ranges; ++k) {
+		const int c0 = k * per, c1 = c0 + per < C ? c0 + per : C;
+		if(cudaStreamWaitEvent(h->copy_stream, done[k], 0) != cudaSuccess) { rc = QPDE_ERR_CUDA; break; }
+		rc = fetch_range(p, r, c0, c1, h->copy_stream);
+	}
+	const cudaError_t e1 = cudaStreamSynchronize(h->stream), e2 = cudaStreamSynchronize(h->copy_stream);
+	for(int k = 0; k < made; ++k) cudaEventDestroy(done[k]);
+	if(rc != QPDE_OK) return rc == QPDE_ERR_CUDA ? fail(h, rc, "ranged sweep failed: %s", cudaGetErrorString(cudaGetLastError())) : rc;
+	if(e1 != cudaSuccess || e2 != cudaSuccess) return fail(h, QPDE_ERR_CUDA, "ranged sweep failed: %s", cudaGetErrorString(e1 != cudaSuccess ? e1 : e2));
 	return QPDE_OK;
 }
 
@@ -758,8 +818,14 @@ int qpde_bs1d_sweep(qpde_handle *h, const qpde_bs1d_batch *batch, qpde_bs1d_resu
 	qpde_bs1d_plan *p = nullptr;
 	int rc = plan_create_impl(h, batch, outputs, &p);
 	if(rc != QPDE_OK) return rc;
-	rc = qpde_bs1d_plan_run(p);
-	if(rc == QPDE_OK) rc = qpde_bs1d_plan_fetch(p, r);
+	const char *no_ranges = getenv("QPDE_SWEEP_NO_RANGES");      // tuning: one launch, copies after it
+	if(p->kernel == QPDE_KERNEL_RESIDENT && !p->jump && p->b.C >= 16 * 2 * h->sm_count && !(no_ranges && no_ranges[0] == '1')) {
+		QPDE_CUDA(h, cudaSetDevice(h->device));
+		rc = run_and_fetch_ranges(p, r);
+	} else {
+		rc = qpde_bs1d_plan_run(p);
+		if(rc == QPDE_OK) rc = qpde_bs1d_plan_fetch(p, r);
+	}
 	qpde_bs1d_plan_destroy(p);
 	return rc;
 }

@@ -14,6 +14,7 @@ namespace qpde {
 // Device copy of qpde_bs1d_batch (all pointers are device pointers).
 struct DeviceBatch {
 	int C, N;
+	int c0;                // RESIDENT family: first contract of this launch (C of them are swept; arrays are indexed by contract)
 	const double *axis; long long axis_stride; int n_axis, refine;
 	const double *r, *sigma, *q;
 	int vol_model;
@@ -105,6 +106,9 @@ void gmwb_shard_exit(GmwbShard *sh, double *x);
 void gmwb_shard_policy(GmwbShard *sh, const double *x, const double *v0, double h0);
 cudaError_t gmwb_shard_sweep(GmwbShard *sh, double *x, int *status_dev);
 void gmwb_shard_relerr(GmwbShard *sh, const double *x, const double *xprev, int *notdone_dev);
+
+// FP64 pipe rate of this device, measured (qpde_peak.cu)
+int measure_fp64_peak(int sm_count, cudaStream_t stream, double *tflops, long long *launches);
 
 // RESIDENT family at two contracts per SM (qpde_lean.cu): American sweeps on 513 < N <= 2049 nodes.
 bool lean_supported(const DeviceBatch &b);

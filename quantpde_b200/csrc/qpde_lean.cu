@@ -94,7 +94,7 @@ k_lean_sweep(DeviceBatch b, DeviceResult out) {
 	extern __shared__ __align__(16) unsigned char smem_raw[];
 	LeanShared<M> &sm = *reinterpret_cast<LeanShared<M> *>(smem_raw);
 
-	const int cidx = blockIdx.x;
+	const int cidx = b.c0 + (int)blockIdx.x;
 	const int tid = threadIdx.x;
 	const int lane = tid & 31, warp = tid >> 5;
 	const int N = b.N;

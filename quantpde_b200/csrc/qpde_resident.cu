@@ -123,7 +123,7 @@ k_resident_sweep(DeviceBatch b, DeviceResult out) {
 	extern __shared__ __align__(16) unsigned char smem_raw[];
 	Smem &sm = *reinterpret_cast<Smem *>(smem_raw);
 
-	const int cidx = blockIdx.x / CL;
+	const int cidx = b.c0 + (int)(blockIdx.x / CL);
 	const int rank = CL == 1 ? 0 : (int)(blockIdx.x % CL);      // == %cluster_ctarank for a 1-D cluster
 	const int tid = threadIdx.x;
 	const int lane = tid & 31, warp = rank * (PT / 32) + (tid >> 5);   // warp: index in the whole system
