@@ -375,7 +375,7 @@ int qpde_gmwb2d_solve(qpde_handle *h, const qpde_gmwb2d *problem, double *V,
  * caller moves the owned lines between ranks (NCCL broadcast / all-gather of the
  * iterate: the impulse targets (w - z, a - z) live on arbitrary lower A) and
  * reduces the flags.  The system is block lower-triangular by A-line, so the
- * lines are solved in ascending A across the ranks: rank k runs its pass after
+ * lines are solved in ascending A across the ranks (v0_dev: V^n of the running time step): rank k runs its pass after
  * rank k-1 has published its lines, and one round is a direct solve.
  * quantpde_b200/gmwb_sharded.py is the driver; see DESIGN.md §5. */
 typedef struct qpde_gmwb2d_shard qpde_gmwb2d_shard;
@@ -384,12 +384,13 @@ int qpde_gmwb2d_shard_create(qpde_handle *h, const qpde_gmwb2d *problem, int a_b
 int qpde_gmwb2d_shard_destroy(qpde_gmwb2d_shard *shard);
 /* V(T) on the owned lines */
 int qpde_gmwb2d_shard_exit(qpde_gmwb2d_shard *shard, double *x_dev);
-/* control searches + row assembly of the owned lines from the full previous iterate */
-int qpde_gmwb2d_shard_policy(qpde_gmwb2d_shard *shard, const double *x_dev, const double *v0_dev, double h0);
+/* control searches + row assembly of the owned lines from the full previous iterate (the rows do not
+ * depend on V^n: the line pass adds it) */
+int qpde_gmwb2d_shard_policy(qpde_gmwb2d_shard *shard, const double *x_dev, double h0);
 /* the line solves of the owned lines in ascending A, exact once the lines below
  * a_begin are final in x_dev; *status_dev (device int) |= 2 if a line that is
  * iterated in place (same-line impulse targets) did not settle in max_sweeps */
-int qpde_gmwb2d_shard_sweep(qpde_gmwb2d_shard *shard, double *x_dev, int *status_dev);
+int qpde_gmwb2d_shard_sweep(qpde_gmwb2d_shard *shard, double *x_dev, const double *v0_dev, int *status_dev);
 /* relativeError(x, xprev) > tolerance on the owned lines; *notdone_dev (device int) |= 1 */
 int qpde_gmwb2d_shard_relerr(qpde_gmwb2d_shard *shard, const double *x_dev, const double *xprev_dev,
 		int *notdone_dev);

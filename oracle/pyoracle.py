@@ -329,7 +329,11 @@ def run_ref(mode, **kw):
     """Runs oracle/_ref/qpde_ref and parses its dump into numpy arrays."""
     args = [REF_PATH, mode] + ["%s=%s" % (k, repr(v) if isinstance(v, float) else v)
                                for k, v in kw.items()]
-    txt = subprocess.check_output(args).decode()
+    return parse_ref_dump(subprocess.check_output(args).decode())
+
+
+def parse_ref_dump(txt):
+    """The dump format of oracle/shim/ref_driver.cpp (hex floats) -> numpy arrays."""
     toks = txt.split()
     out = {}
     i = 0

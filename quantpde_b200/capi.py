@@ -162,8 +162,8 @@ def lib():
         L.qpde_gmwb2d_shard_create.argtypes = [C.c_void_p, C.POINTER(Gmwb2d), C.c_int, C.c_int, C.POINTER(C.c_void_p)]
         L.qpde_gmwb2d_shard_destroy.argtypes = [C.c_void_p]
         L.qpde_gmwb2d_shard_exit.argtypes = [C.c_void_p, C.c_void_p]
-        L.qpde_gmwb2d_shard_policy.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_double]
-        L.qpde_gmwb2d_shard_sweep.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        L.qpde_gmwb2d_shard_policy.argtypes = [C.c_void_p, C.c_void_p, C.c_double]
+        L.qpde_gmwb2d_shard_sweep.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         L.qpde_gmwb2d_shard_relerr.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         _lib = L
     return _lib
@@ -298,11 +298,11 @@ class GmwbShard:
     def exit_values(self, x):
         check(lib().qpde_gmwb2d_shard_exit(self.ptr, x.data_ptr()), self.handle.ptr)
 
-    def policy(self, x, v0, h0):
-        check(lib().qpde_gmwb2d_shard_policy(self.ptr, x.data_ptr(), v0.data_ptr(), float(h0)), self.handle.ptr)
+    def policy(self, x, h0):
+        check(lib().qpde_gmwb2d_shard_policy(self.ptr, x.data_ptr(), float(h0)), self.handle.ptr)
 
-    def sweep(self, x, status):
-        check(lib().qpde_gmwb2d_shard_sweep(self.ptr, x.data_ptr(), status.data_ptr()), self.handle.ptr)
+    def sweep(self, x, v0, status):
+        check(lib().qpde_gmwb2d_shard_sweep(self.ptr, x.data_ptr(), v0.data_ptr(), status.data_ptr()), self.handle.ptr)
 
     def relerr(self, x, xprev, notdone):
         check(lib().qpde_gmwb2d_shard_relerr(self.ptr, x.data_ptr(), xprev.data_ptr(), notdone.data_ptr()),

@@ -790,11 +790,11 @@ int qpde_gmwb2d_shard_destroy(qpde_gmwb2d_shard *s) {
 	return QPDE_OK
 
 int qpde_gmwb2d_shard_exit(qpde_gmwb2d_shard *s, double *x_dev) { QPDE_SHARD_CALL(gmwb_shard_exit(s->impl, x_dev)); }
-int qpde_gmwb2d_shard_policy(qpde_gmwb2d_shard *s, const double *x_dev, const double *v0_dev, double h0) {
-	QPDE_SHARD_CALL(gmwb_shard_policy(s->impl, x_dev, v0_dev, h0));
+int qpde_gmwb2d_shard_policy(qpde_gmwb2d_shard *s, const double *x_dev, double h0) {
+	QPDE_SHARD_CALL(gmwb_shard_policy(s->impl, x_dev, h0));
 }
-int qpde_gmwb2d_shard_sweep(qpde_gmwb2d_shard *s, double *x_dev, int *status_dev) {
-	QPDE_SHARD_CALL(QPDE_CUDA(s->h, gmwb_shard_sweep(s->impl, x_dev, status_dev)));
+int qpde_gmwb2d_shard_sweep(qpde_gmwb2d_shard *s, double *x_dev, const double *v0_dev, int *status_dev) {
+	QPDE_SHARD_CALL(QPDE_CUDA(s->h, gmwb_shard_sweep(s->impl, x_dev, v0_dev, status_dev)));
 }
 int qpde_gmwb2d_shard_relerr(qpde_gmwb2d_shard *s, const double *x_dev, const double *xprev_dev, int *notdone_dev) {
 	QPDE_SHARD_CALL(gmwb_shard_relerr(s->impl, x_dev, xprev_dev, notdone_dev));

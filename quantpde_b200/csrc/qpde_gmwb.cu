@@ -57,8 +57,11 @@ constexpr int GMWB_LUT = 1 << 16;
 
 // Assembled rows: W sub / diagonal / W super, coefficient of the node below in A,
 // right-hand side, and up to four far impulse targets (index -1 = none).
+// The right-hand side is kept in two terms, rhs = h b(q*) and rhs2 = penalty x reward, and the line
+// pass forms (V^n + rhs) + rhs2 — the reference's order — so that the control search of an
+// iteration does not depend on which V^n its line pass will run with (gmwb_run overlaps the two).
 struct GmwbRows {
-	double *ra, *rb, *rc, *raa, *rhs;
+	double *ra, *rb, *rc, *raa, *rhs, *rhs2;
 	int *tgt; double *tw;       // [4][n]
 };
 
@@ -151,7 +154,7 @@ __global__ void k_gmwb_exit(GmwbDev d, double *x, int row_begin, int row_end) {
 }
 
 __global__ void __launch_bounds__(128)
-k_gmwb_policy(GmwbDev d, GmwbRows R, const double *x, const double *v0, double h0, int row_begin, int row_end) {
+k_gmwb_policy(GmwbDev d, GmwbRows R, const double *x, double h0, int row_begin, int row_end) {
 	const int n = d.nw * d.na;
 	const int row = row_begin + blockIdx.x * blockDim.x + threadIdx.x;
 	const int nw = d.nw;
@@ -227,11 +230,12 @@ k_gmwb_policy(GmwbDev d, GmwbRows R, const double *x, const double *v0, double h
 	// 3. penalty flag and the assembled row of I + h L^q* + P (I - M*)
 	const bool active = has && (d.pen * best) < 0.;
 	double a_ = o.aw * h0, b_ = 1. + o.diag * h0, c_ = o.cw * h0;
-	double rhs = v0[row] + h0 * o.b;
+	const double rhs = h0 * o.b;
+	double rhs2 = 0.;
 	int tg[4] = {-1, -1, -1, -1}; double tw[4] = {0., 0., 0., 0.};
 	if(active) {
 		b_ += d.pen;
-		rhs += d.pen * reward;
+		rhs2 = d.pen * reward;
 #pragma unroll
 		for(int m = 0; m < 4; ++m) {
 			const double fm = d.pen * f[m];
@@ -241,7 +245,7 @@ k_gmwb_policy(GmwbDev d, GmwbRows R, const double *x, const double *v0, double h
 			else if(fm != 0.) { tg[m] = t[m]; tw[m] = fm; }
 		}
 	}
-	R.ra[row] = a_; R.rb[row] = b_; R.rc[row] = c_; R.raa[row] = o.aa * h0; R.rhs[row] = rhs;
+	R.ra[row] = a_; R.rb[row] = b_; R.rc[row] = c_; R.raa[row] = o.aa * h0; R.rhs[row] = rhs; R.rhs2[row] = rhs2;
 #pragma unroll
 	for(int m = 0; m < 4; ++m) { R.tgt[m * n + row] = tg[m]; R.tw[m * n + row] = tw[m]; }
 }
@@ -327,7 +331,7 @@ __host__ __device__ constexpr int gmwb_near_k(int PT) { return PT > 256 ? 4 : 8;
 // the diagonal only) is a scalar "tail" equation folded into row nw - 2.
 template <int M, int PT>
 __global__ void __launch_bounds__(PT, 1)
-k_gmwb_lines(GmwbDev d, GmwbRows R, double *x, int ia_begin, int ia_end, int max_local, int *status) {
+k_gmwb_lines(GmwbDev d, GmwbRows R, double *x, const double *v0, const double *xguess, int ia_begin, int ia_end, int max_local, int *status) {
 	// dynamic shared memory, each line buffer [M PT + 2]: row iw = tid M + j at j PT + tid, the
 	// tail row at M PT.  xa / xb: lines ia - 1 / ia - 2, written by the CTAs that solved them;
 	// rhs: the right-hand side under construction; then this thread's list of targets that
@@ -372,7 +376,7 @@ k_gmwb_lines(GmwbDev d, GmwbRows R, double *x, int ia_begin, int ia_end, int max
 #pragma unroll
 				for(int jj = 0; jj < 4; ++jj) {
 					const int j = j0 + jj, iw = tid * M + j, row = base + (iw < n_main ? iw : 0);
-					aa[j] = R.ra[row]; bb[j] = R.rb[row]; cc[j] = R.rc[row]; raa[j] = R.raa[row]; rr[jj] = R.rhs[row];
+					aa[j] = R.ra[row]; bb[j] = R.rb[row]; cc[j] = R.rc[row]; raa[j] = R.raa[row]; rr[jj] = (v0[row] + R.rhs[row]) + R.rhs2[row];
 #pragma unroll
 					for(int m = 0; m < 4; ++m) { tk[4 * jj + m] = R.tgt[m * n + row]; tw[4 * jj + m] = R.tw[m * n + row]; }
 				}
@@ -402,7 +406,7 @@ k_gmwb_lines(GmwbDev d, GmwbRows R, double *x, int ia_begin, int ia_end, int max
 			if(has_tail) {       // uniform: every thread forms the tail row (broadcast loads), its owner uses it
 				const int row = base + nw - 1;
 				raa_t = ia > 0 ? R.raa[row] : 0.; rb_t = R.rb[row]; rinv_t = 1. / rb_t;
-				double rr = R.rhs[row];
+				double rr = (v0[row] + R.rhs[row]) + R.rhs2[row];
 				int tk[4]; double tw[4], xv[4];
 #pragma unroll
 				for(int m = 0; m < 4; ++m) { tk[m] = R.tgt[m * n + row]; tw[m] = R.tw[m * n + row]; }
@@ -441,6 +445,14 @@ k_gmwb_lines(GmwbDev d, GmwbRows R, double *x, int ia_begin, int ia_end, int max
 			else over_tail |= 1u << b;
 		}
 		const bool iterate = __syncthreads_or(same_line ? 1 : 0) != 0;
+		if(iterate && xguess != x) {
+			// a line that is iterated in place starts from the previous iterate of this line
+#pragma unroll
+			for(int j = 0; j < M; ++j) if(tid * M + j < n_main) x[base + tid * M + j] = xguess[base + tid * M + j];
+			if(tail_owner) x[base + nw - 1] = xguess[base + nw - 1];
+			__threadfence_block();
+			__syncthreads();
+		}
 		// ---- stage 2: lines <= ia - 3 are published
 		if(has_a) {
 			if(ia - 3 < ia_begin) mbar_arrive_local(&pre);         // nobody owns line ia - 3 in this pass
@@ -608,29 +620,30 @@ static int gmwb_cluster() {                // CTAs in the cluster: depth of the 
 }
 
 template <int PT>
-static cudaError_t launch_lines_t(GmwbShard &sh, double *x, int ia0, int ia1, int max_local, int *status) {
+static cudaError_t launch_lines_t(GmwbShard &sh, GmwbRows R, double *x, const double *v0, const double *xguess, int ia0, int ia1, int max_local, int *status, cudaStream_t stream) {
 	const size_t smem = sizeof(double) * 3 * (PT * 8 + 2) + (sizeof(double) + sizeof(int)) * gmwb_near_k(PT) * PT;
 	cudaError_t e = cudaFuncSetAttribute(k_gmwb_lines<8, PT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
 	if(e != cudaSuccess) return e;
 	cudaLaunchConfig_t cfg = {};
 	const int G = gmwb_cluster();
 	if(G > 8) { e = cudaFuncSetAttribute(k_gmwb_lines<8, PT>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1); if(e != cudaSuccess) return e; }
-	cfg.gridDim = dim3(G); cfg.blockDim = dim3(PT); cfg.dynamicSmemBytes = smem; cfg.stream = sh.stream;
+	cfg.gridDim = dim3(G); cfg.blockDim = dim3(PT); cfg.dynamicSmemBytes = smem; cfg.stream = stream;
 	cudaLaunchAttribute attr[1];
 	attr[0].id = cudaLaunchAttributeClusterDimension;
 	attr[0].val.clusterDim.x = G; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
 	cfg.attrs = attr; cfg.numAttrs = 1;
-	return cudaLaunchKernelEx(&cfg, k_gmwb_lines<8, PT>, sh.d, sh.R, x, ia0, ia1, max_local, status);
+	return cudaLaunchKernelEx(&cfg, k_gmwb_lines<8, PT>, sh.d, R, x, v0, xguess, ia0, ia1, max_local, status);
 }
 
-static cudaError_t launch_lines(GmwbShard &sh, double *x, int ia0, int ia1, int *status) {
+static cudaError_t launch_lines(GmwbShard &sh, const GmwbRows &R, double *x, const double *v0, const double *xguess,
+		int ia0, int ia1, int *status, cudaStream_t stream) {
 	++*sh.launches;
 	switch(sh.PT) {
-	case 32:  return launch_lines_t<32>(sh, x, ia0, ia1, sh.max_local, status);
-	case 64:  return launch_lines_t<64>(sh, x, ia0, ia1, sh.max_local, status);
-	case 128: return launch_lines_t<128>(sh, x, ia0, ia1, sh.max_local, status);
-	case 256: return launch_lines_t<256>(sh, x, ia0, ia1, sh.max_local, status);
-	default:  return launch_lines_t<512>(sh, x, ia0, ia1, sh.max_local, status);
+	case 32:  return launch_lines_t<32>(sh, R, x, v0, xguess, ia0, ia1, sh.max_local, status, stream);
+	case 64:  return launch_lines_t<64>(sh, R, x, v0, xguess, ia0, ia1, sh.max_local, status, stream);
+	case 128: return launch_lines_t<128>(sh, R, x, v0, xguess, ia0, ia1, sh.max_local, status, stream);
+	case 256: return launch_lines_t<256>(sh, R, x, v0, xguess, ia0, ia1, sh.max_local, status, stream);
+	default:  return launch_lines_t<512>(sh, R, x, v0, xguess, ia0, ia1, sh.max_local, status, stream);
 	}
 }
 
@@ -679,7 +692,7 @@ int gmwb_shard_create(const qpde_gmwb2d *p, const double *W, int nw, const doubl
 	double *dq = (double *)dalloc(sizeof(double) * p->n_controls), *dz = (double *)dalloc(sizeof(double) * nz);
 	GmwbRows &R = sh->R;
 	R.ra = (double *)dalloc(sizeof(double) * n); R.rb = (double *)dalloc(sizeof(double) * n); R.rc = (double *)dalloc(sizeof(double) * n);
-	R.raa = (double *)dalloc(sizeof(double) * n); R.rhs = (double *)dalloc(sizeof(double) * n);
+	R.raa = (double *)dalloc(sizeof(double) * n); R.rhs = (double *)dalloc(sizeof(double) * n); R.rhs2 = (double *)dalloc(sizeof(double) * n);
 	R.tgt = (int *)dalloc(sizeof(int) * 4 * (size_t)n); R.tw = (double *)dalloc(sizeof(double) * 4 * (size_t)n);
 	sh->flags = (int *)dalloc(sizeof(int) * 4);
 	int *dlutW = (int *)dalloc(sizeof(int) * GMWB_LUT), *dlutA = (int *)dalloc(sizeof(int) * GMWB_LUT);
@@ -712,19 +725,23 @@ void gmwb_shard_exit(GmwbShard *sh, double *x) {
 }
 
 // control searches + row assembly for the shard's lines, from the full previous iterate
-void gmwb_shard_policy(GmwbShard *sh, const double *x, const double *v0, double h0) {
-	const int r0 = sh->a_begin * sh->d.nw, r1 = sh->a_end * sh->d.nw;
+static void launch_policy(GmwbShard *sh, const GmwbRows &R, const double *x, double h0, int a0, int a1, cudaStream_t stream) {
+	const int r0 = a0 * sh->d.nw, r1 = a1 * sh->d.nw;
 	if(r1 > r0) {
 		const size_t smem = (size_t)(128 / sh->d.nw + 2) * sh->d.nz * (2 * sizeof(double) + sizeof(int));
-		k_gmwb_policy<<<(r1 - r0 + 127) / 128, 128, smem, sh->stream>>>(sh->d, sh->R, x, v0, h0, r0, r1);
+		k_gmwb_policy<<<(r1 - r0 + 127) / 128, 128, smem, stream>>>(sh->d, R, x, h0, r0, r1);
 		++*sh->launches;
 	}
 }
 
+void gmwb_shard_policy(GmwbShard *sh, const double *x, double h0) {
+	launch_policy(sh, sh->R, x, h0, sh->a_begin, sh->a_end, sh->stream);
+}
+
 // the shard's line solves in ascending A (exact given final lines below a_begin);
 // *status_dev |= 2 if a line's in-place iteration did not settle
-cudaError_t gmwb_shard_sweep(GmwbShard *sh, double *x, int *status_dev) {
-	if(sh->a_end > sh->a_begin) return launch_lines(*sh, x, sh->a_begin, sh->a_end, status_dev);
+cudaError_t gmwb_shard_sweep(GmwbShard *sh, double *x, const double *v0, int *status_dev) {
+	if(sh->a_end > sh->a_begin) return launch_lines(*sh, sh->R, x, v0, x, sh->a_begin, sh->a_end, status_dev, sh->stream);
 	return cudaSuccess;
 }
 
@@ -737,63 +754,225 @@ void gmwb_shard_relerr(GmwbShard *sh, const double *x, const double *xprev, int 
 	}
 }
 
-// Host driver of the single-GPU solve: the reference's time loop and
-// ToleranceIteration around the kernels, on the shard [0, n_a).
+// Host driver of the single-GPU solve: the reference's time loop and ToleranceIteration around the
+// kernels, on the shard [0, n_a).
+//
+// One policy iteration is a control search over every node (k_gmwb_policy: all SMs, FP64-bound) and
+// a line pass (k_gmwb_lines: one cluster of 8 CTAs, a serial chain of n_a line solves).  Run one
+// after the other they leave 140 SMs idle for half of the time and 8 busy for the other half, so
+// the driver overlaps them along the A-axis, which is cut into a few chunks of lines:
+//   * the control search of iteration k+1 on chunk j needs iterate k on the lines of chunks <= j
+//     only (impulses and the upwinded drift point to equal-or-lower A), so it starts as soon as the
+//     line pass of iteration k has finished chunk j — behind the chain, on the idle SMs;
+//   * the line pass of iteration k+1 on chunk j needs that search and its own chunks < j, so it
+//     trails the pass of iteration k by about one chunk on a second cluster.  What it cannot know
+//     yet is whether iteration k converged: if it did, iteration k+1 belongs to the next time step
+//     and runs with V^n = iterate k, otherwise with the old V^n.  The rows do not depend on V^n (it
+//     enters in the line pass), so only the trailing pass is speculative: it is launched on the
+//     likelier outcome ("this step takes as many iterations as the last") into a buffer of its own and simply
+//     discarded — the right one starts at once from the same rows — when the verdict differs.
+// Every iterate lives in a buffer of its own (a ring), so the passes never overwrite what another
+// one reads; results are bit-identical to running the iterations one after the other
+// (QPDE_GMWB_DEPTH=0).  Everything is ordered by events; the host waits for one 8-byte flag copy
+// per iteration.
+namespace {
+
+struct GmwbPass {
+	int cur = -1, prev = -1, v0 = -1, rset = 0, slot = 0;
+	double h0 = 0.;
+	std::vector<cudaEvent_t> lines_done;
+	cudaEvent_t flag_ready = nullptr;
+};
+
+struct GmwbSearch {         // the control search that last filled a row set
+	int prev = -1; double h0 = 0.; bool valid = false;
+	std::vector<cudaEvent_t> done;
+	std::vector<cudaEvent_t> readers;     // line passes that read the row set since
+};
+
+} // namespace
+
 int gmwb_run(const qpde_gmwb2d *p, const double *W, int nw, const double *A, int na, const double *z, int nz,
 		double *V_host, qpde_gmwb2d_stats *stats, cudaStream_t stream, long long *launches, std::string *error) {
 	const int n = nw * na;
 	GmwbShard *sh = nullptr;
 	int rc = gmwb_shard_create(p, W, nw, A, na, z, nz, 0, na, stream, launches, &sh, error);
 	if(rc != QPDE_OK) return rc;
-	auto dalloc = [&] (size_t bytes) -> double * {
+	bool ok = true;
+	auto dalloc = [&] (size_t bytes) -> void * {
 		void *ptr = nullptr;
-		if(cudaMalloc(&ptr, bytes) != cudaSuccess) return nullptr;
+		if(cudaMalloc(&ptr, bytes) != cudaSuccess) { ok = false; return nullptr; }
 		sh->allocs.push_back(ptr);
-		return (double *)ptr;
+		return ptr;
 	};
-	double *x = dalloc(sizeof(double) * n), *xprev = dalloc(sizeof(double) * n), *v0 = dalloc(sizeof(double) * n);
-	if(!x || !xprev || !v0) { gmwb_shard_destroy(sh); *error = "gmwb: out of device memory"; return QPDE_ERR_CUDA; }
-	int *flags = sh->flags;
-	gmwb_shard_exit(sh, x);
+	const char *env_depth = getenv("QPDE_GMWB_DEPTH"), *env_chunks = getenv("QPDE_GMWB_CHUNKS");
+	// Measured on B200 at 4097 x 1025 nodes (64 steps): 3.49 s one after the other, 2.27 s with the
+	// control search overlapped (depth 1).  The speculative trailing pass (depth 2) pays only where the
+	// control search is much shorter than the line pass — here they are level, and a second pass in
+	// flight has nothing left to hide behind — so it is opt-in.
+	int depth = env_depth ? atoi(env_depth) : 1;
+	if(depth < 0 || depth > 2) depth = 1;
+	// chunks of at least 128 lines: a chunk is one cluster launch and one pipeline fill of the chain
+	int n_ch = env_chunks ? atoi(env_chunks) : 8;
+	if(n_ch > na / 128) n_ch = na / 128;
+	if(n_ch < 1 || depth == 0) n_ch = 1;
+	std::vector<int> a0((size_t)n_ch + 1);
+	for(int j = 0; j <= n_ch; ++j) a0[j] = (int)((long long)na * j / n_ch);
+
+	constexpr int NB = 8, NPASS = 6;
+	double *buf[NB];
+	for(int k = 0; k < NB; ++k) buf[k] = (double *)dalloc(sizeof(double) * n);
+	GmwbRows R[2];
+	R[0] = sh->R;
+	R[1].ra = (double *)dalloc(sizeof(double) * n); R[1].rb = (double *)dalloc(sizeof(double) * n); R[1].rc = (double *)dalloc(sizeof(double) * n);
+	R[1].raa = (double *)dalloc(sizeof(double) * n); R[1].rhs = (double *)dalloc(sizeof(double) * n); R[1].rhs2 = (double *)dalloc(sizeof(double) * n);
+	R[1].tgt = (int *)dalloc(sizeof(int) * 4 * (size_t)n); R[1].tw = (double *)dalloc(sizeof(double) * 4 * (size_t)n);
+	int *flags_dev = (int *)dalloc(sizeof(int) * 2 * NPASS);
+	int *hflags = nullptr;
+	if(!ok || cudaHostAlloc((void **)&hflags, sizeof(int) * 2 * NPASS, cudaHostAllocDefault) != cudaSuccess) {
+		gmwb_shard_destroy(sh); *error = "gmwb: out of memory"; return QPDE_ERR_CUDA;
+	}
+	cudaStream_t sL[2], sP, sR;
+	// the line passes are the critical path: their clusters go first when SMs free up
+	int prio_lo = 0, prio_hi = 0;
+	cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
+	cudaStreamCreateWithPriority(&sL[0], cudaStreamNonBlocking, prio_hi); cudaStreamCreateWithPriority(&sL[1], cudaStreamNonBlocking, prio_hi);
+	cudaStreamCreateWithPriority(&sP, cudaStreamNonBlocking, prio_lo); cudaStreamCreateWithPriority(&sR, cudaStreamNonBlocking, prio_hi);
+	std::vector<cudaEvent_t> all_events;
+	auto new_event = [&] () { cudaEvent_t e; cudaEventCreateWithFlags(&e, cudaEventDisableTiming); all_events.push_back(e); return e; };
+	GmwbPass passes[NPASS];
+	for(int k = 0; k < NPASS; ++k) {
+		passes[k].slot = k;
+		for(int j = 0; j < n_ch; ++j) passes[k].lines_done.push_back(new_event());
+		passes[k].flag_ready = new_event();
+	}
+	GmwbSearch search[2];
+	for(int k = 0; k < 2; ++k) for(int j = 0; j < n_ch; ++j) search[k].done.push_back(new_event());
+	std::vector<cudaEvent_t> buf_events[NB];       // what must have finished before buffer b is overwritten
+	cudaEvent_t start_ready = new_event();
+
+	auto cleanup = [&] () {
+		cudaStreamSynchronize(sL[0]); cudaStreamSynchronize(sL[1]); cudaStreamSynchronize(sP); cudaStreamSynchronize(sR);
+		cudaStreamSynchronize(stream);
+		for(cudaEvent_t e : all_events) cudaEventDestroy(e);
+		cudaStreamDestroy(sL[0]); cudaStreamDestroy(sL[1]); cudaStreamDestroy(sP); cudaStreamDestroy(sR);
+		cudaFreeHost(hflags);
+		gmwb_shard_destroy(sh);
+	};
+
+	// the control search of one iteration: reads buf[prev] chunk by chunk behind its producer
+	auto enqueue_search = [&] (int rset, int prev, double h0, const GmwbPass *producer) {
+		GmwbSearch &S = search[rset];
+		for(int j = 0; j < n_ch; ++j) {
+			if(producer) cudaStreamWaitEvent(sP, producer->lines_done[j], 0);
+			else if(j == 0) cudaStreamWaitEvent(sP, start_ready, 0);
+			if(j == 0) for(cudaEvent_t e : S.readers) cudaStreamWaitEvent(sP, e, 0);      // the passes that still read these rows
+			launch_policy(sh, R[rset], buf[prev], h0, a0[j], a0[j + 1], sP);
+			cudaEventRecord(S.done[j], sP);
+		}
+		S.readers.clear();
+		S.prev = prev; S.h0 = h0; S.valid = true;
+		buf_events[prev].push_back(S.done[n_ch - 1]);
+	};
+	int next_pass = 0, next_buf = 1;
+	auto enqueue_pass = [&] (int prev, int v0, double h0, int rset, int line_stream, const int *keep, int n_keep) -> GmwbPass * {
+		GmwbPass &P = passes[next_pass];
+		next_pass = (next_pass + 1) % NPASS;
+		// a buffer nobody of interest holds
+		for(;; next_buf = (next_buf + 1) % NB) {
+			bool held = next_buf == prev || next_buf == v0;
+			for(int q = 0; q < n_keep; ++q) held = held || next_buf == keep[q];
+			if(!held) break;
+		}
+		P.cur = next_buf; next_buf = (next_buf + 1) % NB;
+		P.prev = prev; P.v0 = v0; P.h0 = h0; P.rset = rset;
+		cudaStream_t sl = sL[line_stream];
+		for(cudaEvent_t e : buf_events[P.cur]) cudaStreamWaitEvent(sl, e, 0);
+		buf_events[P.cur].clear();
+		cudaMemsetAsync(flags_dev + 2 * P.slot, 0, sizeof(int) * 2, sl);
+		for(int j = 0; j < n_ch; ++j) {
+			cudaStreamWaitEvent(sl, search[rset].done[j], 0);
+			launch_lines(*sh, R[rset], buf[P.cur], buf[v0], buf[prev], a0[j], a0[j + 1], flags_dev + 2 * P.slot + 1, sl);
+			cudaEventRecord(P.lines_done[j], sl);
+			cudaStreamWaitEvent(sR, P.lines_done[j], 0);
+			const int r0 = a0[j] * nw, r1 = a0[j + 1] * nw;
+			k_gmwb_relerr<<<(r1 - r0 + 255) / 256, 256, 0, sR>>>(r0, r1, buf[P.cur], buf[prev], 1., sh->d.tol, flags_dev + 2 * P.slot);
+			++*launches;
+		}
+		cudaMemcpyAsync(hflags + 2 * P.slot, flags_dev + 2 * P.slot, sizeof(int) * 2, cudaMemcpyDeviceToHost, sR);
+		cudaEventRecord(P.flag_ready, sR);
+		search[rset].readers.push_back(P.lines_done[n_ch - 1]);
+		buf_events[P.cur].push_back(P.flag_ready);
+		buf_events[prev].push_back(P.flag_ready);
+		buf_events[v0].push_back(P.lines_done[n_ch - 1]);
+		return &P;
+	};
+
+	gmwb_shard_exit(sh, buf[0]);
+	cudaEventRecord(start_ready, stream);
 
 	Replay rp; rp.start(p->T, p->T / p->timesteps, 0);
 	double time1 = p->T;
 	long inner_sum = 0; int n_steps = 0, status = 0;
+	int accepted = 0;                     // buffer of the latest accepted iterate
+	const GmwbPass *accepted_pass = nullptr;
+	GmwbPass *spec = nullptr;             // the trailing pass launched on a prediction
+	long k = 0;                           // iteration counter: row set k % 2, line stream k % 2
+	int last_its = 2;                     // iterations the previous step took: the prediction for this one
+	cudaError_t err = cudaSuccess;
 	bool more = true;
-	while(more) {
+	while(more && err == cudaSuccess) {
 		qpde_step st;
 		more = rp.next(st);
 		const double h0 = time1 - st.t;
-		cudaMemcpyAsync(v0, x, sizeof(double) * n, cudaMemcpyDeviceToDevice, stream);
+		// the step after this one, for the look-ahead
+		double h0_next = 0.; bool has_next = more;
+		if(more) { Replay peek = rp; qpde_step st2; peek.next(st2); h0_next = st.t - st2.t; }
+		const int v0 = accepted;
 		int its = 0, notdone = 0;
 		do {
-			cudaMemcpyAsync(xprev, x, sizeof(double) * n, cudaMemcpyDeviceToDevice, stream);
-			gmwb_shard_policy(sh, xprev, v0, h0);
-			cudaError_t le = launch_lines(*sh, x, 0, na, flags + 1);
-			cudaMemsetAsync(flags, 0, sizeof(int), stream);
-			gmwb_shard_relerr(sh, x, xprev, flags);
-			int host_flags[2] = {0, 0};
-			cudaError_t e = le != cudaSuccess ? le : cudaMemcpyAsync(host_flags, flags, sizeof(int) * 2, cudaMemcpyDeviceToHost, stream);
-			if(e == cudaSuccess) e = cudaStreamSynchronize(stream);
-			if(e != cudaSuccess) {
-				gmwb_shard_destroy(sh);
-				*error = std::string("gmwb iteration: ") + cudaGetErrorString(e);
-				return QPDE_ERR_CUDA;
+			GmwbPass *P = nullptr;
+			if(spec && spec->prev == accepted && spec->v0 == v0 && spec->h0 == h0) P = spec;
+			spec = nullptr;
+			const int rset = (int)(k % 2);
+			if(!P) {
+				if(!(search[rset].valid && search[rset].prev == accepted && search[rset].h0 == h0)) enqueue_search(rset, accepted, h0, accepted_pass);
+				P = enqueue_pass(accepted, v0, h0, rset, rset, nullptr, 0);
 			}
-			notdone = host_flags[0];
-			if(host_flags[1]) status = 2;
-			++its;
+			// ---- look ahead to iteration k + 1
+			const bool predict_converged = its + 1 >= last_its;
+			if(depth >= 1 && (!predict_converged || has_next)) {
+				const double h0_la = predict_converged ? h0_next : h0;
+				const int rs1 = (int)((k + 1) % 2);
+				enqueue_search(rs1, P->cur, h0_la, P);
+				if(depth >= 2 && its + 1 < p->max_inner) {
+					const int keep[3] = { P->cur, v0, accepted };
+					spec = enqueue_pass(P->cur, predict_converged ? P->cur : v0, h0_la, rs1, rs1, keep, 3);
+				}
+			}
+			// ---- the verdict of iteration k
+			err = cudaEventSynchronize(P->flag_ready);
+			if(err != cudaSuccess) break;
+			notdone = hflags[2 * P->slot];
+			if(hflags[2 * P->slot + 1]) status = 2;
+			accepted = P->cur; accepted_pass = P;
+			++its; ++k;
 			if(notdone && its >= p->max_inner) { if(!status) status = 1; break; }
 		} while(notdone);
 		if(stats && stats->inner && n_steps < stats->inner_capacity) stats->inner[n_steps] = its;
 		inner_sum += its;
+		last_its = its;
 		++n_steps;
 		time1 = st.t;
 	}
-	cudaError_t e = cudaMemcpyAsync(V_host, x, sizeof(double) * n, cudaMemcpyDeviceToHost, stream);
-	if(e == cudaSuccess) e = cudaStreamSynchronize(stream);
-	gmwb_shard_destroy(sh);
-	if(e != cudaSuccess) { *error = std::string("gmwb fetch: ") + cudaGetErrorString(e); return QPDE_ERR_CUDA; }
+	if(err == cudaSuccess) err = cudaGetLastError();
+	if(err == cudaSuccess) {
+		// the accepted iterate is complete (its flag was read); copy it out on the handle's stream
+		err = cudaMemcpyAsync(V_host, buf[accepted], sizeof(double) * n, cudaMemcpyDeviceToHost, stream);
+		if(err == cudaSuccess) err = cudaStreamSynchronize(stream);
+	}
+	cleanup();
+	if(err != cudaSuccess) { *error = std::string("gmwb solve: ") + cudaGetErrorString(err); return QPDE_ERR_CUDA; }
 	if(stats) { stats->n_steps = n_steps; stats->mean_inner = (double)inner_sum / n_steps; stats->status = status; stats->nodes_w = nw; stats->nodes_a = na; }
 	return QPDE_OK;
 }

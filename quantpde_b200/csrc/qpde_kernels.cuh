@@ -103,8 +103,8 @@ int gmwb_shard_create(const qpde_gmwb2d *p, const double *W, int nw, const doubl
 		int a_begin, int a_end, cudaStream_t stream, long long *launches, GmwbShard **out, std::string *error);
 void gmwb_shard_destroy(GmwbShard *sh);
 void gmwb_shard_exit(GmwbShard *sh, double *x);
-void gmwb_shard_policy(GmwbShard *sh, const double *x, const double *v0, double h0);
-cudaError_t gmwb_shard_sweep(GmwbShard *sh, double *x, int *status_dev);
+void gmwb_shard_policy(GmwbShard *sh, const double *x, double h0);
+cudaError_t gmwb_shard_sweep(GmwbShard *sh, double *x, const double *v0, int *status_dev);
 void gmwb_shard_relerr(GmwbShard *sh, const double *x, const double *xprev, int *notdone_dev);
 
 // FP64 pipe rate of this device, measured (qpde_peak.cu)

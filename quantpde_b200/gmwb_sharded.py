@@ -42,8 +42,8 @@ class CudaBackend:
         return self.torch.zeros(1, dtype=self.torch.int32, device=self.device)
 
     def exit_values(self, x): self.shard.exit_values(x)
-    def policy(self, x, v0, h0): self.shard.policy(x, v0, h0)
-    def sweep(self, x, v0, h0, status): self.shard.sweep(x, status)
+    def policy(self, x, v0, h0): self.shard.policy(x, h0)
+    def sweep(self, x, v0, h0, status): self.shard.sweep(x, v0, status)
     def relerr(self, x, xprev, notdone): self.shard.relerr(x, xprev, notdone)
     def close(self): self.shard.close()
 

@@ -172,4 +172,26 @@ for name, kw in (("gmwb_small", dict(refine=0, a_points=11, timesteps=8, control
     for key in ("W", "A", "V", "Q", "Z", "value", "steps", "mean_inner", "mean_solver"):
         gm[name + "/" + key] = np.asarray(ref[key])
     print(name, len(ref["W"]), len(ref["A"]), ref["steps"], ref["value"], ref["mean_inner"], ref["mean_solver"])
-np.savez_compressed(os.path.join(os.path.dirname(os.path.abspath(__file__)), "gmwb_reference.npz"), **gm)
+# refinement 3 (513 x 401 nodes, 256 steps): 17 minutes of the reference on one core, so it is run
+# only on request (`--gmwb-k3`, or `--gmwb-k3-dump FILE` with the saved stdout of
+# `oracle/_ref/qpde_ref gmwb refine=3`); every 4th node in both directions is kept (129 x 101 values)
+GM_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "gmwb_reference.npz")
+ref3 = None
+if "--gmwb-k3-dump" in sys.argv:
+    ref3 = po.parse_ref_dump(open(sys.argv[sys.argv.index("--gmwb-k3-dump") + 1]).read())
+elif "--gmwb-k3" in sys.argv:
+    ref3 = po.run_ref("gmwb", refine=3)
+if ref3 is not None:
+    nw3, na3 = len(ref3["W"]), len(ref3["A"])
+    gm["gmwb_k3/args"] = np.array(repr(dict(refine=3)))
+    gm["gmwb_k3/stride"] = np.array(4)
+    gm["gmwb_k3/V_strided"] = ref3["V"].reshape(na3, nw3)[::4, ::4].copy()
+    for key in ("W", "A", "value", "steps", "mean_inner", "mean_solver"):
+        gm["gmwb_k3/" + key] = np.asarray(ref3[key])
+    print("gmwb_k3", nw3, na3, ref3["steps"], ref3["value"], ref3["mean_inner"])
+elif os.path.exists(GM_PATH):
+    old = np.load(GM_PATH, allow_pickle=False)
+    for key in old.files:
+        if key.startswith("gmwb_k3/"):
+            gm[key] = old[key]
+np.savez_compressed(GM_PATH, **gm)

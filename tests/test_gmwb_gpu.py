@@ -42,6 +42,39 @@ def test_gmwb_refinement_two_against_oracle(qpde, handle, oracle):
     assert res["W"][iw] == 100. and res["A"][ia] == 100. and 107.6 < res["V"][ia, iw] < 107.8
 
 
+def test_gmwb_refinement_three_against_the_reference(qpde, handle, oracle):
+    """513 x 401 nodes, 256 steps against the reference's own output (17 minutes of qpde_ref on one
+    core; tests/golden/gmwb_reference.npz keeps every 4th node in both directions)."""
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "gmwb_reference.npz"))
+    res = _solve(qpde, handle, oracle, refine=3)
+    stride = int(g["gmwb_k3/stride"])
+    ref = g["gmwb_k3/V_strided"]
+    assert res["status"] == 0 and res["n_steps"] == int(g["gmwb_k3/steps"]) == 256
+    assert np.array_equal(res["W"], g["gmwb_k3/W"]) and np.array_equal(res["A"], g["gmwb_k3/A"])
+    got = res["V"][::stride, ::stride]
+    assert got.shape == ref.shape == (101, 129)
+    err = np.abs(got - ref) / np.maximum(1., np.abs(ref))
+    assert err.max() <= REL_TOL, "%.3e" % err.max()
+    assert res["mean_inner"] == float(g["gmwb_k3/mean_inner"])              # "Mean Policy Iterations"
+    iw, ia = np.searchsorted(res["W"], 100.), np.searchsorted(res["A"], 100.)
+    assert abs(res["V"][ia, iw] - float(g["gmwb_k3/value"])) <= REL_TOL * 108.
+
+
+def test_gmwb_driver_depths_give_the_same_bits(qpde, handle, oracle):
+    """QPDE_GMWB_DEPTH 0 (iterations one after the other), 1 (control search overlapped with the line
+    pass), 2 (+ speculative trailing pass): identical values and iteration counts."""
+    runs = []
+    for depth in ("0", "1", "2"):
+        os.environ["QPDE_GMWB_DEPTH"] = depth
+        try:
+            runs.append(_solve(qpde, handle, oracle, refine=2, a_points=65))     # 257 lines: two chunks
+        finally:
+            del os.environ["QPDE_GMWB_DEPTH"]
+    for r in runs[1:]:
+        assert np.array_equal(r["V"], runs[0]["V"]) and np.array_equal(r["inner"], runs[0]["inner"])
+        assert r["status"] == 0 and r["mean_inner"] == runs[0]["mean_inner"]
+
+
 def test_gmwb_properties_and_errors(qpde, handle, oracle):
     res = _solve(qpde, handle, oracle, refine=1, sigma=0.3)
     payoff = np.maximum(res["W"][None, :], 0.9 * res["A"][:, None])
@@ -55,13 +88,12 @@ def test_gmwb_properties_and_errors(qpde, handle, oracle):
 
 
 class _TwoShards:
-    """Two A-blocks on one GPU, swept in ascending A as two ranks would."""
+    """`count` A-blocks on one GPU, swept in ascending A as that many ranks would."""
 
-    def __init__(self, handle, problem):
+    def __init__(self, handle, problem, count=2):
         from quantpde_b200 import gmwb_sharded
-        mid = problem.na // 2
-        self.parts = [gmwb_sharded.CudaBackend(handle, problem, 0, mid),
-                      gmwb_sharded.CudaBackend(handle, problem, mid, problem.na)]
+        cuts = [problem.na * k // count for k in range(count + 1)]
+        self.parts = [gmwb_sharded.CudaBackend(handle, problem, cuts[k], cuts[k + 1]) for k in range(count)]
         self.stream = self.parts[0].stream
         self.empty, self.flag = self.parts[0].empty, self.parts[0].flag
 
@@ -86,6 +118,22 @@ def test_gmwb_shard_api_two_blocks_equal_whole(qpde, handle, oracle):
         backend.close()
         assert res["status"] == 0 and res["n_steps"] == whole["n_steps"] and res["mean_inner"] == whole["mean_inner"]
         assert np.array_equal(res["V"], whole["V"])
+
+
+def test_gmwb_config_size_shard_counts_give_the_same_bits(qpde, handle, oracle):
+    """BASELINE.json configs[4] grid (4097 x 1025 nodes, 129 impulse candidates), 64 time steps: the
+    single-GPU solve and the sharded driver with 1, 2 and 4 A-blocks agree bit for bit."""
+    from quantpde_b200 import gmwb_sharded
+    args = (oracle.GMWB_W_AXIS, oracle.uniform_axis(0., 100., 17), [0., 10.], oracle.uniform_axis(0., 1., 3), 6, 64)
+    whole = qpde.gmwb_solve(handle, *args)
+    assert whole["V"].shape == (1025, 4097) and whole["status"] == 0
+    prob = qpde.GmwbProblem(*args)
+    for count in (1, 2, 4):
+        backend = _TwoShards(handle, prob, count)
+        res = gmwb_sharded.solve(prob, backend, 0, 1)
+        backend.close()
+        assert res["status"] == 0 and res["mean_inner"] == whole["mean_inner"], count
+        assert np.array_equal(res["V"], whole["V"]), count
 
 
 def test_gmwb_two_ranks_nccl(qpde, oracle, tmp_path):
