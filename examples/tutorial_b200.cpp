@@ -9,10 +9,13 @@
 //
 //   tutorial_b200 [K=100] [r=.04] [alpha=20] [T=1] [dt=.01] [E=10] [D=0] [refine=0]
 //                 [dividends_after_exercise=0] [device=0]
+//                 [print_min=0] [print_step=10] [print_max=200] [precision=6]
+// Without arguments the output is byte for byte that of the reference program.
 #include <QuantPDE_B200/Core.hpp>
 
 #include <cstdlib>
 #include <cstring>
+#include <iomanip>
 #include <iostream>
 #include <map>
 #include <string>
@@ -63,10 +66,12 @@ int main(int argc, char **argv) {
 		B200Solver solver((int) arg(a, "device", 0));
 		Solution V = stepper.solve(refined, payoff, bdf2, solver);
 
-		// Print the solution in a neighbourhood of the strike (tutorial.cpp:130-141 prints a
-		// uniform sample of the interpolated solution)
-		cout.precision(12);
-		for(Real S = .8 * K; S <= 1.2 * K + 1e-9; S += .05 * K) cout << S << "\t" << V(S) << endl;
+		// Print the solution as the reference does (tutorial.cpp:150-154):
+		//   RectilinearGrid1 printGrid( Axis::range(0., 10., 200.) );  cout << accessor( printGrid, V );
+		// i.e. two columns of width 23 in the stream's default notation (Core/Domain.hpp:417-431)
+		RectilinearGrid1 printGrid( Axis::range(arg(a, "print_min", 0.), arg(a, "print_step", 10.), arg(a, "print_max", 200.)) );
+		cout.precision((int) arg(a, "precision", 6));
+		for(Real S : printGrid.nodes()) cout << setw(23) << S << setw(23) << V(S) << endl;
 	} catch(const exception &e) {
 		cerr << e.what() << endl;
 		return 1;

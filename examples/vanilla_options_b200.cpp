@@ -1,116 +1,167 @@
-// vanilla_options_b200.cpp — the reference's examples/vanilla_options.cpp
-// convergence table (European/American put or call, Rannacher time stepping,
-// penalty method) computed on a B200 through QuantPDE_B200/Core.hpp.
+// vanilla_options_b200.cpp — the reference's examples/vanilla_options.cpp (convergence table for
+// a European / American, digital / non-digital call / put; Rannacher time stepping, penalty
+// method) computed on a B200 through QuantPDE_B200/Core.hpp.
 //
-// The wiring below mirrors examples/vanilla_options.cpp:34-130 of the
-// reference; the table layout mirrors Modules/Utilities/Results.hpp:79-146
-// (headers, Value / Change / Ratio / Timing, precision 6, column width 23).
-// All refinement levels are put into ONE batch and swept in one device call.
-//
-//   vanilla_options_b200 [american=1] [call=0] [kn=5] [k0=0] [K=100] [S0=100]
-//                        [r=.04] [vol=.2] [q=0] [T=1] [N=12] [variable=0] [device=0]
-// variable=1: use_variable_timestepping of vanilla_options.cpp:52-58 (ReverseVariableStepper,
-// target 1 / factor)
+// Same invocation as the reference program — `vanilla_options_b200 [CONF_FILE | -i]` with the
+// JSON keys of examples/vanilla_options.cpp:139-156 — and the same stdout: run(k) below mirrors
+// vanilla_options.cpp:34-130 line by line, the table is Modules/Utilities/Results.hpp:79-168
+// (QuantPDE_B200/Utilities.hpp).  Extra: key=value arguments override single entries, and
+// "device" selects the GPU.
 #include <QuantPDE_B200/Core.hpp>
+#include <QuantPDE_B200/Utilities.hpp>
 
-#include <chrono>
-#include <cstdlib>
-#include <cstring>
-#include <iomanip>
 #include <iostream>
-#include <map>
 #include <memory>
-#include <string>
+#include <numeric>
 
 using namespace QuantPDE_B200;
 using namespace std;
 
-static double arg(const map<string, string> &a, const char *k, double d) {
-	auto it = a.find(k);
-	return it == a.end() ? d : atof(it->second.c_str());
+Real T, r, vol, divs, S_0, K;
+int N;
+bool call, digital, american, variable;
+RectilinearGrid1 *grid;
+B200Solver *solver;
+
+ResultsTuple1 run(int k) {
+
+	// 2^k or 2^(2k)
+	int factor = 1;
+	for(int i = 0; i < k; ++i) {
+		if(american) { factor *= 4; }
+		else         { factor *= 2; }
+	}
+	const int N2k = N * factor;
+
+	Payoff payoff = digital ?
+		  ( call ? digitalCallPayoff(K) : digitalPutPayoff(K) )
+		: (call ? callPayoff(K) : putPayoff(K))
+	;
+
+	auto refined_grid = grid->refined(k);
+
+	// Black-Scholes operator (L in V_t = LV)
+	BlackScholes1 bs(
+		refined_grid,
+		r, vol, divs
+	);
+
+	// Timestepping method
+	unique_ptr<ReverseConstantStepper> stepper(variable
+		? (ReverseConstantStepper *) new ReverseVariableStepper(
+			0.,         // startTime
+			T,          // endTime
+			T / N2k,    // dt
+			1. / factor // target
+		)
+		: new ReverseConstantStepper(
+			0.,     // startTime
+			T,      // endTime
+			T / N2k // dt
+		)
+	);
+
+	// Time discretization method
+	ReverseRannacher discretization(refined_grid, bs);
+	discretization.setIteration(*stepper);
+
+	// American-specific components; penalty method or not?
+	IterationNode *root;
+	unique_ptr<ToleranceIteration> tolerance;
+	unique_ptr<MinPenaltyMethodDifference1> penalty;
+	if(american) {
+		// American case
+		penalty = unique_ptr<MinPenaltyMethodDifference1>(
+			new MinPenaltyMethodDifference1(
+				refined_grid,
+				discretization,
+				payoff
+			)
+		);
+
+		tolerance = unique_ptr<ToleranceIteration>(
+			new ToleranceIteration()
+		);
+
+		penalty->setIteration(*tolerance);
+		stepper->setInnerIteration(*tolerance);
+
+		root = penalty.get();
+	} else {
+		// European case
+		root = &discretization;
+	}
+
+	// Compute solution: the whole backward sweep is one device call
+	auto solution = stepper->solve(
+		refined_grid,
+		payoff,
+		*root,
+		*solver
+	);
+
+	// Timesteps
+	unsigned timesteps = stepper->iterations()[0];
+
+	// Average number of policy iterations
+	Real policy_its = nan("");
+	if(american) {
+		auto its = tolerance->iterations();
+		policy_its = accumulate(its.begin(), its.end(), 0.)/its.size();
+	}
+
+	return ResultsTuple1(
+		{(Real) refined_grid.size(), (Real) timesteps, policy_its },
+		solution, S_0
+	);
+
 }
 
 int main(int argc, char **argv) {
-	map<string, string> a;
-	for(int i = 1; i < argc; ++i) {
-		const char *eq = strchr(argv[i], '=');
-		if(!eq) { cerr << "expected key=value, got " << argv[i] << endl; return 2; }
-		a[string(argv[i], eq - argv[i])] = string(eq + 1);
-	}
-	const bool american = arg(a, "american", 1) != 0, call = arg(a, "call", 0) != 0;
-	const int kn = (int) arg(a, "kn", 5), k0 = (int) arg(a, "k0", 0);
-	const Real K = arg(a, "K", 100.), S_0 = arg(a, "S0", 100.);
-	const Real r = arg(a, "r", .04), vol = arg(a, "vol", .2), divs = arg(a, "q", 0.);
-	const Real T = arg(a, "T", 1.);
-	const int N = (int) arg(a, "N", 12);
-	const bool variable = arg(a, "variable", 0) != 0;
-
-	RectilinearGrid1 grid( (S_0 * Axis::special()) + (K * Axis::special()) );
-	const Payoff payoff = call ? callPayoff(K) : putPayoff(K);
-
-	struct Level {
-		RectilinearGrid1 refined_grid;
-		unique_ptr<BlackScholes1> bs;
-		unique_ptr<ReverseConstantStepper> stepper;
-		unique_ptr<ReverseRannacher> discretization;
-		unique_ptr<ToleranceIteration> tolerance;
-		unique_ptr<MinPenaltyMethodDifference1> penalty;
-		IterationNode *root;
-	};
-	vector<unique_ptr<Level>> levels;
-
 	try {
-		B200Solver solver((int) arg(a, "device", 0));
-		const int spacing = 23;
-		cout << setw(spacing) << "Nodes" << setw(spacing) << "Steps"
-		     << setw(spacing) << "Mean Policy Iterations" << setw(spacing) << "Value"
-		     << setw(spacing) << "Change" << setw(spacing) << "Ratio"
-		     << setw(spacing) << "Timing (Seconds)" << endl;
-		cout.precision(6);
-		Real previousValue = nan(""), previousChange = nan("");
+		// Parse configuration file
+		Configuration configuration = getConfiguration(argc, argv);
 
-		for(int k = k0; k <= kn; ++k) {
-			// 2^k or 2^(2k) (vanilla_options.cpp:36-42)
-			int factor = 1;
-			for(int i = 0; i < k; ++i) factor *= american ? 4 : 2;
-			const int N2k = N * factor;
+		// Get options
+		int kn, k0;
+		Real S_max, S_min, dS;
+		kn = getInt(configuration, "maximum_refinement", 5);
+		k0 = getInt(configuration, "minimum_refinement", 0);
+		T = getReal(configuration, "time_to_expiry", 1.);
+		r = getReal(configuration, "interest_rate", .04);
+		vol = getReal(configuration, "volatility", .2);
+		divs = getReal(configuration, "dividend_rate", 0.);
+		S_0 = getReal(configuration, "asset_price", 100.);
+		K = getReal(configuration, "strike_price", 100.);
+		S_min = getReal(configuration, "print_asset_price_minimum", 0.);
+		S_max = getReal(configuration, "print_asset_price_maximum", S_0 * 2.);
+		dS = getReal(configuration, "print_asset_price_step_size", S_0 / 10.);
+		N = getInt(configuration, "initial_number_of_timesteps", 12);
+		call = getBool(configuration, "is_call", true);
+		digital = getBool(configuration, "is_digital", false);
+		american = getBool(configuration, "is_american", false);
+		variable = getBool(configuration, "use_variable_timestepping", false);
+		RectilinearGrid1 default_grid( (S_0 * Axis::special()) + (K * Axis::special()) );
+		RectilinearGrid1 tmp = getGrid(configuration, "initial_grid", default_grid);
+		grid = &tmp;
+		B200Solver device(getInt(configuration, "device", 0));
+		solver = &device;
 
-			unique_ptr<Level> L(new Level());
-			L->refined_grid = grid.refined(k);
-			L->bs.reset(new BlackScholes1(L->refined_grid, r, vol, divs));
-			if(variable) L->stepper.reset(new ReverseVariableStepper(0., T, T / N2k, 1. / factor));
-			else L->stepper.reset(new ReverseConstantStepper(0., T, T / N2k));
-			L->discretization.reset(new ReverseRannacher(L->refined_grid, *L->bs));
-			L->discretization->setIteration(*L->stepper);
-			L->root = L->discretization.get();
-			if(american) {
-				L->penalty.reset(new MinPenaltyMethodDifference1(L->refined_grid, *L->discretization, payoff));
-				L->tolerance.reset(new ToleranceIteration());
-				L->penalty->setIteration(*L->tolerance);
-				L->stepper->setInnerIteration(*L->tolerance);
-				L->root = L->penalty.get();
-			}
+		// Print configuration file
+		cerr << configuration << endl << endl;
 
-			auto start = chrono::steady_clock::now();
-			Solution solution = L->stepper->solve(L->refined_grid, payoff, *L->root, solver);
-			const Real seconds = chrono::duration<Real>(chrono::steady_clock::now() - start).count();
-
-			const Real value = solution(S_0);
-			const Real change = value - previousValue, ratio = previousChange / change;
-			cout << fixed << setw(spacing) << (Real) L->refined_grid.size()
-			     << setw(spacing) << (Real) L->stepper->iterations()[0];
-			const Real its = american ? L->tolerance->meanIterations() : nan("");
-			Real intpart;
-			if(abs(modf(its, &intpart)) < epsilon) cout << fixed; else cout << scientific;
-			cout << setw(spacing) << its;
-			cout << scientific << setw(spacing) << value << setw(spacing) << change
-			     << setw(spacing) << ratio << setw(spacing) << seconds << endl;
-			previousChange = change; previousValue = value;
-			levels.push_back(std::move(L));
-		}
+		// Run and print results
+		ResultsBuffer1 buffer(
+			run,
+			{ "Nodes", "Steps", "Mean Policy Iterations" },
+			kn, k0
+		);
+		buffer.setPrintGrid( RectilinearGrid1(Axis::range(S_min, dS, S_max)) );
+		buffer.stream();
 	} catch(const exception &e) {
 		cerr << e.what() << endl;
 		return 1;
 	}
+
 	return 0;
 }

@@ -25,12 +25,25 @@ def _table(text):
     return np.array([[float(t) for t in ln.split()] for ln in text.strip().splitlines()])
 
 
+def _rows(text):
+    """The rows of the convergence table: what follows the header line up to the first empty line (the
+    solution on the print grid comes after it, Results.hpp:148-164)."""
+    rows = []
+    for ln in text.splitlines()[1:]:
+        if not ln.strip():
+            break
+        rows.append(ln)
+    return rows
+
+
 @pytest.mark.parametrize("case,args", [
     ("bermudan_bdf2_k1", ["dt=0.005", "refine=1"]),
     ("dividend_cash_bdf2_k1", ["dt=0.005", "refine=1", "D=1"]),
 ])
 def test_tutorial_example(examples, golden, oracle, case, args):
-    out = subprocess.run([os.path.join(examples, "tutorial_b200")] + args, check=True, capture_output=True, text=True)
+    out = subprocess.run([os.path.join(examples, "tutorial_b200")] + args
+                         + ["precision=12", "print_min=80", "print_step=5", "print_max=120"],
+                         check=True, capture_output=True, text=True)
     tab = _table(out.stdout)
     S_ref, V_ref = golden[case + "/S"], golden[case + "/V"]
     for S, V in tab:
@@ -40,9 +53,9 @@ def test_tutorial_example(examples, golden, oracle, case, args):
 
 
 def test_vanilla_options_example_table(examples, golden):
-    out = subprocess.run([os.path.join(examples, "vanilla_options_b200"), "kn=2"], check=True,
-                         capture_output=True, text=True)
-    rows = out.stdout.strip().splitlines()[1:]
+    out = subprocess.run([os.path.join(examples, "vanilla_options_b200"), "is_american=true", "is_call=false",
+                          "maximum_refinement=2"], check=True, capture_output=True, text=True)
+    rows = _rows(out.stdout)
     assert len(rows) == 3
     for k, row in enumerate(rows):
         cols = row.split()
@@ -54,9 +67,10 @@ def test_vanilla_options_example_table(examples, golden):
 
 def test_vanilla_options_example_variable_timestepping(examples, golden):
     """use_variable_timestepping of vanilla_options.cpp:52-58 through ReverseVariableStepper."""
-    out = subprocess.run([os.path.join(examples, "vanilla_options_b200"), "k0=1", "kn=3", "variable=1"], check=True,
+    out = subprocess.run([os.path.join(examples, "vanilla_options_b200"), "is_american=true", "is_call=false",
+                          "minimum_refinement=1", "maximum_refinement=3", "use_variable_timestepping=true"], check=True,
                          capture_output=True, text=True)
-    rows = out.stdout.strip().splitlines()[1:]
+    rows = _rows(out.stdout)
     assert len(rows) == 3
     for k, row in zip((1, 2, 3), rows):
         cols = row.split()
@@ -70,9 +84,9 @@ def test_jump_diffusion_example_reproduces_the_reference_table(examples, golden)
     """examples/jump_diffusion.cpp:179-190 records this table for the Kou model (the only known-answer
     table in the reference): 3.970527 at 265 nodes x 97 steps, 3.971451 at 529 x 192, 3.972397 at
     1057 x 385, 3.972930 at 2113 x 768 (the grid of BASELINE.json configs[3])."""
-    out = subprocess.run([os.path.join(examples, "jump_diffusion_b200"), "jump_type=double_exponential", "k0=3", "kn=6"],
-                         check=True, capture_output=True, text=True)
-    rows = [r.split() for r in out.stdout.strip().splitlines()[1:]]
+    out = subprocess.run([os.path.join(examples, "jump_diffusion_b200"), "jump_type=double_exponential",
+                          "minimum_refinement=3", "maximum_refinement=6"], check=True, capture_output=True, text=True)
+    rows = [r.split() for r in _rows(out.stdout)]
     assert len(rows) == 4
     for row, (nodes, steps, value, k) in zip(rows, ((265, 97, 3.970527, 3), (529, 192, 3.971451, 4),
                                                     (1057, 385, 3.972397, 5), (2113, 768, 3.972930, 6))):
@@ -82,9 +96,9 @@ def test_jump_diffusion_example_reproduces_the_reference_table(examples, golden)
     assert abs(float(rows[1][3]) - 9.242709e-04) <= 2e-9                           # the recorded "Change"
     assert abs(float(rows[2][3]) - 9.454750e-04) <= 2e-9 and abs(float(rows[3][3]) - 5.331950e-04) <= 2e-9
     assert abs(float(rows[3][4]) - 1.773226e+00) <= 2e-5                           # the recorded "Ratio"
-    out = subprocess.run([os.path.join(examples, "jump_diffusion_b200"), "k0=1", "kn=3"], check=True,
-                         capture_output=True, text=True)                          # Merton (the example's default)
-    rows = [r.split() for r in out.stdout.strip().splitlines()[1:]]
+    out = subprocess.run([os.path.join(examples, "jump_diffusion_b200"), "minimum_refinement=1",
+                          "maximum_refinement=3"], check=True, capture_output=True, text=True)   # Merton (the default)
+    rows = [r.split() for r in _rows(out.stdout)]
     for row, k in ((rows[0], 1), (rows[2], 3)):
         assert int(float(row[1])) == int(golden["jump_merton_k%d/steps" % k])
         assert rel_err(float(row[2]), float(golden["jump_merton_k%d/value" % k])) <= 1e-6
@@ -92,9 +106,10 @@ def test_jump_diffusion_example_reproduces_the_reference_table(examples, golden)
 
 @pytest.mark.parametrize("position", ["short", "long"])
 def test_unequal_borrowing_lending_rates_example(examples, golden, position):
-    out = subprocess.run([os.path.join(examples, "unequal_borrowing_lending_rates_b200"), "kn=2",
-                          "long_position=%d" % (position == "long")], check=True, capture_output=True, text=True)
-    rows = [r.split() for r in out.stdout.strip().splitlines()[1:]]
+    out = subprocess.run([os.path.join(examples, "unequal_borrowing_lending_rates_b200"), "maximum_refinement=2",
+                          "long_position=%s" % ("true" if position == "long" else "false")], check=True,
+                         capture_output=True, text=True)
+    rows = [r.split() for r in _rows(out.stdout)]
     assert len(rows) == 3
     for k, row in enumerate(rows):
         name = "hjb_%s_bdf2_k%d" % (position, k)       # outputs of the reference's own example wiring

@@ -1,0 +1,55 @@
+"""GPU: the example programs reproduce the stdout of the reference's own example programs byte for
+byte ("same convergence-table order"): same invocation (`prog CONF_FILE`, the JSON
+keys of the reference's examples), same table (Modules/Utilities/Results.hpp:79-168), same solution
+on the print grid.  Fixtures: tests/golden/tables/*.txt, recorded by tests/golden/make_tables.py from
+the unmodified examples/*.cpp of the reference compiled against oracle/shim.  Only the timing
+column (the last 23 characters of a table row) is masked."""
+import os
+import subprocess
+
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+TABLES = os.path.join(ROOT, "tests", "golden", "tables")
+
+PROGRAM = {"vanilla": "vanilla_options_b200", "jump": "jump_diffusion_b200",
+           "hjb": "unequal_borrowing_lending_rates_b200", "tutorial": "tutorial_b200"}
+CASES = sorted(f[:-4] for f in os.listdir(TABLES) if f.endswith(".txt"))
+
+
+@pytest.fixture(scope="module")
+def examples():
+    subprocess.run(["make", "-s", "-C", os.path.join(ROOT, "examples")], check=True)
+    return os.path.join(ROOT, "examples", "bin")
+
+
+def mask_timing(text):
+    """Blanks the "Timing (Seconds)" column of the table rows (the block before the first empty line)."""
+    out, table = [], True
+    for k, ln in enumerate(text.splitlines()):
+        if ln.strip() == "":
+            table = False
+        if table and k > 0 and "Timing (Seconds)" in text.splitlines()[0]:
+            ln = ln[:-23] + " " * 23
+        out.append(ln)
+    return "\n".join(out)
+
+
+@pytest.mark.parametrize("case", CASES)
+def test_stdout_equals_the_reference_program(examples, case):
+    prog = PROGRAM[case.split("_")[0]]
+    conf = os.path.join(TABLES, case + ".json")
+    args = [os.path.join(examples, prog)] + ([conf] if os.path.exists(conf) else [])
+    got = subprocess.run(args, check=True, capture_output=True, text=True).stdout
+    want = open(os.path.join(TABLES, case + ".txt")).read()
+    assert mask_timing(got) == mask_timing(want)
+
+
+def test_interactive_mode_reads_the_configuration_from_stdin(examples):
+    """`prog -i < conf` (Configuration.hpp:36-76)"""
+    conf = open(os.path.join(TABLES, "vanilla_digital_put.json")).read()
+    got = subprocess.run([os.path.join(examples, "vanilla_options_b200"), "-i"], input=conf, check=True,
+                         capture_output=True, text=True).stdout
+    assert mask_timing(got) == mask_timing(open(os.path.join(TABLES, "vanilla_digital_put.txt")).read())
