@@ -191,9 +191,11 @@ def sweep(S, lo, di, up, v0, T, steps, n_steps, scheme="rannacher",
 
 
 def american_put(K, r, vol, T, n_steps, refine_times, q=0.0, S0=None, call=False,
-                 american=True, scheme="rannacher", solver=0, variable_target=None, max_steps=100000):
+                 american=True, scheme="rannacher", solver=0, variable_target=None, max_steps=100000,
+                 E=0, dividend=None, dividend_kind="cash", dividend_first=False, exercise=False):
     """The vanilla_options.cpp wiring on the oracle.  variable_target: ReverseVariableStepper(0, T,
-    T / n_steps, target) as vanilla_options.cpp:52-58 builds it."""
+    T / n_steps, target) as vanilla_options.cpp:52-58 builds it.  E > 0: events at T e / E on top of the
+    penalty method — the README's discrete dividends (README.md:357-375) and / or the exercise transform."""
     S = vanilla_grid(K, S0, refine_times)
     lo, di, up = bs_coeffs(S, r, vol, q)
     payoff = np.where(S < K, 0.0, S - K) if call else np.where(S < K, K - S, 0.0)
@@ -202,9 +204,11 @@ def american_put(K, r, vol, T, n_steps, refine_times, q=0.0, S0=None, call=False
                     solver=solver, variable=(T / n_steps, variable_target, 1.0))
         out["S"] = S
         return out
-    steps, n = schedule(T, T / n_steps)
+    steps, n = schedule(T, T / n_steps, [T / E * e for e in range(E)])
     out = sweep(S, lo, di, up, payoff, T, steps, n, scheme=scheme,
-                american=american, obstacle=payoff, solver=solver)
+                american=american, obstacle=payoff, solver=solver,
+                event_obstacle=(K - S) if (E > 0 and exercise) else None,
+                dividend=None if (E == 0 or dividend is None) else (dividend_kind, dividend, dividend_first))
     out["S"] = S
     out["n_steps"] = n
     return out

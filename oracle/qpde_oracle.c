@@ -558,6 +558,7 @@ int qpo_sweep_1d(const qpo_problem *p, double *V, int *inner,
 	double *rhs = (double *)malloc(sizeof(double) * (size_t)n);
 	double *x = (double *)malloc(sizeof(double) * (size_t)n);
 	double *xprev = (double *)malloc(sizeof(double) * (size_t)n);
+	double *xin = (double *)calloc((size_t)n, sizeof(double));
 	double *v1 = (double *)malloc(sizeof(double) * (size_t)n); /* iterand(0) */
 	double *v0 = (double *)malloc(sizeof(double) * (size_t)n); /* iterand(1) */
 	double *bj = (double *)calloc((size_t)n, sizeof(double)); /* op.b(): explicit jump term or 0 */
@@ -837,6 +838,9 @@ int qpo_sweep_1d(const qpo_problem *p, double *V, int *inner,
 		}
 		initialized = 1;
 		if(inner) inner[s] = its;
+		/* the tolerance iteration's iterand(0): what constraintMask() reads, untouched by the events
+		 * below (they transform the stepper's iterand) */
+		memcpy(xin, x, sizeof(double) * (size_t)n);
 
 		/* stepper history push (lookback = the BDF order, else >= 1) */
 		for(k = order - 3; k >= 0; --k) {
@@ -896,7 +900,7 @@ int qpo_sweep_1d(const qpo_problem *p, double *V, int *inner,
 		/* PenaltyMethod::constraintMask (PenaltyMethod.hpp:127-139) on the
 		 * tolerance iteration's last iterand */
 		for(i = 0; i < n; ++i) {
-			const double acc = 0. + 1. * v1[i];
+			const double acc = 0. + 1. * xin[i];
 			mask[i] = (acc - (p->obstacle ? p->obstacle[i] : 0.)) < 0.;
 		}
 	}
@@ -904,7 +908,7 @@ int qpo_sweep_1d(const qpo_problem *p, double *V, int *inner,
 
 	tri_free(&lu);
 	free(A_lo); free(A_di); free(A_up); free(M_lo); free(M_di); free(M_up);
-	free(bj); free(P_di); free(lb); free(rhs); free(x); free(xprev); free(v1); free(v0);
+	free(bj); free(P_di); free(lb); free(rhs); free(x); free(xprev); free(v1); free(v0); free(xin);
 	for(i = 0; i < 4; ++i) free(vh[i]);
 	return status;
 }

@@ -132,6 +132,22 @@ int runVanilla(const Args &a) {
 	// examples/vanilla_options.cpp:52-64: ReverseVariableStepper(0, T, T / N2k, 1 / factor)
 	const Real variableTarget = num(a, "variable_target", 0.);
 
+	// optional events (none by default)
+	const int E = (int) integer(a, "E", 0);
+	const Real D = num(a, "dividend", 0.);
+	const std::string dividendKind = str(a, "dividend_kind", "none");
+	const bool dividendFirst = integer(a, "dividend_first", 0) != 0;  // first in the reverse sweep = add()ed last
+	const bool withExercise = integer(a, "exercise", 0) != 0;
+	auto exercise = [K] (const Interpolant1 &V, Real S) {
+		return max(V(S), K - S);
+	};
+	auto cashDividend = [D] (const Interpolant1 &V, Real S) {
+		return V( max( S - D, 0. ) );
+	};
+	auto proportionalDividend = [D] (const Interpolant1 &V, Real S) {
+		return V( (1. - D) * S );
+	};
+
 	for(int rep = 0; rep < repeat; ++rep) {
 		BlackScholes1 bs(grid, r, vol, q);
 		std::unique_ptr<ReverseConstantStepper> constantStepper;
@@ -139,6 +155,20 @@ int runVanilla(const Args &a) {
 		if(variableTarget > 0.) variableStepper.reset(new ReverseVariableStepper(0., T, T / steps, variableTarget));
 		else constantStepper.reset(new ReverseConstantStepper(0., T, T / steps));
 		Iteration &stepper = variableTarget > 0. ? (Iteration &) *variableStepper : (Iteration &) *constantStepper;
+
+		// README.md:357-375 on top of the penalty method: E event times T e / E with a dividend transform
+		// and / or the exercise transform, add()ed in the order the arguments ask for
+		if(E > 0 && constantStepper) {
+			auto addDividends = [&] () {
+				for(int e = 0; e < E; ++e) {
+					if(dividendKind == "cash") constantStepper->add(T / E * e, cashDividend, grid);
+					else if(dividendKind == "proportional") constantStepper->add(T / E * e, proportionalDividend, grid);
+				}
+			};
+			if(!dividendFirst) addDividends();
+			if(withExercise) for(int e = 0; e < E; ++e) constantStepper->add(T / E * e, exercise, grid);
+			if(dividendFirst) addDividends();
+		}
 
 		std::unique_ptr<IterationNode> discretization;
 		if(scheme == "rannacher") {
@@ -495,7 +525,7 @@ int runGmwb(const Args &a) {
 
 void usage() {
 	std::fprintf(stderr,
-		"qpde_ref vanilla  K= S0= r= vol= q= T= steps= refine= american=0|1 "
+		"qpde_ref vanilla  K= S0= r= vol= q= T= steps= refine= american=0|1 [E= dividend= dividend_kind= dividend_first= exercise=] "
 		"call=0|1 scheme=rannacher|cn|bdf1|bdf2|...|bdf6 axis=special|tutorial repeat=\n"
 		"qpde_ref bermudan K= r= alpha= q= T= steps= E= refine= "
 		"scheme=bdf2|...|bdf6|bdf1|rannacher|cn axis= repeat=\n"

@@ -356,6 +356,15 @@ k_interleaved_sweep(DeviceBatch b, InterleavedWork w, DeviceResult out) {
 		}
 
 		if(st.event_after) {
+			// PenaltyMethod::constraintMask (PenaltyMethod.hpp:127-139) reads the tolerance iteration's last
+			// iterand, which the events below do not touch (they transform the stepper's): with user events
+			// the mask is taken here, before them; the last step of a sweep always ends in an event
+			if(out.active && ob && b.n_exercise > 0) {
+				for(int i = 0; i < N; ++i) {
+					const double pred = (0. + 1. * x[(size_t)i * C]) - ob[(size_t)i * C];
+					out.active[(size_t)c * out.active_stride + i] = pred < 0. ? 1 : 0;
+				}
+			}
 			// Events at one time go in descending add() order (IterativeMethod.hpp:1340-1352)
 			for(int ue = 0; ue < st.user_events; ++ue) {
 				for(int op = 0; op < 2; ++op) {
@@ -402,7 +411,7 @@ k_interleaved_sweep(DeviceBatch b, InterleavedWork w, DeviceResult out) {
 	// ---- outputs (contract-major) ------------------------------------------
 	if(out.V) for(int i = 0; i < N; ++i) out.V[(size_t)c * out.V_stride + i] = x[(size_t)i * C];
 	if(out.S) for(int i = 0; i < N; ++i) out.S[(size_t)c * out.S_stride + i] = w.S[(size_t)i * C + base];
-	if(out.active) {
+	if(out.active && !(ob && b.n_exercise > 0)) {
 		for(int i = 0; i < N; ++i) {
 			const double pred = ob ? (0. + 1. * x[(size_t)i * C]) - ob[(size_t)i * C] : 0.;
 			out.active[(size_t)c * out.active_stride + i] = pred < 0. ? 1 : 0;

@@ -391,6 +391,15 @@ k_interleaved_sweep_tma(const __grid_constant__ TmaMaps maps, DeviceBatch b, Int
 			}
 
 			if(st.event_after) {
+				// PenaltyMethod::constraintMask (PenaltyMethod.hpp:127-139) reads the tolerance iteration's
+				// last iterand, which the events below do not touch: with user events the mask is taken
+				// here, before them; the last step of a sweep always ends in an event
+				if(out.active && ob && b.n_exercise > 0) {
+					for(int i = 0; i < N; ++i) {
+						const double pred = (0. + 1. * x[(size_t)i * ld]) - ob[(size_t)i * ld];
+						out.active[(size_t)c * out.active_stride + i] = pred < 0. ? 1 : 0;
+					}
+				}
 				// Events at one time go in descending add() order (IterativeMethod.hpp:1340-1352).
 				// Rare (E times per sweep): ordinary loads and stores.
 				for(int ue = 0; ue < st.user_events; ++ue) {
@@ -440,7 +449,7 @@ k_interleaved_sweep_tma(const __grid_constant__ TmaMaps maps, DeviceBatch b, Int
 	// ---- outputs (contract-major) ------------------------------------------
 	if(out.V) for(int i = 0; i < N; ++i) out.V[(size_t)c * out.V_stride + i] = x[(size_t)i * ld];
 	if(out.S) for(int i = 0; i < N; ++i) out.S[(size_t)c * out.S_stride + i] = w.S[(size_t)i * ld + base];
-	if(out.active) {
+	if(out.active && !(ob && b.n_exercise > 0)) {
 		for(int i = 0; i < N; ++i) {
 			const double pred = ob ? (0. + 1. * x[(size_t)i * ld]) - ob[(size_t)i * ld] : 0.;
 			out.active[(size_t)c * out.active_stride + i] = pred < 0. ? 1 : 0;

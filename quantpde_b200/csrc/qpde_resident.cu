@@ -235,6 +235,7 @@ k_resident_sweep(DeviceBatch b, DeviceResult out) {
 	PartitionSolver<M, PT, CL> ps;   // cached factorisation (registers)
 	ps.init();
 	unsigned curmask = 0, newmask = 0;  // bit j: row j penalised; bit M: tail row
+	unsigned outmask = 0;               // penalty + events: the active set of the last penalty iterate
 	// row N-2 (row M-1 of the last thread) couples to the tail row; that thread
 	// owns the tail equation and folds the coupling into its rhs.
 	const bool tail_owner = has_tail && rank == CL - 1 && tid == P - 1;
@@ -577,6 +578,10 @@ k_resident_sweep(DeviceBatch b, DeviceResult out) {
 		}
 
 		if(st.event_after) {
+			// PenaltyMethod::constraintMask (PenaltyMethod.hpp:127-139) reads the tolerance iteration's last
+			// iterand, which events do not touch (they transform the stepper's): the mask that goes out is
+			// the one of the last penalty iterate (the last step of a sweep always ends in an event)
+			if(AMERICAN && EVENTS) outmask = newmask;
 			if(EVENTS && st.user_events > 0) {
 				// Events at one time go in descending add() order (IterativeMethod.hpp:1340-1352)
 				for(int ue = 0; ue < st.user_events; ++ue) {
@@ -620,12 +625,25 @@ k_resident_sweep(DeviceBatch b, DeviceResult out) {
 							if(tail_owner) sm.tail.x = xt;
 						}
 						if(!is_dividend && b.exercise_kind != QPDE_EXERCISE_NONE) {
-							// Event<1>::_doEvent with max(V(S), K - S): Core/Event.hpp:100-112
+							// Event<1>::_doEvent with max(V(S), K - S): Core/Event.hpp:100-112.  Under the penalty
+							// iteration pz holds the obstacle, so the exercise value is formed from the grid.
 #pragma unroll
-							for(int j = 0; j < M; ++j) x[j] = x[j] > pz[j] ? x[j] : pz[j];
-							if(tail_owner) sm.tail.x = sm.tail.x > sm.tail.pz ? sm.tail.x : sm.tail.pz;
+							for(int j = 0; j < M; ++j) {
+								const double ev = AMERICAN ? (i0 + j < n_main ? payoff_value(b.exercise_kind, sm_S[j * P + tid], K) : -CUDART_INF) : pz[j];
+								x[j] = x[j] > ev ? x[j] : ev;
+							}
+							if(tail_owner) {
+								const double ev = AMERICAN ? payoff_value(b.exercise_kind, sm.tail.S, K) : sm.tail.pz;
+								sm.tail.x = sm.tail.x > ev ? sm.tail.x : ev;
+							}
 						}
 					}
+				}
+				if(AMERICAN) {
+					// the next step's first penalty iteration assembles P from the transformed solution
+					// (PenaltyMethod.hpp:37-69 reads iterand(0)): new active set, stale factorisation
+					QPDE_MASK_OF(newmask);
+					refactor = true;
 				}
 				team_sync<CL>();
 				publish_first(x[0]);
@@ -651,7 +669,7 @@ k_resident_sweep(DeviceBatch b, DeviceResult out) {
 			if(out.S) out.S[(size_t)cidx * out.S_stride + i] = sm_S[j * P + tid];
 			if(out.active) {
 				const double pred = AMERICAN ? (0. + 1. * x[j]) - pz[j] : 0.;
-				out.active[(size_t)cidx * out.active_stride + i] = pred < 0. ? 1 : 0;
+				out.active[(size_t)cidx * out.active_stride + i] = (AMERICAN && EVENTS ? (outmask >> j & 1u) != 0u : pred < 0.) ? 1 : 0;
 			}
 		}
 	}
@@ -661,7 +679,7 @@ k_resident_sweep(DeviceBatch b, DeviceResult out) {
 		if(out.S) out.S[(size_t)cidx * out.S_stride + N - 1] = sm.tail.S;
 		if(out.active) {
 			const double pred = AMERICAN ? (0. + 1. * sm.tail.x) - sm.tail.pz : 0.;
-			out.active[(size_t)cidx * out.active_stride + N - 1] = pred < 0. ? 1 : 0;
+			out.active[(size_t)cidx * out.active_stride + N - 1] = (AMERICAN && EVENTS ? (outmask >> M & 1u) != 0u : pred < 0.) ? 1 : 0;
 		}
 	}
 	if(rank == 0 && tid == 0) {
@@ -726,7 +744,7 @@ bool resident_supported(const DeviceBatch &b) {
 	if(b.scheme > QPDE_SCHEME_BDF2) return false;   // BDF3 .. BDF6: INTERLEAVED family
 	if(!pick_geometry(b.N, &M, &PT, &CL)) return false;
 	if(CL > 1 && (b.variable_target || b.dividend_kind != QPDE_DIVIDEND_NONE)) return false; // one-CTA features
-	if(b.american && b.n_exercise > 0) return false; // penalty + events: INTERLEAVED family
+	if(b.american && b.n_exercise > 0 && (CL > 1 || (M == 4 && PT == 512))) return false; // penalty + events: one CTA per contract, the default geometries
 	if(b.n_controls != 0 && b.n_controls != 2) return false; // more control values: INTERLEAVED family
 	if(b.variable_target && !((M == 8 && PT == 32) || (M == 8 && PT == 64) || (M == 8 && PT == 256))) return false; // no room for V^n: INTERLEAVED family
 	return true;
@@ -775,7 +793,13 @@ static int launch_rows(const DeviceBatch &b, const DeviceResult &out, cudaStream
 		if(VARIABLE_OK) return launch_extra<M, PT, VARIABLE_OK ? EXTRA_VARIABLE : EXTRA_NONE, CL>(b, out, stream);
 		return QPDE_ERR_UNSUPPORTED;
 	}
-	if(b.n_exercise > 0) {      // events: linear sweeps only (penalty + events: INTERLEAVED family)
+	if(b.n_exercise > 0) {      // events: linear sweeps, and penalised ones on one CTA (American with discrete dividends)
+		constexpr bool PENALTY_OK = CL == 1 && !(M == 4 && PT == 512);
+		if(b.american) {
+			if(!PENALTY_OK) return QPDE_ERR_UNSUPPORTED;
+			return bdf2 ? launch_variant<M, PT, PENALTY_OK ? MODE_PENALTY : MODE_LINEAR, true, EXTRA_EVENTS, CL>(b, out, stream)
+			            : launch_variant<M, PT, PENALTY_OK ? MODE_PENALTY : MODE_LINEAR, false, EXTRA_EVENTS, CL>(b, out, stream);
+		}
 		return bdf2 ? launch_variant<M, PT, MODE_LINEAR, true, EXTRA_EVENTS, CL>(b, out, stream)
 		            : launch_variant<M, PT, MODE_LINEAR, false, EXTRA_EVENTS, CL>(b, out, stream);
 	}

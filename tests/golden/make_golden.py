@@ -133,6 +133,21 @@ for k in (5, 6):
 CASES.append(("jump_merton_k6", "jump",
               dict(steps=768, refine=6, density="lognormal", K=100.0, r=0.05, vol=0.15, T=0.25,
                    mu=-0.1, sd=0.45, **{"lambda": 0.1})))
+# penalty method + events: the README's discrete dividends (README.md:357-375) on an American put
+# (examples/vanilla_options.cpp wiring + stepper.add), also with an exercise transform, up to the
+# BASELINE grid size
+CASES.append(("american_dividend_cash_rannacher_k2", "vanilla",
+              dict(american=1, steps=100, refine=2, K=100.0, r=0.04, vol=0.2, T=1.0, E=4,
+                   dividend=1.0, dividend_kind="cash", dividend_first=0)))
+CASES.append(("american_dividend_prop_bdf2_k3", "vanilla",
+              dict(american=1, steps=150, refine=3, K=95.0, r=0.03, vol=0.3, T=1.5, E=5, scheme="bdf2",
+                   dividend=0.02, dividend_kind="proportional", dividend_first=1)))
+CASES.append(("american_exercise_dividend_bdf1_k2", "vanilla",
+              dict(american=1, steps=80, refine=2, K=100.0, r=0.04, vol=0.25, T=1.0, E=4, scheme="bdf1",
+                   dividend=0.7, dividend_kind="cash", dividend_first=0, exercise=1)))
+CASES.append(("american_dividend_cash_rannacher_k6", "vanilla",
+              dict(american=1, steps=200, refine=6, K=100.0, r=0.04, vol=0.2, T=1.0, E=4,
+                   dividend=1.0, dividend_kind="cash", dividend_first=0)))
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "reference_cases.npz")
 # cases already in the file with the same arguments are kept (pass --all to re-run everything)
 have = np.load(GOLDEN, allow_pickle=False) if os.path.exists(GOLDEN) and "--all" not in sys.argv else None

@@ -6,7 +6,7 @@ amounts against the oracle, the American + dividend combination, and properties.
 import numpy as np
 import pytest
 
-from helpers import REL_TOL, rel_err
+from helpers import REL_TOL, mask_mismatches, rel_err
 
 pytestmark = pytest.mark.gpu
 
@@ -57,29 +57,49 @@ def test_zero_dividend_is_the_identity_and_dividends_raise_put_values(qpde, hand
     assert np.all(r1.V >= r0.V - 1e-12)
 
 
-def test_american_put_with_cash_dividends_vs_oracle(qpde, handle, oracle):
-    """Penalty iteration + events: the INTERLEAVED family (constant volatility)."""
+@pytest.mark.parametrize("kernel", ["resident", "interleaved"])
+@pytest.mark.parametrize("refine,scheme,kind,exercise", [
+    (2, "rannacher", "cash", "none"),          # 129 nodes: one warp per contract
+    (4, "bdf2", "proportional", "none"),       # 513 nodes
+    (6, "rannacher", "cash", "none"),          # 2049 nodes: the README tutorial's case at the BASELINE grid size
+    (6, "bdf1", "cash", "k_minus_s"),          # an exercise transform on top of the penalty constraint
+])
+def test_american_put_with_dividends_vs_oracle(qpde, handle, oracle, kernel, refine, scheme, kind, exercise):
+    """Penalty iteration + events (README.md:357-375 on an American put): both kernel families — the RESIDENT
+    sweep rebuilds the active set from the transformed solution after every event."""
     Cn = 6
     rng = np.random.default_rng(11)
-    K = rng.uniform(90, 110, Cn); vol = rng.uniform(.15, .4, Cn); T = np.full(Cn, 1.); D = rng.uniform(.5, 2., Cn)
+    K = rng.uniform(90, 110, Cn); vol = rng.uniform(.15, .4, Cn); T = np.full(Cn, 1.)
+    D = rng.uniform(.5, 2., Cn) if kind == "cash" else rng.uniform(.005, .03, Cn)
+    nsteps = 100 if refine < 6 else 200
     axis = oracle.special_axis()[None, :] * K[:, None]
-    spec = qpde.BatchSpec(axis=axis, refine=2, r=.04, sigma=vol, q=0., T=T, dt=T / 100, strike=K,
-                          scheme="rannacher", american=True, payoff="put", n_exercise=4, exercise="none",
-                          dividend=dict(kind="cash", amount=D), kernel="auto")
+    spec = qpde.BatchSpec(axis=axis, refine=refine, r=.04, sigma=vol, q=0., T=T, dt=T / nsteps, strike=K,
+                          scheme=scheme, american=True, payoff="put", n_exercise=4, exercise=exercise,
+                          dividend=dict(kind=kind, amount=D), kernel=kernel)
     with qpde.Plan(handle, spec) as plan:
-        assert plan.kernel == "interleaved"
+        assert plan.kernel == kernel
         plan.run(); res = plan.fetch()
     for c in range(Cn):
-        S = oracle.refine(oracle.axis_union(oracle.special_axis() * K[c], oracle.special_axis() * K[c]), 2)
+        S = oracle.refine(oracle.axis_union(oracle.special_axis() * K[c], oracle.special_axis() * K[c]), refine)
         lo, di, up = oracle.bs_coeffs(S, .04, vol[c], 0.)
         payoff = np.where(S < K[c], K[c] - S, 0.)
-        steps, n = oracle.schedule(1., 1. / 100, [1. / 4 * e for e in range(4)])
-        o = oracle.sweep(S, lo, di, up, payoff, 1., steps, n, scheme="rannacher", american=True, obstacle=payoff,
-                         dividend=("cash", D[c], False))
+        steps, n = oracle.schedule(1., 1. / nsteps, [1. / 4 * e for e in range(4)])
+        o = oracle.sweep(S, lo, di, up, payoff, 1., steps, n, scheme=scheme, american=True, obstacle=payoff,
+                         event_obstacle=(K[c] - S) if exercise != "none" else None, dividend=(kind, D[c], False))
         assert res.status[c] == 0 and res.n_steps[c] == n
         err = rel_err(res.V[c], o["V"]).max()
         assert err <= REL_TOL, "contract %d: %.3e" % (c, err)
         assert np.array_equal(res.inner[c, :n], o["inner"])
+        assert mask_mismatches(res.active[c], o["mask"], o["V"], payoff)[0] == 0
+
+
+def test_american_with_events_takes_the_resident_sweep_by_default(qpde, handle, oracle):
+    K = np.array([100., 105.])
+    spec = qpde.BatchSpec(axis=oracle.special_axis()[None, :] * K[:, None], refine=6, r=.04, sigma=.2, q=0., T=1.,
+                          dt=1. / 50, strike=K, scheme="rannacher", american=True, payoff="put", n_exercise=2,
+                          exercise="none", dividend=dict(kind="cash", amount=np.array([1., 1.])), kernel="auto")
+    with qpde.Plan(handle, spec) as plan:
+        assert plan.kernel == "resident"
 
 
 def test_dividend_validation(qpde, handle, oracle):
