@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define QPDE_ABI_VERSION 3
+#define QPDE_ABI_VERSION 4
 
 /* ---- status codes ----------------------------------------------------- */
 enum {
@@ -136,7 +136,14 @@ typedef struct {
 	const double *sigma;     /* [C] volatility parameter (see vol_model)    */
 	const double *q;         /* [C] dividend rate                           */
 	int32_t vol_model;       /* QPDE_VOL_*                                  */
-	int32_t reserved0;
+	int32_t forward;         /* 0: ReverseConstantStepper and the Reverse* discretisations (every example of
+	                            the reference); 1: the forward-time classes — ForwardConstantStepper(0, T, dt)
+	                            (TimeIteration<true>, IterativeMethod.hpp:1494-1495, Stepper.hpp:41) with
+	                            ForwardRannacher / CrankNicolson / BDFOne .. BDFSix: time runs from 0 up to T,
+	                            the payoff is the condition at t = 0, user events sit at T e / E for
+	                            e = 1 .. n_exercise, and events at one time are applied in ascending add()
+	                            order (dividend_first still names the transform applied first).  Constant
+	                            steps only. */
 	const double *sigma_nodes; /* [C][N] when vol_model == QPDE_VOL_NODES   */
 	int64_t sigma_nodes_stride;
 
@@ -283,6 +290,10 @@ int qpde_host_free(void *p);
 /* Replays the reference time loop.  Returns the number of steps (>= 0) and
  * writes min(n, max_steps) entries; out may be NULL to count. */
 int qpde_make_schedule(double T, double dt, const double *event_times,
+		int n_events, qpde_step *out, int max_steps);
+/* The same for ForwardConstantStepper(0, T, dt) (TimeIteration<true>, IterativeMethod.hpp:1494-1495):
+ * time runs from 0 up to T, the smallest event time is popped first. */
+int qpde_make_schedule_forward(double T, double dt, const double *event_times,
 		int n_events, qpde_step *out, int max_steps);
 /* N after refinement. */
 int qpde_refined_size(int n_axis, int refine);

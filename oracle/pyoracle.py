@@ -44,7 +44,7 @@ class Problem(C.Structure):
                 ("solver", C.c_int),
                 ("dividend_kind", C.c_int), ("dividend_first", C.c_int), ("dividend", C.c_double),
                 ("variable_target", C.c_double), ("variable_scale", C.c_double), ("variable_dt0", C.c_double),
-                ("steps_taken", C.POINTER(C.c_int))]
+                ("steps_taken", C.POINTER(C.c_int)), ("forward", C.c_int)]
 
 
 DIVIDENDS = {None: 0, "none": 0, "cash": 1, "proportional": 2}
@@ -109,12 +109,12 @@ def vanilla_grid(K, S0=None, refine_times=0):
     return refine(axis_union(sp * S0, sp * K), refine_times)
 
 
-def schedule(T, dt, event_times=()):
+def schedule(T, dt, event_times=(), forward=False):
     ev = np.ascontiguousarray(event_times, dtype=np.float64)
     cap = int(T / dt) + 8 + 2 * len(ev)
     buf = (Step * cap)()
-    n = lib().qpo_schedule(C.c_double(T), C.c_double(dt), _dp(ev) if len(ev) else None,
-                           len(ev), buf, cap)
+    fn = lib().qpo_schedule_forward if forward else lib().qpo_schedule
+    n = fn(C.c_double(T), C.c_double(dt), _dp(ev) if len(ev) else None, len(ev), buf, cap)
     assert n <= cap
     return buf, n
 
@@ -140,7 +140,7 @@ def interp(x, v, c):
 def sweep(S, lo, di, up, v0, T, steps, n_steps, scheme="rannacher",
           american=False, obstacle=None, event_obstacle=None,
           tolerance=1e-6, scale=1.0, penalty_tol=1e-6, max_inner=1000, solver=0,
-          policy_rows=None, policy_max=False, jump=None, dividend=None, variable=None):
+          policy_rows=None, policy_max=False, jump=None, dividend=None, variable=None, forward=False):
     """Returns dict(V, inner, mask, status).  dividend = (kind, D, first); variable = (dt0, target,
     scale): ReverseVariableStepper, `steps` ignored, n_steps = capacity, out['n_steps'] = steps taken.  policy_rows = (lo, di, up), each
     [n_controls][n]: PolicyIteration over the controls."""
@@ -167,6 +167,7 @@ def sweep(S, lo, di, up, v0, T, steps, n_steps, scheme="rannacher",
         p.event_obstacle = _dp(event_obstacle)
     p.tolerance, p.scale, p.penalty_tol, p.max_inner = tolerance, scale, penalty_tol, max_inner
     p.solver = solver
+    p.forward = int(forward)
     if dividend is not None:
         p.dividend_kind, p.dividend, p.dividend_first = DIVIDENDS[dividend[0]], float(dividend[1]), int(dividend[2])
     if jump is not None:
@@ -209,6 +210,26 @@ def american_put(K, r, vol, T, n_steps, refine_times, q=0.0, S0=None, call=False
                 american=american, obstacle=payoff, solver=solver,
                 event_obstacle=(K - S) if (E > 0 and exercise) else None,
                 dividend=None if (E == 0 or dividend is None) else (dividend_kind, dividend, dividend_first))
+    out["S"] = S
+    out["n_steps"] = n
+    return out
+
+
+def forward_option(K, r, vol, T, n_steps, refine_times, q=0.0, call=False, american=False, scheme="rannacher",
+                   alpha=0.0, E=0, dividend=None, dividend_kind="cash", dividend_first=False, exercise=False):
+    """The forward-time classes on the oracle (ForwardConstantStepper(0, T, T / n_steps) + ForwardRannacher /
+    CrankNicolson / BDFk, IterativeMethod.hpp:1494-1495): marched from the payoff at t = 0 up to T; events at
+    T e / E, e = 1 .. E.  alpha > 0: local volatility alpha / S instead of vol."""
+    S = vanilla_grid(K, None, refine_times)
+    with np.errstate(divide="ignore"):
+        v = alpha / S if alpha > 0 else vol
+    lo, di, up = bs_coeffs(S, r, v, q)
+    payoff = np.where(S < K, 0.0, S - K) if call else np.where(S < K, K - S, 0.0)
+    steps, n = schedule(T, T / n_steps, [T / E * e for e in range(1, E + 1)], forward=True)
+    out = sweep(S, lo, di, up, payoff, T, steps, n, scheme=scheme, american=american, obstacle=payoff,
+                event_obstacle=(K - S) if (E > 0 and exercise) else None,
+                dividend=None if (E == 0 or dividend is None) else (dividend_kind, dividend, dividend_first),
+                forward=True)
     out["S"] = S
     out["n_steps"] = n
     return out

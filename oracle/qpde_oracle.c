@@ -120,6 +120,61 @@ int qpo_schedule(double T, double dt_const, const double *event_times,
 	return n;
 }
 
+static int cmp_asc(const void *a, const void *b) {
+	const double x = *(const double *)a, y = *(const double *)b;
+	return x < y ? -1 : (x > y ? 1 : 0);
+}
+
+/* TimeIteration<true> (IterativeMethod.hpp:1494-1495) driven by ForwardConstantStepper
+ * (Stepper.hpp:41): direction = +1, Order = std::greater, so the queue pops the SMALLEST time
+ * first and, among events at one time, the one add()ed first (TimeOrder, :1340-1352); the
+ * NullEvent (id UINT_MAX) sits at the terminal time T and goes last there. */
+int qpo_schedule_forward(double T, double dt_const, const double *event_times,
+		int n_events, qpo_step *out, int max_steps) {
+	double *ev = (double *)malloc(sizeof(double) * (size_t)(n_events + 1));
+	int n = 0, e = 0, i;
+	double t = 0., dt = -1., dtPrevious;
+	for(i = 0; i < n_events; ++i) ev[i] = event_times[i];
+	qsort(ev, (size_t)n_events, sizeof(double), cmp_asc);
+
+	do {
+		/* top of the queue: the smallest remaining user event time, or the NullEvent at T if
+		 * that comes first */
+		const double nextEventTime = (e < n_events && ev[e] <= T) ? ev[e] : T;
+		int users = 0;
+		do {
+			double tmp;
+			dtPrevious = dt;
+			dt = dt_const;
+			tmp = t + 1. * dt;
+			if(fabs(tmp - nextEventTime) < DBL_EPSILON) {
+				tmp = nextEventTime;
+			} else if(tmp > nextEventTime) {
+				tmp = nextEventTime;
+				dt = 1. * (nextEventTime - t);
+			}
+			t = tmp;
+			if(n < max_steps) {
+				out[n].t = t;
+				out[n].dt = dt;
+				out[n].same_dt = (dt == dtPrevious);
+				out[n].event_after = 0;
+				out[n].user_events = 0;
+			}
+			++n;
+		} while(nextEventTime > t + 1. * DBL_EPSILON);
+		t = nextEventTime;
+		while(e < n_events && ev[e] == t) { ++e; ++users; }
+		if(n - 1 < max_steps) {
+			out[n - 1].event_after = 1;
+			out[n - 1].user_events = users;
+		}
+	} while(T > t);
+
+	free(ev);
+	return n;
+}
+
 /* ------------------------------------------------------------------------ */
 /* Operator rows: Modules/Operators/BlackScholes.hpp:136-226                 */
 /* ------------------------------------------------------------------------ */
@@ -543,6 +598,9 @@ static void bdf_coefficients(int k, const double *g, double *c, double *hh) {
  * saw an active set different from the one of the previous solve */
 long qpo_diag_solves = 0, qpo_diag_mask_changes = 0;
 
+/* time elapsed between a history time and the new implicit time (Rannacher.hpp:17-21) */
+#define LAPSE(then, now) (p->forward ? (now) - (then) : (then) - (now))
+
 int qpo_sweep_1d(const qpo_problem *p, double *V, int *inner,
 		unsigned char *mask) {
 	const int n = p->n;
@@ -586,7 +644,7 @@ int qpo_sweep_1d(const qpo_problem *p, double *V, int *inner,
 	for(i = 0; i < n; ++i) P_di[i] = 0.;
 	memcpy(v1, p->v0, sizeof(double) * (size_t)n);
 	/* the stepper pushes (T, V^0) (:1171-1174) */
-	time1 = p->T;
+	time1 = p->forward ? 0. : p->T;   /* initialTime() */
 	hist = 1;
 
 	for(s = 0; ; ++s) {
@@ -665,12 +723,12 @@ int qpo_sweep_1d(const qpo_problem *p, double *V, int *inner,
 
 		/* --- left-hand side  lA  and right-hand side  lb ----------------- */
 		{
-			const double h0 = time1 - t; /* difference(t1, t0), reverse time */
+			const double h0 = LAPSE(time1, t); /* difference(t1, t0): t0 - t1 in reverse time, t1 - t0 forward */
 			if(use_bdfk) {
 				/* BDF.hpp:139-470: A = I + hh op.A, b = (c v_new - c' v' + ... + op.b) hh */
 				double g[6], c[6], hh;
-				g[0] = time1 - t; g[1] = time0 - t;
-				for(k = 2; k < use_bdfk; ++k) g[k] = th[k - 2] - t;
+				g[0] = LAPSE(time1, t); g[1] = LAPSE(time0, t);
+				for(k = 2; k < use_bdfk; ++k) g[k] = LAPSE(th[k - 2], t);
 				bdf_coefficients(use_bdfk, g, c, &hh);
 				hA = hh;
 				for(i = 0; i < n; ++i) {
@@ -687,8 +745,8 @@ int qpo_sweep_1d(const qpo_problem *p, double *V, int *inner,
 				}
 			} else if(use_bdf2) {
 				/* BDF.hpp:68-117 */
-				const double h1 = time1 - t;
-				const double hh0 = time0 - t;
+				const double h1 = LAPSE(time1, t);
+				const double hh0 = LAPSE(time0, t);
 				const double hh = (hh0 * h1) / (hh0 + h1);
 				const double c1 = hh0 / h1, c0 = h1 / hh0, den = hh0 - h1;
 				hA = hh;

@@ -52,6 +52,9 @@ int qpo_axis_refine(const double *in, int n, int times, double *out);
  * (any order).  Returns the number of steps (writes at most max_steps). */
 int qpo_schedule(double T, double dt, const double *event_times, int n_events,
 		qpo_step *out, int max_steps);
+/* The same for ForwardConstantStepper (time runs from 0 up to T; events may not sit at 0). */
+int qpo_schedule_forward(double T, double dt, const double *event_times, int n_events,
+		qpo_step *out, int max_steps);
 
 /* BlackScholes<1,0>::A rows (Modules/Operators/BlackScholes.hpp:136-226).
  * r, v, q, lambda are per-node arrays of length n. */
@@ -114,6 +117,9 @@ typedef struct {
 	 * reference's stepper reads a history slot that clear() has emptied). */
 	double variable_target, variable_scale, variable_dt0;
 	int *steps_taken;
+	/* 1: the forward-time classes (TimeIteration<true>, ForwardConstantStepper, ForwardRannacher ...):
+	 * v0 is the condition at t = 0, `steps` comes from qpo_schedule_forward.  Constant steps only. */
+	int forward;
 } qpo_problem;
 enum { QPO_DIVIDEND_NONE = 0, QPO_DIVIDEND_CASH = 1, QPO_DIVIDEND_PROPORTIONAL = 2 };
 

@@ -232,6 +232,93 @@ int runVanilla(const Args &a) {
 }
 
 ////////////////////////////////////////////////////////////////////////////////
+// forward: the forward-time classes (TimeIteration<true>, IterativeMethod.hpp:1494-1495;
+// ForwardConstantStepper, Stepper.hpp:41; ForwardRannacher / CrankNicolson / BDFOne .. BDFSix):
+// V_t + L V = 0 marched from t = 0 to T from the payoff, constant or alpha / S volatility,
+// optional penalty method, optional events at T e / E, e = 1 .. E (an event at the initial
+// time is not allowed, IterativeMethod.hpp:1411)
+////////////////////////////////////////////////////////////////////////////////
+
+int runForward(const Args &a) {
+	const Real K = num(a, "K", 100.);
+	const Real r = num(a, "r", .04), vol = num(a, "vol", .2), alpha = num(a, "alpha", 0.);
+	const Real q = num(a, "q", 0.), T = num(a, "T", 1.);
+	const long steps = integer(a, "steps", 100);
+	const int E = (int) integer(a, "E", 0);
+	const int refine = (int) integer(a, "refine", 0);
+	const bool american = integer(a, "american", 0) != 0;
+	const bool call = integer(a, "call", 0) != 0;
+	const std::string scheme = str(a, "scheme", "rannacher");
+	const Real D = num(a, "dividend", 0.);
+	const std::string dividendKind = str(a, "dividend_kind", "none");
+	const bool dividendFirst = integer(a, "dividend_first", 0) != 0;  // applied first = add()ed first (forward: ascending id)
+	const bool withExercise = integer(a, "exercise", 0) != 0;
+
+	RectilinearGrid1 coarse( baseAxis(str(a, "axis", "special"), K, K) );
+	auto grid = coarse.refined(refine);
+
+	Function1 payoff = call ? callPayoff(K) : putPayoff(K);
+	auto exercise = [K] (const Interpolant1 &V, Real S) { return max(V(S), K - S); };
+	auto cashDividend = [D] (const Interpolant1 &V, Real S) { return V( max( S - D, 0. ) ); };
+	auto proportionalDividend = [D] (const Interpolant1 &V, Real S) { return V( (1. - D) * S ); };
+	auto localVol = [alpha] (Real S) { return alpha / S; };
+
+	ForwardConstantStepper stepper(0., T, T / steps);
+	auto addDividends = [&] () {
+		for(int e = 1; e <= E; ++e) {
+			if(dividendKind == "cash") stepper.add(T / E * e, cashDividend, grid);
+			else if(dividendKind == "proportional") stepper.add(T / E * e, proportionalDividend, grid);
+		}
+	};
+	if(dividendFirst) addDividends();
+	if(withExercise) for(int e = 1; e <= E; ++e) stepper.add(T / E * e, exercise, grid);
+	if(!dividendFirst) addDividends();
+
+	std::unique_ptr<BlackScholes1> bs(alpha > 0. ? new BlackScholes1(grid, r, localVol, q) : new BlackScholes1(grid, r, vol, q));
+
+	std::unique_ptr<IterationNode> discretization;
+	if(scheme == "rannacher") discretization.reset(new ForwardRannacher(grid, *bs));
+	else if(scheme == "cn") discretization.reset(new ForwardCrankNicolson(grid, *bs));
+	else if(scheme == "bdf1") discretization.reset(new ForwardBDFOne(grid, *bs));
+	else if(scheme == "bdf2") discretization.reset(new ForwardBDFTwo(grid, *bs));
+	else if(scheme == "bdf3") discretization.reset(new ForwardBDFThree(grid, *bs));
+	else if(scheme == "bdf4") discretization.reset(new ForwardBDFFour(grid, *bs));
+	else if(scheme == "bdf5") discretization.reset(new ForwardBDFFive(grid, *bs));
+	else if(scheme == "bdf6") discretization.reset(new ForwardBDFSix(grid, *bs));
+	else { std::fprintf(stderr, "unknown scheme\n"); return 2; }
+	discretization->setIteration(stepper);
+
+	ToleranceIteration tolerance;
+	std::unique_ptr<MinPenaltyMethodDifference1> penalty;
+	IterationNode *root = discretization.get();
+	if(american) {
+		penalty.reset(new MinPenaltyMethodDifference1(grid, *discretization, payoff));
+		penalty->setIteration(tolerance);
+		stepper.setInnerIteration(tolerance);
+		root = penalty.get();
+	}
+
+	SparseLUSolver solver;
+	auto begin = std::chrono::steady_clock::now();
+	auto solution = stepper.solve(grid, payoff, *root, solver);
+	auto end = std::chrono::steady_clock::now();
+
+	std::vector<long> inner, mask;
+	if(american) {
+		for(auto k : tolerance.iterations()) inner.push_back((long)k);
+		for(bool b : penalty->constraintMask()) mask.push_back(b);
+	}
+	std::printf("value %a\n", (double) solution(K));
+	std::printf("seconds %.9g\n", std::chrono::duration<double>(end - begin).count());
+	std::printf("steps %ld\n", (long) stepper.iterations()[0]);
+	dumpReals("S", nodes(grid));
+	dumpReals("V", nodeValues(grid, solution));
+	dumpInts("inner", inner);
+	dumpInts("mask", mask);
+	return 0;
+}
+
+////////////////////////////////////////////////////////////////////////////////
 // bermudan: local volatility alpha / S, E exercise dates at T e / E,
 // BDF2 (tutorial.cpp) or Rannacher, no inner iteration
 ////////////////////////////////////////////////////////////////////////////////
@@ -550,6 +637,7 @@ int main(int argc, char **argv) {
 	const std::string mode(argv[1]);
 	if(mode == "vanilla")  return runVanilla(a);
 	if(mode == "bermudan") return runBermudan(a);
+	if(mode == "forward") return runForward(a);
 	if(mode == "hjb")      return runHjb(a);
 	if(mode == "jump")     return runJump(a);
 	if(mode == "gmwb")     return runGmwb(a);

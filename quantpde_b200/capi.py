@@ -13,7 +13,7 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "lib", "libqpde_b200.so")
 
-ABI_VERSION = 3
+ABI_VERSION = 4
 
 OK, ERR_INVALID, ERR_CUDA, ERR_NO_DEVICE, ERR_NOT_CONVERGED, ERR_UNSUPPORTED = 0, -1, -2, -3, -4, -5
 
@@ -44,7 +44,7 @@ class Batch(C.Structure):
         ("abi_version", C.c_int32), ("n_contracts", C.c_int32),
         ("axis", _dp), ("axis_stride", C.c_int64), ("n_axis", C.c_int32), ("refine", C.c_int32),
         ("r", _dp), ("sigma", _dp), ("q", _dp),
-        ("vol_model", C.c_int32), ("reserved0", C.c_int32),
+        ("vol_model", C.c_int32), ("forward", C.c_int32),
         ("sigma_nodes", _dp), ("sigma_nodes_stride", C.c_int64),
         ("T", _dp), ("dt", _dp), ("scheme", C.c_int32), ("max_steps", C.c_int32),
         ("variable_target", _dp), ("variable_scale", C.c_double),
@@ -104,7 +104,7 @@ class Gmwb2dStats(C.Structure):
 EXPORTS = [
     "qpde_abi_version", "qpde_create", "qpde_destroy", "qpde_last_error", "qpde_stream",
     "qpde_synchronize", "qpde_launch_count", "qpde_sm_count", "qpde_measure_fp64_peak", "qpde_host_alloc",
-    "qpde_host_free", "qpde_make_schedule", "qpde_refined_size", "qpde_bs1d_sweep",
+    "qpde_host_free", "qpde_make_schedule", "qpde_make_schedule_forward", "qpde_refined_size", "qpde_bs1d_sweep",
     "qpde_bs1d_plan_create", "qpde_bs1d_plan_run", "qpde_bs1d_plan_fetch",
     "qpde_bs1d_plan_destroy", "qpde_bs1d_plan_kernel", "qpde_bs1d_plan_nodes", "qpde_bs1d_plan_tma_staged",
     "qpde_bs1d_plan_max_steps", "qpde_jump_nfft", "qpde_jump_setup", "qpde_refine_axis",
@@ -144,6 +144,8 @@ def lib():
         L.qpde_host_free.argtypes = [C.c_void_p]
         L.qpde_make_schedule.argtypes = [C.c_double, C.c_double, _dp, C.c_int,
                                          C.POINTER(Step), C.c_int]
+        L.qpde_make_schedule_forward.argtypes = [C.c_double, C.c_double, _dp, C.c_int,
+                                                 C.POINTER(Step), C.c_int]
         L.qpde_refined_size.argtypes = [C.c_int, C.c_int]
         L.qpde_bs1d_sweep.argtypes = [C.c_void_p, C.POINTER(Batch), C.POINTER(Result)]
         L.qpde_bs1d_plan_create.argtypes = [C.c_void_p, C.POINTER(Batch), C.POINTER(C.c_void_p)]
@@ -176,15 +178,16 @@ def check(code, handle=None):
     return code
 
 
-def make_schedule(T, dt, event_times=()):
-    """Host-only replay of the reference time loop (no GPU needed)."""
+def make_schedule(T, dt, event_times=(), forward=False):
+    """Host-only replay of the reference time loop (no GPU needed); forward: ForwardConstantStepper."""
     ev = np.ascontiguousarray(event_times, dtype=np.float64)
     evp = ev.ctypes.data_as(_dp) if len(ev) else None
-    n = lib().qpde_make_schedule(T, dt, evp, len(ev), None, 0)
+    fn = lib().qpde_make_schedule_forward if forward else lib().qpde_make_schedule
+    n = fn(T, dt, evp, len(ev), None, 0)
     if n < 0:
         raise QpdeError(n, "qpde_make_schedule")
     buf = (Step * n)()
-    lib().qpde_make_schedule(T, dt, evp, len(ev), buf, n)
+    fn(T, dt, evp, len(ev), buf, n)
     return buf
 
 
@@ -348,7 +351,7 @@ class BatchSpec:
                  n_exercise=0, exercise="k_minus_s", spot=None, tolerance=1e-6, scale=1.0,
                  penalty_tolerance=1e-6, max_inner=100, kernel="auto", outputs=OUT_ALL,
                  n_contracts=None, controls=None, policy_max=False, jump=None, dividend=None,
-                 variable_target=None, variable_scale=1.0, max_steps=0):
+                 variable_target=None, variable_scale=1.0, max_steps=0, forward=False):
         axis = np.ascontiguousarray(axis, dtype=np.float64)
         if n_contracts is None:
             n_contracts = axis.shape[0] if axis.ndim == 2 else len(np.atleast_1d(strike))
@@ -378,6 +381,7 @@ class BatchSpec:
 
         b.r, b.sigma, b.q = vec(r), vec(sigma), vec(q)
         b.vol_model = VOL[vol_model]
+        b.forward = int(bool(forward))
         if sigma_nodes is not None:
             b.sigma_nodes, b.sigma_nodes_stride = rows(sigma_nodes)
         b.T, b.dt = vec(T), vec(dt)

@@ -303,6 +303,42 @@ int qpde_make_schedule(double T, double dt, const double *event_times,
 	return n;
 }
 
+int qpde_make_schedule_forward(double T, double dt, const double *event_times,
+		int n_events, qpde_step *out, int max_steps) {
+	// qpde::Replay::next_forward with an explicit, ascending event list
+	if(!(T > 0.) || !(dt > 0.) || n_events < 0) return QPDE_ERR_INVALID;
+	std::vector<double> ev(event_times, event_times + n_events);
+	std::sort(ev.begin(), ev.end());
+	int n = 0;
+	size_t e = 0;
+	double t = 0., step = -1., prev;
+	do {
+		const double nextEventTime = (e < ev.size() && ev[e] <= T) ? ev[e] : T;
+		do {
+			prev = step;
+			step = dt;
+			double tmp = t + 1. * step;
+			if(fabs(tmp - nextEventTime) < DBL_EPSILON) {
+				tmp = nextEventTime;
+			} else if(tmp > nextEventTime) {
+				tmp = nextEventTime;
+				step = 1. * (nextEventTime - t);
+			}
+			t = tmp;
+			if(out && n < max_steps) {
+				out[n].t = t; out[n].dt = step; out[n].same_dt = step == prev;
+				out[n].event_after = 0; out[n].user_events = 0; out[n].reserved = 0;
+			}
+			++n;
+		} while(nextEventTime > t + 1. * DBL_EPSILON);
+		t = nextEventTime;
+		int users = 0;
+		while(e < ev.size() && ev[e] == t) { ++e; ++users; }
+		if(out && n - 1 < max_steps) { out[n - 1].event_after = 1; out[n - 1].user_events = users; }
+	} while(T > t);
+	return n;
+}
+
 int qpde_refined_size(int n_axis, int refine) {
 	if(n_axis < 1 || refine < 0 || refine > 20) return QPDE_ERR_INVALID;
 	if(n_axis < 2) return n_axis;
@@ -392,6 +428,8 @@ static int plan_create_impl(qpde_handle *h, const qpde_bs1d_batch *in,
 		if(in->n_exercise > 0 || in->jump_lambda) return fail(h, QPDE_ERR_UNSUPPORTED, "variable time steps with events or a jump term are not supported");
 		for(int c = 0; c < C; ++c) if(!(in->variable_target[c] > 0.)) return fail(h, QPDE_ERR_INVALID, "contract %d: variable_target must be > 0", c);
 	}
+	if(in->forward != 0 && in->forward != 1) return fail(h, QPDE_ERR_INVALID, "forward must be 0 or 1");
+	if(in->forward && in->variable_target) return fail(h, QPDE_ERR_UNSUPPORTED, "forward time with variable time steps is not supported");
 	if(in->n_exercise < 0) return fail(h, QPDE_ERR_INVALID, "n_exercise < 0");
 	if(in->n_exercise > 0 && in->exercise_kind != QPDE_EXERCISE_NONE && !is_generator(in->exercise_kind)) {
 		return fail(h, QPDE_ERR_INVALID, "exercise_kind must be a generator or QPDE_EXERCISE_NONE");
@@ -429,6 +467,7 @@ static int plan_create_impl(qpde_handle *h, const qpde_bs1d_batch *in,
 	const int N = b.N;
 	b.vol_model = in->vol_model;
 	b.scheme = in->scheme;
+	b.forward = in->forward ? 1 : 0;
 	b.n_exercise = in->n_exercise; b.exercise_kind = in->exercise_kind;
 	b.dividend_kind = in->dividend_kind; b.dividend_first = in->dividend_first ? 1 : 0;
 	b.payoff_kind = in->payoff_kind;

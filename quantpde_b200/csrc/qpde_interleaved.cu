@@ -85,9 +85,10 @@ __global__ void k_interleaved_setup(DeviceBatch b, InterleavedWork w) {
 struct BdfHigh { double c[6]; double hh; };
 
 __device__ __noinline__ BdfHigh bdf_high_setup(int k, double t, double time1, double time0,
-		double th0, double th1, double th2, double th3) {
+		double th0, double th1, double th2, double th3, int forward) {
 	BdfHigh f;
 	double g[6] = { time1 - t, time0 - t, th0 - t, th1 - t, th2 - t, th3 - t };
+	if(forward) for(int m = 0; m < 6; ++m) g[m] = 0. - g[m];      // t - time(m): exact negation
 	for(int m = 0; m < 6; ++m) f.c[m] = 0.;
 	bdf_coefficients(k, g, f.c, &f.hh);
 	return f;
@@ -128,9 +129,9 @@ k_interleaved_sweep(DeviceBatch b, InterleavedWork w, DeviceResult out) {
 	const bool policy = b.n_controls > 0;
 	const bool iterate = b.american || policy;   // a ToleranceIteration wraps every step
 	const size_t NC = (size_t)N * (size_t)w.ld;               // one array (one set of operator rows)
-	Replay rp; rp.start(b.T[c], b.dt[c], b.n_exercise);
+	Replay rp; rp.start(b.T[c], b.dt[c], b.n_exercise, b.forward);
 	NodeState ns; ns.start(b.scheme);
-	double time1 = rp.T, time0 = rp.T; // times of iterand(0), iterand(1)
+	double time1 = rp.initial(), time0 = rp.initial(); // times of iterand(0), iterand(1)
 	Gamma gA; gA.kind = STEP_IMPLICIT; gA.h = 0.; // what the factorised A was built with
 	int n_steps = 0, inner_total = 0, status = 0;
 	bool more = true;
@@ -139,7 +140,7 @@ k_interleaved_sweep(DeviceBatch b, InterleavedWork w, DeviceResult out) {
 	const int order = bdf_order(b.scheme);
 	const int slots = order > 2 ? order - 1 : 1;
 	int head = 0;
-	double th0 = rp.T, th1 = rp.T, th2 = rp.T, th3 = rp.T;
+	double th0 = rp.initial(), th1 = rp.initial(), th2 = rp.initial(), th3 = rp.initial();
 
 	// ReverseVariableStepper (Core/Stepper.hpp:60-126)
 	const bool variable = b.variable_target != nullptr;
@@ -155,18 +156,18 @@ k_interleaved_sweep(DeviceBatch b, InterleavedWork w, DeviceResult out) {
 		more = rp.next(st);
 		const double t = st.t;
 		const int kind = ns.kind();
-		const double h0 = time1 - t;
+		const double h0 = rp.lapse(time1, t);
 		Gamma gb; gb.kind = kind; gb.h = h0;
 		double c1 = 0., c0 = 0., den = 1.;
 		if(kind == STEP_BDF2) {
-			const double h1 = time1 - t, hh0 = time0 - t;     // BDF.hpp:68-73
+			const double h1 = rp.lapse(time1, t), hh0 = rp.lapse(time0, t);     // BDF.hpp:68-73
 			gb.h = (hh0 * h1) / (hh0 + h1);
 			c1 = hh0 / h1; c0 = h1 / hh0; den = hh0 - h1;
 		}
 		const double rden = 1. / den;
 		if(kind >= STEP_BDF3) {
 			// BDF.hpp:139-470: A = I + hh op.A; the right-hand side goes to lb here
-			const BdfHigh f = bdf_high_setup(kind - STEP_BDF3 + 3, t, time1, time0, th0, th1, th2, th3);
+			const BdfHigh f = bdf_high_setup(kind - STEP_BDF3 + 3, t, time1, time0, th0, th1, th2, th3, b.forward);
 			gb.h = f.hh;
 			bdf_high_rhs(kind - STEP_BDF3 + 3, f, N, NC, x, xp, head, slots, lb);
 		}

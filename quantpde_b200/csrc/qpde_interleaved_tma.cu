@@ -159,9 +159,9 @@ k_interleaved_sweep_tma(const __grid_constant__ TmaMaps maps, DeviceBatch b, Int
 	const int nb = (N + TR - 1) / TR;            // tiles per pass
 	const int lead = nb < stages ? nb : stages;
 
-	Replay rp; rp.start(b.T[cc], b.dt[cc], b.n_exercise);
+	Replay rp; rp.start(b.T[cc], b.dt[cc], b.n_exercise, b.forward);
 	NodeState ns; ns.start(b.scheme);
-	double time1 = rp.T, time0 = rp.T; // times of iterand(0), iterand(1)
+	double time1 = rp.initial(), time0 = rp.initial(); // times of iterand(0), iterand(1)
 	Gamma gA; gA.kind = STEP_IMPLICIT; gA.h = 0.; // what the factorised A was built with
 	int n_steps = 0, inner_total = 0, computed = 0, status = 0;
 	bool more = valid;
@@ -185,10 +185,10 @@ k_interleaved_sweep_tma(const __grid_constant__ TmaMaps maps, DeviceBatch b, Int
 			more = rp.next(st);
 			t = st.t;
 			kind = ns.kind();
-			h0 = time1 - t;
+			h0 = rp.lapse(time1, t);
 			gb.kind = kind; gb.h = h0;
 			if(kind == STEP_BDF2) {
-				const double h1 = time1 - t, hh0 = time0 - t;     // BDF.hpp:68-73
+				const double h1 = rp.lapse(time1, t), hh0 = rp.lapse(time0, t);     // BDF.hpp:68-73
 				gb.h = (hh0 * h1) / (hh0 + h1);
 				c1 = hh0 / h1; c0 = h1 / hh0; den = hh0 - h1;
 			}

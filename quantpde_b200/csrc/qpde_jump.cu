@@ -324,9 +324,9 @@ k_jump_sweep(DeviceBatch b, JumpWork work, DeviceResult out) {
 	x_next = 0.;
 	__syncthreads();
 
-	Replay rp; rp.start(b.T[cidx], b.dt[cidx], 0);
+	Replay rp; rp.start(b.T[cidx], b.dt[cidx], 0, b.forward);
 	NodeState ns; ns.start(b.scheme);
-	double time1 = rp.T, time0 = rp.T;
+	double time1 = rp.initial(), time0 = rp.initial();
 	int cur_kind = -1; double cur_h = 0.;
 	int n_steps = 0;
 	bool more = true;
@@ -336,11 +336,11 @@ k_jump_sweep(DeviceBatch b, JumpWork work, DeviceResult out) {
 		more = rp.next(st);
 		const double t = st.t;
 		const int kind = ns.kind();
-		const double h0 = time1 - t;
+		const double h0 = rp.lapse(time1, t);
 		Gamma g; g.kind = kind; g.h = h0;
 		double c1 = 0., c0 = 0., den = 1.;
 		if(BDF2 && kind == STEP_BDF2) {
-			const double h1 = time1 - t, hh0 = time0 - t;
+			const double h1 = rp.lapse(time1, t), hh0 = rp.lapse(time0, t);
 			g.h = (hh0 * h1) / (hh0 + h1);
 			c1 = hh0 / h1; c0 = h1 / hh0; den = hh0 - h1;
 		}

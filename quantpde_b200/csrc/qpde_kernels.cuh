@@ -21,6 +21,7 @@ struct DeviceBatch {
 	const double *sigma_nodes; long long sigma_nodes_stride;
 	const double *T, *dt;
 	int scheme, max_steps;
+	int forward;           // 1: forward-time classes (time runs from 0 to T)
 	const double *variable_target; double variable_scale;
 	int n_exercise, exercise_kind;
 	int dividend_kind, dividend_first;

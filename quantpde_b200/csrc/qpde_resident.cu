@@ -311,14 +311,14 @@ k_resident_sweep(DeviceBatch b, DeviceResult out) {
 	// ------------------------------------------------------------------
 	// Time loop
 	// ------------------------------------------------------------------
-	Replay rp; rp.start(b.T[cidx], b.dt[cidx], b.n_exercise);
+	Replay rp; rp.start(b.T[cidx], b.dt[cidx], b.n_exercise, b.forward);
 	NodeState ns; ns.start(b.scheme);
 	// ReverseVariableStepper (Core/Stepper.hpp:60-126): dt of the next step from the
 	// relative change over the last one
 	constexpr bool variable = VARIABLE;
 	const double vtarget = variable ? b.variable_target[cidx] : 0.;
 	double vdt = b.dt[cidx];
-	double time1 = rp.T, time0 = rp.T;
+	double time1 = rp.initial(), time0 = rp.initial();
 	int cur_kind = -1; double cur_h = 0.;
 	int n_steps = 0, inner_total = 0, computed = 0, status = 0;
 	bool more = true;
@@ -334,11 +334,11 @@ k_resident_sweep(DeviceBatch b, DeviceResult out) {
 		more = rp.next(st);
 		const double t = st.t;
 		const int kind = ns.kind();
-		const double h0 = time1 - t;
+		const double h0 = rp.lapse(time1, t);
 		Gamma g; g.kind = kind; g.h = h0;
 		double c1 = 0., c0 = 0., den = 1.;
 		if(BDF2 && kind == STEP_BDF2) {
-			const double h1 = time1 - t, hh0 = time0 - t;      // BDF.hpp:68-73
+			const double h1 = rp.lapse(time1, t), hh0 = rp.lapse(time0, t);      // BDF.hpp:68-73
 			g.h = (hh0 * h1) / (hh0 + h1);
 			c1 = hh0 / h1; c0 = h1 / hh0; den = hh0 - h1;
 		}

@@ -9,7 +9,7 @@
 //   Core/Axis.hpp:98,205-257,270-358,445-459  Axis         Axis  {ticks, special, uniform, range, *, +}
 //   Core/Domain.hpp:1092-1172   RectilinearGrid1           RectilinearGrid1 (+ refined(k))
 //   Modules/Operators/BlackScholes.hpp:114-134             BlackScholes1(grid, r, v, q)
-//   Core/Stepper.hpp:27-36      ReverseConstantStepper     ReverseConstantStepper(t0, T, dt)
+//   Core/Stepper.hpp:27-41      Reverse/ForwardConstantStepper   ReverseConstantStepper(t0, T, dt), ForwardConstantStepper
 //   Core/IterativeMethod.hpp:1243 ToleranceIteration       ToleranceIteration(tolerance, scale)
 //   Core/Rannacher.hpp:123  CrankNicolson.hpp:97  BDF.hpp:496,570
 //                                                          ReverseRannacher / ReverseCrankNicolson /
@@ -314,10 +314,11 @@ public:
 	const BlackScholes1 &op;
 	const PolicyIteration1_1 *policy;   // non-null when the operator is wrapped in a policy iteration
 	int scheme;
-	Discretization(const RectilinearGrid1 &g, const BlackScholes1 &o, int s)
-			: grid(g), op(o), policy(nullptr), scheme(s) {}
-	Discretization(const RectilinearGrid1 &g, const PolicyIteration1_1 &p, int s)
-			: grid(g), op(p.system), policy(&p), scheme(s) {}
+	bool forward;                       // a Forward* class: goes with a ForwardConstantStepper
+	Discretization(const RectilinearGrid1 &g, const BlackScholes1 &o, int s, bool forward = false)
+			: grid(g), op(o), policy(nullptr), scheme(s), forward(forward) {}
+	Discretization(const RectilinearGrid1 &g, const PolicyIteration1_1 &p, int s, bool forward = false)
+			: grid(g), op(p.system), policy(&p), scheme(s), forward(forward) {}
 };
 struct ReverseRannacher : Discretization {
 	ReverseRannacher(const RectilinearGrid1 &g, const BlackScholes1 &o) : Discretization(g, o, QPDE_SCHEME_RANNACHER) {}
@@ -347,6 +348,24 @@ QPDE_B200_BDF_CLASS(ReverseBDFFour,  QPDE_SCHEME_BDF4)
 QPDE_B200_BDF_CLASS(ReverseBDFFive,  QPDE_SCHEME_BDF5)
 QPDE_B200_BDF_CLASS(ReverseBDFSix,   QPDE_SCHEME_BDF6)
 #undef QPDE_B200_BDF_CLASS
+// The forward-time classes (Rannacher<true>, CrankNicolson<true>, BDFOne<true> .. BDFSix<true>:
+// Core/Rannacher.hpp:140, CrankNicolson.hpp:110, BDF.hpp:512-942): same formulas with
+// h = t_new - t_old; they go with a ForwardConstantStepper.
+#define QPDE_B200_FORWARD_CLASS(NAME, SCHEME) \
+struct NAME : Discretization { \
+	NAME(const RectilinearGrid1 &g, const BlackScholes1 &o) : Discretization(g, o, SCHEME, true) {} \
+	NAME(const RectilinearGrid1 &g, const PolicyIteration1_1 &p) : Discretization(g, p, SCHEME, true) {} \
+};
+QPDE_B200_FORWARD_CLASS(ForwardRannacher,     QPDE_SCHEME_RANNACHER)
+QPDE_B200_FORWARD_CLASS(ForwardCrankNicolson, QPDE_SCHEME_CN)
+QPDE_B200_FORWARD_CLASS(ForwardBDFOne,        QPDE_SCHEME_BDF1)
+QPDE_B200_FORWARD_CLASS(ForwardBDFTwo,        QPDE_SCHEME_BDF2)
+QPDE_B200_FORWARD_CLASS(ForwardBDFThree,      QPDE_SCHEME_BDF3)
+QPDE_B200_FORWARD_CLASS(ForwardBDFFour,       QPDE_SCHEME_BDF4)
+QPDE_B200_FORWARD_CLASS(ForwardBDFFive,       QPDE_SCHEME_BDF5)
+QPDE_B200_FORWARD_CLASS(ForwardBDFSix,        QPDE_SCHEME_BDF6)
+#undef QPDE_B200_FORWARD_CLASS
+typedef ForwardBDFOne ForwardImplicitEuler;
 
 // MinPenaltyMethodDifference1(grid, constraintNode, payoff, tolerance) —
 // Core/PenaltyMethod.hpp:281-301
@@ -438,10 +457,11 @@ class ReverseConstantStepper : public Iteration {
 protected:
 	Real vTarget, vScale;      // > 0: ReverseVariableStepper
 	int stepLimit_;
+	bool forward_;             // ForwardConstantStepper
 public:
 	ReverseConstantStepper(Real startTime, Real endTime, Real dt)
 			: t0(startTime), T(endTime), dt(dt), inner(nullptr), nExercise(0), nDividend(0),
-			  dividendAddedFirst(false), vTarget(0.), vScale(1.), stepLimit_(0) {
+			  dividendAddedFirst(false), vTarget(0.), vScale(1.), stepLimit_(0), forward_(false) {
 		if(startTime != 0.) throw std::invalid_argument("QuantPDE_B200: startTime must be 0");
 	}
 	void setInnerIteration(ToleranceIteration &it) { inner = &it; }   // IterativeMethod.hpp:977
@@ -469,14 +489,29 @@ public:
 	int eventDates() const { return nExercise > 0 ? nExercise : nDividend; }
 	const Dividend &dividend() const { return dividend_; }
 	bool hasDividends() const { return nDividend > 0 && dividend_.kind != QPDE_DIVIDEND_NONE; }
-	// the dividend transform goes first in the reverse sweep iff its events were add()ed last
-	bool dividendFirstInSweep() const { return hasDividends() && nExercise > 0 && !dividendAddedFirst; }
+	// the dividend transform goes first in the reverse sweep iff its events were add()ed last; a forward
+	// sweep applies events at one time in ascending add() order (TimeOrder, IterativeMethod.hpp:1340-1352)
+	bool dividendFirstInSweep() const {
+		return hasDividends() && nExercise > 0 && (forward_ ? dividendAddedFirst : !dividendAddedFirst);
+	}
+	bool isForward() const { return forward_; }
 	ToleranceIteration *innerIteration() const { return inner; }
 
 	// Iteration::solve(domain, initialCondition, root, solver) — IterativeMethod.hpp:1065-1079
 	inline Solution solve(const RectilinearGrid1 &grid, const Payoff &payoff, IterationNode &root,
 			B200Solver &solver);
 	friend class Batch;
+};
+
+// ForwardConstantStepper(t0, T, dt) — Core/Stepper.hpp:41 (TimeIteration<true>,
+// IterativeMethod.hpp:1494-1495): time runs from 0 up to T, solve() takes the condition at t = 0;
+// addExerciseDates / addDividendDates(E, ...) place their events at T e / E for e = 1 .. E (an
+// event may not sit at the initial time).  Goes with the Forward* discretisations.
+class ForwardConstantStepper : public ReverseConstantStepper {
+public:
+	ForwardConstantStepper(Real startTime, Real endTime, Real dt) : ReverseConstantStepper(startTime, endTime, dt) {
+		forward_ = true;
+	}
 };
 
 // ReverseVariableStepper(t0, T, dt, target, scale) — Core/Stepper.hpp:60-126: dt is the first
@@ -554,8 +589,13 @@ public:
 			const Item &it = items[c];
 			const Discretization *d; MinPenaltyMethodDifference1 *p;
 			decode(it.root, d, p);
+			if(d->forward != it.stepper->isForward()) {
+				throw std::invalid_argument("QuantPDE_B200: a Forward* discretisation goes with a ForwardConstantStepper "
+					"(and a Reverse* one with a ReverseConstantStepper)");
+			}
 			if(it.grid->size() != N || it.grid->coarse().size() != nAxis || it.grid->refinement() != refine
 					|| d->scheme != d0->scheme || (p != nullptr) != american
+					|| it.stepper->isForward() != items[0].stepper->isForward()
 					|| it.stepper->exerciseDates() != nEx || it.stepper->eventDates() != nEv
 					|| it.stepper->hasDividends() != dividends
 					|| (it.stepper->variableTarget() > 0.) != variableSteps
@@ -636,6 +676,7 @@ public:
 		b.vol_model = volModel;
 		if(volModel == QPDE_VOL_NODES) { b.sigma_nodes = sigArr.data(); b.sigma_nodes_stride = N; }
 		b.T = T.data(); b.dt = dt.data(); b.scheme = d0->scheme; b.max_steps = 0;
+		b.forward = items[0].stepper->isForward() ? 1 : 0;
 		b.n_exercise = nEv;
 		b.exercise_kind = nEx > 0 ? items[0].stepper->exercisePayoff().kind() : QPDE_EXERCISE_NONE;
 		if(dividends) { b.dividend_kind = divKind; b.dividend_first = divFirst ? 1 : 0; b.dividend = divAmount.data(); }

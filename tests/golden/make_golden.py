@@ -148,6 +148,24 @@ CASES.append(("american_exercise_dividend_bdf1_k2", "vanilla",
 CASES.append(("american_dividend_cash_rannacher_k6", "vanilla",
               dict(american=1, steps=200, refine=6, K=100.0, r=0.04, vol=0.2, T=1.0, E=4,
                    dividend=1.0, dividend_kind="cash", dividend_first=0)))
+# forward-time classes (TimeIteration<true>, ForwardConstantStepper, ForwardRannacher / CrankNicolson /
+# BDFk: IterativeMethod.hpp:1494-1495, Stepper.hpp:41): no example of the reference uses them, so these
+# run the classes themselves (qpde_ref forward) — European and American, every scheme family, events
+for name, kw in (
+        ("forward_european_rannacher_k2", dict(steps=50, refine=2, american=0, scheme="rannacher")),
+        ("forward_european_cn_k2", dict(steps=50, refine=2, american=0, scheme="cn", call=1)),
+        ("forward_european_bdf2_k2", dict(steps=50, refine=2, american=0, scheme="bdf2")),
+        ("forward_european_bdf4_events_k2", dict(steps=50, refine=2, american=0, scheme="bdf4", E=3, exercise=1)),
+        ("forward_american_rannacher_k3", dict(steps=100, refine=3, american=1, scheme="rannacher")),
+        ("forward_american_bdf1_k1", dict(steps=37, refine=1, american=1, scheme="bdf1", T=0.7, K=93.0, vol=0.35, r=0.02)),
+        ("forward_american_cn_dividend_k2", dict(steps=64, refine=2, american=1, scheme="cn", E=4, dividend=1.0,
+                                                 dividend_kind="cash")),
+        ("forward_localvol_events_k2", dict(steps=64, refine=2, american=0, scheme="rannacher", alpha=20.0, E=5,
+                                            dividend=0.02, dividend_kind="proportional", dividend_first=1, exercise=1)),
+        ("forward_american_rannacher_k6", dict(steps=200, refine=6, american=1, scheme="rannacher"))):
+    base = dict(K=100.0, r=0.04, vol=0.2, T=1.0)
+    base.update(kw)
+    CASES.append((name, "forward", base))
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "reference_cases.npz")
 # cases already in the file with the same arguments are kept (pass --all to re-run everything)
 have = np.load(GOLDEN, allow_pickle=False) if os.path.exists(GOLDEN) and "--all" not in sys.argv else None

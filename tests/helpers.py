@@ -51,6 +51,11 @@ def run_oracle_case(po, mode, kw):
                                variable_target=kw.get("variable_target"), E=kw.get("E", 0),
                                dividend=kw.get("dividend"), dividend_kind=kw.get("dividend_kind", "cash"),
                                dividend_first=bool(kw.get("dividend_first", 0)), exercise=bool(kw.get("exercise", 0)))
+    if mode == "forward":
+        return po.forward_option(kw["K"], kw["r"], kw["vol"], kw["T"], kw["steps"], kw["refine"], call=bool(kw.get("call", 0)),
+                                 american=bool(kw["american"]), scheme=kw["scheme"], alpha=kw.get("alpha", 0.0),
+                                 E=kw.get("E", 0), dividend=kw.get("dividend"), dividend_kind=kw.get("dividend_kind", "cash"),
+                                 dividend_first=bool(kw.get("dividend_first", 0)), exercise=bool(kw.get("exercise", 0)))
     if mode == "jump":
         return po.jump_call(kw["K"], kw["r"], kw["vol"], kw["T"], kw["lambda"], kw["steps"], kw["refine"],
                             density=kw["density"], params=jump_params(kw), scheme=kw.get("scheme", "bdf1"))
@@ -75,6 +80,18 @@ def spec_for_case(qpde, po, mode, kw, kernel="auto", copies=1):
             scheme=kw.get("scheme", "rannacher"), american=bool(kw["american"]),
             payoff="call" if call else "put", kernel=kernel,
             variable_target=kw.get("variable_target"), max_steps=4000 if "variable_target" in kw else 0,
+            n_exercise=kw.get("E", 0), exercise="k_minus_s" if kw.get("exercise", 0) else "none",
+            dividend=None if "dividend" not in kw else dict(kind=kw["dividend_kind"], amount=kw["dividend"],
+                                                          first=bool(kw.get("dividend_first", 0))))
+    if mode == "forward":
+        K = kw["K"]
+        axis = po.axis_union(po.special_axis() * K, po.special_axis() * K)
+        local = kw.get("alpha", 0.0) > 0
+        return qpde.BatchSpec(
+            axis=np.tile(axis, (copies, 1)), refine=kw["refine"], r=kw["r"], sigma=kw["alpha"] if local else kw["vol"],
+            vol_model="inverse_s" if local else "const", q=0.0, T=kw["T"], dt=kw["T"] / kw["steps"],
+            strike=np.full(copies, K), scheme=kw["scheme"], american=bool(kw["american"]),
+            payoff="call" if kw.get("call", 0) else "put", kernel=kernel, forward=True,
             n_exercise=kw.get("E", 0), exercise="k_minus_s" if kw.get("exercise", 0) else "none",
             dividend=None if "dividend" not in kw else dict(kind=kw["dividend_kind"], amount=kw["dividend"],
                                                           first=bool(kw.get("dividend_first", 0))))

@@ -65,6 +65,23 @@ def test_schedule_helper_matches_oracle(qpde, oracle):
                    (b.t, b.dt, b.same_dt, b.event_after, b.user_events)
 
 
+def test_forward_schedule_helper_matches_oracle(qpde, oracle):
+    """ForwardConstantStepper's loop (TimeIteration<true>): time runs up from 0, smallest event first,
+    the terminal NullEvent at T; the oracle's replay is pinned bit for bit by the forward_* fixtures."""
+    cases = [(1.0, 1.0 / 12, ()), (0.7316, 0.7316 / 1000, ()), (2.0, 0.013, ()),
+             (1.0, 0.01, tuple(1.0 / 10 * e for e in range(1, 11))),
+             (1.3, 1.3 / 77, (0.4, 0.4, 1.1, 1.3)), (0.9, 0.9 / 64, tuple(0.9 / 7 * e for e in range(1, 8)))]
+    for T, dt, ev in cases:
+        mine = qpde.make_schedule(T, dt, ev, forward=True)
+        theirs, n = oracle.schedule(T, dt, ev, forward=True)
+        assert len(mine) == n
+        for i in range(n):
+            a, b = mine[i], theirs[i]
+            assert (a.t, a.dt, a.same_dt, a.event_after, a.user_events) == \
+                   (b.t, b.dt, b.same_dt, b.event_after, b.user_events)
+        assert mine[n - 1].t == T and mine[n - 1].event_after == 1
+
+
 def test_jump_setup_matches_oracle(qpde, oracle):
     """qpde_jump_setup (product host code) vs the oracle's restatement of the
     reference's construction-time quadrature: bit-identical x0, dx, kappa, weights."""
