@@ -379,7 +379,24 @@ int qpde_gmwb2d_nodes(const qpde_gmwb2d *problem, int *nodes_w, int *nodes_a);
 int qpde_gmwb2d_solve(qpde_handle *h, const qpde_gmwb2d *problem, double *V,
 		double *W_out, double *A_out, qpde_gmwb2d_stats *stats);
 
-/* ---- GMWB sharded by the A-axis (one shard per rank / GPU) ------------------ */
+/* ---- GMWB sharded by the A-axis over the GPUs of a node: the library's own driver --------
+ * One process per GPU.  A handle gets a communicator (NCCL over NVLink /
+ * NVSwitch, loaded at run time): rank 0 makes an id with qpde_comm_unique_id, the caller ships the
+ * 128 bytes to the other ranks by whatever it has (MPI, torch.distributed, a file), every rank calls
+ * qpde_comm_init on its own handle.  qpde_gmwb2d_solve_sharded is then a COLLECTIVE call with the
+ * arguments of qpde_gmwb2d_solve: the control search (HJBQVI.hpp:590-754 — the impulse arg-max over
+ * every node) is cut along the A-axis over the ranks, the assembled rows of each block reach all
+ * ranks by NCCL broadcasts on the library's streams (the all-gather in front of the impulse step),
+ * and every rank returns the full V, bit-identical to the single-GPU solve.  No host round trip
+ * besides the stopping flag; DESIGN.md §5. */
+#define QPDE_COMM_ID_BYTES 128
+int qpde_comm_unique_id(unsigned char id[QPDE_COMM_ID_BYTES]);
+int qpde_comm_init(qpde_handle *h, const unsigned char id[QPDE_COMM_ID_BYTES], int rank, int world);
+int qpde_comm_destroy(qpde_handle *h);
+int qpde_gmwb2d_solve_sharded(qpde_handle *h, const qpde_gmwb2d *problem, double *V,
+		double *W_out, double *A_out, qpde_gmwb2d_stats *stats);
+
+/* ---- GMWB sharded by the A-axis, piecewise (one shard per rank / GPU; the caller drives) ---- */
 /* The pieces of one inner iteration restricted to the refined A-lines
  * [a_begin, a_end) a rank owns.  x, v0, xprev are DEVICE pointers to full-grid
  * vectors [nodes_a][nodes_w] replicated on every rank (e.g. torch tensors); the

@@ -108,7 +108,8 @@ EXPORTS = [
     "qpde_bs1d_plan_create", "qpde_bs1d_plan_run", "qpde_bs1d_plan_fetch",
     "qpde_bs1d_plan_destroy", "qpde_bs1d_plan_kernel", "qpde_bs1d_plan_nodes", "qpde_bs1d_plan_tma_staged",
     "qpde_bs1d_plan_max_steps", "qpde_jump_nfft", "qpde_jump_setup", "qpde_refine_axis",
-    "qpde_gmwb2d_nodes", "qpde_gmwb2d_solve", "qpde_gmwb2d_shard_create", "qpde_gmwb2d_shard_destroy",
+    "qpde_gmwb2d_nodes", "qpde_gmwb2d_solve", "qpde_gmwb2d_solve_sharded", "qpde_comm_unique_id", "qpde_comm_init",
+    "qpde_comm_destroy", "qpde_gmwb2d_shard_create", "qpde_gmwb2d_shard_destroy",
     "qpde_gmwb2d_shard_exit", "qpde_gmwb2d_shard_policy", "qpde_gmwb2d_shard_sweep", "qpde_gmwb2d_shard_relerr",
 ]
 
@@ -161,6 +162,10 @@ def lib():
         L.qpde_refine_axis.argtypes = [_dp, C.c_int, C.c_int, _dp]
         L.qpde_gmwb2d_nodes.argtypes = [C.POINTER(Gmwb2d), C.POINTER(C.c_int), C.POINTER(C.c_int)]
         L.qpde_gmwb2d_solve.argtypes = [C.c_void_p, C.POINTER(Gmwb2d), _dp, _dp, _dp, C.POINTER(Gmwb2dStats)]
+        L.qpde_gmwb2d_solve_sharded.argtypes = [C.c_void_p, C.POINTER(Gmwb2d), _dp, _dp, _dp, C.POINTER(Gmwb2dStats)]
+        L.qpde_comm_unique_id.argtypes = [C.c_char_p]
+        L.qpde_comm_init.argtypes = [C.c_void_p, C.c_char_p, C.c_int, C.c_int]
+        L.qpde_comm_destroy.argtypes = [C.c_void_p]
         L.qpde_gmwb2d_shard_create.argtypes = [C.c_void_p, C.POINTER(Gmwb2d), C.c_int, C.c_int, C.POINTER(C.c_void_p)]
         L.qpde_gmwb2d_shard_destroy.argtypes = [C.c_void_p]
         L.qpde_gmwb2d_shard_exit.argtypes = [C.c_void_p, C.c_void_p]
@@ -252,6 +257,15 @@ class Handle:
     def sm_count(self):
         return lib().qpde_sm_count(self.ptr)
 
+    def comm_init(self, comm_id, rank, world):
+        """qpde_comm_init: joins the NCCL communicator identified by the 128 bytes rank 0 made with
+        comm_unique_id() (shipped by the caller).  Collective over the `world` ranks."""
+        assert len(comm_id) == COMM_ID_BYTES
+        check(lib().qpde_comm_init(self.ptr, bytes(comm_id), int(rank), int(world)), self.ptr)
+
+    def comm_destroy(self):
+        lib().qpde_comm_destroy(self.ptr)
+
     def fp64_peak_tflops(self):
         """Measured FP64 rate of the device (qpde_measure_fp64_peak)."""
         v = C.c_double()
@@ -317,9 +331,21 @@ class GmwbShard:
             self.ptr = C.c_void_p()
 
 
+COMM_ID_BYTES = 128
+
+
+def comm_unique_id():
+    """qpde_comm_unique_id: the 128 bytes that identify a new communicator (rank 0 makes them)."""
+    buf = C.create_string_buffer(COMM_ID_BYTES)
+    check(lib().qpde_comm_unique_id(buf))
+    return buf.raw
+
+
 def gmwb_solve(handle, w_axis, a_axis, controls, impulse_axis, refine, timesteps, T=10., r=.05, eta=0.,
-               sigma=.2, kappa=.1, c=0., scaling_factor=1e-2, tolerance=1e-6, max_inner=200, max_sweeps=500):
-    """qpde_gmwb2d_solve: the 2-D GMWB HJBQVI (host arrays in, host arrays out)."""
+               sigma=.2, kappa=.1, c=0., scaling_factor=1e-2, tolerance=1e-6, max_inner=200, max_sweeps=500,
+               sharded=False):
+    """qpde_gmwb2d_solve: the 2-D GMWB HJBQVI (host arrays in, host arrays out).  sharded=True:
+    qpde_gmwb2d_solve_sharded, a collective call over the ranks of the handle's communicator."""
     keep = [np.ascontiguousarray(a, dtype=np.float64) for a in (w_axis, a_axis, controls, impulse_axis)]
     g = Gmwb2d()
     g.abi_version, g.refine = ABI_VERSION, int(refine)
@@ -336,8 +362,9 @@ def gmwb_solve(handle, w_axis, a_axis, controls, impulse_axis, refine, timesteps
     inner = np.zeros(int(timesteps) + 8, dtype=np.int32)
     st = Gmwb2dStats()
     st.inner = inner.ctypes.data_as(C.POINTER(C.c_int32)); st.inner_capacity = len(inner)
-    check(lib().qpde_gmwb2d_solve(handle.ptr, C.byref(g), V.ctypes.data_as(_dp), W.ctypes.data_as(_dp),
-                                  A.ctypes.data_as(_dp), C.byref(st)), handle.ptr)
+    fn = lib().qpde_gmwb2d_solve_sharded if sharded else lib().qpde_gmwb2d_solve
+    check(fn(handle.ptr, C.byref(g), V.ctypes.data_as(_dp), W.ctypes.data_as(_dp), A.ctypes.data_as(_dp), C.byref(st)),
+          handle.ptr)
     return dict(V=V, W=W, A=A, n_steps=st.n_steps, mean_inner=st.mean_inner, status=st.status,
                 inner=inner[:st.n_steps].copy())
 

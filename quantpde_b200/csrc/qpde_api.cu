@@ -67,6 +67,7 @@ struct qpde_handle {
 	long long launches;
 	std::string error;
 	DevicePool pool;
+	Comm *comm = nullptr;       // qpde_comm_init: the ranks of a sharded GMWB solve
 };
 
 struct qpde_bs1d_plan {
@@ -227,6 +228,7 @@ int qpde_destroy(qpde_handle *h) {
 	cudaStreamSynchronize(h->stream);
 	cudaStreamSynchronize(h->copy_stream);
 	h->pool.release();
+	comm_destroy(h->comm);
 	cudaStreamDestroy(h->copy_stream);
 	cudaStreamDestroy(h->stream);
 	delete h;
@@ -762,8 +764,49 @@ int qpde_gmwb2d_nodes(const qpde_gmwb2d *g, int *nodes_w, int *nodes_a) {
 	return *nodes_w > 0 && *nodes_a > 0 ? QPDE_OK : QPDE_ERR_INVALID;
 }
 
+int qpde_comm_unique_id(unsigned char id[QPDE_COMM_ID_BYTES]) {
+	if(!id) return fail(nullptr, QPDE_ERR_INVALID, "qpde_comm_unique_id: NULL argument");
+	std::string error;
+	const int rc = comm_unique_id(id, &error);
+	return rc == QPDE_OK ? rc : fail(nullptr, rc, "%s", error.c_str());
+}
+
+int qpde_comm_init(qpde_handle *h, const unsigned char id[QPDE_COMM_ID_BYTES], int rank, int world) {
+	if(!h) return fail(nullptr, QPDE_ERR_INVALID, "qpde_comm_init: NULL handle");
+	if(!id || world < 1 || rank < 0 || rank >= world) return fail(h, QPDE_ERR_INVALID, "qpde_comm_init: bad rank / world");
+	if(h->comm) return fail(h, QPDE_ERR_INVALID, "qpde_comm_init: the handle already has a communicator");
+	QPDE_CUDA(h, cudaSetDevice(h->device));
+	std::string error;
+	const int rc = comm_create(id, rank, world, &h->comm, &error);
+	return rc == QPDE_OK ? rc : fail(h, rc, "%s", error.c_str());
+}
+
+int qpde_comm_destroy(qpde_handle *h) {
+	if(!h) return QPDE_OK;
+	cudaSetDevice(h->device);
+	cudaStreamSynchronize(h->stream);
+	comm_destroy(h->comm);
+	h->comm = nullptr;
+	return QPDE_OK;
+}
+
+static int gmwb_solve_impl(qpde_handle *h, const qpde_gmwb2d *g, double *V, double *W_out, double *A_out,
+		qpde_gmwb2d_stats *stats, Comm *comm);
+
+int qpde_gmwb2d_solve_sharded(qpde_handle *h, const qpde_gmwb2d *g, double *V, double *W_out, double *A_out,
+		qpde_gmwb2d_stats *stats) {
+	if(!h) return fail(nullptr, QPDE_ERR_INVALID, "qpde_gmwb2d_solve_sharded: NULL handle");
+	if(!h->comm) return fail(h, QPDE_ERR_INVALID, "qpde_gmwb2d_solve_sharded: the handle has no communicator (qpde_comm_init)");
+	return gmwb_solve_impl(h, g, V, W_out, A_out, stats, h->comm);
+}
+
 int qpde_gmwb2d_solve(qpde_handle *h, const qpde_gmwb2d *g, double *V, double *W_out, double *A_out,
 		qpde_gmwb2d_stats *stats) {
+	return gmwb_solve_impl(h, g, V, W_out, A_out, stats, nullptr);
+}
+
+static int gmwb_solve_impl(qpde_handle *h, const qpde_gmwb2d *g, double *V, double *W_out, double *A_out,
+		qpde_gmwb2d_stats *stats, Comm *comm) {
 	if(!h) return fail(nullptr, QPDE_ERR_INVALID, "qpde_gmwb2d_solve: NULL handle");
 	if(!g || !V) return fail(h, QPDE_ERR_INVALID, "qpde_gmwb2d_solve: NULL argument");
 	{ const int vrc = gmwb_validate(h, g); if(vrc != QPDE_OK) return vrc; }
@@ -776,7 +819,7 @@ int qpde_gmwb2d_solve(qpde_handle *h, const qpde_gmwb2d *g, double *V, double *W
 	qpde_refine_axis(g->impulse_axis, g->n_impulse_axis, g->refine, Z.data());
 	QPDE_CUDA(h, cudaSetDevice(h->device));
 	std::string error;
-	const int rc = gmwb_run(g, W.data(), nw, A.data(), na, Z.data(), nz, V, stats, h->stream, &h->launches, &error);
+	const int rc = gmwb_run(g, W.data(), nw, A.data(), na, Z.data(), nz, V, stats, h->stream, &h->launches, &error, comm);
 	if(rc != QPDE_OK) return fail(h, rc, "%s", error.c_str());
 	if(W_out) memcpy(W_out, W.data(), sizeof(double) * nw);
 	if(A_out) memcpy(A_out, A.data(), sizeof(double) * na);

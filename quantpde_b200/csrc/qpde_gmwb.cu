@@ -29,10 +29,14 @@
 //                  machine-epsilon residual);
 //   k_gmwb_relerr  relativeError(x_new, x_old) > tolerance.
 #include <cooperative_groups.h>
+#include <cuda.h>
 #include <math_constants.h>
 
 #include <algorithm>
+#include <chrono>
+#include <cstdio>
 #include <cstdlib>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -153,8 +157,16 @@ __global__ void k_gmwb_exit(GmwbDev d, double *x, int row_begin, int row_end) {
 	x[row] = qmax(w, (1 - d.kfee) * a - d.c);                // gmwb.cpp:168
 }
 
+// MODE 0: control search + row assembly (one GPU).  Sharded over ranks the two halves run apart:
+// MODE 1 searches and leaves one word per node — the index of the stochastic control (bits 0 .. 7, 255 =
+// none) and, where the penalty is active, the index of the impulse candidate + 1 (bits 8 ..) — which is
+// all a rank has to send; MODE 2 assembles the rows of any node from such a word with the expressions
+// of the search, hence to the same bits.
+enum { POLICY_FUSED = 0, POLICY_SEARCH = 1, POLICY_ASSEMBLE = 2 };
+
+template <int MODE>
 __global__ void __launch_bounds__(128)
-k_gmwb_policy(GmwbDev d, GmwbRows R, const double *x, double h0, int row_begin, int row_end) {
+k_gmwb_policy(GmwbDev d, GmwbRows R, const double *x, double h0, int row_begin, int row_end, int *decision) {
 	const int n = d.nw * d.na;
 	const int row = row_begin + blockIdx.x * blockDim.x + threadIdx.x;
 	const int nw = d.nw;
@@ -182,7 +194,12 @@ k_gmwb_policy(GmwbDev d, GmwbRows R, const double *x, double h0, int row_begin, 
 
 	// 1. stochastic control: argmin_q (L^q x - f^q)_row, strict <, grid order
 	OpRow o; o.aw = o.cw = o.aa = o.ca = 0.; o.diag = 0.; o.b = 0.;
-	{
+	const int word = MODE == POLICY_ASSEMBLE ? decision[row] : 0;
+	int kq_sel = 255, kz_sel = -1;
+	if(MODE == POLICY_ASSEMBLE) {
+		kq_sel = word & 255;
+		if(kq_sel != 255) o = controlled_row(d, iw, ia, d.q[kq_sel]);
+	} else {
 		double best = CUDART_INF;
 		for(int k = 0; k < d.nq; ++k) {
 			const OpRow c = controlled_row(d, iw, ia, d.q[k]);
@@ -193,7 +210,7 @@ k_gmwb_policy(GmwbDev d, GmwbRows R, const double *x, double h0, int row_begin, 
 			if(iw > 0 && iw < nw - 1) acc += c.cw * x[row + 1];
 			if(ia > 0 && ia < d.na - 1) acc += c.ca * x[row + nw];
 			const double cand = acc - c.b;
-			if(cand < best) { best = cand; o = c; }
+			if(cand < best) { best = cand; o = c; kq_sel = k; }
 		}
 	}
 	// 2. impulse control: argmin_z ((I - M_z) x - g_z)_row
@@ -201,7 +218,11 @@ k_gmwb_policy(GmwbDev d, GmwbRows R, const double *x, double h0, int row_begin, 
 	double best = CUDART_INF; bool has = false;
 	{
 		const double w = d.W[iw], a = d.A[ia];
-		for(int k = 0; k < d.nz; ++k) {
+		// the search walks every candidate; the assembly re-forms the chosen one (none where the penalty is off)
+		const int chosen = (word >> 8) - 1;                       // -1: the penalty is off at this node
+		const int k_begin = MODE == POLICY_ASSEMBLE && chosen >= 0 ? chosen : 0;
+		const int k_end = MODE == POLICY_ASSEMBLE ? (chosen >= 0 ? chosen + 1 : 0) : d.nz;
+		for(int k = k_begin; k < k_end; ++k) {
 			const double z = tab_z[tab0 + k];
 			const double w_plus = qmax(w - z, 0.), a_plus = a - z;     // gmwb.cpp:139-148
 			int i0; double f0;
@@ -220,15 +241,19 @@ k_gmwb_policy(GmwbDev d, GmwbRows R, const double *x, double h0, int row_begin, 
 			}
 			if(!diag_done) acc += 1. * x[row];
 			const double cand = acc - g;
-			if(cand < best) {
-				best = cand; has = true; reward = g;
+			if(MODE == POLICY_ASSEMBLE || cand < best) {
+				best = cand; has = true; reward = g; kz_sel = k;
 #pragma unroll
 				for(int m = 0; m < 4; ++m) { t[m] = tt[m]; f[m] = ff[m]; }
 			}
 		}
 	}
 	// 3. penalty flag and the assembled row of I + h L^q* + P (I - M*)
-	const bool active = has && (d.pen * best) < 0.;
+	const bool active = MODE == POLICY_ASSEMBLE ? has : has && (d.pen * best) < 0.;
+	if(MODE == POLICY_SEARCH) {
+		decision[row] = kq_sel | (active ? (kz_sel + 1) << 8 : 0);
+		return;
+	}
 	double a_ = o.aw * h0, b_ = 1. + o.diag * h0, c_ = o.cw * h0;
 	const double rhs = h0 * o.b;
 	double rhs2 = 0.;
@@ -622,11 +647,25 @@ static int gmwb_cluster() {                // CTAs in the cluster: depth of the 
 template <int PT>
 static cudaError_t launch_lines_t(GmwbShard &sh, GmwbRows R, double *x, const double *v0, const double *xguess, int ia0, int ia1, int max_local, int *status, cudaStream_t stream) {
 	const size_t smem = sizeof(double) * 3 * (PT * 8 + 2) + (sizeof(double) + sizeof(int)) * gmwb_near_k(PT) * PT;
-	cudaError_t e = cudaFuncSetAttribute(k_gmwb_lines<8, PT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-	if(e != cudaSuccess) return e;
-	cudaLaunchConfig_t cfg = {};
+	cudaError_t e = cudaSuccess;
 	const int G = gmwb_cluster();
-	if(G > 8) { e = cudaFuncSetAttribute(k_gmwb_lines<8, PT>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1); if(e != cudaSuccess) return e; }
+	// The function attributes are per device and are set once per device: cudaFuncSetAttribute is not
+	// stream-ordered — called per launch it held the host back until the line kernels in flight had
+	// finished, so a pass meant to trail another one was issued only when that one was over (seen with
+	// QPDE_GMWB_TIMELINE).
+	{
+		static std::mutex lock;
+		static bool configured[64] = {};
+		int device = 0; cudaGetDevice(&device);
+		std::lock_guard<std::mutex> guard(lock);
+		if(device < 0 || device >= 64 || !configured[device]) {
+			e = cudaFuncSetAttribute(k_gmwb_lines<8, PT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+			if(e != cudaSuccess) return e;
+			if(G > 8) { e = cudaFuncSetAttribute(k_gmwb_lines<8, PT>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1); if(e != cudaSuccess) return e; }
+			if(device >= 0 && device < 64) configured[device] = true;
+		}
+	}
+	cudaLaunchConfig_t cfg = {};
 	cfg.gridDim = dim3(G); cfg.blockDim = dim3(PT); cfg.dynamicSmemBytes = smem; cfg.stream = stream;
 	cudaLaunchAttribute attr[1];
 	attr[0].id = cudaLaunchAttributeClusterDimension;
@@ -725,11 +764,15 @@ void gmwb_shard_exit(GmwbShard *sh, double *x) {
 }
 
 // control searches + row assembly for the shard's lines, from the full previous iterate
-static void launch_policy(GmwbShard *sh, const GmwbRows &R, const double *x, double h0, int a0, int a1, cudaStream_t stream) {
+static void launch_policy(GmwbShard *sh, const GmwbRows &R, const double *x, double h0, int a0, int a1, cudaStream_t stream,
+		int mode = POLICY_FUSED, int *decision = nullptr) {
 	const int r0 = a0 * sh->d.nw, r1 = a1 * sh->d.nw;
 	if(r1 > r0) {
 		const size_t smem = (size_t)(128 / sh->d.nw + 2) * sh->d.nz * (2 * sizeof(double) + sizeof(int));
-		k_gmwb_policy<<<(r1 - r0 + 127) / 128, 128, smem, stream>>>(sh->d, R, x, h0, r0, r1);
+		const int grid = (r1 - r0 + 127) / 128;
+		if(mode == POLICY_SEARCH) k_gmwb_policy<POLICY_SEARCH><<<grid, 128, smem, stream>>>(sh->d, R, x, h0, r0, r1, decision);
+		else if(mode == POLICY_ASSEMBLE) k_gmwb_policy<POLICY_ASSEMBLE><<<grid, 128, smem, stream>>>(sh->d, R, x, h0, r0, r1, decision);
+		else k_gmwb_policy<POLICY_FUSED><<<grid, 128, smem, stream>>>(sh->d, R, x, h0, r0, r1, decision);
 		++*sh->launches;
 	}
 }
@@ -777,6 +820,60 @@ void gmwb_shard_relerr(GmwbShard *sh, const double *x, const double *xprev, int 
 // per iteration.
 namespace {
 
+// Spatial partition of the SMs (CUDA green contexts, driver API through cudaGetDriverEntryPoint: no link-time
+// libcuda).  A line kernel is a cluster of G CTAs that each need a whole SM (512 threads x 128 registers);
+// next to a control search whose small CTAs refill every SM the moment one of them retires, a second cluster
+// never finds G empty SMs at once and the "concurrent" trailing pass runs only in the gaps (measured with
+// QPDE_GMWB_TIMELINE: it started when the leading pass ended).  So the two line streams get G SMs each for
+// themselves and the search, the convergence test and the exchange get the rest.
+struct SmPartition {
+	bool on = false;
+	CUgreenCtx ctx[3] = { nullptr, nullptr, nullptr };      // line stream 0, line stream 1, the rest
+	CUresult (*destroy)(CUgreenCtx) = nullptr;
+	int line_sms = 0, rest_sms = 0;
+};
+
+template <typename F>
+bool driver_entry(const char *name, F *fn) {
+	void *ptr = nullptr;
+	cudaDriverEntryPointQueryResult q;
+	if(cudaGetDriverEntryPoint(name, &ptr, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess || !ptr) return false;
+	*fn = (F)ptr;
+	return true;
+}
+
+// streams[0..1]: the line streams, streams[2..3]: search and convergence test.  false: the caller uses ordinary streams.
+bool sm_partition_create(int device, int cluster, int prio_hi, int prio_lo, SmPartition *part, cudaStream_t streams[4]) {
+	CUresult (*getRes)(CUdevice, CUdevResource *, CUdevResourceType) = nullptr;
+	CUresult (*split)(CUdevResource *, unsigned int *, const CUdevResource *, CUdevResource *, unsigned int, unsigned int) = nullptr;
+	CUresult (*genDesc)(CUdevResourceDesc *, CUdevResource *, unsigned int) = nullptr;
+	CUresult (*create)(CUgreenCtx *, CUdevResourceDesc, CUdevice, unsigned int) = nullptr;
+	CUresult (*streamCreate)(CUstream *, CUgreenCtx, unsigned int, int) = nullptr;
+	if(!driver_entry("cuDeviceGetDevResource", &getRes) || !driver_entry("cuDevSmResourceSplitByCount", &split)
+			|| !driver_entry("cuDevResourceGenerateDesc", &genDesc) || !driver_entry("cuGreenCtxCreate", &create)
+			|| !driver_entry("cuGreenCtxStreamCreate", &streamCreate) || !driver_entry("cuGreenCtxDestroy", &part->destroy)) return false;
+	CUdevResource all, groups[2], rest;
+	if(getRes((CUdevice)device, &all, CU_DEV_RESOURCE_TYPE_SM) != CUDA_SUCCESS) return false;
+	unsigned int nb = 2;
+	const unsigned int want = (unsigned int)((cluster + 7) / 8 * 8);          // granularity on sm_90+: multiples of 8
+	if(split(groups, &nb, &all, &rest, 0, want) != CUDA_SUCCESS || nb != 2 || rest.sm.smCount < 64) return false;
+	CUdevResource *res[3] = { &groups[0], &groups[1], &rest };
+	for(int k = 0; k < 3; ++k) {
+		CUdevResourceDesc desc;
+		if(genDesc(&desc, res[k], 1) != CUDA_SUCCESS || create(&part->ctx[k], desc, (CUdevice)device, CU_GREEN_CTX_DEFAULT_STREAM) != CUDA_SUCCESS) {
+			for(int q = 0; q < k; ++q) part->destroy(part->ctx[q]);
+			return false;
+		}
+	}
+	bool ok = streamCreate(&streams[0], part->ctx[0], CU_STREAM_NON_BLOCKING, prio_hi) == CUDA_SUCCESS
+		&& streamCreate(&streams[1], part->ctx[1], CU_STREAM_NON_BLOCKING, prio_hi) == CUDA_SUCCESS
+		&& streamCreate(&streams[2], part->ctx[2], CU_STREAM_NON_BLOCKING, prio_lo) == CUDA_SUCCESS
+		&& streamCreate(&streams[3], part->ctx[2], CU_STREAM_NON_BLOCKING, prio_hi) == CUDA_SUCCESS;
+	if(!ok) { for(int q = 0; q < 3; ++q) part->destroy(part->ctx[q]); return false; }
+	part->on = true; part->line_sms = (int)groups[0].sm.smCount; part->rest_sms = (int)rest.sm.smCount;
+	return true;
+}
+
 struct GmwbPass {
 	int cur = -1, prev = -1, v0 = -1, rset = 0, slot = 0;
 	double h0 = 0.;
@@ -786,15 +883,29 @@ struct GmwbPass {
 
 struct GmwbSearch {         // the control search that last filled a row set
 	int prev = -1; double h0 = 0.; bool valid = false;
-	std::vector<cudaEvent_t> done;
+	int n_ch = 1; long gen = -1;          // generation of the search: its events are ring[(gen % slots) n_ch + chunk]
+	std::vector<cudaEvent_t> ring;
 	std::vector<cudaEvent_t> readers;     // line passes that read the row set since
+	cudaEvent_t done(int chunk) const { const long slots = (long)ring.size() / n_ch; return ring[(size_t)((gen % slots) * n_ch + chunk)]; }
 };
 
 } // namespace
 
 int gmwb_run(const qpde_gmwb2d *p, const double *W, int nw, const double *A, int na, const double *z, int nz,
-		double *V_host, qpde_gmwb2d_stats *stats, cudaStream_t stream, long long *launches, std::string *error) {
+		double *V_host, qpde_gmwb2d_stats *stats, cudaStream_t stream, long long *launches, std::string *error,
+		Comm *comm) {
 	const int n = nw * na;
+	// Sharded by the A-axis: what shards is the control search — the part of an iteration
+	// that is throughput-bound (every node x every impulse candidate).  Rank r searches its block of the
+	// lines of every chunk, the decisions of the blocks (4 bytes per node) are exchanged with NCCL broadcasts
+	// (the "all-gather before the impulse step") and every rank assembles all rows from them; the line pass — a latency-bound chain on one cluster of 8 SMs —
+	// is run by every rank on the full grid, which costs nothing and saves the exchange of the iterate and
+	// of the stopping flag: all ranks hold the same rows, hence bit-identical iterates and verdicts, and
+	// take the same (deterministic) decisions, speculative ones included.
+	const int world = comm_world(comm), rank = comm_rank(comm);
+	bool comm_ok = true;
+	// QPDE_GMWB_SPLIT=1: the sharded code path (search -> decisions -> assembly) on one rank, for testing
+	const bool split = world > 1 || (getenv("QPDE_GMWB_SPLIT") && atoi(getenv("QPDE_GMWB_SPLIT")) != 0);
 	GmwbShard *sh = nullptr;
 	int rc = gmwb_shard_create(p, W, nw, A, na, z, nz, 0, na, stream, launches, &sh, error);
 	if(rc != QPDE_OK) return rc;
@@ -810,7 +921,8 @@ int gmwb_run(const qpde_gmwb2d *p, const double *W, int nw, const double *A, int
 	// control search overlapped (depth 1).  The speculative trailing pass (depth 2) pays only where the
 	// control search is much shorter than the line pass — here they are level, and a second pass in
 	// flight has nothing left to hide behind — so it is opt-in.
-	int depth = env_depth ? atoi(env_depth) : 1;
+	// With the search cut into `world` pieces the line chain dominates and the trailing pass pays: depth 2.
+	int depth = env_depth ? atoi(env_depth) : (world > 1 ? 2 : 1);
 	if(depth < 0 || depth > 2) depth = 1;
 	// chunks of at least 128 lines: a chunk is one cluster launch and one pipeline fill of the chain
 	int n_ch = env_chunks ? atoi(env_chunks) : 8;
@@ -819,7 +931,12 @@ int gmwb_run(const qpde_gmwb2d *p, const double *W, int nw, const double *A, int
 	std::vector<int> a0((size_t)n_ch + 1);
 	for(int j = 0; j <= n_ch; ++j) a0[j] = (int)((long long)na * j / n_ch);
 
-	constexpr int NB = 8, NPASS = 6;
+	// Events are re-recorded when their pass slot / search generation comes round again, and a wait binds to
+	// the latest record: a reference kept in buf_events[] must not outlive its slot.  A buffer is reused
+	// after at most NB passes, so rings of 3 NB pass slots and search generations keep every kept
+	// reference on the record it was made for (with 6 slots a recycled buffer made each new pass wait for
+	// the END of the pass before it through a stale flag_ready: no two passes ever overlapped).
+	constexpr int NB = 8, NPASS = 3 * NB, NSEARCH = 3 * NB;
 	double *buf[NB];
 	for(int k = 0; k < NB; ++k) buf[k] = (double *)dalloc(sizeof(double) * n);
 	GmwbRows R[2];
@@ -828,18 +945,49 @@ int gmwb_run(const qpde_gmwb2d *p, const double *W, int nw, const double *A, int
 	R[1].raa = (double *)dalloc(sizeof(double) * n); R[1].rhs = (double *)dalloc(sizeof(double) * n); R[1].rhs2 = (double *)dalloc(sizeof(double) * n);
 	R[1].tgt = (int *)dalloc(sizeof(int) * 4 * (size_t)n); R[1].tw = (double *)dalloc(sizeof(double) * 4 * (size_t)n);
 	int *flags_dev = (int *)dalloc(sizeof(int) * 2 * NPASS);
+	int *decision[2] = { nullptr, nullptr };      // sharded: what the control search of a row set decided, per node
+	if(split) for(int k = 0; k < 2; ++k) decision[k] = (int *)dalloc(sizeof(int) * n);
 	int *hflags = nullptr;
 	if(!ok || cudaHostAlloc((void **)&hflags, sizeof(int) * 2 * NPASS, cudaHostAllocDefault) != cudaSuccess) {
 		gmwb_shard_destroy(sh); *error = "gmwb: out of memory"; return QPDE_ERR_CUDA;
 	}
-	cudaStream_t sL[2], sP, sR;
+	cudaStream_t sL[2], sP, sR, sC = nullptr;
 	// the line passes are the critical path: their clusters go first when SMs free up
 	int prio_lo = 0, prio_hi = 0;
 	cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
-	cudaStreamCreateWithPriority(&sL[0], cudaStreamNonBlocking, prio_hi); cudaStreamCreateWithPriority(&sL[1], cudaStreamNonBlocking, prio_hi);
-	cudaStreamCreateWithPriority(&sP, cudaStreamNonBlocking, prio_lo); cudaStreamCreateWithPriority(&sR, cudaStreamNonBlocking, prio_hi);
+	// with two passes in flight the line streams own their SMs (SmPartition above); QPDE_GMWB_PARTITION=0 / 1 overrides
+	SmPartition part;
+	{
+		const char *env_part = getenv("QPDE_GMWB_PARTITION");
+		const bool want = env_part ? atoi(env_part) != 0 : depth >= 2;
+		int device = 0; cudaGetDevice(&device);
+		cudaStream_t st4[4];
+		if(want && sm_partition_create(device, gmwb_cluster(), prio_hi, prio_lo, &part, st4)) {
+			sL[0] = st4[0]; sL[1] = st4[1]; sP = st4[2]; sR = st4[3];
+		} else {
+			cudaStreamCreateWithPriority(&sL[0], cudaStreamNonBlocking, prio_hi); cudaStreamCreateWithPriority(&sL[1], cudaStreamNonBlocking, prio_hi);
+			cudaStreamCreateWithPriority(&sP, cudaStreamNonBlocking, prio_lo); cudaStreamCreateWithPriority(&sR, cudaStreamNonBlocking, prio_hi);
+		}
+	}
+	// the exchange of the rows runs behind the search of the next chunk, on a stream of its own
+	if(split) cudaStreamCreateWithPriority(&sC, cudaStreamNonBlocking, prio_hi);
+	cudaEvent_t searched = nullptr;
 	std::vector<cudaEvent_t> all_events;
-	auto new_event = [&] () { cudaEvent_t e; cudaEventCreateWithFlags(&e, cudaEventDisableTiming); all_events.push_back(e); return e; };
+	// QPDE_GMWB_TIMELINE=n: events carry times, and the start / end of every launch of the last n passes is printed
+	const int timeline = getenv("QPDE_GMWB_TIMELINE") ? atoi(getenv("QPDE_GMWB_TIMELINE")) : 0;
+	auto new_event = [&] () { cudaEvent_t e; cudaEventCreateWithFlags(&e, timeline > 0 ? cudaEventDefault : cudaEventDisableTiming); all_events.push_back(e); return e; };
+	struct Mark { char what; long pass; int chunk; cudaEvent_t begin, end; double host_ms; };
+	std::vector<Mark> marks;
+	long pass_counter = 0;
+	auto mark_begin = [&] (char what, long pass, int chunk, cudaStream_t s) -> size_t {
+		if(timeline <= 0) return 0;
+		const double now = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
+		Mark m{what, pass, chunk, new_event(), new_event(), now};
+		cudaEventRecord(m.begin, s);
+		marks.push_back(m);
+		return marks.size() - 1;
+	};
+	auto mark_end = [&] (size_t at, cudaStream_t s) { if(timeline > 0) cudaEventRecord(marks[at].end, s); };
 	GmwbPass passes[NPASS];
 	for(int k = 0; k < NPASS; ++k) {
 		passes[k].slot = k;
@@ -847,7 +995,7 @@ int gmwb_run(const qpde_gmwb2d *p, const double *W, int nw, const double *A, int
 		passes[k].flag_ready = new_event();
 	}
 	GmwbSearch search[2];
-	for(int k = 0; k < 2; ++k) for(int j = 0; j < n_ch; ++j) search[k].done.push_back(new_event());
+	for(int k = 0; k < 2; ++k) { search[k].n_ch = n_ch; for(int j = 0; j < n_ch * NSEARCH; ++j) search[k].ring.push_back(new_event()); }
 	std::vector<cudaEvent_t> buf_events[NB];       // what must have finished before buffer b is overwritten
 	cudaEvent_t start_ready = new_event();
 
@@ -855,7 +1003,9 @@ int gmwb_run(const qpde_gmwb2d *p, const double *W, int nw, const double *A, int
 		cudaStreamSynchronize(sL[0]); cudaStreamSynchronize(sL[1]); cudaStreamSynchronize(sP); cudaStreamSynchronize(sR);
 		cudaStreamSynchronize(stream);
 		for(cudaEvent_t e : all_events) cudaEventDestroy(e);
+		if(sC) { cudaStreamSynchronize(sC); cudaStreamDestroy(sC); }
 		cudaStreamDestroy(sL[0]); cudaStreamDestroy(sL[1]); cudaStreamDestroy(sP); cudaStreamDestroy(sR);
+		if(part.on) for(int q = 0; q < 3; ++q) part.destroy(part.ctx[q]);
 		cudaFreeHost(hflags);
 		gmwb_shard_destroy(sh);
 	};
@@ -863,16 +1013,40 @@ int gmwb_run(const qpde_gmwb2d *p, const double *W, int nw, const double *A, int
 	// the control search of one iteration: reads buf[prev] chunk by chunk behind its producer
 	auto enqueue_search = [&] (int rset, int prev, double h0, const GmwbPass *producer) {
 		GmwbSearch &S = search[rset];
+		++S.gen;                               // a fresh set of events for this search
 		for(int j = 0; j < n_ch; ++j) {
 			if(producer) cudaStreamWaitEvent(sP, producer->lines_done[j], 0);
 			else if(j == 0) cudaStreamWaitEvent(sP, start_ready, 0);
 			if(j == 0) for(cudaEvent_t e : S.readers) cudaStreamWaitEvent(sP, e, 0);      // the passes that still read these rows
-			launch_policy(sh, R[rset], buf[prev], h0, a0[j], a0[j + 1], sP);
-			cudaEventRecord(S.done[j], sP);
+			const size_t mk = mark_begin('S', pass_counter, j, sP);
+			if(!split) {
+				launch_policy(sh, R[rset], buf[prev], h0, a0[j], a0[j + 1], sP);
+			} else {
+				// this rank searches its block of the chunk; the decisions (one word per node) of every block reach
+				// every rank, and every rank assembles the rows of the whole chunk from them
+				auto cut = [&] (int r) { return a0[j] + (int)((long long)(a0[j + 1] - a0[j]) * r / world); };
+				launch_policy(sh, R[rset], buf[prev], h0, cut(rank), cut(rank + 1), sP, POLICY_SEARCH, decision[rset]);
+				if(!searched) searched = new_event();
+				// one event serves every chunk: a wait binds to the record that precedes it
+				cudaEventRecord(searched, sP);
+				cudaStreamWaitEvent(sC, searched, 0);
+				if(j == 0) for(cudaEvent_t e : S.readers) cudaStreamWaitEvent(sC, e, 0);
+				if(world > 1) {
+					comm_ok = comm_ok && comm_group_start(comm);
+					for(int r = 0; r < world; ++r) {
+						const size_t r0 = (size_t)cut(r) * nw, cnt = (size_t)(cut(r + 1) - cut(r)) * nw;
+						if(cnt) comm_ok = comm_ok && comm_broadcast(comm, decision[rset] + r0, cnt * sizeof(int), r, sC);
+					}
+					comm_ok = comm_ok && comm_group_end(comm);
+				}
+				launch_policy(sh, R[rset], buf[prev], h0, a0[j], a0[j + 1], sC, POLICY_ASSEMBLE, decision[rset]);
+			}
+			mark_end(mk, split ? sC : sP);
+			cudaEventRecord(S.done(j), split ? sC : sP);
 		}
 		S.readers.clear();
 		S.prev = prev; S.h0 = h0; S.valid = true;
-		buf_events[prev].push_back(S.done[n_ch - 1]);
+		buf_events[prev].push_back(S.done(n_ch - 1));
 	};
 	int next_pass = 0, next_buf = 1;
 	auto enqueue_pass = [&] (int prev, int v0, double h0, int rset, int line_stream, const int *keep, int n_keep) -> GmwbPass * {
@@ -891,8 +1065,10 @@ int gmwb_run(const qpde_gmwb2d *p, const double *W, int nw, const double *A, int
 		buf_events[P.cur].clear();
 		cudaMemsetAsync(flags_dev + 2 * P.slot, 0, sizeof(int) * 2, sl);
 		for(int j = 0; j < n_ch; ++j) {
-			cudaStreamWaitEvent(sl, search[rset].done[j], 0);
+			cudaStreamWaitEvent(sl, search[rset].done(j), 0);
+			const size_t mk = mark_begin('L', pass_counter, j, sl);
 			launch_lines(*sh, R[rset], buf[P.cur], buf[v0], buf[prev], a0[j], a0[j + 1], flags_dev + 2 * P.slot + 1, sl);
+			mark_end(mk, sl);
 			cudaEventRecord(P.lines_done[j], sl);
 			cudaStreamWaitEvent(sR, P.lines_done[j], 0);
 			const int r0 = a0[j] * nw, r1 = a0[j + 1] * nw;
@@ -901,6 +1077,7 @@ int gmwb_run(const qpde_gmwb2d *p, const double *W, int nw, const double *A, int
 		}
 		cudaMemcpyAsync(hflags + 2 * P.slot, flags_dev + 2 * P.slot, sizeof(int) * 2, cudaMemcpyDeviceToHost, sR);
 		cudaEventRecord(P.flag_ready, sR);
+		++pass_counter;
 		search[rset].readers.push_back(P.lines_done[n_ch - 1]);
 		buf_events[P.cur].push_back(P.flag_ready);
 		buf_events[prev].push_back(P.flag_ready);
@@ -917,6 +1094,7 @@ int gmwb_run(const qpde_gmwb2d *p, const double *W, int nw, const double *A, int
 	int accepted = 0;                     // buffer of the latest accepted iterate
 	const GmwbPass *accepted_pass = nullptr;
 	GmwbPass *spec = nullptr;             // the trailing pass launched on a prediction
+	long spec_used = 0, spec_wasted = 0;  // trailing passes that were kept / discarded (QPDE_GMWB_TRACE)
 	long k = 0;                           // iteration counter: row set k % 2, line stream k % 2
 	int last_its = 2;                     // iterations the previous step took: the prediction for this one
 	cudaError_t err = cudaSuccess;
@@ -933,6 +1111,7 @@ int gmwb_run(const qpde_gmwb2d *p, const double *W, int nw, const double *A, int
 		do {
 			GmwbPass *P = nullptr;
 			if(spec && spec->prev == accepted && spec->v0 == v0 && spec->h0 == h0) P = spec;
+			if(spec) { if(P) ++spec_used; else ++spec_wasted; }
 			spec = nullptr;
 			const int rset = (int)(k % 2);
 			if(!P) {
@@ -971,7 +1150,24 @@ int gmwb_run(const qpde_gmwb2d *p, const double *W, int nw, const double *A, int
 		err = cudaMemcpyAsync(V_host, buf[accepted], sizeof(double) * n, cudaMemcpyDeviceToHost, stream);
 		if(err == cudaSuccess) err = cudaStreamSynchronize(stream);
 	}
+	if(timeline > 0 && !marks.empty() && rank == 0) {
+		cudaDeviceSynchronize();
+		const long first = pass_counter - timeline;
+		cudaEvent_t base = nullptr; double base_host = 0.;
+		for(const Mark &m : marks) if(m.pass >= first && (m.what == 'L' || m.what == 'S')) { base = m.begin; base_host = m.host_ms; break; }
+		for(const Mark &m : marks) {
+			if(m.pass < first || !base) continue;
+			float b = 0.f, e = 0.f;
+			cudaEventElapsedTime(&b, base, m.begin); cudaEventElapsedTime(&e, base, m.end);
+			fprintf(stderr, "timeline %c pass %ld chunk %d: %8.3f .. %8.3f ms (issued by the host at %8.3f)\n", m.what, m.pass, m.chunk, b, e, m.host_ms - base_host);
+		}
+	}
 	cleanup();
+	if(!comm_ok) { *error = "gmwb solve: an NCCL call failed"; return QPDE_ERR_CUDA; }
+	if(getenv("QPDE_GMWB_TRACE")) {
+		fprintf(stderr, "gmwb: rank %d of %d, SM partition %d + %d + %d, depth %d, %d chunks, %ld iterations in %d steps, trailing passes kept %ld, discarded %ld\n",
+			rank, world, part.on ? part.line_sms : 0, part.on ? part.line_sms : 0, part.on ? part.rest_sms : 0, depth, n_ch, k, n_steps, spec_used, spec_wasted);
+	}
 	if(err != cudaSuccess) { *error = std::string("gmwb solve: ") + cudaGetErrorString(err); return QPDE_ERR_CUDA; }
 	if(stats) { stats->n_steps = n_steps; stats->mean_inner = (double)inner_sum / n_steps; stats->status = status; stats->nodes_w = nw; stats->nodes_a = na; }
 	return QPDE_OK;

@@ -95,9 +95,23 @@ bool jump_supported(const DeviceBatch &b);
 int launch_jump(const DeviceBatch &b, const JumpWork &w, const DeviceResult &out,
 		cudaStream_t stream, long long *launches);
 
-// GMWB 2-D sweep (qpde_gmwb.cu): host-driven loop over the kernels.
+// The communicator of a handle (qpde_comm.cu): NCCL, loaded at run time.  Only the sharded GMWB solve uses it.
+struct Comm;
+int comm_unique_id(unsigned char *id, std::string *error);
+int comm_create(const unsigned char *id, int rank, int world, Comm **out, std::string *error);
+void comm_destroy(Comm *c);
+int comm_rank(const Comm *c);
+int comm_world(const Comm *c);
+bool comm_group_start(Comm *c);
+bool comm_group_end(Comm *c);
+bool comm_broadcast(Comm *c, void *buf, size_t bytes, int root, cudaStream_t stream);
+bool comm_allreduce_max(Comm *c, int *buf, int count, cudaStream_t stream);
+
+// GMWB 2-D sweep (qpde_gmwb.cu): host-driven loop over the kernels.  comm != nullptr: the control search
+// is sharded by the A-axis over the communicator's ranks (a collective call).
 int gmwb_run(const qpde_gmwb2d *p, const double *W, int nw, const double *A, int na, const double *z, int nz,
-		double *V_host, qpde_gmwb2d_stats *stats, cudaStream_t stream, long long *launches, std::string *error);
+		double *V_host, qpde_gmwb2d_stats *stats, cudaStream_t stream, long long *launches, std::string *error,
+		Comm *comm = nullptr);
 
 struct GmwbShard;
 int gmwb_shard_create(const qpde_gmwb2d *p, const double *W, int nw, const double *A, int na, const double *z, int nz,

@@ -153,3 +153,43 @@ def test_gmwb_two_ranks_nccl(qpde, oracle, tmp_path):
     with qpde.Handle(0) as h:
         whole = _solve(qpde, h, oracle, refine=1)
     assert np.array_equal(got["V"], whole["V"]) and float(got["mean_inner"]) == whole["mean_inner"]
+
+
+def test_gmwb_library_sharded_two_ranks(qpde, oracle, tmp_path):
+    """qpde_comm_init + qpde_gmwb2d_solve_sharded at world size 2: NCCL inside the library, torch only
+    ships the communicator id.  Bit-identical to the single-GPU solve (needs two GPUs)."""
+    import subprocess
+    import sys
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("one GPU visible")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = str(tmp_path / "sharded_library.npz")
+    subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                    "--master-addr", "127.0.0.1", "--master-port", "29633",
+                    os.path.join(root, "tools", "gmwb_sharded_library.py"), "--refine", "2", "--out", out],
+                   check=True, cwd=root, timeout=900)
+    got = np.load(out)
+    with qpde.Handle(0) as h:
+        whole = _solve(qpde, h, oracle, refine=2)
+    assert np.array_equal(got["V"], whole["V"]) and float(got["mean_inner"]) == whole["mean_inner"]
+
+
+def test_sharded_solve_needs_a_communicator(qpde, handle, oracle):
+    with pytest.raises(qpde.QpdeError):
+        qpde.gmwb_solve(handle, oracle.GMWB_W_AXIS, oracle.uniform_axis(0., 100., 11), [0., 10.], [0., .5, 1.], 0, 8,
+                        sharded=True)
+
+
+@pytest.mark.parametrize("depth,partition", [("1", "0"), ("2", "1"), ("2", "0")])
+def test_split_search_and_assembly_equals_the_fused_kernel(qpde, handle, oracle, monkeypatch, depth, partition):
+    """The sharded code path on one rank (QPDE_GMWB_SPLIT=1): control search -> one decision word per node ->
+    row assembly from the words, with and without the trailing pass and the SM partition (green contexts).
+    Bit-identical to the fused search + assembly kernel."""
+    whole = _solve(qpde, handle, oracle, refine=2)
+    monkeypatch.setenv("QPDE_GMWB_SPLIT", "1")
+    monkeypatch.setenv("QPDE_GMWB_DEPTH", depth)
+    monkeypatch.setenv("QPDE_GMWB_PARTITION", partition)
+    res = _solve(qpde, handle, oracle, refine=2)
+    assert res["status"] == 0 and res["mean_inner"] == whole["mean_inner"]
+    assert np.array_equal(res["V"], whole["V"])
