@@ -615,6 +615,87 @@ def run_other_config(args):
     print(json.dumps(line), flush=True)
 
 
+def run_gmwb_sharded(args, rank, world, local):
+    """--config 5 on N > 1 GPUs: configs[4] with the control search sharded by the A-axis over the ranks
+    (qpde_comm_init + qpde_gmwb2d_solve_sharded: NCCL inside the library; torch.distributed / gloo only ships
+    the 128-byte communicator id and reduces the wall time).  Strong scaling: one problem, N GPUs."""
+    import torch
+    import torch.distributed as dist
+    from quantpde_b200 import capi
+    sys.stdout.flush()
+    result_fd = os.dup(1)
+    os.dup2(2, 1)
+    torch.cuda.set_device(local)
+    dist.init_process_group("gloo")
+    refine, a_points, ts0 = args.gmwb_refine, 17, args.gmwb_timesteps0
+    A = np.array([0. + (100. / (a_points - 1)) * i for i in range(a_points)])
+    Z = np.array([0., .5, 1.])
+    handle = capi.Handle(local)
+    ident = torch.zeros(capi.COMM_ID_BYTES, dtype=torch.uint8)
+    if rank == 0:
+        ident = torch.frombuffer(bytearray(capi.comm_unique_id()), dtype=torch.uint8).clone()
+    dist.broadcast(ident, 0)
+    handle.comm_init(ident.numpy().tobytes(), rank, world)
+    capi.gmwb_solve(handle, GMWB_W, A, [0., 10.], Z, 1, 2, sharded=True)          # warm-up: module load, NCCL channels
+    # parity first (every rank takes part): refinement 1 of the reference's default problem against its own output
+    g = np.load(os.path.join(ROOT, "tests", "golden", "gmwb_reference.npz"), allow_pickle=False)
+    A51 = np.array([0. + 2. * i for i in range(51)])
+    small = capi.gmwb_solve(handle, GMWB_W, A51, [0., 10.], Z, 1, 64, sharded=True)
+    worst = _rel(small["V"], g["gmwb_k1/V"].reshape(small["V"].shape))
+    assert worst <= 1e-9 and small["mean_inner"] == float(g["gmwb_k1/mean_inner"]), worst
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ts = []
+    nrun = max(1, min(args.steps, 2))
+    l0 = handle.launches
+    for _ in range(nrun):
+        dist.barrier()
+        t0 = time.perf_counter()
+        res = capi.gmwb_solve(handle, GMWB_W, A, [0., 10.], Z, refine, ts0 * 2 ** refine, sharded=True)
+        secs = torch.tensor([time.perf_counter() - t0], dtype=torch.float64)
+        dist.all_reduce(secs, op=dist.ReduceOp.MAX)
+        ts.append(float(secs.item()))
+    launches = (handle.launches - l0) // nrun
+    clocks = sampler.stop() if rank == 0 else None
+    # every rank holds the full V: they must agree bit for bit
+    digest = torch.tensor([float(np.frombuffer(res["V"].tobytes(), dtype=np.uint64).sum() % (2 ** 52))], dtype=torch.float64)
+    lo, hi = digest.clone(), digest.clone()
+    dist.all_reduce(lo, op=dist.ReduceOp.MIN); dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+    secs = float(np.mean(ts))
+    nw, na, nz = len(res["W"]), len(res["A"]), 2 * 2 ** refine + 1
+    its = float(res["mean_inner"]) * res["n_steps"]
+    flops = (60.0 * nz + 2 * 12.0 + 30.0) * nw * na * its
+    line = {"metric": "GMWB HJBQVI solves/sec (2-D impulse control, %d x %d nodes, %d BDF1 steps)" % (nw, na, res["n_steps"]),
+            "value": 1.0 / secs, "unit": "solves/s", "n_gpus": world, "steps": nrun, "warmup": 1, "ms_per_step": 1e3 * secs,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "gmwb_2d_impulse_control_%dx%d (BASELINE.json configs[4])" % (nw, na), "nodes_w": nw,
+                       "nodes_a": na, "impulse_candidates": nz, "time_steps": int(res["n_steps"]),
+                       "mean_policy_iterations": float(res["mean_inner"]), "status": int(res["status"]),
+                       "seconds_per_solve": secs,
+                       "parallelism": "control search sharded by the A-axis over %d ranks, decisions exchanged by NCCL "
+                                      "broadcasts inside the library, line chain replicated" % world,
+                       "ranks_bit_identical": bool(lo.item() == hi.item())},
+            "roofline": {"bound": "fp64", "achieved": flops / secs / 1e12, "peak": None, "unit": "TFLOP/s", "frac": None,
+                         "traffic": None, "algorithmic_flops_per_launch": flops / max(1, launches),
+                         "model": "per node and policy iteration: 60 flops per impulse candidate + 24 for the two stochastic "
+                                  "controls + 30 for the line solve, summed over the ranks"},
+            "gpu_launches": int(launches), "clocks": clocks,
+            "e2e": {"value": 1.0 / secs, "unit": "solves/s", "h2d_bytes_per_step": int(8 * (len(GMWB_W) + len(A) + len(Z) + 2)),
+                    "d2h_bytes_per_step": int(8 * nw * na), "ms_per_step": 1e3 * secs,
+                    "api": "qpde_gmwb2d_solve_sharded (host axes in, V[n_a][n_w] out on every rank): the timed call itself"},
+            "parity_sample": {"n": 1, "worst_rel_err": worst, "tolerance": 1e-9,
+                              "against": "tests/golden/gmwb_reference.npz gmwb_k1 (the reference's own output), solved sharded"}}
+    handle.close()
+    dist.barrier()
+    dist.destroy_process_group()
+    sys.stdout.flush()
+    os.dup2(result_fd, 1)
+    os.close(result_fd)
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+
+
 def run_reference_arm_other(args):
     """--impl reference --config {3,4,5,hjb}: the reference's CPU path on a bounded sample of that config."""
     from concurrent.futures import ProcessPoolExecutor
@@ -691,6 +772,9 @@ def main():
 
     if args.impl == "reference":
         run_reference_arm(args, rank, world)
+        return
+    if args.config == "5" and world > 1:
+        run_gmwb_sharded(args, rank, world, local)         # every rank: the sharded solve is a collective call
         return
     if args.config != "1":
         if rank == 0:
