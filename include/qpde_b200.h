@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define QPDE_ABI_VERSION 4
+#define QPDE_ABI_VERSION 5
 
 /* ---- status codes ----------------------------------------------------- */
 enum {
@@ -103,6 +103,33 @@ enum {
 	QPDE_OUT_COMPUTED    = 256,
 	QPDE_OUT_ALL         = 511
 };
+
+/* Op codes of an event program (qpde_bs1d_batch.event_program): the transform of a general
+ * Event<1> (Core/Event.hpp:60-184) — what the reference takes as a lambda
+ * [..] (const Interpolant1 &V, Real S) { ... } — written as a postfix expression over a small
+ * stack, evaluated at every node S_i with V the piecewise-linear interpolant of the solution
+ * before the event (Core/Event.hpp:100-112, Core/Interpolant.hpp:153-181,331-374).  Every
+ * arithmetic op is one IEEE double operation on the two topmost entries (a below b), so a program
+ * that spells the lambda's expression in its order reproduces it bit for bit.  CONST and PARAM are
+ * followed by one operand word (an index). */
+enum {
+	QPDE_EV_END    = 0,  /* the result is the top of the stack                                  */
+	QPDE_EV_S      = 1,  /* push S_i                                                              */
+	QPDE_EV_CONST  = 2,  /* push event_consts[operand]                                            */
+	QPDE_EV_PARAM  = 3,  /* push event_params[contract][event][operand] (per event time)          */
+	QPDE_EV_ADD    = 4,  /* a + b                                                                 */
+	QPDE_EV_SUB    = 5,  /* a - b                                                                 */
+	QPDE_EV_MUL    = 6,  /* a * b                                                                 */
+	QPDE_EV_DIV    = 7,  /* a / b                                                                 */
+	QPDE_EV_MAX    = 8,  /* b > a ? b : a   ("if(tmp > best) best = tmp", QuantPDE::max)          */
+	QPDE_EV_MIN    = 9,  /* b < a ? b : a                                                         */
+	QPDE_EV_NEG    = 10, /* -a                                                                    */
+	QPDE_EV_V      = 11, /* V(a): the interpolant of the pre-event solution, clamped at the ends  */
+	QPDE_EV_GT     = 12, /* a > b ? 1 : 0                                                         */
+	QPDE_EV_SELECT = 13  /* c, t, f on the stack (f on top): c != 0 ? t : f                       */
+};
+#define QPDE_EV_MAX_STACK 8
+#define QPDE_EV_MAX_LENGTH 64
 
 typedef struct qpde_handle qpde_handle;       /* device context + stream   */
 typedef struct qpde_bs1d_plan qpde_bs1d_plan; /* device-resident batch     */
@@ -231,7 +258,20 @@ typedef struct {
 	const double *jump_weights;  /* [C][n_fft] density weights f'_j (wrapped order) */
 	int64_t jump_weights_stride; /* 0 = one weight vector shared by all contracts */
 	int32_t n_fft;               /* power of two >= N (qpde_jump_nfft)       */
-	int32_t reserved2;
+	int32_t event_program_length;/* words in event_program (<= QPDE_EV_MAX_LENGTH), 0 = none */
+
+	/* --- general events: at each of the n_exercise event times the solution is replaced by
+	 * program(V, S_i) at every node (QPDE_EV_* above; e.g. the three-way choice of
+	 * examples/experimental/glwb.cpp:84-121).  Takes the place of the tagged exercise / dividend
+	 * transforms (exercise_kind = QPDE_EXERCISE_NONE, dividend_kind = QPDE_DIVIDEND_NONE); linear
+	 * and penalised sweeps, no policy iteration, no jump term. */
+	const int32_t *event_program;
+	const double *event_consts;  /* [n_event_consts] shared by the batch                    */
+	const double *event_params;  /* [C][n_exercise][n_event_params]; row e belongs to the event at T e / E
+	                                (forward: T (e + 1) / E)                                  */
+	int64_t event_params_stride; /* doubles between contracts; 0 = one table shared by all contracts */
+	int32_t n_event_consts;
+	int32_t n_event_params;
 
 	int32_t kernel;          /* QPDE_KERNEL_* (AUTO picks by N)             */
 	int32_t outputs;         /* split form only: QPDE_OUT_* mask of the outputs

@@ -44,7 +44,10 @@ class Problem(C.Structure):
                 ("solver", C.c_int),
                 ("dividend_kind", C.c_int), ("dividend_first", C.c_int), ("dividend", C.c_double),
                 ("variable_target", C.c_double), ("variable_scale", C.c_double), ("variable_dt0", C.c_double),
-                ("steps_taken", C.POINTER(C.c_int)), ("forward", C.c_int)]
+                ("steps_taken", C.POINTER(C.c_int)),
+                ("event_program", C.POINTER(C.c_int)), ("event_consts", C.POINTER(C.c_double)),
+                ("event_params", C.POINTER(C.c_double)), ("n_events", C.c_int), ("n_event_params", C.c_int),
+                ("forward", C.c_int)]
 
 
 DIVIDENDS = {None: 0, "none": 0, "cash": 1, "proportional": 2}
@@ -140,7 +143,7 @@ def interp(x, v, c):
 def sweep(S, lo, di, up, v0, T, steps, n_steps, scheme="rannacher",
           american=False, obstacle=None, event_obstacle=None,
           tolerance=1e-6, scale=1.0, penalty_tol=1e-6, max_inner=1000, solver=0,
-          policy_rows=None, policy_max=False, jump=None, dividend=None, variable=None, forward=False):
+          policy_rows=None, policy_max=False, jump=None, dividend=None, variable=None, forward=False, event=None):
     """Returns dict(V, inner, mask, status).  dividend = (kind, D, first); variable = (dt0, target,
     scale): ReverseVariableStepper, `steps` ignored, n_steps = capacity, out['n_steps'] = steps taken.  policy_rows = (lo, di, up), each
     [n_controls][n]: PolicyIteration over the controls."""
@@ -168,6 +171,14 @@ def sweep(S, lo, di, up, v0, T, steps, n_steps, scheme="rannacher",
     p.tolerance, p.scale, p.penalty_tol, p.max_inner = tolerance, scale, penalty_tol, max_inner
     p.solver = solver
     p.forward = int(forward)
+    if event is not None:
+        # event = dict(program=int words, consts=[..], params=[n_events][n_params])
+        ev_prog = np.ascontiguousarray(event["program"], dtype=np.int32)
+        ev_consts = np.ascontiguousarray(list(event.get("consts", [])) + [0.0], dtype=np.float64)
+        ev_params = np.ascontiguousarray(event["params"], dtype=np.float64)
+        p.event_program = ev_prog.ctypes.data_as(C.POINTER(C.c_int))
+        p.event_consts, p.event_params = _dp(ev_consts), _dp(ev_params)
+        p.n_events, p.n_event_params = ev_params.shape[0], ev_params.shape[1]
     if dividend is not None:
         p.dividend_kind, p.dividend, p.dividend_first = DIVIDENDS[dividend[0]], float(dividend[1]), int(dividend[2])
     if jump is not None:
@@ -193,7 +204,7 @@ def sweep(S, lo, di, up, v0, T, steps, n_steps, scheme="rannacher",
 
 def american_put(K, r, vol, T, n_steps, refine_times, q=0.0, S0=None, call=False,
                  american=True, scheme="rannacher", solver=0, variable_target=None, max_steps=100000,
-                 E=0, dividend=None, dividend_kind="cash", dividend_first=False, exercise=False):
+                 E=0, dividend=None, dividend_kind="cash", dividend_first=False, exercise=False, event=None):
     """The vanilla_options.cpp wiring on the oracle.  variable_target: ReverseVariableStepper(0, T,
     T / n_steps, target) as vanilla_options.cpp:52-58 builds it.  E > 0: events at T e / E on top of the
     penalty method — the README's discrete dividends (README.md:357-375) and / or the exercise transform."""
@@ -209,10 +220,29 @@ def american_put(K, r, vol, T, n_steps, refine_times, q=0.0, S0=None, call=False
     out = sweep(S, lo, di, up, payoff, T, steps, n, scheme=scheme,
                 american=american, obstacle=payoff, solver=solver,
                 event_obstacle=(K - S) if (E > 0 and exercise) else None,
-                dividend=None if (E == 0 or dividend is None) else (dividend_kind, dividend, dividend_first))
+                dividend=None if (E == 0 or dividend is None) else (dividend_kind, dividend, dividend_first), event=event)
     out["S"] = S
     out["n_steps"] = n
     return out
+
+
+def glwb_event(E, bonus=.06, GQ=5.):
+    """The three-way choice of examples/experimental/glwb.cpp:84-121 (bonus / withdrawal / surrender) as an event
+    program, with the per-event survival and penalty rates oracle/shim/ref_driver.cpp uses (event=glwb):
+        best = (1 + bonus) V(S / (1 + bonus));  tmp = V(max(S - GQ, 0)) + R GQ;  if(S > GQ) tmp = R (GQ + (1 - pen)(S - GQ))
+    consts: [1 + bonus, GQ, 0, 1, -inf]; params per event: [R_e, pen_e]."""
+    OPS = {"end": 0, "S": 1, "const": 2, "param": 3, "add": 4, "sub": 5, "mul": 6, "div": 7, "max": 8, "min": 9,
+           "neg": 10, "V": 11, "gt": 12, "select": 13}
+    toks = [("const", 0), "S", ("const", 0), "div", "V", "mul",                                  # (1 + b) V(S / (1 + b))
+            "S", ("const", 1), "sub", ("const", 2), "max", "V", ("param", 0), ("const", 1), "mul", "add", "max",
+            "S", ("const", 1), "gt",                                                             # S > GQ ?
+            ("param", 0), ("const", 1), ("const", 3), ("param", 1), "sub", "S", ("const", 1), "sub", "mul", "add", "mul",
+            ("const", 4), "select", "max", "end"]
+    words = []
+    for t in toks:
+        words += [OPS[t[0]], t[1]] if isinstance(t, tuple) else [OPS[t]]
+    params = np.array([[1. - .01 * (e + 1), max(.03 - .01 * e, 0.)] for e in range(E)])
+    return dict(program=np.array(words, dtype=np.int32), consts=[1. + bonus, GQ, 0., 1., -np.inf], params=params)
 
 
 def forward_option(K, r, vol, T, n_steps, refine_times, q=0.0, call=False, american=False, scheme="rannacher",

@@ -598,6 +598,37 @@ static void bdf_coefficients(int k, const double *g, double *c, double *hh) {
  * saw an active set different from the one of the previous solve */
 long qpo_diag_solves = 0, qpo_diag_mask_changes = 0;
 
+/* One evaluation of an event program at price S (Event<1>::_doEvent, Core/Event.hpp:100-112: the user's
+ * transform called with the interpolant of the solution before the event). */
+static double event_program_eval(const qpo_problem *p, const double *params, int n, const double *vold, double S) {
+	double st[16];
+	int sp = 0, pc = 0;
+	for(;;) {
+		const int op = p->event_program[pc++];
+		double a, b;
+		if(op == 0) break;
+		switch(op) {
+		case 1: st[sp++] = S; break;
+		case 2: st[sp++] = p->event_consts[p->event_program[pc++]]; break;
+		case 3: st[sp++] = params[p->event_program[pc++]]; break;
+		case 10: st[sp - 1] = -st[sp - 1]; break;
+		case 11: st[sp - 1] = qpo_interp(n, p->S, vold, st[sp - 1]); break;
+		case 13: sp -= 2; st[sp - 1] = st[sp - 1] != 0. ? st[sp] : st[sp + 1]; break;
+		default:
+			b = st[--sp]; a = st[sp - 1];
+			if(op == 4) a = a + b;
+			else if(op == 5) a = a - b;
+			else if(op == 6) a = a * b;
+			else if(op == 7) a = a / b;
+			else if(op == 8) a = b > a ? b : a;
+			else if(op == 9) a = b < a ? b : a;
+			else a = a > b ? 1. : 0.;
+			st[sp - 1] = a;
+		}
+	}
+	return st[sp - 1];
+}
+
 /* time elapsed between a history time and the new implicit time (Rannacher.hpp:17-21) */
 #define LAPSE(then, now) (p->forward ? (now) - (then) : (then) - (now))
 
@@ -633,6 +664,7 @@ int qpo_sweep_1d(const qpo_problem *p, double *V, int *inner,
 	/* stepper history: times of iterand(0), iterand(1) */
 	double time1 = 0., time0 = 0.;
 	int hist = 0;          /* number of iterands in the stepper's ring */
+	int events_popped = 0; /* user events applied so far */
 	int initialized = 0;   /* IterativeMethod.hpp:1150-1157 */
 	/* node state machines */
 	int ran_phase = 1;     /* Rannacher: 1,2 = implicit steps, 3 = first CN, 4 = CN */
@@ -921,6 +953,16 @@ int qpo_sweep_1d(const qpo_problem *p, double *V, int *inner,
 			 * IterativeMethod.hpp:1340-1352): the event add()ed last goes first. */
 			for(k = 0; k < st->user_events; ++k) {
 				int op;
+				if(p->event_program) {
+					/* events pop in descending time (forward: ascending): the e-th row of the parameter table */
+					const int e = p->forward ? events_popped : p->n_events - 1 - events_popped;
+					++events_popped;
+					memcpy(x, v1, sizeof(double) * (size_t)n);
+					for(i = 0; i < n; ++i) {
+						v1[i] = event_program_eval(p, p->event_params + (size_t)e * p->n_event_params, n, x, p->S[i]);
+					}
+					continue;
+				}
 				for(op = 0; op < 2; ++op) {
 					const int is_dividend = (op == 0) == (p->dividend_first != 0);
 					if(is_dividend && p->dividend_kind != QPO_DIVIDEND_NONE) {

@@ -117,6 +117,14 @@ typedef struct {
 	 * reference's stepper reads a history slot that clear() has emptied). */
 	double variable_target, variable_scale, variable_dt0;
 	int *steps_taken;
+	/* general Event<1> transforms (Core/Event.hpp:60-184) as a postfix program over a stack, the op codes of
+	 * include/qpde_b200.h (QPDE_EV_*) restated here: 0 END, 1 S, 2 CONST i, 3 PARAM i, 4 ADD, 5 SUB, 6 MUL, 7 DIV,
+	 * 8 MAX (b > a ? b : a), 9 MIN, 10 NEG, 11 V (interpolant of the pre-event solution), 12 GT, 13 SELECT.
+	 * NULL = the tagged transforms above.  event_params: [n_events][n_event_params], row e for the event at
+	 * T e / E (reverse) or T (e + 1) / E (forward). */
+	const int *event_program;
+	const double *event_consts, *event_params;
+	int n_events, n_event_params;
 	/* 1: the forward-time classes (TimeIteration<true>, ForwardConstantStepper, ForwardRannacher ...):
 	 * v0 is the condition at t = 0, `steps` comes from qpo_schedule_forward.  Constant steps only. */
 	int forward;

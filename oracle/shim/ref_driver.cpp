@@ -108,6 +108,10 @@ std::vector<double> nodes(const G &grid) {
 // Crank-Nicolson, BDF1 or BDF2 time stepping, penalty method for American
 ////////////////////////////////////////////////////////////////////////////////
 
+// per-event parameters of the GLWB-like event (tests hand the same numbers to the device as event_params)
+static Real glwbSurvival(int e) { return 1. - .01 * (e + 1); }
+static Real glwbPenalty(int e) { const Real p = .03 - .01 * e; return p > 0. ? p : 0.; }
+
 int runVanilla(const Args &a) {
 	const Real K = num(a, "K", 100.), S0 = num(a, "S0", K);
 	const Real r = num(a, "r", .04), vol = num(a, "vol", .2);
@@ -138,6 +142,8 @@ int runVanilla(const Args &a) {
 	const std::string dividendKind = str(a, "dividend_kind", "none");
 	const bool dividendFirst = integer(a, "dividend_first", 0) != 0;  // first in the reverse sweep = add()ed last
 	const bool withExercise = integer(a, "exercise", 0) != 0;
+	const std::string eventKind = str(a, "event", "tagged");
+	const Real bonus = num(a, "bonus", .06), GQ = num(a, "GQ", 5.);
 	auto exercise = [K] (const Interpolant1 &V, Real S) {
 		return max(V(S), K - S);
 	};
@@ -158,7 +164,27 @@ int runVanilla(const Args &a) {
 
 		// README.md:357-375 on top of the penalty method: E event times T e / E with a dividend transform
 		// and / or the exercise transform, add()ed in the order the arguments ask for
-		if(E > 0 && constantStepper) {
+		if(E > 0 && constantStepper && eventKind == "glwb") {
+			// the three-way choice of examples/experimental/glwb.cpp:84-121 (non-withdrawal with bonus, withdrawal,
+			// surrender) as the event at every T e / E, with per-event survival and penalty rates
+			for(int e = 0; e < E; ++e) {
+				const Real Rn = glwbSurvival(e), pen = glwbPenalty(e);
+				auto event = [=] (const Interpolant1 &V, Real S) {
+					Real best = (1. + bonus) * V(S / (1. + bonus));
+					{
+						const Real S_plus = max(S - GQ, 0.);
+						const Real tmp = V(S_plus) + Rn * GQ;
+						if(tmp > best) best = tmp;
+					}
+					if(S > GQ) {
+						const Real tmp = Rn * (GQ + (1. - pen) * (S - GQ));
+						if(tmp > best) best = tmp;
+					}
+					return best;
+				};
+				constantStepper->add(T / E * e, event, grid);
+			}
+		} else if(E > 0 && constantStepper) {
 			auto addDividends = [&] () {
 				for(int e = 0; e < E; ++e) {
 					if(dividendKind == "cash") constantStepper->add(T / E * e, cashDividend, grid);

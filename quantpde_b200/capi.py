@@ -13,7 +13,7 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "lib", "libqpde_b200.so")
 
-ABI_VERSION = 4
+ABI_VERSION = 5
 
 OK, ERR_INVALID, ERR_CUDA, ERR_NO_DEVICE, ERR_NOT_CONVERGED, ERR_UNSUPPORTED = 0, -1, -2, -3, -4, -5
 
@@ -23,6 +23,22 @@ PAYOFF = {"array": 0, "put": 1, "call": 2, "digital_put": 3, "digital_call": 4,
 DIVIDEND = {None: 0, "none": 0, "cash": 1, "proportional": 2}
 VOL = {"const": 0, "inverse_s": 1, "nodes": 2}
 KERNEL = {"auto": 0, "interleaved": 1, "resident": 2}
+# event program op codes (QPDE_EV_*)
+EV = {"end": 0, "S": 1, "const": 2, "param": 3, "add": 4, "sub": 5, "mul": 6, "div": 7, "max": 8, "min": 9,
+      "neg": 10, "V": 11, "gt": 12, "select": 13}
+
+
+def event_program(*tokens):
+    """Assembles an event program from tokens: op names ("S", "add", "V", ...), ("const", i) and ("param", i)."""
+    words = []
+    for t in tokens:
+        if isinstance(t, tuple):
+            words += [EV[t[0]], int(t[1])]
+        else:
+            words.append(EV[t])
+    if not words or words[-1] != EV["end"]:
+        words.append(EV["end"])
+    return np.array(words, dtype=np.int32)
 KERNEL_NAME = {v: k for k, v in KERNEL.items()}
 
 OUT_V, OUT_S, OUT_VALUE, OUT_STEPS, OUT_INNER_TOTAL, OUT_INNER, OUT_ACTIVE, OUT_STATUS = (
@@ -60,7 +76,9 @@ class Batch(C.Structure):
         ("controls", _dp), ("controls_stride", C.c_int64),
         ("jump_lambda", _dp), ("jump_kappa", _dp), ("jump_x0", _dp), ("jump_dx", _dp),
         ("jump_weights", _dp), ("jump_weights_stride", C.c_int64),
-        ("n_fft", C.c_int32), ("reserved2", C.c_int32),
+        ("n_fft", C.c_int32), ("event_program_length", C.c_int32),
+        ("event_program", C.POINTER(C.c_int32)), ("event_consts", _dp), ("event_params", _dp),
+        ("event_params_stride", C.c_int64), ("n_event_consts", C.c_int32), ("n_event_params", C.c_int32),
         ("kernel", C.c_int32), ("outputs", C.c_int32),
     ]
 
@@ -378,7 +396,7 @@ class BatchSpec:
                  n_exercise=0, exercise="k_minus_s", spot=None, tolerance=1e-6, scale=1.0,
                  penalty_tolerance=1e-6, max_inner=100, kernel="auto", outputs=OUT_ALL,
                  n_contracts=None, controls=None, policy_max=False, jump=None, dividend=None,
-                 variable_target=None, variable_scale=1.0, max_steps=0, forward=False):
+                 variable_target=None, variable_scale=1.0, max_steps=0, forward=False, event=None):
         axis = np.ascontiguousarray(axis, dtype=np.float64)
         if n_contracts is None:
             n_contracts = axis.shape[0] if axis.ndim == 2 else len(np.atleast_1d(strike))
@@ -419,6 +437,17 @@ class BatchSpec:
             b.variable_scale = float(variable_scale)
         b.n_exercise = int(n_exercise)
         b.exercise_kind = PAYOFF[exercise]
+        if event is not None:
+            # event = dict(program=int32 words, consts=[..], params=[n_exercise][n_params] or [C][n_exercise][n_params])
+            prog = np.ascontiguousarray(event["program"], dtype=np.int32)
+            consts = np.ascontiguousarray(event.get("consts", []), dtype=np.float64)
+            params = np.ascontiguousarray(event.get("params", np.zeros((int(n_exercise), 0))), dtype=np.float64)
+            self.keep += [prog, consts, params]
+            b.event_program = prog.ctypes.data_as(C.POINTER(C.c_int32))
+            b.event_program_length = len(prog)
+            b.event_consts, b.n_event_consts = consts.ctypes.data_as(_dp), len(consts)
+            b.event_params, b.n_event_params = params.ctypes.data_as(_dp), params.shape[-1]
+            b.event_params_stride = params.shape[1] * params.shape[2] if params.ndim == 3 else 0
         if dividend is not None:
             # dividend = dict(kind="cash" | "proportional", amount=[C] or scalar, first=bool)
             b.dividend_kind = DIVIDEND[dividend["kind"]]

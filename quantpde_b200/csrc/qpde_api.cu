@@ -436,6 +436,20 @@ static int plan_create_impl(qpde_handle *h, const qpde_bs1d_batch *in,
 	if(in->n_exercise > 0 && in->exercise_kind != QPDE_EXERCISE_NONE && !is_generator(in->exercise_kind)) {
 		return fail(h, QPDE_ERR_INVALID, "exercise_kind must be a generator or QPDE_EXERCISE_NONE");
 	}
+	if(in->event_program_length != 0 || in->event_program) {
+		if(in->n_exercise < 1) return fail(h, QPDE_ERR_INVALID, "an event program needs n_exercise >= 1 event times");
+		if(in->exercise_kind != QPDE_EXERCISE_NONE || in->dividend_kind != QPDE_DIVIDEND_NONE) {
+			return fail(h, QPDE_ERR_INVALID, "an event program takes the place of the tagged transforms: exercise_kind must be QPDE_EXERCISE_NONE and dividend_kind QPDE_DIVIDEND_NONE");
+		}
+		if(in->n_event_consts < 0 || in->n_event_params < 0 || (in->n_event_consts > 0 && !in->event_consts)
+				|| (in->n_event_params > 0 && !in->event_params)) return fail(h, QPDE_ERR_INVALID, "event program: constants / parameters missing");
+		if(in->event_params_stride != 0 && in->event_params_stride < (long long)in->n_exercise * in->n_event_params) {
+			return fail(h, QPDE_ERR_INVALID, "event_params_stride < n_exercise * n_event_params");
+		}
+		const int bad = event_program_check(in->event_program, in->event_program_length, in->n_event_consts, in->n_event_params);
+		if(bad) return fail(h, QPDE_ERR_INVALID, "event program is malformed (check %d: unknown op, operand out of range, or stack depth outside 1 .. %d)", bad, QPDE_EV_MAX_STACK);
+		if(in->n_controls != 0 || in->jump_lambda) return fail(h, QPDE_ERR_UNSUPPORTED, "event programs with policy iteration or a jump term are not supported");
+	}
 	if(in->dividend_kind != QPDE_DIVIDEND_NONE) {
 		if(in->dividend_kind != QPDE_DIVIDEND_CASH && in->dividend_kind != QPDE_DIVIDEND_PROPORTIONAL) return fail(h, QPDE_ERR_INVALID, "unknown dividend_kind");
 		if(!in->dividend || in->n_exercise < 1) return fail(h, QPDE_ERR_INVALID, "dividends need the amounts and n_exercise >= 1 event times");
@@ -508,6 +522,22 @@ static int plan_create_impl(qpde_handle *h, const qpde_bs1d_batch *in,
 	if(in->spot) QPDE_TRY(upload_vec(p, in->spot, C, &b.spot));
 	if(in->variable_target) { QPDE_TRY(upload_vec(p, in->variable_target, C, &b.variable_target)); b.variable_scale = in->variable_scale; }
 	if(in->dividend_kind != QPDE_DIVIDEND_NONE) QPDE_TRY(upload_vec(p, in->dividend, C, &b.dividend));
+	if(in->event_program) {
+		// program words (as doubles' worth of ints), constants and the per-event parameter tables
+		int *code = nullptr;
+		QPDE_TRY(dev_alloc(p, &code, (size_t)in->event_program_length));
+		if(cudaMemcpyAsync(code, in->event_program, sizeof(int) * in->event_program_length, cudaMemcpyHostToDevice, h->stream) != cudaSuccess) {
+			qpde_bs1d_plan_destroy(p);
+			return fail(h, QPDE_ERR_CUDA, "event program upload failed");
+		}
+		b.event_program = code;
+		const double zero = 0.;
+		QPDE_TRY(upload_vec(p, in->n_event_consts > 0 ? in->event_consts : &zero, in->n_event_consts > 0 ? in->n_event_consts : 1, &b.event_consts));
+		const int row = in->n_exercise * in->n_event_params;
+		if(row > 0) QPDE_TRY(upload_rows(p, in->event_params, in->event_params_stride, C, row, &b.event_params, &b.event_params_stride));
+		else { QPDE_TRY(upload_vec(p, &zero, 1, &b.event_params)); b.event_params_stride = 0; }
+		b.n_event_params = in->n_event_params;
+	}
 	if(p->jump) {
 		b.n_fft = in->n_fft;
 		QPDE_TRY(upload_vec(p, in->jump_lambda, C, &b.jump_lambda));

@@ -368,6 +368,34 @@ k_interleaved_sweep(DeviceBatch b, InterleavedWork w, DeviceResult out) {
 			}
 			// Events at one time go in descending add() order (IterativeMethod.hpp:1340-1352)
 			for(int ue = 0; ue < st.user_events; ++ue) {
+				if(b.event_program) {
+					// a general Event<1> transform (QPDE_EV_* program): V is the interpolant of the pre-event
+					// solution, so that goes to the right-hand-side array first (free between steps)
+					const int ev_index = b.forward ? rp.e - st.user_events + ue : rp.e + st.user_events - ue;
+					const double *const ev_params = b.event_params + (size_t)c * b.event_params_stride + (size_t)ev_index * b.n_event_params;
+					const double *S = w.S + base;
+					double *const old = w.lb + base;
+					for(int i = 0; i < N; ++i) old[(size_t)i * C] = x[(size_t)i * C];
+					const double Sfirst = S[0], Slast = S[(size_t)(N - 1) * C];
+					auto V_interp = [&] (double at) -> double {
+						// linearInterpolationData + PiecewiseLinear::interpolate (Core/Interpolant.hpp:153-181,331-374)
+						int k; double wgt;
+						if(at <= Sfirst) { k = 0; wgt = 1.; }
+						else if(at >= Slast) { k = N - 2; wgt = 0.; }
+						else {
+							int lo = 0, hi = N - 2;
+							while(lo < hi) { const int mid = (lo + hi + 1) >> 1; if(S[(size_t)mid * C] <= at) lo = mid; else hi = mid - 1; }
+							k = lo;
+							wgt = (S[(size_t)(k + 1) * C] - at) / (S[(size_t)(k + 1) * C] - S[(size_t)k * C]);
+						}
+						double sum = 0.;
+						if(wgt > DBL_EPSILON) sum += wgt * old[(size_t)k * C];
+						if(1. - wgt > DBL_EPSILON) sum += (1. - wgt) * old[(size_t)(k + 1) * C];
+						return sum;
+					};
+					for(int i = 0; i < N; ++i) x[(size_t)i * C] = event_eval(b.event_program, b.event_consts, ev_params, S[(size_t)i * C], V_interp);
+					continue;
+				}
 				for(int op = 0; op < 2; ++op) {
 					const bool is_dividend = (op == 0) == (b.dividend_first != 0);
 					if(is_dividend && b.dividend_kind != QPDE_DIVIDEND_NONE) {

@@ -512,7 +512,7 @@ bool interleaved_tma_supported(const DeviceBatch &b) {
 	// algorithmic for the plain-load sweep); below a few tiles per pass it is all prologue.
 	int min_nodes = 32;
 	if(const char *e = std::getenv("QPDE_TMA_MIN_NODES")) { const int v = std::atoi(e); if(v >= 2) min_nodes = v; }   // tuning knob
-	return b.n_controls == 0 && b.N >= min_nodes && b.scheme <= QPDE_SCHEME_BDF2;
+	return b.n_controls == 0 && b.N >= min_nodes && b.scheme <= QPDE_SCHEME_BDF2 && !b.event_program;   // event programs: plain-load sweep
 }
 
 bool interleaved_tma_prepare(InterleavedTma *t, double *block, long long rows, int arrays, std::string *error) {

@@ -38,6 +38,9 @@ struct DeviceBatch {
 	const double *controls; long long controls_stride;
 	const double *jump_lambda, *jump_kappa, *jump_x0, *jump_dx, *jump_weights;
 	long long jump_weights_stride; int n_fft;
+	// general events (QPDE_EV_* programs); event_program == nullptr: the tagged exercise / dividend transforms
+	const int *event_program; const double *event_consts, *event_params;
+	long long event_params_stride; int n_event_params;
 };
 
 // Device output buffers (contract-major); any pointer may be null.

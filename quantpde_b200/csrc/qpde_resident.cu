@@ -587,19 +587,24 @@ k_resident_sweep(DeviceBatch b, DeviceResult out) {
 				for(int ue = 0; ue < st.user_events; ++ue) {
 					for(int op = 0; op < 2; ++op) {
 						const bool is_dividend = (op == 0) == (b.dividend_first != 0);
-						if(CL == 1 && is_dividend && b.dividend_kind != QPDE_DIVIDEND_NONE) {   // reads any node: one CTA only
+						const bool program = op == 0 && b.event_program != nullptr;            // a general Event<1> transform
+						if(CL == 1 && ((is_dividend && b.dividend_kind != QPDE_DIVIDEND_NONE) || program)) {   // reads any node: one CTA only
 							// Event<1>::_doEvent with V(max(S - D, 0)) or V((1 - D) S): the solution goes to
 							// shared memory (sm_lb is free between steps), every node reads its two
 							// neighbours of the shifted price (Core/Interpolant.hpp:153-181,331-374).
 							// Fixed-trip bisection: no divergence in front of the solver's shuffles.
-							const double D = b.dividend[cidx];
+							const double D = program ? 0. : b.dividend[cidx];
+							// the parameters of this event: user events are popped in descending (forward: ascending) index
+							const int ev_index = b.forward ? rp.e - st.user_events + ue : rp.e + st.user_events - ue;
+							const double *const ev_params = program
+								? b.event_params + (size_t)cidx * b.event_params_stride + (size_t)ev_index * b.n_event_params : nullptr;
 #pragma unroll
 							for(int j = 0; j < M; ++j) sm_lb[j * P + tid] = x[j];
 							__syncthreads();
 							auto V_at = [&] (int i) -> double { return i >= n_main ? sm.tail.x : sm_lb[(i % M) * P + (i / M)]; };
 							const double Sfirst = S_at(0), Slast = S_at(N - 1);
-							auto shifted = [&] (double Si) -> double {
-								double at = b.dividend_kind == QPDE_DIVIDEND_CASH ? (Si - D > 0. ? Si - D : 0.) : (1. - D) * Si;
+							// PiecewiseLinear::interpolate of the pre-event solution at any price
+							auto V_interp = [&] (double at) -> double {
 								int lo = 0, hi = N - 2;
 								for(int it = 0; it < 13; ++it) {          // 2^13 > any supported N
 									const int mid = (lo + hi + 1) >> 1;
@@ -614,6 +619,10 @@ k_resident_sweep(DeviceBatch b, DeviceResult out) {
 								if(wgt > DBL_EPSILON) sum += wgt * V_at(idx);
 								if(1. - wgt > DBL_EPSILON) sum += (1. - wgt) * V_at(idx + 1);
 								return sum;
+							};
+							auto shifted = [&] (double Si) -> double {
+								if(program) return event_eval(b.event_program, b.event_consts, ev_params, Si, V_interp);
+								return V_interp(b.dividend_kind == QPDE_DIVIDEND_CASH ? (Si - D > 0. ? Si - D : 0.) : (1. - D) * Si);
 							};
 							double xn[M];
 #pragma unroll
@@ -743,7 +752,7 @@ bool resident_supported(const DeviceBatch &b) {
 	if(b.N < 10) return false;
 	if(b.scheme > QPDE_SCHEME_BDF2) return false;   // BDF3 .. BDF6: INTERLEAVED family
 	if(!pick_geometry(b.N, &M, &PT, &CL)) return false;
-	if(CL > 1 && (b.variable_target || b.dividend_kind != QPDE_DIVIDEND_NONE)) return false; // one-CTA features
+	if(CL > 1 && (b.variable_target || b.dividend_kind != QPDE_DIVIDEND_NONE || b.event_program)) return false; // one-CTA features
 	if(b.american && b.n_exercise > 0 && (CL > 1 || (M == 4 && PT == 512))) return false; // penalty + events: one CTA per contract, the default geometries
 	if(b.n_controls != 0 && b.n_controls != 2) return false; // more control values: INTERLEAVED family
 	if(b.variable_target && !((M == 8 && PT == 32) || (M == 8 && PT == 64) || (M == 8 && PT == 256))) return false; // no room for V^n: INTERLEAVED family

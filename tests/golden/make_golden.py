@@ -166,6 +166,16 @@ for name, kw in (
     base = dict(K=100.0, r=0.04, vol=0.2, T=1.0)
     base.update(kw)
     CASES.append((name, "forward", base))
+# general Event<1> transforms: the three-way choice of examples/experimental/glwb.cpp:84-121 (bonus /
+# withdrawal / surrender, per-event survival and penalty rates) as the event of a Black-Scholes sweep
+# (qpde_ref vanilla event=glwb); the device evaluates it as a QPDE_EV_* program
+for name, kw in (("event_glwb_bdf2_k2", dict(american=0, steps=50, refine=2, E=5, scheme="bdf2")),
+                 ("event_glwb_american_rannacher_k3", dict(american=1, steps=80, refine=3, E=4, scheme="rannacher")),
+                 ("event_glwb_cn_k2", dict(american=0, steps=64, refine=2, E=8, scheme="cn", vol=0.3, K=90.0)),
+                 ("event_glwb_bdf2_k6", dict(american=0, steps=200, refine=6, E=10, scheme="bdf2"))):
+    base = dict(K=100.0, r=0.04, vol=0.2, T=1.0, event="glwb")
+    base.update(kw)
+    CASES.append((name, "vanilla", base))
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "reference_cases.npz")
 # cases already in the file with the same arguments are kept (pass --all to re-run everything)
 have = np.load(GOLDEN, allow_pickle=False) if os.path.exists(GOLDEN) and "--all" not in sys.argv else None

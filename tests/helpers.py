@@ -50,7 +50,8 @@ def run_oracle_case(po, mode, kw):
                                american=bool(kw["american"]), scheme=kw.get("scheme", "rannacher"),
                                variable_target=kw.get("variable_target"), E=kw.get("E", 0),
                                dividend=kw.get("dividend"), dividend_kind=kw.get("dividend_kind", "cash"),
-                               dividend_first=bool(kw.get("dividend_first", 0)), exercise=bool(kw.get("exercise", 0)))
+                               dividend_first=bool(kw.get("dividend_first", 0)), exercise=bool(kw.get("exercise", 0)),
+                               event=po.glwb_event(kw["E"]) if kw.get("event") == "glwb" else None)
     if mode == "forward":
         return po.forward_option(kw["K"], kw["r"], kw["vol"], kw["T"], kw["steps"], kw["refine"], call=bool(kw.get("call", 0)),
                                  american=bool(kw["american"]), scheme=kw["scheme"], alpha=kw.get("alpha", 0.0),
@@ -82,7 +83,8 @@ def spec_for_case(qpde, po, mode, kw, kernel="auto", copies=1):
             variable_target=kw.get("variable_target"), max_steps=4000 if "variable_target" in kw else 0,
             n_exercise=kw.get("E", 0), exercise="k_minus_s" if kw.get("exercise", 0) else "none",
             dividend=None if "dividend" not in kw else dict(kind=kw["dividend_kind"], amount=kw["dividend"],
-                                                          first=bool(kw.get("dividend_first", 0))))
+                                                          first=bool(kw.get("dividend_first", 0))),
+            event=po.glwb_event(kw["E"]) if kw.get("event") == "glwb" else None)
     if mode == "forward":
         K = kw["K"]
         axis = po.axis_union(po.special_axis() * K, po.special_axis() * K)
