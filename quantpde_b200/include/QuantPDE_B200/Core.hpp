@@ -446,6 +446,65 @@ struct Dividend {
 	static Dividend proportional(Real D) { return Dividend(QPDE_DIVIDEND_PROPORTIONAL, D); }
 };
 
+// A general event transform — what the reference takes as a lambda
+//     [..] (const Interpolant1 &V, Real S) { return ...; }            (Core/Event.hpp:60-184)
+// — written as an expression over S, V(.), constants and per-event parameters.  A lambda cannot cross the
+// C ABI; an expression can: it is lowered to the postfix program of include/qpde_b200.h (QPDE_EV_*) and
+// evaluated at every node inside the sweep.  Every operator is one IEEE operation, so an expression that
+// spells the lambda in its order reproduces it bit for bit.  Example (examples/experimental/glwb.cpp:84-121):
+//     EventExpression S = EventExpression::S(), R = EventExpression::param(0), pen = EventExpression::param(1);
+//     auto best = max(max(c(1. + bonus) * V(S / c(1. + bonus)), V(max(S - c(GQ), c(0.))) + R * c(GQ)),
+//                     select(S > c(GQ), R * (c(GQ) + (c(1.) - pen) * (S - c(GQ))), c(-infinity)));
+//     stepper.addEvents(E, best, table);          // table[e] = { R_e, pen_e } for the event at T e / E
+class EventExpression {
+	std::vector<int32_t> code;          // postfix words; constants are interned into consts at lowering
+	std::vector<Real> consts;
+	static EventExpression binary(const EventExpression &a, const EventExpression &b, int op) {
+		EventExpression r;
+		r.consts = a.consts;
+		r.code = a.code;
+		for(size_t k = 0; k < b.code.size(); ++k) {
+			r.code.push_back(b.code[k]);
+			if(b.code[k] == QPDE_EV_CONST) { r.consts.push_back(b.consts[(size_t)b.code[k + 1]]); r.code.push_back((int32_t)r.consts.size() - 1); ++k; }
+			else if(b.code[k] == QPDE_EV_PARAM) { r.code.push_back(b.code[k + 1]); ++k; }
+		}
+		r.code.push_back(op);
+		return r;
+	}
+	static EventExpression unary(const EventExpression &a, int op) { EventExpression r = a; r.code.push_back(op); return r; }
+public:
+	static EventExpression S() { EventExpression r; r.code.push_back(QPDE_EV_S); return r; }
+	static EventExpression constant(Real v) { EventExpression r; r.consts.push_back(v); r.code.push_back(QPDE_EV_CONST); r.code.push_back(0); return r; }
+	static EventExpression param(int index) { EventExpression r; r.code.push_back(QPDE_EV_PARAM); r.code.push_back(index); return r; }
+	friend EventExpression operator+(const EventExpression &a, const EventExpression &b) { return binary(a, b, QPDE_EV_ADD); }
+	friend EventExpression operator-(const EventExpression &a, const EventExpression &b) { return binary(a, b, QPDE_EV_SUB); }
+	friend EventExpression operator*(const EventExpression &a, const EventExpression &b) { return binary(a, b, QPDE_EV_MUL); }
+	friend EventExpression operator/(const EventExpression &a, const EventExpression &b) { return binary(a, b, QPDE_EV_DIV); }
+	friend EventExpression operator-(const EventExpression &a) { return unary(a, QPDE_EV_NEG); }
+	friend EventExpression operator>(const EventExpression &a, const EventExpression &b) { return binary(a, b, QPDE_EV_GT); }
+	// max(a, b) = b > a ? b : a, the "if(tmp > best) best = tmp" of the reference's examples
+	friend EventExpression max(const EventExpression &a, const EventExpression &b) { return binary(a, b, QPDE_EV_MAX); }
+	friend EventExpression min(const EventExpression &a, const EventExpression &b) { return binary(a, b, QPDE_EV_MIN); }
+	// the interpolant of the solution before the event, at any price
+	friend EventExpression V(const EventExpression &at) { return unary(at, QPDE_EV_V); }
+	friend EventExpression select(const EventExpression &condition, const EventExpression &yes, const EventExpression &no) {
+		return binary(binary(condition, yes, -1), no, QPDE_EV_SELECT);      // -1: a join without an op word (removed below)
+	}
+	// the program words (END appended) and the constants they index
+	void lower(std::vector<int32_t> &words, std::vector<Real> &constants) const {
+		words.clear();
+		for(size_t k = 0; k < code.size(); ++k) {
+			if(code[k] == -1) continue;
+			words.push_back(code[k]);
+			if(code[k] == QPDE_EV_CONST || code[k] == QPDE_EV_PARAM) { words.push_back(code[k + 1]); ++k; }
+		}
+		words.push_back(QPDE_EV_END);
+		constants = consts;
+	}
+	bool empty() const { return code.empty(); }
+};
+inline EventExpression c(Real v) { return EventExpression::constant(v); }
+
 // ReverseConstantStepper(t0, T, dt) — Core/Stepper.hpp:27-36
 class ReverseConstantStepper : public Iteration {
 	Real t0, T, dt;
@@ -454,6 +513,8 @@ class ReverseConstantStepper : public Iteration {
 	Payoff exercise;
 	Dividend dividend_;
 	bool dividendAddedFirst;
+	EventExpression eventExpression_;
+	std::vector<std::vector<Real>> eventTable_;
 protected:
 	Real vTarget, vScale;      // > 0: ReverseVariableStepper
 	int stepLimit_;
@@ -478,6 +539,17 @@ public:
 		if(nExercise > 0 && nExercise != E) throw std::invalid_argument("QuantPDE_B200: exercise and dividend dates must coincide");
 		nDividend = E; dividend_ = d; dividendAddedFirst = nExercise == 0;
 	}
+
+	// stepper.add(T / E * e, event, grid) for e = 0 .. E-1 (forward: e = 1 .. E) with a general transform:
+	// table[e] holds the parameters param(0), param(1), ... of the event at that time (may be empty rows)
+	void addEvents(int E, EventExpression event, std::vector<std::vector<Real>> table = {}) {
+		if(nExercise > 0 || nDividend > 0) throw std::invalid_argument("QuantPDE_B200: a general event takes the place of the tagged exercise / dividend events");
+		if(!table.empty() && (int)table.size() != E) throw std::invalid_argument("QuantPDE_B200: one parameter row per event time");
+		nExercise = E; exercise = Payoff(QPDE_EXERCISE_NONE, 0.);
+		eventExpression_ = std::move(event); eventTable_ = std::move(table);
+	}
+	const EventExpression &eventExpression() const { return eventExpression_; }
+	const std::vector<std::vector<Real>> &eventTable() const { return eventTable_; }
 
 	Real expiry() const { return T; }
 	Real timestep() const { return dt; }
@@ -643,17 +715,17 @@ public:
 			if(variableSteps) vTargets.push_back(it.stepper->variableTarget());
 			K[c] = it.payoff.kind() != QPDE_PAYOFF_ARRAY ? it.payoff.strike()
 				: (american && p->obstacle.kind() != QPDE_PAYOFF_ARRAY ? p->obstacle.strike()
-				: (nEx > 0 ? it.stepper->exercisePayoff().strike() : 0.));
+				: (nEx > 0 && it.stepper->exercisePayoff().kind() > QPDE_PAYOFF_ARRAY ? it.stepper->exercisePayoff().strike() : 0.));
 			// one strike per contract crosses the C ABI: every generator of the tree must use it
 			if(it.payoff.kind() != QPDE_PAYOFF_ARRAY) {
 				if((american && p->obstacle.kind() != QPDE_PAYOFF_ARRAY && p->obstacle.strike() != K[c])
-						|| (nEx > 0 && it.stepper->exercisePayoff().kind() != QPDE_PAYOFF_ARRAY
+						|| (nEx > 0 && it.stepper->exercisePayoff().kind() > QPDE_PAYOFF_ARRAY
 							&& it.stepper->exercisePayoff().strike() != K[c])) {
 					throw std::invalid_argument("QuantPDE_B200: payoff, obstacle and exercise generators of one "
 						"problem must share their strike (pass the obstacle as an array otherwise)");
 				}
 			} else if(american && p->obstacle.kind() != QPDE_PAYOFF_ARRAY && nEx > 0
-					&& it.stepper->exercisePayoff().kind() != QPDE_PAYOFF_ARRAY
+					&& it.stepper->exercisePayoff().kind() > QPDE_PAYOFF_ARRAY
 					&& it.stepper->exercisePayoff().strike() != K[c]) {
 				throw std::invalid_argument("QuantPDE_B200: obstacle and exercise generators of one problem must share their strike");
 			}
@@ -680,6 +752,27 @@ public:
 		b.n_exercise = nEv;
 		b.exercise_kind = nEx > 0 ? items[0].stepper->exercisePayoff().kind() : QPDE_EXERCISE_NONE;
 		if(dividends) { b.dividend_kind = divKind; b.dividend_first = divFirst ? 1 : 0; b.dividend = divAmount.data(); }
+		std::vector<int32_t> evWords; std::vector<Real> evConsts, evParams;
+		if(!items[0].stepper->eventExpression().empty()) {
+			items[0].stepper->eventExpression().lower(evWords, evConsts);
+			const size_t width = items[0].stepper->eventTable().empty() ? 0 : items[0].stepper->eventTable()[0].size();
+			for(int cc = 0; cc < C; ++cc) {
+				std::vector<int32_t> w; std::vector<Real> k;
+				items[cc].stepper->eventExpression().lower(w, k);
+				const auto &tab = items[cc].stepper->eventTable();
+				if(w != evWords || k != evConsts || (tab.empty() ? 0 : tab[0].size()) != width) {
+					throw std::invalid_argument("QuantPDE_B200: all problems of a batch must share the event expression (parameters may differ)");
+				}
+				for(const auto &row : tab) {
+					if(row.size() != width) throw std::invalid_argument("QuantPDE_B200: ragged event parameter table");
+					evParams.insert(evParams.end(), row.begin(), row.end());
+				}
+			}
+			b.event_program = evWords.data(); b.event_program_length = (int32_t)evWords.size();
+			b.event_consts = evConsts.data(); b.n_event_consts = (int32_t)evConsts.size();
+			b.event_params = evParams.data(); b.n_event_params = (int32_t)width;
+			b.event_params_stride = (int64_t)nEv * (int64_t)width;
+		}
 		b.strike = K.data();
 		b.payoff_kind = payKind; b.obstacle_kind = obsKind;
 		if(payKind == QPDE_PAYOFF_ARRAY) { b.payoff = payArr.data(); b.payoff_stride = N; }

@@ -62,3 +62,83 @@ def test_two_translation_units_link_and_fail_loudly_without_a_gpu(tmp_path, qpde
         assert run.returncode == 0, run.stderr
     else:
         assert run.returncode == 7 and run.stderr.strip(), (run.returncode, run.stderr)   # an error message, not a fallback
+
+
+EVENT_PROGRAM = r"""
+#include <QuantPDE_B200/Core.hpp>
+#include <cstdio>
+#include <limits>
+using namespace QuantPDE_B200;
+int main() {
+	// examples/experimental/glwb.cpp:84-121 as an expression
+	const Real bonus = .06, GQ = 5.;
+	EventExpression S = EventExpression::S(), R = EventExpression::param(0), pen = EventExpression::param(1);
+	EventExpression best = max(max(c(1. + bonus) * V(S / c(1. + bonus)), V(max(S - c(GQ), c(0.))) + R * c(GQ)),
+		select(S > c(GQ), R * (c(GQ) + (c(1.) - pen) * (S - c(GQ))), c(-std::numeric_limits<Real>::infinity())));
+	std::vector<int32_t> words; std::vector<Real> consts;
+	best.lower(words, consts);
+	for(int32_t w : words) std::printf("%d ", (int) w);
+	std::printf("\n");
+	for(Real k : consts) std::printf("%a ", k);
+	std::printf("\n");
+	// the stepper keeps it with its parameter table; forward steppers and Forward* discretisations exist
+	ReverseConstantStepper stepper(0., 1., .01);
+	stepper.addEvents(2, best, {{.99, .03}, {.98, .02}});
+	ForwardConstantStepper forward(0., 1., .01);
+	RectilinearGrid1 grid(Axis::special());
+	BlackScholes1 bs(grid, .04, .2, 0.);
+	ForwardRannacher fr(grid, bs); ForwardBDFTwo fb(grid, bs);
+	return stepper.eventDates() == 2 && forward.isForward() && fr.forward && fb.forward ? 0 : 1;
+}
+"""
+
+
+def test_event_expression_lowers_to_a_program_with_the_lambdas_value(tmp_path):
+    """EventExpression (Core.hpp): the GLWB three-way choice written as a C++ expression lowers to QPDE_EV_*
+    words whose value — interpreted here — equals the lambda of examples/experimental/glwb.cpp:84-121 bit for bit."""
+    import numpy as np
+    src = tmp_path / "ev.cpp"
+    src.write_text(EVENT_PROGRAM)
+    exe = str(tmp_path / "ev")
+    subprocess.run(["g++", "-std=c++11", "-Wall", "-Werror", "-I" + os.path.join(ROOT, "include"),
+                    "-I" + os.path.join(ROOT, "quantpde_b200", "include"), str(src), "-o", exe,
+                    "-L" + os.path.join(ROOT, "quantpde_b200", "lib"), "-lqpde_b200",
+                    "-Wl,-rpath," + os.path.join(ROOT, "quantpde_b200", "lib")], check=True)
+    out = subprocess.run([exe], check=True, capture_output=True, text=True).stdout.splitlines()
+    words = [int(t) for t in out[0].split()]
+    consts = [float.fromhex(t) for t in out[1].split()]
+    xs = np.linspace(0., 200., 41); vs = np.maximum(100. - xs, 0.) + .01 * xs
+
+    def V(at):
+        return float(np.interp(at, xs, vs))
+
+    def run(S, params):
+        st, pc = [], 0
+        while True:
+            op = words[pc]; pc += 1
+            if op == 0:
+                assert len(st) == 1
+                return st[0]
+            if op == 1: st.append(S)
+            elif op == 2: st.append(consts[words[pc]]); pc += 1
+            elif op == 3: st.append(params[words[pc]]); pc += 1
+            elif op == 10: st[-1] = -st[-1]
+            elif op == 11: st[-1] = V(st[-1])
+            elif op == 13:
+                f = st.pop(); t = st.pop(); st[-1] = t if st[-1] != 0. else f
+            else:
+                b = st.pop(); a = st[-1]
+                st[-1] = {4: a + b, 5: a - b, 6: a * b, 7: a / b if b else float("inf"), 8: b if b > a else a,
+                          9: b if b < a else a, 12: 1. if a > b else 0.}[op]
+            assert len(st) <= 8
+
+    bonus, GQ = .06, 5.
+    for S in (0., 3., 5., 5.0001, 60., 100., 140., 400.):
+        for Rn, pen in ((.99, .03), (.5, 0.)):
+            best = (1. + bonus) * V(S / (1. + bonus))
+            tmp = V(max(S - GQ, 0.)) + Rn * GQ
+            best = tmp if tmp > best else best
+            if S > GQ:
+                tmp = Rn * (GQ + (1. - pen) * (S - GQ))
+                best = tmp if tmp > best else best
+            assert run(S, (Rn, pen)) == best
