@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define QPDE_ABI_VERSION 5
+#define QPDE_ABI_VERSION 6
 
 /* ---- status codes ----------------------------------------------------- */
 enum {
@@ -272,6 +272,21 @@ typedef struct {
 	int64_t event_params_stride; /* doubles between contracts; 0 = one table shared by all contracts */
 	int32_t n_event_consts;
 	int32_t n_event_params;
+
+	/* --- explicit event times: stepper.add(event_times[e], ...) instead of the uniform T e / E
+	 * ([n_exercise], shared by the batch, any order, within [0, T]; NULL = uniform).  Row e of
+	 * event_params belongs to the e-th SMALLEST time.  A time equal to the initial time of the sweep is
+	 * taken as the reference takes it: a zero-length first step, then the event
+	 * (examples/experimental/glwb.cpp:84-121 adds one at t = T). */
+	const double *event_times;
+
+	/* --- operator source: b(t) of the LinearSystem = source_table[floor(t)] * S_i instead of 0 — the
+	 * GLWBOperator of examples/experimental/glwb.cpp:31-45, b(t) = -(R[n+1] - R[n]) S with n = floor(t)
+	 * (the index is clamped to the table).  [n_source], shared by the batch; NULL = none.  BDF1 / BDF2
+	 * only (b enters at one time), no penalty, no policy iteration, no jump term. */
+	const double *source_table;
+	int32_t n_source;
+	int32_t reserved3;
 
 	int32_t kernel;          /* QPDE_KERNEL_* (AUTO picks by N)             */
 	int32_t outputs;         /* split form only: QPDE_OUT_* mask of the outputs

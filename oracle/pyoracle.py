@@ -47,6 +47,7 @@ class Problem(C.Structure):
                 ("steps_taken", C.POINTER(C.c_int)),
                 ("event_program", C.POINTER(C.c_int)), ("event_consts", C.POINTER(C.c_double)),
                 ("event_params", C.POINTER(C.c_double)), ("n_events", C.c_int), ("n_event_params", C.c_int),
+                ("source_table", C.POINTER(C.c_double)), ("n_source", C.c_int),
                 ("forward", C.c_int)]
 
 
@@ -143,7 +144,8 @@ def interp(x, v, c):
 def sweep(S, lo, di, up, v0, T, steps, n_steps, scheme="rannacher",
           american=False, obstacle=None, event_obstacle=None,
           tolerance=1e-6, scale=1.0, penalty_tol=1e-6, max_inner=1000, solver=0,
-          policy_rows=None, policy_max=False, jump=None, dividend=None, variable=None, forward=False, event=None):
+          policy_rows=None, policy_max=False, jump=None, dividend=None, variable=None, forward=False, event=None,
+          source=None):
     """Returns dict(V, inner, mask, status).  dividend = (kind, D, first); variable = (dt0, target,
     scale): ReverseVariableStepper, `steps` ignored, n_steps = capacity, out['n_steps'] = steps taken.  policy_rows = (lo, di, up), each
     [n_controls][n]: PolicyIteration over the controls."""
@@ -171,6 +173,9 @@ def sweep(S, lo, di, up, v0, T, steps, n_steps, scheme="rannacher",
     p.tolerance, p.scale, p.penalty_tol, p.max_inner = tolerance, scale, penalty_tol, max_inner
     p.solver = solver
     p.forward = int(forward)
+    if source is not None:
+        src = np.ascontiguousarray(source, dtype=np.float64)
+        p.source_table, p.n_source = _dp(src), len(src)
     if event is not None:
         # event = dict(program=int words, consts=[..], params=[n_events][n_params])
         ev_prog = np.ascontiguousarray(event["program"], dtype=np.int32)
@@ -243,6 +248,38 @@ def glwb_event(E, bonus=.06, GQ=5.):
         words += [OPS[t[0]], t[1]] if isinstance(t, tuple) else [OPS[t]]
     params = np.array([[1. - .01 * (e + 1), max(.03 - .01 * e, 0.)] for e in range(E)])
     return dict(program=np.array(words, dtype=np.int32), consts=[1. + bonus, GQ, 0., 1., -np.inf], params=params)
+
+
+def glwb_tables(years):
+    """The synthetic mortality / penalty tables of oracle/shim/ref_driver.cpp (mode glwb) and what follows from
+    them: survival R[0 .. years + 1], the operator's source g[n] = -(R[n+1] - R[n]), the per-event parameters
+    [R[n], penalty[n-1]] of the event at year n = 1 .. years."""
+    mortality = np.array([1. if n == years - 1 else .01 * (n + 1) for n in range(years)])
+    penalty = np.array([max(.03 - .01 * n, 0.) for n in range(years)])
+    R = np.ones(years + 2)
+    for n in range(1, years + 1):
+        R[n] = R[n - 1] * (1. - mortality[n - 1])
+    R[years + 1] = R[years]
+    source = np.array([-(R[n + 1] - R[n]) for n in range(years + 1)])
+    params = np.array([[R[n], penalty[n - 1]] for n in range(1, years + 1)])
+    return R, source, params
+
+
+def glwb(years, n_steps, refine_times, r=.04, vol=.2, S0=100., management_rate=.015, withdrawal_rate=.05,
+         bonus_rate=.06, scheme="bdf2"):
+    """examples/experimental/glwb.cpp run(k) on the oracle: GLWBOperator (source term), an event at every year
+    1 .. years (the last AT the initial time: a zero-length first step), zero initial condition."""
+    S = refine(special_axis() * S0, refine_times)
+    lo, di, up = bs_coeffs(S, r, vol, management_rate)
+    _, source, params = glwb_tables(years)
+    ev = glwb_event(years, bonus=bonus_rate, GQ=withdrawal_rate * S0)
+    ev["params"] = params
+    T = float(years)
+    steps, n = schedule(T, T / n_steps, [float(k) for k in range(1, years + 1)])
+    out = sweep(S, lo, di, up, np.zeros(len(S)), T, steps, n, scheme=scheme, event=ev, source=source)
+    out["S"] = S
+    out["n_steps"] = n
+    return out
 
 
 def forward_option(K, r, vol, T, n_steps, refine_times, q=0.0, call=False, american=False, scheme="rannacher",

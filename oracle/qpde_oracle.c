@@ -751,6 +751,16 @@ int qpo_sweep_1d(const qpo_problem *p, double *V, int *inner,
 		if(p->jump_weights) {
 			qpo_jump_term(n, p->S, v1, p->jump_lambda, p->jump_nfft, p->jump_x0,
 					p->jump_dx, p->jump_weights, bj);
+		} else if(p->source_table) {
+			/* an operator whose b(t) is a scalar of time times the grid, as GLWBOperator::b
+			 * (examples/experimental/glwb.cpp:40-44):  b(t) = g(floor(t)) S,  g(n) = -(R[n+1] - R[n]) */
+			int nidx = (int)floor(t);
+			double g;
+			if(use_cn) { status = 2; break; }   /* restated for the BDF schemes only (b at one time) */
+			if(nidx < 0) nidx = 0;
+			if(nidx > p->n_source - 1) nidx = p->n_source - 1;
+			g = p->source_table[nidx];
+			for(i = 0; i < n; ++i) bj[i] = g * p->S[i];
 		}
 
 		/* --- left-hand side  lA  and right-hand side  lb ----------------- */

@@ -125,6 +125,8 @@ typedef struct {
 	const int *event_program;
 	const double *event_consts, *event_params;
 	int n_events, n_event_params;
+	/* b(t) of the operator = source_table[floor(t)] * S (NULL = 0): GLWBOperator::b, glwb.cpp:40-44 */
+	const double *source_table; int n_source;
 	/* 1: the forward-time classes (TimeIteration<true>, ForwardConstantStepper, ForwardRannacher ...):
 	 * v0 is the condition at t = 0, `steps` comes from qpo_schedule_forward.  Constant steps only. */
 	int forward;

@@ -345,6 +345,89 @@ int runForward(const Args &a) {
 }
 
 ////////////////////////////////////////////////////////////////////////////////
+// glwb: examples/experimental/glwb.cpp run(k) — GLWBOperator (a BlackScholes1 whose b(t) is
+// -(R[n+1] - R[n]) S, n = floor(t)), ReverseBDFTwo (or BDFOne), an event at every year
+// n = 1 .. years (the last one AT the initial time of the reverse sweep) with the three-way choice,
+// zero initial condition.  Mortality and penalty tables are synthetic and short:
+// mortality[n] = .01 (n + 1) (the last year 1), penalty[n] = max(.03 - .01 n, 0).
+////////////////////////////////////////////////////////////////////////////////
+
+namespace glwbmode {
+Real *R;
+class GLWBOperator : public BlackScholes1 {
+public:
+	GLWBOperator(RectilinearGrid1 &grid, Real r, Real vol, Real management_rate) noexcept
+			: BlackScholes1(grid, r, vol, management_rate) {}
+	virtual Vector b(Real t) {
+		Vector S_vec = G.image([] (Real S) { return S; });
+		int n = floor(t);
+		return -(R[n+1] - R[n]) * S_vec;
+	}
+};
+}
+
+int runGlwb(const Args &a) {
+	const Real r = num(a, "r", .04), vol = num(a, "vol", .2), S_0 = num(a, "S0", 100.);
+	const Real management_rate = num(a, "management_rate", .015), withdrawal_rate = num(a, "withdrawal_rate", .05);
+	const Real bonus_rate = num(a, "bonus_rate", .06);
+	const int T = (int) integer(a, "years", 6);
+	const long steps = integer(a, "steps", 12 * T);
+	const int refine = (int) integer(a, "refine", 0);
+	const std::string scheme = str(a, "scheme", "bdf2");
+
+	std::vector<Real> mortality((size_t) T), penalty((size_t) T), R((size_t) T + 2);
+	for(int n = 0; n < T; ++n) { mortality[n] = n == T - 1 ? 1. : .01 * (n + 1); penalty[n] = max(.03 - .01 * n, 0.); }
+	R[0] = 1.;
+	for(int n = 1; n <= T; ++n) R[n] = R[n-1] * (1. - mortality[n-1]);
+	R[T + 1] = R[T];            // the reference reads R[T+1] in its zero-length first step (multiplied by h = 0)
+	glwbmode::R = R.data();
+
+	RectilinearGrid1 coarse( S_0 * Axis::special );
+	auto grid = coarse.refined(refine);
+
+	glwbmode::GLWBOperator op(grid, r, vol, management_rate);
+	ReverseConstantStepper stepper(0., (Real) T, (Real) T / steps);
+	std::unique_ptr<IterationNode> discretization;
+	if(scheme == "bdf2") discretization.reset(new ReverseBDFTwo(grid, op));
+	else discretization.reset(new ReverseBDFOne(grid, op));
+	discretization->setIteration(stepper);
+
+	const Real Q = S_0;
+	const Real *Rp = R.data();
+	for(int n = 1; n <= T; ++n) {
+		const Real pen = penalty[n-1];
+		auto event = [=] (const Interpolant1 &V, Real S) {
+			const Real GQ = withdrawal_rate * Q;
+			Real best = (1. + bonus_rate) * V(S / (1. + bonus_rate));
+			{
+				const Real S_plus = max(S - GQ, 0.);
+				const Real tmp = V(S_plus) + Rp[n] * GQ;
+				if(tmp > best) best = tmp;
+			}
+			if(S > GQ) {
+				const Real tmp = Rp[n] * ( GQ + ( 1. - pen ) * (S - GQ) );
+				if(tmp > best) best = tmp;
+			}
+			return best;
+		};
+		stepper.add((Real) n, event, grid);
+	}
+
+	SparseLUSolver solver;
+	auto begin = std::chrono::steady_clock::now();
+	auto solution = stepper.solve(grid, [] (Real) { return 0.; }, *discretization, solver);
+	auto end = std::chrono::steady_clock::now();
+
+	std::printf("value %a\n", (double) solution(S_0));
+	std::printf("seconds %.9g\n", std::chrono::duration<double>(end - begin).count());
+	std::printf("steps %ld\n", (long) stepper.iterations()[0]);
+	dumpReals("S", nodes(grid));
+	dumpReals("V", nodeValues(grid, solution));
+	dumpReals("R", R);
+	return 0;
+}
+
+////////////////////////////////////////////////////////////////////////////////
 // bermudan: local volatility alpha / S, E exercise dates at T e / E,
 // BDF2 (tutorial.cpp) or Rannacher, no inner iteration
 ////////////////////////////////////////////////////////////////////////////////
@@ -664,6 +747,7 @@ int main(int argc, char **argv) {
 	if(mode == "vanilla")  return runVanilla(a);
 	if(mode == "bermudan") return runBermudan(a);
 	if(mode == "forward") return runForward(a);
+	if(mode == "glwb") return runGlwb(a);
 	if(mode == "hjb")      return runHjb(a);
 	if(mode == "jump")     return runJump(a);
 	if(mode == "gmwb")     return runGmwb(a);

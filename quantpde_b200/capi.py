@@ -13,7 +13,7 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "lib", "libqpde_b200.so")
 
-ABI_VERSION = 5
+ABI_VERSION = 6
 
 OK, ERR_INVALID, ERR_CUDA, ERR_NO_DEVICE, ERR_NOT_CONVERGED, ERR_UNSUPPORTED = 0, -1, -2, -3, -4, -5
 
@@ -79,6 +79,7 @@ class Batch(C.Structure):
         ("n_fft", C.c_int32), ("event_program_length", C.c_int32),
         ("event_program", C.POINTER(C.c_int32)), ("event_consts", _dp), ("event_params", _dp),
         ("event_params_stride", C.c_int64), ("n_event_consts", C.c_int32), ("n_event_params", C.c_int32),
+        ("event_times", _dp), ("source_table", _dp), ("n_source", C.c_int32), ("reserved3", C.c_int32),
         ("kernel", C.c_int32), ("outputs", C.c_int32),
     ]
 
@@ -396,7 +397,8 @@ class BatchSpec:
                  n_exercise=0, exercise="k_minus_s", spot=None, tolerance=1e-6, scale=1.0,
                  penalty_tolerance=1e-6, max_inner=100, kernel="auto", outputs=OUT_ALL,
                  n_contracts=None, controls=None, policy_max=False, jump=None, dividend=None,
-                 variable_target=None, variable_scale=1.0, max_steps=0, forward=False, event=None):
+                 variable_target=None, variable_scale=1.0, max_steps=0, forward=False, event=None, event_times=None,
+                 source=None):
         axis = np.ascontiguousarray(axis, dtype=np.float64)
         if n_contracts is None:
             n_contracts = axis.shape[0] if axis.ndim == 2 else len(np.atleast_1d(strike))
@@ -437,6 +439,15 @@ class BatchSpec:
             b.variable_scale = float(variable_scale)
         b.n_exercise = int(n_exercise)
         b.exercise_kind = PAYOFF[exercise]
+        if event_times is not None:
+            et = np.ascontiguousarray(event_times, dtype=np.float64)
+            assert len(et) == int(n_exercise)
+            self.keep.append(et)
+            b.event_times = et.ctypes.data_as(_dp)
+        if source is not None:
+            src = np.ascontiguousarray(source, dtype=np.float64)
+            self.keep.append(src)
+            b.source_table, b.n_source = src.ctypes.data_as(_dp), len(src)
         if event is not None:
             # event = dict(program=int32 words, consts=[..], params=[n_exercise][n_params] or [C][n_exercise][n_params])
             prog = np.ascontiguousarray(event["program"], dtype=np.int32)

@@ -436,6 +436,23 @@ static int plan_create_impl(qpde_handle *h, const qpde_bs1d_batch *in,
 	if(in->n_exercise > 0 && in->exercise_kind != QPDE_EXERCISE_NONE && !is_generator(in->exercise_kind)) {
 		return fail(h, QPDE_ERR_INVALID, "exercise_kind must be a generator or QPDE_EXERCISE_NONE");
 	}
+	if(in->event_times) {
+		if(in->n_exercise < 1) return fail(h, QPDE_ERR_INVALID, "event_times needs n_exercise >= 1");
+		if(in->variable_target) return fail(h, QPDE_ERR_UNSUPPORTED, "explicit event times with variable steps are not supported");
+		double tmax = 0.;
+		for(int c = 0; c < C; ++c) tmax = in->T[c] > tmax ? in->T[c] : tmax;
+		for(int e = 0; e < in->n_exercise; ++e) {
+			if(!(in->event_times[e] >= 0.) || !(in->event_times[e] <= tmax)) return fail(h, QPDE_ERR_INVALID, "event_times[%d] outside [0, T]", e);
+		}
+		for(int c = 0; c < C; ++c) if(in->T[c] != in->T[0]) return fail(h, QPDE_ERR_INVALID, "explicit event times need one expiry for the whole batch");
+	}
+	if(in->source_table || in->n_source != 0) {
+		if(!in->source_table || in->n_source < 1) return fail(h, QPDE_ERR_INVALID, "source_table / n_source");
+		if(in->scheme != QPDE_SCHEME_BDF1 && in->scheme != QPDE_SCHEME_BDF2) return fail(h, QPDE_ERR_UNSUPPORTED, "an operator source needs scheme BDF1 or BDF2");
+		if(in->american || in->n_controls != 0 || in->jump_lambda || in->variable_target) {
+			return fail(h, QPDE_ERR_UNSUPPORTED, "an operator source with a penalty constraint, controls, a jump term or variable steps is not supported");
+		}
+	}
 	if(in->event_program_length != 0 || in->event_program) {
 		if(in->n_exercise < 1) return fail(h, QPDE_ERR_INVALID, "an event program needs n_exercise >= 1 event times");
 		if(in->exercise_kind != QPDE_EXERCISE_NONE || in->dividend_kind != QPDE_DIVIDEND_NONE) {
@@ -522,6 +539,16 @@ static int plan_create_impl(qpde_handle *h, const qpde_bs1d_batch *in,
 	if(in->spot) QPDE_TRY(upload_vec(p, in->spot, C, &b.spot));
 	if(in->variable_target) { QPDE_TRY(upload_vec(p, in->variable_target, C, &b.variable_target)); b.variable_scale = in->variable_scale; }
 	if(in->dividend_kind != QPDE_DIVIDEND_NONE) QPDE_TRY(upload_vec(p, in->dividend, C, &b.dividend));
+	if(in->event_times) {
+		std::vector<double> sorted(in->event_times, in->event_times + in->n_exercise);
+		std::sort(sorted.begin(), sorted.end());
+		QPDE_TRY(upload_vec(p, sorted.data(), in->n_exercise, &b.event_times));
+		if(cudaStreamSynchronize(h->stream) != cudaSuccess) {      // `sorted` goes away
+			qpde_bs1d_plan_destroy(p);
+			return fail(h, QPDE_ERR_CUDA, "event_times upload failed");
+		}
+	}
+	if(in->source_table) { QPDE_TRY(upload_vec(p, in->source_table, in->n_source, &b.source_table)); b.n_source = in->n_source; }
 	if(in->event_program) {
 		// program words (as doubles' worth of ints), constants and the per-event parameter tables
 		int *code = nullptr;

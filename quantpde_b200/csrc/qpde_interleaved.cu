@@ -129,7 +129,7 @@ k_interleaved_sweep(DeviceBatch b, InterleavedWork w, DeviceResult out) {
 	const bool policy = b.n_controls > 0;
 	const bool iterate = b.american || policy;   // a ToleranceIteration wraps every step
 	const size_t NC = (size_t)N * (size_t)w.ld;               // one array (one set of operator rows)
-	Replay rp; rp.start(b.T[c], b.dt[c], b.n_exercise, b.forward);
+	Replay rp; rp.start(b.T[c], b.dt[c], b.n_exercise, b.forward, b.event_times);
 	NodeState ns; ns.start(b.scheme);
 	double time1 = rp.initial(), time0 = rp.initial(); // times of iterand(0), iterand(1)
 	Gamma gA; gA.kind = STEP_IMPLICIT; gA.h = 0.; // what the factorised A was built with
@@ -180,6 +180,13 @@ k_interleaved_sweep(DeviceBatch b, InterleavedWork w, DeviceResult out) {
 		// ---- lb = root.b(t) of the discretisation node ------------------
 		// x holds iterand(0) = V^n, xp holds iterand(1) for BDF2.
 		if(kind < STEP_BDF3) {
+			// b(t) of the operator: 0, or source_table[floor(t)] S (GLWBOperator::b, glwb.cpp:40-44)
+			double gsrc = 0.;
+			if(b.source_table) {
+				int nidx = (int)floor(t);
+				nidx = nidx < 0 ? 0 : (nidx > b.n_source - 1 ? b.n_source - 1 : nidx);
+				gsrc = b.source_table[nidx];
+			}
 			// blocks of ROWS rows with all loads issued first (see the elimination loop)
 			double vm = 0.;
 			for(int ib = 0; ib < N; ib += ROWS) {
@@ -200,9 +207,9 @@ k_interleaved_sweep(DeviceBatch b, InterleavedWork w, DeviceResult out) {
 					const double vi = vx[u], vp = i + 1 < N ? vx[u + 1] : 0.;
 					double val;
 					if(kind == STEP_IMPLICIT) {
-						val = vi + 0. * h0;
+						val = b.source_table ? vi + h0 * (gsrc * w.S[base + (size_t)i * C]) : vi + 0. * h0;
 					} else if(kind == STEP_BDF2) {
-						val = (div_by(c1 * vi - c0 * vxp[u], den, rden) + 0.) * gb.h;
+						val = (div_by(c1 * vi - c0 * vxp[u], den, rden) + (b.source_table ? gsrc * w.S[base + (size_t)i * C] : 0.)) * gb.h;
 					} else {
 						// (I - A h/2) v0, row-major SpMV from zero in column order
 						double acc = 0.;

@@ -159,7 +159,7 @@ k_interleaved_sweep_tma(const __grid_constant__ TmaMaps maps, DeviceBatch b, Int
 	const int nb = (N + TR - 1) / TR;            // tiles per pass
 	const int lead = nb < stages ? nb : stages;
 
-	Replay rp; rp.start(b.T[cc], b.dt[cc], b.n_exercise, b.forward);
+	Replay rp; rp.start(b.T[cc], b.dt[cc], b.n_exercise, b.forward, b.event_times);
 	NodeState ns; ns.start(b.scheme);
 	double time1 = rp.initial(), time0 = rp.initial(); // times of iterand(0), iterand(1)
 	Gamma gA; gA.kind = STEP_IMPLICIT; gA.h = 0.; // what the factorised A was built with
@@ -512,7 +512,7 @@ bool interleaved_tma_supported(const DeviceBatch &b) {
 	// algorithmic for the plain-load sweep); below a few tiles per pass it is all prologue.
 	int min_nodes = 32;
 	if(const char *e = std::getenv("QPDE_TMA_MIN_NODES")) { const int v = std::atoi(e); if(v >= 2) min_nodes = v; }   // tuning knob
-	return b.n_controls == 0 && b.N >= min_nodes && b.scheme <= QPDE_SCHEME_BDF2 && !b.event_program;   // event programs: plain-load sweep
+	return b.n_controls == 0 && b.N >= min_nodes && b.scheme <= QPDE_SCHEME_BDF2 && !b.event_program && !b.source_table;   // event programs, operator sources: plain-load sweep
 }
 
 bool interleaved_tma_prepare(InterleavedTma *t, double *block, long long rows, int arrays, std::string *error) {

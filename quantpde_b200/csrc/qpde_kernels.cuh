@@ -41,6 +41,8 @@ struct DeviceBatch {
 	// general events (QPDE_EV_* programs); event_program == nullptr: the tagged exercise / dividend transforms
 	const int *event_program; const double *event_consts, *event_params;
 	long long event_params_stride; int n_event_params;
+	const double *event_times;      // [n_exercise] ascending, or nullptr: uniform T e / E
+	const double *source_table; int n_source;   // b(t) = source_table[floor(t)] S, or nullptr
 };
 
 // Device output buffers (contract-major); any pointer may be null.

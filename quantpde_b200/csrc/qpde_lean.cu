@@ -599,7 +599,7 @@ k_lean_sweep(DeviceBatch b, DeviceResult out) {
 bool lean_supported(const DeviceBatch &b) {
 	const char *env = getenv("QPDE_RESIDENT_LEAN");             // "0": A/B against k_resident_sweep (read per call)
 	if(env && env[0] == '0') return false;
-	if(!b.american || b.n_controls != 0 || b.n_exercise > 0 || b.variable_target || b.forward) return false;
+	if(!b.american || b.n_controls != 0 || b.n_exercise > 0 || b.variable_target || b.forward || b.source_table) return false;
 	if(b.scheme != QPDE_SCHEME_RANNACHER && b.scheme != QPDE_SCHEME_CN && b.scheme != QPDE_SCHEME_BDF1) return false;
 	if(b.obstacle_kind != QPDE_PAYOFF_PUT && b.obstacle_kind != QPDE_PAYOFF_CALL) return false;
 	if(b.N <= 8 * 64 + 1 || b.N > 8 * LP + 1) return false;

@@ -311,7 +311,7 @@ k_resident_sweep(DeviceBatch b, DeviceResult out) {
 	// ------------------------------------------------------------------
 	// Time loop
 	// ------------------------------------------------------------------
-	Replay rp; rp.start(b.T[cidx], b.dt[cidx], b.n_exercise, b.forward);
+	Replay rp; rp.start(b.T[cidx], b.dt[cidx], b.n_exercise, b.forward, b.event_times);
 	NodeState ns; ns.start(b.scheme);
 	// ReverseVariableStepper (Core/Stepper.hpp:60-126): dt of the next step from the
 	// relative change over the last one
@@ -374,14 +374,24 @@ k_resident_sweep(DeviceBatch b, DeviceResult out) {
 		// memory; rr = lb + penalty terms of the current active set ----------
 		{
 			double lb[M];
+			// b(t) of the operator: 0, or source_table[floor(t)] S (GLWBOperator::b, glwb.cpp:40-44); enters the
+			// BDF right-hand sides v + h b (BDF.hpp:41-46) and ((..) / (h0 - h1) + b) hh (BDF.hpp:96-108)
+			double gsrc = 0.;
+			if(b.source_table) {
+				int nidx = (int)floor(t);
+				nidx = nidx < 0 ? 0 : (nidx > b.n_source - 1 ? b.n_source - 1 : nidx);
+				gsrc = b.source_table[nidx];
+			}
 			if(kind == STEP_IMPLICIT) {
 #pragma unroll
-				for(int j = 0; j < M; ++j) lb[j] = x[j] + 0. * h0;
-				if(tail_owner) sm.tail.lb = sm.tail.x + 0. * h0;
+				for(int j = 0; j < M; ++j) lb[j] = b.source_table ? x[j] + h0 * (gsrc * sm_S[j * P + tid]) : x[j] + 0. * h0;
+				if(tail_owner) sm.tail.lb = b.source_table ? sm.tail.x + h0 * (gsrc * sm.tail.S) : sm.tail.x + 0. * h0;
 			} else if(BDF2 && kind == STEP_BDF2) {
 #pragma unroll
-				for(int j = 0; j < M; ++j) lb[j] = (div_by(c1 * x[j] - c0 * vprev[j], den, rden) + 0.) * g.h;
-				if(tail_owner) sm.tail.lb = (div_by(c1 * sm.tail.x - c0 * sm.tail.vprev, den, rden) + 0.) * g.h;
+				for(int j = 0; j < M; ++j) {
+					lb[j] = (div_by(c1 * x[j] - c0 * vprev[j], den, rden) + (b.source_table ? gsrc * sm_S[j * P + tid] : 0.)) * g.h;
+				}
+				if(tail_owner) sm.tail.lb = (div_by(c1 * sm.tail.x - c0 * sm.tail.vprev, den, rden) + (b.source_table ? gsrc * sm.tail.S : 0.)) * g.h;
 			} else {
 				// (I - A h/2) V^n: row-major SpMV accumulated from zero in column order
 				const double xm = sm_xlast[tid];       // x of row i0 - 1

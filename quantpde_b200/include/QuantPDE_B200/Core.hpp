@@ -225,6 +225,11 @@ public:
 	const RectilinearGrid1 &grid;
 	Real r; Volatility v; Real q;
 	bool rIsControl;
+	// b(t) of the operator: 0 (BlackScholes.hpp:228-230), or sourceTable[floor(t)] * S — what a subclass of the
+	// reference's BlackScholes1 that overrides b(t) with a scalar of time times the grid amounts to
+	// (GLWBOperator, examples/experimental/glwb.cpp:31-45)
+	std::vector<Real> sourceTable;
+	void setSource(std::vector<Real> table) { sourceTable = std::move(table); }
 	BlackScholes1(const RectilinearGrid1 &grid, Real r, Volatility v, Real q)
 			: grid(grid), r(r), v(std::move(v)), q(q), rIsControl(false) {}
 	BlackScholes1(const RectilinearGrid1 &grid, Control1, Volatility v, Real q)
@@ -515,6 +520,7 @@ class ReverseConstantStepper : public Iteration {
 	bool dividendAddedFirst;
 	EventExpression eventExpression_;
 	std::vector<std::vector<Real>> eventTable_;
+	std::vector<Real> eventTimes_;      // explicit event times (else uniform T e / E)
 protected:
 	Real vTarget, vScale;      // > 0: ReverseVariableStepper
 	int stepLimit_;
@@ -548,6 +554,13 @@ public:
 		nExercise = E; exercise = Payoff(QPDE_EXERCISE_NONE, 0.);
 		eventExpression_ = std::move(event); eventTable_ = std::move(table);
 	}
+	// the same at explicit times: stepper.add(times[e], event, grid); table[e] goes with the e-th SMALLEST time.
+	// A time equal to the initial time of the sweep is allowed (the reference then takes a zero-length first step).
+	void addEvents(std::vector<Real> times, EventExpression event, std::vector<std::vector<Real>> table = {}) {
+		addEvents((int)times.size(), std::move(event), std::move(table));
+		eventTimes_ = std::move(times);
+	}
+	const std::vector<Real> &eventTimes() const { return eventTimes_; }
 	const EventExpression &eventExpression() const { return eventExpression_; }
 	const std::vector<std::vector<Real>> &eventTable() const { return eventTable_; }
 
@@ -752,6 +765,15 @@ public:
 		b.n_exercise = nEv;
 		b.exercise_kind = nEx > 0 ? items[0].stepper->exercisePayoff().kind() : QPDE_EXERCISE_NONE;
 		if(dividends) { b.dividend_kind = divKind; b.dividend_first = divFirst ? 1 : 0; b.dividend = divAmount.data(); }
+		for(int cc = 0; cc < C; ++cc) {
+			const Discretization *dd; MinPenaltyMethodDifference1 *pp;
+			decode(items[cc].root, dd, pp);
+			if(dd->op.sourceTable != d0->op.sourceTable || items[cc].stepper->eventTimes() != items[0].stepper->eventTimes()) {
+				throw std::invalid_argument("QuantPDE_B200: all problems of a batch must share the operator's source table and the event times");
+			}
+		}
+		if(!d0->op.sourceTable.empty()) { b.source_table = d0->op.sourceTable.data(); b.n_source = (int32_t)d0->op.sourceTable.size(); }
+		if(!items[0].stepper->eventTimes().empty()) b.event_times = items[0].stepper->eventTimes().data();
 		std::vector<int32_t> evWords; std::vector<Real> evConsts, evParams;
 		if(!items[0].stepper->eventExpression().empty()) {
 			items[0].stepper->eventExpression().lower(evWords, evConsts);

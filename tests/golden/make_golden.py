@@ -176,6 +176,12 @@ for name, kw in (("event_glwb_bdf2_k2", dict(american=0, steps=50, refine=2, E=5
     base = dict(K=100.0, r=0.04, vol=0.2, T=1.0, event="glwb")
     base.update(kw)
     CASES.append((name, "vanilla", base))
+# examples/experimental/glwb.cpp run(k) itself (qpde_ref glwb: GLWBOperator with its source term b(t), an
+# event at every year incl. one AT the initial time, zero initial condition; short synthetic tables)
+for name, kw in (("glwb_bdf2_k1", dict(years=4, steps=24, refine=1)), ("glwb_bdf2_k2", dict(years=6, steps=72, refine=2)),
+                 ("glwb_bdf1_k2", dict(years=5, steps=40, refine=2, scheme="bdf1")),
+                 ("glwb_bdf2_k4", dict(years=8, steps=192, refine=4)), ("glwb_bdf2_k6", dict(years=6, steps=144, refine=6))):
+    CASES.append((name, "glwb", dict(kw)))
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "reference_cases.npz")
 # cases already in the file with the same arguments are kept (pass --all to re-run everything)
 have = np.load(GOLDEN, allow_pickle=False) if os.path.exists(GOLDEN) and "--all" not in sys.argv else None

@@ -36,6 +36,12 @@ CASES = {
     "hjb_long": ("unequal_borrowing_lending_rates", {"long_position": True, "maximum_refinement": 3,
                                                      "interest_rate_long": 0.06, "volatility": 0.25}),
     "tutorial": ("tutorial", None),
+    # examples/experimental/glwb.cpp: the default DAV2004R mortality table (57 years), and short tables of its own
+    "glwb_default": ("glwb", {"maximum_refinement": 4}),
+    "glwb_short_tables": ("glwb", {"maximum_refinement": 5, "minimum_refinement": 1, "volatility": 0.25,
+                                   "initial_number_of_timesteps": 16, "bonus_rate": 0.05, "withdrawal_rate": 0.06,
+                                   "mortality_data": [[0.01, 0.02, 0.04, 0.08, 0.15, 0.3, 0.5, 1.0]],
+                                   "penalty_data": [[0.05, 0.04, 0.03, 0.02, 0.01, 0.0, 0.0, 0.0]]}),
 }
 
 

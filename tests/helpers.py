@@ -52,6 +52,8 @@ def run_oracle_case(po, mode, kw):
                                dividend=kw.get("dividend"), dividend_kind=kw.get("dividend_kind", "cash"),
                                dividend_first=bool(kw.get("dividend_first", 0)), exercise=bool(kw.get("exercise", 0)),
                                event=po.glwb_event(kw["E"]) if kw.get("event") == "glwb" else None)
+    if mode == "glwb":
+        return po.glwb(kw["years"], kw["steps"], kw["refine"], scheme=kw.get("scheme", "bdf2"))
     if mode == "forward":
         return po.forward_option(kw["K"], kw["r"], kw["vol"], kw["T"], kw["steps"], kw["refine"], call=bool(kw.get("call", 0)),
                                  american=bool(kw["american"]), scheme=kw["scheme"], alpha=kw.get("alpha", 0.0),
@@ -85,6 +87,18 @@ def spec_for_case(qpde, po, mode, kw, kernel="auto", copies=1):
             dividend=None if "dividend" not in kw else dict(kind=kw["dividend_kind"], amount=kw["dividend"],
                                                           first=bool(kw.get("dividend_first", 0))),
             event=po.glwb_event(kw["E"]) if kw.get("event") == "glwb" else None)
+    if mode == "glwb":
+        years, S0 = kw["years"], 100.0
+        _, source, params = po.glwb_tables(years)
+        ev = po.glwb_event(years, bonus=.06, GQ=.05 * S0)
+        axis = po.special_axis() * S0
+        N = qpde.refined_size(len(axis), kw["refine"])
+        return qpde.BatchSpec(
+            axis=np.tile(axis, (copies, 1)), refine=kw["refine"], r=.04, sigma=.2, q=.015, T=float(years),
+            dt=float(years) / kw["steps"], strike=np.full(copies, S0), scheme=kw.get("scheme", "bdf2"), american=False,
+            payoff_array=np.zeros((copies, N)), n_exercise=years, exercise="none", kernel=kernel,
+            event=dict(program=ev["program"], consts=ev["consts"], params=params),
+            event_times=[float(n) for n in range(1, years + 1)], source=source)
     if mode == "forward":
         K = kw["K"]
         axis = po.axis_union(po.special_axis() * K, po.special_axis() * K)

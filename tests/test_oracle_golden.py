@@ -12,7 +12,7 @@ from helpers import case_args, run_oracle_case
 
 def test_golden_cases_bit_exact(oracle, golden):
     names = [str(n) for n in golden["names"]]
-    assert len(names) >= 71
+    assert len(names) >= 76
     for name in names:
         mode, kw = case_args(golden, name)
         out = run_oracle_case(oracle, mode, kw)
