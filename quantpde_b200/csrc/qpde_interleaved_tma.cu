@@ -22,7 +22,13 @@
 // up, x [+ obstacle, xprev], writes lb, cp, dp [+ xprev]), every further penalty iteration
 // has a forward elimination (reads lo, di, up, lb [+ obstacle, x], writes cp, dp), and every
 // solve a back substitution (reads cp, dp [+ obstacle, x], writes x).  A penalty iteration
-// whose active set equals the previous one's is counted, not computed.
+// whose active set equals the previous one's is counted, not computed, and a further penalty
+// iteration starts its forward elimination at the first row whose active-set bit changed (minimum
+// over the warp's contracts that iterate): cp, dp of the rows before it are those of the previous
+// elimination bit for bit (same rows, same lb, same penalty terms).
+// (Tried and dropped: re-generating a put / call obstacle per row from the coarse axis instead of
+// streaming it — 8 B per row and pass less, but no faster at 65,536 x 2049 and 1.5x slower at
+// 16,384 contracts, where a warp has a scheduler to itself and every added instruction is latency.)
 // Results written with ordinary stores are read by later TMA loads: every pass starts
 // with a device-scope fence + fence.proxy.async.
 #include <cuda.h>
@@ -218,6 +224,7 @@ k_interleaved_sweep_tma(const __grid_constant__ TmaMaps maps, DeviceBatch b, Int
 		};
 
 		int its = 0;
+		int fstart = 0;                          // first row of the next forward elimination
 		bool again = act;
 		bool first = true;
 		do {
@@ -280,10 +287,14 @@ k_interleaved_sweep_tma(const __grid_constant__ TmaMaps maps, DeviceBatch b, Int
 			{
 				// slots: lo di up | lb | obstacle x
 				const Boxes bx = { { 3, 1, american ? 2 : 0 }, { ta.coef, ta.lb, ta.obx }, { 0, 3, 4 } };
+				// rows before the first changed active-set bit keep their cp, dp (see the header)
+				const int js = american ? fstart / TR : 0;
+				const int lead2 = nb - js < stages ? nb - js : stages;
 				pass_begin();
-				for(int j = 0; j < lead; ++j) ring_issue(ring, maps, blk0, bx, j * TR, lane);
+				for(int j = 0; j < lead2; ++j) ring_issue(ring, maps, blk0, bx, (js + j) * TR, lane);
 				cprev = 0.; dprev = 0.;
-				for(int j = 0; j < nb; ++j) {
+				if(js > 0) { cprev = cp[(size_t)(js * TR - 1) * ld]; dprev = dp[(size_t)(js * TR - 1) * ld]; }
+				for(int j = js; j < nb; ++j) {
 					const int s = ring_wait(ring);
 					const double *tile = sm + s * STAGE_DOUBLES;
 					double vlo[TR], vdi[TR], vup[TR], vlb[TR], vob[TR], vx[TR];
@@ -314,6 +325,7 @@ k_interleaved_sweep_tma(const __grid_constant__ TmaMaps maps, DeviceBatch b, Int
 			// has some contract whose free boundary has just crossed a node (three iterations
 			// instead of two): without the shortcut every warp would take three solves per step.
 			bool notdone = false, changed = false;
+			int fc = N;
 			{
 				// slots: cp dp | obstacle x   (iterate == american in this kernel)
 				const Boxes bx = { { 2, american ? 2 : 0, 0 }, { ta.cpdp, ta.obx, -1 }, { 0, 2, 0 } };
@@ -349,7 +361,7 @@ k_interleaved_sweep_tma(const __grid_constant__ TmaMaps maps, DeviceBatch b, Int
 							const double diff = fabs(xn - xo), bound = tol * d;
 							if(diff > bound * (1. + 8e-15)) notdone = true;
 							else if(diff >= bound * (1. - 8e-15) && diff / d > tol) notdone = true;
-							if(american && ((xn < vob[u]) != (xo < vob[u]))) changed = true;
+							if(american && ((xn < vob[u]) != (xo < vob[u]))) { changed = true; fc = i; }   // descending: ends as the first changed row
 						}
 						if(again) x[(size_t)i * ld] = xn;
 					}
@@ -364,6 +376,7 @@ k_interleaved_sweep_tma(const __grid_constant__ TmaMaps maps, DeviceBatch b, Int
 					again = false;
 				} else if(again && its >= b.max_inner) { status = 1; again = false; }
 			}
+			fstart = __reduce_min_sync(FULL, again ? fc : N);      // warp-uniform; N when no contract iterates
 		} while(__any_sync(FULL, again));
 
 		if(act) {

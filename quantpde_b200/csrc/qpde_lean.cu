@@ -205,7 +205,9 @@ k_lean_sweep(DeviceBatch b, DeviceResult out) {
 	int cur_kind = -1; double cur_h = 0.;
 	if(tid == 0) { sm.n_steps = 0; sm.inner_total = 0; sm.computed = 0; sm.status = 0; }
 	bool more = true;
-	bool refactor = true;
+	bool refactor = true;             // block-wide: some warp's rows or active set changed
+	bool wrefactor = true;            // this warp's rows or active set changed: levels 1 and 2 of the factorisation are
+	                                  // functions of the warp's own rows, so the other warps keep theirs
 
 	while(more) {
 		double t = time1 + -1. * dt_c;
@@ -221,7 +223,7 @@ k_lean_sweep(DeviceBatch b, DeviceResult out) {
 		if(kind != cur_kind || fabs(g.h - cur_h) > 1e-11 * cur_h) {
 			cur_kind = kind; cur_h = g.h;
 			rescale(g);
-			refactor = true;
+			refactor = true; wrefactor = true;
 		}
 
 		// ---- lb = b(t) of the discretisation node (V^n = x)
@@ -263,6 +265,8 @@ k_lean_sweep(DeviceBatch b, DeviceResult out) {
 			// ==========================================================
 			if(refactor) {
 				refactor = false;
+				if(wrefactor) {
+				wrefactor = false;
 				curmask = newmask;
 				wpen = __any_sync(FULL, curmask != 0u);
 				double Vs1, Ws1, Vs7, Ws7, a0, c0, b0;
@@ -346,6 +350,7 @@ k_lean_sweep(DeviceBatch b, DeviceResult out) {
 				if(lane == 31) { sm.f_Vs7[warp] = Vs7; sm.f_Ws7[warp] = Ws7; sm.f_V2l[warp] = f_V2; sm.f_W2l[warp] = f_W2; }
 				if(lane == 1)  { sm.f_V2f[warp] = f_V2; sm.f_W2f[warp] = f_W2; }
 				if(lane == 0)  { sm.f_a0[warp] = a0; sm.f_Bp[warp] = Bpart; sm.f_Ct[warp] = Ct; }
+				}
 				__syncthreads();
 				if(warp == 0) {
 					// level 3: LW x LW tridiagonal over the warp separators, lanes 0 .. LW-1
@@ -514,6 +519,7 @@ k_lean_sweep(DeviceBatch b, DeviceResult out) {
 			const int votes = __syncthreads_count(lane == 31 ? (wbits & 1u) : (wbits >> 1 & 1u));
 			const bool notdone = votes % 31 != 0, changed = votes >= 31;
 			refactor = changed;
+			wrefactor = (wbits >> 1 & 1u) != 0u;
 			again = notdone;
 			if(tid == 0) ++sm.computed;
 			if(notdone && !changed) {
