@@ -193,3 +193,26 @@ def test_split_search_and_assembly_equals_the_fused_kernel(qpde, handle, oracle,
     res = _solve(qpde, handle, oracle, refine=2)
     assert res["status"] == 0 and res["mean_inner"] == whole["mean_inner"]
     assert np.array_equal(res["V"], whole["V"])
+
+
+def test_gmwb_problems_of_several_threads_overlap_and_keep_their_bits(qpde, handle, oracle):
+    """Several GMWB problems at once: one handle (its own streams) per host thread.  The line pass of a
+    problem occupies one cluster of 8 SMs, so independent problems fill the rest of the GPU
+    (tools/profile_gmwb_concurrent.py: 3.7x the throughput at 8 problems); every problem returns the bits
+    of its stand-alone run."""
+    import threading
+    sig = [.2, .25, .3, .35]
+    alone = [_solve(qpde, handle, oracle, refine=1, sigma=s) for s in sig]
+    handles = [qpde.Handle(0) for _ in sig]
+    out = [None] * len(sig)
+
+    def run(k):
+        out[k] = _solve(qpde, handles[k], oracle, refine=1, sigma=sig[k])
+    th = [threading.Thread(target=run, args=(k,)) for k in range(len(sig))]
+    for t in th: t.start()
+    for t in th: t.join()
+    for hh in handles: hh.close()
+    for k in range(len(sig)):
+        assert out[k] is not None and out[k]["status"] == 0
+        assert np.array_equal(out[k]["V"], alone[k]["V"]) and out[k]["mean_inner"] == alone[k]["mean_inner"]
+    assert not np.array_equal(out[0]["V"], out[1]["V"])
