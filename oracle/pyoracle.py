@@ -362,6 +362,36 @@ def gmwb(refine_times=0, a_points=51, timesteps=32, control_points=3, T=10., r=.
                 n_steps=n_steps.value, status=status)
 
 
+class Hjbqvi1d(C.Structure):
+    _fields_ = [("n_x", C.c_int), ("x", C.POINTER(C.c_double)),
+                ("n_q", C.c_int), ("q", C.POINTER(C.c_double)),
+                ("n_z", C.c_int), ("z", C.POINTER(C.c_double)),
+                ("T", C.c_double), ("timesteps", C.c_int),
+                ("rho", C.c_double), ("sigma", C.c_double), ("a", C.c_double), ("b", C.c_double),
+                ("m", C.c_double), ("lam", C.c_double), ("c", C.c_double),
+                ("scaling_factor", C.c_double), ("tolerance", C.c_double), ("max_inner", C.c_int)]
+
+
+def exchange_rate(x_axis, q_axis, z_axis, refine_times=0, timesteps=16, T=10., rho=.02, sigma=.3, a=.25, b=3.,
+                  m=0., lam=1., c=.1, max_inner=1000):
+    """The examples/hjbqvi/exchange_rate.cpp wiring on the oracle.  The coarse axes come from the caller
+    (Axis::cluster goes through libm's asinh / sinh: the fixtures carry the reference's own ticks);
+    HJBQVI::solve(refinement) doubles the time steps per level and refines all three grids."""
+    X, Q, Z = (refine(np.asarray(ax, dtype=np.float64), refine_times) for ax in (x_axis, q_axis, z_axis))
+    p = Hjbqvi1d()
+    p.n_x, p.x, p.n_q, p.q, p.n_z, p.z = len(X), _dp(X), len(Q), _dp(Q), len(Z), _dp(Z)
+    p.T, p.timesteps = T, timesteps * 2 ** refine_times
+    p.rho, p.sigma, p.a, p.b, p.m, p.lam, p.c = rho, sigma, a, b, m, lam, c
+    p.scaling_factor, p.tolerance, p.max_inner = 1e-2, 1e-6, max_inner
+    V, Qs, Zs = np.zeros(len(X)), np.zeros(len(X)), np.zeros(len(X))
+    mask = np.zeros(len(X), dtype=np.uint8)
+    mean_inner, n_steps = C.c_double(), C.c_int()
+    status = lib().qpo_hjbqvi1d_solve(C.byref(p), _dp(V), _dp(Qs), _dp(Zs),
+                                      mask.ctypes.data_as(C.POINTER(C.c_ubyte)), C.byref(mean_inner), C.byref(n_steps))
+    return dict(X=X, QA=Q, ZA=Z, V=V, Q=Qs, Z=Zs, mask=mask, mean_inner=mean_inner.value,
+                n_steps=n_steps.value, status=status)
+
+
 JUMP_AXIS_EXTRA = 1000.0   # examples/jump_diffusion.cpp:166: + S_0 * Axis{1000.}
 
 

@@ -162,6 +162,22 @@ void qpo_gmwb_policy(qpo_gmwb_state *s, const double *xprev, int lo, int hi);
 double qpo_gmwb_sweep(qpo_gmwb_state *s, double *x, const double *v0, double h0, int lo, int hi);
 double qpo_gmwb_relerr(const qpo_gmwb *p, const double *x, const double *xprev, int lo, int hi);
 
+/* ---- 1-D impulse-control HJBQVI of examples/hjbqvi/exchange_rate.cpp (qpde_oracle_hjbqvi1d.c) ---- */
+typedef struct {
+	int n_x; const double *x;   /* refined spatial grid                              */
+	int n_q; const double *q;   /* stochastic control grid (interest-rate differential) */
+	int n_z; const double *z;   /* impulse control grid (the new state)              */
+	double T; int timesteps;
+	double rho, sigma, a, b, m, lambda, c;   /* exchange_rate.cpp:52-69               */
+	double scaling_factor;      /* HJBQVI default 1e-2: penalty = 1 / (this * dt)    */
+	double tolerance;           /* iteration_tolerance, 1e-6                         */
+	int max_inner;
+} qpo_hjbqvi1d;
+/* V, Q, Z [n_x] out (controls NaN where the other control acts), mask [n_x] out; any of Q, Z, mask
+ * may be NULL.  Returns 0, 1 (max_inner hit) or 2 (the lagged entries did not settle). */
+int qpo_hjbqvi1d_solve(const qpo_hjbqvi1d *p, double *V, double *Q, double *Z, unsigned char *mask,
+		double *mean_inner, int *n_steps);
+
 #ifdef __cplusplus
 }
 #endif

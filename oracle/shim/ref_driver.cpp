@@ -719,6 +719,70 @@ int runGmwb(const Args &a) {
 	return 0;
 }
 
+////////////////////////////////////////////////////////////////////////////////
+// exchange: the 1-D combined stochastic / impulse control of the exchange rate
+// (Mundaca & Oksendal), penalised scheme + BiCGSTAB, wired as
+// examples/hjbqvi/exchange_rate.cpp:29-175.  Dumps the coarse axes, the refined
+// grids, the solution, both control vectors (NaN where the other control acts,
+// HJBQVI.hpp:977-990) and the iteration statistics of HJBQVI::solve(refinement).
+////////////////////////////////////////////////////////////////////////////////
+
+int runExchange(const Args &a) {
+	constexpr int Dimension = 1, SC = 1, IC = 1;
+	const Real x_min = num(a, "x_min", -2.), x_max = num(a, "x_max", 2.), m = num(a, "m", 0.);
+	const Real q_min = num(a, "q_min", -.07), q_max = num(a, "q_max", .07);
+	const Real T = num(a, "T", 10.), rho = num(a, "rho", .02), sigma = num(a, "sigma", .3);
+	const Real aa = num(a, "a", .25), b = num(a, "b", 3.), lambda = num(a, "lambda", 1.), c = num(a, "c", .1);
+	const Real intensity = num(a, "intensity", 10.);
+	const int points = (int) integer(a, "points", 32);
+	const int q_points = (int) integer(a, "q_points", 9);
+	const int z_points = (int) integer(a, "z_points", 16);
+	const int timesteps = (int) integer(a, "timesteps", 16);
+	const int refinement = (int) integer(a, "refine", 0);
+
+	const Axis x = Axis::cluster(x_min, m, x_max, points, intensity);
+	const Axis w = Axis::uniform(q_min, q_max, q_points);
+	const Axis x_impulse = Axis::cluster(x_min, m, x_max, z_points, intensity);
+
+	HJBQVI<Dimension, SC, IC> hjbqvi(timesteps, { x }, { w }, { x_impulse }, T,
+		[=] (Real, Real) { return rho; },
+		{ [=] (Real, Real) { return sigma; } },
+		{ [=] (Real, Real, Real q) { return -aa * q; } },
+		[=] (Real, Real xv, Real q) { const Real tmp = xv - m; return - tmp * tmp - q * q * b; },
+		{ [=] (Real, Real, Real x_new) { return x_new; } },
+		[=] (Real, Real xv, Real x_new) {
+			if(std::abs(x_new - m) >= std::abs(xv - m)) return -std::numeric_limits<Real>::infinity();
+			return - lambda * std::fabs(x_new - xv) - c; },
+		[=] (Real, Real) { return 0.; });
+	hjbqvi.usePenalizedScheme();
+	hjbqvi.useBiCGSTABSolver();
+	hjbqvi.coefficientsAreTimeIndependent();
+
+	auto result = hjbqvi.solve(refinement);
+	PiecewiseLinear<Dimension> u(result.spatial_grid, result.solution_vector);
+	std::printf("value %a\n", (double) u.interpolate({{ m }}));
+	std::printf("seconds %.9g\n", (double) result.execution_time_seconds);
+	std::printf("steps %d\n", (int) result.timesteps);
+	std::printf("mean_inner %a\n", (double) result.mean_inner_iterations);
+	std::printf("mean_solver %a\n", (double) result.mean_solver_iterations);
+	std::vector<double> X0, Q0, Z0, X, QA, ZA, V, Q, Z;
+	for(Index i = 0; i < x.size(); ++i) X0.push_back(x[i]);
+	for(Index i = 0; i < w.size(); ++i) Q0.push_back(w[i]);
+	for(Index i = 0; i < x_impulse.size(); ++i) Z0.push_back(x_impulse[i]);
+	for(Index i = 0; i < result.spatial_grid[0].size(); ++i) X.push_back(result.spatial_grid[0][i]);
+	for(Index i = 0; i < result.stochastic_control_grid[0].size(); ++i) QA.push_back(result.stochastic_control_grid[0][i]);
+	for(Index i = 0; i < result.impulse_control_grid[0].size(); ++i) ZA.push_back(result.impulse_control_grid[0][i]);
+	for(Index i = 0; i < result.solution_vector.size(); ++i) {
+		V.push_back(result.solution_vector(i));
+		Q.push_back(result.stochastic_control_vector[0](i));
+		Z.push_back(result.impulse_control_vector[0](i));
+	}
+	dumpReals("X0", X0); dumpReals("Q0", Q0); dumpReals("Z0", Z0);
+	dumpReals("X", X); dumpReals("QA", QA); dumpReals("ZA", ZA);
+	dumpReals("V", V); dumpReals("Q", Q); dumpReals("Z", Z);
+	return 0;
+}
+
 void usage() {
 	std::fprintf(stderr,
 		"qpde_ref vanilla  K= S0= r= vol= q= T= steps= refine= american=0|1 [E= dividend= dividend_kind= dividend_first= exercise=] "
@@ -729,7 +793,8 @@ void usage() {
 		"scheme=bdf2|bdf1 repeat=\n"
 		"qpde_ref jump     K= S0= r= vol= q= T= lambda= steps= refine= density=lognormal|kou "
 		"mu= sd= p_up= eta1= eta2= scheme=bdf1|bdf2 repeat=\n"
-		"qpde_ref gmwb     T= r= eta= sigma= G= k= c= w0= timesteps= a_points= control_points= refine=\n");
+		"qpde_ref gmwb     T= r= eta= sigma= G= k= c= w0= timesteps= a_points= control_points= refine=\n"
+		"qpde_ref exchange x_min= x_max= m= q_min= q_max= T= rho= sigma= a= b= lambda= c= intensity= points= q_points= z_points= timesteps= refine=\n");
 }
 
 } // namespace
@@ -751,6 +816,7 @@ int main(int argc, char **argv) {
 	if(mode == "hjb")      return runHjb(a);
 	if(mode == "jump")     return runJump(a);
 	if(mode == "gmwb")     return runGmwb(a);
+	if(mode == "exchange") return runExchange(a);
 	usage();
 	return 2;
 }

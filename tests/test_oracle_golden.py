@@ -166,3 +166,38 @@ def test_gmwb_oracle_against_reference_fixtures(oracle):
         err = np.abs(o["V"] - ref) / np.maximum(1., np.abs(ref))
         assert err.max() <= 1e-9, "%s: %.3e" % (name, err.max())
         assert np.array_equal(o["W"], g[name + "/W"]) and np.array_equal(o["A"], g[name + "/A"])
+
+
+def _er_kwargs(args):
+    """`qpde_ref exchange` arguments -> keyword arguments of the model (oracle.exchange_rate / capi)."""
+    kw = {("lam" if k == "lambda" else k): v for k, v in args.items()
+          if k not in ("refine", "q_points", "z_points", "points", "timesteps")}
+    return dict(refine_times=args.get("refine", 0), timesteps=args.get("timesteps", 16), **kw)
+
+
+def test_hjbqvi1d_oracle_against_reference_fixtures(oracle):
+    """oracle/qpde_oracle_hjbqvi1d.c against the reference's own outputs of examples/hjbqvi/exchange_rate.cpp
+    (tests/golden/hjbqvi1d_reference.npz): grids bit-exact, every node within 1e-9 relative (measured: 1e-13),
+    identical "Mean Policy Iterations", identical control vectors and impulse regions."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "hjbqvi1d_reference.npz"))
+    for name in g["names"]:
+        name = str(name)
+        args = eval(str(g[name + "/args"]))
+        o = oracle.exchange_rate(g[name + "/X0"], g[name + "/Q0"], g[name + "/Z0"], **_er_kwargs(args))
+        assert o["status"] == 0 and o["n_steps"] == int(g[name + "/steps"]), name
+        for key in ("X", "QA", "ZA"):
+            assert np.array_equal(o[key], g[name + "/" + key]), (name, key)
+        ref = g[name + "/V"]
+        err = np.abs(o["V"] - ref) / np.maximum(1., np.abs(ref))
+        assert err.max() <= 1e-9, "%s: %.3e" % (name, err.max())
+        assert o["mean_inner"] == float(g[name + "/mean_inner"]), name
+        for key in ("Q", "Z"):
+            assert np.array_equal(o[key], g[name + "/" + key], equal_nan=True), (name, key)
+        assert np.array_equal(o["mask"] != 0, np.isnan(g[name + "/Q"])), name
+    # the convergence table of the example (the value at the parity m): -1.5954, -1.6018, -1.6001, -1.5988, -1.5980
+    vals = [float(g["er_k%d/value" % k]) for k in range(5)]
+    assert all(-1.61 < v < -1.59 for v in vals)
+    if oracle.have_ref():
+        ref = oracle.run_ref("exchange", refine=1)
+        assert np.array_equal(ref["V"], g["er_k1/V"])
