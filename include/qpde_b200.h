@@ -434,6 +434,50 @@ int qpde_gmwb2d_nodes(const qpde_gmwb2d *problem, int *nodes_w, int *nodes_a);
 int qpde_gmwb2d_solve(qpde_handle *h, const qpde_gmwb2d *problem, double *V,
 		double *W_out, double *A_out, qpde_gmwb2d_stats *stats);
 
+/* ---- 1-D impulse-control HJBQVI, penalised scheme: a batch of problems in one launch --------
+ * One call does what HJBQVI<1,1,1>::solve(refinement) does (Modules/HJBQVI/HJBQVI.hpp:590-811 with
+ * usePenalizedScheme(), useBiCGSTABSolver(), no boundary routines) for every problem of a batch; one CTA
+ * per problem, the whole sweep on chip (qpde_hjbqvi1d.cu).  The coefficient functions are tagged forms:
+ *   QPDE_HJBQVI1D_EXCHANGE_RATE   examples/hjbqvi/exchange_rate.cpp:118-152
+ *     params[7] = { rho, sigma, a, b, m, lambda, c }:  discount rho, volatility sigma, drift -a q,
+ *     flow -(x - m)^2 - b q^2, impulse x -> z with reward -lambda |z - x| - c (candidates with
+ *     |z - m| >= |x - m| are pruned), exit value 0
+ *   time    ReverseConstantStepper(0, T, T / timesteps), BDF1, ToleranceIteration(tolerance)
+ *   penalty 1 / (scaling_factor dt)
+ * Grids: the coarse axes refined `refine` times (RectilinearGrid::refined); `timesteps` is the count at
+ * this refinement (the reference doubles it per level).  An axis stride of 0 shares the axis. */
+#define QPDE_HJBQVI1D_EXCHANGE_RATE 1
+#define QPDE_HJBQVI1D_MAX_NODES 2048
+typedef struct {
+	int32_t abi_version;
+	int32_t model;            /* QPDE_HJBQVI1D_*                                         */
+	int32_t n_problems;
+	int32_t refine;
+	const double *x_axis;       int32_t n_x_axis;       int32_t reserved0; int64_t x_axis_stride;       /* state grid            */
+	const double *control_axis; int32_t n_control_axis; int32_t reserved1; int64_t control_axis_stride; /* stochastic controls q */
+	const double *impulse_axis; int32_t n_impulse_axis; int32_t reserved2; int64_t impulse_axis_stride; /* impulse controls z    */
+	const double *params;       int32_t n_params;       int32_t reserved3; int64_t params_stride;       /* [n_problems][n_params] */
+	double T; int32_t timesteps; int32_t max_inner;  /* inner-iteration guard per step       */
+	double scaling_factor;    /* HJBQVI default 1e-2                                     */
+	double tolerance;         /* iteration_tolerance, 1e-6                               */
+	int32_t max_sweeps;       /* guard of the linear solve's lagged sweeps, e.g. 500     */
+	int32_t reserved4;
+} qpde_hjbqvi1d_batch;
+
+/* HOST buffers, [n_problems][nodes] (any but V may be NULL); Q / Z are NaN where the other control
+ * acts (HJBQVI.hpp:977-990), mask is PenaltyMethod::constraintMask (PenaltyMethod.hpp:127-139). */
+typedef struct {
+	double *V, *X, *Q, *Z;
+	unsigned char *mask;
+	double *mean_inner;       /* [n_problems] "Mean Policy Iterations" of HJBQVI_main      */
+	int32_t *n_steps;         /* [n_problems]                                             */
+	int32_t *status;          /* [n_problems] 0 ok, 1 max_inner hit, 2 the lagged sweeps did not settle */
+} qpde_hjbqvi1d_result;
+
+/* Refined sizes for the buffers the caller allocates. */
+int qpde_hjbqvi1d_nodes(const qpde_hjbqvi1d_batch *batch, int *nodes, int *n_controls, int *n_impulses);
+int qpde_hjbqvi1d_solve(qpde_handle *h, const qpde_hjbqvi1d_batch *batch, qpde_hjbqvi1d_result *result);
+
 /* ---- GMWB sharded by the A-axis over the GPUs of a node: the library's own driver --------
  * One process per GPU.  A handle gets a communicator (NCCL over NVLink /
  * NVSwitch, loaded at run time): rank 0 makes an id with qpde_comm_unique_id, the caller ships the

@@ -119,6 +119,28 @@ class Gmwb2dStats(C.Structure):
     ]
 
 
+class Hjbqvi1dBatch(C.Structure):
+    _fields_ = [
+        ("abi_version", C.c_int32), ("model", C.c_int32), ("n_problems", C.c_int32), ("refine", C.c_int32),
+        ("x_axis", _dp), ("n_x_axis", C.c_int32), ("reserved0", C.c_int32), ("x_axis_stride", C.c_int64),
+        ("control_axis", _dp), ("n_control_axis", C.c_int32), ("reserved1", C.c_int32), ("control_axis_stride", C.c_int64),
+        ("impulse_axis", _dp), ("n_impulse_axis", C.c_int32), ("reserved2", C.c_int32), ("impulse_axis_stride", C.c_int64),
+        ("params", _dp), ("n_params", C.c_int32), ("reserved3", C.c_int32), ("params_stride", C.c_int64),
+        ("T", C.c_double), ("timesteps", C.c_int32), ("max_inner", C.c_int32),
+        ("scaling_factor", C.c_double), ("tolerance", C.c_double),
+        ("max_sweeps", C.c_int32), ("reserved4", C.c_int32),
+    ]
+
+
+class Hjbqvi1dResult(C.Structure):
+    _fields_ = [
+        ("V", _dp), ("X", _dp), ("Q", _dp), ("Z", _dp), ("mask", C.POINTER(C.c_ubyte)),
+        ("mean_inner", _dp), ("n_steps", C.POINTER(C.c_int32)), ("status", C.POINTER(C.c_int32)),
+    ]
+
+
+HJBQVI1D_EXCHANGE_RATE = 1
+
 # every symbol include/qpde_b200.h declares
 EXPORTS = [
     "qpde_abi_version", "qpde_create", "qpde_destroy", "qpde_last_error", "qpde_stream",
@@ -130,6 +152,7 @@ EXPORTS = [
     "qpde_gmwb2d_nodes", "qpde_gmwb2d_solve", "qpde_gmwb2d_solve_sharded", "qpde_comm_unique_id", "qpde_comm_init",
     "qpde_comm_destroy", "qpde_gmwb2d_shard_create", "qpde_gmwb2d_shard_destroy",
     "qpde_gmwb2d_shard_exit", "qpde_gmwb2d_shard_policy", "qpde_gmwb2d_shard_sweep", "qpde_gmwb2d_shard_relerr",
+    "qpde_hjbqvi1d_nodes", "qpde_hjbqvi1d_solve",
 ]
 
 _lib = None
@@ -191,6 +214,8 @@ def lib():
         L.qpde_gmwb2d_shard_policy.argtypes = [C.c_void_p, C.c_void_p, C.c_double]
         L.qpde_gmwb2d_shard_sweep.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         L.qpde_gmwb2d_shard_relerr.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.qpde_hjbqvi1d_nodes.argtypes = [C.POINTER(Hjbqvi1dBatch), C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]
+        L.qpde_hjbqvi1d_solve.argtypes = [C.c_void_p, C.POINTER(Hjbqvi1dBatch), C.POINTER(Hjbqvi1dResult)]
         _lib = L
     return _lib
 
@@ -386,6 +411,41 @@ def gmwb_solve(handle, w_axis, a_axis, controls, impulse_axis, refine, timesteps
           handle.ptr)
     return dict(V=V, W=W, A=A, n_steps=st.n_steps, mean_inner=st.mean_inner, status=st.status,
                 inner=inner[:st.n_steps].copy())
+
+
+def exchange_rate_solve(handle, x_axis, q_axis, z_axis, params, refine, timesteps, T=10., scaling_factor=1e-2,
+                        tolerance=1e-6, max_inner=200, max_sweeps=500):
+    """qpde_hjbqvi1d_solve for the exchange-rate model (examples/hjbqvi/exchange_rate.cpp): a batch of problems.
+    x_axis / q_axis / z_axis: coarse axes, one ([n]) shared by the batch or one per problem ([P][n]);
+    params: [P][7] = rho, sigma, a, b, m, lambda, c.  Host arrays in, host arrays out."""
+    params = np.ascontiguousarray(np.atleast_2d(params), dtype=np.float64)
+    P = params.shape[0]
+    axes = [np.ascontiguousarray(a, dtype=np.float64) for a in (x_axis, q_axis, z_axis)]
+    g = Hjbqvi1dBatch()
+    g.abi_version, g.model, g.n_problems, g.refine = ABI_VERSION, HJBQVI1D_EXCHANGE_RATE, P, int(refine)
+    for name, a in zip(("x", "control", "impulse"), axes):
+        if a.ndim == 2 and a.shape[0] != P:
+            raise ValueError("%s axis: one row per problem" % name)
+        setattr(g, name + "_axis", a.ctypes.data_as(_dp))
+        setattr(g, "n_%s_axis" % name, a.shape[-1])
+        setattr(g, name + "_axis_stride", a.shape[-1] if a.ndim == 2 else 0)
+    g.params, g.n_params, g.params_stride = params.ctypes.data_as(_dp), params.shape[1], params.shape[1]
+    g.T, g.timesteps, g.max_inner = T, int(timesteps), int(max_inner)
+    g.scaling_factor, g.tolerance, g.max_sweeps = scaling_factor, tolerance, int(max_sweeps)
+    n, nq, nz = C.c_int(), C.c_int(), C.c_int()
+    check(lib().qpde_hjbqvi1d_nodes(C.byref(g), C.byref(n), C.byref(nq), C.byref(nz)))
+    N = n.value
+    V, X, Q, Z = (np.zeros((P, N)) for _ in range(4))
+    mask = np.zeros((P, N), dtype=np.uint8)
+    mean_inner = np.zeros(P); n_steps = np.zeros(P, dtype=np.int32); status = np.zeros(P, dtype=np.int32)
+    r = Hjbqvi1dResult()
+    r.V, r.X, r.Q, r.Z = (a.ctypes.data_as(_dp) for a in (V, X, Q, Z))
+    r.mask = mask.ctypes.data_as(C.POINTER(C.c_ubyte))
+    r.mean_inner = mean_inner.ctypes.data_as(_dp)
+    r.n_steps = n_steps.ctypes.data_as(C.POINTER(C.c_int32)); r.status = status.ctypes.data_as(C.POINTER(C.c_int32))
+    check(lib().qpde_hjbqvi1d_solve(handle.ptr, C.byref(g), C.byref(r)), handle.ptr)
+    return dict(V=V, X=X, Q=Q, Z=Z, mask=mask, mean_inner=mean_inner, n_steps=n_steps, status=status,
+                n_controls=nq.value, n_impulses=nz.value)
 
 
 class BatchSpec:

@@ -821,6 +821,93 @@ int qpde_gmwb2d_nodes(const qpde_gmwb2d *g, int *nodes_w, int *nodes_a) {
 	return *nodes_w > 0 && *nodes_a > 0 ? QPDE_OK : QPDE_ERR_INVALID;
 }
 
+// ---- 1-D impulse-control HJBQVI (qpde_hjbqvi1d.cu) ------------------------------------------
+
+int qpde_hjbqvi1d_nodes(const qpde_hjbqvi1d_batch *g, int *nodes, int *n_controls, int *n_impulses) {
+	if(!g || !nodes) return QPDE_ERR_INVALID;
+	*nodes = qpde_refined_size(g->n_x_axis, g->refine);
+	if(n_controls) *n_controls = qpde_refined_size(g->n_control_axis, g->refine);
+	if(n_impulses) *n_impulses = qpde_refined_size(g->n_impulse_axis, g->refine);
+	return *nodes > 0 ? QPDE_OK : QPDE_ERR_INVALID;
+}
+
+int qpde_hjbqvi1d_solve(qpde_handle *h, const qpde_hjbqvi1d_batch *g, qpde_hjbqvi1d_result *res) {
+	if(!h) return fail(nullptr, QPDE_ERR_INVALID, "qpde_hjbqvi1d_solve: NULL handle");
+	if(!g || !res || !res->V) return fail(h, QPDE_ERR_INVALID, "qpde_hjbqvi1d_solve: NULL argument");
+	if(g->abi_version != QPDE_ABI_VERSION) return fail(h, QPDE_ERR_INVALID, "batch.abi_version %d != %d", g->abi_version, QPDE_ABI_VERSION);
+	if(g->model != QPDE_HJBQVI1D_EXCHANGE_RATE) return fail(h, QPDE_ERR_UNSUPPORTED, "hjbqvi1d: unknown model %d", g->model);
+	const int P = g->n_problems;
+	if(P < 1) return fail(h, QPDE_ERR_INVALID, "hjbqvi1d: n_problems must be >= 1");
+	if(g->refine < 0 || g->refine > 12) return fail(h, QPDE_ERR_INVALID, "hjbqvi1d: refine out of range");
+	if(!g->x_axis || g->n_x_axis < 3 || !g->control_axis || g->n_control_axis < 1 || !g->impulse_axis || g->n_impulse_axis < 1) {
+		return fail(h, QPDE_ERR_INVALID, "hjbqvi1d: axes missing (x needs >= 3 ticks, the control grids >= 1)");
+	}
+	if((g->x_axis_stride != 0 && g->x_axis_stride < g->n_x_axis) || (g->control_axis_stride != 0 && g->control_axis_stride < g->n_control_axis)
+			|| (g->impulse_axis_stride != 0 && g->impulse_axis_stride < g->n_impulse_axis)) return fail(h, QPDE_ERR_INVALID, "hjbqvi1d: axis stride below the axis length");
+	if(!g->params || g->n_params < 7 || (g->params_stride != 0 && g->params_stride < g->n_params)) return fail(h, QPDE_ERR_INVALID, "hjbqvi1d: the exchange-rate model takes 7 parameters per problem");
+	if(!(g->T > 0.) || g->timesteps < 1 || g->max_inner < 1 || g->max_sweeps < 1) return fail(h, QPDE_ERR_INVALID, "hjbqvi1d: T, timesteps, max_inner and max_sweeps must be positive");
+	if(!(g->scaling_factor > 0.) || !(g->tolerance > 0.)) return fail(h, QPDE_ERR_INVALID, "hjbqvi1d: scaling_factor and tolerance must be > 0");
+	const int N = qpde_refined_size(g->n_x_axis, g->refine);
+	const int single = g->n_control_axis < 2 ? 0 : g->refine, single_z = g->n_impulse_axis < 2 ? 0 : g->refine;
+	const int nq = qpde_refined_size(g->n_control_axis, single), nz = qpde_refined_size(g->n_impulse_axis, single_z);
+	if(N > QPDE_HJBQVI1D_MAX_NODES) return fail(h, QPDE_ERR_UNSUPPORTED, "hjbqvi1d: %d nodes, at most %d", N, QPDE_HJBQVI1D_MAX_NODES);
+	if(hjbqvi1d_shared_bytes(nq, nz) > (size_t)227 * 1024) return fail(h, QPDE_ERR_UNSUPPORTED, "hjbqvi1d: %d + %d control nodes do not fit the shared memory of an SM", nq, nz);
+	for(int p = 0; p < P; ++p) {
+		const double *ax[3] = { g->x_axis + (size_t)p * g->x_axis_stride, g->control_axis + (size_t)p * g->control_axis_stride, g->impulse_axis + (size_t)p * g->impulse_axis_stride };
+		const int len[3] = { g->n_x_axis, g->n_control_axis, g->n_impulse_axis };
+		for(int k = 0; k < 3; ++k) for(int i = 1; i < len[k]; ++i) if(!(ax[k][i] > ax[k][i - 1])) return fail(h, QPDE_ERR_INVALID, "hjbqvi1d: problem %d: axis %d is not strictly increasing", p, k);
+		const double *pp = g->params + (size_t)p * g->params_stride;
+		if(!(pp[1] >= 0.)) return fail(h, QPDE_ERR_INVALID, "hjbqvi1d: problem %d: sigma < 0", p);
+	}
+	QPDE_CUDA(h, cudaSetDevice(h->device));
+	// device copies: inputs in one block, outputs in another
+	const size_t nx_in = (g->x_axis_stride ? (size_t)P : 1) * g->n_x_axis, nq_in = (g->control_axis_stride ? (size_t)P : 1) * g->n_control_axis;
+	const size_t nz_in = (g->impulse_axis_stride ? (size_t)P : 1) * g->n_impulse_axis, np_in = (g->params_stride ? (size_t)P : 1) * g->n_params;
+	std::vector<double> in(nx_in + nq_in + nz_in + np_in);
+	auto pack = [&](double *dst, const double *src, long long stride, int len, size_t total) {
+		if(stride == 0) { memcpy(dst, src, sizeof(double) * len); return; }
+		for(size_t p = 0; p * len < total; ++p) memcpy(dst + p * len, src + p * (size_t)stride, sizeof(double) * len);
+	};
+	pack(in.data(), g->x_axis, g->x_axis_stride, g->n_x_axis, nx_in);
+	pack(in.data() + nx_in, g->control_axis, g->control_axis_stride, g->n_control_axis, nq_in);
+	pack(in.data() + nx_in + nq_in, g->impulse_axis, g->impulse_axis_stride, g->n_impulse_axis, nz_in);
+	pack(in.data() + nx_in + nq_in + nz_in, g->params, g->params_stride, g->n_params, np_in);
+	const size_t PN = (size_t)P * N;
+	const size_t out_bytes = sizeof(double) * (4 * PN + P) + sizeof(int) * 2 * (size_t)P + PN;
+	double *d_in = nullptr; unsigned char *d_out = nullptr;
+	QPDE_CUDA(h, cudaMalloc((void **)&d_in, sizeof(double) * in.size()));
+	if(cudaMalloc((void **)&d_out, out_bytes) != cudaSuccess) { cudaFree(d_in); return fail(h, QPDE_ERR_CUDA, "hjbqvi1d: out of device memory"); }
+	int rc = QPDE_OK;
+	do {
+		if(cudaMemcpyAsync(d_in, in.data(), sizeof(double) * in.size(), cudaMemcpyHostToDevice, h->stream) != cudaSuccess) { rc = QPDE_ERR_CUDA; break; }
+		Hjbqvi1dBatch b;
+		b.n_problems = P; b.model = g->model; b.N = N; b.nq = nq; b.nz = nz;
+		b.refine = g->refine; b.refine_q = single; b.refine_z = single_z;
+		b.x_axis = d_in; b.q_axis = d_in + nx_in; b.z_axis = d_in + nx_in + nq_in; b.params = d_in + nx_in + nq_in + nz_in;
+		b.x_axis_stride = g->x_axis_stride ? g->n_x_axis : 0; b.q_axis_stride = g->control_axis_stride ? g->n_control_axis : 0;
+		b.z_axis_stride = g->impulse_axis_stride ? g->n_impulse_axis : 0; b.params_stride = g->params_stride ? g->n_params : 0;
+		b.T = g->T; b.timesteps = g->timesteps; b.max_inner = g->max_inner; b.max_sweeps = g->max_sweeps;
+		b.scaling_factor = g->scaling_factor; b.tolerance = g->tolerance;
+		Hjbqvi1dResult o;
+		double *dd = reinterpret_cast<double *>(d_out);
+		o.V = dd; o.X = dd + PN; o.Q = dd + 2 * PN; o.Z = dd + 3 * PN; o.mean_inner = dd + 4 * PN;
+		o.n_steps = reinterpret_cast<int *>(dd + 4 * PN + P); o.status = o.n_steps + P;
+		o.mask = reinterpret_cast<unsigned char *>(o.status + P);
+		rc = launch_hjbqvi1d(b, o, h->stream, &h->launches);
+		if(rc != QPDE_OK) break;
+		auto fetch = [&](void *dst, const void *src, size_t bytes) { return !dst || cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, h->stream) == cudaSuccess; };
+		const bool ok = fetch(res->V, o.V, sizeof(double) * PN) && fetch(res->X, o.X, sizeof(double) * PN) && fetch(res->Q, o.Q, sizeof(double) * PN)
+			&& fetch(res->Z, o.Z, sizeof(double) * PN) && fetch(res->mask, o.mask, PN) && fetch(res->mean_inner, o.mean_inner, sizeof(double) * P)
+			&& fetch(res->n_steps, o.n_steps, sizeof(int) * P) && fetch(res->status, o.status, sizeof(int) * P);
+		if(!ok || cudaStreamSynchronize(h->stream) != cudaSuccess) rc = QPDE_ERR_CUDA;
+	} while(0);
+	const cudaError_t last = cudaGetLastError();
+	cudaFree(d_in); cudaFree(d_out);
+	if(rc == QPDE_ERR_UNSUPPORTED) return fail(h, rc, "hjbqvi1d: this grid / model is not covered by the kernel");
+	if(rc != QPDE_OK) return fail(h, rc, "hjbqvi1d: CUDA error: %s", cudaGetErrorString(last));
+	return QPDE_OK;
+}
+
 int qpde_comm_unique_id(unsigned char id[QPDE_COMM_ID_BYTES]) {
 	if(!id) return fail(nullptr, QPDE_ERR_INVALID, "qpde_comm_unique_id: NULL argument");
 	std::string error;

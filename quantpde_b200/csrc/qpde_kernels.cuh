@@ -127,6 +127,23 @@ void gmwb_shard_policy(GmwbShard *sh, const double *x, double h0);
 cudaError_t gmwb_shard_sweep(GmwbShard *sh, double *x, const double *v0, int *status_dev);
 void gmwb_shard_relerr(GmwbShard *sh, const double *x, const double *xprev, int *notdone_dev);
 
+// 1-D impulse-control HJBQVI (qpde_hjbqvi1d.cu): one CTA per problem.  Device pointers.
+struct Hjbqvi1dBatch {
+	int n_problems, model, N, nq, nz;
+	int refine, refine_q, refine_z;
+	const double *x_axis, *q_axis, *z_axis; long long x_axis_stride, q_axis_stride, z_axis_stride;   // coarse axes per problem (stride 0: shared)
+	const double *params; long long params_stride;
+	double T; int timesteps, max_inner, max_sweeps;
+	double scaling_factor, tolerance;
+};
+struct Hjbqvi1dResult {
+	double *V, *X, *Q, *Z;          // [n_problems][N]; any may be null
+	unsigned char *mask;
+	double *mean_inner; int *n_steps, *status;
+};
+size_t hjbqvi1d_shared_bytes(int nq, int nz);
+int launch_hjbqvi1d(const Hjbqvi1dBatch &b, const Hjbqvi1dResult &out, cudaStream_t stream, long long *launches);
+
 // FP64 pipe rate of this device, measured (qpde_peak.cu)
 int measure_fp64_peak(int sm_count, cudaStream_t stream, double *tflops, long long *launches);
 

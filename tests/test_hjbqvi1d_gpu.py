@@ -1,0 +1,80 @@
+"""GPU: the 1-D impulse-control HJBQVI of examples/hjbqvi/exchange_rate.cpp through the C ABI
+(qpde_hjbqvi1d_solve, one CTA per problem) against the reference's own outputs
+(tests/golden/hjbqvi1d_reference.npz, made by `qpde_ref exchange` on the unmodified reference headers)
+and against the oracle."""
+import os
+
+import numpy as np
+import pytest
+
+from helpers import REL_TOL
+from test_oracle_golden import _er_kwargs
+
+pytestmark = pytest.mark.gpu
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "hjbqvi1d_reference.npz")
+DEFAULTS = dict(rho=.02, sigma=.3, a=.25, b=3., m=0., lam=1., c=.1)
+
+
+def _params(kw):
+    p = dict(DEFAULTS); p.update({k: v for k, v in kw.items() if k in DEFAULTS})
+    return [p[k] for k in ("rho", "sigma", "a", "b", "m", "lam", "c")]
+
+
+def test_exchange_rate_against_reference_fixtures(qpde, handle):
+    g = np.load(GOLDEN)
+    for name in g["names"]:
+        name = str(name)
+        kw = _er_kwargs(eval(str(g[name + "/args"])))
+        res = qpde.exchange_rate_solve(handle, g[name + "/X0"], g[name + "/Q0"], g[name + "/Z0"], [_params(kw)],
+                                       kw["refine_times"], kw["timesteps"] * 2 ** kw["refine_times"], T=kw.get("T", 10.))
+        assert res["status"][0] == 0 and res["n_steps"][0] == int(g[name + "/steps"]), name
+        assert np.array_equal(res["X"][0], g[name + "/X"]), name
+        ref = g[name + "/V"]
+        err = np.abs(res["V"][0] - ref) / np.maximum(1., np.abs(ref))
+        assert err.max() <= REL_TOL, "%s: %.3e" % (name, err.max())
+        assert res["mean_inner"][0] == float(g[name + "/mean_inner"]), name     # "Mean Policy Iterations"
+        # the impulse region and both control vectors, NaN where the other control acts
+        assert np.array_equal(res["mask"][0] != 0, np.isnan(g[name + "/Q"])), name
+        for key in ("Q", "Z"):
+            assert np.array_equal(res[key][0], g[name + "/" + key], equal_nan=True), (name, key)
+
+
+def test_exchange_rate_batch_of_problems_against_oracle(qpde, handle, oracle):
+    """A batch with per-problem parameters and per-problem grids (the parity m moves the clustering) in one
+    launch; refinement 5 (993 nodes, 512 steps) for one of them against the oracle."""
+    g = np.load(GOLDEN)
+    X0, Q0, Z0 = g["er_k0/X0"], g["er_k0/Q0"], g["er_k0/Z0"]
+    rng = np.random.default_rng(7)
+    P = 12
+    par = np.array([[.02 + .03 * rng.random(), .2 + .2 * rng.random(), .1 + .4 * rng.random(), 1. + 3. * rng.random(),
+                     0., .5 + rng.random(), .05 + .1 * rng.random()] for _ in range(P)])
+    res = qpde.exchange_rate_solve(handle, X0, Q0, Z0, par, 2, 64)
+    for p in range(P):
+        o = oracle.exchange_rate(X0, Q0, Z0, refine_times=2, **dict(zip(("rho", "sigma", "a", "b", "m", "lam", "c"), par[p])))
+        assert res["status"][p] == 0 and o["status"] == 0 and res["n_steps"][p] == o["n_steps"]
+        err = np.abs(res["V"][p] - o["V"]) / np.maximum(1., np.abs(o["V"]))
+        assert err.max() <= REL_TOL, "problem %d: %.3e" % (p, err.max())
+        assert res["mean_inner"][p] == o["mean_inner"], p
+        assert np.array_equal(res["mask"][p], o["mask"]), p
+    # per-problem axes: the off-centre fixture next to the centred one
+    Xs = np.stack([g["er_k1/X0"], g["er_parity_off_centre/X0"]]); Zs = np.stack([g["er_k1/Z0"], g["er_parity_off_centre/Z0"]])
+    two = qpde.exchange_rate_solve(handle, Xs, g["er_k1/Q0"], Zs, [_params({}), _params(dict(m=.25))], 1, 32)
+    for p, name in enumerate(("er_k1", "er_parity_off_centre")):
+        err = np.abs(two["V"][p] - g[name + "/V"]) / np.maximum(1., np.abs(g[name + "/V"]))
+        assert err.max() <= REL_TOL and two["mean_inner"][p] == float(g[name + "/mean_inner"]), name
+    big = qpde.exchange_rate_solve(handle, X0, Q0, Z0, [_params({})], 5, 512)
+    o = oracle.exchange_rate(X0, Q0, Z0, refine_times=5)
+    err = np.abs(big["V"][0] - o["V"]) / np.maximum(1., np.abs(o["V"]))
+    assert big["status"][0] == 0 and err.max() <= REL_TOL and big["mean_inner"][0] == o["mean_inner"]
+
+
+def test_exchange_rate_errors(qpde, handle):
+    g = np.load(GOLDEN)
+    X0, Q0, Z0 = g["er_k0/X0"], g["er_k0/Q0"], g["er_k0/Z0"]
+    with pytest.raises(qpde.QpdeError):      # 7 refinements: 3969 nodes
+        qpde.exchange_rate_solve(handle, X0, Q0, Z0, [_params({})], 7, 2048)
+    with pytest.raises(qpde.QpdeError):
+        qpde.exchange_rate_solve(handle, X0[::-1], Q0, Z0, [_params({})], 0, 16)
+    with pytest.raises(qpde.QpdeError):
+        qpde.exchange_rate_solve(handle, X0, Q0, Z0, [[.02, .3, .25]], 0, 16)
