@@ -447,7 +447,7 @@ int qpde_gmwb2d_solve(qpde_handle *h, const qpde_gmwb2d *problem, double *V,
  * Grids: the coarse axes refined `refine` times (RectilinearGrid::refined); `timesteps` is the count at
  * this refinement (the reference doubles it per level).  An axis stride of 0 shares the axis. */
 #define QPDE_HJBQVI1D_EXCHANGE_RATE 1
-#define QPDE_HJBQVI1D_MAX_NODES 2048
+#define QPDE_HJBQVI1D_MAX_NODES 2304
 typedef struct {
 	int32_t abi_version;
 	int32_t model;            /* QPDE_HJBQVI1D_*                                         */
@@ -470,6 +470,7 @@ typedef struct {
 	double *V, *X, *Q, *Z;
 	unsigned char *mask;
 	double *mean_inner;       /* [n_problems] "Mean Policy Iterations" of HJBQVI_main      */
+	double *mean_sweeps;      /* [n_problems] tridiagonal solves per policy iteration (the reference reports BiCGSTAB's "Mean Solver Iterations" there) */
 	int32_t *n_steps;         /* [n_problems]                                             */
 	int32_t *status;          /* [n_problems] 0 ok, 1 max_inner hit, 2 the lagged sweeps did not settle */
 } qpde_hjbqvi1d_result;

@@ -135,7 +135,7 @@ class Hjbqvi1dBatch(C.Structure):
 class Hjbqvi1dResult(C.Structure):
     _fields_ = [
         ("V", _dp), ("X", _dp), ("Q", _dp), ("Z", _dp), ("mask", C.POINTER(C.c_ubyte)),
-        ("mean_inner", _dp), ("n_steps", C.POINTER(C.c_int32)), ("status", C.POINTER(C.c_int32)),
+        ("mean_inner", _dp), ("mean_sweeps", _dp), ("n_steps", C.POINTER(C.c_int32)), ("status", C.POINTER(C.c_int32)),
     ]
 
 
@@ -437,14 +437,14 @@ def exchange_rate_solve(handle, x_axis, q_axis, z_axis, params, refine, timestep
     N = n.value
     V, X, Q, Z = (np.zeros((P, N)) for _ in range(4))
     mask = np.zeros((P, N), dtype=np.uint8)
-    mean_inner = np.zeros(P); n_steps = np.zeros(P, dtype=np.int32); status = np.zeros(P, dtype=np.int32)
+    mean_inner = np.zeros(P); mean_sweeps = np.zeros(P); n_steps = np.zeros(P, dtype=np.int32); status = np.zeros(P, dtype=np.int32)
     r = Hjbqvi1dResult()
     r.V, r.X, r.Q, r.Z = (a.ctypes.data_as(_dp) for a in (V, X, Q, Z))
     r.mask = mask.ctypes.data_as(C.POINTER(C.c_ubyte))
-    r.mean_inner = mean_inner.ctypes.data_as(_dp)
+    r.mean_inner = mean_inner.ctypes.data_as(_dp); r.mean_sweeps = mean_sweeps.ctypes.data_as(_dp)
     r.n_steps = n_steps.ctypes.data_as(C.POINTER(C.c_int32)); r.status = status.ctypes.data_as(C.POINTER(C.c_int32))
     check(lib().qpde_hjbqvi1d_solve(handle.ptr, C.byref(g), C.byref(r)), handle.ptr)
-    return dict(V=V, X=X, Q=Q, Z=Z, mask=mask, mean_inner=mean_inner, n_steps=n_steps, status=status,
+    return dict(V=V, X=X, Q=Q, Z=Z, mask=mask, mean_inner=mean_inner, mean_sweeps=mean_sweeps, n_steps=n_steps, status=status,
                 n_controls=nq.value, n_impulses=nz.value)
 
 

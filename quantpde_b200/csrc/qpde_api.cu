@@ -851,7 +851,7 @@ int qpde_hjbqvi1d_solve(qpde_handle *h, const qpde_hjbqvi1d_batch *g, qpde_hjbqv
 	const int single = g->n_control_axis < 2 ? 0 : g->refine, single_z = g->n_impulse_axis < 2 ? 0 : g->refine;
 	const int nq = qpde_refined_size(g->n_control_axis, single), nz = qpde_refined_size(g->n_impulse_axis, single_z);
 	if(N > QPDE_HJBQVI1D_MAX_NODES) return fail(h, QPDE_ERR_UNSUPPORTED, "hjbqvi1d: %d nodes, at most %d", N, QPDE_HJBQVI1D_MAX_NODES);
-	if(hjbqvi1d_shared_bytes(nq, nz) > (size_t)227 * 1024) return fail(h, QPDE_ERR_UNSUPPORTED, "hjbqvi1d: %d + %d control nodes do not fit the shared memory of an SM", nq, nz);
+	if(hjbqvi1d_shared_bytes(N, nq, nz) > (size_t)227 * 1024) return fail(h, QPDE_ERR_UNSUPPORTED, "hjbqvi1d: %d + %d control nodes do not fit the shared memory of an SM", nq, nz);
 	for(int p = 0; p < P; ++p) {
 		const double *ax[3] = { g->x_axis + (size_t)p * g->x_axis_stride, g->control_axis + (size_t)p * g->control_axis_stride, g->impulse_axis + (size_t)p * g->impulse_axis_stride };
 		const int len[3] = { g->n_x_axis, g->n_control_axis, g->n_impulse_axis };
@@ -873,7 +873,7 @@ int qpde_hjbqvi1d_solve(qpde_handle *h, const qpde_hjbqvi1d_batch *g, qpde_hjbqv
 	pack(in.data() + nx_in + nq_in, g->impulse_axis, g->impulse_axis_stride, g->n_impulse_axis, nz_in);
 	pack(in.data() + nx_in + nq_in + nz_in, g->params, g->params_stride, g->n_params, np_in);
 	const size_t PN = (size_t)P * N;
-	const size_t out_bytes = sizeof(double) * (4 * PN + P) + sizeof(int) * 2 * (size_t)P + PN;
+	const size_t out_bytes = sizeof(double) * (4 * PN + 2 * P) + sizeof(int) * 2 * (size_t)P + PN;
 	double *d_in = nullptr; unsigned char *d_out = nullptr;
 	QPDE_CUDA(h, cudaMalloc((void **)&d_in, sizeof(double) * in.size()));
 	if(cudaMalloc((void **)&d_out, out_bytes) != cudaSuccess) { cudaFree(d_in); return fail(h, QPDE_ERR_CUDA, "hjbqvi1d: out of device memory"); }
@@ -890,14 +890,14 @@ int qpde_hjbqvi1d_solve(qpde_handle *h, const qpde_hjbqvi1d_batch *g, qpde_hjbqv
 		b.scaling_factor = g->scaling_factor; b.tolerance = g->tolerance;
 		Hjbqvi1dResult o;
 		double *dd = reinterpret_cast<double *>(d_out);
-		o.V = dd; o.X = dd + PN; o.Q = dd + 2 * PN; o.Z = dd + 3 * PN; o.mean_inner = dd + 4 * PN;
-		o.n_steps = reinterpret_cast<int *>(dd + 4 * PN + P); o.status = o.n_steps + P;
+		o.V = dd; o.X = dd + PN; o.Q = dd + 2 * PN; o.Z = dd + 3 * PN; o.mean_inner = dd + 4 * PN; o.mean_sweeps = dd + 4 * PN + P;
+		o.n_steps = reinterpret_cast<int *>(dd + 4 * PN + 2 * P); o.status = o.n_steps + P;
 		o.mask = reinterpret_cast<unsigned char *>(o.status + P);
 		rc = launch_hjbqvi1d(b, o, h->stream, &h->launches);
 		if(rc != QPDE_OK) break;
 		auto fetch = [&](void *dst, const void *src, size_t bytes) { return !dst || cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, h->stream) == cudaSuccess; };
 		const bool ok = fetch(res->V, o.V, sizeof(double) * PN) && fetch(res->X, o.X, sizeof(double) * PN) && fetch(res->Q, o.Q, sizeof(double) * PN)
-			&& fetch(res->Z, o.Z, sizeof(double) * PN) && fetch(res->mask, o.mask, PN) && fetch(res->mean_inner, o.mean_inner, sizeof(double) * P)
+			&& fetch(res->Z, o.Z, sizeof(double) * PN) && fetch(res->mask, o.mask, PN) && fetch(res->mean_inner, o.mean_inner, sizeof(double) * P) && fetch(res->mean_sweeps, o.mean_sweeps, sizeof(double) * P)
 			&& fetch(res->n_steps, o.n_steps, sizeof(int) * P) && fetch(res->status, o.status, sizeof(int) * P);
 		if(!ok || cudaStreamSynchronize(h->stream) != cudaSuccess) rc = QPDE_ERR_CUDA;
 	} while(0);

@@ -30,7 +30,7 @@ namespace qpde {
 
 namespace {
 
-constexpr int HM = 8, HP = 256, HMP = HM * HP;   // rows per thread, threads, rows of a system
+constexpr int HP = 256;   // threads per problem; M rows per thread (8: up to 2048 nodes, 9: up to 2304), MP = M * HP rows of a system
 
 // model 1: examples/hjbqvi/exchange_rate.cpp:118-152
 struct ExchangeRate {
@@ -50,29 +50,31 @@ struct ExchangeRate {
 };
 
 // node i of a node-addressable shared-memory array: the rows of one thread are HP doubles apart
-__device__ __forceinline__ int slot(int i) { return (i & (HM - 1)) * HP + (i >> 3); }
+template <int M>
+__device__ __forceinline__ int slot(int i) { return (i % M) * HP + (i / M); }
 
 struct Hjbqvi1dSmem {
 	PartitionSmem ps;
-	int n_steps, status; long long inner_sum;
+	int n_steps, status; long long inner_sum, sweep_sum;
 };
 
 // shared memory: 7 row arrays + the control grids and the per-candidate tables (doubles), then two int arrays
-__host__ __device__ inline size_t hjbqvi1d_smem_bytes(int nq, int nz) {
-	return ((sizeof(Hjbqvi1dSmem) + 15) / 16) * 16 + sizeof(double) * ((size_t)7 * HMP + nq + 5 * (size_t)nz) + sizeof(int) * ((size_t)HMP + nz);
+__host__ __device__ inline size_t hjbqvi1d_smem_bytes(int M, int nq, int nz) {
+	return ((sizeof(Hjbqvi1dSmem) + 15) / 16) * 16 + sizeof(double) * ((size_t)7 * M * HP + nq + 5 * (size_t)nz) + sizeof(int) * ((size_t)M * HP + nz);
 }
 
 // linearInterpolationData (Core/Interpolant.hpp:153-181) over a node-addressable grid
+template <int M>
 __device__ __forceinline__ void interp_nodes(const double *sX, int n, double ci, int &idx, double &w) {
-	if(ci <= sX[slot(0)]) { idx = 0; w = 1.; return; }
-	if(ci >= sX[slot(n - 1)]) { idx = n - 2; w = 0.; return; }
+	if(ci <= sX[slot<M>(0)]) { idx = 0; w = 1.; return; }
+	if(ci >= sX[slot<M>(n - 1)]) { idx = n - 2; w = 0.; return; }
 	int lo = 0, hi = n - 2, mid = 0;
 	w = 0.;
 	while(lo <= hi) {
 		mid = (lo + hi) / 2;
-		if(ci < sX[slot(mid)]) hi = mid - 1;
-		else if(ci >= sX[slot(mid + 1)]) lo = mid + 1;
-		else { w = (sX[slot(mid + 1)] - ci) / (sX[slot(mid + 1)] - sX[slot(mid)]); break; }
+		if(ci < sX[slot<M>(mid)]) hi = mid - 1;
+		else if(ci >= sX[slot<M>(mid + 1)]) lo = mid + 1;
+		else { w = (sX[slot<M>(mid + 1)] - ci) / (sX[slot<M>(mid + 1)] - sX[slot<M>(mid)]); break; }
 	}
 	idx = mid;
 }
@@ -88,12 +90,13 @@ __device__ __forceinline__ double impulse_lhs(int row, int idx, double w, double
 
 } // namespace
 
-template <typename Model>
+template <typename Model, int M>
 __global__ void __launch_bounds__(HP, 1)
 k_hjbqvi1d(Hjbqvi1dBatch b, Hjbqvi1dResult out) {
+	constexpr int HM = M, HMP = M * HP;
 	extern __shared__ __align__(16) unsigned char smem_raw[];
 	Hjbqvi1dSmem &sm = *reinterpret_cast<Hjbqvi1dSmem *>(smem_raw);
-	double *const sX = reinterpret_cast<double *>(smem_raw + ((sizeof(Hjbqvi1dSmem) + 15) / 16) * 16);   // grid, node-addressable (slot())
+	double *const sX = reinterpret_cast<double *>(smem_raw + ((sizeof(Hjbqvi1dSmem) + 15) / 16) * 16);   // grid, node-addressable (slot<M>())
 	double *const sx = sX + HMP;          // current iterate, node-addressable
 	double *const r_b = sx + HMP;         // [j][tid]: the flow b^q* of the chosen stochastic control ...
 	double *const r_q = r_b + HMP;        // ... and the control itself
@@ -119,14 +122,14 @@ k_hjbqvi1d(Hjbqvi1dBatch b, Hjbqvi1dResult out) {
 	const double *const zaxis = b.z_axis + (size_t)pidx * b.z_axis_stride;
 
 	// ---- set-up: refined grids (RectilinearGrid::refined, Core/Domain.hpp:1092-1151), targets
-	for(int i = tid; i < HMP; i += HP) sX[slot(i)] = i < N ? refined_node(xaxis, b.refine, i) : 0.;
+	for(int i = tid; i < HMP; i += HP) sX[slot<M>(i)] = i < N ? refined_node(xaxis, b.refine, i) : 0.;
 	for(int k = tid; k < nq; k += HP) sq[k] = refined_node(qaxis, b.refine_q, k);
 	for(int k = tid; k < nz; k += HP) sz[k] = refined_node(zaxis, b.refine_z, k);
-	if(tid == 0) { sm.n_steps = 0; sm.status = 0; sm.inner_sum = 0; }
+	if(tid == 0) { sm.n_steps = 0; sm.status = 0; sm.inner_sum = 0; sm.sweep_sum = 0; }
 	__syncthreads();
 	for(int k = tid; k < nz; k += HP) {
 		int idx; double w;
-		interp_nodes(sX, N, mdl.transition(0., sz[k]), idx, w);      // node-independent transition (Model::transition ignores x)
+		interp_nodes<M>(sX, N, mdl.transition(0., sz[k]), idx, w);      // node-independent transition (Model::transition ignores x)
 		z_idx[k] = idx; z_w[k] = w;
 		sdz[k] = fabs(sz[k] - mdl.m);
 	}
@@ -157,8 +160,8 @@ k_hjbqvi1d(Hjbqvi1dBatch b, Hjbqvi1dResult out) {
 			__syncthreads();
 			for(int k = tid; k < nz; k += HP) {
 				const int idx = z_idx[k]; const double w = z_w[k];
-				sA[k] = (0. - w) * sx[slot(idx)];
-				sB[k] = (0. - (-w + 1.)) * sx[slot(idx + 1)];
+				sA[k] = (0. - w) * sx[slot<M>(idx)];
+				sB[k] = (0. - (-w + 1.)) * sx[slot<M>(idx + 1)];
 			}
 			__syncthreads();
 			active = 0; far = 0;
@@ -172,11 +175,11 @@ k_hjbqvi1d(Hjbqvi1dBatch b, Hjbqvi1dResult out) {
 				// 1. stochastic policy: argmin_q (A(q) x - b(q))_i, strict < (PolicyIteration.hpp:88-96)
 				double dxb = 1., dxc = 1., dxf = 1., alpha_common = 0., beta_common = 0., vm = 0., vp = 0.;
 				if(interior) {
-					const double xm = sX[slot(i - 1)], xp = sX[slot(i + 1)];
+					const double xm = sX[slot<M>(i - 1)], xp = sX[slot<M>(i + 1)];
 					dxb = xi - xm; dxc = xp - xm; dxf = xp - xi;
 					const double v = mdl.volatility(xi), vv = v * v;
 					alpha_common = vv / dxb / dxc; beta_common = vv / dxf / dxc;
-					vm = sx[slot(i - 1)]; vp = sx[slot(i + 1)];
+					vm = sx[slot<M>(i - 1)]; vp = sx[slot<M>(i + 1)];
 				}
 				const double rho = mdl.discount(xi);
 				double best = CUDART_INF, blo = 0., bup = 0., bdi = 0., bfl = 0., bq = 0.;
@@ -213,9 +216,9 @@ k_hjbqvi1d(Hjbqvi1dBatch b, Hjbqvi1dResult out) {
 				// (PolicyIteration.hpp:64-66 hands setInputs a fresh domain->vector())
 				double zsel, rew, wsel; int isel;
 				if(bk >= 0) { zsel = sz[bk]; isel = z_idx[bk]; wsel = z_w[bk]; }
-				else { zsel = 0.; interp_nodes(sX, N, mdl.transition(xi, 0.), isel, wsel); }
+				else { zsel = 0.; interp_nodes<M>(sX, N, mdl.transition(xi, 0.), isel, wsel); }
 				rew = mdl.impulse_flow(xi, zsel);
-				const double lhs = impulse_lhs(i, isel, wsel, vi, (0. - wsel) * sx[slot(isel)], (0. - (-wsel + 1.)) * sx[slot(isel + 1)]);
+				const double lhs = impulse_lhs(i, isel, wsel, vi, (0. - wsel) * sx[slot<M>(isel)], (0. - (-wsel + 1.)) * sx[slot<M>(isel + 1)]);
 				// 3. penalty: active iff scale * ((I - M*) x - reward*) < 0 (PenaltyMethod.hpp:45-68)
 				const bool act = (pen * (lhs - rew)) < 0.;
 				i_k[at] = isel; i_z[at] = zsel; i_rew[at] = rew; i_w[at] = wsel;
@@ -245,8 +248,8 @@ k_hjbqvi1d(Hjbqvi1dBatch b, Hjbqvi1dResult out) {
 						if(active >> j & 1u) {
 							r_ += pen * i_rew[at];
 							const int isel = i_k[at]; const double wsel = i_w[at];
-							if(far >> (2 * j) & 1u) r_ += (pen * wsel) * sx[slot(isel)];
-							if(far >> (2 * j + 1) & 1u) r_ += (pen * (-wsel + 1.)) * sx[slot(isel + 1)];
+							if(far >> (2 * j) & 1u) r_ += (pen * wsel) * sx[slot<M>(isel)];
+							if(far >> (2 * j + 1) & 1u) r_ += (pen * (-wsel + 1.)) * sx[slot<M>(isel + 1)];
 						}
 					}
 					r[j] = r_;
@@ -267,6 +270,7 @@ k_hjbqvi1d(Hjbqvi1dBatch b, Hjbqvi1dResult out) {
 				++sweep;
 			} while(unsettled && sweep < b.max_sweeps);
 			if(unsettled && tid == 0) sm.status = 2;
+			if(tid == 0) sm.sweep_sum += sweep;
 			++its;
 			// relativeError(iterand(0), iterand(1)) > tolerance (IterativeMethod.hpp:1125-1137, scale 1)
 			bool nd = false;
@@ -293,28 +297,30 @@ k_hjbqvi1d(Hjbqvi1dBatch b, Hjbqvi1dResult out) {
 		if(i >= N) continue;
 		const size_t o = (size_t)pidx * N + i;
 		const int isel = i_k[at]; const double wsel = i_w[at];
-		const double lhs = impulse_lhs(i, isel, wsel, x[j], (0. - wsel) * sx[slot(isel)], (0. - (-wsel + 1.)) * sx[slot(isel + 1)]);
+		const double lhs = impulse_lhs(i, isel, wsel, x[j], (0. - wsel) * sx[slot<M>(isel)], (0. - (-wsel + 1.)) * sx[slot<M>(isel + 1)]);
 		const bool act = lhs - i_rew[at] < 0.;
 		if(out.V) out.V[o] = x[j];
 		if(out.X) out.X[o] = sX[at];
 		if(out.mask) out.mask[o] = act ? 1 : 0;
-		if(out.Q) out.Q[o] = act ? CUDART_NAN : r_q[at];
-		if(out.Z) out.Z[o] = act ? i_z[at] : CUDART_NAN;
+		const double qnan = __longlong_as_double(0x7ff8000000000000LL);      // std::nan(""): the positive quiet NaN
+		if(out.Q) out.Q[o] = act ? qnan : r_q[at];
+		if(out.Z) out.Z[o] = act ? i_z[at] : qnan;
 	}
 	if(tid == 0) {
 		if(out.n_steps) out.n_steps[pidx] = sm.n_steps;
 		if(out.mean_inner) out.mean_inner[pidx] = (double)sm.inner_sum / (double)sm.n_steps;
+		if(out.mean_sweeps) out.mean_sweeps[pidx] = (double)sm.sweep_sum / (double)sm.inner_sum;
 		if(out.status) out.status[pidx] = sm.status;
 	}
 }
 
-size_t hjbqvi1d_shared_bytes(int nq, int nz) { return hjbqvi1d_smem_bytes(nq, nz); }
+size_t hjbqvi1d_shared_bytes(int N, int nq, int nz) { return hjbqvi1d_smem_bytes(N <= 8 * HP ? 8 : 9, nq, nz); }
 
 int launch_hjbqvi1d(const Hjbqvi1dBatch &b, const Hjbqvi1dResult &out, cudaStream_t stream, long long *launches) {
-	if(b.N < 3 || b.N > HMP || b.model != QPDE_HJBQVI1D_EXCHANGE_RATE) return QPDE_ERR_UNSUPPORTED;
-	const size_t bytes = hjbqvi1d_smem_bytes(b.nq, b.nz);
+	if(b.N < 3 || b.N > 9 * HP || b.model != QPDE_HJBQVI1D_EXCHANGE_RATE) return QPDE_ERR_UNSUPPORTED;
+	const size_t bytes = hjbqvi1d_shared_bytes(b.N, b.nq, b.nz);
 	if(bytes > 227 * 1024) return QPDE_ERR_UNSUPPORTED;
-	auto kern = k_hjbqvi1d<ExchangeRate>;
+	auto kern = b.N <= 8 * HP ? k_hjbqvi1d<ExchangeRate, 8> : k_hjbqvi1d<ExchangeRate, 9>;
 	if(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes) != cudaSuccess) return QPDE_ERR_CUDA;
 	kern<<<b.n_problems, HP, bytes, stream>>>(b, out);
 	*launches += 1;

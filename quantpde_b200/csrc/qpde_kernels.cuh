@@ -139,9 +139,9 @@ struct Hjbqvi1dBatch {
 struct Hjbqvi1dResult {
 	double *V, *X, *Q, *Z;          // [n_problems][N]; any may be null
 	unsigned char *mask;
-	double *mean_inner; int *n_steps, *status;
+	double *mean_inner, *mean_sweeps; int *n_steps, *status;
 };
-size_t hjbqvi1d_shared_bytes(int nq, int nz);
+size_t hjbqvi1d_shared_bytes(int N, int nq, int nz);
 int launch_hjbqvi1d(const Hjbqvi1dBatch &b, const Hjbqvi1dResult &out, cudaStream_t stream, long long *launches);
 
 // FP64 pipe rate of this device, measured (qpde_peak.cu)

@@ -88,6 +88,29 @@ public:
 		for(Index i = 0; i < points; ++i) v[i] = begin + dx * i;
 		return Axis(std::move(v));
 	}
+	// points clustered around one feature by a sinh map (Core/Axis.hpp:51-90); the ticks go through libm's
+	// asinh / sinh on the host exactly as the reference's do
+	static Axis nonsymmetricCluster(Real begin, Real feature, Real end, Index points, Real intensity = 1.) {
+		Real K = (feature - begin) / (end - begin);
+		bool flipped = false;
+		if(K < 0.5) { flipped = true; K = 1. - K; }
+		const Real c = K / intensity;
+		const Real xi_0 = std::asinh((0. - K) / c);
+		const Real dxi = (std::asinh((1. - K) / c) - xi_0) / (points - 1);
+		std::vector<Real> v((size_t)points);
+		v[0] = begin;
+		for(Index i = 1; i < points - 1; ++i) {
+			if(flipped) v[points - 1 - i] = (1. - (K + c * std::sinh(xi_0 + i * dxi))) * (end - begin) + begin;
+			else v[i] = ((K + c * std::sinh(xi_0 + i * dxi))) * (end - begin) + begin;
+		}
+		v[points - 1] = end;
+		return Axis(std::move(v));
+	}
+	// Core/Axis.hpp:238-257 (an even number of points gives points + 1)
+	static Axis cluster(Real begin, Real feature, Real end, Index points, Real intensity = 1.) {
+		const Index p = (points + 1 + (points % 2 == 0 ? 1 : 0)) / 2;
+		return nonsymmetricCluster(begin, feature, feature, p, intensity) + nonsymmetricCluster(feature, feature, end, p, intensity);
+	}
 	// union, Core/Axis.hpp:270-313
 	friend Axis operator+(const Axis &a, const Axis &b) {
 		std::vector<Real> c;
@@ -961,6 +984,118 @@ public:
 		}
 		res.steps = st.n_steps; res.meanPolicyIterations = st.mean_inner;
 		return res;
+	}
+};
+
+////////////////////////////////////////////////////////////////////////////////
+// ExchangeRate — examples/hjbqvi/exchange_rate.cpp on Modules/HJBQVI/HJBQVI.hpp: the combined stochastic /
+// impulse control of an exchange rate (Mundaca & Oksendal), a 1-D HJBQVI under the penalised scheme.  The
+// reference takes the coefficient functions as lambdas; a lambda cannot cross the C ABI, so the model is a
+// tagged form of qpde_hjbqvi1d_batch with the example's parameters as members.  solve(solver, problems, k)
+// sweeps a batch of problems in one launch (one CTA per problem).
+////////////////////////////////////////////////////////////////////////////////
+
+class ExchangeRate {
+public:
+	Real x_min, x_max, m;                    // exchange_rate.cpp:36-47: state domain and optimal parity
+	Real q_min, q_max;                       // interest rate differential bounds
+	Real T, rho, sigma, a, b, lambda, c;     // :52-69
+	Real intensity;                          // clustering of the nodes around the parity
+	int points, stochasticControlPoints, impulseControlPoints, timesteps;   // :40-42, :72
+	Real scalingFactor, iterationTolerance;  // HJBQVI defaults: 1e-2, 1e-6
+	int maxIterations, maxSweeps;            // guards (the reference has none)
+
+	ExchangeRate() : x_min(-2.), x_max(2.), m(0.), q_min(-.07), q_max(.07), T(10.), rho(.02), sigma(.3), a(.25),
+			b(3.), lambda(1.), c(.1), intensity(10.), points(32), stochasticControlPoints(9), impulseControlPoints(16),
+			timesteps(16), scalingFactor(1e-2), iterationTolerance(1e-6), maxIterations(200), maxSweeps(500) {}
+
+	Axis xAxis() const { return Axis::cluster(x_min, m, x_max, points, intensity); }                      // :79-85
+	Axis controlAxis() const { return Axis::uniform(q_min, q_max, stochasticControlPoints); }             // :88
+	Axis impulseAxis() const { return Axis::cluster(x_min, m, x_max, impulseControlPoints, intensity); }  // :91-97
+
+	struct Result {
+		std::vector<Real> X, V, Q, Z;        // nodes, value, controls (NaN where the other control acts)
+		int stochasticControlNodes, impulseControlNodes, steps;
+		Real meanPolicyIterations, meanSolverIterations;
+		// PiecewiseLinear<1>::interpolate (Core/Interpolant.hpp:153-181,331-374)
+		Real operator()(Real x) const {
+			const int n = (int)X.size();
+			int i; Real w;
+			if(x <= X[0]) { i = 0; w = 1.; }
+			else if(x >= X[n - 1]) { i = n - 2; w = 0.; }
+			else {
+				int lo = 0, hi = n - 2, mid = 0; w = 0.;
+				while(lo <= hi) {
+					mid = (lo + hi) / 2;
+					if(x < X[mid]) hi = mid - 1;
+					else if(x >= X[mid + 1]) lo = mid + 1;
+					else { w = (X[mid + 1] - x) / (X[mid + 1] - X[mid]); break; }
+				}
+				i = mid;
+			}
+			Real sum = 0.;
+			if(w > epsilon) sum += w * V[i];
+			if(1. - w > epsilon) sum += (1. - w) * V[i + 1];
+			return sum;
+		}
+	};
+
+	Result solve(B200Solver &solver, int refinement) const {
+		return solve(solver, std::vector<ExchangeRate>(1, *this), refinement)[0];
+	}
+
+	// Problems of one batch share the discretisation counts (points, timesteps, T, tolerances); the model
+	// parameters and the axes are per problem.
+	static std::vector<Result> solve(B200Solver &solver, const std::vector<ExchangeRate> &problems, int refinement) {
+		if(problems.empty()) return std::vector<Result>();
+		const ExchangeRate &first = problems[0];
+		const size_t P = problems.size();
+		std::vector<Real> xa, qa, za, par;
+		int nx = 0, nq = 0, nz = 0;
+		for(const ExchangeRate &e : problems) {
+			const Axis x = e.xAxis(), q = e.controlAxis(), z = e.impulseAxis();
+			if(&e == &first) { nx = x.size(); nq = q.size(); nz = z.size(); }
+			if(x.size() != nx || q.size() != nq || z.size() != nz || e.timesteps != first.timesteps || e.T != first.T
+					|| e.scalingFactor != first.scalingFactor || e.iterationTolerance != first.iterationTolerance) {
+				throw std::invalid_argument("QuantPDE_B200: the problems of one ExchangeRate batch share the grid sizes, T, timesteps and tolerances");
+			}
+			xa.insert(xa.end(), x.data(), x.data() + nx); qa.insert(qa.end(), q.data(), q.data() + nq);
+			za.insert(za.end(), z.data(), z.data() + nz);
+			const Real pp[7] = { e.rho, e.sigma, e.a, e.b, e.m, e.lambda, e.c };
+			par.insert(par.end(), pp, pp + 7);
+		}
+		qpde_hjbqvi1d_batch g = qpde_hjbqvi1d_batch();
+		g.abi_version = QPDE_ABI_VERSION; g.model = QPDE_HJBQVI1D_EXCHANGE_RATE;
+		g.n_problems = (int32_t)P; g.refine = refinement;
+		g.x_axis = xa.data(); g.n_x_axis = nx; g.x_axis_stride = nx;
+		g.control_axis = qa.data(); g.n_control_axis = nq; g.control_axis_stride = nq;
+		g.impulse_axis = za.data(); g.n_impulse_axis = nz; g.impulse_axis_stride = nz;
+		g.params = par.data(); g.n_params = 7; g.params_stride = 7;
+		g.T = first.T; g.timesteps = first.timesteps;
+		for(int k = 0; k < refinement; ++k) g.timesteps *= 2;       // HJBQVI.hpp:629-632
+		g.max_inner = first.maxIterations; g.max_sweeps = first.maxSweeps;
+		g.scaling_factor = first.scalingFactor; g.tolerance = first.iterationTolerance;
+		int N = 0, cq = 0, cz = 0;
+		solver.check(qpde_hjbqvi1d_nodes(&g, &N, &cq, &cz));
+		std::vector<Real> V(P * N), X(P * N), Q(P * N), Z(P * N), mi(P), ms(P);
+		std::vector<int32_t> steps(P), status(P);
+		qpde_hjbqvi1d_result r = qpde_hjbqvi1d_result();
+		r.V = V.data(); r.X = X.data(); r.Q = Q.data(); r.Z = Z.data();
+		r.mean_inner = mi.data(); r.mean_sweeps = ms.data(); r.n_steps = steps.data(); r.status = status.data();
+		solver.check(qpde_hjbqvi1d_solve(solver.handle(), &g, &r));
+		std::vector<Result> out(P);
+		for(size_t p = 0; p < P; ++p) {
+			if(status[p] != 0) {
+				throw std::runtime_error(status[p] == 1 ? "QuantPDE_B200: ExchangeRate policy iteration hit maxIterations"
+					: "QuantPDE_B200: ExchangeRate lagged sweeps did not settle");
+			}
+			Result &res = out[p];
+			res.X.assign(X.begin() + p * N, X.begin() + (p + 1) * N); res.V.assign(V.begin() + p * N, V.begin() + (p + 1) * N);
+			res.Q.assign(Q.begin() + p * N, Q.begin() + (p + 1) * N); res.Z.assign(Z.begin() + p * N, Z.begin() + (p + 1) * N);
+			res.stochasticControlNodes = cq; res.impulseControlNodes = cz; res.steps = steps[p];
+			res.meanPolicyIterations = mi[p]; res.meanSolverIterations = ms[p];
+		}
+		return out;
 	}
 };
 

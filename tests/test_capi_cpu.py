@@ -39,6 +39,9 @@ int main(void) {
     sizeof(qpde_step), offsetof(qpde_bs1d_batch, T), offsetof(qpde_bs1d_batch, strike),
     offsetof(qpde_bs1d_batch, tolerance), offsetof(qpde_bs1d_batch, kernel),
     offsetof(qpde_bs1d_result, active));
+  printf("%zu %zu %zu %zu %zu %zu\n", sizeof(qpde_hjbqvi1d_batch), sizeof(qpde_hjbqvi1d_result),
+    offsetof(qpde_hjbqvi1d_batch, params_stride), offsetof(qpde_hjbqvi1d_batch, T),
+    offsetof(qpde_hjbqvi1d_batch, max_sweeps), offsetof(qpde_hjbqvi1d_result, status));
   return 0; }'''
     with tempfile.TemporaryDirectory() as d:
         open(os.path.join(d, "t.c"), "w").write(prog)
@@ -48,6 +51,8 @@ int main(void) {
     B, R = qpde.Batch, qpde.Result
     want = [C.sizeof(B), C.sizeof(R), C.sizeof(qpde.Step), B.T.offset, B.strike.offset,
             B.tolerance.offset, B.kernel.offset, R.active.offset]
+    HB, HR = qpde.Hjbqvi1dBatch, qpde.Hjbqvi1dResult
+    want += [C.sizeof(HB), C.sizeof(HR), HB.params_stride.offset, HB.T.offset, HB.max_sweeps.offset, HR.status.offset]
     assert got == want
 
 

@@ -78,3 +78,29 @@ def test_exchange_rate_errors(qpde, handle):
         qpde.exchange_rate_solve(handle, X0[::-1], Q0, Z0, [_params({})], 0, 16)
     with pytest.raises(qpde.QpdeError):
         qpde.exchange_rate_solve(handle, X0, Q0, Z0, [[.02, .3, .25]], 0, 16)
+
+
+def test_example_program_reproduces_the_reference_programs_stdout():
+    """examples/bin/exchange_rate_b200 against the recorded stdout of the reference's own, unmodified
+    examples/hjbqvi/exchange_rate.cpp (oracle/_ref/examples/exchange_rate: 7 minutes on one host core;
+    tests/golden/tables_hjbqvi/exchange_rate.txt): the convergence table over the refinement levels 0 .. 6
+    (2049 nodes, 513 + 1025 controls, 1024 steps at the last) and the solution with both controls at every node
+    of the finest level.  Equal character for character except the two columns that cannot be ("Mean Solver
+    Iterations": BiCGSTAB's count there, tridiagonal solves here; the execution time), and "Change" / "Ratio",
+    differences of values that agree to ~1e-13, to 2e-6 relative."""
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    subprocess.run(["make", "-s", "-C", os.path.join(root, "examples")], check=True)
+    got = subprocess.run([os.path.join(root, "examples", "bin", "exchange_rate_b200")], check=True, capture_output=True,
+                         text=True).stdout.splitlines()
+    want = open(os.path.join(root, "tests", "golden", "tables_hjbqvi", "exchange_rate.txt")).read().splitlines()
+    assert len(got) == len(want)
+    assert got[0] == want[0]
+    blank = want.index("")
+    for g, w in zip(got[1:blank], want[1:blank]):
+        assert len(g) == len(w) == 12 * 23
+        gf, wf = [g[23 * k:23 * (k + 1)] for k in range(12)], [w[23 * k:23 * (k + 1)] for k in range(12)]
+        assert gf[:7] == wf[:7] and gf[8] == wf[8], (g, w)       # nodes, steps, scaling, tolerance, policy iterations, value
+        for a, b in zip(gf[9:11], wf[9:11]):
+            assert a == b or abs(float(a) - float(b)) <= 2e-6 * abs(float(b)), (g, w)
+    assert got[blank:] == want[blank:]                               # header and 2049 rows: x, u, q*, z*
