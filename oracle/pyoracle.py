@@ -392,6 +392,39 @@ def exchange_rate(x_axis, q_axis, z_axis, refine_times=0, timesteps=16, T=10., r
                 n_steps=n_steps.value, status=status)
 
 
+class Hjbqvi2d(C.Structure):
+    _fields_ = [("n_w", C.c_int), ("n_b", C.c_int), ("W", C.POINTER(C.c_double)), ("B", C.POINTER(C.c_double)),
+                ("n_q", C.c_int), ("q", C.POINTER(C.c_double)), ("n_z", C.c_int), ("zfrac", C.POINTER(C.c_double)),
+                ("T", C.c_double), ("timesteps", C.c_int),
+                ("rho", C.c_double), ("r", C.c_double), ("mu", C.c_double), ("sigma", C.c_double), ("gamma", C.c_double),
+                ("lam", C.c_double), ("c", C.c_double), ("boundary", C.c_double),
+                ("scaling_factor", C.c_double), ("tolerance", C.c_double), ("max_inner", C.c_int), ("max_sweeps", C.c_int)]
+
+
+def optimal_consumption(refine_times=0, timesteps=32, control_points=16, spatial_points=20, T=40., rho=.1, r=.07, mu=.11,
+                        sigma=.3, gamma=.3, lam=.1, c=.05, q_max=100., boundary=200., max_inner=1000, max_sweeps=5000):
+    """The examples/hjbqvi/optimal_consumption.cpp wiring on the oracle."""
+    W = refine(uniform_axis(0., boundary, spatial_points), refine_times)
+    B = W.copy()
+    q = refine(uniform_axis(0., q_max, control_points), refine_times)
+    z = refine(uniform_axis(0., 1., control_points), refine_times)
+    p = Hjbqvi2d()
+    p.n_w, p.n_b, p.W, p.B = len(W), len(B), _dp(W), _dp(B)
+    p.n_q, p.q, p.n_z, p.zfrac = len(q), _dp(q), len(z), _dp(z)
+    p.T, p.timesteps = T, timesteps * 2 ** refine_times
+    p.rho, p.r, p.mu, p.sigma, p.gamma, p.lam, p.c, p.boundary = rho, r, mu, sigma, gamma, lam, c, boundary
+    p.scaling_factor, p.tolerance, p.max_inner, p.max_sweeps = 1e-2, 1e-6, max_inner, max_sweeps
+    n = len(W) * len(B)
+    V, Qs, Zs = np.zeros(n), np.zeros(n), np.zeros(n)
+    mask = np.zeros(n, dtype=np.uint8)
+    mean_inner, n_steps = C.c_double(), C.c_int()
+    status = lib().qpo_hjbqvi2d_solve(C.byref(p), _dp(V), _dp(Qs), _dp(Zs), mask.ctypes.data_as(C.POINTER(C.c_ubyte)),
+                                      C.byref(mean_inner), C.byref(n_steps))
+    shape = (len(B), len(W))
+    return dict(W=W, B=B, QA=q, ZA=z, V=V.reshape(shape), Q=Qs.reshape(shape), Z=Zs.reshape(shape), mask=mask.reshape(shape),
+                mean_inner=mean_inner.value, n_steps=n_steps.value, status=status)
+
+
 JUMP_AXIS_EXTRA = 1000.0   # examples/jump_diffusion.cpp:166: + S_0 * Axis{1000.}
 
 

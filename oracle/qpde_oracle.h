@@ -178,6 +178,22 @@ typedef struct {
 int qpo_hjbqvi1d_solve(const qpo_hjbqvi1d *p, double *V, double *Q, double *Z, unsigned char *mask,
 		double *mean_inner, int *n_steps);
 
+/* ---- 2-D impulse-control HJBQVI of examples/hjbqvi/optimal_consumption.cpp (qpde_oracle_hjbqvi2d.c) ---- */
+typedef struct {
+	int n_w, n_b;
+	const double *W, *B;        /* refined axes; node (iw, ib) is row iw + n_w ib      */
+	int n_q; const double *q;   /* consumption-rate grid                             */
+	int n_z; const double *zfrac; /* impulse control grid (fractions of the admissible transfer) */
+	double T; int timesteps;
+	double rho, r, mu, sigma, gamma, lambda, c, boundary;   /* optimal_consumption.cpp:36-80 */
+	double scaling_factor, tolerance;
+	int max_inner, max_sweeps;
+} qpo_hjbqvi2d;
+/* V, Q, Z [n_w n_b] out (controls NaN where the other control acts), mask out; Q, Z, mask may be NULL.
+ * Returns 0, 1 (max_inner hit) or 2 (the line sweeps did not settle). */
+int qpo_hjbqvi2d_solve(const qpo_hjbqvi2d *p, double *V, double *Q, double *Z, unsigned char *mask,
+		double *mean_inner, int *n_steps);
+
 #ifdef __cplusplus
 }
 #endif

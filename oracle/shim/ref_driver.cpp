@@ -783,6 +783,74 @@ int runExchange(const Args &a) {
 	return 0;
 }
 
+////////////////////////////////////////////////////////////////////////////////
+// consumption: optimal consumption with fixed and proportional transaction costs, a 2-D (w, b)
+// HJBQVI with impulses pointing both ways in the state, penalised scheme + BiCGSTAB, wired as
+// examples/hjbqvi/optimal_consumption.cpp:29-203.
+////////////////////////////////////////////////////////////////////////////////
+
+int runConsumption(const Args &a) {
+	constexpr int Dimension = 2, SC = 1, IC = 1;
+	const Real T = num(a, "T", 40.), rho = num(a, "rho", .1), r = num(a, "r", .07), mu = num(a, "mu", .11);
+	const Real sigma = num(a, "sigma", .3), gamma = num(a, "gamma", .3), lambda = num(a, "lambda", .1), c = num(a, "c", .05);
+	const Real q_max = num(a, "q_max", 100.), w_0 = num(a, "w0", 45.2), b_0 = num(a, "b0", 45.2);
+	const Real boundary = num(a, "boundary", 200.);
+	const int timesteps = (int) integer(a, "timesteps", 32);
+	const int control_points = (int) integer(a, "control_points", 16);
+	const int spatial_points = (int) integer(a, "spatial_points", 20);
+	const int refinement = (int) integer(a, "refine", 0);
+	const Axis axis = Axis::uniform(0., boundary, spatial_points);
+
+	auto z_bounded = [=] (Real, Real w, Real b, Real z_frac) {
+		const Real tmp1 = b - c;
+		const Real tmp2 = tmp1 - boundary;
+		const Real lo = max(-w, (tmp2 > 0) ? (tmp2 / (1 - lambda)) : (tmp2 / (1 + lambda)));
+		const Real hi = min(boundary - w, (tmp1 > 0) ? (tmp1 / (1 + lambda)) : (tmp1 / (1 - lambda)));
+		const Real z = z_frac * (hi - lo) + lo;
+		if(std::fabs(z) < QuantPDE::epsilon) { return 0.; }
+		return z;
+	};
+
+	HJBQVI<Dimension, SC, IC> hjbqvi(timesteps, { axis, axis },
+		{ Axis::uniform(0., q_max, control_points) }, { Axis::uniform(0., 1., control_points) }, T,
+		[=] (Real, Real, Real) { return rho; },
+		{ [=] (Real, Real w, Real) { return sigma * w; }, [=] (Real, Real, Real) { return 0.; } },
+		{ [=] (Real, Real w, Real, Real) { return mu * w; },
+		  [=] (Real, Real, Real b, Real q) { return r * b + ((0 < b && b < boundary) ? -q : 0.); } },
+		[=] (Real, Real, Real b, Real q) { return (0 < b && b < boundary) ? std::pow(q, gamma) / gamma : 0.; },
+		{ [=] (Real t, Real w, Real b, Real z_frac) { const Real z = z_bounded(t, w, b, z_frac); return w + z; },
+		  [=] (Real t, Real w, Real b, Real z_frac) { const Real z = z_bounded(t, w, b, z_frac); return b - z - lambda * std::fabs(z) - c; } },
+		[=] (Real t, Real w, Real b, Real z_frac) {
+			const Real z = z_bounded(t, w, b, z_frac);
+			return z == 0. ? -std::numeric_limits<Real>::infinity() : 0.; },
+		[=] (Real, Real w, Real b) { const Real liquidate = max(b + (1 - lambda) * w - c, 0.); return std::pow(liquidate, gamma) / gamma; });
+	hjbqvi.usePenalizedScheme();
+	hjbqvi.useBiCGSTABSolver();
+	hjbqvi.coefficientsAreTimeIndependent();
+	hjbqvi.ignoreExtrapolatoryControls();
+
+	auto result = hjbqvi.solve(refinement);
+	PiecewiseLinear<Dimension> u(result.spatial_grid, result.solution_vector);
+	std::printf("value %a\n", (double) u.interpolate({{ w_0, b_0 }}));
+	std::printf("seconds %.9g\n", (double) result.execution_time_seconds);
+	std::printf("steps %d\n", (int) result.timesteps);
+	std::printf("mean_inner %a\n", (double) result.mean_inner_iterations);
+	std::printf("mean_solver %a\n", (double) result.mean_solver_iterations);
+	std::vector<double> W, B, QA, ZA, V, Q, Z;
+	for(Index i = 0; i < result.spatial_grid[0].size(); ++i) W.push_back(result.spatial_grid[0][i]);
+	for(Index i = 0; i < result.spatial_grid[1].size(); ++i) B.push_back(result.spatial_grid[1][i]);
+	for(Index i = 0; i < result.stochastic_control_grid[0].size(); ++i) QA.push_back(result.stochastic_control_grid[0][i]);
+	for(Index i = 0; i < result.impulse_control_grid[0].size(); ++i) ZA.push_back(result.impulse_control_grid[0][i]);
+	for(Index i = 0; i < result.solution_vector.size(); ++i) {
+		V.push_back(result.solution_vector(i));
+		Q.push_back(result.stochastic_control_vector[0](i));
+		Z.push_back(result.impulse_control_vector[0](i));
+	}
+	dumpReals("W", W); dumpReals("B", B); dumpReals("QA", QA); dumpReals("ZA", ZA);
+	dumpReals("V", V); dumpReals("Q", Q); dumpReals("Z", Z);
+	return 0;
+}
+
 void usage() {
 	std::fprintf(stderr,
 		"qpde_ref vanilla  K= S0= r= vol= q= T= steps= refine= american=0|1 [E= dividend= dividend_kind= dividend_first= exercise=] "
@@ -794,6 +862,7 @@ void usage() {
 		"qpde_ref jump     K= S0= r= vol= q= T= lambda= steps= refine= density=lognormal|kou "
 		"mu= sd= p_up= eta1= eta2= scheme=bdf1|bdf2 repeat=\n"
 		"qpde_ref gmwb     T= r= eta= sigma= G= k= c= w0= timesteps= a_points= control_points= refine=\n"
+		"qpde_ref consumption T= rho= r= mu= sigma= gamma= lambda= c= q_max= w0= b0= boundary= timesteps= control_points= spatial_points= refine=\n"
 		"qpde_ref exchange x_min= x_max= m= q_min= q_max= T= rho= sigma= a= b= lambda= c= intensity= points= q_points= z_points= timesteps= refine=\n");
 }
 
@@ -817,6 +886,7 @@ int main(int argc, char **argv) {
 	if(mode == "jump")     return runJump(a);
 	if(mode == "gmwb")     return runGmwb(a);
 	if(mode == "exchange") return runExchange(a);
+	if(mode == "consumption") return runConsumption(a);
 	usage();
 	return 2;
 }
