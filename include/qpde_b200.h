@@ -479,6 +479,56 @@ typedef struct {
 int qpde_hjbqvi1d_nodes(const qpde_hjbqvi1d_batch *batch, int *nodes, int *n_controls, int *n_impulses);
 int qpde_hjbqvi1d_solve(qpde_handle *h, const qpde_hjbqvi1d_batch *batch, qpde_hjbqvi1d_result *result);
 
+/* ---- 2-D impulse-control HJBQVI, penalised scheme, impulses in both directions ----------------
+ * One call does what HJBQVI<2,1,1>::solve(refinement) does (Modules/HJBQVI/HJBQVI.hpp:590-811 with
+ * usePenalizedScheme(), useBiCGSTABSolver(), no boundary routines) for a model whose impulses point both
+ * ways in the state, so that the matrix of an inner iteration has no block-triangular order (the GMWB
+ * entry points above exploit one).  Tagged coefficient forms:
+ *   QPDE_HJBQVI2D_OPTIMAL_CONSUMPTION   examples/hjbqvi/optimal_consumption.cpp:85-176
+ *     params[8] = { rho, r, mu, sigma, gamma, lambda, c, boundary }: state (w, b) = (stock, bank) on
+ *     [0, boundary]^2, volatility (sigma w, 0), drift (mu w, r b - q 1{0 < b < boundary}), flow
+ *     q^gamma / gamma 1{..}, discount rho; impulse z = z_frac (hi - lo) + lo within the admissible
+ *     transfers: (w, b) -> (w + z, b - z - lambda |z| - c), reward 0 (-inf if z = 0); exit value
+ *     max(b + (1 - lambda) w - c, 0)^gamma / gamma
+ *   time    ReverseConstantStepper(0, T, T / timesteps), BDF1, ToleranceIteration(tolerance)
+ *   penalty 1 / (scaling_factor dt)
+ * All four axes are refined `refine` times; `timesteps` is the count at this refinement.  Node (iw, ib)
+ * is element ib * n_w + iw of the outputs (w fastest, Core/Domain.hpp:1408-1428). */
+#define QPDE_HJBQVI2D_OPTIMAL_CONSUMPTION 1
+typedef struct {
+	int32_t abi_version;
+	int32_t model;            /* QPDE_HJBQVI2D_*                                         */
+	int32_t refine;
+	int32_t n_params;
+	const double *w_axis;       int32_t n_w_axis;       int32_t reserved0;
+	const double *b_axis;       int32_t n_b_axis;       int32_t reserved1;
+	const double *control_axis; int32_t n_control_axis; int32_t reserved2;   /* consumption rates q */
+	const double *impulse_axis; int32_t n_impulse_axis; int32_t reserved3;   /* z_frac in [0, 1]    */
+	const double *params;
+	double T; int32_t timesteps; int32_t max_inner;
+	double scaling_factor;    /* HJBQVI default 1e-2                                     */
+	double tolerance;         /* iteration_tolerance, 1e-6                               */
+	int32_t max_sweeps;       /* guard of the linear solve's line sweeps, e.g. 20000     */
+	int32_t reserved4;
+} qpde_hjbqvi2d;
+
+typedef struct {
+	int32_t nodes_w, nodes_b; /* refined grid sizes                                     */
+	int32_t n_steps;          /* time steps taken                                       */
+	int32_t status;           /* 0 ok, 1 max_inner hit, 2 the line sweeps did not settle */
+	double  mean_inner;       /* "Mean Policy Iterations" of HJBQVI_main                */
+	double  mean_sweeps;      /* line sweeps per policy iteration (the reference reports BiCGSTAB's "Mean Solver Iterations") */
+	int32_t *inner;           /* [inner_capacity] per-step inner iterations, or NULL    */
+	int32_t inner_capacity;
+	int32_t reserved;
+} qpde_hjbqvi2d_stats;
+
+int qpde_hjbqvi2d_nodes(const qpde_hjbqvi2d *problem, int *nodes_w, int *nodes_b);
+/* V: HOST buffer [nodes_b][nodes_w] out; Q, Z (controls, NaN where the other control acts), mask
+ * (PenaltyMethod::constraintMask), W_out, B_out: optional. */
+int qpde_hjbqvi2d_solve(qpde_handle *h, const qpde_hjbqvi2d *problem, double *V, double *Q, double *Z,
+		unsigned char *mask, double *W_out, double *B_out, qpde_hjbqvi2d_stats *stats);
+
 /* ---- GMWB sharded by the A-axis over the GPUs of a node: the library's own driver --------
  * One process per GPU.  A handle gets a communicator (NCCL over NVLink /
  * NVSwitch, loaded at run time): rank 0 makes an id with qpde_comm_unique_id, the caller ships the

@@ -128,6 +128,10 @@ static double relative_error2(int n, const double *a, const double *b, double sc
 	return m;
 }
 
+static long last_sweeps, last_solves;
+/* symmetric sweeps per linear solve of the last call (diagnostic) */
+double qpo_hjbqvi2d_mean_sweeps(void) { return last_solves ? (double)last_sweeps / (double)last_solves : 0.; }
+
 int qpo_hjbqvi2d_solve(const qpo_hjbqvi2d *p, double *V, double *Q, double *Z, unsigned char *mask,
 		double *mean_inner, int *n_steps_out) {
 	const int nw = p->n_w, nb = p->n_b, n = nw * nb;
@@ -148,6 +152,7 @@ int qpo_hjbqvi2d_solve(const qpo_hjbqvi2d *p, double *V, double *Q, double *Z, u
 	int s, i, k, status = 0; long inner_sum = 0;
 	double time1 = p->T;
 
+	last_sweeps = 0; last_solves = 0;
 	for(k = 0; k < p->n_q; ++k) flow_q[k] = pow(p->q[k], p->gamma) / p->gamma;          /* :138-141 */
 	for(i = 0; i < n; ++i) {                                                            /* :165-168 */
 		const double w = p->W[i % nw], b = p->B[i / nw];
@@ -235,6 +240,7 @@ int qpo_hjbqvi2d_solve(const qpo_hjbqvi2d *p, double *V, double *Q, double *Z, u
 				if(worst <= 1e-15) break;
 			}
 			if(sweep >= p->max_sweeps) status = 2;
+			last_sweeps += sweep + 1; ++last_solves;
 			++its;
 			notdone = relative_error2(n, x, xprev, 1.) > p->tolerance;
 			if(notdone && its >= p->max_inner) { status = status ? status : 1; break; }

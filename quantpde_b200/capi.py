@@ -141,6 +141,31 @@ class Hjbqvi1dResult(C.Structure):
 
 HJBQVI1D_EXCHANGE_RATE = 1
 
+
+class Hjbqvi2d(C.Structure):
+    _fields_ = [
+        ("abi_version", C.c_int32), ("model", C.c_int32), ("refine", C.c_int32), ("n_params", C.c_int32),
+        ("w_axis", _dp), ("n_w_axis", C.c_int32), ("reserved0", C.c_int32),
+        ("b_axis", _dp), ("n_b_axis", C.c_int32), ("reserved1", C.c_int32),
+        ("control_axis", _dp), ("n_control_axis", C.c_int32), ("reserved2", C.c_int32),
+        ("impulse_axis", _dp), ("n_impulse_axis", C.c_int32), ("reserved3", C.c_int32),
+        ("params", _dp),
+        ("T", C.c_double), ("timesteps", C.c_int32), ("max_inner", C.c_int32),
+        ("scaling_factor", C.c_double), ("tolerance", C.c_double),
+        ("max_sweeps", C.c_int32), ("reserved4", C.c_int32),
+    ]
+
+
+class Hjbqvi2dStats(C.Structure):
+    _fields_ = [
+        ("nodes_w", C.c_int32), ("nodes_b", C.c_int32), ("n_steps", C.c_int32), ("status", C.c_int32),
+        ("mean_inner", C.c_double), ("mean_sweeps", C.c_double),
+        ("inner", C.POINTER(C.c_int32)), ("inner_capacity", C.c_int32), ("reserved", C.c_int32),
+    ]
+
+
+HJBQVI2D_OPTIMAL_CONSUMPTION = 1
+
 # every symbol include/qpde_b200.h declares
 EXPORTS = [
     "qpde_abi_version", "qpde_create", "qpde_destroy", "qpde_last_error", "qpde_stream",
@@ -152,7 +177,7 @@ EXPORTS = [
     "qpde_gmwb2d_nodes", "qpde_gmwb2d_solve", "qpde_gmwb2d_solve_sharded", "qpde_comm_unique_id", "qpde_comm_init",
     "qpde_comm_destroy", "qpde_gmwb2d_shard_create", "qpde_gmwb2d_shard_destroy",
     "qpde_gmwb2d_shard_exit", "qpde_gmwb2d_shard_policy", "qpde_gmwb2d_shard_sweep", "qpde_gmwb2d_shard_relerr",
-    "qpde_hjbqvi1d_nodes", "qpde_hjbqvi1d_solve",
+    "qpde_hjbqvi1d_nodes", "qpde_hjbqvi1d_solve", "qpde_hjbqvi2d_nodes", "qpde_hjbqvi2d_solve",
 ]
 
 _lib = None
@@ -216,6 +241,9 @@ def lib():
         L.qpde_gmwb2d_shard_relerr.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         L.qpde_hjbqvi1d_nodes.argtypes = [C.POINTER(Hjbqvi1dBatch), C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]
         L.qpde_hjbqvi1d_solve.argtypes = [C.c_void_p, C.POINTER(Hjbqvi1dBatch), C.POINTER(Hjbqvi1dResult)]
+        L.qpde_hjbqvi2d_nodes.argtypes = [C.POINTER(Hjbqvi2d), C.POINTER(C.c_int), C.POINTER(C.c_int)]
+        L.qpde_hjbqvi2d_solve.argtypes = [C.c_void_p, C.POINTER(Hjbqvi2d), _dp, _dp, _dp, C.POINTER(C.c_ubyte), _dp, _dp,
+                                          C.POINTER(Hjbqvi2dStats)]
         _lib = L
     return _lib
 
@@ -446,6 +474,39 @@ def exchange_rate_solve(handle, x_axis, q_axis, z_axis, params, refine, timestep
     check(lib().qpde_hjbqvi1d_solve(handle.ptr, C.byref(g), C.byref(r)), handle.ptr)
     return dict(V=V, X=X, Q=Q, Z=Z, mask=mask, mean_inner=mean_inner, mean_sweeps=mean_sweeps, n_steps=n_steps, status=status,
                 n_controls=nq.value, n_impulses=nz.value)
+
+
+def optimal_consumption_solve(handle, refine, timesteps=32, control_points=16, spatial_points=20, T=40., rho=.1, r=.07, mu=.11,
+                              sigma=.3, gamma=.3, lam=.1, c=.05, q_max=100., boundary=200., scaling_factor=1e-2,
+                              tolerance=1e-6, max_inner=200, max_sweeps=20000):
+    """qpde_hjbqvi2d_solve for the model of examples/hjbqvi/optimal_consumption.cpp; `timesteps` is the count at
+    refinement 0 (doubled per level, as HJBQVI::solve does).  Host arrays out."""
+    def uniform(begin, end, points):
+        dx = (end - begin) / (points - 1)                       # Axis::uniform, Core/Axis.hpp:219-226
+        return np.array([begin + dx * i for i in range(points)])
+    axis = uniform(0., boundary, spatial_points)
+    qa, za = uniform(0., q_max, control_points), uniform(0., 1., control_points)
+    par = np.array([rho, r, mu, sigma, gamma, lam, c, boundary])
+    g = Hjbqvi2d()
+    g.abi_version, g.model, g.refine, g.n_params = ABI_VERSION, HJBQVI2D_OPTIMAL_CONSUMPTION, int(refine), len(par)
+    g.w_axis, g.n_w_axis, g.b_axis, g.n_b_axis = axis.ctypes.data_as(_dp), len(axis), axis.ctypes.data_as(_dp), len(axis)
+    g.control_axis, g.n_control_axis = qa.ctypes.data_as(_dp), len(qa)
+    g.impulse_axis, g.n_impulse_axis = za.ctypes.data_as(_dp), len(za)
+    g.params = par.ctypes.data_as(_dp)
+    g.T, g.timesteps, g.max_inner = T, int(timesteps) * 2 ** int(refine), int(max_inner)
+    g.scaling_factor, g.tolerance, g.max_sweeps = scaling_factor, tolerance, int(max_sweeps)
+    nw, nb = C.c_int(), C.c_int()
+    check(lib().qpde_hjbqvi2d_nodes(C.byref(g), C.byref(nw), C.byref(nb)))
+    shape = (nb.value, nw.value)
+    V, Q, Z = np.zeros(shape), np.zeros(shape), np.zeros(shape)
+    mask = np.zeros(shape, dtype=np.uint8)
+    W, B = np.zeros(nw.value), np.zeros(nb.value)
+    st = Hjbqvi2dStats()
+    check(lib().qpde_hjbqvi2d_solve(handle.ptr, C.byref(g), V.ctypes.data_as(_dp), Q.ctypes.data_as(_dp), Z.ctypes.data_as(_dp),
+                                    mask.ctypes.data_as(C.POINTER(C.c_ubyte)), W.ctypes.data_as(_dp), B.ctypes.data_as(_dp),
+                                    C.byref(st)), handle.ptr)
+    return dict(V=V, Q=Q, Z=Z, mask=mask, W=W, B=B, n_steps=st.n_steps, mean_inner=st.mean_inner, mean_sweeps=st.mean_sweeps,
+                status=st.status)
 
 
 class BatchSpec:

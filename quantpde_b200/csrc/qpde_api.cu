@@ -908,6 +908,50 @@ int qpde_hjbqvi1d_solve(qpde_handle *h, const qpde_hjbqvi1d_batch *g, qpde_hjbqv
 	return QPDE_OK;
 }
 
+// ---- 2-D impulse-control HJBQVI with impulses both ways (qpde_hjbqvi2d.cu) -------------------
+
+int qpde_hjbqvi2d_nodes(const qpde_hjbqvi2d *g, int *nodes_w, int *nodes_b) {
+	if(!g || !nodes_w || !nodes_b) return QPDE_ERR_INVALID;
+	*nodes_w = qpde_refined_size(g->n_w_axis, g->refine);
+	*nodes_b = qpde_refined_size(g->n_b_axis, g->refine);
+	return *nodes_w > 0 && *nodes_b > 0 ? QPDE_OK : QPDE_ERR_INVALID;
+}
+
+int qpde_hjbqvi2d_solve(qpde_handle *h, const qpde_hjbqvi2d *g, double *V, double *Q, double *Z, unsigned char *mask,
+		double *W_out, double *B_out, qpde_hjbqvi2d_stats *stats) {
+	if(!h) return fail(nullptr, QPDE_ERR_INVALID, "qpde_hjbqvi2d_solve: NULL handle");
+	if(!g || !V) return fail(h, QPDE_ERR_INVALID, "qpde_hjbqvi2d_solve: NULL argument");
+	if(g->abi_version != QPDE_ABI_VERSION) return fail(h, QPDE_ERR_INVALID, "problem.abi_version %d != %d", g->abi_version, QPDE_ABI_VERSION);
+	if(g->model != QPDE_HJBQVI2D_OPTIMAL_CONSUMPTION) return fail(h, QPDE_ERR_UNSUPPORTED, "hjbqvi2d: unknown model %d", g->model);
+	if(g->refine < 0 || g->refine > 10) return fail(h, QPDE_ERR_INVALID, "hjbqvi2d: refine out of range");
+	if(!g->w_axis || g->n_w_axis < 3 || !g->b_axis || g->n_b_axis < 3 || !g->control_axis || g->n_control_axis < 1
+			|| !g->impulse_axis || g->n_impulse_axis < 1) return fail(h, QPDE_ERR_INVALID, "hjbqvi2d: axes missing (the state axes need >= 3 ticks)");
+	if(!g->params || g->n_params < 8) return fail(h, QPDE_ERR_INVALID, "hjbqvi2d: the optimal-consumption model takes 8 parameters");
+	if(!(g->T > 0.) || g->timesteps < 1 || g->max_inner < 1 || g->max_sweeps < 1) return fail(h, QPDE_ERR_INVALID, "hjbqvi2d: T, timesteps, max_inner and max_sweeps must be positive");
+	if(!(g->scaling_factor > 0.) || !(g->tolerance > 0.)) return fail(h, QPDE_ERR_INVALID, "hjbqvi2d: scaling_factor and tolerance must be > 0");
+	const double *ax[4] = { g->w_axis, g->b_axis, g->control_axis, g->impulse_axis };
+	const int len[4] = { g->n_w_axis, g->n_b_axis, g->n_control_axis, g->n_impulse_axis };
+	for(int k = 0; k < 4; ++k) for(int i = 1; i < len[k]; ++i) if(!(ax[k][i] > ax[k][i - 1])) return fail(h, QPDE_ERR_INVALID, "hjbqvi2d: axis %d is not strictly increasing", k);
+	if(!(g->params[5] >= 0. && g->params[5] < 1.)) return fail(h, QPDE_ERR_INVALID, "hjbqvi2d: the proportional cost lambda must lie in [0, 1)");
+	if(!(g->params[4] > 0.)) return fail(h, QPDE_ERR_INVALID, "hjbqvi2d: gamma must be > 0");
+	int size[4];
+	std::vector<double> grid[4];
+	for(int k = 0; k < 4; ++k) {
+		size[k] = qpde_refined_size(len[k], g->refine);
+		grid[k].resize((size_t)size[k]);
+		qpde_refine_axis(ax[k], len[k], len[k] < 2 ? 0 : g->refine, grid[k].data());
+	}
+	if((long long)size[0] * size[1] > (1ll << 26)) return fail(h, QPDE_ERR_UNSUPPORTED, "hjbqvi2d: more than 2^26 nodes");
+	QPDE_CUDA(h, cudaSetDevice(h->device));
+	std::string error;
+	const int rc = hjbqvi2d_run(g, grid[0].data(), size[0], grid[1].data(), size[1], grid[2].data(), size[2], grid[3].data(), size[3],
+		V, Q, Z, mask, stats, h->stream, &h->launches, &error);
+	if(rc != QPDE_OK) return fail(h, rc, "%s", error.c_str());
+	if(W_out) memcpy(W_out, grid[0].data(), sizeof(double) * size[0]);
+	if(B_out) memcpy(B_out, grid[1].data(), sizeof(double) * size[1]);
+	return QPDE_OK;
+}
+
 int qpde_comm_unique_id(unsigned char id[QPDE_COMM_ID_BYTES]) {
 	if(!id) return fail(nullptr, QPDE_ERR_INVALID, "qpde_comm_unique_id: NULL argument");
 	std::string error;

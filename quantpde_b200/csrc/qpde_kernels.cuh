@@ -144,6 +144,11 @@ struct Hjbqvi1dResult {
 size_t hjbqvi1d_shared_bytes(int N, int nq, int nz);
 int launch_hjbqvi1d(const Hjbqvi1dBatch &b, const Hjbqvi1dResult &out, cudaStream_t stream, long long *launches);
 
+// 2-D impulse-control HJBQVI with impulses both ways (qpde_hjbqvi2d.cu): host-driven loop over the kernels.
+int hjbqvi2d_run(const qpde_hjbqvi2d *p, const double *W, int nw, const double *B, int nb, const double *q, int nq,
+		const double *z, int nz, double *V_host, double *Q_host, double *Z_host, unsigned char *mask_host,
+		qpde_hjbqvi2d_stats *stats, cudaStream_t stream, long long *launches, std::string *error);
+
 // FP64 pipe rate of this device, measured (qpde_peak.cu)
 int measure_fp64_peak(int sm_count, cudaStream_t stream, double *tflops, long long *launches);
 

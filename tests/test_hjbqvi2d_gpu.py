@@ -1,0 +1,67 @@
+"""GPU: the 2-D impulse-control HJBQVI with impulses both ways (examples/hjbqvi/optimal_consumption.cpp) through
+the C ABI (qpde_hjbqvi2d_solve) against the reference's own outputs (tests/golden/hjbqvi2d_reference.npz, made by
+`qpde_ref consumption` on the unmodified reference headers)."""
+import os
+import time
+
+import numpy as np
+import pytest
+
+from helpers import REL_TOL
+
+pytestmark = pytest.mark.gpu
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "hjbqvi2d_reference.npz")
+
+
+def _kwargs(args):
+    kw = {("lam" if k == "lambda" else k): v for k, v in args.items()}
+    return kw.pop("refine", 0), kw
+
+
+def test_optimal_consumption_against_reference_fixtures(qpde, handle):
+    g = np.load(GOLDEN)
+    for name in g["names"]:
+        name = str(name)
+        refine, kw = _kwargs(eval(str(g[name + "/args"])))
+        res = qpde.optimal_consumption_solve(handle, refine, **kw)
+        assert res["status"] == 0 and res["n_steps"] == int(g[name + "/steps"]), name
+        assert np.array_equal(res["W"], g[name + "/W"]) and np.array_equal(res["B"], g[name + "/B"]), name
+        ref = g[name + "/V"].reshape(res["V"].shape)                 # w fastest (Core/Domain.hpp:1416-1425)
+        err = np.abs(res["V"] - ref) / np.maximum(1., np.abs(ref))
+        assert err.max() <= REL_TOL, "%s: %.3e" % (name, err.max())
+        assert res["mean_inner"] == float(g[name + "/mean_inner"]), name     # "Mean Policy Iterations"
+        refQ, refZ = g[name + "/Q"].reshape(ref.shape), g[name + "/Z"].reshape(ref.shape)
+        assert np.array_equal(res["mask"] != 0, np.isnan(refQ)), name        # the transaction region
+        # the controls are arg-mins over smooth objectives: an entry may move to a neighbouring grid value where
+        # two candidates tie to rounding; everywhere else they are the reference's
+        for key, want in (("Q", refQ), ("Z", refZ)):
+            same = (res[key] == want) | (np.isnan(res[key]) & np.isnan(want))
+            assert same.mean() >= 0.995, (name, key, same.mean())
+
+
+def test_optimal_consumption_refinement_three_against_the_reference(qpde, handle):
+    """153 x 153 nodes, 121 + 121 controls, 256 steps: 11 minutes of the reference on one host core
+    (tests/golden keeps every 4th node in both directions)."""
+    g = np.load(GOLDEN)
+    t0 = time.perf_counter()
+    res = qpde.optimal_consumption_solve(handle, 3)
+    seconds = time.perf_counter() - t0
+    stride = int(g["oc_k3/stride"])
+    ref = g["oc_k3/V_strided"]
+    got = res["V"][::stride, ::stride]
+    err = np.abs(got - ref) / np.maximum(1., np.abs(ref))
+    assert res["status"] == 0 and res["n_steps"] == int(g["oc_k3/steps"])
+    assert err.max() <= REL_TOL, "%.3e" % err.max()
+    assert res["mean_inner"] == float(g["oc_k3/mean_inner"])
+    assert np.array_equal(res["mask"][::stride, ::stride] != 0, g["oc_k3/mask_strided"])
+    print("optimal consumption, refinement 3: %.2f s, %.1f line sweeps per policy iteration" % (seconds, res["mean_sweeps"]))
+
+
+def test_optimal_consumption_errors(qpde, handle):
+    with pytest.raises(qpde.QpdeError):
+        qpde.optimal_consumption_solve(handle, 0, lam=1.5)
+    with pytest.raises(qpde.QpdeError):
+        qpde.optimal_consumption_solve(handle, 0, gamma=0.)
+    with pytest.raises(qpde.QpdeError):
+        qpde.optimal_consumption_solve(handle, 0, spatial_points=2)
