@@ -1099,6 +1099,91 @@ public:
 	}
 };
 
+////////////////////////////////////////////////////////////////////////////////
+// OptimalConsumption — examples/hjbqvi/optimal_consumption.cpp on Modules/HJBQVI/HJBQVI.hpp: optimal
+// consumption with fixed and proportional transaction costs, a 2-D (stock w, bank b) HJBQVI under the
+// penalised scheme whose impulses (buying and selling stock) point both ways in the state.  The model is a
+// tagged form of qpde_hjbqvi2d with the example's parameters as members.
+////////////////////////////////////////////////////////////////////////////////
+
+class OptimalConsumption {
+public:
+	Real T, rho, r, mu, sigma, gamma, lambda, c, q_max;   // optimal_consumption.cpp:36-63
+	Real w_0, b_0;                                        // :66-67: the convergence test point
+	Real boundary;                                        // :79
+	int timesteps, controlPoints, spatialPoints;          // :70, :73, :80
+	Real scalingFactor, iterationTolerance;               // HJBQVI defaults: 1e-2, 1e-6
+	int maxIterations, maxSweeps;                         // guards (the reference has none)
+
+	OptimalConsumption() : T(40.), rho(.1), r(.07), mu(.11), sigma(.3), gamma(.3), lambda(.1), c(.05), q_max(100.),
+			w_0(45.2), b_0(45.2), boundary(200.), timesteps(32), controlPoints(16), spatialPoints(20),
+			scalingFactor(1e-2), iterationTolerance(1e-6), maxIterations(200), maxSweeps(20000) {}
+
+	struct Result {
+		std::vector<Real> W, B, V, Q, Z;     // V[ib * W.size() + iw] (w fastest, Core/Domain.hpp:1416-1425)
+		int stochasticControlNodes, impulseControlNodes, steps;
+		Real meanPolicyIterations, meanSolverIterations;
+		// PiecewiseLinear<2>::interpolate (Core/Interpolant.hpp:153-181,331-374)
+		Real operator()(Real w, Real b) const {
+			auto bracket = [] (const std::vector<Real> &x, Real c, int &i, Real &wt) {
+				const int n = (int)x.size();
+				if(c <= x[0]) { i = 0; wt = 1.; return; }
+				if(c >= x[n - 1]) { i = n - 2; wt = 0.; return; }
+				int lo = 0, hi = n - 2, mid = 0; wt = 0.;
+				while(lo <= hi) {
+					mid = (lo + hi) / 2;
+					if(c < x[mid]) hi = mid - 1;
+					else if(c >= x[mid + 1]) lo = mid + 1;
+					else { wt = (x[mid + 1] - c) / (x[mid + 1] - x[mid]); break; }
+				}
+				i = mid;
+			};
+			int iw, ib; Real fw, fb;
+			bracket(W, w, iw, fw); bracket(B, b, ib, fb);
+			const size_t nw = W.size();
+			// corner order of Interpolant.hpp:343-368: bit j of the corner index set <=> lower node in dimension j
+			const Real wt[4] = { (1. - fw) * (1. - fb), fw * (1. - fb), (1. - fw) * fb, fw * fb };
+			const size_t at[4] = { (ib + 1) * nw + iw + 1, (ib + 1) * nw + iw, ib * nw + iw + 1, ib * nw + iw };
+			Real sum = 0.;
+			for(int m = 0; m < 4; ++m) if(wt[m] > epsilon) sum += wt[m] * V[at[m]];
+			return sum;
+		}
+	};
+
+	Result solve(B200Solver &solver, int refinement) const {
+		const Axis axis = Axis::uniform(0., boundary, spatialPoints);                                     // :80-81
+		const Axis controls = Axis::uniform(0., q_max, controlPoints), impulses = Axis::uniform(0., 1., controlPoints);   // :110-113
+		const Real par[8] = { rho, r, mu, sigma, gamma, lambda, c, boundary };
+		qpde_hjbqvi2d g = qpde_hjbqvi2d();
+		g.abi_version = QPDE_ABI_VERSION; g.model = QPDE_HJBQVI2D_OPTIMAL_CONSUMPTION; g.refine = refinement;
+		g.w_axis = axis.data(); g.n_w_axis = axis.size(); g.b_axis = axis.data(); g.n_b_axis = axis.size();
+		g.control_axis = controls.data(); g.n_control_axis = controls.size();
+		g.impulse_axis = impulses.data(); g.n_impulse_axis = impulses.size();
+		g.params = par; g.n_params = 8;
+		g.T = T; g.timesteps = timesteps;
+		for(int k = 0; k < refinement; ++k) g.timesteps *= 2;       // HJBQVI.hpp:629-632
+		g.max_inner = maxIterations; g.max_sweeps = maxSweeps;
+		g.scaling_factor = scalingFactor; g.tolerance = iterationTolerance;
+		int nw = 0, nb = 0;
+		solver.check(qpde_hjbqvi2d_nodes(&g, &nw, &nb));
+		Result res;
+		const size_t n = (size_t)nw * nb;
+		res.W.resize(nw); res.B.resize(nb); res.V.resize(n); res.Q.resize(n); res.Z.resize(n);
+		qpde_hjbqvi2d_stats st = qpde_hjbqvi2d_stats();
+		solver.check(qpde_hjbqvi2d_solve(solver.handle(), &g, res.V.data(), res.Q.data(), res.Z.data(), nullptr,
+			res.W.data(), res.B.data(), &st));
+		if(st.status != 0) {
+			throw std::runtime_error(st.status == 1 ? "QuantPDE_B200: OptimalConsumption policy iteration hit maxIterations"
+				: "QuantPDE_B200: OptimalConsumption line sweeps did not settle");
+		}
+		int cn = controlPoints - 1;
+		for(int k = 0; k < refinement; ++k) cn *= 2;
+		res.stochasticControlNodes = cn + 1; res.impulseControlNodes = cn + 1;
+		res.steps = st.n_steps; res.meanPolicyIterations = st.mean_inner; res.meanSolverIterations = st.mean_sweeps;
+		return res;
+	}
+};
+
 inline Solution ReverseConstantStepper::solve(const RectilinearGrid1 &grid, const Payoff &payoff,
 		IterationNode &root, B200Solver &solver) {
 	Batch batch;

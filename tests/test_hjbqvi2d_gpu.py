@@ -65,3 +65,24 @@ def test_optimal_consumption_errors(qpde, handle):
         qpde.optimal_consumption_solve(handle, 0, gamma=0.)
     with pytest.raises(qpde.QpdeError):
         qpde.optimal_consumption_solve(handle, 0, spatial_points=2)
+
+
+def test_example_program_reproduces_the_reference_programs_table():
+    """examples/bin/optimal_consumption_b200 against the stdout of the reference's own, unmodified
+    examples/hjbqvi/optimal_consumption.cpp (oracle/_ref/examples/optimal_consumption), recorded for as long as it
+    got in 15 minutes on one host core: refinement levels 0 .. 3 of the 0 .. 6 it is fixed at
+    (tests/golden/tables_hjbqvi/optimal_consumption_levels_0_3.txt).  The rows are equal character for character
+    except "Mean Solver Iterations" and the execution time, and "Change" / "Ratio" to 2e-6 relative."""
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    subprocess.run(["make", "-s", "-C", os.path.join(root, "examples")], check=True)
+    got = subprocess.run([os.path.join(root, "examples", "bin", "optimal_consumption_b200"), "max_refinement=3", "dump=0"],
+                         check=True, capture_output=True, text=True).stdout.splitlines()
+    want = open(os.path.join(root, "tests", "golden", "tables_hjbqvi", "optimal_consumption_levels_0_3.txt")).read().splitlines()
+    assert len(got) == len(want) == 5 and got[0] == want[0]
+    for g, w in zip(got[1:], want[1:]):
+        assert len(g) == len(w) == 12 * 23
+        gf, wf = [g[23 * k:23 * (k + 1)] for k in range(12)], [w[23 * k:23 * (k + 1)] for k in range(12)]
+        assert gf[:7] == wf[:7] and gf[8] == wf[8], (g, w)
+        for a, b in zip(gf[9:11], wf[9:11]):
+            assert a == b or abs(float(a) - float(b)) <= 2e-6 * abs(float(b)), (g, w)
