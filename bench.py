@@ -6,7 +6,7 @@ a batch of American puts (varied strike / vol / T / r, seeded as SURVEY.md
     python bench.py --gpus N --steps K --warmup W [--impl reference]
     torchrun ... bench.py --gpus N ...      (one rank per GPU, N > 1)
 
-    python bench.py --config {1,3,4,5,hjb}      (1 = BASELINE.json configs[1], the default and the
+    python bench.py --config {1,3,4,5,hjb,er,oc}      (1 = BASELINE.json configs[1], the default and the
                                                  driver's contract; 3 / 4 / 5 = configs[2] / [3] / [4],
                                                  hjb = the policy-iteration example: one GPU each)
 
@@ -548,6 +548,123 @@ def run_other_config(args):
             cb = cpu_ref(rjobs)
             if cb:
                 line["cpu_baseline"] = cb
+    elif cfg == "er":
+        # ---- examples/hjbqvi/exchange_rate.cpp: a batch of 1-D impulse-control HJBQVI problems (varied
+        # sigma, a, b, lambda, c), one CTA each; qpde_hjbqvi1d_solve takes host arrays in and out, so the
+        # timed call IS the end-to-end one
+        g = np.load(os.path.join(ROOT, "tests", "golden", "hjbqvi1d_reference.npz"), allow_pickle=False)
+        X0, Q0, Z0 = g["er_k0/X0"], g["er_k0/Q0"], g["er_k0/Z0"]
+        refine = args.hjbqvi_refine if args.hjbqvi_refine >= 0 else 4
+        Pn = args.contracts or 2 * handle.sm_count
+        rng = np.random.default_rng(4321)
+        par = np.stack([np.full(Pn, .02), rng.uniform(.2, .4, Pn), rng.uniform(.15, .5, Pn), rng.uniform(1., 4., Pn),
+                        np.zeros(Pn), rng.uniform(.5, 1.5, Pn), rng.uniform(.05, .15, Pn)], axis=1)
+        steps = 16 * 2 ** refine
+        # parity first: the reference's own outputs at this model's default parameters, refinements 2 and 3
+        worst = 0.
+        for name in ("er_k2", "er_k3"):
+            k = int(name[-1])
+            small = capi.exchange_rate_solve(handle, X0, Q0, Z0, [[.02, .3, .25, 3., 0., 1., .1]], k, 16 * 2 ** k)
+            worst = max(worst, _rel(small["V"][0], g[name + "/V"]))
+            assert small["mean_inner"][0] == float(g[name + "/mean_inner"]), name
+        assert worst <= 1e-9, worst
+        capi.exchange_rate_solve(handle, X0, Q0, Z0, par[:2], 1, 32)            # warm-up
+        ts = []
+        l0 = handle.launches
+        nrun = max(1, min(args.steps, 3))
+        for _ in range(nrun):
+            t0 = time.perf_counter()
+            res = capi.exchange_rate_solve(handle, X0, Q0, Z0, par, refine, steps)
+            ts.append(time.perf_counter() - t0)
+        launches = (handle.launches - l0) // nrun
+        secs = float(np.mean(ts))
+        N, nq, nz = res["V"].shape[1], res["n_controls"], res["n_impulses"]
+        its = float((res["mean_inner"] * res["n_steps"]).sum())              # policy iterations over the batch
+        sweeps = float((res["mean_inner"] * res["n_steps"] * res["mean_sweeps"]).sum())
+        flops = N * (its * (24.0 * nq + 12.0 * nz) + sweeps * 40.0)
+        tf = flops / secs / 1e12
+        line = {"metric": "exchange-rate HJBQVI solves/sec (1-D impulse control, %d nodes, %d + %d controls, %d BDF1 steps)" % (N, nq, nz, steps),
+                "value": Pn / secs, "unit": "solves/s", "n_gpus": 1, "steps": nrun, "warmup": 1, "ms_per_step": 1e3 * secs,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": {"workload": "exchange_rate_hjbqvi_1d_batch (examples/hjbqvi/exchange_rate.cpp at refinement %d)" % refine,
+                           "problems": Pn, "nodes": N, "stochastic_controls": nq, "impulse_controls": nz, "time_steps": steps,
+                           "mean_policy_iterations": float(res["mean_inner"].mean()), "mean_sweeps": float(res["mean_sweeps"].mean()),
+                           "not_ok": int((res["status"] != 0).sum())},
+                "roofline": {"bound": "fp64", "achieved": tf, "peak": fp64_peak, "unit": "TFLOP/s", "frac": tf / fp64_peak,
+                             "traffic": None, "peak_source": "measured (qpde_measure_fp64_peak: independent DFMA chains)",
+                             "algorithmic_flops_per_launch": flops,
+                             "model": "per node and policy iteration: 24 flops per stochastic candidate (upwinded row, flow, "
+                                      "3-term product) + 12 per admissible impulse candidate, + 40 per node and lagged tridiagonal "
+                                      "solve; one launch, one CTA per problem (DESIGN.md 4.7)"},
+                "gpu_launches": int(launches),
+                "e2e": {"value": Pn / secs, "unit": "solves/s", "h2d_bytes_per_step": int(8 * (len(X0) + len(Q0) + len(Z0) + par.size)),
+                        "d2h_bytes_per_step": int(Pn * N * 33 + Pn * 24), "ms_per_step": 1e3 * secs,
+                        "api": "qpde_hjbqvi1d_solve (host axes and parameters in; V, X, Q, Z, mask out): the timed call itself"},
+                "parity_sample": {"n": 2, "worst_rel_err": worst, "tolerance": 1e-9, "policy_iteration_counts_equal": True,
+                                  "against": "tests/golden/hjbqvi1d_reference.npz er_k2, er_k3 (the reference's own outputs)"}}
+        if not args.no_cpu:
+            from oracle import pyoracle as po
+            if po.have_ref():
+                n_jobs = min(Pn, 2 * cores)
+                jobs = [("exchange", dict(refine=refine, sigma=float(par[c, 1]), a=float(par[c, 2]), b=float(par[c, 3]),
+                                          c=float(par[c, 6]), **{"lambda": float(par[c, 5])})) for c in range(n_jobs)]
+                cb = cpu_ref(jobs)
+                if cb:
+                    line["cpu_baseline"] = cb
+    elif cfg == "oc":
+        # ---- examples/hjbqvi/optimal_consumption.cpp: the 2-D HJBQVI with impulses both ways; the timed call is
+        # qpde_hjbqvi2d_solve (host in, host out) at refinement 4 (305 x 305 nodes, 241 + 241 controls, 512 steps)
+        refine = args.hjbqvi_refine if args.hjbqvi_refine >= 0 else 4
+        g = np.load(os.path.join(ROOT, "tests", "golden", "hjbqvi2d_reference.npz"), allow_pickle=False)
+        small = capi.optimal_consumption_solve(handle, 2)                       # warm-up + parity: the reference's own output
+        worst = _rel(small["V"], g["oc_k2/V"].reshape(small["V"].shape))
+        assert worst <= 1e-9 and small["mean_inner"] == float(g["oc_k2/mean_inner"]), worst
+        ts = []
+        l0 = handle.launches
+        nrun = max(1, min(args.steps, 2))
+        for _ in range(nrun):
+            t0 = time.perf_counter()
+            res = capi.optimal_consumption_solve(handle, refine)
+            ts.append(time.perf_counter() - t0)
+        launches = (handle.launches - l0) // nrun
+        secs = float(np.mean(ts))
+        nw, nb = len(res["W"]), len(res["B"])
+        ncand = 15 * 2 ** refine + 1
+        its = float(res["mean_inner"]) * res["n_steps"]
+        flops = nw * nb * its * (30.0 * ncand + 90.0 * ncand + float(res["mean_sweeps"]) * 30.0)
+        tf = flops / secs / 1e12
+        line = {"metric": "optimal-consumption HJBQVI solves/sec (2-D impulse control both ways, %d x %d nodes, %d BDF1 steps)" % (nw, nb, res["n_steps"]),
+                "value": 1.0 / secs, "unit": "solves/s", "n_gpus": 1, "steps": nrun, "warmup": 1, "ms_per_step": 1e3 * secs,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": {"workload": "optimal_consumption_hjbqvi_2d (examples/hjbqvi/optimal_consumption.cpp at refinement %d)" % refine,
+                           "nodes_w": nw, "nodes_b": nb, "stochastic_controls": ncand, "impulse_controls": ncand,
+                           "time_steps": int(res["n_steps"]), "mean_policy_iterations": float(res["mean_inner"]),
+                           "line_sweeps_per_policy_iteration": float(res["mean_sweeps"]), "status": int(res["status"]),
+                           "seconds_per_solve": secs, "node_steps_per_s": nw * nb * res["n_steps"] / secs},
+                "roofline": {"bound": "fp64", "achieved": tf, "peak": fp64_peak, "unit": "TFLOP/s", "frac": tf / fp64_peak,
+                             "traffic": None, "peak_source": "measured (qpde_measure_fp64_peak: independent DFMA chains)",
+                             "algorithmic_flops_per_launch": flops / max(1, launches),
+                             "model": "per node and policy iteration: 30 flops per stochastic candidate + 90 per impulse candidate "
+                                      "(admissible transfer, two brackets, bilinear row) + 30 per node and line sweep; the solve is "
+                                      "launch- and latency-bound on small grids: 2 launches per sweep of ~150 sweeps (DESIGN.md 4.8)"},
+                "gpu_launches": int(launches),
+                "e2e": {"value": 1.0 / secs, "unit": "solves/s", "h2d_bytes_per_step": int(8 * (nw * nb + 2 * 16 + 2 * 20 + 8)),
+                        "d2h_bytes_per_step": int(nw * nb * 25), "ms_per_step": 1e3 * secs,
+                        "api": "qpde_hjbqvi2d_solve (host axes and parameters in; V, Q, Z, mask out): the timed call itself"},
+                "parity_sample": {"n": 1, "worst_rel_err": worst, "tolerance": 1e-9, "policy_iteration_counts_equal": True,
+                                  "against": "tests/golden/hjbqvi2d_reference.npz oc_k2 (the reference's own output, 77 x 77 nodes, 128 steps)"}}
+        if not args.no_cpu:
+            from oracle import pyoracle as po
+            if po.have_ref():
+                t0 = time.perf_counter()
+                ref = po.run_ref("consumption", refine=2)
+                wall = time.perf_counter() - t0
+                n1 = len(ref["W"]) * len(ref["B"]) * int(ref["steps"])
+                line["cpu_baseline"] = {"value": 1.0 / wall, "unit": "solves/s", "cores": 1, "kind": "reference",
+                                        "node_steps_per_s": n1 / wall,
+                                        "sample": "refinement 2 of the same problem (77 x 77 nodes, 61 + 61 controls, 128 steps): %.1f s on "
+                                                  "one core (the reference is single-threaded; refinement 3 takes it 633 s, refinement 4 "
+                                                  "hours); compare node_steps_per_s, not solves/s" % wall}
     else:
         # ---- configs[4]: GMWB 2-D impulse control, 4097 x 1025 nodes; qpde_gmwb2d_solve takes host arrays
         # in and out, so the timed call IS the end-to-end one
@@ -709,6 +826,31 @@ def run_reference_arm_other(args):
         value = 1.0 / float(np.mean(walls))
         sample = "refinement 1 of the reference's default GMWB problem (129 x 101 nodes, 64 steps) on one core"
         workload, n_jobs = "gmwb_2d_impulse_control (BASELINE.json configs[4]), bounded sample", 1
+    elif cfg == "oc":
+        walls = []
+        for _ in range(max(1, min(args.steps, 2))):
+            t0 = time.perf_counter(); ref = po.run_ref("consumption", refine=2); walls.append(time.perf_counter() - t0)
+        value = 1.0 / float(np.mean(walls))
+        sample = "refinement 2 of the reference's optimal-consumption problem (77 x 77 nodes, 128 steps) on one core"
+        workload, n_jobs = "optimal_consumption_hjbqvi_2d, bounded sample", 1
+    elif cfg == "er":
+        refine = args.hjbqvi_refine if args.hjbqvi_refine >= 0 else 4
+        n_jobs = args.cpu_sample or 2 * cores
+        rng = np.random.default_rng(4321)
+        Pn = max(n_jobs, 296)
+        sig, a_, b_, lam, c_ = rng.uniform(.2, .4, Pn), rng.uniform(.15, .5, Pn), rng.uniform(1., 4., Pn), rng.uniform(.5, 1.5, Pn), rng.uniform(.05, .15, Pn)
+        jobs = [("exchange", dict(refine=refine, sigma=float(sig[c]), a=float(a_[c]), b=float(b_[c]), c=float(c_[c]),
+                                  **{"lambda": float(lam[c])})) for c in range(n_jobs)]
+        walls = []
+        for k in range(args.warmup + args.steps):
+            t0 = time.perf_counter()
+            with ProcessPoolExecutor(max_workers=cores) as ex:
+                list(ex.map(_ref_job, jobs))
+            if k >= args.warmup:
+                walls.append(time.perf_counter() - t0)
+        value = n_jobs * len(walls) / float(sum(walls))
+        sample = "%d problems of the workload per step, one per worker process on %d cores" % (n_jobs, cores)
+        workload = "exchange_rate_hjbqvi_1d_batch (examples/hjbqvi/exchange_rate.cpp at refinement %d)" % refine
     else:
         P = _other_config_problem(cfg, args.contracts)
         n_jobs = args.cpu_sample or 2 * cores
@@ -738,7 +880,7 @@ def run_reference_arm_other(args):
                       "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * float(np.mean(walls)),
                       "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
                       "config": {"workload": workload, "contracts_per_step": n_jobs},
-                      "cpu_baseline": {"value": value, "unit": "solves/s", "cores": cores if cfg != "5" else 1, "kind": "reference",
+                      "cpu_baseline": {"value": value, "unit": "solves/s", "cores": cores if cfg not in ("5", "oc") else 1, "kind": "reference",
                                        "sample": sample},
                       "e2e": {"value": value, "unit": "solves/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                       "gpu_launches": 0}))
@@ -750,13 +892,14 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--config", default="1", choices=["1", "3", "4", "5", "hjb"],
+    ap.add_argument("--config", default="1", choices=["1", "3", "4", "5", "hjb", "er", "oc"],
                     help="1: BASELINE.json configs[1] (default); 3 / 4 / 5: configs[2] / [3] / [4]; hjb: policy iteration")
     ap.add_argument("--contracts", type=int, default=0, help="contracts per GPU (default: the config's batch size)")
     ap.add_argument("--kernel", default="auto", choices=["auto", "interleaved", "resident"])
     ap.add_argument("--cpu-sample", type=int, default=0)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--hjbqvi-refine", type=int, default=-1, help="--config er / oc: grid refinement (default 4)")
     ap.add_argument("--gmwb-refine", type=int, default=6, help="--config 5: grid refinement (6 = 4097 x 1025)")
     ap.add_argument("--gmwb-timesteps0", type=int, default=32, help="--config 5: time steps before refinement (32 -> 2048 at refinement 6)")
     ap.add_argument("--no-strong", action="store_true", help="N > 1: skip the strong-scaling leg (65,536 contracts in total)")

@@ -30,7 +30,8 @@ namespace qpde {
 
 namespace {
 
-constexpr int HP = 256;   // threads per problem; M rows per thread (8: up to 2048 nodes, 9: up to 2304), MP = M * HP rows of a system
+constexpr int HP = 256;   // threads per problem; M rows per thread (the smallest of 2, 3, 5, 8, 9 with M * HP >= nodes: rows are
+                          // contiguous per thread, so a larger M would leave most threads without rows), MP = M * HP rows of a system
 
 // model 1: examples/hjbqvi/exchange_rate.cpp:118-152
 struct ExchangeRate {
@@ -314,13 +315,26 @@ k_hjbqvi1d(Hjbqvi1dBatch b, Hjbqvi1dResult out) {
 	}
 }
 
-size_t hjbqvi1d_shared_bytes(int N, int nq, int nz) { return hjbqvi1d_smem_bytes(N <= 8 * HP ? 8 : 9, nq, nz); }
+static int rows_per_thread(int N) {
+	const int choices[5] = { 2, 3, 5, 8, 9 };
+	for(int m : choices) if(N <= m * HP) return m;
+	return 0;
+}
+
+size_t hjbqvi1d_shared_bytes(int N, int nq, int nz) { return hjbqvi1d_smem_bytes(rows_per_thread(N) ? rows_per_thread(N) : 9, nq, nz); }
 
 int launch_hjbqvi1d(const Hjbqvi1dBatch &b, const Hjbqvi1dResult &out, cudaStream_t stream, long long *launches) {
 	if(b.N < 3 || b.N > 9 * HP || b.model != QPDE_HJBQVI1D_EXCHANGE_RATE) return QPDE_ERR_UNSUPPORTED;
 	const size_t bytes = hjbqvi1d_shared_bytes(b.N, b.nq, b.nz);
 	if(bytes > 227 * 1024) return QPDE_ERR_UNSUPPORTED;
-	auto kern = b.N <= 8 * HP ? k_hjbqvi1d<ExchangeRate, 8> : k_hjbqvi1d<ExchangeRate, 9>;
+	void (*kern)(Hjbqvi1dBatch, Hjbqvi1dResult) = nullptr;
+	switch(rows_per_thread(b.N)) {
+	case 2: kern = k_hjbqvi1d<ExchangeRate, 2>; break;
+	case 3: kern = k_hjbqvi1d<ExchangeRate, 3>; break;
+	case 5: kern = k_hjbqvi1d<ExchangeRate, 5>; break;
+	case 8: kern = k_hjbqvi1d<ExchangeRate, 8>; break;
+	default: kern = k_hjbqvi1d<ExchangeRate, 9>; break;
+	}
 	if(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes) != cudaSuccess) return QPDE_ERR_CUDA;
 	kern<<<b.n_problems, HP, bytes, stream>>>(b, out);
 	*launches += 1;
