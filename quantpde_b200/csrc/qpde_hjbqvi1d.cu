@@ -92,7 +92,7 @@ __device__ __forceinline__ double impulse_lhs(int row, int idx, double w, double
 } // namespace
 
 template <typename Model, int M>
-__global__ void __launch_bounds__(HP, 1)
+__global__ void __launch_bounds__(HP, M <= 3 ? 2 : 1)
 k_hjbqvi1d(Hjbqvi1dBatch b, Hjbqvi1dResult out) {
 	constexpr int HM = M, HMP = M * HP;
 	extern __shared__ __align__(16) unsigned char smem_raw[];
