@@ -114,3 +114,27 @@ def test_example_program_reproduces_the_reference_programs_stdout():
         assert len(g) == len(w) and g[:23] == w[:23] and g[46:] == w[46:], (g, w)          # node and both controls
         assert abs(float(g[23:46]) - float(w[23:46])) <= 2e-11 * abs(float(w[23:46])), (g, w)
     assert off <= len(want) // 4
+
+
+def test_exchange_rate_edge_parameters_against_oracle(qpde, handle, oracle):
+    """Corners of the model in one batch: interventions that never pay (c = 5) or nearly always do (tiny costs),
+    no diffusion at all (sigma = 0: the rows are pure upwinding), no discounting, a free stochastic control
+    (b = 0).  The oracle agrees with the reference on each of them (checked when the fixtures were made:
+    <= 8e-13, identical policy-iteration counts and impulse regions)."""
+    g = np.load(GOLDEN)
+    X0, Q0, Z0 = g["er_k0/X0"], g["er_k0/Q0"], g["er_k0/Z0"]
+    cases = [dict(c=5.), dict(c=1e-3, lam=.05), dict(sigma=0.), dict(sigma=1e-3, a=2.), dict(lam=0., c=1e-6), dict(rho=0.), dict(b=0.)]
+    res = qpde.exchange_rate_solve(handle, X0, Q0, Z0, [_params(kw) for kw in cases], 2, 64)
+    for p, kw in enumerate(cases):
+        o = oracle.exchange_rate(X0, Q0, Z0, refine_times=2, **kw)
+        assert res["status"][p] == 0 and o["status"] == 0, kw
+        err = np.abs(res["V"][p] - o["V"]) / np.maximum(1., np.abs(o["V"]))
+        assert err.max() <= REL_TOL, "%s: %.3e" % (kw, err.max())
+        assert res["mean_inner"][p] == o["mean_inner"], kw
+        assert np.array_equal(res["mask"][p], o["mask"]), kw
+    # one-point control grids: no stochastic control to choose, a single intervention target
+    one = qpde.exchange_rate_solve(handle, X0, [0.], [0.], [_params({})], 1, 32)
+    o = oracle.exchange_rate(X0, [0.], [0.], refine_times=1)
+    err = np.abs(one["V"][0] - o["V"]) / np.maximum(1., np.abs(o["V"]))
+    assert one["status"][0] == 0 and err.max() <= REL_TOL and one["mean_inner"][0] == o["mean_inner"]
+    assert one["n_controls"] == 1 and one["n_impulses"] == 1
