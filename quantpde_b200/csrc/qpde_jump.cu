@@ -48,7 +48,7 @@ inline size_t jump_smem_bytes(int M, int P, int NF) {
 	// points (real data, see below): work buffer, twiddles of the half-size transform,
 	// exp(-2 pi i k / NF) for k <= NF / 4, spectrum of the density weights for k <= NF / 2
 	const int NH = NF / 2;
-	return sizeof(JumpSmem) + sizeof(double) * ((size_t)JUMP_ROW_ARRAYS * M * P + 2)
+	return sizeof(JumpSmem) + sizeof(double) * ((size_t)JUMP_ROW_ARRAYS * M * P + P + 2)
 		+ sizeof(double2) * ((size_t)pad_buf_size(NH) + pad_tw_size(NH) + (NH / 2 + 1) + (NH + 1));
 }
 
@@ -207,10 +207,10 @@ k_jump_sweep(DeviceBatch b, JumpWork work, DeviceResult out) {
 	double *const sm_lo = sm_S + MP;
 	double *const sm_di = sm_lo + MP;
 	double *const sm_up = sm_di + MP;
-	double *const sm_V  = sm_up + MP;             // [MP + 1]: current solution, node-addressable
+	double *const sm_V  = sm_up + MP;             // [MP + P + 1]: current solution in node order (at_node below)
 	const int NF = b.n_fft, NH = NF / 2;          // NF real points = NH complex points (spectral_pass)
 	const int logNH = 31 - __clz(NH);
-	double2 *const sm_buf = reinterpret_cast<double2 *>(sm_V + MP + 2);   // [NH], padded (pad_buf)
+	double2 *const sm_buf = reinterpret_cast<double2 *>(sm_V + MP + P + 2);   // [NH], padded (pad_buf)
 	double2 *const sm_tw = sm_buf + pad_buf_size(NH);                     // [NH / 2], padded (pad_tw): exp(-2 pi i k / NH)
 	double2 *const sm_tq = sm_tw + pad_tw_size(NH);                       // [NH / 2 + 1]: exp(-2 pi i k / NF)
 	double2 *const sm_F = sm_tq + (NH / 2 + 1);                           // [NH + 1]: spectrum of the density weights
@@ -233,7 +233,11 @@ k_jump_sweep(DeviceBatch b, JumpWork work, DeviceResult out) {
 	double *const n_w = work.n_w + (size_t)cidx * N;
 
 	// node i of V / S in shared memory
-	auto at_node = [&] (int i) -> int { return i >= n_main ? MP : (i % M) * P + (i / M); };
+	// The log-grid gather reads V at neighbouring nodes from neighbouring lanes: V is kept in node order, so that
+	// they fall into neighbouring banks (in the [row][thread] order of the other row arrays, nodes i and i + 1 are
+	// P doubles apart — the same bank: 38 % of the kernel's shared-memory wavefronts were conflicts).  One pad per
+	// thread when M is even keeps the threads' own stores (M rows each) conflict-free too.
+	auto at_node = [&] (int i) -> int { return i >= n_main ? MP + P : (M % 2 == 0 ? i + i / M : i); };
 
 	// ------------------------------------------------------------------
 	// Setup
@@ -361,8 +365,8 @@ k_jump_sweep(DeviceBatch b, JumpWork work, DeviceResult out) {
 
 		// ---- (1) V onto the log-grid, bit-reversed ------------------------
 #pragma unroll
-		for(int j = 0; j < M; ++j) sm_V[j * P + tid] = x[j];
-		if(tail_owner) sm_V[MP] = sm.tail.x;
+		for(int j = 0; j < M; ++j) sm_V[M % 2 == 0 ? i0 + j + tid : i0 + j] = x[j];
+		if(tail_owner) sm_V[MP + P] = sm.tail.x;
 		__syncthreads();
 		// two real points per complex element; the table loads of two elements are issued together
 		for(int m0 = tid; m0 < NH; m0 += 2 * P) {
