@@ -142,3 +142,38 @@ def test_event_expression_lowers_to_a_program_with_the_lambdas_value(tmp_path):
                 tmp = Rn * (GQ + (1. - pen) * (S - GQ))
                 best = tmp if tmp > best else best
             assert run(S, (Rn, pen)) == best
+
+
+def test_axis_cluster_reproduces_the_reference_axes(tmp_path):
+    """Axis::cluster (Core/Axis.hpp:51-90,238-257) on the host gives the ticks the reference's own program dumped
+    (tests/golden/hjbqvi1d_reference.npz: X0 = cluster(-2, 0, 2, 32, 10), Z0 = cluster(-2, 0, 2, 16, 10)) bit for
+    bit, and the ExchangeRate / OptimalConsumption classes carry the examples' default parameters."""
+    import numpy as np
+    src = tmp_path / "cluster.cpp"
+    src.write_text(textwrap.dedent("""
+        #include <QuantPDE_B200/Core.hpp>
+        #include <cstdio>
+        using namespace QuantPDE_B200;
+        int main() {
+            ExchangeRate e;
+            OptimalConsumption o;
+            const Axis x = e.xAxis(), z = e.impulseAxis(), q = e.controlAxis();
+            std::printf("%d %d %d %d\\n", (int) x.size(), (int) z.size(), (int) q.size(), o.spatialPoints);
+            for(Index i = 0; i < x.size(); ++i) std::printf("%a ", x[i]);
+            std::printf("\\n");
+            for(Index i = 0; i < z.size(); ++i) std::printf("%a ", z[i]);
+            std::printf("\\n");
+            for(Index i = 0; i < q.size(); ++i) std::printf("%a ", q[i]);
+            std::printf("\\n");
+            return e.rho == .02 && e.lambda == 1. && o.gamma == .3 && o.boundary == 200. ? 0 : 1;
+        }
+    """))
+    exe = tmp_path / "cluster"
+    subprocess.run(["g++", "-std=c++11", "-Wall", "-Werror", "-I" + os.path.join(ROOT, "include"),
+                    "-I" + os.path.join(ROOT, "quantpde_b200", "include"), str(src), "-o", str(exe),
+                    "-L" + LIB, "-lqpde_b200", "-Wl,-rpath," + LIB], check=True)
+    out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.splitlines()
+    g = np.load(os.path.join(ROOT, "tests", "golden", "hjbqvi1d_reference.npz"))
+    assert out[0].split() == ["33", "17", "9", "20"]
+    for line, key in zip(out[1:4], ("er_k0/X0", "er_k0/Z0", "er_k0/Q0")):
+        assert np.array_equal(np.array([float.fromhex(t) for t in line.split()]), g[key]), key
