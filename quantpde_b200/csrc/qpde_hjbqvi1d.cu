@@ -60,8 +60,10 @@ struct Hjbqvi1dSmem {
 };
 
 // shared memory: 7 row arrays + the control grids and the per-candidate tables (doubles), then two int arrays
+// (M < 9: three more row arrays and a byte per row for the hand-over of the balanced search, see the kernel)
 __host__ __device__ inline size_t hjbqvi1d_smem_bytes(int M, int nq, int nz) {
-	return ((sizeof(Hjbqvi1dSmem) + 15) / 16) * 16 + sizeof(double) * ((size_t)7 * M * HP + nq + 5 * (size_t)nz) + sizeof(int) * ((size_t)M * HP + nz);
+	return ((sizeof(Hjbqvi1dSmem) + 15) / 16) * 16 + sizeof(double) * ((size_t)(M < 9 ? 10 : 7) * M * HP + nq + 5 * (size_t)nz)
+		+ sizeof(int) * ((size_t)M * HP + nz) + (M < 9 ? (size_t)M * HP : 0);
 }
 
 // linearInterpolationData (Core/Interpolant.hpp:153-181) over a node-addressable grid
@@ -110,8 +112,17 @@ k_hjbqvi1d(Hjbqvi1dBatch b, Hjbqvi1dResult out) {
 	double *const z_w = sdz + b.nz;
 	double *const sA = z_w + b.nz;
 	double *const sB = sA + b.nz;
-	int *const i_k = reinterpret_cast<int *>(sB + b.nz);   // [j][tid]: lower interpolation node of the chosen impulse target
+	// BAL: the searches run node-strided (thread t takes the nodes t, t + 256, ...), so that every warp gets near and
+	// far nodes alike — the admissible impulse candidates of a node grow with its distance from the parity, and with
+	// the solver's contiguous rows per thread the warps at the ends of the grid searched while the central ones sat
+	// at the solver's barrier (ncu: 32 % of the stall samples).  The rows then reach their owners through shared memory.
+	constexpr bool BAL = M < 9;
+	double *const h_a = sB + b.nz;        // BAL: hand-over of the assembled rows
+	double *const h_b = h_a + (BAL ? HMP : 0);
+	double *const h_c = h_b + (BAL ? HMP : 0);
+	int *const i_k = reinterpret_cast<int *>(h_c + (BAL ? HMP : 0));   // [j][tid]: lower interpolation node of the chosen impulse target
 	int *const z_idx = i_k + HMP;         // [nz]: lower interpolation node of candidate k's target
+	unsigned char *const h_f = reinterpret_cast<unsigned char *>(z_idx + b.nz);   // BAL: bit 0 active, bits 1-2 far entries
 
 	const int pidx = blockIdx.x;
 	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -169,9 +180,14 @@ k_hjbqvi1d(Hjbqvi1dBatch b, Hjbqvi1dResult out) {
 			double aa[HM], bb[HM], cc[HM];
 #pragma unroll
 			for(int j = 0; j < HM; ++j) {
-				const int i = i0 + j, at = j * HP + tid;
-				if(i >= N) { aa[j] = 0.; bb[j] = 1.; cc[j] = 0.; continue; }
-				const double xi = sX[at], vi = xprev[j];
+				const int i = BAL ? j * HP + tid : i0 + j;              // the node this thread searches
+				const int at = BAL ? slot<M>(i) : j * HP + tid;         // its place in the [row][thread] arrays
+				if(i >= N) {
+					if(BAL) { if(i < HMP) { h_a[at] = 0.; h_b[at] = 1.; h_c[at] = 0.; h_f[at] = 0; } }
+					else { aa[j] = 0.; bb[j] = 1.; cc[j] = 0.; }
+					continue;
+				}
+				const double xi = sX[at], vi = BAL ? sx[at] : xprev[j];
 				const bool interior = i > 0 && i < N - 1;
 				// 1. stochastic policy: argmin_q (A(q) x - b(q))_i, strict < (PolicyIteration.hpp:88-96)
 				double dxb = 1., dxc = 1., dxf = 1., alpha_common = 0., beta_common = 0., vm = 0., vp = 0.;
@@ -183,25 +199,39 @@ k_hjbqvi1d(Hjbqvi1dBatch b, Hjbqvi1dResult out) {
 					vm = sx[slot<M>(i - 1)]; vp = sx[slot<M>(i + 1)];
 				}
 				const double rho = mdl.discount(xi);
-				double best = CUDART_INF, blo = 0., bup = 0., bdi = 0., bfl = 0., bq = 0.;
-				for(int k = 0; k < nq; ++k) {
-					const double q = sq[k];
-					double lo = 0., up = 0., total = 0.;
+				// The search divides the drift of every candidate by a spacing of the node: the quotient comes from a
+				// reciprocal formed once per node plus one correction (div_by: the correctly rounded quotient but for
+				// rare last-bit cases) instead of the ~25-instruction division sequence; the row of the CHOSEN control
+				// is then formed again with the reference's plain divisions, so that the matrix is the reference's.
+				const double rdxc = 1. / dxc, rdxf = 1. / dxf, rdxb = 1. / dxb;
+				auto row_of = [&] (double q, bool exact, double &lo, double &up, double &di) {
+					lo = 0.; up = 0.;
+					double total = 0.;
 					if(interior) {
 						const double mu = 0. + mdl.drift(xi, q);
-						double alpha = alpha_common - mu / dxc, beta = beta_common + mu / dxc;
-						if(alpha < 0.) { alpha = alpha_common; beta = beta_common + mu / dxf; }
-						else if(beta < 0.) { alpha = alpha_common - mu / dxb; beta = beta_common; }
+						const double mc = exact ? mu / dxc : div_by(mu, dxc, rdxc);
+						double alpha = alpha_common - mc, beta = beta_common + mc;
+						if(alpha < 0.) { alpha = alpha_common; beta = beta_common + (exact ? mu / dxf : div_by(mu, dxf, rdxf)); }
+						else if(beta < 0.) { alpha = alpha_common - (exact ? mu / dxb : div_by(mu, dxb, rdxb)); beta = beta_common; }
 						lo = -alpha; up = -beta; total += alpha + beta;
 					}
-					const double di = total + rho, fl = mdl.flow(xi, q);
+					di = total + rho;
+				};
+				double best = CUDART_INF, bfl = 0., bq = 0.;
+				for(int k = 0; k < nq; ++k) {
+					const double q = sq[k];
+					double lo, up, di;
+					row_of(q, false, lo, up, di);
+					const double fl = mdl.flow(xi, q);
 					double acc = 0.;
 					if(interior) acc += lo * vm;
 					acc += di * vi;
 					if(interior) acc += up * vp;
 					const double cand = acc - fl;
-					if(cand < best) { best = cand; blo = lo; bup = up; bdi = di; bfl = fl; bq = q; }
+					if(cand < best) { best = cand; bfl = fl; bq = q; }
 				}
+				double blo, bup, bdi;
+				row_of(bq, true, blo, bup, bdi);
 				r_b[at] = bfl; r_q[at] = bq;
 				// 2. impulse policy: argmin_z ((I - M_z) x - reward_z)_i, strict <; pruned candidates are +inf
 				best = CUDART_INF;
@@ -225,14 +255,29 @@ k_hjbqvi1d(Hjbqvi1dBatch b, Hjbqvi1dResult out) {
 				i_k[at] = isel; i_z[at] = zsel; i_rew[at] = rew; i_w[at] = wsel;
 				// 4. row of (I + h0 L^q + P (I - M*)): entries on the three diagonals folded in
 				double a_ = blo * h0, b_ = 1. + bdi * h0, c_ = bup * h0;
+				unsigned fl = 0;                // bit 0: penalised; bits 1, 2: entry idx / idx + 1 is off the three diagonals
 				if(act) {
-					active |= 1u << j;
+					fl = 1u;
 					b_ += pen;
 					const double f0 = pen * wsel, f1 = pen * (-wsel + 1.);
-					if(isel == i) b_ -= f0; else if(isel == i - 1) a_ -= f0; else if(isel == i + 1) c_ -= f0; else far |= 1u << (2 * j);
-					if(isel + 1 == i) b_ -= f1; else if(isel + 1 == i - 1) a_ -= f1; else if(isel + 1 == i + 1) c_ -= f1; else far |= 2u << (2 * j);
+					if(isel == i) b_ -= f0; else if(isel == i - 1) a_ -= f0; else if(isel == i + 1) c_ -= f0; else fl |= 2u;
+					if(isel + 1 == i) b_ -= f1; else if(isel + 1 == i - 1) a_ -= f1; else if(isel + 1 == i + 1) c_ -= f1; else fl |= 4u;
 				}
-				aa[j] = a_; bb[j] = b_; cc[j] = c_;
+				if(BAL) { h_a[at] = a_; h_b[at] = b_; h_c[at] = c_; h_f[at] = (unsigned char)fl; }
+				else {
+					aa[j] = a_; bb[j] = b_; cc[j] = c_;
+					active |= (fl & 1u) << j; far |= (fl >> 1) << (2 * j);
+				}
+			}
+			if(BAL) {
+				__syncthreads();
+#pragma unroll
+				for(int j = 0; j < HM; ++j) {
+					const int at = j * HP + tid;
+					const unsigned fl = h_f[at];
+					aa[j] = h_a[at]; bb[j] = h_b[at]; cc[j] = h_c[at];
+					active |= (fl & 1u) << j; far |= (fl >> 1) << (2 * j);
+				}
 			}
 			ps.factorize(aa, bb, cc, sm.ps, lane, warp);
 			// ---- linear solve: lagged far entries, repeated to a 1e-15 relative update
