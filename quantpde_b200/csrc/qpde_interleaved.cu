@@ -161,10 +161,10 @@ k_interleaved_sweep(DeviceBatch b, InterleavedWork w, DeviceResult out) {
 		double c1 = 0., c0 = 0., den = 1.;
 		if(kind == STEP_BDF2) {
 			const double h1 = rp.lapse(time1, t), hh0 = rp.lapse(time0, t);     // BDF.hpp:68-73
-			gb.h = (hh0 * h1) / (hh0 + h1);
-			c1 = hh0 / h1; c0 = h1 / hh0; den = hh0 - h1;
+			gb.h = div_step(hh0 * h1, hh0 + h1);
+			c1 = div_step(hh0, h1); c0 = div_step(h1, hh0); den = hh0 - h1;
 		}
-		const double rden = 1. / den;
+		const double rden = div_step(1., den);
 		if(kind >= STEP_BDF3) {
 			// BDF.hpp:139-470: A = I + hh op.A; the right-hand side goes to lb here
 			const BdfHigh f = bdf_high_setup(kind - STEP_BDF3 + 3, t, time1, time0, th0, th1, th2, th3, b.forward);

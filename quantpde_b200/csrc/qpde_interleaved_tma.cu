@@ -195,14 +195,14 @@ k_interleaved_sweep_tma(const __grid_constant__ TmaMaps maps, DeviceBatch b, Int
 			gb.kind = kind; gb.h = h0;
 			if(kind == STEP_BDF2) {
 				const double h1 = rp.lapse(time1, t), hh0 = rp.lapse(time0, t);     // BDF.hpp:68-73
-				gb.h = (hh0 * h1) / (hh0 + h1);
-				c1 = hh0 / h1; c0 = h1 / hh0; den = hh0 - h1;
+				gb.h = div_step(hh0 * h1, hh0 + h1);
+				c1 = div_step(hh0, h1); c0 = div_step(h1, hh0); den = hh0 - h1;
 			}
 			// IterativeMethod.hpp:906: re-assemble A unless the root says it is the same
 			// (a penalty node in the tree keeps LinearSystem's default: never)
 			if(iterate || !ns.initialized || !ns.a_same(st.same_dt)) gA = gb;
 		}
-		const double rden = 1. / den;
+		const double rden = div_step(1., den);
 
 		// One row of the elimination of (lA + P) x = lb + P obstacle (the serial chain)
 		const double hsA = gA.factor(), hsb = gb.factor();   // Gamma::off(l) == l * factor(), without the switch

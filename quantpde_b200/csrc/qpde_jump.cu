@@ -345,10 +345,10 @@ k_jump_sweep(DeviceBatch b, JumpWork work, DeviceResult out) {
 		double c1 = 0., c0 = 0., den = 1.;
 		if(BDF2 && kind == STEP_BDF2) {
 			const double h1 = rp.lapse(time1, t), hh0 = rp.lapse(time0, t);
-			g.h = (hh0 * h1) / (hh0 + h1);
-			c1 = hh0 / h1; c0 = h1 / hh0; den = hh0 - h1;
+			g.h = div_step(hh0 * h1, hh0 + h1);
+			c1 = div_step(hh0, h1); c0 = div_step(h1, hh0); den = hh0 - h1;
 		}
-		const double rden = 1. / den;
+		const double rden = div_step(1., den);
 		// the matrix I + g.h * A is constant in time: factorise when the step changes
 		if(kind != cur_kind || fabs(g.h - cur_h) > 1e-11 * cur_h) {
 			cur_kind = kind; cur_h = g.h;

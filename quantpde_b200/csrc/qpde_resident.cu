@@ -339,10 +339,10 @@ k_resident_sweep(DeviceBatch b, DeviceResult out) {
 		double c1 = 0., c0 = 0., den = 1.;
 		if(BDF2 && kind == STEP_BDF2) {
 			const double h1 = rp.lapse(time1, t), hh0 = rp.lapse(time0, t);      // BDF.hpp:68-73
-			g.h = (hh0 * h1) / (hh0 + h1);
-			c1 = hh0 / h1; c0 = h1 / hh0; den = hh0 - h1;
+			g.h = div_step(hh0 * h1, hh0 + h1);
+			c1 = div_step(hh0, h1); c0 = div_step(h1, hh0); den = hh0 - h1;
 		}
-		const double rden = 1. / den;
+		const double rden = div_step(1., den);
 		// (Re)build the system rows when the step kind or size changes.  h0 is a
 		// difference of accumulated times and moves in its last bits from step
 		// to step (by ulp(t) / dt, ~1e-13 relative); moves below 1e-11 relative
