@@ -196,7 +196,8 @@ __device__ __forceinline__ double interp_apply(double w, double v0, double v1) {
 
 } // namespace
 
-template <int M, int PT, bool BDF2>
+// GT: forward-time sweeps (the common reverse sweep compiles the direction in, see ReplayT)
+template <int M, int PT, bool BDF2, bool GT>
 __global__ void __launch_bounds__(PT, 1)
 k_jump_sweep(DeviceBatch b, JumpWork work, DeviceResult out) {
 	constexpr int P = PT;
@@ -328,7 +329,7 @@ k_jump_sweep(DeviceBatch b, JumpWork work, DeviceResult out) {
 	x_next = 0.;
 	__syncthreads();
 
-	Replay rp; rp.start(b.T[cidx], b.dt[cidx], 0, b.forward);
+	ReplayT<GT> rp; rp.start(b.T[cidx], b.dt[cidx], 0, b.forward);
 	NodeState ns; ns.start(b.scheme);
 	double time1 = rp.initial(), time0 = rp.initial();
 	int cur_kind = -1; double cur_h = 0.;
@@ -499,7 +500,7 @@ bool jump_supported(const DeviceBatch &b) {
 
 template <int M, int PT, bool BDF2>
 static int launch_jump_variant(const DeviceBatch &b, const JumpWork &w, const DeviceResult &out, cudaStream_t stream) {
-	auto kern = k_jump_sweep<M, PT, BDF2>;
+	auto kern = b.forward ? k_jump_sweep<M, PT, BDF2, true> : k_jump_sweep<M, PT, BDF2, false>;
 	const size_t bytes = jump_smem_bytes(M, PT, b.n_fft);
 	if(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes) != cudaSuccess) {
 		return QPDE_ERR_CUDA;
