@@ -112,7 +112,7 @@ enum { EXTRA_NONE = 0, EXTRA_EVENTS = 1, EXTRA_VARIABLE = 2 };
 // CL: CTAs per contract.  CL = 2 is a thread-block cluster: the two CTAs hold the lower and the
 // upper half of the rows (N up to 2 PT M + 1 = 4097), exchange the row at their boundary and the
 // warps' separator data through distributed shared memory, and every barrier is the cluster's.
-// GT ("general time"): forward-time sweeps, explicit event times, an operator source b(t).  The common
+// GT ("general time"): forward-time sweeps, explicit event times, an operator source b(t), event programs.  The common
 // sweep (GT = false, qpde_resident.cu) compiles them out of its time loop; qpde_resident_gt.cu holds the
 // GT = true instantiations.
 template <int M, int PT, int MODE, bool BDF2, int EXTRA, int CL, bool GT>
@@ -600,7 +600,7 @@ k_resident_sweep(DeviceBatch b, DeviceResult out) {
 				for(int ue = 0; ue < st.user_events; ++ue) {
 					for(int op = 0; op < 2; ++op) {
 						const bool is_dividend = (op == 0) == (b.dividend_first != 0);
-						const bool program = op == 0 && b.event_program != nullptr;            // a general Event<1> transform
+						const bool program = GT && op == 0 && b.event_program != nullptr;            // a general Event<1> transform
 						if(CL == 1 && ((is_dividend && b.dividend_kind != QPDE_DIVIDEND_NONE) || program)) {   // reads any node: one CTA only
 							// Event<1>::_doEvent with V(max(S - D, 0)) or V((1 - D) S): the solution goes to
 							// shared memory (sm_lb is free between steps), every node reads its two
@@ -851,7 +851,7 @@ int launch_resident(const DeviceBatch &b, const DeviceResult &out, cudaStream_t 
 	int M = 0, PT = 0, CL = 1;
 	if(!resident_supported(b) || !pick_geometry(b.N, &M, &PT, &CL)) return QPDE_ERR_UNSUPPORTED;
 	if(lean_supported(b)) return launch_lean(b, out, stream, launches);      // two contracts per SM (qpde_lean.cu)
-	const bool general_time = b.forward || b.event_times || b.source_table;
+	const bool general_time = b.forward || b.event_times || b.source_table || b.event_program;   // (event programs ride along: their interpreter stays out of the common kernel's code)
 	const int rc = general_time ? launch_resident_general_time(b, out, stream, M, PT, CL)
 	                            : launch_resident_common_time(b, out, stream, M, PT, CL);
 	if(rc == QPDE_OK) *launches += 1;
