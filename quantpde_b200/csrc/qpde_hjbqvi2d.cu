@@ -22,6 +22,8 @@
 //     k_rhs    one thread per node: right-hand side with the off-line entries from the last sweep
 //     k_lines  one warp per w-line: forward / back substitution with the cached factors, both first-order
 //              linear recurrences, as warp scans over tiles of 32 rows (composition of affine maps)
+//     (folding k_rhs into k_lines — one launch per sweep — was slower: 1.7 -> 2.3 s at 153 x 153 nodes; the
+//     gathers of the right-hand side want one thread per node, not one warp per line walking its tiles)
 //   Every sweep is parallel over all lines (a sequential symmetric line Gauss-Seidel on the CPU needs as
 //   many line solves: measured 105 / 128 / 154 Jacobi sweeps per solve at refinements 0 / 1 / 2 against
 //   47 / 54 / 65 symmetric Gauss-Seidel sweeps of two passes each).  The reference drives BiCGSTAB +
@@ -65,18 +67,19 @@ struct Rows2 {
 	unsigned char *active;
 };
 
-__device__ __forceinline__ void interp_dev(const double *x, int length, double ci, int &idx, double &w) {
+// linearInterpolationData (Core/Interpolant.hpp:153-181): the bracket x[idx] <= ci < x[idx + 1] is unique, so it is
+// found from a guess on the mean spacing and a short walk instead of a bisection (the axes of this model are
+// refined uniform axes: the guess is right or one off; any strictly increasing axis still ends at the same bracket
+// and the same weight).  ncu: the bisections were 45 % of k_policy's stall samples.
+__device__ __forceinline__ void interp_dev(const double *x, int length, double inv_mean, double ci, int &idx, double &w) {
 	if(ci <= x[0]) { idx = 0; w = 1.; return; }
 	if(ci >= x[length - 1]) { idx = length - 2; w = 0.; return; }
-	int lo = 0, hi = length - 2, mid = 0;
-	w = 0.;
-	while(lo <= hi) {
-		mid = (lo + hi) / 2;
-		if(ci < x[mid]) hi = mid - 1;
-		else if(ci >= x[mid + 1]) lo = mid + 1;
-		else { w = (x[mid + 1] - ci) / (x[mid + 1] - x[mid]); break; }
-	}
-	idx = mid;
+	int i = (int)((ci - x[0]) * inv_mean);
+	i = i < 0 ? 0 : (i > length - 2 ? length - 2 : i);
+	while(x[i] > ci) --i;                 // terminates: x[0] < ci
+	while(x[i + 1] <= ci) ++i;            // terminates: ci < x[length - 1]
+	idx = i;
+	w = (x[i + 1] - ci) / (x[i + 1] - x[i]);
 }
 
 // one dimension of the stencil (HJBQVI.hpp:224-274)
@@ -109,14 +112,14 @@ __device__ __forceinline__ double impulse_lhs(const Imp4 &m, int row, const doub
 	return acc;
 }
 
-__device__ __forceinline__ Imp4 impulse_of(const Model2 &md, const Grid2 &g, const double *sW, const double *sB, double w, double b,
-		double lo, double hi, double z_frac, double &reward) {
+__device__ __forceinline__ Imp4 impulse_of(const Model2 &md, const Grid2 &g, const double *sW, const double *sB, double invW, double invB,
+		double w, double b, double lo, double hi, double z_frac, double &reward) {
 	double z = z_frac * (hi - lo) + lo;                         // z_bounded, optimal_consumption.cpp:85-99
 	if(fabs(z) < DBL_EPSILON) z = 0.;
 	const double w_plus = w + z, b_plus = b - z - md.lambda * fabs(z) - md.c;
 	int i0, i1; double f0, f1;
-	interp_dev(sW, g.nw, w_plus, i0, f0);
-	interp_dev(sB, g.nb, b_plus, i1, f1);
+	interp_dev(sW, g.nw, invW, w_plus, i0, f0);
+	interp_dev(sB, g.nb, invB, b_plus, i1, f1);
 	Imp4 m;
 	m.t[0] = i0 + g.nw * i1;           m.f[0] = 1. * f0 * f1;
 	m.t[1] = i0 + 1 + g.nw * i1;       m.f[1] = 1. * (-f0 + 1.) * f1;
@@ -140,6 +143,7 @@ k_policy(Model2 md, Grid2 g, Rows2 R, const double *xprev, const double *v0, dou
 	const int ib = s / nw, iw = s % nw;
 	const int row = s;
 	const double w = sW[iw], b = sB[ib];
+	const double invW = (double)(nw - 1) / (sW[nw - 1] - sW[0]), invB = (double)(nb - 1) / (sB[nb - 1] - sB[0]);
 	const bool inside = 0 < b && b < md.boundary;
 	const bool wint = iw > 0 && iw < nw - 1, bint = ib > 0 && ib < nb - 1;
 	const double xc = xprev[s];
@@ -173,14 +177,14 @@ k_policy(Model2 md, Grid2 g, Rows2 R, const double *xprev, const double *v0, dou
 	double zbest = 0.;
 	for(int k = 0; k < g.nz; ++k) {
 		double rew;
-		const Imp4 m = impulse_of(md, g, sW, sB, w, b, lo, hi, g.zfrac[k], rew);
+		const Imp4 m = impulse_of(md, g, sW, sB, invW, invB, w, b, lo, hi, g.zfrac[k], rew);
 		if(rew != 0.) continue;                                      // -inf: the impulse does not move the state
 		const double cand = impulse_lhs(m, row, xprev, nw, nb) - rew;
 		if(cand < best) { best = cand; zbest = g.zfrac[k]; }
 	}
 	// a node without an admissible candidate keeps the control of a zero-filled vector
 	double rew;
-	const Imp4 m = impulse_of(md, g, sW, sB, w, b, lo, hi, zbest, rew);
+	const Imp4 m = impulse_of(md, g, sW, sB, invW, invB, w, b, lo, hi, zbest, rew);
 	// 3. penalty (PenaltyMethod.hpp:45-68)
 	const bool act = (pen * (impulse_lhs(m, row, xprev, nw, nb) - rew)) < 0.;
 	// 4. the row, split
