@@ -848,7 +848,10 @@ int qpo_sweep_1d(const qpo_problem *p, double *V, int *inner,
 			 * A is I + hA * bs.A(control), b is the BDF right-hand side.  The
 			 * discretisation node's isATheSame() is false because its operator
 			 * (the policy node) keeps LinearSystem's default. */
-			if(use_cn) { status = 2; break; }   /* not restated: theta schemes re-evaluate A(t0) */
+			/* Under the theta schemes the explicit half is the policy node's A as well: Rannacher::_b2 /
+			 * CrankNicolson::b call system.A(t0) (Rannacher.hpp:60-73, CrankNicolson.hpp:64-78), and
+			 * PolicyIteration::A hands back the controlled operator under the controls of the CURRENT inner
+			 * iteration — so the right-hand side is re-formed with every control update. */
 			memcpy(x, v1, sizeof(double) * (size_t)n);
 			do {
 				memcpy(xprev, x, sizeof(double) * (size_t)n);
@@ -873,7 +876,25 @@ int qpo_sweep_1d(const qpo_problem *p, double *V, int *inner,
 						const double d = p->pdi[(size_t)best_k * n + i];
 						const double u = p->pup[(size_t)best_k * n + i];
 						if(use_bdf2 || use_bdfk) { A_lo[i] = hA * l; A_di[i] = 1. + hA * d; A_up[i] = hA * u; }
+						else if(use_cn == 1) { A_lo[i] = l * hA / 2.; A_di[i] = 1. + d * hA / 2.; A_up[i] = u * hA / 2.; }
+						else if(use_cn == 2) { A_lo[i] = l * 0.5 * hA; A_di[i] = 1. + d * 0.5 * hA; A_up[i] = u * 0.5 * hA; }
 						else         { A_lo[i] = l * hA; A_di[i] = 1. + d * hA; A_up[i] = u * hA; }
+						if(use_cn) {
+							/* row i of (I - (1 - theta) h A(q*)) V^n, SpMV in column order (the rows of A(q*) carry the
+							 * control of their own node) */
+							double acc = 0.;
+							if(use_cn == 1) {
+								if(i > 0) acc += (0. - l * hA / 2.) * v1[i - 1];
+								acc += (1. - d * hA / 2.) * v1[i];
+								if(i < n - 1) acc += (0. - u * hA / 2.) * v1[i + 1];
+								lb[i] = acc + (bj[i] + bj[i]) / 2.;
+							} else {
+								if(i > 0) acc += (0. - l * (1 - 0.5) * hA) * v1[i - 1];
+								acc += (1. - d * (1 - 0.5) * hA) * v1[i];
+								if(i < n - 1) acc += (0. - u * (1 - 0.5) * hA) * v1[i + 1];
+								lb[i] = acc + (0.5 * bj[i] + (1 - 0.5) * bj[i]);
+							}
+						}
 					}
 				}
 				memcpy(x, lb, sizeof(double) * (size_t)n);

@@ -567,6 +567,8 @@ int runHjb(const Args &a) {
 		else if(scheme == "bdf4") discretization.reset(new ReverseBDFFour(grid, *policy));
 		else if(scheme == "bdf5") discretization.reset(new ReverseBDFFive(grid, *policy));
 		else if(scheme == "bdf6") discretization.reset(new ReverseBDFSix(grid, *policy));
+		else if(scheme == "rannacher") discretization.reset(new ReverseRannacher(grid, *policy));
+		else if(scheme == "cn")   discretization.reset(new ReverseCrankNicolson(grid, *policy));
 		else                      discretization.reset(new ReverseBDFOne(grid, *policy));
 		discretization->setIteration(stepper);
 

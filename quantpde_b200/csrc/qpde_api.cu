@@ -402,9 +402,6 @@ static int plan_create_impl(qpde_handle *h, const qpde_bs1d_batch *in,
 		if(!in->controls) return fail(h, QPDE_ERR_INVALID, "controls required");
 		if(in->controls_stride != 0 && in->controls_stride < in->n_controls) return fail(h, QPDE_ERR_INVALID, "controls_stride < n_controls");
 		if(in->american || in->n_exercise > 0) return fail(h, QPDE_ERR_UNSUPPORTED, "policy iteration with a penalty constraint or events is not supported");
-		if(bdf_order(in->scheme) == 0) {
-			return fail(h, QPDE_ERR_UNSUPPORTED, "policy iteration needs a BDF scheme (theta schemes re-evaluate A(t0) under the current control)");
-		}
 		if(!(in->tolerance > 0.) || !(in->scale > 0.) || in->max_inner < 1) {
 			return fail(h, QPDE_ERR_INVALID, "policy iteration: tolerance, scale > 0 and max_inner >= 1 required");
 		}
@@ -636,7 +633,8 @@ static int plan_create_impl(qpde_handle *h, const qpde_bs1d_batch *in,
 		w.ld = ((long long)C + 31) / 32 * 32;                 // a warp of contracts per 256-byte row segment
 		const size_t NC = (size_t)N * (size_t)w.ld;
 		const size_t sets = b.n_controls > 0 ? (size_t)b.n_controls : 1;   // operator rows per control value
-		const bool need_xprev = bdf_order(b.scheme) >= 2 || b.variable_target;
+		// (policy iteration under a theta scheme re-forms the right-hand side from V^n at every control update)
+		const bool need_xprev = bdf_order(b.scheme) >= 2 || b.variable_target || (b.n_controls > 0 && bdf_order(b.scheme) == 0);
 		const size_t hist_slots = bdf_order(b.scheme) > 2 ? (size_t)bdf_order(b.scheme) - 1 : 1;   // iterand(1) .. iterand(order - 1)
 		const bool need_evobst = b.n_exercise > 0 && b.exercise_kind != QPDE_EXERCISE_NONE;
 		p->tma.enabled = false;

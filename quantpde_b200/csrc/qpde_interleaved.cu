@@ -225,7 +225,12 @@ k_interleaved_sweep(DeviceBatch b, InterleavedWork w, DeviceResult out) {
 		}
 		// history push: iterand(1) <- iterand(0).  For BDF2 the previous
 		// iterand must survive the solve, so copy it before x is overwritten.
-		if(order >= 2 || variable) {   // the variable stepper needs V^n after the solve, too
+		// Policy iteration under a theta scheme: Rannacher::_b2 / CrankNicolson::b form (I - (1 - theta) h A(t0)) V^n with
+		// the policy node's A, i.e. under the controls of the CURRENT inner iteration (Rannacher.hpp:60-73,
+		// CrankNicolson.hpp:64-78, PolicyIteration.hpp:107-115): the right-hand side is re-formed from V^n at every
+		// control update, so V^n must survive the solves.
+		const bool policy_theta = policy && (kind == STEP_CN_R || kind == STEP_CN_T);
+		if(order >= 2 || variable || policy_theta) {   // the variable stepper needs V^n after the solve, too
 			head = head == 0 ? slots - 1 : head - 1;    // the oldest slot becomes iterand(1)
 			it1 = xp + (size_t)head * NC;
 			for(int i = 0; i < N; ++i) it1[(size_t)i * C] = x[(size_t)i * C];
@@ -293,6 +298,15 @@ k_interleaved_sweep(DeviceBatch b, InterleavedWork w, DeviceResult out) {
 					double b_i = 1. + gA.off(di[rows]);
 					double c_i = gA.off(up[rows]);
 					double rhs = lb[at];
+					if(policy_theta) {
+						// row i of (I - (1 - theta) h A(q*)) V^n, SpMV from zero in column order; the row of A(q*)
+						// carries the control chosen at its own node
+						double acc = 0.;
+						if(i > 0) acc += (0. - gb.off(lo[rows])) * it1[at - C];
+						acc += (1. - gb.off(di[rows])) * it1[at];
+						if(i < N - 1) acc += (0. - gb.off(up[rows])) * it1[at + C];
+						rhs = acc + 0.;
+					}
 					if(b.american) {
 						// PenaltyMethod.hpp:45,61-68: predicate on the previous iterand
 						// (scale * (x - payoff)) < 0  <=>  x < payoff

@@ -769,6 +769,7 @@ bool resident_supported(const DeviceBatch &b) {
 	if(CL > 1 && (b.variable_target || b.dividend_kind != QPDE_DIVIDEND_NONE || b.event_program)) return false; // one-CTA features
 	if(b.american && b.n_exercise > 0 && (CL > 1 || (M == 4 && PT == 512))) return false; // penalty + events: one CTA per contract, the default geometries
 	if(b.n_controls != 0 && b.n_controls != 2) return false; // more control values: INTERLEAVED family
+	if(b.n_controls != 0 && bdf_order(b.scheme) == 0) return false; // policy iteration under a theta scheme (the right-hand side follows the controls): INTERLEAVED family
 	if(b.variable_target && !((M == 8 && PT == 32) || (M == 8 && PT == 64) || (M == 8 && PT == 256))) return false; // no room for V^n: INTERLEAVED family
 	return true;
 }

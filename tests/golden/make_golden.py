@@ -111,6 +111,12 @@ CASES.append(("dividend_cash_bdf4_k1", "bermudan",
 
 CASES.append(("hjb_short_bdf4_k2", "hjb",
               dict(steps=48, refine=2, long=0, scheme="bdf4", K=100.0, r_l=0.03, r_b=0.05, vol=0.3, T=1.0)))
+# policy iteration under the theta schemes: the explicit half follows the controls of the running inner iteration
+# (Rannacher.hpp:60-73 / CrankNicolson.hpp:64-78 call the policy node's A(t0))
+for lp, k in ((0, 1), (1, 2)):
+    for sch in ("rannacher", "cn"):
+        CASES.append(("hjb_%s_%s_k%d" % ("long" if lp else "short", sch, k), "hjb",
+                      dict(steps=12 * 2 ** k, refine=k, long=lp, scheme=sch, K=100.0, r_l=0.03, r_b=0.05, vol=0.3, T=1.0)))
 CASES.append(("variable_american_bdf4", "vanilla",
               dict(american=1, steps=40, refine=2, variable_target=0.3, scheme="bdf4", K=100.0, r=0.04, vol=0.2, T=1.0)))
 

@@ -264,3 +264,25 @@ def test_invalid_arguments(qpde, handle):
     spec.struct.abi_version = 99
     with pytest.raises(qpde.QpdeError):
         qpde.Plan(handle, spec)
+
+
+def test_policy_iteration_under_theta_schemes(qpde, handle, oracle, golden):
+    """PolicyIteration under ReverseRannacher / ReverseCrankNicolson: the explicit half of the step is the policy
+    node's A(t0) under the controls of the running inner iteration (Rannacher.hpp:60-73, CrankNicolson.hpp:64-78,
+    PolicyIteration.hpp:107-115), so the right-hand side follows every control update.  INTERLEAVED family (AUTO
+    falls to it); the four fixtures are the reference's own outputs, per-step inner iteration counts included."""
+    names = ["hjb_short_rannacher_k1", "hjb_short_cn_k1", "hjb_long_rannacher_k2", "hjb_long_cn_k2"]
+    for name in names:
+        mode, kw = case_args(golden, name)
+        for kernel in ("interleaved", "auto"):
+            spec = spec_for_case(qpde, oracle, mode, kw, kernel=kernel, copies=2)
+            with qpde.Plan(handle, spec) as plan:
+                assert plan.kernel == "interleaved"
+                plan.run()
+                res = plan.fetch()
+            n = res.n_steps[0]
+            assert n == int(golden[name + "/steps"]) and res.status[0] == 0, name
+            assert rel_err(res.V[0], golden[name + "/V"]).max() <= REL_TOL, name
+            assert np.array_equal(res.inner[0, :n], golden[name + "/inner"]), name
+        with pytest.raises(qpde.QpdeError):
+            qpde.Plan(handle, spec_for_case(qpde, oracle, mode, kw, kernel="resident", copies=1))
