@@ -402,10 +402,11 @@ class Hjbqvi2d(C.Structure):
 
 
 def optimal_consumption(refine_times=0, timesteps=32, control_points=16, spatial_points=20, T=40., rho=.1, r=.07, mu=.11,
-                        sigma=.3, gamma=.3, lam=.1, c=.05, q_max=100., boundary=200., max_inner=1000, max_sweeps=5000):
+                        sigma=.3, gamma=.3, lam=.1, c=.05, q_max=100., boundary=200., max_inner=1000, max_sweeps=5000,
+                        spatial_points_b=None):
     """The examples/hjbqvi/optimal_consumption.cpp wiring on the oracle."""
     W = refine(uniform_axis(0., boundary, spatial_points), refine_times)
-    B = W.copy()
+    B = W.copy() if spatial_points_b is None else refine(uniform_axis(0., boundary, spatial_points_b), refine_times)
     q = refine(uniform_axis(0., q_max, control_points), refine_times)
     z = refine(uniform_axis(0., 1., control_points), refine_times)
     p = Hjbqvi2d()

@@ -478,18 +478,19 @@ def exchange_rate_solve(handle, x_axis, q_axis, z_axis, params, refine, timestep
 
 def optimal_consumption_solve(handle, refine, timesteps=32, control_points=16, spatial_points=20, T=40., rho=.1, r=.07, mu=.11,
                               sigma=.3, gamma=.3, lam=.1, c=.05, q_max=100., boundary=200., scaling_factor=1e-2,
-                              tolerance=1e-6, max_inner=200, max_sweeps=20000):
+                              tolerance=1e-6, max_inner=200, max_sweeps=20000, spatial_points_b=None):
     """qpde_hjbqvi2d_solve for the model of examples/hjbqvi/optimal_consumption.cpp; `timesteps` is the count at
     refinement 0 (doubled per level, as HJBQVI::solve does).  Host arrays out."""
     def uniform(begin, end, points):
         dx = (end - begin) / (points - 1)                       # Axis::uniform, Core/Axis.hpp:219-226
         return np.array([begin + dx * i for i in range(points)])
     axis = uniform(0., boundary, spatial_points)
+    axis_b = axis if spatial_points_b is None else uniform(0., boundary, spatial_points_b)
     qa, za = uniform(0., q_max, control_points), uniform(0., 1., control_points)
     par = np.array([rho, r, mu, sigma, gamma, lam, c, boundary])
     g = Hjbqvi2d()
     g.abi_version, g.model, g.refine, g.n_params = ABI_VERSION, HJBQVI2D_OPTIMAL_CONSUMPTION, int(refine), len(par)
-    g.w_axis, g.n_w_axis, g.b_axis, g.n_b_axis = axis.ctypes.data_as(_dp), len(axis), axis.ctypes.data_as(_dp), len(axis)
+    g.w_axis, g.n_w_axis, g.b_axis, g.n_b_axis = axis.ctypes.data_as(_dp), len(axis), axis_b.ctypes.data_as(_dp), len(axis_b)
     g.control_axis, g.n_control_axis = qa.ctypes.data_as(_dp), len(qa)
     g.impulse_axis, g.n_impulse_axis = za.ctypes.data_as(_dp), len(za)
     g.params = par.ctypes.data_as(_dp)

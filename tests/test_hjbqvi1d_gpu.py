@@ -138,3 +138,25 @@ def test_exchange_rate_edge_parameters_against_oracle(qpde, handle, oracle):
     err = np.abs(one["V"][0] - o["V"]) / np.maximum(1., np.abs(o["V"]))
     assert one["status"][0] == 0 and err.max() <= REL_TOL and one["mean_inner"][0] == o["mean_inner"]
     assert one["n_controls"] == 1 and one["n_impulses"] == 1
+
+
+@pytest.mark.parametrize("nodes", [5, 33, 512, 513, 768, 769, 1280, 2048, 2049, 2304])
+def test_exchange_rate_grid_sizes_at_the_geometry_boundaries(qpde, handle, oracle, nodes):
+    """Every rows-per-thread geometry (2, 3, 5, 8, 9 rows x 256 threads) with and without padding rows, down to a
+    5-node grid, against the oracle: uniform axes, 4 time steps."""
+    X0 = np.linspace(-2., 2., nodes)
+    Q0 = np.linspace(-.07, .07, 3)
+    Z0 = np.linspace(-1.5, 1.5, 7)
+    res = qpde.exchange_rate_solve(handle, X0, Q0, Z0, [_params({}), _params(dict(c=.02, lam=.3))], 0, 4)
+    for p, kw in enumerate((dict(), dict(c=.02, lam=.3))):
+        o = oracle.exchange_rate(X0, Q0, Z0, refine_times=0, timesteps=4, **kw)
+        assert res["status"][p] == 0 and o["status"] == 0
+        err = np.abs(res["V"][p] - o["V"]) / np.maximum(1., np.abs(o["V"]))
+        assert err.max() <= REL_TOL, "%d nodes: %.3e" % (nodes, err.max())
+        assert res["mean_inner"][p] == o["mean_inner"]
+        assert np.array_equal(res["mask"][p], o["mask"])
+
+
+def test_exchange_rate_rejects_grids_beyond_the_largest_geometry(qpde, handle):
+    with pytest.raises(qpde.QpdeError):
+        qpde.exchange_rate_solve(handle, np.linspace(-2., 2., 2305), [0.], [0.], [_params({})], 0, 4)

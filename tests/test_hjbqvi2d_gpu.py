@@ -87,3 +87,16 @@ def test_example_program_reproduces_the_reference_programs_table():
         assert gf[8] == wf[8] or abs(float(gf[8]) - float(wf[8])) <= 2e-11 * abs(float(wf[8])), (g, w)   # value: 12th digit
         for a, b in zip(gf[9:11], wf[9:11]):
             assert a == b or abs(float(a) - float(b)) <= 2e-6 * abs(float(b)), (g, w)
+
+
+@pytest.mark.parametrize("nw,nb,refine", [(20, 9, 0), (9, 20, 1), (33, 12, 0), (12, 17, 2)])
+def test_optimal_consumption_rectangular_grids_against_oracle(qpde, handle, oracle, nw, nb, refine):
+    """Grids that are not square and lines that are not a multiple of the 32-row scan tile, against the oracle."""
+    kw = dict(spatial_points=nw, spatial_points_b=nb, control_points=5, timesteps=4)
+    res = qpde.optimal_consumption_solve(handle, refine, **kw)
+    o = oracle.optimal_consumption(refine_times=refine, **kw)
+    assert res["status"] == 0 and o["status"] == 0 and res["V"].shape == o["V"].shape
+    err = np.abs(res["V"] - o["V"]) / np.maximum(1., np.abs(o["V"]))
+    assert err.max() <= REL_TOL, "%.3e" % err.max()
+    assert res["mean_inner"] == o["mean_inner"]
+    assert np.array_equal(res["mask"], o["mask"])
