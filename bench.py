@@ -1090,10 +1090,11 @@ def main():
                          "achieved": s_alg / (s_ms / 1e3) / 1e9, "peak": speak, "unit": "GB/s",
                          "frac": s_alg / (s_ms / 1e3) / 1e9 / speak,
                          "not_converged": int((sres.status != 0).sum()),
-                         "note": "achieved = 56 B x nodes x inner solves / time (SURVEY.md 8d); the kernel itself moves "
-                                 "104 B per computed inner solve and node (DESIGN.md 4.1); ncu capture of the same "
-                                 "batch at 20 steps: 6.10 TB/s of DRAM traffic = 93 % of the measured peak "
-                                 "(profiles/r1_interleaved_tma_ncu_raw_subset.csv)"}
+                         "note": "achieved = 56 B x nodes x inner solves / time (SURVEY.md 8d); the kernel itself moves up "
+                                 "to 104 B per computed inner solve and node, less where a further penalty iteration restarts "
+                                 "at the first changed row and on zero-obstacle tiles (DESIGN.md 4.1); ncu capture of the same "
+                                 "batch at 20 steps: 3.94 TB of DRAM traffic per launch (round 1: 4.85 TB) at 6.20 TB/s = 95 % "
+                                 "of the measured peak (profiles/r2_interleaved_tma_ncu_raw_subset.csv)"}
 
     peak, peak_src = load_peaks()
     alg_bytes = ALG_BYTES_PER_NODE_SOLVE * N * (inner_sum_all / world)   # per launch (one rank's batch)
