@@ -60,10 +60,12 @@ struct Hjbqvi1dSmem {
 };
 
 // shared memory: 7 row arrays + the control grids and the per-candidate tables (doubles), then two int arrays
-// (M < 9: three more row arrays and a byte per row for the hand-over of the balanced search, see the kernel)
+// 8 row arrays of doubles (grid, iterate, flow, reward and weight of the chosen controls, the hand-over of the
+// assembled rows), the control grids and per-candidate tables, two int arrays, two u16 arrays (the chosen
+// controls as grid indices), one byte array (flags)
 __host__ __device__ inline size_t hjbqvi1d_smem_bytes(int M, int nq, int nz) {
-	return ((sizeof(Hjbqvi1dSmem) + 15) / 16) * 16 + sizeof(double) * ((size_t)(M < 9 ? 10 : 7) * M * HP + nq + 5 * (size_t)nz)
-		+ sizeof(int) * ((size_t)M * HP + nz) + (M < 9 ? (size_t)M * HP : 0);
+	return ((sizeof(Hjbqvi1dSmem) + 15) / 16) * 16 + sizeof(double) * ((size_t)8 * M * HP + nq + 5 * (size_t)nz)
+		+ sizeof(int) * ((size_t)M * HP + nz) + sizeof(unsigned short) * 2 * (size_t)M * HP + (size_t)M * HP;
 }
 
 // linearInterpolationData (Core/Interpolant.hpp:153-181) over a node-addressable grid
@@ -101,28 +103,27 @@ k_hjbqvi1d(Hjbqvi1dBatch b, Hjbqvi1dResult out) {
 	Hjbqvi1dSmem &sm = *reinterpret_cast<Hjbqvi1dSmem *>(smem_raw);
 	double *const sX = reinterpret_cast<double *>(smem_raw + ((sizeof(Hjbqvi1dSmem) + 15) / 16) * 16);   // grid, node-addressable (slot<M>())
 	double *const sx = sX + HMP;          // current iterate, node-addressable
-	double *const r_b = sx + HMP;         // [j][tid]: the flow b^q* of the chosen stochastic control ...
-	double *const r_q = r_b + HMP;        // ... and the control itself
-	double *const i_z = r_q + HMP;        // the chosen impulse control, its reward and interpolation weight
-	double *const i_rew = i_z + HMP;
+	double *const r_b = sx + HMP;         // [j][tid]: the flow b^q* of the chosen stochastic control
+	double *const i_rew = r_b + HMP;      // reward and interpolation weight of the chosen impulse control
 	double *const i_w = i_rew + HMP;
-	double *const sq = i_w + HMP;         // stochastic control grid [nq]
+	// The searches run node-strided (thread t takes the nodes t, t + 256, ...), so that every warp gets near and
+	// far nodes alike — the admissible impulse candidates of a node grow with its distance from the parity, and with
+	// the solver's contiguous rows per thread the warps at the ends of the grid searched while the central ones sat
+	// at the solver's barrier (ncu: 32 % of the stall samples).  The rows then reach their owners through shared memory.
+	double *const h_a = i_w + HMP;        // hand-over of the assembled rows
+	double *const h_b = h_a + HMP;
+	double *const h_c = h_b + HMP;
+	double *const sq = h_c + HMP;         // stochastic control grid [nq]
 	double *const sz = sq + b.nq;         // impulse control grid [nz], its distance to the parity, weight of the target,
 	double *const sdz = sz + b.nz;        // A_k, B_k (impulse_lhs)
 	double *const z_w = sdz + b.nz;
 	double *const sA = z_w + b.nz;
 	double *const sB = sA + b.nz;
-	// BAL: the searches run node-strided (thread t takes the nodes t, t + 256, ...), so that every warp gets near and
-	// far nodes alike — the admissible impulse candidates of a node grow with its distance from the parity, and with
-	// the solver's contiguous rows per thread the warps at the ends of the grid searched while the central ones sat
-	// at the solver's barrier (ncu: 32 % of the stall samples).  The rows then reach their owners through shared memory.
-	constexpr bool BAL = M < 9;
-	double *const h_a = sB + b.nz;        // BAL: hand-over of the assembled rows
-	double *const h_b = h_a + (BAL ? HMP : 0);
-	double *const h_c = h_b + (BAL ? HMP : 0);
-	int *const i_k = reinterpret_cast<int *>(h_c + (BAL ? HMP : 0));   // [j][tid]: lower interpolation node of the chosen impulse target
+	int *const i_k = reinterpret_cast<int *>(sB + b.nz);   // [j][tid]: lower interpolation node of the chosen impulse target
 	int *const z_idx = i_k + HMP;         // [nz]: lower interpolation node of candidate k's target
-	unsigned char *const h_f = reinterpret_cast<unsigned char *>(z_idx + b.nz);   // BAL: bit 0 active, bits 1-2 far entries
+	unsigned short *const q_k = reinterpret_cast<unsigned short *>(z_idx + b.nz);   // [j][tid]: chosen stochastic control (index into sq)
+	unsigned short *const z_k = q_k + HMP;                                          // chosen impulse control: index into sz + 1, 0 = none
+	unsigned char *const h_f = reinterpret_cast<unsigned char *>(z_k + HMP);        // bit 0 active, bits 1-2 far entries
 
 	const int pidx = blockIdx.x;
 	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -180,14 +181,10 @@ k_hjbqvi1d(Hjbqvi1dBatch b, Hjbqvi1dResult out) {
 			double aa[HM], bb[HM], cc[HM];
 #pragma unroll
 			for(int j = 0; j < HM; ++j) {
-				const int i = BAL ? j * HP + tid : i0 + j;              // the node this thread searches
-				const int at = BAL ? slot<M>(i) : j * HP + tid;         // its place in the [row][thread] arrays
-				if(i >= N) {
-					if(BAL) { if(i < HMP) { h_a[at] = 0.; h_b[at] = 1.; h_c[at] = 0.; h_f[at] = 0; } }
-					else { aa[j] = 0.; bb[j] = 1.; cc[j] = 0.; }
-					continue;
-				}
-				const double xi = sX[at], vi = BAL ? sx[at] : xprev[j];
+				const int i = j * HP + tid;                 // the node this thread searches
+				const int at = slot<M>(i);                  // its place in the [row][thread] arrays
+				if(i >= N) { h_a[at] = 0.; h_b[at] = 1.; h_c[at] = 0.; h_f[at] = 0; continue; }
+				const double xi = sX[at], vi = sx[at];
 				const bool interior = i > 0 && i < N - 1;
 				// 1. stochastic policy: argmin_q (A(q) x - b(q))_i, strict < (PolicyIteration.hpp:88-96)
 				double dxb = 1., dxc = 1., dxf = 1., alpha_common = 0., beta_common = 0., vm = 0., vp = 0.;
@@ -218,6 +215,7 @@ k_hjbqvi1d(Hjbqvi1dBatch b, Hjbqvi1dResult out) {
 					di = total + rho;
 				};
 				double best = CUDART_INF, bfl = 0., bq = 0.;
+				int bqk = 0;
 				for(int k = 0; k < nq; ++k) {
 					const double q = sq[k];
 					double lo, up, di;
@@ -228,11 +226,11 @@ k_hjbqvi1d(Hjbqvi1dBatch b, Hjbqvi1dResult out) {
 					acc += di * vi;
 					if(interior) acc += up * vp;
 					const double cand = acc - fl;
-					if(cand < best) { best = cand; bfl = fl; bq = q; }
+					if(cand < best) { best = cand; bfl = fl; bq = q; bqk = k; }
 				}
 				double blo, bup, bdi;
 				row_of(bq, true, blo, bup, bdi);
-				r_b[at] = bfl; r_q[at] = bq;
+				r_b[at] = bfl; q_k[at] = (unsigned short)bqk;
 				// 2. impulse policy: argmin_z ((I - M_z) x - reward_z)_i, strict <; pruned candidates are +inf
 				best = CUDART_INF;
 				int bk = -1;
@@ -252,7 +250,7 @@ k_hjbqvi1d(Hjbqvi1dBatch b, Hjbqvi1dResult out) {
 				const double lhs = impulse_lhs(i, isel, wsel, vi, (0. - wsel) * sx[slot<M>(isel)], (0. - (-wsel + 1.)) * sx[slot<M>(isel + 1)]);
 				// 3. penalty: active iff scale * ((I - M*) x - reward*) < 0 (PenaltyMethod.hpp:45-68)
 				const bool act = (pen * (lhs - rew)) < 0.;
-				i_k[at] = isel; i_z[at] = zsel; i_rew[at] = rew; i_w[at] = wsel;
+				i_k[at] = isel; z_k[at] = (unsigned short)(bk + 1); i_rew[at] = rew; i_w[at] = wsel;
 				// 4. row of (I + h0 L^q + P (I - M*)): entries on the three diagonals folded in
 				double a_ = blo * h0, b_ = 1. + bdi * h0, c_ = bup * h0;
 				unsigned fl = 0;                // bit 0: penalised; bits 1, 2: entry idx / idx + 1 is off the three diagonals
@@ -263,21 +261,15 @@ k_hjbqvi1d(Hjbqvi1dBatch b, Hjbqvi1dResult out) {
 					if(isel == i) b_ -= f0; else if(isel == i - 1) a_ -= f0; else if(isel == i + 1) c_ -= f0; else fl |= 2u;
 					if(isel + 1 == i) b_ -= f1; else if(isel + 1 == i - 1) a_ -= f1; else if(isel + 1 == i + 1) c_ -= f1; else fl |= 4u;
 				}
-				if(BAL) { h_a[at] = a_; h_b[at] = b_; h_c[at] = c_; h_f[at] = (unsigned char)fl; }
-				else {
-					aa[j] = a_; bb[j] = b_; cc[j] = c_;
-					active |= (fl & 1u) << j; far |= (fl >> 1) << (2 * j);
-				}
+				h_a[at] = a_; h_b[at] = b_; h_c[at] = c_; h_f[at] = (unsigned char)fl;
 			}
-			if(BAL) {
-				__syncthreads();
+			__syncthreads();
 #pragma unroll
-				for(int j = 0; j < HM; ++j) {
-					const int at = j * HP + tid;
-					const unsigned fl = h_f[at];
-					aa[j] = h_a[at]; bb[j] = h_b[at]; cc[j] = h_c[at];
-					active |= (fl & 1u) << j; far |= (fl >> 1) << (2 * j);
-				}
+			for(int j = 0; j < HM; ++j) {
+				const int at = j * HP + tid;
+				const unsigned fl = h_f[at];
+				aa[j] = h_a[at]; bb[j] = h_b[at]; cc[j] = h_c[at];
+				active |= (fl & 1u) << j; far |= (fl >> 1) << (2 * j);
 			}
 			ps.factorize(aa, bb, cc, sm.ps, lane, warp);
 			// ---- linear solve: lagged far entries, repeated to a 1e-15 relative update
@@ -349,8 +341,8 @@ k_hjbqvi1d(Hjbqvi1dBatch b, Hjbqvi1dResult out) {
 		if(out.X) out.X[o] = sX[at];
 		if(out.mask) out.mask[o] = act ? 1 : 0;
 		const double qnan = __longlong_as_double(0x7ff8000000000000LL);      // std::nan(""): the positive quiet NaN
-		if(out.Q) out.Q[o] = act ? qnan : r_q[at];
-		if(out.Z) out.Z[o] = act ? i_z[at] : qnan;
+		if(out.Q) out.Q[o] = act ? qnan : sq[q_k[at]];
+		if(out.Z) out.Z[o] = act ? (z_k[at] ? sz[z_k[at] - 1] : 0.) : qnan;
 	}
 	if(tid == 0) {
 		if(out.n_steps) out.n_steps[pidx] = sm.n_steps;
