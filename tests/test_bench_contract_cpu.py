@@ -22,3 +22,16 @@ def test_reference_arm_prints_one_json_line():
     assert cb["kind"] in ("reference", "port") and cb["cores"] >= 1 and cb["value"] == d["value"] and cb["sample"]
     e2e = d["e2e"]
     assert e2e["value"] == d["value"] and e2e["h2d_bytes_per_step"] == 0 and e2e["d2h_bytes_per_step"] == 0
+
+
+def test_reference_arm_of_the_hjbqvi_configs():
+    """--impl reference --config er / oc: the reference's own HJBQVI<..>::solve on a bounded sample."""
+    for cfg, extra in (("er", ["--cpu-sample", "2", "--hjbqvi-refine", "2"]), ("oc", [])):
+        run = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--config", cfg,
+                              "--steps", "1", "--warmup", "0"] + extra, capture_output=True, text=True, timeout=900, cwd=ROOT)
+        assert run.returncode == 0, run.stderr
+        lines = [ln for ln in run.stdout.splitlines() if ln.strip()]
+        assert len(lines) == 1
+        d = json.loads(lines[0])
+        assert d["impl"] == "reference" and d["value"] > 0 and d["cpu_baseline"]["kind"] == "reference"
+        assert ("exchange_rate" if cfg == "er" else "optimal_consumption") in d["config"]["workload"]
