@@ -165,6 +165,10 @@ def test_axis_cluster_reproduces_the_reference_axes(tmp_path):
             std::printf("\\n");
             for(Index i = 0; i < q.size(); ++i) std::printf("%a ", q[i]);
             std::printf("\\n");
+            ExchangeRate off; off.m = .25;                 // the flipped branch of nonsymmetricCluster on one side
+            const Axis xo = off.xAxis();
+            for(Index i = 0; i < xo.size(); ++i) std::printf("%a ", xo[i]);
+            std::printf("\\n");
             return e.rho == .02 && e.lambda == 1. && o.gamma == .3 && o.boundary == 200. ? 0 : 1;
         }
     """))
@@ -175,5 +179,5 @@ def test_axis_cluster_reproduces_the_reference_axes(tmp_path):
     out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.splitlines()
     g = np.load(os.path.join(ROOT, "tests", "golden", "hjbqvi1d_reference.npz"))
     assert out[0].split() == ["33", "17", "9", "20"]
-    for line, key in zip(out[1:4], ("er_k0/X0", "er_k0/Z0", "er_k0/Q0")):
+    for line, key in zip(out[1:5], ("er_k0/X0", "er_k0/Z0", "er_k0/Q0", "er_parity_off_centre/X0")):
         assert np.array_equal(np.array([float.fromhex(t) for t in line.split()]), g[key]), key
